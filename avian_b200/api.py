@@ -1,0 +1,460 @@
+"""ctypes binding of include/avian_b200.h — the same C ABI the Rust shim binds.
+
+Nothing here computes: arrays go in as numpy buffers, the CUDA library does the work.  If the library or a
+CUDA device is missing the constructors raise — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _build
+
+GRAPH_COLOR_COUNT = 24
+COLOR_OVERFLOW = 23
+DYNAMIC_COLOR_COUNT = 20
+MAX_MANIFOLD_POINTS = 4
+NO_BODY = -1
+BODY_DYNAMIC, BODY_KINEMATIC, BODY_STATIC = 0, 1, 2
+JOINT_FIXED, JOINT_REVOLUTE, JOINT_SPHERICAL, JOINT_PRISMATIC, JOINT_DISTANCE = range(5)
+JOINT_TYPE_COUNT = 5
+AABB_IS_INACTIVE, AABB_CONTACT_EVENTS, AABB_GENERATE_CONSTRAINTS, AABB_CUSTOM_FILTER, AABB_MODIFY_CONTACTS = 1, 2, 4, 8, 16
+PAIR_CONTACT_EVENTS, PAIR_MODIFY_CONTACTS, PAIR_GENERATE_CONSTRAINTS, PAIR_NEEDS_HOOK = 1, 2, 4, 8
+CFG_FAST_TRIG = 1
+OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+
+_vp = C.c_void_p
+
+
+class AvnConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("scalar_bits", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class AvnStepParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("h", C.c_double), ("substeps", C.c_uint32), ("restitution_iterations", C.c_uint32),
+        ("gravity", C.c_double * 3), ("contact_damping_ratio", C.c_double), ("contact_frequency_factor", C.c_double),
+        ("max_overlap_solve_speed", C.c_double), ("warm_start_coefficient", C.c_double), ("restitution_threshold", C.c_double),
+        ("length_unit", C.c_double), ("match_contacts", C.c_uint32), ("solver_iterations", C.c_uint32),
+    ]
+
+
+class AvnBodyColumns(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in (
+            "kind", "position", "rotation", "linear_velocity", "angular_velocity", "inverse_mass", "inverse_inertia_local",
+            "center_of_mass", "locked_axes", "dominance", "linear_damping", "angular_damping", "gravity_scale",
+            "linear_acceleration", "angular_acceleration", "max_linear_speed", "max_angular_speed", "integration_flags")]
+
+
+class AvnManifoldColumns(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("point_count", C.c_uint32), ("color_offsets", C.c_uint32 * (GRAPH_COLOR_COUNT + 1))] + [
+        (n, _vp) for n in (
+            "body1", "body2", "normal", "friction", "restitution", "tangent_velocity", "point_offsets", "anchor1", "anchor2",
+            "penetration", "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")]
+
+
+class AvnJointColumns(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in (
+            "body1", "body2", "local_anchor1", "local_anchor2", "local_basis1", "local_basis2", "axis", "limit_enabled",
+            "limit_min", "limit_max", "limit2_min", "limit2_max", "compliance0", "compliance1", "compliance2",
+            "damping_enabled", "damping_linear", "damping_angular", "force", "torque")]
+
+
+class AvnJointSet(C.Structure):
+    _fields_ = [("types", AvnJointColumns * JOINT_TYPE_COUNT)]
+
+
+class AvnAabbColumns(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in ("collider", "body", "aabb_min", "aabb_max", "memberships", "filters", "flags", "order_out")] + [
+        ("existing_pairs", _vp), ("existing_pair_count", C.c_uint64), ("joint_disabled_body_pairs", _vp), ("joint_disabled_pair_count", C.c_uint64)]
+
+
+class AvnPairList(C.Structure):
+    _fields_ = [("capacity", C.c_uint64), ("count", C.c_uint64)] + [(n, _vp) for n in ("collider1", "collider2", "body1", "body2", "flags")]
+
+
+class AvnTimings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "prepare_ms", "substep_loop_ms", "finalize_ms", "d2h_ms", "broad_phase_ms", "total_ms")] + [
+        (n, C.c_uint32) for n in ("kernel_launches", "contact_constraint_count", "joint_levels", "active_colors", "_pad")]
+
+
+class AvianError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"avian_b200 error {status}: {message}")
+        self.status = status
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "column must be C-contiguous"
+    return a.ctypes.data
+
+
+def default_step_params(dt: float = 1.0 / 60.0, substeps: int = 6, gravity=(0.0, -9.81, 0.0), scalar=np.float32, **kw) -> AvnStepParams:
+    """SolverConfig / Gravity / SubstepCount defaults of the reference (solver/plugin.rs:291-302,
+    integrator/mod.rs:158-162, solver/schedule.rs:187-191).  dt, h are derived like the reference derives them:
+    Duration arithmetic in integer nanoseconds (solver/schedule.rs:195-200)."""
+    p = AvnStepParams()
+    dt_ns = round(dt * 1e9)                       # Duration::from_secs_f64 rounds to the nearest ns
+    h_ns = round(dt_ns / 1e9 / substeps * 1e9)    # Duration::div_f64 = from_secs_f64(as_secs_f64() / rhs)
+    p.dt = dt_ns / 1e9
+    p.h = h_ns / 1e9
+    p.substeps = substeps
+    p.restitution_iterations = 1
+    p.gravity[0], p.gravity[1], p.gravity[2] = gravity
+    p.contact_damping_ratio = 10.0
+    p.contact_frequency_factor = 1.5
+    p.max_overlap_solve_speed = 4.0
+    p.warm_start_coefficient = 1.0
+    p.restitution_threshold = 1.0
+    p.length_unit = 1.0
+    p.match_contacts = 1
+    p.solver_iterations = 1
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@dataclass
+class Bodies:
+    """Host columns of the rigid bodies (numpy, dtype = scalar type).  Mirrors AvnBodyColumns."""
+    kind: np.ndarray
+    position: np.ndarray
+    rotation: np.ndarray
+    linear_velocity: np.ndarray
+    angular_velocity: np.ndarray
+    inverse_mass: np.ndarray
+    inverse_inertia_local: np.ndarray
+    center_of_mass: np.ndarray | None = None
+    locked_axes: np.ndarray | None = None
+    dominance: np.ndarray | None = None
+    linear_damping: np.ndarray | None = None
+    angular_damping: np.ndarray | None = None
+    gravity_scale: np.ndarray | None = None
+    linear_acceleration: np.ndarray | None = None
+    angular_acceleration: np.ndarray | None = None
+    max_linear_speed: np.ndarray | None = None
+    max_angular_speed: np.ndarray | None = None
+    integration_flags: np.ndarray | None = None
+
+    @property
+    def count(self) -> int:
+        return int(self.position.shape[0])
+
+    def as_struct(self) -> AvnBodyColumns:
+        s = AvnBodyColumns()
+        s.count = self.count
+        for name, _ in AvnBodyColumns._fields_[2:]:
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+    def copy(self) -> "Bodies":
+        return Bodies(**{k: (None if v is None else v.copy()) for k, v in self.__dict__.items()})
+
+
+@dataclass
+class Manifolds:
+    color_offsets: np.ndarray          # uint32[25]
+    body1: np.ndarray                  # int32[M]
+    body2: np.ndarray
+    normal: np.ndarray                 # [M,3]
+    friction: np.ndarray
+    restitution: np.ndarray
+    point_offsets: np.ndarray          # uint32[M+1]
+    anchor1: np.ndarray                # [P,3]
+    anchor2: np.ndarray
+    penetration: np.ndarray
+    normal_speed: np.ndarray
+    warm_start_normal_impulse: np.ndarray
+    warm_start_tangent_impulse: np.ndarray   # [P,2]
+    normal_impulse: np.ndarray
+    tangent_velocity: np.ndarray | None = None
+
+    @property
+    def count(self) -> int:
+        return int(self.body1.shape[0])
+
+    def as_struct(self) -> AvnManifoldColumns:
+        s = AvnManifoldColumns()
+        s.count = self.count
+        s.point_count = int(self.penetration.shape[0])
+        for i in range(GRAPH_COLOR_COUNT + 1):
+            s.color_offsets[i] = int(self.color_offsets[i])
+        for name, _ in AvnManifoldColumns._fields_[3:]:
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+    def copy(self) -> "Manifolds":
+        return Manifolds(**{k: (None if v is None else v.copy()) for k, v in self.__dict__.items()})
+
+
+@dataclass
+class Joints:
+    """One typed joint array (AvnJointColumns)."""
+    body1: np.ndarray
+    body2: np.ndarray
+    local_anchor1: np.ndarray
+    local_anchor2: np.ndarray
+    local_basis1: np.ndarray | None = None
+    local_basis2: np.ndarray | None = None
+    axis: np.ndarray | None = None
+    limit_enabled: np.ndarray | None = None
+    limit_min: np.ndarray | None = None
+    limit_max: np.ndarray | None = None
+    limit2_min: np.ndarray | None = None
+    limit2_max: np.ndarray | None = None
+    compliance0: np.ndarray | None = None
+    compliance1: np.ndarray | None = None
+    compliance2: np.ndarray | None = None
+    damping_enabled: np.ndarray | None = None
+    damping_linear: np.ndarray | None = None
+    damping_angular: np.ndarray | None = None
+    force: np.ndarray | None = None
+    torque: np.ndarray | None = None
+
+    @property
+    def count(self) -> int:
+        return int(self.body1.shape[0])
+
+    def fill(self, s: AvnJointColumns) -> None:
+        s.count = self.count
+        for name, _ in AvnJointColumns._fields_[2:]:
+            setattr(s, name, _ptr(getattr(self, name)))
+
+    def copy(self) -> "Joints":
+        return Joints(**{k: (None if v is None else v.copy()) for k, v in self.__dict__.items()})
+
+
+@dataclass
+class JointSet:
+    types: dict = field(default_factory=dict)   # AvnJointType -> Joints
+
+    def as_struct(self) -> AvnJointSet:
+        s = AvnJointSet()
+        for t, j in self.types.items():
+            j.fill(s.types[t])
+        return s
+
+    def copy(self) -> "JointSet":
+        return JointSet({t: j.copy() for t, j in self.types.items()})
+
+    @property
+    def count(self) -> int:
+        return sum(j.count for j in self.types.values())
+
+
+@dataclass
+class Aabbs:
+    collider: np.ndarray     # uint32[C]
+    body: np.ndarray         # uint32[C]
+    aabb_min: np.ndarray     # [C,3]
+    aabb_max: np.ndarray
+    flags: np.ndarray        # uint8[C]
+    memberships: np.ndarray | None = None
+    filters: np.ndarray | None = None
+    order_out: np.ndarray | None = None
+    existing_pairs: np.ndarray | None = None          # uint64
+    joint_disabled_body_pairs: np.ndarray | None = None
+
+    def as_struct(self) -> AvnAabbColumns:
+        s = AvnAabbColumns()
+        s.count = int(self.collider.shape[0])
+        for name in ("collider", "body", "aabb_min", "aabb_max", "memberships", "filters", "flags", "order_out"):
+            setattr(s, name, _ptr(getattr(self, name)))
+        s.existing_pairs = _ptr(self.existing_pairs)
+        s.existing_pair_count = 0 if self.existing_pairs is None else int(self.existing_pairs.shape[0])
+        s.joint_disabled_body_pairs = _ptr(self.joint_disabled_body_pairs)
+        s.joint_disabled_pair_count = 0 if self.joint_disabled_body_pairs is None else int(self.joint_disabled_body_pairs.shape[0])
+        return s
+
+
+@dataclass
+class PairList:
+    collider1: np.ndarray
+    collider2: np.ndarray
+    body1: np.ndarray
+    body2: np.ndarray
+    flags: np.ndarray
+    count: int = 0
+
+    @staticmethod
+    def empty(capacity: int) -> "PairList":
+        u = lambda: np.zeros(capacity, dtype=np.uint32)
+        return PairList(u(), u(), u(), u(), np.zeros(capacity, dtype=np.uint8))
+
+    def as_struct(self) -> AvnPairList:
+        s = AvnPairList()
+        s.capacity = int(self.collider1.shape[0])
+        for name in ("collider1", "collider2", "body1", "body2", "flags"):
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+    def trimmed(self) -> "PairList":
+        n = self.count
+        return PairList(self.collider1[:n], self.collider2[:n], self.body1[:n], self.body2[:n], self.flags[:n], n)
+
+
+def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
+    """Declare argument/return types of every entry point of include/avian_b200.h on `lib`."""
+    P = C.POINTER
+    sig = {
+        "create": ([P(AvnConfig), P(_vp)], C.c_int),
+        "destroy": ([_vp], None),
+        "last_error": ([_vp], C.c_char_p),
+        "abi_version": ([], C.c_uint32),
+        "alloc_pinned": ([_vp, C.c_size_t, P(_vp)], C.c_int),
+        "free_pinned": ([_vp, _vp], C.c_int),
+        "solver_step": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnManifoldColumns), P(AvnJointSet)], C.c_int),
+        "solver_upload": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnManifoldColumns), P(AvnJointSet)], C.c_int),
+        "solver_run": ([_vp], C.c_int),
+        "solver_download": ([_vp], C.c_int),
+        "broadphase": ([_vp, P(AvnAabbColumns), P(AvnPairList)], C.c_int),
+        "broadphase_upload": ([_vp, P(AvnAabbColumns)], C.c_int),
+        "broadphase_run": ([_vp], C.c_int),
+        "broadphase_download": ([_vp, P(AvnPairList)], C.c_int),
+        "get_timings": ([_vp, P(AvnTimings)], C.c_int),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, f"{prefix}_{name}")
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+
+ABI_SYMBOLS = [
+    "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
+    "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
+    "avn_broadphase_download", "avn_get_timings"]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load (building if needed) libavian_b200.so.  Raises if it cannot be had: no fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.build_cuda()
+        lib = C.CDLL(str(path))
+        bind_abi(lib)
+        _lib = lib
+    return _lib
+
+
+class Context:
+    """An AvnContext: one CUDA device, one stream, persistent device buffers."""
+
+    def __init__(self, device: int = 0, scalar=np.float32, flags: int = 0):
+        self.lib = load_library()
+        self.scalar = np.dtype(scalar)
+        cfg = AvnConfig(self.lib.avn_abi_version(), device, 32 if self.scalar == np.float32 else 64, flags)
+        h = _vp()
+        st = self.lib.avn_create(C.byref(cfg), C.byref(h))
+        if st != OK:
+            raise AvianError(st, self.lib.avn_last_error(None).decode())
+        self.handle = h
+        self._pinned: list[int] = []
+        self._keep = None
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            for p in self._pinned:
+                self.lib.avn_free_pinned(self.handle, _vp(p))
+            self._pinned.clear()
+            self.lib.avn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int) -> None:
+        if st != OK:
+            raise AvianError(st, self.lib.avn_last_error(self.handle).decode())
+
+    def pinned(self, shape, dtype) -> np.ndarray:
+        """A numpy array backed by page-locked memory from avn_alloc_pinned (lives as long as the context)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _vp()
+        self._check(self.lib.avn_alloc_pinned(self.handle, max(n, 1), C.byref(p)))
+        self._pinned.append(p.value)
+        buf = (C.c_byte * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pin_like(self, a: np.ndarray | None) -> np.ndarray | None:
+        if a is None:
+            return None
+        out = self.pinned(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    # ---- solver stage ------------------------------------------------------------------------------------
+    def _solver_args(self, params, bodies: Bodies, manifolds: Manifolds | None, joints: JointSet | None):
+        b = bodies.as_struct()
+        m = manifolds.as_struct() if manifolds is not None and manifolds.count else None
+        j = joints.as_struct() if joints is not None and joints.count else None
+        self._keep = (params, bodies, manifolds, joints, b, m, j)
+        return (C.byref(params), C.byref(b), C.byref(m) if m is not None else None, C.byref(j) if j is not None else None)
+
+    def solver_step(self, params, bodies, manifolds=None, joints=None) -> None:
+        self._check(self.lib.avn_solver_step(self.handle, *self._solver_args(params, bodies, manifolds, joints)))
+
+    def solver_upload(self, params, bodies, manifolds=None, joints=None) -> None:
+        self._check(self.lib.avn_solver_upload(self.handle, *self._solver_args(params, bodies, manifolds, joints)))
+
+    def solver_run(self) -> None:
+        self._check(self.lib.avn_solver_run(self.handle))
+
+    def solver_download(self) -> None:
+        self._check(self.lib.avn_solver_download(self.handle))
+
+    # ---- broad phase -------------------------------------------------------------------------------------
+    def broadphase(self, aabbs: Aabbs, capacity: int | None = None) -> PairList:
+        """Runs the sweep; grows the output list and retries once when the capacity guess was too small."""
+        cap = capacity if capacity is not None else max(1024, 16 * int(aabbs.collider.shape[0]))
+        a = aabbs.as_struct()
+        self._keep_bp = (aabbs, a)
+        self._check(self.lib.avn_broadphase_upload(self.handle, C.byref(a)))
+        self._check(self.lib.avn_broadphase_run(self.handle))
+        out = PairList.empty(cap)
+        s = out.as_struct()
+        st = self.lib.avn_broadphase_download(self.handle, C.byref(s))
+        if st == ERR_CAPACITY:
+            out = PairList.empty(int(s.count))
+            s = out.as_struct()
+            st = self.lib.avn_broadphase_download(self.handle, C.byref(s))
+        self._check(st)
+        out.count = int(s.count)
+        return out.trimmed()
+
+    def broadphase_upload(self, aabbs: Aabbs) -> None:
+        a = aabbs.as_struct()
+        self._keep_bp = (aabbs, a)
+        self._check(self.lib.avn_broadphase_upload(self.handle, C.byref(a)))
+
+    def broadphase_run(self) -> None:
+        self._check(self.lib.avn_broadphase_run(self.handle))
+
+    def broadphase_download(self, out: PairList) -> PairList:
+        s = out.as_struct()
+        self._check(self.lib.avn_broadphase_download(self.handle, C.byref(s)))
+        out.count = int(s.count)
+        return out
+
+    def timings(self) -> dict:
+        t = AvnTimings()
+        self._check(self.lib.avn_get_timings(self.handle, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in AvnTimings._fields_ if n != "_pad"}

@@ -1,0 +1,146 @@
+// extern "C" surface of libavian_b200.so (declared in include/avian_b200.h).
+#include <memory>
+#include <mutex>
+
+#include "context.hpp"
+
+struct AvnContext {
+    int device = 0;
+    uint32_t scalar_bits = 32;
+    cudaStream_t stream = nullptr;
+    avn::ErrorSink err;
+    std::unique_ptr<avn::SolverBase> solver;
+    std::unique_ptr<avn::BroadphaseBase> broadphase;
+    AvnTimings last{};
+};
+
+namespace {
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+AvnStatus create_fail(AvnStatus code, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_create_mutex);
+    g_create_error = msg;
+    return code;
+}
+bool bind(AvnContext* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess; }
+}  // namespace
+
+extern "C" {
+
+uint32_t avn_abi_version(void) { return AVN_ABI_VERSION; }
+
+AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
+    if (!config || !out_ctx) return create_fail(AVN_ERR_INVALID_ARGUMENT, "config and out_ctx are required");
+    *out_ctx = nullptr;
+    if (config->abi_version != AVN_ABI_VERSION) return create_fail(AVN_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+    if (config->scalar_bits != 32 && config->scalar_bits != 64) return create_fail(AVN_ERR_INVALID_ARGUMENT, "scalar_bits must be 32 or 64");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return create_fail(AVN_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (config->device < 0 || config->device >= count) return create_fail(AVN_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    if ((e = cudaSetDevice(config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return create_fail(AVN_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; device is ") + prop.name + " (sm_" +
+                                                    std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    auto ctx = std::make_unique<AvnContext>();
+    ctx->device = config->device;
+    ctx->scalar_bits = config->scalar_bits;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+    ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
+    ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
+    if (!ctx->solver || !ctx->broadphase) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
+    *out_ctx = ctx.release();
+    return AVN_OK;
+}
+
+void avn_destroy(AvnContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->solver.reset();
+    ctx->broadphase.reset();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* avn_last_error(const AvnContext* ctx) {
+    if (ctx) return ctx->err.msg.c_str();
+    std::lock_guard<std::mutex> lk(g_create_mutex);
+    return g_create_error.c_str();
+}
+
+AvnStatus avn_alloc_pinned(AvnContext* ctx, size_t bytes, void** out_ptr) {
+    if (!ctx || !out_ptr) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return ctx->err.fail(AVN_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return AVN_OK;
+}
+
+AvnStatus avn_free_pinned(AvnContext* ctx, void* ptr) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!ptr) return AVN_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return ctx->err.fail(AVN_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
+    return AVN_OK;
+}
+
+AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->upload(params, bodies, manifolds, joints);
+}
+AvnStatus avn_solver_run(AvnContext* ctx) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->run();
+}
+AvnStatus avn_solver_download(AvnContext* ctx) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    AvnStatus st = ctx->solver->download();
+    ctx->solver->timings(&ctx->last);
+    return st;
+}
+AvnStatus avn_solver_step(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) {
+    AvnStatus st = avn_solver_upload(ctx, params, bodies, manifolds, joints);
+    if (st != AVN_OK) return st;
+    if ((st = avn_solver_run(ctx)) != AVN_OK) return st;
+    return avn_solver_download(ctx);
+}
+
+AvnStatus avn_broadphase_upload(AvnContext* ctx, AvnAabbColumns* aabbs) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->broadphase->upload(aabbs);
+}
+AvnStatus avn_broadphase_run(AvnContext* ctx) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->broadphase->run();
+}
+AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    AvnStatus st = ctx->broadphase->download(out_pairs);
+    ctx->broadphase->timings(&ctx->last);
+    return st;
+}
+AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* out_pairs) {
+    AvnStatus st = avn_broadphase_upload(ctx, aabbs);
+    if (st != AVN_OK) return st;
+    if ((st = avn_broadphase_run(ctx)) != AVN_OK) return st;
+    return avn_broadphase_download(ctx, out_pairs);
+}
+
+AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {
+    if (!ctx || !out) return AVN_ERR_INVALID_ARGUMENT;
+    *out = ctx->last;
+    return AVN_OK;
+}
+
+}  // extern "C"

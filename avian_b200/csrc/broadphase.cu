@@ -1,0 +1,517 @@
+// Sweep-and-prune broad phase on the device.  Replaces collect_collision_pairs / sweep_and_prune
+// (src/collision/broad_phase.rs:343-487).
+//
+// The reference keeps the intervals in a persistent Vec, insertion-sorts it by aabb.min.x every step (a STABLE sort:
+// it swaps only on strict '>'; broad_phase.rs:383,479-487) and sweeps i<j with a break on min.x[j] > max.x[i].
+// The emitted pairs are ordered by (rank of i, rank of j) in that sorted array.  Device plan, bit-exact with it:
+//   1. key = order-preserving integer image of min.x with -0.0 canonicalised to +0.0 (they compare equal in the
+//      reference), value = position in the persistent order;
+//   2. hand-written stable LSD radix sort, 8-bit digits: per-tile digit histogram -> single-block exclusive scan ->
+//      stable scatter ranked with warp match/ballot (4 passes for f32 keys, 8 for f64);
+//   3. gather the interval columns into sorted SoA arrays (coalesced for the sweep);
+//   4. per interval i: upper bound of max.x[i] in the sorted min.x = the reference's `break` position;
+//   5. one warp per i strides the candidates j in (i, end_i): y/z overlap (inclusive), inactive/layers/same-body,
+//      existing-pair hash set, joint-disabled hash set — count pass, exclusive scan, emit pass: ballot + popc keep
+//      the j order inside a warp, the scan keeps the i order across warps.
+#include <algorithm>
+#include <cstring>
+
+#include "avn_math.cuh"
+#include "context.hpp"
+
+namespace avn {
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 8;                       // elements per thread per tile
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;    // 2048 keys per block
+
+template <class S> struct KeyOf;
+template <> struct KeyOf<float> { using type = uint32_t; static constexpr int passes = 4; };
+template <> struct KeyOf<double> { using type = uint64_t; static constexpr int passes = 8; };
+
+__device__ __forceinline__ uint32_t sortable(float f) {
+    uint32_t b = __float_as_uint(f);
+    if (b == 0x80000000u) b = 0;  // -0.0 == +0.0 for the reference's comparison
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t sortable(double f) {
+    uint64_t b = (uint64_t)__double_as_longlong(f);
+    if (b == 0x8000000000000000ull) b = 0;
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <class S>
+__global__ void make_keys(const S* __restrict__ aabb_min, int n, typename KeyOf<S>::type* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = sortable(aabb_min[3 * i]);
+        vals[i] = uint32_t(i);
+    }
+}
+
+// digit histogram of one tile -> hist[digit * nblocks + block]
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        int i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// exclusive scan of `len` counters by one block (len = 256 * nblocks, a few 10^4 at most)
+__global__ void __launch_bounds__(1024) rs_scan(uint32_t* data, int len) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < len; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < len ? data[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            warp_sums[threadIdx.x] = z - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        uint32_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
+        if (i < len) data[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+// stable scatter of one tile.  Warp w owns the contiguous sub-tile [w*256, (w+1)*256) and walks it in 8 rounds of
+// 32 consecutive keys, so (warp, round, lane) order == input order; ranks come from match_any + popc.
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int n, int shift,
+                                                         const uint32_t* __restrict__ offsets, int nblocks, K* __restrict__ keys_out,
+                                                         uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t wcnt[RS_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int d = threadIdx.x; d < RS_WARPS * 256; d += RS_THREADS) (&wcnt[0][0])[d] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE + warp * (32 * RS_ROUNDS);
+    K key[RS_ROUNDS];
+    uint32_t val[RS_ROUNDS], rank[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        int i = base + r * 32 + lane;
+        bool ok = i < n;
+        key[r] = ok ? keys_in[i] : K(0);
+        val[r] = ok ? vals_in[i] : 0u;
+        uint32_t digit = uint32_t(key[r] >> shift) & 0xff;
+        uint32_t active = __ballot_sync(0xffffffffu, ok);
+        uint32_t same = __match_any_sync(0xffffffffu, ok ? digit : 0x100u + lane) & active;
+        uint32_t before = __popc(same & ((1u << lane) - 1u));
+        uint32_t prev = ok ? wcnt[warp][digit] : 0u;
+        rank[r] = prev + before;
+        __syncwarp();
+        if (ok && before == 0) wcnt[warp][digit] = prev + __popc(same);  // leader of each digit group
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit (one thread each): exclusive prefix across the 8 warps + global offset of (digit, block)
+    {
+        const int d = threadIdx.x;
+        uint32_t run = offsets[d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        int i = base + r * 32 + lane;
+        if (i < n) {
+            uint32_t digit = uint32_t(key[r] >> shift) & 0xff;
+            uint32_t pos = wcnt[warp][digit] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+// sorted SoA for the sweep
+template <class S>
+struct Sweep {
+    int n;
+    const S* minx; const S* maxx;          // [n]
+    const Vec4<S>* yz;                     // [n] {min.y, max.y, min.z, max.z}
+    const uint4* meta;                     // [n] {collider, body, memberships, filters}
+    const uint8_t* flags;                  // [n]
+    const int* end;                        // [n] first j with min.x[j] > max.x[i]
+    const uint64_t* existing; uint64_t existing_mask;   // open-addressing hash set of PairKey (0 = empty; keys stored +1)
+    const uint64_t* jdis; uint64_t jdis_mask;
+};
+
+template <class S>
+__global__ void gather_sorted(const uint32_t* __restrict__ order, int n, const S* __restrict__ mn, const S* __restrict__ mx,
+                              const uint32_t* __restrict__ collider, const uint32_t* __restrict__ body, const uint32_t* __restrict__ memberships,
+                              const uint32_t* __restrict__ filters, const uint8_t* __restrict__ flags, S* __restrict__ minx, S* __restrict__ maxx,
+                              Vec4<S>* __restrict__ yz, uint4* __restrict__ meta, uint8_t* __restrict__ sflags) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t p = order[r];
+    minx[r] = mn[3 * p];
+    maxx[r] = mx[3 * p];
+    yz[r] = mk4<S>(mn[3 * p + 1], mx[3 * p + 1], mn[3 * p + 2], mx[3 * p + 2]);
+    meta[r] = make_uint4(collider[p], body[p], memberships ? memberships[p] : 1u, filters ? filters[p] : 0xFFFFFFFFu);
+    sflags[r] = flags ? flags[p] : uint8_t(AVN_AABB_GENERATE_CONSTRAINTS);
+}
+
+// end[i] = first j > i with min.x[j] > max.x[i]  (the `break` of broad_phase.rs:390-392)
+template <class S>
+__global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, int n, int* __restrict__ end) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S m = maxx[i];
+    int lo = i + 1, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (minx[mid] > m) hi = mid; else lo = mid + 1;
+    }
+    end[i] = lo;
+}
+
+__device__ __forceinline__ uint64_t hash64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__global__ void hash_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* table, uint64_t mask) {
+    uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i] + 1;  // 0 is the empty marker
+    uint64_t h = hash64(k) & mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long*)&table[h], 0ull, (unsigned long long)k);
+        if (prev == 0ull || prev == k) return;
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ bool hash_contains(const uint64_t* table, uint64_t mask, uint64_t key) {
+    uint64_t k = key + 1;
+    uint64_t h = hash64(k) & mask;
+    for (;;) {
+        uint64_t v = table[h];
+        if (v == k) return true;
+        if (v == 0) return false;
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ uint64_t pair_key(uint32_t a, uint32_t b) {  // data_structures/pair_key.rs:15-21
+    return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a;
+}
+
+// the filters of broad_phase.rs:394-428 for the candidate (i, j); `mi`, `fi` describe i
+template <class S>
+__device__ __forceinline__ bool pair_passes(const Sweep<S>& s, Vec4<S> yi, uint4 mi, uint32_t fi, int j, uint32_t& pair_flags, uint4& mj) {
+    Vec4<S> yj = s.yz[j];
+    if (yi.x > yj.y || yi.y < yj.x) return false;   // aabb1.min.y > aabb2.max.y || aabb1.max.y < aabb2.min.y
+    if (yi.z > yj.w || yi.w < yj.z) return false;   // same on z
+    mj = s.meta[j];
+    uint32_t fj = s.flags[j];
+    bool interacts = (mi.z & mj.w) != 0 && (mj.z & mi.w) != 0;  // CollisionLayers::interacts_with, layers.rs:423-426
+    if ((fi & fj & AVN_AABB_IS_INACTIVE) || !interacts || mi.y == mj.y) return false;
+    if (s.existing && hash_contains(s.existing, s.existing_mask, pair_key(mi.x, mj.x))) return false;
+    if (s.jdis && hash_contains(s.jdis, s.jdis_mask, pair_key(mi.y, mj.y))) return false;
+    uint32_t u = fi | fj;
+    pair_flags = ((u & AVN_AABB_CONTACT_EVENTS) ? AVN_PAIR_CONTACT_EVENTS : 0u) | ((u & AVN_AABB_MODIFY_CONTACTS) ? AVN_PAIR_MODIFY_CONTACTS : 0u) |
+                 ((u & AVN_AABB_GENERATE_CONSTRAINTS) ? AVN_PAIR_GENERATE_CONSTRAINTS : 0u) | ((u & AVN_AABB_CUSTOM_FILTER) ? AVN_PAIR_NEEDS_HOOK : 0u);
+    return true;
+}
+
+// one warp per interval i.  EMIT = false: counts[i]; EMIT = true: writes pairs at offsets[i] + running index.
+template <class S, bool EMIT>
+__global__ void __launch_bounds__(256) sweep_kernel(const __grid_constant__ Sweep<S> s, uint32_t* __restrict__ counts,
+                                                    const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
+                                                    uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
+                                                    uint8_t* __restrict__ out_flags) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < s.n; i += warps_per_grid) {
+        const int e = s.end[i];
+        const Vec4<S> yi = s.yz[i];
+        const uint4 mi = s.meta[i];
+        const uint32_t fi = s.flags[i];
+        uint64_t running = EMIT ? offsets[i] : 0ull;
+        uint32_t total = 0;
+        for (int j0 = i + 1; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            uint32_t pf = 0;
+            uint4 mj = make_uint4(0, 0, 0, 0);
+            bool ok = j < e && pair_passes(s, yi, mi, fi, j, pf, mj);
+            uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (EMIT) {
+                if (ok) {
+                    uint64_t pos = running + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < capacity) {
+                        out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
+                    }
+                }
+                running += __popc(bal);
+            } else {
+                total += __popc(bal);
+            }
+        }
+        if (!EMIT && lane == 0) counts[i] = total;
+    }
+}
+
+// exclusive scan of n 32-bit counts into 64-bit offsets (single block; n <= a few 10^6), total -> offsets[n]
+__global__ void __launch_bounds__(1024) scan_counts(const uint32_t* __restrict__ counts, int n, uint64_t* __restrict__ offsets) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        uint64_t v = i < n ? counts[i] : 0u, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = warp_sums[threadIdx.x], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            warp_sums[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        uint64_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
+        if (i < n) offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+template <class S>
+class Broadphase final : public BroadphaseBase {
+    using K = typename KeyOf<S>::type;
+
+   public:
+    Broadphase(cudaStream_t stream, ErrorSink* err, int device) : stream_(stream), err_(err) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sm_count_ = prop.multiProcessorCount;
+        cudaEventCreate(&ev0_);
+        cudaEventCreate(&ev1_);
+        cudaHostAlloc(&h_total_, sizeof(uint64_t), cudaHostAllocDefault);
+    }
+    ~Broadphase() override {
+        cudaEventDestroy(ev0_);
+        cudaEventDestroy(ev1_);
+        if (h_total_) cudaFreeHost(h_total_);
+    }
+    AvnStatus upload(AvnAabbColumns* a) override;
+    AvnStatus run() override;
+    AvnStatus download(AvnPairList* out) override;
+    void timings(AvnTimings* t) const override { *t = tm_; }
+
+   private:
+    template <class T> AvnStatus up(DevBuf& buf, const void* host, size_t count, const T** dev) {
+        *dev = nullptr;
+        if (!host || count == 0) return AVN_OK;
+        AVN_CUDA(buf.ensure(count * sizeof(T)));
+        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        *dev = buf.as<T>();
+        return AVN_OK;
+    }
+    AvnStatus build_set(DevBuf& keys_buf, DevBuf& table_buf, const uint64_t* host_keys, uint64_t count, const uint64_t** table, uint64_t* mask);
+
+    cudaStream_t stream_;
+    ErrorSink* err_;
+    int sm_count_ = 148;
+    cudaEvent_t ev0_, ev1_;
+    uint64_t* h_total_ = nullptr;
+    AvnTimings tm_{};
+    uint32_t launches_ = 0;
+    bool uploaded_ = false, ran_ = false;
+    int n_ = 0;
+    uint64_t pair_capacity_ = 0;
+    AvnAabbColumns host_{};
+    const S* d_min_ = nullptr; const S* d_max_ = nullptr;
+    const uint32_t* d_collider_ = nullptr; const uint32_t* d_body_ = nullptr; const uint32_t* d_memb_ = nullptr; const uint32_t* d_filt_ = nullptr;
+    const uint8_t* d_flags_ = nullptr;
+    const uint64_t* d_existing_ = nullptr; uint64_t existing_mask_ = 0;
+    const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
+    DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
+    DevBuf k0_, k1_, v0_, v1_, hist_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_;
+    DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
+    uint32_t* d_order_ = nullptr;
+};
+
+template <class S>
+AvnStatus Broadphase<S>::build_set(DevBuf& keys_buf, DevBuf& table_buf, const uint64_t* host_keys, uint64_t count, const uint64_t** table, uint64_t* mask) {
+    *table = nullptr;
+    *mask = 0;
+    if (!host_keys || count == 0) return AVN_OK;
+    uint64_t cap = 64;
+    while (cap < count * 2) cap <<= 1;
+    const uint64_t* dkeys;
+    AvnStatus st = up<uint64_t>(keys_buf, host_keys, count, &dkeys);
+    if (st != AVN_OK) return st;
+    AVN_CUDA(table_buf.ensure(cap * sizeof(uint64_t)));
+    AVN_CUDA(cudaMemsetAsync(table_buf.p, 0, cap * sizeof(uint64_t), stream_));
+    hash_insert<<<unsigned((count + 255) / 256), 256, 0, stream_>>>(dkeys, count, table_buf.as<uint64_t>(), cap - 1);
+    ++launches_;
+    *table = table_buf.as<uint64_t>();
+    *mask = cap - 1;
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Broadphase<S>::upload(AvnAabbColumns* a) {
+    if (!a) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs is required");
+    if (a->count && (!a->collider || !a->body || !a->aabb_min || !a->aabb_max))
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs: collider, body, aabb_min and aabb_max are required");
+    if (a->count > 0x7fffffffu - RS_TILE) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs: too many intervals");
+    uploaded_ = ran_ = false;
+    launches_ = 0;
+    n_ = int(a->count);
+    host_ = *a;
+    const size_t n = a->count;
+    AvnStatus st;
+#define UPB(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
+    UPB(b_min_, a->aabb_min, 3 * n, S, d_min_);
+    UPB(b_max_, a->aabb_max, 3 * n, S, d_max_);
+    UPB(b_col_, a->collider, n, uint32_t, d_collider_);
+    UPB(b_body_, a->body, n, uint32_t, d_body_);
+    UPB(b_memb_, a->memberships, n, uint32_t, d_memb_);
+    UPB(b_filt_, a->filters, n, uint32_t, d_filt_);
+    UPB(b_flags_, a->flags, n, uint8_t, d_flags_);
+#undef UPB
+    if ((st = build_set(b_exk_, b_ext_, a->existing_pairs, a->existing_pair_count, &d_existing_, &existing_mask_)) != AVN_OK) return st;
+    if ((st = build_set(b_jdk_, b_jdt_, a->joint_disabled_body_pairs, a->joint_disabled_pair_count, &d_jdis_, &jdis_mask_)) != AVN_OK) return st;
+    uploaded_ = true;
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Broadphase<S>::run() {
+    if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_broadphase_run before avn_broadphase_upload");
+    const int n = n_;
+    cudaEventRecord(ev0_, stream_);
+    *h_total_ = 0;
+    if (n > 0) {
+        const int nblocks = (n + RS_TILE - 1) / RS_TILE;
+        AVN_CUDA(k0_.ensure(size_t(n) * sizeof(K))); AVN_CUDA(k1_.ensure(size_t(n) * sizeof(K)));
+        AVN_CUDA(v0_.ensure(size_t(n) * 4)); AVN_CUDA(v1_.ensure(size_t(n) * 4));
+        AVN_CUDA(hist_.ensure(size_t(256) * nblocks * 4));
+        K* ka = k0_.as<K>(); K* kb = k1_.as<K>();
+        uint32_t* va = v0_.as<uint32_t>(); uint32_t* vb = v1_.as<uint32_t>();
+        make_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_min_, n, ka, va);
+        ++launches_;
+        for (int pass = 0; pass < KeyOf<S>::passes; ++pass) {
+            const int shift = 8 * pass;
+            rs_histogram<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, n, shift, hist_.as<uint32_t>(), nblocks);
+            rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+            rs_scatter<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+            launches_ += 3;
+            std::swap(ka, kb);
+            std::swap(va, vb);
+        }
+        d_order_ = va;  // even number of passes: back in buffer 0
+        AVN_CUDA(s_minx_.ensure(size_t(n) * sizeof(S))); AVN_CUDA(s_maxx_.ensure(size_t(n) * sizeof(S)));
+        AVN_CUDA(s_yz_.ensure(size_t(n) * sizeof(Vec4<S>))); AVN_CUDA(s_meta_.ensure(size_t(n) * sizeof(uint4)));
+        AVN_CUDA(s_flags_.ensure(size_t(n))); AVN_CUDA(s_end_.ensure(size_t(n) * 4));
+        AVN_CUDA(counts_.ensure(size_t(n) * 4)); AVN_CUDA(offsets_.ensure((size_t(n) + 1) * 8));
+        gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
+                                                               s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
+                                                               s_flags_.as<uint8_t>());
+        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>());
+        Sweep<S> sw;
+        sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
+        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>();
+        sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
+        const int grid = std::min((n + 7) / 8, sm_count_ * 8);
+        sweep_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+        scan_counts<<<1, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, offsets_.as<uint64_t>());
+        launches_ += 4;
+        // the pair count decides the size of the output buffers: one 8-byte readback
+        AVN_CUDA(cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        const uint64_t total = *h_total_;
+        pair_capacity_ = total;
+        if (total > 0) {
+            AVN_CUDA(o_c1_.ensure(total * 4)); AVN_CUDA(o_c2_.ensure(total * 4)); AVN_CUDA(o_b1_.ensure(total * 4)); AVN_CUDA(o_b2_.ensure(total * 4));
+            AVN_CUDA(o_fl_.ensure(total));
+            sweep_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
+                                                            o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+            ++launches_;
+        }
+    }
+    cudaEventRecord(ev1_, stream_);
+    AVN_CUDA(cudaGetLastError());
+    ran_ = true;
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Broadphase<S>::download(AvnPairList* out) {
+    if (!ran_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_broadphase_download before avn_broadphase_run");
+    if (!out) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "out_pairs is required");
+    const uint64_t total = *h_total_;
+    out->count = total;
+    const uint64_t ncopy = std::min<uint64_t>(total, out->capacity);
+    if (ncopy) {
+        if (!out->collider1 || !out->collider2 || !out->body1 || !out->body2 || !out->flags)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "out_pairs arrays are required when capacity > 0");
+        AVN_CUDA(cudaMemcpyAsync(out->collider1, o_c1_.p, ncopy * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(out->collider2, o_c2_.p, ncopy * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(out->body1, o_b1_.p, ncopy * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(out->body2, o_b2_.p, ncopy * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(out->flags, o_fl_.p, ncopy, cudaMemcpyDeviceToHost, stream_));
+    }
+    if (host_.order_out && n_ > 0) AVN_CUDA(cudaMemcpyAsync(host_.order_out, d_order_, size_t(n_) * 4, cudaMemcpyDeviceToHost, stream_));
+    AVN_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    tm_ = AvnTimings{};
+    if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) { tm_.broad_phase_ms = ms; tm_.total_ms = ms; }
+    tm_.kernel_launches = launches_;
+    if (total > out->capacity) return err_->fail(AVN_ERR_CAPACITY, "pair list capacity %llu < %llu pairs found", (unsigned long long)out->capacity,
+                                                 (unsigned long long)total);
+    return AVN_OK;
+}
+
+}  // namespace
+
+BroadphaseBase* make_broadphase(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, int device) {
+    if (scalar_bits == 32) return new Broadphase<float>(stream, err, device);
+    if (scalar_bits == 64) return new Broadphase<double>(stream, err, device);
+    return nullptr;
+}
+
+}  // namespace avn

@@ -1,0 +1,74 @@
+// Host-side plumbing shared by the ABI translation units: error reporting, grow-only device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/avian_b200.h"
+
+namespace avn {
+
+struct ErrorSink {
+    std::string msg;
+    AvnStatus fail(AvnStatus code, const char* fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        msg = buf;
+        return code;
+    }
+};
+
+#define AVN_CUDA(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return err_->fail(_e == cudaErrorMemoryAllocation ? AVN_ERR_OUT_OF_MEMORY : AVN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                                   \
+    } while (0)
+
+// grow-only device allocation
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) = 0;
+    virtual AvnStatus run() = 0;
+    virtual AvnStatus download() = 0;
+    virtual void timings(AvnTimings* t) const = 0;
+};
+struct BroadphaseBase {
+    virtual ~BroadphaseBase() {}
+    virtual AvnStatus upload(AvnAabbColumns* aabbs) = 0;
+    virtual AvnStatus run() = 0;
+    virtual AvnStatus download(AvnPairList* out) = 0;
+    virtual void timings(AvnTimings* t) const = 0;
+};
+
+SolverBase* make_solver(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device);
+BroadphaseBase* make_broadphase(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, int device);
+
+}  // namespace avn

@@ -1,0 +1,529 @@
+// Device-side data layout and per-item routines of the solver stage.
+//
+// HBM layout (S = float or double; Vec4<S> = one 128-bit (f32) or 2x128-bit (f64) access):
+//   bodies   vel[2*(B+1)]  = {lin.xyz,-}{ang.xyz,-}            SolverBody velocities      (solver_body/mod.rs:59-91)
+//            dlt[2*(B+1)]  = {delta_position.xyz,-}{delta_rotation.xyzw}
+//            inr[2*(B+1)]  = {inv_mass, flags, m00, m01}{m02, m11, m12, m22}   SolverBodyInertia (mod.rs:218-261)
+//            itg[2*B]      = {linear_increment.xyz, linear_damping_rhs}{angular_increment.xyz, angular_damping_rhs}
+//            slot B is SolverBody::DUMMY / SolverBodyInertia::DUMMY (static bodies, AVN_NO_BODY).
+//   contacts cst[20][Mpad] planes, manifold-major inside a plane so that a warp reads 32 consecutive Vec4:
+//            0 {n.xyz, friction} 1 {t1.xyz, restitution} 2 {tangent_velocity.xyz,-} 3 {body1, body2, info, first_point}
+//            4+4k {anchor1.xyz, initial_separation} 5+4k {anchor2.xyz, normal effective_mass}
+//            6+4k {normal impulse, total normal impulse, tangent impulse.x, .y}   <- the only plane written in the loop
+//            7+4k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
+//   joints   jnt[14][Jpad] planes in level-schedule order (see JP_* below).
+#pragma once
+#include "../../include/avian_b200.h"
+#include "avn_math.cuh"
+
+namespace avn {
+
+enum { CP_N = 0, CP_T1 = 1, CP_TV = 2, CP_IDX = 3, CP_PT0 = 4, CP_PLANES = 4 + 4 * AVN_MAX_MANIFOLD_POINTS };
+// info lane of plane CP_IDX
+enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7 };
+// flags lane of inr[2*i]
+enum { BF_LOCK_MASK = 0x3f, BF_HAS_SOLVER_BODY = 1 << 8, BF_KINEMATIC = 1 << 9, BF_GYRO = 1 << 10, BF_DYNAMIC = 1 << 11,
+       BF_CUSTOM_VEL = 1 << 12, BF_CUSTOM_POS = 1 << 13, BF_DOMINANCE_SHIFT = 16 };
+
+enum { JP_IDX = 0,   // {body1, body2, type | limit_enabled<<8 | damping<<16 | zero1<<24 | zero2<<25, original index}
+       JP_R1 = 1,    // {world_r1.xyz, compliance0}
+       JP_R2 = 2,    // {world_r2.xyz, compliance1}
+       JP_CD = 3,    // {center_difference.xyz, compliance2}
+       JP_RD = 4,    // rotation_difference quaternion (fixed / prismatic)
+       JP_A1 = 5,    // {a1.xyz, limit_min}
+       JP_A2 = 6,    // {a2.xyz, limit_max}
+       JP_B1 = 7,    // {b1.xyz, limit2_min}
+       JP_B2 = 8,    // {b2.xyz, limit2_max}
+       JP_LP = 9,    // {total_position_lagrange.xyz, damping_linear}
+       JP_LA = 10,   // {total rotation lagrange (first angular constraint).xyz, damping_angular}
+       JP_LB = 11,   // {total rotation lagrange (second angular constraint).xyz, -}
+       JP_PLANES = 12 };
+
+template <class S>
+struct Soft { S bias, mass_scale, impulse_scale; };
+
+template <class S>
+struct DevSolver {
+    int B, M, P, Mpad, J, Jpad, n_levels;
+    int color_off[AVN_GRAPH_COLOR_COUNT + 1];
+    int substeps, iters, rest_iters, fast_trig, match_contacts;
+    S h, dt, max_overlap_speed, warm_coeff, rest_threshold, joint_force_rhs;
+    S gx, gy, gz;
+    Soft<S> soft_dyn, soft_nondyn;
+    // raw body columns (device copies of the ABI columns; NULL when the host column was NULL)
+    const uint8_t* kind; const uint8_t* locked; const int8_t* dominance; const uint8_t* integ_flags;
+    const S* position; const S* rotation; const S* linvel; const S* angvel; const S* inv_mass; const S* inv_inertia_local;
+    const S* com; const S* lin_damp; const S* ang_damp; const S* grav_scale; const S* lin_acc; const S* ang_acc;
+    const S* max_lin; const S* max_ang;
+    S* out_position; S* out_rotation; S* out_linvel; S* out_angvel;
+    Vec4<S>* vel; Vec4<S>* dlt; Vec4<S>* inr; Vec4<S>* itg; Vec4<S>* pre;
+    // raw manifold columns
+    const int* m_body1; const int* m_body2; const S* m_normal; const S* m_friction; const S* m_restitution; const S* m_tanvel;
+    const uint32_t* m_point_off; const S* p_anchor1; const S* p_anchor2; const S* p_penetration; const S* p_normal_speed;
+    S* p_ws_normal; S* p_ws_tangent; S* p_normal_impulse;
+    Vec4<S>* cst;
+    int* any_restitution;
+    // joints
+    const int* j_src_type; const int* j_src_index;  // schedule slot -> (type, index in type)
+    const int* level_off;                           // [n_levels+1]
+    Vec4<S>* jnt;
+    const S* jc[AVN_JOINT_TYPE_COUNT][12];  // per type raw columns: la1 la2 lb1 lb2 axis lmin lmax l2min l2max c0 c1 c2
+    const S* jdamp_lin[AVN_JOINT_TYPE_COUNT]; const S* jdamp_ang[AVN_JOINT_TYPE_COUNT];
+    const uint8_t* jlimit_en[AVN_JOINT_TYPE_COUNT]; const uint8_t* jdamp_en[AVN_JOINT_TYPE_COUNT];
+    const int* jbody1[AVN_JOINT_TYPE_COUNT]; const int* jbody2[AVN_JOINT_TYPE_COUNT];
+    S* jforce[AVN_JOINT_TYPE_COUNT]; S* jtorque[AVN_JOINT_TYPE_COUNT];
+    int any_joint_damping;
+};
+
+template <class S> __device__ __forceinline__ V3<S> ldv3(const S* p, int i) { return mk3<S>(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+template <class S> __device__ __forceinline__ V3<S> ldv3_or0(const S* p, int i) { return p ? ldv3(p, i) : zero3<S>(); }
+template <class S> __device__ __forceinline__ Q4<S> ldq(const S* p, int i) {
+    Q4<S> q; q.x = p[4 * i]; q.y = p[4 * i + 1]; q.z = p[4 * i + 2]; q.w = p[4 * i + 3]; return q;
+}
+template <class S> __device__ __forceinline__ void stv3(S* p, int i, V3<S> v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+template <class S> struct BodyInertia {
+    V3<S> inv_mass;  // effective (locked axes applied)
+    Sym3<S> ii;
+};
+template <class S> __device__ __forceinline__ BodyInertia<S> zero_inertia() {
+    BodyInertia<S> r;
+    r.inv_mass = zero3<S>();
+    r.ii.m00 = r.ii.m01 = r.ii.m02 = r.ii.m11 = r.ii.m12 = r.ii.m22 = S(0);
+    return r;
+}
+// SolverBodyInertia::effective_inv_mass (solver_body/mod.rs:437-451)
+template <class S> __device__ __forceinline__ BodyInertia<S> unpack_inertia(Vec4<S> a, Vec4<S> b) {
+    BodyInertia<S> r;
+    int f = as_int(a.y);
+    r.inv_mass = mk3<S>((f & AVN_LOCK_TRANSLATION_X) ? S(0) : a.x, (f & AVN_LOCK_TRANSLATION_Y) ? S(0) : a.x,
+                        (f & AVN_LOCK_TRANSLATION_Z) ? S(0) : a.x);
+    r.ii.m00 = a.z; r.ii.m01 = a.w; r.ii.m02 = b.x; r.ii.m11 = b.y; r.ii.m12 = b.z; r.ii.m22 = b.w;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// prepare_solver_bodies (solver_body/plugin.rs:173-251) + pre_process_velocity_increments (integrator/mod.rs:260-313)
+// ---------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ void prepare_body_item(const DevSolver<S>& d, int i) {
+    Vec4<S> lin = mk4<S>(0, 0, 0, 0), ang = lin, dp = lin, dq = mk4<S>(0, 0, 0, 1);
+    Vec4<S> ia = mk4<S>(S(0), int_as(S(0), 128 << BF_DOMINANCE_SHIFT), S(0), S(0)), ib = mk4<S>(0, 0, 0, 0);
+    int kind = i < d.B ? (d.kind ? d.kind[i] : AVN_BODY_DYNAMIC) : AVN_BODY_STATIC;
+    if (kind != AVN_BODY_STATIC) {
+        V3<S> v = ldv3(d.linvel, i), w = ldv3(d.angvel, i);
+        lin = mk4<S>(v.x, v.y, v.z, 0);
+        ang = mk4<S>(w.x, w.y, w.z, 0);
+        int locked = d.locked ? d.locked[i] : 0;
+        S inv_mass = d.inv_mass[i];
+        Sym3<S> il;
+        il.m00 = d.inv_inertia_local[6 * i]; il.m01 = d.inv_inertia_local[6 * i + 1]; il.m02 = d.inv_inertia_local[6 * i + 2];
+        il.m11 = d.inv_inertia_local[6 * i + 3]; il.m12 = d.inv_inertia_local[6 * i + 4]; il.m22 = d.inv_inertia_local[6 * i + 5];
+        Sym3<S> iw = rotate_inv_inertia(il, ldq(d.rotation, i));
+        // SolverBodyInertia::new (solver_body/mod.rs:378-423)
+        if (locked & AVN_LOCK_ROTATION_X) { iw.m00 = 0; iw.m01 = 0; iw.m02 = 0; }
+        if (locked & AVN_LOCK_ROTATION_Y) { iw.m01 = 0; iw.m11 = 0; iw.m12 = 0; }
+        if (locked & AVN_LOCK_ROTATION_Z) { iw.m02 = 0; iw.m12 = 0; iw.m22 = 0; }
+        int dom = (kind == AVN_BODY_DYNAMIC) ? (d.dominance ? int(d.dominance[i]) : 0) : 128;
+        int flags = (locked & BF_LOCK_MASK) | BF_HAS_SOLVER_BODY | ((dom & 0xffff) << BF_DOMINANCE_SHIFT);
+        if (kind == AVN_BODY_KINEMATIC) flags |= BF_KINEMATIC;
+        if (kind == AVN_BODY_DYNAMIC) flags |= BF_DYNAMIC;
+        int ifl = d.integ_flags ? d.integ_flags[i] : 0;
+        if (ifl & AVN_CUSTOM_VELOCITY_INTEGRATION) flags |= BF_CUSTOM_VEL;
+        if (ifl & AVN_CUSTOM_POSITION_INTEGRATION) flags |= BF_CUSTOM_POS;
+        // gyroscopic iff rotation not fully locked and local inverse inertia not isotropic (eps 1e-6), plugin.rs:241-247
+        bool rot_locked = (locked & 0x7) == 0x7;
+        S eps = S(1e-6);
+        bool iso = !(avn_abs(il.m00 - il.m11) > eps || avn_abs(il.m11 - il.m22) > eps) && avn_abs(il.m01) < eps &&
+                   avn_abs(il.m02) < eps && avn_abs(il.m12) < eps;
+        if (!rot_locked && !iso) flags |= BF_GYRO;
+        ia = mk4<S>(inv_mass, int_as(S(0), flags), iw.m00, iw.m01);
+        ib = mk4<S>(iw.m02, iw.m11, iw.m12, iw.m22);
+    }
+    st4(&d.vel[2 * i], lin); st4(&d.vel[2 * i + 1], ang);
+    st4(&d.dlt[2 * i], dp); st4(&d.dlt[2 * i + 1], dq);
+    st4(&d.inr[2 * i], ia); st4(&d.inr[2 * i + 1], ib);
+    if (i < d.B) {
+        V3<S> li = ldv3_or0(d.lin_acc, i), ai = ldv3_or0(d.ang_acc, i);
+        S lr = S(1), ar = S(1);
+        if (kind == AVN_BODY_DYNAMIC) {
+            int locked = d.locked ? d.locked[i] : 0;
+            lr = S(1) / (S(1) + d.h * (d.lin_damp ? d.lin_damp[i] : S(0)));
+            ar = S(1) / (S(1) + d.h * (d.ang_damp ? d.ang_damp[i] : S(0)));
+            li = li + mk3<S>(d.gx, d.gy, d.gz) * (d.grav_scale ? d.grav_scale[i] : S(1));
+            if (locked & AVN_LOCK_TRANSLATION_X) li.x = 0;
+            if (locked & AVN_LOCK_TRANSLATION_Y) li.y = 0;
+            if (locked & AVN_LOCK_TRANSLATION_Z) li.z = 0;
+            if (locked & AVN_LOCK_ROTATION_X) ai.x = 0;
+            if (locked & AVN_LOCK_ROTATION_Y) ai.y = 0;
+            if (locked & AVN_LOCK_ROTATION_Z) ai.z = 0;
+            li = li * d.h;
+            ai = ai * d.h;
+        }
+        st4(&d.itg[2 * i], mk4<S>(li.x, li.y, li.z, lr));
+        st4(&d.itg[2 * i + 1], mk4<S>(ai.x, ai.y, ai.z, ar));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// prepare_contact_constraints -> ContactConstraint::generate (solver/plugin.rs:363-448, contact/mod.rs:110-220,
+// normal_part.rs:39-112, tangent_part.rs:35-151)
+// ---------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
+    int rb1 = d.m_body1[m], rb2 = d.m_body2[m];
+    int b1 = rb1 < 0 ? d.B : rb1, b2 = rb2 < 0 ? d.B : rb2;
+    Vec4<S> i1a = ld4(&d.inr[2 * b1]), i1b = ld4(&d.inr[2 * b1 + 1]);
+    Vec4<S> i2a = ld4(&d.inr[2 * b2]), i2b = ld4(&d.inr[2 * b2 + 1]);
+    int f1 = as_int(i1a.y), f2 = as_int(i2a.y);
+    uint32_t p0 = d.m_point_off[m], p1 = d.m_point_off[m + 1];
+    int np = int(p1 - p0);
+    Vec4<S>* c = d.cst + m;
+    const size_t MP = size_t(d.Mpad);
+    // skip contacts between two non-dynamic bodies (plugin.rs:415-418) and empty manifolds (:434)
+    if ((!(f1 & BF_DYNAMIC) && !(f2 & BF_DYNAMIC)) || np <= 0) {
+        st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), 0), int_as(S(0), int(p0))));
+        return;
+    }
+    int dom1 = (f1 >> BF_DOMINANCE_SHIFT) << 16 >> 16, dom2 = (f2 >> BF_DOMINANCE_SHIFT) << 16 >> 16;  // sign-extend i16
+    int rel = dom1 - dom2;
+    BodyInertia<S> in1 = rel > 0 ? zero_inertia<S>() : unpack_inertia(i1a, i1b);
+    BodyInertia<S> in2 = rel < 0 ? zero_inertia<S>() : unpack_inertia(i2a, i2b);
+    int info = np;
+    if (rel > 0 || !(f1 & BF_HAS_SOLVER_BODY)) info |= CI_ZERO1;
+    if (rel < 0 || !(f2 & BF_HAS_SOLVER_BODY)) info |= CI_ZERO2;
+    if (rel != 0) info |= CI_NONDYN;
+    V3<S> mass_sum = in1.inv_mass + in2.inv_mass;
+    V3<S> n = ldv3(d.m_normal, m);
+    // compute_tangent_directions (contact/mod.rs:427-449): LinearVelocity components of the rigid bodies
+    V3<S> v1 = rb1 >= 0 ? ldv3(d.linvel, rb1) : zero3<S>();
+    V3<S> v2 = rb2 >= 0 ? ldv3(d.linvel, rb2) : zero3<S>();
+    V3<S> fd = -n;
+    V3<S> rv = v1 - v2;
+    V3<S> tvv = rv - fd * dot(fd, rv);
+    V3<S> t1;
+    {
+        S rcp = S(1) / len(tvv);
+        if (avn_finite(rcp) && rcp > S(0)) t1 = tvv * rcp; else t1 = any_orthonormal(fd);
+    }
+    V3<S> t2 = cross(fd, t1);
+    S friction = d.m_friction[m], restitution = d.m_restitution[m];
+    if (friction > S(0)) info |= CI_TANGENT;
+    if (restitution != S(0)) *d.any_restitution = 1;
+    V3<S> tv = ldv3_or0(d.m_tanvel, m);
+    st4(&c[CP_N * MP], mk4<S>(n.x, n.y, n.z, friction));
+    st4(&c[CP_T1 * MP], mk4<S>(t1.x, t1.y, t1.z, restitution));
+    st4(&c[CP_TV * MP], mk4<S>(tv.x, tv.y, tv.z, S(0)));
+    st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), info), int_as(S(0), int(p0))));
+    bool warm = d.match_contacts != 0;
+    for (int k = 0; k < np; ++k) {
+        uint32_t p = p0 + k;
+        V3<S> r1 = ldv3(d.p_anchor1, p), r2 = ldv3(d.p_anchor2, p);
+        V3<S> r1xn = cross(r1, n), r2xn = cross(r2, n);
+        S k_linear = dot(n, cmul(mass_sum, n));
+        S kk = k_linear + dot(r1xn, smul(in1.ii, r1xn)) + dot(r2xn, smul(in2.ii, r2xn));
+        S meff = recip_or_zero(kk);
+        S sep0 = -d.p_penetration[p] - dot(r2 - r1, n);
+        S imp_n = warm ? d.p_ws_normal[p] : S(0);
+        S itx = S(0), ity = S(0), K1 = S(0), K2 = S(0), K3 = S(0);
+        if (info & CI_TANGENT) {
+            if (warm) { itx = d.p_ws_tangent[2 * p]; ity = d.p_ws_tangent[2 * p + 1]; }
+            V3<S> rt11 = cross(r1, t1), rt12 = cross(r2, t1), rt21 = cross(r1, t2), rt22 = cross(r2, t2);
+            V3<S> i1_rt11 = smul(in1.ii, rt11), i2_rt12 = smul(in2.ii, rt12), i1_rt21 = smul(in1.ii, rt21), i2_rt22 = smul(in2.ii, rt22);
+            S kl1 = dot(t1, cmul(mass_sum, t1)), kl2 = dot(t2, cmul(mass_sum, t2));
+            K1 = kl1 + dot(rt11, i1_rt11) + dot(rt12, i2_rt12);
+            K2 = kl2 + dot(rt21, i1_rt21) + dot(rt22, i2_rt22);
+            K3 = S(2) * (dot(rt11, i1_rt21) + dot(rt12, i2_rt22));
+        }
+        Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
+        st4(&cp[0], mk4<S>(r1.x, r1.y, r1.z, sep0));
+        st4(&cp[MP], mk4<S>(r2.x, r2.y, r2.z, meff));
+        st4(&cp[2 * MP], mk4<S>(imp_n, S(0), itx, ity));
+        st4(&cp[3 * MP], mk4<S>(K1, K2, K3, d.p_normal_speed[p]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// warm_start / solve_contacts<BIAS> / relax / restitution for ONE manifold (one thread)
+// ---------------------------------------------------------------------------------------------------------
+enum { PASS_WARM = 0, PASS_SOLVE_BIAS = 1, PASS_RELAX = 2, PASS_RESTITUTION = 3 };
+
+template <class S>
+__device__ __forceinline__ void apply_impulse(V3<S>& v1, V3<S>& w1, V3<S>& v2, V3<S>& w2, const BodyInertia<S>& in1, const BodyInertia<S>& in2,
+                                              V3<S> r1, V3<S> r2, V3<S> imp) {
+    v1 = v1 - cmul(imp, in1.inv_mass);
+    w1 = w1 - smul(in1.ii, cross(r1, imp));
+    v2 = v2 + cmul(imp, in2.inv_mass);
+    w2 = w2 + smul(in2.ii, cross(r2, imp));
+}
+
+template <class S, int PASS>
+__device__ __forceinline__ void contact_item(const DevSolver<S>& d, int m) {
+    const size_t MP = size_t(d.Mpad);
+    Vec4<S>* c = d.cst + m;
+    Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
+    const int info = as_int(hidx.z);
+    const int np = info & CI_NP_MASK;
+    if (np == 0) return;
+    const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
+    // ---- issue every load up front (independent 128-bit loads -> memory-level parallelism)
+    Vec4<S> hn = ld4(&c[CP_N * MP]);
+    Vec4<S> ht1 = ld4(&c[CP_T1 * MP]);
+    Vec4<S> htv = mk4<S>(0, 0, 0, 0);
+    if (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) htv = ld4(&c[CP_TV * MP]);
+    Vec4<S> l1 = ld4(&d.vel[2 * b1]), a1 = ld4(&d.vel[2 * b1 + 1]);
+    Vec4<S> l2 = ld4(&d.vel[2 * b2]), a2 = ld4(&d.vel[2 * b2 + 1]);
+    BodyInertia<S> in1 = zero_inertia<S>(), in2 = zero_inertia<S>();
+    if (!(info & CI_ZERO1)) in1 = unpack_inertia(ld4(&d.inr[2 * b1]), ld4(&d.inr[2 * b1 + 1]));
+    if (!(info & CI_ZERO2)) in2 = unpack_inertia(ld4(&d.inr[2 * b2]), ld4(&d.inr[2 * b2 + 1]));
+    Vec4<S> dp1, dq1, dp2, dq2;
+    if (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) {
+        dp1 = ld4(&d.dlt[2 * b1]); dq1 = ld4(&d.dlt[2 * b1 + 1]);
+        dp2 = ld4(&d.dlt[2 * b2]); dq2 = ld4(&d.dlt[2 * b2 + 1]);
+    }
+    Vec4<S> PA[AVN_MAX_MANIFOLD_POINTS], PB[AVN_MAX_MANIFOLD_POINTS], PC[AVN_MAX_MANIFOLD_POINTS], PD[AVN_MAX_MANIFOLD_POINTS];
+#pragma unroll
+    for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+        if (k < np) {
+            Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
+            PA[k] = ld4(&cp[0]);
+            PB[k] = ld4(&cp[MP]);
+            PC[k] = ld4(&cp[2 * MP]);
+            if (PASS == PASS_RESTITUTION || ((PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) && (info & CI_TANGENT))) PD[k] = ld4(&cp[3 * MP]);
+        }
+    }
+    V3<S> v1 = xyz(l1), w1 = xyz(a1), v2 = xyz(l2), w2 = xyz(a2);
+    const V3<S> n = xyz(hn), t1 = xyz(ht1);
+    const V3<S> t2 = cross(t1, n);  // tangent_directions(): [tangent1, tangent1 x normal] (contact/mod.rs:411-421)
+
+    if (PASS == PASS_WARM) {
+        // ContactConstraint::warm_start (contact/mod.rs:223-264)
+#pragma unroll
+        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+            if (k < np) {
+                V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                S tx = (info & CI_TANGENT) ? PC[k].z : S(0), ty = (info & CI_TANGENT) ? PC[k].w : S(0);
+                V3<S> p = d.warm_coeff * ((PC[k].x * n + tx * t1) + ty * t2);
+                apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, p);
+            }
+        }
+    } else if (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) {
+        // ContactConstraint::solve (contact/mod.rs:267-354)
+        const Soft<S> soft = (info & CI_NONDYN) ? d.soft_nondyn : d.soft_dyn;
+        Q4<S> q1; q1.x = dq1.x; q1.y = dq1.y; q1.z = dq1.z; q1.w = dq1.w;
+        Q4<S> q2; q2.x = dq2.x; q2.y = dq2.y; q2.z = dq2.z; q2.w = dq2.w;
+        const V3<S> delta_translation = xyz(dp2) - xyz(dp1);
+#pragma unroll
+        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+            if (k < np) {
+                V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                V3<S> rr1 = qrot(q1, r1), rr2 = qrot(q2, r2);
+                V3<S> dsep = delta_translation + (rr2 - rr1);
+                S separation = dot(dsep, n) + PA[k].w;
+                V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
+                // ContactNormalPart::solve_impulse (normal_part.rs:116-166)
+                S vn = dot(relv, n);
+                S meff = PB[k].w, acc = PC[k].x;
+                S impulse;
+                if (separation > S(0)) {
+                    impulse = -meff * (vn + separation / d.h);
+                } else if (PASS == PASS_SOLVE_BIAS) {
+                    S bias = avn_max(soft.bias * separation, -d.max_overlap_speed);
+                    S scaled_mass = soft.mass_scale * meff;
+                    S scaled_impulse = soft.impulse_scale * acc;
+                    impulse = -scaled_mass * (vn + bias) - scaled_impulse;
+                } else {
+                    impulse = -meff * vn;
+                }
+                S new_impulse = avn_max(acc + impulse, S(0));
+                impulse = new_impulse - acc;
+                PC[k].x = new_impulse;
+                PC[k].y = PC[k].y + new_impulse;
+                apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, impulse * n);
+            }
+        }
+        if (info & CI_TANGENT) {
+            const S friction = hn.w;
+            const V3<S> surf = xyz(htv);
+#pragma unroll
+            for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+                if (k < np) {
+                    V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                    V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
+                    // ContactTangentPart::solve_impulse (tangent_part.rs:155-244)
+                    S limit = friction * PC[k].x;
+                    relv = relv + surf;
+                    S ts1 = dot(relv, t1), ts2 = dot(relv, t2);
+                    S t11 = ts1 * ts1, t22 = ts2 * ts2, t12 = ts1 * ts2;
+                    S inv = (t11 * PD[k].x + t22 * PD[k].y) + t12 * PD[k].z;
+                    S em = (t11 + t22) * (S(1) / inv);
+                    V3<S> imp = zero3<S>();
+                    if (avn_finite(em)) {
+                        S nx = PC[k].z - em * ts1, ny = PC[k].w - em * ts2;
+                        S l2 = nx * nx + ny * ny;
+                        if (l2 > limit * limit) {  // Vec2::clamp_length_max
+                            S l = avn_sqrt(l2);
+                            nx = limit * (nx / l);
+                            ny = limit * (ny / l);
+                        }
+                        S dx = nx - PC[k].z, dy = ny - PC[k].w;
+                        PC[k].z = nx;
+                        PC[k].w = ny;
+                        imp = dx * t1 + dy * t2;
+                    }
+                    apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, imp);
+                }
+            }
+        }
+    } else {
+        // solve_restitution_internal + ContactConstraint::apply_restitution (plugin.rs:676-718, contact/mod.rs:358-407)
+        const S e = ht1.w;
+        if (e == S(0)) return;
+        const int iterations = np > 1 ? d.rest_iters : 1;
+        for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+            for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+                if (k < np) {
+                    if (PD[k].w > -d.rest_threshold || PC[k].y == S(0)) continue;
+                    V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                    V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
+                    S vn = dot(relv, n);
+                    S impulse = -PB[k].w * (vn + e * PD[k].w);
+                    S new_impulse = avn_max(PC[k].x + impulse, S(0));
+                    impulse = new_impulse - PC[k].x;
+                    PC[k].x = new_impulse;
+                    PC[k].y = PC[k].y + impulse;
+                    apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, impulse * n);
+                }
+            }
+        }
+    }
+    // ---- write back: impulses (plane 6+4k) and the velocities of the non-dominant sides
+    if (PASS != PASS_WARM) {
+#pragma unroll
+        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
+            if (k < np) st4(&c[size_t(CP_PT0 + 4 * k + 2) * MP], PC[k]);
+    }
+    if (!(info & CI_ZERO1)) {
+        st4(&d.vel[2 * b1], mk4<S>(v1.x, v1.y, v1.z, S(0)));
+        st4(&d.vel[2 * b1 + 1], mk4<S>(w1.x, w1.y, w1.z, S(0)));
+    }
+    if (!(info & CI_ZERO2)) {
+        st4(&d.vel[2 * b2], mk4<S>(v2.x, v2.y, v2.z, S(0)));
+        st4(&d.vel[2 * b2 + 1], mk4<S>(w2.x, w2.y, w2.z, S(0)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// integrate_velocities + clamp_velocities (integrator/mod.rs:343-391, 467-500)
+// ---------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, int i) {
+    Vec4<S> ia = ld4(&d.inr[2 * i]);
+    int f = as_int(ia.y);
+    if (!(f & BF_HAS_SOLVER_BODY)) return;
+    Vec4<S> l = ld4(&d.vel[2 * i]), a = ld4(&d.vel[2 * i + 1]);
+    V3<S> v = xyz(l), w = xyz(a);
+    bool touched = false;
+    if (!(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC)) {
+        Vec4<S> li = ld4(&d.itg[2 * i]), ai = ld4(&d.itg[2 * i + 1]);
+        v = v * li.w;
+        w = w * ai.w;
+        v = v + xyz(li);
+        w = w + xyz(ai);
+        if (f & BF_GYRO) {
+            // solve_gyroscopic_torque (integrator/mod.rs:403-460)
+            Vec4<S> dq4 = ld4(&d.dlt[2 * i + 1]);
+            Q4<S> dq; dq.x = dq4.x; dq.y = dq4.y; dq.z = dq4.z; dq.w = dq4.w;
+            Q4<S> rot = qmul(dq, ldq(d.rotation, i));
+            Sym3<S> il;
+            il.m00 = d.inv_inertia_local[6 * i]; il.m01 = d.inv_inertia_local[6 * i + 1]; il.m02 = d.inv_inertia_local[6 * i + 2];
+            il.m11 = d.inv_inertia_local[6 * i + 3]; il.m12 = d.inv_inertia_local[6 * i + 4]; il.m22 = d.inv_inertia_local[6 * i + 5];
+            V3<S> lw = qrot(qconj(rot), w);
+            Sym3<S> tensor = sym_inverse_or_zero(il);
+            V3<S> L = smul(tensor, lw);
+            V3<S> Ln = L - d.h * cross(lw, L);
+            S l2 = len2(Ln);
+            if (l2 == S(0)) {
+                w = zero3<S>();
+            } else {
+                Ln = Ln * avn_sqrt(len2(L) / l2);
+                w = qrot(rot, smul(il, Ln));
+            }
+        }
+        touched = true;
+    }
+    if (d.max_lin) {
+        S ms = d.max_lin[i];
+        S l2 = len2(v);
+        if (avn_finite(ms) && l2 > ms * ms) { v = v * (ms / avn_sqrt(l2)); touched = true; }
+    }
+    if (d.max_ang) {
+        S ms = d.max_ang[i];
+        S l2 = len2(w);
+        if (avn_finite(ms) && l2 > ms * ms) { w = w * (ms / avn_sqrt(l2)); touched = true; }
+    }
+    if (touched) {
+        st4(&d.vel[2 * i], mk4<S>(v.x, v.y, v.z, S(0)));
+        st4(&d.vel[2 * i + 1], mk4<S>(w.x, w.y, w.z, S(0)));
+    }
+}
+
+// integrate_positions (integrator/mod.rs:503-535)
+template <class S>
+__device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, int i) {
+    Vec4<S> ia = ld4(&d.inr[2 * i]);
+    int f = as_int(ia.y);
+    if (!(f & BF_HAS_SOLVER_BODY) || (f & BF_CUSTOM_POS)) return;
+    Vec4<S> l = ld4(&d.vel[2 * i]), a = ld4(&d.vel[2 * i + 1]);
+    Vec4<S> dp = ld4(&d.dlt[2 * i]), dq4 = ld4(&d.dlt[2 * i + 1]);
+    V3<S> ndp = xyz(dp) + xyz(l) * d.h;
+    Q4<S> dq; dq.x = dq4.x; dq.y = dq4.y; dq.z = dq4.z; dq.w = dq4.w;
+    Q4<S> nq = qmul(q_from_scaled_axis(xyz(a) * d.h, d.fast_trig != 0), dq);
+    st4(&d.dlt[2 * i], mk4<S>(ndp.x, ndp.y, ndp.z, S(0)));
+    st4(&d.dlt[2 * i + 1], mk4<S>(nq.x, nq.y, nq.z, nq.w));
+}
+
+// writeback_solver_bodies (solver_body/plugin.rs:255-284)
+template <class S>
+__device__ __forceinline__ void writeback_body_item(const DevSolver<S>& d, int i) {
+    Vec4<S> ia = ld4(&d.inr[2 * i]);
+    int f = as_int(ia.y);
+    V3<S> pos = ldv3(d.position, i);
+    Q4<S> rot = ldq(d.rotation, i);
+    V3<S> lv = ldv3(d.linvel, i), av = ldv3(d.angvel, i);
+    if (f & BF_HAS_SOLVER_BODY) {
+        Vec4<S> l = ld4(&d.vel[2 * i]), a = ld4(&d.vel[2 * i + 1]);
+        Vec4<S> dp = ld4(&d.dlt[2 * i]), dq4 = ld4(&d.dlt[2 * i + 1]);
+        V3<S> com = ldv3_or0(d.com, i);
+        V3<S> old_com = qrot(rot, com);
+        Q4<S> dq; dq.x = dq4.x; dq.y = dq4.y; dq.z = dq4.z; dq.w = dq4.w;
+        rot = q_fast_renormalize(qmul(dq, rot));
+        V3<S> new_com = qrot(rot, com);
+        pos = pos + ((xyz(dp) + old_com) - new_com);
+        lv = xyz(l);
+        av = xyz(a);
+    }
+    stv3(d.out_position, i, pos);
+    d.out_rotation[4 * i] = rot.x; d.out_rotation[4 * i + 1] = rot.y; d.out_rotation[4 * i + 2] = rot.z; d.out_rotation[4 * i + 3] = rot.w;
+    stv3(d.out_linvel, i, lv);
+    stv3(d.out_angvel, i, av);
+}
+
+// store_contact_impulses (solver/plugin.rs:722-755)
+template <class S>
+__device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m) {
+    const size_t MP = size_t(d.Mpad);
+    const Vec4<S>* c = d.cst + m;
+    Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
+    int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = as_int(hidx.w);
+    for (int k = 0; k < np; ++k) {
+        Vec4<S> pc = ld4(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
+        d.p_ws_normal[p0 + k] = pc.x;
+        d.p_ws_tangent[2 * (p0 + k)] = (info & CI_TANGENT) ? pc.z : S(0);
+        d.p_ws_tangent[2 * (p0 + k) + 1] = (info & CI_TANGENT) ? pc.w : S(0);
+        d.p_normal_impulse[p0 + k] = pc.y;
+    }
+}
+
+}  // namespace avn

@@ -1,0 +1,440 @@
+// Host driver of the solver stage: column upload, level schedule for joints, kernel launch, result download.
+// Reference systems replaced: see avn_solver_step in include/avian_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "context.hpp"
+#include "solver_kernels.cuh"
+
+namespace avn {
+
+namespace {
+
+// SoftnessParameters::new + compute_coefficients (softness_parameters/mod.rs:22-79), evaluated in S like the reference
+template <class S>
+Soft<S> softness(S damping_ratio, S hz, S delta_secs) {
+    S double_damping_ratio = S(2) * damping_ratio;
+    S angular_frequency = S(6.283185307179586476925286766559) * hz;
+    S a1 = double_damping_ratio + angular_frequency * delta_secs;
+    S a2 = angular_frequency * delta_secs * a1;
+    S a3 = S(1) / (S(1) + a2);
+    Soft<S> s;
+    s.bias = angular_frequency / a1;
+    s.mass_scale = a2 * a3;
+    s.impulse_scale = a3;
+    return s;
+}
+
+template <class S>
+class Solver final : public SolverBase {
+   public:
+    Solver(cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device) : stream_(stream), err_(err), cfg_flags_(cfg_flags) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+            sm_count_ = prop.multiProcessorCount;
+            coop_ok_ = prop.cooperativeLaunch != 0;
+        }
+        const char* mode = getenv("AVN_LAUNCH_MODE");
+        if (mode && !strcmp(mode, "phases")) use_mega_ = false;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_megakernel<S>, MEGA_BLOCK, 0) == cudaSuccess && per_sm > 0)
+            mega_grid_ = per_sm * sm_count_;
+        else
+            coop_ok_ = false;
+        for (auto& e : ev_) cudaEventCreate(&e);
+    }
+    ~Solver() override {
+        for (auto& e : ev_) cudaEventDestroy(e);
+    }
+
+    AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
+    AvnStatus run() override;
+    AvnStatus download() override;
+    void timings(AvnTimings* t) const override { *t = tm_; }
+
+   private:
+    static constexpr int kBlock = 256;
+    enum { EV_H2D0, EV_H2D1, EV_RUN0, EV_PREP, EV_LOOP, EV_RUN1, EV_D2H0, EV_D2H1, EV_COUNT };
+
+    // copy one host column to the device; returns nullptr for a NULL host column
+    template <class T>
+    AvnStatus up(DevBuf& buf, const void* host, size_t count, const T** dev) {
+        *dev = nullptr;
+        if (!host || count == 0) return AVN_OK;
+        AVN_CUDA(buf.ensure(count * sizeof(T)));
+        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        *dev = buf.as<T>();
+        h2d_bytes_ += count * sizeof(T);
+        return AVN_OK;
+    }
+    AvnStatus build_joint_schedule(const AvnBodyColumns& bc, const AvnJointSet& js);
+    template <int OP> void launch_phase(int begin, int count, bool serial = false) {
+        if (count <= 0) return;
+        int grid = serial ? 1 : std::min((count + kBlock - 1) / kBlock, sm_count_ * 8);
+        phase_kernel<S, OP><<<grid, kBlock, 0, stream_>>>(dev_, begin, count, serial ? 1 : 0);
+        ++launches_;
+    }
+    template <int OP> void launch_contact_pass() {
+        const int* off = dev_.color_off;
+        launch_phase<OP>(off[AVN_COLOR_OVERFLOW], off[AVN_COLOR_OVERFLOW + 1] - off[AVN_COLOR_OVERFLOW], true);
+        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) launch_phase<OP>(off[c], off[c + 1] - off[c]);
+    }
+
+    cudaStream_t stream_;
+    ErrorSink* err_;
+    uint32_t cfg_flags_;
+    int sm_count_ = 148;
+    bool coop_ok_ = false, use_mega_ = true;
+    int mega_grid_ = 0;
+    cudaEvent_t ev_[EV_COUNT];
+    AvnTimings tm_{};
+    uint32_t launches_ = 0;
+    size_t h2d_bytes_ = 0;
+    bool uploaded_ = false, ran_ = false, host_any_restitution_ = false;
+
+    DevSolver<S> dev_{};
+    // host pointers for download
+    AvnBodyColumns hb_{};
+    AvnManifoldColumns hm_{};
+    AvnJointSet hj_{};
+    bool have_m_ = false, have_j_ = false;
+
+    // device storage
+    DevBuf b_kind_, b_locked_, b_dom_, b_iflags_, b_pos_, b_rot_, b_lv_, b_av_, b_im_, b_iil_, b_com_, b_ld_, b_ad_, b_gs_, b_la_, b_aa_, b_ml_, b_ma_;
+    DevBuf o_pos_, o_rot_, o_lv_, o_av_;
+    DevBuf s_vel_, s_dlt_, s_inr_, s_itg_, s_pre_;
+    DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_;
+    DevBuf c_planes_, c_flag_;
+    DevBuf j_type_, j_index_, j_level_, j_planes_;
+    DevBuf jcol_[AVN_JOINT_TYPE_COUNT][12], jb1_[AVN_JOINT_TYPE_COUNT], jb2_[AVN_JOINT_TYPE_COUNT], jle_[AVN_JOINT_TYPE_COUNT],
+        jde_[AVN_JOINT_TYPE_COUNT], jdl_[AVN_JOINT_TYPE_COUNT], jda_[AVN_JOINT_TYPE_COUNT], jfo_[AVN_JOINT_TYPE_COUNT], jto_[AVN_JOINT_TYPE_COUNT];
+    std::vector<int> h_type_, h_index_, h_level_off_;
+};
+
+template <class S>
+AvnStatus Solver<S>::build_joint_schedule(const AvnBodyColumns& bc, const AvnJointSet& js) {
+    // global joint order = the reference's serial solve order: type order, then table order (xpbd/plugin.rs:58-86)
+    size_t J = 0;
+    for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) J += js.types[t].count;
+    const uint32_t B = bc.count;
+    std::vector<int> type(J), index(J), b1(J), b2(J);
+    std::vector<uint8_t> conflict(B, 0);
+    bool any_damping = false;
+    size_t g = 0;
+    auto dom_of = [&](int b) -> int {
+        uint8_t kind = bc.kind ? bc.kind[b] : uint8_t(AVN_BODY_DYNAMIC);
+        return kind == AVN_BODY_DYNAMIC ? (bc.dominance ? int(bc.dominance[b]) : 0) : 128;
+    };
+    auto has_sb = [&](int b) { return (bc.kind ? bc.kind[b] : uint8_t(AVN_BODY_DYNAMIC)) != AVN_BODY_STATIC; };
+    for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) {
+        const AvnJointColumns& jc = js.types[t];
+        if (jc.count && (!jc.body1 || !jc.body2 || !jc.local_anchor1 || !jc.local_anchor2))
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "joint type %d: body1/body2/local_anchor1/local_anchor2 are required", t);
+        for (uint32_t k = 0; k < jc.count; ++k, ++g) {
+            int x = jc.body1[k], y = jc.body2[k];
+            if (x < 0 || y < 0 || uint32_t(x) >= B || uint32_t(y) >= B)
+                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "joint type %d #%u references body %d/%d outside [0,%u)", t, k, x, y, B);
+            type[g] = t; index[g] = int(k); b1[g] = x; b2[g] = y;
+            if (jc.damping_enabled && jc.damping_enabled[k]) any_damping = true;
+        }
+    }
+    // a body orders the joints that touch it iff some joint WRITES it: it has a SolverBody and is not the dominated
+    // side there.  With joint damping every SolverBody is written (solver/plugin.rs:789-803).
+    for (g = 0; g < J; ++g) {
+        int rel = dom_of(b1[g]) - dom_of(b2[g]);
+        if (has_sb(b1[g]) && (any_damping || !(rel > 0))) conflict[b1[g]] = 1;
+        if (has_sb(b2[g]) && (any_damping || !(rel < 0))) conflict[b2[g]] = 1;
+    }
+    std::vector<int> last(B, 0), level(J);
+    int n_levels = 0;
+    for (g = 0; g < J; ++g) {
+        int l = 0;
+        if (conflict[b1[g]]) l = std::max(l, last[b1[g]]);
+        if (conflict[b2[g]]) l = std::max(l, last[b2[g]]);
+        level[g] = l;  // 0-based
+        if (conflict[b1[g]]) last[b1[g]] = l + 1;
+        if (conflict[b2[g]]) last[b2[g]] = l + 1;
+        n_levels = std::max(n_levels, l + 1);
+    }
+    h_level_off_.assign(n_levels + 1, 0);
+    for (g = 0; g < J; ++g) ++h_level_off_[level[g] + 1];
+    for (int l = 0; l < n_levels; ++l) h_level_off_[l + 1] += h_level_off_[l];
+    h_type_.resize(J);
+    h_index_.resize(J);
+    std::vector<int> cursor(h_level_off_.begin(), h_level_off_.end() - 1);
+    for (g = 0; g < J; ++g) {  // stable within a level
+        int s = cursor[level[g]]++;
+        h_type_[s] = type[g];
+        h_index_[s] = index[g];
+    }
+    dev_.J = int(J);
+    dev_.Jpad = int((J + 31) & ~size_t(31));
+    dev_.n_levels = n_levels;
+    dev_.any_joint_damping = any_damping ? 1 : 0;
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) {
+    if (!prm || !bc) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "params and bodies are required");
+    if (bc->count && (!bc->position || !bc->rotation || !bc->linear_velocity || !bc->angular_velocity || !bc->inverse_mass || !bc->inverse_inertia_local))
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "bodies: position, rotation, velocities, inverse_mass and inverse_inertia_local are required");
+    if (!(prm->h > 0) || !(prm->dt > 0) || prm->substeps == 0) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "dt, h and substeps must be positive");
+    uploaded_ = false;
+    ran_ = false;
+    h2d_bytes_ = 0;
+    DevSolver<S>& d = dev_;
+    d = DevSolver<S>{};
+    const size_t B = bc->count;
+    cudaEventRecord(ev_[EV_H2D0], stream_);
+    // ---- parameters
+    d.B = int(B);
+    d.substeps = int(prm->substeps);
+    d.iters = prm->solver_iterations ? int(prm->solver_iterations) : 1;
+    d.rest_iters = int(prm->restitution_iterations);
+    d.fast_trig = (cfg_flags_ & AVN_CFG_FAST_TRIG) ? 1 : 0;
+    d.match_contacts = int(prm->match_contacts);
+    d.h = S(prm->h);
+    d.dt = S(prm->dt);
+    d.max_overlap_speed = S(prm->max_overlap_solve_speed) * S(prm->length_unit);
+    d.warm_coeff = S(prm->warm_start_coefficient);
+    d.rest_threshold = S(prm->restitution_threshold) * S(prm->length_unit);
+    d.gx = S(prm->gravity[0]); d.gy = S(prm->gravity[1]); d.gz = S(prm->gravity[2]);
+    {
+        // update_contact_softness (solver/plugin.rs:326-350)
+        S max_hz = S(1) / (d.dt * S(2));
+        S hz = S(prm->contact_frequency_factor) * std::min(max_hz, S(0.25) / d.h);
+        d.soft_dyn = softness<S>(S(prm->contact_damping_ratio), hz, d.h);
+        d.soft_nondyn = softness<S>(S(prm->contact_damping_ratio), S(2) * hz, d.h);
+        // writeback_joint_forces rhs (xpbd/plugin.rs:253): (h*h).recip_or_zero() * substeps
+        S hh = d.h * d.h;
+        d.joint_force_rhs = ((hh != S(0) && std::isfinite(hh)) ? S(1) / hh : S(0)) * S(prm->substeps);
+    }
+    // ---- body columns
+    AvnStatus st;
+#define UP(buf, host, n, T, field) if ((st = up<T>(buf, host, n, &d.field)) != AVN_OK) return st
+    UP(b_kind_, bc->kind, B, uint8_t, kind);
+    UP(b_locked_, bc->locked_axes, B, uint8_t, locked);
+    UP(b_dom_, bc->dominance, B, int8_t, dominance);
+    UP(b_iflags_, bc->integration_flags, B, uint8_t, integ_flags);
+    UP(b_pos_, bc->position, 3 * B, S, position);
+    UP(b_rot_, bc->rotation, 4 * B, S, rotation);
+    UP(b_lv_, bc->linear_velocity, 3 * B, S, linvel);
+    UP(b_av_, bc->angular_velocity, 3 * B, S, angvel);
+    UP(b_im_, bc->inverse_mass, B, S, inv_mass);
+    UP(b_iil_, bc->inverse_inertia_local, 6 * B, S, inv_inertia_local);
+    UP(b_com_, bc->center_of_mass, 3 * B, S, com);
+    UP(b_ld_, bc->linear_damping, B, S, lin_damp);
+    UP(b_ad_, bc->angular_damping, B, S, ang_damp);
+    UP(b_gs_, bc->gravity_scale, B, S, grav_scale);
+    UP(b_la_, bc->linear_acceleration, 3 * B, S, lin_acc);
+    UP(b_aa_, bc->angular_acceleration, 3 * B, S, ang_acc);
+    UP(b_ml_, bc->max_linear_speed, B, S, max_lin);
+    UP(b_ma_, bc->max_angular_speed, B, S, max_ang);
+    AVN_CUDA(o_pos_.ensure(3 * B * sizeof(S) + 16)); d.out_position = o_pos_.as<S>();
+    AVN_CUDA(o_rot_.ensure(4 * B * sizeof(S) + 16)); d.out_rotation = o_rot_.as<S>();
+    AVN_CUDA(o_lv_.ensure(3 * B * sizeof(S) + 16)); d.out_linvel = o_lv_.as<S>();
+    AVN_CUDA(o_av_.ensure(3 * B * sizeof(S) + 16)); d.out_angvel = o_av_.as<S>();
+    const size_t state_bytes = 2 * (B + 1) * sizeof(Vec4<S>);
+    AVN_CUDA(s_vel_.ensure(state_bytes)); d.vel = s_vel_.as<Vec4<S>>();
+    AVN_CUDA(s_dlt_.ensure(state_bytes)); d.dlt = s_dlt_.as<Vec4<S>>();
+    AVN_CUDA(s_inr_.ensure(state_bytes)); d.inr = s_inr_.as<Vec4<S>>();
+    AVN_CUDA(s_itg_.ensure(state_bytes)); d.itg = s_itg_.as<Vec4<S>>();
+    AVN_CUDA(s_pre_.ensure(state_bytes)); d.pre = s_pre_.as<Vec4<S>>();
+    hb_ = *bc;
+    // ---- manifolds
+    have_m_ = mc && mc->count > 0;
+    AVN_CUDA(c_flag_.ensure(sizeof(int)));
+    d.any_restitution = c_flag_.as<int>();
+    if (have_m_) {
+        const size_t M = mc->count, P = mc->point_count;
+        if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
+            !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+        if (mc->color_offsets[0] != 0 || mc->color_offsets[AVN_GRAPH_COLOR_COUNT] != M)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must span [0, count]");
+        for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
+            if (mc->color_offsets[c] > mc->color_offsets[c + 1]) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must be non-decreasing");
+        if (mc->point_offsets[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
+        d.M = int(M);
+        d.P = int(P);
+        d.Mpad = int((M + 31) & ~size_t(31));
+        for (int c = 0; c <= AVN_GRAPH_COLOR_COUNT; ++c) d.color_off[c] = int(mc->color_offsets[c]);
+        UP(m_b1_, mc->body1, M, int, m_body1);
+        UP(m_b2_, mc->body2, M, int, m_body2);
+        UP(m_n_, mc->normal, 3 * M, S, m_normal);
+        UP(m_f_, mc->friction, M, S, m_friction);
+        UP(m_r_, mc->restitution, M, S, m_restitution);
+        UP(m_tv_, mc->tangent_velocity, 3 * M, S, m_tanvel);
+        UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_off);
+        UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
+        UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
+        UP(p_pen_, mc->penetration, P, S, p_penetration);
+        UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
+        // the two in/out columns are uploaded into buffers the kernels also write
+        AVN_CUDA(p_wn_.ensure(P * sizeof(S) + 16));
+        AVN_CUDA(cudaMemcpyAsync(p_wn_.p, mc->warm_start_normal_impulse, P * sizeof(S), cudaMemcpyHostToDevice, stream_));
+        d.p_ws_normal = p_wn_.as<S>();
+        AVN_CUDA(p_wt_.ensure(2 * P * sizeof(S) + 16));
+        AVN_CUDA(cudaMemcpyAsync(p_wt_.p, mc->warm_start_tangent_impulse, 2 * P * sizeof(S), cudaMemcpyHostToDevice, stream_));
+        d.p_ws_tangent = p_wt_.as<S>();
+        h2d_bytes_ += 3 * P * sizeof(S);
+        AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
+        d.p_normal_impulse = p_ni_.as<S>();
+        AVN_CUDA(c_planes_.ensure(size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>)));
+        d.cst = c_planes_.as<Vec4<S>>();
+        hm_ = *mc;
+        host_any_restitution_ = false;
+        {
+            const S* r = static_cast<const S*>(mc->restitution);
+            for (size_t i = 0; i < M; ++i) host_any_restitution_ |= (r[i] != S(0));
+        }
+    }
+    // ---- joints
+    have_j_ = false;
+    if (js) {
+        size_t J = 0;
+        for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) J += js->types[t].count;
+        if (J > 0) {
+            if ((st = build_joint_schedule(*bc, *js)) != AVN_OK) return st;
+            have_j_ = true;
+            for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) {
+                const AvnJointColumns& jc = js->types[t];
+                const size_t n = jc.count;
+                const void* cols[12] = {jc.local_anchor1, jc.local_anchor2, jc.local_basis1, jc.local_basis2, jc.axis, jc.limit_min,
+                                        jc.limit_max, jc.limit2_min, jc.limit2_max, jc.compliance0, jc.compliance1, jc.compliance2};
+                const size_t width[12] = {3, 3, 4, 4, 3, 1, 1, 1, 1, 1, 1, 1};
+                for (int c = 0; c < 12; ++c) UP(jcol_[t][c], cols[c], width[c] * n, S, jc[t][c]);
+                UP(jb1_[t], jc.body1, n, int, jbody1[t]);
+                UP(jb2_[t], jc.body2, n, int, jbody2[t]);
+                UP(jle_[t], jc.limit_enabled, n, uint8_t, jlimit_en[t]);
+                UP(jde_[t], jc.damping_enabled, n, uint8_t, jdamp_en[t]);
+                UP(jdl_[t], jc.damping_linear, n, S, jdamp_lin[t]);
+                UP(jda_[t], jc.damping_angular, n, S, jdamp_ang[t]);
+                d.jforce[t] = nullptr;
+                d.jtorque[t] = nullptr;
+                if (n && jc.force) { AVN_CUDA(jfo_[t].ensure(3 * n * sizeof(S))); d.jforce[t] = jfo_[t].as<S>(); }
+                if (n && jc.torque) { AVN_CUDA(jto_[t].ensure(3 * n * sizeof(S))); d.jtorque[t] = jto_[t].as<S>(); }
+            }
+            UP(j_type_, h_type_.data(), h_type_.size(), int, j_src_type);
+            UP(j_index_, h_index_.data(), h_index_.size(), int, j_src_index);
+            UP(j_level_, h_level_off_.data(), h_level_off_.size(), int, level_off);
+            AVN_CUDA(j_planes_.ensure(size_t(JP_PLANES) * d.Jpad * sizeof(Vec4<S>)));
+            d.jnt = j_planes_.as<Vec4<S>>();
+            hj_ = *js;
+        }
+    }
+#undef UP
+    cudaEventRecord(ev_[EV_H2D1], stream_);
+    uploaded_ = true;
+    tm_ = AvnTimings{};
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::run() {
+    if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run before avn_solver_upload");
+    launches_ = 0;
+    cudaEventRecord(ev_[EV_RUN0], stream_);
+    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, sizeof(int), stream_));
+    const DevSolver<S>& d = dev_;
+    bool mega = use_mega_ && coop_ok_;
+    if (mega) {
+        void* args[] = {(void*)&dev_};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_megakernel<S>, dim3(mega_grid_), dim3(MEGA_BLOCK), args, 0, stream_);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            mega = false;  // fall through to phase launches (still the same CUDA arithmetic)
+        } else {
+            ++launches_;
+            cudaEventRecord(ev_[EV_PREP], stream_);
+            cudaEventRecord(ev_[EV_LOOP], stream_);
+        }
+    }
+    if (!mega) {
+        launch_phase<OP_PREPARE_BODY>(0, d.B + 1);
+        launch_phase<OP_PREPARE_CONSTRAINT>(0, d.M);
+        launch_phase<OP_PREPARE_JOINT>(0, d.J);
+        cudaEventRecord(ev_[EV_PREP], stream_);
+        for (int sub = 0; sub < d.substeps; ++sub) {
+            launch_phase<OP_INTEGRATE_VEL>(0, d.B);
+            if (d.M > 0) {
+                launch_contact_pass<OP_WARM>();
+                for (int it = 0; it < d.iters; ++it) launch_contact_pass<OP_SOLVE_BIAS>();
+            }
+            launch_phase<OP_INTEGRATE_POS>(0, d.B);
+            if (d.M > 0) launch_contact_pass<OP_RELAX>();
+            if (d.J > 0) {
+                for (int l = 0; l < d.n_levels; ++l) launch_phase<OP_SOLVE_JOINT>(h_level_off_[l], h_level_off_[l + 1] - h_level_off_[l]);
+                launch_phase<OP_PROJECT_VEL>(0, d.B);
+                if (d.any_joint_damping)
+                    for (int l = 0; l < d.n_levels; ++l) launch_phase<OP_DAMP_JOINT>(h_level_off_[l], h_level_off_[l + 1] - h_level_off_[l]);
+            }
+        }
+        cudaEventRecord(ev_[EV_LOOP], stream_);
+        // restitution kernels early-out per manifold when e == 0; skipping the launches needs the device flag, which
+        // would cost a sync, so in phase mode they are launched only when the host saw a non-zero coefficient
+        if (d.M > 0 && host_any_restitution_) launch_contact_pass<OP_RESTITUTION>();
+        launch_phase<OP_WRITEBACK_BODY>(0, d.B);
+        launch_phase<OP_STORE_IMPULSE>(0, d.M);
+        launch_phase<OP_JOINT_FORCE>(0, d.J);
+    }
+    cudaEventRecord(ev_[EV_RUN1], stream_);
+    AVN_CUDA(cudaGetLastError());
+    ran_ = true;
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::download() {
+    if (!ran_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_download before avn_solver_run");
+    const size_t B = hb_.count;
+    cudaEventRecord(ev_[EV_D2H0], stream_);
+    if (B) {
+        AVN_CUDA(cudaMemcpyAsync(hb_.position, dev_.out_position, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hb_.rotation, dev_.out_rotation, 4 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hb_.linear_velocity, dev_.out_linvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hb_.angular_velocity, dev_.out_angvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+    }
+    if (have_m_) {
+        const size_t P = hm_.point_count;
+        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_normal_impulse, dev_.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_tangent_impulse, dev_.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.normal_impulse, dev_.p_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+    }
+    if (have_j_) {
+        for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) {
+            const size_t n = hj_.types[t].count;
+            if (n && dev_.jforce[t]) AVN_CUDA(cudaMemcpyAsync(hj_.types[t].force, dev_.jforce[t], 3 * n * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+            if (n && dev_.jtorque[t]) AVN_CUDA(cudaMemcpyAsync(hj_.types[t].torque, dev_.jtorque[t], 3 * n * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        }
+    }
+    cudaEventRecord(ev_[EV_D2H1], stream_);
+    AVN_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_[EV_H2D0], ev_[EV_H2D1]) == cudaSuccess) tm_.h2d_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev_[EV_RUN0], ev_[EV_PREP]) == cudaSuccess) tm_.prepare_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev_[EV_PREP], ev_[EV_LOOP]) == cudaSuccess) tm_.substep_loop_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev_[EV_LOOP], ev_[EV_RUN1]) == cudaSuccess) tm_.finalize_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev_[EV_D2H0], ev_[EV_D2H1]) == cudaSuccess) tm_.d2h_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev_[EV_RUN0], ev_[EV_RUN1]) == cudaSuccess) tm_.total_ms = ms;
+    tm_.kernel_launches = launches_;
+    tm_.contact_constraint_count = uint32_t(dev_.M);
+    tm_.joint_levels = uint32_t(dev_.n_levels);
+    uint32_t ac = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) ac += dev_.color_off[c + 1] > dev_.color_off[c];
+    tm_.active_colors = ac;
+    return AVN_OK;
+}
+
+}  // namespace
+
+SolverBase* make_solver(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device) {
+    if (scalar_bits == 32) return new Solver<float>(stream, err, cfg_flags, device);
+    if (scalar_bits == 64) return new Solver<double>(stream, err, cfg_flags, device);
+    return nullptr;
+}
+
+}  // namespace avn

@@ -1,0 +1,591 @@
+// libavian_host.so — the host-side FIXTURE that stands in for the parts of an avian3d app that stay on the CPU
+// around the GPU hot path, so the hot path can be exercised and benchmarked without Bevy:
+//   * swept collider AABBs        (restates update_aabb for cuboids/spheres, collider/backend.rs:498-625)
+//   * ContactGraph bookkeeping    (pair set, lowest-free ContactId, contact_graph.rs:521-631; id_pool.rs:43-52)
+//   * a narrow phase for cuboid / sphere pairs (SAT + face clipping; the reference delegates this arithmetic
+//     to parry3d 0.25, which is not vendored, so this is OUR manifold generator: a fixture, identical for the
+//     oracle and the GPU path, not a parity claim), contact matching (contact_types/mod.rs:426-470),
+//     the status-change loop and ConstraintGraph push/pop colouring (narrow_phase/system_param.rs:136-389,
+//     constraint_graph.rs:163-296)
+//   * export of the manifolds as per-colour columns in the layout of AvnManifoldColumns.
+// It contains no solver or broad-phase code: those are the GPU library (product) or oracle/ (tests).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/avian_b200.h"
+
+namespace {
+
+using S = double;  // fixture geometry is evaluated in double and rounded to the column scalar type on export
+
+struct V3 { S x, y, z; };
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, S s) { return {a.x * s, a.y * s, a.z * s}; }
+inline S dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline S len(V3 a) { return std::sqrt(dot(a, a)); }
+inline S comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+struct Q { S x, y, z, w; };
+inline V3 rot(Q q, V3 v) {
+    V3 b{q.x, q.y, q.z};
+    S b2 = dot(b, b);
+    return v * (q.w * q.w - b2) + b * (dot(v, b) * 2) + cross(b, v) * (q.w * 2);
+}
+inline Q qmul(Q a, Q b) {
+    return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+            a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+inline Q q_from_scaled_axis(V3 v) {
+    S l = len(v);
+    if (l == 0) return {0, 0, 0, 1};
+    S s = std::sin(l * 0.5) / l;
+    return {v.x * s, v.y * s, v.z * s, std::cos(l * 0.5)};
+}
+struct M3 { V3 c[3]; };  // columns = world directions of the local axes
+inline M3 to_mat(Q q) { return {{rot(q, {1, 0, 0}), rot(q, {0, 1, 0}), rot(q, {0, 0, 1})}}; }
+
+template <class T> struct ColR {  // typed reader over a void* column of float or double
+    const void* p; bool f64;
+    S at(size_t i) const { return f64 ? static_cast<const double*>(p)[i] : S(static_cast<const float*>(p)[i]); }
+    V3 v3(size_t i) const { return {at(3 * i), at(3 * i + 1), at(3 * i + 2)}; }
+    Q q(size_t i) const { return {at(4 * i), at(4 * i + 1), at(4 * i + 2), at(4 * i + 3)}; }
+};
+using Col = ColR<void>;
+struct ColW {
+    void* p; bool f64;
+    void set(size_t i, S v) const { if (f64) static_cast<double*>(p)[i] = v; else static_cast<float*>(p)[i] = float(v); }
+    void set3(size_t i, V3 v) const { set(3 * i, v.x); set(3 * i + 1, v.y); set(3 * i + 2, v.z); }
+};
+
+enum ShapeType { SHAPE_CUBOID = 0, SHAPE_SPHERE = 1 };
+struct Shape { int type; V3 he; S friction, restitution; };
+
+struct Point {
+    V3 anchor1, anchor2;  // world-space offsets from each body's centre of mass
+    S penetration, normal_speed;
+    S ws_normal = 0, ws_tx = 0, ws_ty = 0, normal_impulse = 0;
+};
+struct Manifold { V3 normal; std::vector<Point> pts; };
+struct Handle { int color; uint32_t local; };
+
+struct Pair {
+    uint32_t collider1, collider2, body1, body2;
+    uint8_t flags;                 // AVN_PAIR_*
+    bool alive = false, touching = false, static1 = false, static2 = false;
+    std::vector<Manifold> manifolds;
+    std::vector<Handle> handles;   // ContactEdge::constraint_handles
+};
+
+// ConstraintGraph (constraint_graph.rs:39-296)
+struct Color {
+    std::vector<uint8_t> body_set;
+    std::vector<std::pair<uint32_t, uint32_t>> handles;  // (contact id, manifold index)
+    bool get(uint32_t i) const { return i < body_set.size() && body_set[i]; }
+    void set(uint32_t i) { if (i >= body_set.size()) body_set.resize(size_t(i) + 1, 0); body_set[i] = 1; }
+    void unset(uint32_t i) { if (i < body_set.size()) body_set[i] = 0; }
+};
+
+struct Pipeline {
+    uint32_t n = 0;
+    std::vector<Shape> shapes;
+    std::vector<uint32_t> order;          // AabbIntervals persistent order (positions -> collider index)
+    std::vector<Pair> pairs;              // indexed by ContactId (stable graph edges)
+    std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_ids;  // IdPool: lowest free id
+    std::unordered_map<uint64_t, uint32_t> pair_set;  // PairKey -> ContactId
+    std::vector<uint32_t> active;         // ContactGraph::active_pairs order
+    Color colors[AVN_GRAPH_COLOR_COUNT];
+    S contact_tolerance = 0.005, length_unit = 1.0;
+    // export bookkeeping: the (contact id, manifold, point) of every exported point, in column order
+    struct Ref { uint32_t id, mi, pi; };
+    std::vector<Ref> export_refs;
+};
+
+inline uint64_t pair_key(uint32_t a, uint32_t b) { return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a; }
+
+// ---- ConstraintGraph::push_manifold / pop_manifold -----------------------------------------------------------
+void push_manifold(Pipeline& P, uint32_t id) {
+    Pair& pr = P.pairs[id];
+    int color = AVN_COLOR_OVERFLOW;
+    if (!pr.static1 && !pr.static2) {
+        for (int i = 0; i < AVN_DYNAMIC_COLOR_COUNT; ++i) {
+            Color& c = P.colors[i];
+            if (c.get(pr.body1) || c.get(pr.body2)) continue;
+            c.set(pr.body1); c.set(pr.body2); color = i; break;
+        }
+    } else if (!pr.static1) {
+        for (int i = AVN_COLOR_OVERFLOW - 1; i >= 1; --i) {
+            Color& c = P.colors[i];
+            if (c.get(pr.body1)) continue;
+            c.set(pr.body1); color = i; break;
+        }
+    } else if (!pr.static2) {
+        for (int i = AVN_COLOR_OVERFLOW - 1; i >= 1; --i) {
+            Color& c = P.colors[i];
+            if (c.get(pr.body2)) continue;
+            c.set(pr.body2); color = i; break;
+        }
+    }
+    Color& c = P.colors[color];
+    uint32_t manifold_index = uint32_t(pr.handles.size());
+    pr.handles.push_back({color, uint32_t(c.handles.size())});
+    c.handles.push_back({id, manifold_index});
+}
+void pop_manifold(Pipeline& P, uint32_t id) {
+    Pair& pr = P.pairs[id];
+    if (pr.handles.empty()) return;
+    Handle h = pr.handles.back();
+    pr.handles.pop_back();
+    Color& c = P.colors[h.color];
+    if (h.color != AVN_COLOR_OVERFLOW) { c.unset(pr.body1); c.unset(pr.body2); }
+    uint32_t moved = uint32_t(c.handles.size()) - 1;
+    c.handles[h.local] = c.handles[moved];
+    c.handles.pop_back();
+    if (moved != h.local) {
+        auto mh = c.handles[h.local];
+        P.pairs[mh.first].handles[mh.second].local = h.local;
+    }
+}
+
+// ---- manifold generation (fixture) -----------------------------------------------------------------------------
+struct Box { V3 c; M3 r; V3 he; };
+
+// support face of `b` most aligned with direction d: returns 4 corners (world) and the face normal
+void box_face(const Box& b, int axis, S sign, V3 out[4]) {
+    int u = (axis + 1) % 3, v = (axis + 2) % 3;
+    V3 n = b.r.c[axis] * (sign * comp(b.he, axis));
+    V3 eu = b.r.c[u] * comp(b.he, u), ev = b.r.c[v] * comp(b.he, v);
+    V3 fc = b.c + n;
+    out[0] = fc + eu + ev; out[1] = fc - eu + ev; out[2] = fc - eu - ev; out[3] = fc + eu - ev;
+}
+
+int clip_poly(const V3* in, int n, V3 plane_n, S plane_d, V3* out) {  // keep dot(n,p) <= d
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        V3 a = in[i], b = in[(i + 1) % n];
+        S da = dot(plane_n, a) - plane_d, db = dot(plane_n, b) - plane_d;
+        if (da <= 0) out[m++] = a;
+        if ((da < 0 && db > 0) || (da > 0 && db < 0)) out[m++] = a + (b - a) * (da / (da - db));
+    }
+    return m;
+}
+
+// returns false when the boxes are farther apart than max_dist. normal points from A to B.
+bool box_box(const Box& A, const Box& B, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts /* (on A, on B) */) {
+    pts.clear();
+    V3 d = B.c - A.c;
+    S best_sep = -1e300;
+    int best_kind = -1, best_i = 0, best_j = 0;
+    V3 best_n{0, 1, 0};
+    auto radius = [](const Box& b, V3 n) {
+        return std::fabs(dot(b.r.c[0], n)) * b.he.x + std::fabs(dot(b.r.c[1], n)) * b.he.y + std::fabs(dot(b.r.c[2], n)) * b.he.z;
+    };
+    auto consider = [&](V3 n, int kind, int i, int j, S bias) {
+        S l = len(n);
+        if (l < 1e-9) return;
+        n = n * (1 / l);
+        if (dot(n, d) < 0) n = -n;
+        S sep = dot(n, d) - radius(A, n) - radius(B, n);
+        // face axes are preferred over edge axes by a small bias, earlier axes win ties: stable feature choice
+        if (sep - bias > best_sep + 1e-9) { best_sep = sep - bias; best_kind = kind; best_i = i; best_j = j; best_n = n; }
+    };
+    for (int i = 0; i < 3; ++i) consider(A.r.c[i], 0, i, 0, 0);
+    for (int i = 0; i < 3; ++i) consider(B.r.c[i], 1, i, 0, 0);
+    S face_sep = best_sep;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) consider(cross(A.r.c[i], B.r.c[j]), 2, i, j, 1e-4);
+    (void)face_sep;
+    S sep = best_kind == 2 ? best_sep + 1e-4 : best_sep;
+    if (sep > max_dist) return false;
+    normal = best_n;
+    if (best_kind == 2) {
+        // edge-edge: closest points of the two supporting edges
+        V3 ea = A.r.c[best_i], eb = B.r.c[best_j];
+        V3 pa = A.c, pb = B.c;
+        for (int k = 0; k < 3; ++k) {
+            if (k != best_i) pa = pa + A.r.c[k] * (comp(A.he, k) * (dot(A.r.c[k], normal) > 0 ? 1 : -1));
+            if (k != best_j) pb = pb + B.r.c[k] * (comp(B.he, k) * (dot(B.r.c[k], normal) < 0 ? 1 : -1));
+        }
+        V3 r = pa - pb;
+        S a = dot(ea, ea), e = dot(eb, eb), f = dot(eb, r), c = dot(ea, r), b = dot(ea, eb);
+        S den = a * e - b * b;
+        S s = den > 1e-12 ? (b * f - c * e) / den : 0;
+        S t = (b * s + f) / e;
+        S ha = comp(A.he, best_i), hb = comp(B.he, best_j);
+        s = std::max(-ha, std::min(ha, s));
+        t = std::max(-hb, std::min(hb, t));
+        pts.push_back({pa + ea * s, pb + eb * t});
+        return true;
+    }
+    // face contact: reference box R (face axis), incident box I
+    const bool ref_is_a = best_kind == 0;
+    const Box& R = ref_is_a ? A : B;
+    const Box& I = ref_is_a ? B : A;
+    V3 rn = ref_is_a ? normal : -normal;  // outward normal of the reference face
+    S rsign = dot(R.r.c[best_i], rn) > 0 ? 1 : -1;
+    // incident face: the face of I most anti-parallel to rn
+    int inc_axis = 0;
+    S inc_best = -1;
+    for (int k = 0; k < 3; ++k) {
+        S v = std::fabs(dot(I.r.c[k], rn));
+        if (v > inc_best) { inc_best = v; inc_axis = k; }
+    }
+    S isign = dot(I.r.c[inc_axis], rn) > 0 ? -1 : 1;
+    V3 poly[16], tmp[16];
+    box_face(I, inc_axis, isign, poly);
+    int np = 4;
+    int u = (best_i + 1) % 3, v = (best_i + 2) % 3;
+    const int axes[2] = {u, v};
+    for (int a = 0; a < 2 && np > 0; ++a) {
+        V3 sn = R.r.c[axes[a]];
+        S he = comp(R.he, axes[a]);
+        np = clip_poly(poly, np, sn, dot(sn, R.c) + he, tmp);
+        np = clip_poly(tmp, np, -sn, -dot(sn, R.c) + he, poly);
+    }
+    S face_d = dot(rn, R.c) + comp(R.he, best_i) * 1.0;
+    (void)rsign;
+    for (int k = 0; k < np; ++k) {
+        S dist = dot(rn, poly[k]) - face_d;  // signed distance of the incident point above the reference face
+        if (dist > max_dist) continue;
+        V3 on_ref = poly[k] - rn * dist;
+        // drop near-duplicates
+        bool dup = false;
+        for (auto& q : pts) {
+            V3 e = (ref_is_a ? q.second : q.first) - poly[k];
+            if (dot(e, e) < 1e-12) { dup = true; break; }
+        }
+        if (dup) continue;
+        if (ref_is_a) pts.push_back({on_ref, poly[k]}); else pts.push_back({poly[k], on_ref});
+    }
+    return !pts.empty();
+}
+
+// keep at most 4 points: deepest, farthest from it, farthest from that segment on each side (cf. prune_points,
+// contact_types/mod.rs:478-566, itself after Jolt's PruneContactPoints)
+void prune4(std::vector<std::pair<V3, V3>>& pts, V3 n) {
+    if (pts.size() <= 4) return;
+    auto depth = [&](size_t i) { return dot(pts[i].first - pts[i].second, n); };
+    size_t p0 = 0;
+    for (size_t i = 1; i < pts.size(); ++i) if (depth(i) > depth(p0) + 1e-12) p0 = i;
+    size_t p1 = p0;
+    S best = -1;
+    for (size_t i = 0; i < pts.size(); ++i) { V3 e = pts[i].first - pts[p0].first; S v = dot(e, e); if (v > best) { best = v; p1 = i; } }
+    V3 dir = cross(pts[p1].first - pts[p0].first, n);
+    size_t p2 = p0, p3 = p0;
+    S mx = 0, mn = 0;
+    for (size_t i = 0; i < pts.size(); ++i) {
+        S v = dot(pts[i].first - pts[p0].first, dir);
+        if (v > mx) { mx = v; p2 = i; }
+        if (v < mn) { mn = v; p3 = i; }
+    }
+    std::vector<size_t> keep{p0};
+    for (size_t c : {p1, p2, p3}) if (std::find(keep.begin(), keep.end(), c) == keep.end()) keep.push_back(c);
+    std::sort(keep.begin(), keep.end());
+    std::vector<std::pair<V3, V3>> out;
+    for (size_t k : keep) out.push_back(pts[k]);
+    pts.swap(out);
+}
+
+bool sphere_sphere(V3 ca, S ra, V3 cb, S rb, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts) {
+    pts.clear();
+    V3 d = cb - ca;
+    S l = len(d);
+    if (l - ra - rb > max_dist) return false;
+    normal = l > 1e-12 ? d * (1 / l) : V3{0, 1, 0};
+    pts.push_back({ca + normal * ra, cb - normal * rb});
+    return true;
+}
+bool box_sphere(const Box& A, V3 cs, S rs, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts) {  // normal from box to sphere
+    pts.clear();
+    V3 d = cs - A.c;
+    V3 local{dot(d, A.r.c[0]), dot(d, A.r.c[1]), dot(d, A.r.c[2])};
+    V3 cl{std::max(-A.he.x, std::min(A.he.x, local.x)), std::max(-A.he.y, std::min(A.he.y, local.y)), std::max(-A.he.z, std::min(A.he.z, local.z))};
+    V3 on_box = A.c + A.r.c[0] * cl.x + A.r.c[1] * cl.y + A.r.c[2] * cl.z;
+    V3 e = cs - on_box;
+    S l = len(e);
+    if (l > 1e-9) {
+        if (l - rs > max_dist) return false;
+        normal = e * (1 / l);
+    } else {  // centre inside the box: push out through the nearest face
+        int ax = 0; S best = 1e300;
+        for (int k = 0; k < 3; ++k) { S v = comp(A.he, k) - std::fabs(comp(local, k)); if (v < best) { best = v; ax = k; } }
+        S sgn = comp(local, ax) >= 0 ? 1 : -1;
+        normal = A.r.c[ax] * sgn;
+        on_box = cs + normal * best;
+    }
+    pts.push_back({on_box, cs - normal * rs});
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+struct AvhPipeline;  // opaque = Pipeline
+
+AvhPipeline* avh_create(uint32_t n_bodies) {
+    Pipeline* p = new Pipeline();
+    p->n = n_bodies;
+    p->shapes.assign(n_bodies, Shape{SHAPE_CUBOID, {0.5, 0.5, 0.5}, 0.5, 0.0});
+    return reinterpret_cast<AvhPipeline*>(p);
+}
+void avh_destroy(AvhPipeline* h) { delete reinterpret_cast<Pipeline*>(h); }
+
+// shape_type[n], dims[n][3] (half extents, or radius in [0]), friction[n], restitution[n] — doubles
+void avh_set_shapes(AvhPipeline* h, const int32_t* shape_type, const double* dims, const double* friction, const double* restitution) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    for (uint32_t i = 0; i < P.n; ++i)
+        P.shapes[i] = Shape{shape_type[i], {dims[3 * i], dims[3 * i + 1], dims[3 * i + 2]}, friction[i], restitution[i]};
+}
+
+// update_aabb (collider/backend.rs:498-625) for the default configuration: speculative margin = MAX, no collision
+// margin, collider at the body origin.  AABB = merge(aabb(start pose), aabb(end pose)) grown by contact_tolerance.
+void avh_update_aabbs(AvhPipeline* h, uint32_t scalar_bits, const void* position, const void* rotation, const void* linvel, const void* angvel,
+                      double dt, void* out_min, void* out_max) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    const bool f64 = scalar_bits == 64;
+    Col pos{position, f64}, rt{rotation, f64}, lv{linvel, f64}, av{angvel, f64};
+    ColW omin{out_min, f64}, omax{out_max, f64};
+    const S tol = P.contact_tolerance * P.length_unit;
+    for (uint32_t i = 0; i < P.n; ++i) {
+        const Shape& sh = P.shapes[i];
+        V3 p0 = pos.v3(i), v = lv.v3(i), w = av.v3(i);
+        Q q0 = rt.q(i);
+        Q q1 = qmul(q_from_scaled_axis(w * dt), q0);
+        S l2 = q1.x * q1.x + q1.y * q1.y + q1.z * q1.z + q1.w * q1.w, k = 0.5 * (3 - l2);
+        q1 = {q1.x * k, q1.y * k, q1.z * k, q1.w * k};
+        V3 p1 = p0 + v * dt;
+        V3 lo{1e300, 1e300, 1e300}, hi{-1e300, -1e300, -1e300};
+        for (int e = 0; e < 2; ++e) {
+            V3 c = e ? p1 : p0;
+            V3 ext;
+            if (sh.type == SHAPE_SPHERE) {
+                ext = {sh.he.x, sh.he.x, sh.he.x};
+            } else {
+                M3 m = to_mat(e ? q1 : q0);
+                ext = {std::fabs(m.c[0].x) * sh.he.x + std::fabs(m.c[1].x) * sh.he.y + std::fabs(m.c[2].x) * sh.he.z,
+                       std::fabs(m.c[0].y) * sh.he.x + std::fabs(m.c[1].y) * sh.he.y + std::fabs(m.c[2].y) * sh.he.z,
+                       std::fabs(m.c[0].z) * sh.he.x + std::fabs(m.c[1].z) * sh.he.y + std::fabs(m.c[2].z) * sh.he.z};
+            }
+            lo = {std::min(lo.x, c.x - ext.x), std::min(lo.y, c.y - ext.y), std::min(lo.z, c.z - ext.z)};
+            hi = {std::max(hi.x, c.x + ext.x), std::max(hi.y, c.y + ext.y), std::max(hi.z, c.z + ext.z)};
+        }
+        omin.set3(i, {lo.x - tol, lo.y - tol, lo.z - tol});
+        omax.set3(i, {hi.x + tol, hi.y + tol, hi.z + tol});
+    }
+}
+
+// AabbIntervals persistent order (broad_phase.rs:296-315).  order[] holds collider indices.
+uint32_t avh_get_order(AvhPipeline* h, uint32_t* out) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    if (P.order.size() != P.n) {  // first use: add_new_aabb_intervals appends in spawn order
+        P.order.resize(P.n);
+        for (uint32_t i = 0; i < P.n; ++i) P.order[i] = i;
+    }
+    if (out) std::memcpy(out, P.order.data(), sizeof(uint32_t) * P.n);
+    return P.n;
+}
+void avh_set_order(AvhPipeline* h, const uint32_t* order) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    P.order.assign(order, order + P.n);
+}
+
+uint64_t avh_existing_pairs(AvhPipeline* h, uint64_t* out, uint64_t capacity) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    uint64_t k = 0;
+    for (uint32_t id : P.active) {
+        if (out && k < capacity) out[k] = pair_key(P.pairs[id].collider1, P.pairs[id].collider2);
+        ++k;
+    }
+    return k;
+}
+
+// ContactGraph::add_edge_and_key_with for each emitted pair, in list order (broad_phase.rs:443-471)
+void avh_add_pairs(AvhPipeline* h, const uint32_t* c1, const uint32_t* c2, const uint32_t* b1, const uint32_t* b2, const uint8_t* flags, uint64_t count) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    for (uint64_t k = 0; k < count; ++k) {
+        uint64_t key = pair_key(c1[k], c2[k]);
+        if (P.pair_set.count(key)) continue;
+        uint32_t id;
+        if (!P.free_ids.empty()) { id = P.free_ids.top(); P.free_ids.pop(); }
+        else { id = uint32_t(P.pairs.size()); P.pairs.emplace_back(); }
+        Pair& pr = P.pairs[id];
+        pr = Pair{};
+        pr.collider1 = c1[k]; pr.collider2 = c2[k]; pr.body1 = b1[k]; pr.body2 = b2[k]; pr.flags = flags[k]; pr.alive = true;
+        P.pair_set[key] = id;
+        P.active.push_back(id);
+    }
+}
+
+// NarrowPhase::update (narrow_phase/system_param.rs:114-400) with the fixture manifold generator.
+// kind[n] = AvnBodyKind.  Returns the number of exported manifolds; *out_points = number of points.
+uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* kind, const void* position, const void* rotation, const void* linvel,
+                          const void* angvel, const void* aabb_min, const void* aabb_max, double dt, uint32_t match_contacts, uint32_t* out_points) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    const bool f64 = scalar_bits == 64;
+    Col pos{position, f64}, rt{rotation, f64}, lv{linvel, f64}, av{angvel, f64}, amin{aabb_min, f64}, amax{aabb_max, f64};
+    const S tol = P.contact_tolerance * P.length_unit;
+    std::vector<uint32_t> changed;  // contact ids whose status changed
+    std::vector<uint8_t> disjoint(P.pairs.size(), 0), started(P.pairs.size(), 0), stopped(P.pairs.size(), 0);
+    std::vector<int> count_change(P.pairs.size(), 0);
+    std::vector<std::pair<V3, V3>> pts;
+    for (uint32_t id : P.active) {
+        Pair& pr = P.pairs[id];
+        const uint32_t a = pr.collider1, b = pr.collider2;
+        V3 mina = amin.v3(a), maxa = amax.v3(a), minb = amin.v3(b), maxb = amax.v3(b);
+        bool overlap = !(mina.x > maxb.x || maxa.x < minb.x || mina.y > maxb.y || maxa.y < minb.y || mina.z > maxb.z || maxa.z < minb.z);
+        if (!overlap) { disjoint[id] = 1; changed.push_back(id); continue; }
+        pr.static1 = kind[pr.body1] == AVN_BODY_STATIC;
+        pr.static2 = kind[pr.body2] == AVN_BODY_STATIC;
+        const Shape& sa = P.shapes[a];
+        const Shape& sb = P.shapes[b];
+        V3 v1 = lv.v3(pr.body1), v2 = lv.v3(pr.body2), w1 = av.v3(pr.body1), w2 = av.v3(pr.body2);
+        V3 rel = v2 - v1;
+        S eff_margin = dt * len(rel);  // effective speculative margin (system_param.rs:663-681) with margin = MAX
+        S max_dist = std::max(eff_margin, tol);
+        std::vector<Manifold> old = std::move(pr.manifolds);
+        pr.manifolds.clear();
+        V3 normal;
+        bool hit = false;
+        V3 pa = pos.v3(a), pb = pos.v3(b);
+        if (sa.type == SHAPE_CUBOID && sb.type == SHAPE_CUBOID) {
+            Box A{pa, to_mat(rt.q(a)), sa.he}, B{pb, to_mat(rt.q(b)), sb.he};
+            hit = box_box(A, B, max_dist, normal, pts);
+            if (hit) prune4(pts, normal);
+        } else if (sa.type == SHAPE_SPHERE && sb.type == SHAPE_SPHERE) {
+            hit = sphere_sphere(pa, sa.he.x, pb, sb.he.x, max_dist, normal, pts);
+        } else if (sa.type == SHAPE_CUBOID) {
+            Box A{pa, to_mat(rt.q(a)), sa.he};
+            hit = box_sphere(A, pb, sb.he.x, max_dist, normal, pts);
+        } else {
+            Box B{pb, to_mat(rt.q(b)), sb.he};
+            hit = box_sphere(B, pa, sa.he.x, max_dist, normal, pts);
+            if (hit) { normal = -normal; for (auto& q : pts) std::swap(q.first, q.second); }
+        }
+        if (hit) {
+            Manifold m;
+            m.normal = normal;
+            for (auto& q : pts) {
+                Point pt;
+                pt.anchor1 = q.first - pa;   // collider at the body origin, centre of mass at the origin
+                pt.anchor2 = q.second - pb;
+                pt.penetration = dot(q.first - q.second, normal);
+                V3 rv = rel + cross(w2, pt.anchor2) - cross(w1, pt.anchor1);
+                pt.normal_speed = dot(rv, normal);
+                // keep rule of system_param.rs:748-756
+                bool keep = -pt.penetration < eff_margin || (pt.normal_speed * dt - pt.penetration < eff_margin);
+                if (!keep) continue;
+                m.pts.push_back(pt);
+            }
+            if (!m.pts.empty()) pr.manifolds.push_back(std::move(m));
+        }
+        bool touching = !pr.manifolds.empty();
+        if (touching && match_contacts && pr.manifolds.size() <= 4) {
+            // ContactManifold::match_contacts with unknown feature ids (contact_types/mod.rs:426-470)
+            const S thr2 = (0.1 * P.length_unit) * (0.1 * P.length_unit);
+            auto d2 = [](V3 x, V3 y) { V3 e = x - y; return dot(e, e); };
+            for (Manifold& m : pr.manifolds)
+                for (const Manifold& om : old)
+                    for (Point& c : m.pts)
+                        for (const Point& pc : om.pts) {
+                            if ((d2(c.anchor1, pc.anchor1) < thr2 && d2(c.anchor2, pc.anchor2) < thr2) ||
+                                (d2(c.anchor1, pc.anchor2) < thr2 && d2(c.anchor2, pc.anchor1) < thr2)) {
+                                c.ws_normal = pc.ws_normal; c.ws_tx = pc.ws_tx; c.ws_ty = pc.ws_ty;
+                                break;
+                            }
+                        }
+        }
+        count_change[id] = int(pr.manifolds.size()) - int(old.size());
+        if (touching && !pr.touching) { started[id] = 1; changed.push_back(id); }
+        else if (!touching && pr.touching) { stopped[id] = 1; changed.push_back(id); }
+        else if (count_change[id] != 0) changed.push_back(id);
+    }
+    // status changes in ascending ContactId (system_param.rs:136-389)
+    std::sort(changed.begin(), changed.end());
+    for (uint32_t id : changed) {
+        Pair& pr = P.pairs[id];
+        const bool gen = pr.flags & AVN_PAIR_GENERATE_CONSTRAINTS;
+        if (disjoint[id]) {
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+            P.pair_set.erase(pair_key(pr.collider1, pr.collider2));
+            auto it = std::find(P.active.begin(), P.active.end(), id);  // remove_edge_by_id: swap_remove (contact_graph.rs:615-628)
+            if (it != P.active.end()) { *it = P.active.back(); P.active.pop_back(); }
+            pr = Pair{};
+            P.free_ids.push(id);
+        } else if (started[id]) {
+            pr.touching = true;
+            if (gen) for (size_t k = 0; k < pr.manifolds.size(); ++k) push_manifold(P, id);
+        } else if (stopped[id]) {
+            pr.touching = false;
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] > 0) {
+            for (int k = 0; k < count_change[id]; ++k) push_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] < 0) {
+            for (int k = 0; k < -count_change[id]; ++k) pop_manifold(P, id);
+        }
+    }
+    uint32_t M = 0, Pn = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
+        for (auto& hnd : P.colors[c].handles) { ++M; Pn += uint32_t(P.pairs[hnd.first].manifolds[hnd.second].pts.size()); }
+    if (out_points) *out_points = Pn;
+    return M;
+}
+
+// Export the manifolds grouped by colour in manifold_handles order (what prepare_contact_constraints walks,
+// solver/plugin.rs:389-434).  Arrays are sized from avh_narrow_phase's return values.
+void avh_export_manifolds(AvhPipeline* h, uint32_t scalar_bits, uint32_t* color_offsets /*[25]*/, int32_t* body1, int32_t* body2, void* normal,
+                          void* friction, void* restitution, uint32_t* point_offsets, void* anchor1, void* anchor2, void* penetration,
+                          void* normal_speed, void* ws_normal, void* ws_tangent) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    const bool f64 = scalar_bits == 64;
+    ColW wn{normal, f64}, wf{friction, f64}, wr{restitution, f64}, wa1{anchor1, f64}, wa2{anchor2, f64}, wp{penetration, f64}, ws{normal_speed, f64},
+        wwn{ws_normal, f64}, wwt{ws_tangent, f64};
+    P.export_refs.clear();
+    uint32_t m = 0, p = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) {
+        color_offsets[c] = m;
+        for (auto& hnd : P.colors[c].handles) {
+            const Pair& pr = P.pairs[hnd.first];
+            const Manifold& mf = pr.manifolds[hnd.second];
+            body1[m] = int32_t(pr.body1);
+            body2[m] = int32_t(pr.body2);
+            wn.set3(m, mf.normal);
+            wf.set(m, (P.shapes[pr.collider1].friction + P.shapes[pr.collider2].friction) * 0.5);
+            wr.set(m, (P.shapes[pr.collider1].restitution + P.shapes[pr.collider2].restitution) * 0.5);
+            point_offsets[m] = p;
+            for (uint32_t k = 0; k < mf.pts.size(); ++k) {
+                const Point& pt = mf.pts[k];
+                wa1.set3(p, pt.anchor1); wa2.set3(p, pt.anchor2);
+                wp.set(p, pt.penetration); ws.set(p, pt.normal_speed);
+                wwn.set(p, pt.ws_normal); wwt.set(2 * p, pt.ws_tx); wwt.set(2 * p + 1, pt.ws_ty);
+                P.export_refs.push_back({hnd.first, hnd.second, k});
+                ++p;
+            }
+            ++m;
+        }
+    }
+    color_offsets[AVN_GRAPH_COLOR_COUNT] = m;
+    point_offsets[m] = p;
+}
+
+// store_contact_impulses' destination: ContactPoint::{warm_start_*, normal_impulse} (solver/plugin.rs:741-750)
+void avh_store_impulses(AvhPipeline* h, uint32_t scalar_bits, const void* ws_normal, const void* ws_tangent, const void* normal_impulse) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    const bool f64 = scalar_bits == 64;
+    Col n{ws_normal, f64}, t{ws_tangent, f64}, ni{normal_impulse, f64};
+    for (size_t p = 0; p < P.export_refs.size(); ++p) {
+        auto r = P.export_refs[p];
+        Point& pt = P.pairs[r.id].manifolds[r.mi].pts[r.pi];
+        pt.ws_normal = n.at(p); pt.ws_tx = t.at(2 * p); pt.ws_ty = t.at(2 * p + 1); pt.normal_impulse = ni.at(p);
+    }
+}
+
+uint32_t avh_pair_count(AvhPipeline* h) { return uint32_t(reinterpret_cast<Pipeline*>(h)->active.size()); }
+
+}  // extern "C"

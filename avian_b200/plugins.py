@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's plugin interface for the hot path.
+
+In avian3d an app swaps plugins like this (src/lib.rs:718-733, crates/avian3d/examples/custom_broad_phase.rs:10-16):
+
+    PhysicsPlugins::default().build().disable::<BroadPhasePlugin>().add(GpuBroadPhasePlugin)
+
+The Rust shim that does exactly that is in INTEGRATION.md (no Rust toolchain exists in this image).  This module is
+the same structure in Python so the tests and the bench read like the reference's: a `PhysicsPlugins` group holds
+`IntegratorPlugin`, `BroadPhasePlugin` and `SolverPlugin` (which covers `XpbdSolverPlugin`, as in the GPU library one
+call runs the whole substep schedule); `.disable(...)` / `.add(...)` swap implementations; `World.step()` runs the
+PhysicsSchedule order  BroadPhase -> NarrowPhase -> Solver  (src/schedule/mod.rs:96-108).
+
+The GPU plugins call the C ABI (avian_b200.api) and nothing else.  A plugin backed by the CPU oracle exists only in
+tests/ (tests/oracle_lib.py) — the product has no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+from .fixture import HostPipeline
+from .scenes import Scene
+
+
+class Gravity:
+    """integrator/mod.rs:150-166"""
+    def __init__(self, x=0.0, y=-9.81, z=0.0):
+        self.value = (x, y, z)
+
+    ZERO = None
+
+
+Gravity.ZERO = Gravity(0.0, 0.0, 0.0)
+
+
+class SubstepCount(int):
+    """solver/schedule.rs:185-191 (default 6)"""
+    def __new__(cls, value: int = 6):
+        return super().__new__(cls, value)
+
+
+class SolverConfig:
+    """solver/plugin.rs:216-302"""
+    def __init__(self, contact_damping_ratio=10.0, contact_frequency_factor=1.5, max_overlap_solve_speed=4.0, warm_start_coefficient=1.0,
+                 restitution_threshold=1.0, restitution_iterations=1):
+        self.contact_damping_ratio = contact_damping_ratio
+        self.contact_frequency_factor = contact_frequency_factor
+        self.max_overlap_solve_speed = max_overlap_solve_speed
+        self.warm_start_coefficient = warm_start_coefficient
+        self.restitution_threshold = restitution_threshold
+        self.restitution_iterations = restitution_iterations
+
+
+class IntegratorPlugin:
+    """integrator/mod.rs:45-88.  Owns the `Gravity` resource; the integration kernels run inside the solver stage
+    (integrate_velocities / integrate_positions are systems of the SubstepSchedule, solver/schedule.rs:59-69)."""
+    def __init__(self, gravity: Gravity | None = None):
+        self.gravity = gravity or Gravity()
+
+
+class BroadPhasePlugin:
+    """collision/broad_phase.rs:44-155 on the GPU: collect_collision_pairs -> avn_broadphase."""
+    def __init__(self, ctx: api.Context):
+        self.ctx = ctx
+
+    def collect_collision_pairs(self, aabbs: api.Aabbs) -> api.PairList:
+        return self.ctx.broadphase(aabbs)
+
+
+class SolverPlugin:
+    """solver/plugin.rs:88-157 + xpbd/plugin.rs:21-110 + solver_body/plugin.rs on the GPU: one avn_solver_step."""
+    def __init__(self, ctx: api.Context, config: SolverConfig | None = None):
+        self.ctx = ctx
+        self.config = config or SolverConfig()
+
+    def step(self, params: api.AvnStepParams, bodies: api.Bodies, manifolds: api.Manifolds | None, joints: api.JointSet | None) -> None:
+        self.ctx.solver_step(params, bodies, manifolds, joints)
+
+
+class PhysicsPlugins:
+    """The plugin group (src/lib.rs:813-843) restricted to the hot path."""
+    def __init__(self, ctx: api.Context | None = None):
+        self._plugins = {}
+        if ctx is not None:
+            self.add(IntegratorPlugin()).add(BroadPhasePlugin(ctx)).add(SolverPlugin(ctx))
+
+    def build(self):
+        return self
+
+    def disable(self, cls):
+        for k in [k for k, v in self._plugins.items() if isinstance(v, cls) or k == getattr(cls, "__name__", cls)]:
+            del self._plugins[k]
+        return self
+
+    def add(self, plugin, name: str | None = None):
+        self._plugins[name or _slot_of(plugin)] = plugin
+        return self
+
+    def get(self, name):
+        try:
+            return self._plugins[name]
+        except KeyError:
+            raise RuntimeError(f"{name} missing: add it to PhysicsPlugins (cf. `expect(\"add PhysicsSchedule first\")`, solver/plugin.rs:104-106)")
+
+
+def _slot_of(plugin) -> str:
+    for base in type(plugin).__mro__:
+        if base.__name__ in ("IntegratorPlugin", "BroadPhasePlugin", "SolverPlugin"):
+            return base.__name__
+    name = type(plugin).__name__
+    for slot in ("IntegratorPlugin", "BroadPhasePlugin", "SolverPlugin"):
+        if slot.replace("Plugin", "") in name:
+            return slot
+    return name
+
+
+class World:
+    """A headless world: body columns + the CPU fixture around the hot path + the plugin group."""
+
+    def __init__(self, scene: Scene, plugins: PhysicsPlugins, dt: float = 1.0 / 60.0, substeps: int = 6, solver_iterations: int = 1):
+        self.scene = scene
+        self.bodies = scene.bodies
+        self.joints = scene.joints
+        self.scalar = scene.bodies.position.dtype
+        self.plugins = plugins
+        self.pipeline = HostPipeline(scene.shape_type, scene.dims, scene.friction, scene.restitution, scalar=self.scalar)
+        integ = plugins.get("IntegratorPlugin")
+        cfg = getattr(plugins.get("SolverPlugin"), "config", None) or SolverConfig()
+        self.params = api.default_step_params(dt=dt, substeps=substeps, gravity=integ.gravity.value, solver_iterations=solver_iterations,
+                                              contact_damping_ratio=cfg.contact_damping_ratio, contact_frequency_factor=cfg.contact_frequency_factor,
+                                              max_overlap_solve_speed=cfg.max_overlap_solve_speed, warm_start_coefficient=cfg.warm_start_coefficient,
+                                              restitution_threshold=cfg.restitution_threshold, restitution_iterations=cfg.restitution_iterations)
+        self.last_manifolds: api.Manifolds | None = None
+        self.last_pairs: api.PairList | None = None
+        self.last_aabbs: api.Aabbs | None = None
+        self.step_index = 0
+
+    # the stages of one PhysicsSchedule run, separately callable so tests/bench can snapshot in between
+    def broad_phase(self) -> api.PairList:
+        dt = self.params.dt
+        self.aabb_min, self.aabb_max = self.pipeline.update_aabbs(self.bodies, dt)
+        aabbs = self.pipeline.intervals(self.bodies, self.aabb_min, self.aabb_max)
+        aabbs.joint_disabled_body_pairs = self.scene.joint_disabled_body_pairs
+        pairs = self.plugins.get("BroadPhasePlugin").collect_collision_pairs(aabbs)
+        self.pipeline.commit_broadphase(aabbs, pairs)
+        self.last_aabbs, self.last_pairs = aabbs, pairs
+        return pairs
+
+    def narrow_phase(self) -> api.Manifolds:
+        self.last_manifolds = self.pipeline.narrow_phase(self.bodies, self.aabb_min, self.aabb_max, self.params.dt, bool(self.params.match_contacts))
+        return self.last_manifolds
+
+    def solve(self) -> None:
+        m = self.last_manifolds
+        self.plugins.get("SolverPlugin").step(self.params, self.bodies, m, self.joints)
+        if m is not None and m.count:
+            self.pipeline.store_impulses(m)
+
+    def step(self) -> None:
+        self.broad_phase()
+        self.narrow_phase()
+        self.solve()
+        self.step_index += 1

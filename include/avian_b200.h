@@ -1,0 +1,307 @@
+/*
+ * avian_b200.h — C ABI of libavian_b200.so, the B200-native replacement for the avian3d substep hot path.
+ *
+ * The reference (avianphysics/avian @ 5bef382) has no FFI: its hot path is three Bevy plugins
+ * (`IntegratorPlugin`, `BroadPhasePlugin`, `SolverPlugin` + `XpbdSolverPlugin`).  A thin Rust shim
+ *  snapshots the ECS component columns those plugins read into the column structs
+ * below once per physics step, calls the entry points here, and scatters the results back.
+ *
+ * Each entry point cites the reference system(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns an AvnStatus (0 = ok, < 0 = error); nothing throws or aborts across the ABI;
+ *     avn_last_error() returns a human-readable message for the last failing call on that context.
+ *   - the caller owns all host buffers; they must stay valid until the call returns.  Buffers obtained
+ *     from avn_alloc_pinned() are page-locked, which makes the host<->device copies asynchronous DMA.
+ *   - the library owns all device memory.  One call in flight per context; a context is not thread-safe,
+ *     but any host thread may call (the context binds its CUDA device on entry).
+ *   - "scalar" columns are `float` when the context was created with scalar_bits = 32 and `double` when
+ *     scalar_bits = 64 (reference features `f32` / `f64`, crates/avian3d/Cargo.toml:14-77).
+ *   - Vec3 columns are packed [n][3], quaternions are packed [n][4] in glam order x,y,z,w, symmetric 3x3
+ *     matrices are packed [n][6] = m00,m01,m02,m11,m12,m22 (glam_matrix_extras::SymmetricMat3).
+ *   - there is NO CPU fallback: if no CUDA device is usable avn_create() fails with AVN_ERR_CUDA.
+ */
+#ifndef AVIAN_B200_H
+#define AVIAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVN_ABI_VERSION 1u
+
+/* src/dynamics/solver/constraint_graph.rs:39-48 */
+#define AVN_GRAPH_COLOR_COUNT 24
+#define AVN_COLOR_OVERFLOW 23
+#define AVN_DYNAMIC_COLOR_COUNT 20
+/* ContactManifold::prune_points keeps at most 4 points in 3D (src/collision/contact_types/mod.rs:478-566). */
+#define AVN_MAX_MANIFOLD_POINTS 4
+/* A contact/joint body that has no solver body and no column entry (static, zero velocity). */
+#define AVN_NO_BODY (-1)
+
+typedef enum AvnStatus {
+    AVN_OK = 0,
+    AVN_ERR_INVALID_ARGUMENT = -1,
+    AVN_ERR_CUDA = -2,
+    AVN_ERR_OUT_OF_MEMORY = -3,
+    AVN_ERR_UNSUPPORTED = -4,
+    AVN_ERR_CAPACITY = -5,
+    AVN_ERR_NCCL = -6
+} AvnStatus;
+
+/* RigidBody (src/dynamics/rigid_body/mod.rs). Static entries are optional: they carry pose for joints and
+ * LinearVelocity for contact tangents but are SolverBody::DUMMY inside the solver (solver_body/mod.rs:93-104). */
+typedef enum AvnBodyKind { AVN_BODY_DYNAMIC = 0, AVN_BODY_KINEMATIC = 1, AVN_BODY_STATIC = 2 } AvnBodyKind;
+
+/* LockedAxes bit layout (src/dynamics/rigid_body/locked_axes.rs; same bits as SolverBodyFlags, solver_body/mod.rs:133-146). */
+#define AVN_LOCK_TRANSLATION_X 0x20u
+#define AVN_LOCK_TRANSLATION_Y 0x10u
+#define AVN_LOCK_TRANSLATION_Z 0x08u
+#define AVN_LOCK_ROTATION_X 0x04u
+#define AVN_LOCK_ROTATION_Y 0x02u
+#define AVN_LOCK_ROTATION_Z 0x01u
+
+/* integration_flags bits: marker components integrator/mod.rs:168-195 */
+#define AVN_CUSTOM_VELOCITY_INTEGRATION 0x1u
+#define AVN_CUSTOM_POSITION_INTEGRATION 0x2u
+
+/* AabbIntervalFlags, src/collision/broad_phase.rs:187-196 */
+#define AVN_AABB_IS_INACTIVE 0x01u
+#define AVN_AABB_CONTACT_EVENTS 0x02u
+#define AVN_AABB_GENERATE_CONSTRAINTS 0x04u
+#define AVN_AABB_CUSTOM_FILTER 0x08u
+#define AVN_AABB_MODIFY_CONTACTS 0x10u
+
+/* Flag bits of an emitted pair (what collect_collision_pairs stores on ContactEdge / ContactPair,
+ * broad_phase.rs:443-468) plus NEEDS_HOOK: the shim must still call CollisionHooks::filter_pairs for it
+ * (broad_phase.rs:431-439), in list order, and drop the pair when the hook says no. */
+#define AVN_PAIR_CONTACT_EVENTS 0x01u
+#define AVN_PAIR_MODIFY_CONTACTS 0x02u
+#define AVN_PAIR_GENERATE_CONSTRAINTS 0x04u
+#define AVN_PAIR_NEEDS_HOOK 0x08u
+
+typedef struct AvnContext AvnContext;
+
+typedef struct AvnConfig {
+    uint32_t abi_version;     /* AVN_ABI_VERSION */
+    int32_t device;           /* CUDA device ordinal */
+    uint32_t scalar_bits;     /* 32 (feature f32) or 64 (feature f64) */
+    uint32_t flags;           /* AVN_CFG_* */
+} AvnConfig;
+
+/* Evaluate sin/cos of Quat::from_scaled_axis in double and round (bit-compatible with a correctly rounded
+ * libm; default).  Without it the f32 path uses the CUDA sinf/cosf (<= 1 ulp). */
+#define AVN_CFG_FAST_TRIG 0x1u
+
+/* ---- step parameters: resources read by the three plugins -------------------------------------------- */
+typedef struct AvnStepParams {
+    double dt;                /* Time<Physics>::delta_secs_f64()  (src/schedule/mod.rs:247-260) */
+    double h;                 /* Time<Substeps>::delta_secs_f64() (solver/schedule.rs:195-200)  */
+    uint32_t substeps;        /* SubstepCount (solver/schedule.rs:187-191) */
+    uint32_t restitution_iterations; /* SolverConfig (solver/plugin.rs:291-302) */
+    double gravity[3];        /* Gravity (integrator/mod.rs:150-162) */
+    double contact_damping_ratio;
+    double contact_frequency_factor;
+    double max_overlap_solve_speed;
+    double warm_start_coefficient;
+    double restitution_threshold;
+    double length_unit;       /* PhysicsLengthUnit (solver/plugin.rs:200-207) */
+    uint32_t match_contacts;  /* NarrowPhaseConfig::match_contacts: warm starting enabled (plugin.rs:432) */
+    uint32_t solver_iterations; /* EXTENSION, reference semantics = 1: repeats the biased solve pass */
+} AvnStepParams;
+
+/* ---- bodies: Appendix B of SURVEY.md; queries at solver_body/plugin.rs:174-185, integrator/mod.rs:261-268 */
+typedef struct AvnBodyColumns {
+    uint32_t count;
+    uint32_t _pad;
+    const uint8_t* kind;              /* AvnBodyKind */
+    void* position;                   /* [n][3] in/out  Position */
+    void* rotation;                   /* [n][4] in/out  Rotation */
+    void* linear_velocity;            /* [n][3] in/out  LinearVelocity */
+    void* angular_velocity;           /* [n][3] in/out  AngularVelocity */
+    const void* inverse_mass;         /* [n]     ComputedMass::inverse() */
+    const void* inverse_inertia_local;/* [n][6]  ComputedAngularInertia::inverse() (local frame) */
+    const void* center_of_mass;       /* [n][3]  ComputedCenterOfMass (local); NULL = zero */
+    const uint8_t* locked_axes;       /* NULL = none */
+    const int8_t* dominance;          /* NULL = 0 */
+    const void* linear_damping;       /* [n] NULL = 0 */
+    const void* angular_damping;      /* [n] NULL = 0 */
+    const void* gravity_scale;        /* [n] NULL = 1 */
+    const void* linear_acceleration;  /* [n][3] VelocityIntegrationData::linear_increment as written by ForcePlugin
+                                         (an acceleration until UpdateVelocityIncrements); NULL = 0 */
+    const void* angular_acceleration; /* [n][3] NULL = 0 */
+    const void* max_linear_speed;     /* [n] MaxLinearSpeed; NULL or +inf = absent */
+    const void* max_angular_speed;    /* [n] MaxAngularSpeed; NULL or +inf = absent */
+    const uint8_t* integration_flags; /* NULL = 0 */
+} AvnBodyColumns;
+
+/* ---- contact manifolds, grouped by graph colour (ConstraintGraph.colors[c].manifold_handles order,
+ *      solver/plugin.rs:389-434; ContactManifold/ContactPoint at contact_types/mod.rs:342-378,603-660) ---- */
+typedef struct AvnManifoldColumns {
+    uint32_t count;                                     /* M */
+    uint32_t point_count;                               /* P = point_offsets[M] */
+    uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];  /* colour c owns manifolds [off[c], off[c+1]) */
+    const int32_t* body1;             /* [M] index into AvnBodyColumns or AVN_NO_BODY */
+    const int32_t* body2;
+    const void* normal;               /* [M][3] */
+    const void* friction;             /* [M] */
+    const void* restitution;          /* [M] */
+    const void* tangent_velocity;     /* [M][3] NULL = 0 */
+    const uint32_t* point_offsets;    /* [M+1], at most AVN_MAX_MANIFOLD_POINTS per manifold */
+    const void* anchor1;              /* [P][3] */
+    const void* anchor2;              /* [P][3] */
+    const void* penetration;          /* [P] */
+    const void* normal_speed;         /* [P] */
+    void* warm_start_normal_impulse;  /* [P]    in/out (store_contact_impulses, plugin.rs:741-750) */
+    void* warm_start_tangent_impulse; /* [P][2] in/out */
+    void* normal_impulse;             /* [P]    out: ContactPoint::normal_impulse (total) */
+} AvnManifoldColumns;
+
+/* ---- joints: five typed arrays in the reference's solve order (xpbd/plugin.rs:58-86), each in ECS table
+ *      order.  Frames are the already-localised ones (update_local_frames in joints/{fixed,revolute,...}.rs). ------------------ */
+typedef enum AvnJointType {
+    AVN_JOINT_FIXED = 0,
+    AVN_JOINT_REVOLUTE = 1,
+    AVN_JOINT_SPHERICAL = 2,
+    AVN_JOINT_PRISMATIC = 3,
+    AVN_JOINT_DISTANCE = 4,
+    AVN_JOINT_TYPE_COUNT = 5
+} AvnJointType;
+
+typedef struct AvnJointColumns {
+    uint32_t count;
+    uint32_t _pad;
+    const int32_t* body1;             /* [J] index into AvnBodyColumns (static bodies need an entry: pose is read) */
+    const int32_t* body2;
+    const void* local_anchor1;        /* [J][3] */
+    const void* local_anchor2;        /* [J][3] */
+    const void* local_basis1;         /* [J][4] (unused by Distance); NULL = identity */
+    const void* local_basis2;
+    const void* axis;                 /* [J][3] hinge_axis / twist_axis / slider_axis; NULL = type default (Z / Y / X) */
+    const uint8_t* limit_enabled;     /* [J] bit0: angle_limit | swing_limit | prismatic limits ; bit1: twist_limit.
+                                         Distance joints always use limit (min,max). NULL = 0 */
+    const void* limit_min;            /* [J] */
+    const void* limit_max;            /* [J] */
+    const void* limit2_min;           /* [J] spherical twist_limit */
+    const void* limit2_max;
+    /* compliances, NULL = 0.  meaning per type:
+     *   fixed:     c0 point      c1 angle
+     *   revolute:  c0 point      c1 align     c2 limit
+     *   spherical: c0 point      c1 swing     c2 twist
+     *   prismatic: c0 align(pos) c1 angle     c2 limit (unused by the reference solve, kept for layout)
+     *   distance:  c0 compliance */
+    const void* compliance0;
+    const void* compliance1;
+    const void* compliance2;
+    const uint8_t* damping_enabled;   /* [J] JointDamping present; NULL = none */
+    const void* damping_linear;       /* [J] */
+    const void* damping_angular;      /* [J] */
+    void* force;                      /* [J][3] out: JointForces::force  (xpbd/plugin.rs:242-260); NULL = skip */
+    void* torque;                     /* [J][3] out */
+} AvnJointColumns;
+
+typedef struct AvnJointSet {
+    AvnJointColumns types[AVN_JOINT_TYPE_COUNT];
+} AvnJointSet;
+
+/* ---- broad phase: AabbIntervals (broad_phase.rs:176-202), in the PERSISTENT interval order (previous
+ *      frame's sorted order, then newly added colliders appended, broad_phase.rs:296-315) -------------- */
+typedef struct AvnAabbColumns {
+    uint32_t count;                   /* C */
+    uint32_t _pad;
+    const uint32_t* collider;         /* [C] Entity::index() of the collider */
+    const uint32_t* body;             /* [C] Entity::index() of ColliderOf::body */
+    const void* aabb_min;             /* [C][3] ColliderAabb::min */
+    const void* aabb_max;             /* [C][3] */
+    const uint32_t* memberships;      /* [C] CollisionLayers; NULL = 1 (default layer) */
+    const uint32_t* filters;          /* [C] NULL = 0xFFFFFFFF */
+    const uint8_t* flags;             /* [C] AVN_AABB_* */
+    uint32_t* order_out;              /* [C] out: new persistent order, as indices into these columns; NULL = skip */
+    /* pairs already in ContactGraph::pair_set (contact_graph.rs:95): PairKey u64, any order */
+    const uint64_t* existing_pairs;
+    uint64_t existing_pair_count;
+    /* body pairs (PairKey of body Entity::index()) whose joints disable collision (broad_phase.rs:423-428) */
+    const uint64_t* joint_disabled_body_pairs;
+    uint64_t joint_disabled_pair_count;
+} AvnAabbColumns;
+
+typedef struct AvnPairList {
+    uint64_t capacity;                /* in: elements available in each array below */
+    uint64_t count;                   /* out: pairs found (may exceed capacity -> AVN_ERR_CAPACITY, arrays hold the prefix) */
+    uint32_t* collider1;              /* [capacity] out: Entity::index() (i before j in the sorted order) */
+    uint32_t* collider2;
+    uint32_t* body1;
+    uint32_t* body2;
+    uint8_t* flags;                   /* AVN_PAIR_* */
+} AvnPairList;
+
+/* Device-time per phase in milliseconds of the last avn_solver_step / avn_broadphase call, named after
+ * SolverDiagnostics (src/dynamics/solver/diagnostics.rs:13-39) and CollisionDiagnostics (collision/diagnostics.rs:13-20). */
+typedef struct AvnTimings {
+    float h2d_ms;
+    float prepare_ms;          /* prepare_solver_bodies + prepare_joints + prepare_constraints + update_velocity_increments */
+    float substep_loop_ms;     /* integrate_velocities .. joint damping, all substeps */
+    float finalize_ms;         /* apply_restitution + finalize + store_impulses */
+    float d2h_ms;
+    float broad_phase_ms;
+    float total_ms;
+    uint32_t kernel_launches;  /* kernels launched by the last call */
+    uint32_t contact_constraint_count;
+    uint32_t joint_levels;
+    uint32_t active_colors;
+    uint32_t _pad;
+} AvnTimings;
+
+/* lifecycle ------------------------------------------------------------------------------------------- */
+AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx);
+void avn_destroy(AvnContext* ctx);
+const char* avn_last_error(const AvnContext* ctx); /* ctx may be NULL: error of the last failed avn_create */
+uint32_t avn_abi_version(void);
+
+/* pinned host memory for the column buffers */
+AvnStatus avn_alloc_pinned(AvnContext* ctx, size_t bytes, void** out_ptr);
+AvnStatus avn_free_pinned(AvnContext* ctx, void* ptr);
+
+/*
+ * One full solver stage of a physics step.  Replaces, in order:
+ *   prepare_solver_bodies (solver_body/plugin.rs:173-251), prepare_xpbd_joint<T> x5 (xpbd/plugin.rs:125-142),
+ *   update_contact_softness + prepare_contact_constraints (solver/plugin.rs:326-448),
+ *   pre_process_velocity_increments (integrator/mod.rs:260-313),
+ *   run_substep_schedule (solver/schedule.rs:194-213): integrate_velocities, clamp_velocities, warm_start,
+ *     solve_contacts<true>, integrate_positions, solve_contacts<false>, solve_xpbd_joint<T> x5,
+ *     project_linear/angular_velocity, joint_damping<T> x5,
+ *   solve_restitution (solver/plugin.rs:630-718), writeback_solver_bodies (solver_body/plugin.rs:255-284),
+ *   writeback_joint_forces (xpbd/plugin.rs:242-260), store_contact_impulses (solver/plugin.rs:722-755).
+ * Host buffers in, host buffers out (copies are inside the call).  manifolds / joints may be NULL.
+ */
+AvnStatus avn_solver_step(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies,
+                          AvnManifoldColumns* manifolds, AvnJointSet* joints);
+
+/* The same stage split in three so a caller can keep the snapshot resident in HBM:
+ *   upload (H2D only) -> run (kernels only, repeatable: every run restarts from the uploaded snapshot)
+ *   -> download (D2H of the last run's results into the column buffers given to upload). */
+AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies,
+                            AvnManifoldColumns* manifolds, AvnJointSet* joints);
+AvnStatus avn_solver_run(AvnContext* ctx);
+AvnStatus avn_solver_download(AvnContext* ctx);
+
+/*
+ * Sweep-and-prune pair generation.  Replaces collect_collision_pairs / sweep_and_prune (broad_phase.rs:343-474)
+ * over the intervals that update_aabb_intervals / add_new_aabb_intervals maintain (broad_phase.rs:214-315).
+ * The emitted list is exactly the sequence of ContactGraph::add_edge_and_key_with calls the reference makes
+ * (same pairs, same order); pairs flagged AVN_PAIR_NEEDS_HOOK still need the host filter_pairs callback.
+ */
+AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* out_pairs);
+AvnStatus avn_broadphase_upload(AvnContext* ctx, AvnAabbColumns* aabbs);
+AvnStatus avn_broadphase_run(AvnContext* ctx);
+AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs);
+
+AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVIAN_B200_H */
