@@ -1,0 +1,249 @@
+"""GPU parity tests proper: every test drives the CUDA path through the C ABI (avian_b200.api.Context) and compares
+with the CPU oracle on the same seeded inputs.  Bars: bit-exact for the broad phase pair lists (integer/index work),
+1e-5 relative for post-step body state and impulses (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from avian_b200 import api, plugins, scenes
+
+import oracle_lib
+from helpers import RTOL, advance_to_solver_input, assert_bodies_close, assert_manifolds_close, oracle_world, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_step(ctx, prm, b, m=None, j=None):
+    ctx.solver_step(prm, b, m, j)
+
+
+def _free_bodies(n=257, seed=7, scalar=np.float32):
+    rng = np.random.default_rng(seed)
+    s = np.dtype(scalar)
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    inv_i = np.zeros((n, 6))
+    diag = rng.uniform(0.5, 4.0, size=(n, 3))
+    iso = rng.random(n) < 0.5
+    diag[iso] = diag[iso, :1]
+    inv_i[:, 0], inv_i[:, 3], inv_i[:, 5] = diag[:, 0], diag[:, 1], diag[:, 2]
+    off = ~iso & (rng.random(n) < 0.5)
+    inv_i[off, 1] = 0.05; inv_i[off, 4] = -0.03
+    kind = rng.choice([0, 0, 0, 1, 2], size=n).astype(np.uint8)
+    b = api.Bodies(kind=kind, position=rng.normal(size=(n, 3)).astype(s) * 10, rotation=q.astype(s),
+                   linear_velocity=rng.normal(size=(n, 3)).astype(s), angular_velocity=(rng.normal(size=(n, 3)) * 3).astype(s),
+                   inverse_mass=rng.uniform(0.1, 2.0, size=n).astype(s), inverse_inertia_local=inv_i.astype(s),
+                   center_of_mass=(rng.normal(size=(n, 3)) * 0.1).astype(s))
+    b.locked_axes = rng.choice([0, 0, 0, 0x20, 0x12, 0x07, 0x3f], size=n).astype(np.uint8)
+    b.linear_damping = rng.uniform(0, 1, size=n).astype(s)
+    b.angular_damping = rng.uniform(0, 1, size=n).astype(s)
+    b.gravity_scale = rng.uniform(-1, 2, size=n).astype(s)
+    b.linear_acceleration = rng.normal(size=(n, 3)).astype(s)
+    b.angular_acceleration = rng.normal(size=(n, 3)).astype(s)
+    b.max_linear_speed = np.where(rng.random(n) < 0.3, 1.0, np.inf).astype(s)
+    b.max_angular_speed = np.where(rng.random(n) < 0.3, 2.0, np.inf).astype(s)
+    b.integration_flags = rng.choice([0, 0, 0, 1, 2, 3], size=n).astype(np.uint8)
+    return b
+
+
+def test_integrator_all_options(gpu_ctx):
+    """I0-I3 + S1 + S6: damping, gravity scale, locked axes, accelerations, gyroscopic torque, speed clamps, kinematic and
+    static bodies, custom-integration markers — no contacts."""
+    b = _free_bodies()
+    prm = api.default_step_params(dt=1.0 / 60.0, substeps=5)
+    bo, bg = b.copy(), b.copy()
+    for _ in range(3):
+        oracle_lib.solver_step(prm, bo)
+        _gpu_step(gpu_ctx, prm, bg)
+    assert_bodies_close(bg, bo, rtol=2e-6, what="integrator: ")
+    # static bodies must come back untouched
+    st = b.kind == api.BODY_STATIC
+    assert np.array_equal(bg.position[st], b.position[st]) and np.array_equal(bg.linear_velocity[st], b.linear_velocity[st])
+
+
+def test_reference_integrator_test_on_gpu(gpu_ctx):
+    """integrator/mod.rs:561-629 through the CUDA path."""
+    s = np.float32
+    b = api.Bodies(kind=np.array([0], dtype=np.uint8), position=np.zeros((1, 3), dtype=s), rotation=np.array([[0, 0, 0, 1]], dtype=s),
+                   linear_velocity=np.zeros((1, 3), dtype=s), angular_velocity=np.array([[0, 0, 2.0]], dtype=s), inverse_mass=np.ones(1, dtype=s),
+                   inverse_inertia_local=np.array([[6.0, 0, 0, 6.0, 0, 6.0]], dtype=s))
+    prm = api.default_step_params(dt=0.1, substeps=1)
+    for _ in range(100):
+        _gpu_step(gpu_ctx, prm, b)
+    assert abs(b.position[0, 1] + 490.5) < 10.0
+    assert np.allclose(b.linear_velocity[0], [0, -98.1, 0], atol=1e-4)
+    assert np.allclose(b.angular_velocity[0], [0, 0, 2.0], atol=1e-5)
+
+
+@pytest.mark.parametrize("scene_fn,steps,substeps", [
+    (lambda: scenes.cubes_example(3), 45, 1),          # BASELINE config 1: 27 cubes, 1 substep, falling then landing
+    (lambda: scenes.cubes_example(4), 50, 6),          # the literal examples/cubes.rs scene
+    (lambda: scenes.cube_stack(6, 6, 6, brick=True), 3, 8),
+    (lambda: scenes.cube_stack(8, 4, 8, brick=False, restitution=0.4), 2, 4),
+])
+def test_contact_solver_single_step(gpu_ctx, scene_fn, steps, substeps):
+    """S0-S7: one solver stage from the same snapshot (bodies + manifolds + warm-start impulses)."""
+    _, (prm, b, m, j) = advance_to_solver_input(scene_fn(), steps=steps, substeps=substeps)
+    assert m is not None and m.count > 0
+    bo, mo, bg, mg = b.copy(), m.copy(), b.copy(), m.copy()
+    oracle_lib.solver_step(prm, bo, mo)
+    _gpu_step(gpu_ctx, prm, bg, mg)
+    assert_bodies_close(bg, bo, what="contacts: ")
+    assert_manifolds_close(mg, mo, what="contacts: ")
+
+
+def test_contact_solver_trajectory(gpu_ctx):
+    """60 full steps (warm-start impulses round-tripping through store_contact_impulses and the narrow-phase fixture):
+    GPU world vs oracle world."""
+    sc_o, sc_g = scenes.cubes_example(3), scenes.cubes_example(3)
+    wo = oracle_world(sc_o, substeps=1)
+    wg = plugins.World(sc_g, plugins.PhysicsPlugins(gpu_ctx), substeps=1)
+    worst = 0.0
+    for i in range(60):
+        wo.step(); wg.step()
+        worst = max(worst, rel_err(wg.bodies.position, wo.bodies.position), rel_err(wg.bodies.linear_velocity, wo.bodies.linear_velocity))
+    assert wg.last_pairs.count == wo.last_pairs.count
+    assert worst <= RTOL, f"trajectory diverged: {worst:.3e}"
+
+
+def test_dominance_kinematic_and_overflow_colour(gpu_ctx):
+    """relative dominance (contact/mod.rs:129-154), kinematic bodies, and the serial overflow colour 23."""
+    w, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(4, 3, 4, brick=True), steps=2, substeps=4)
+    b.dominance = np.zeros(b.count, dtype=np.int8)
+    b.dominance[5::7] = 3
+    b.kind = b.kind.copy(); b.kind[9] = api.BODY_KINEMATIC; b.linear_velocity[9] = (0.2, 0.0, 0.0)
+    # move the last third of colour 0 into the overflow colour (legal: overflow is solved serially, first)
+    off = m.color_offsets.astype(np.int64)
+    n0 = int(off[1] - off[0]); k = n0 // 3
+    perm = np.concatenate([np.arange(0, n0 - k), np.arange(n0, m.count), np.arange(n0 - k, n0)])
+    pts = [np.arange(m.point_offsets[i], m.point_offsets[i + 1]) for i in perm]
+    counts = np.array([len(p) for p in pts]); pidx = np.concatenate(pts)
+    m2 = api.Manifolds(color_offsets=m.color_offsets.copy(), body1=m.body1[perm].copy(), body2=m.body2[perm].copy(), normal=m.normal[perm].copy(),
+                       friction=m.friction[perm].copy(), restitution=m.restitution[perm].copy(),
+                       point_offsets=np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32), anchor1=m.anchor1[pidx].copy(),
+                       anchor2=m.anchor2[pidx].copy(), penetration=m.penetration[pidx].copy(), normal_speed=m.normal_speed[pidx].copy(),
+                       warm_start_normal_impulse=m.warm_start_normal_impulse[pidx].copy(), warm_start_tangent_impulse=m.warm_start_tangent_impulse[pidx].copy(),
+                       normal_impulse=m.normal_impulse[pidx].copy())
+    co = off.copy(); co[1:] -= k; co[api.COLOR_OVERFLOW + 1] = m.count
+    m2.color_offsets = co.astype(np.uint32)
+    bo, mo, bg, mg = b.copy(), m2.copy(), b.copy(), m2.copy()
+    oracle_lib.solver_step(prm, bo, mo)
+    _gpu_step(gpu_ctx, prm, bg, mg)
+    assert_bodies_close(bg, bo, what="dominance: ")
+    assert_manifolds_close(mg, mo, what="dominance: ")
+
+
+def test_launch_modes_agree(gpu_ctx):
+    """the persistent megakernel and the one-launch-per-phase path are the same arithmetic: bit-identical results"""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(5, 5, 5, brick=True), steps=2, substeps=4)
+    bg, mg = b.copy(), m.copy()
+    _gpu_step(gpu_ctx, prm, bg, mg)
+    assert gpu_ctx.timings()["kernel_launches"] == 1, "the megakernel path should be ONE launch per step"
+    os.environ["AVN_LAUNCH_MODE"] = "phases"
+    try:
+        with api.Context(device=0) as ctx2:
+            bp, mp = b.copy(), m.copy()
+            ctx2.solver_step(prm, bp, mp)
+            assert ctx2.timings()["kernel_launches"] > 10
+    finally:
+        del os.environ["AVN_LAUNCH_MODE"]
+    for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
+        assert np.array_equal(getattr(bg, name), getattr(bp, name)), name
+    assert np.array_equal(mg.warm_start_normal_impulse, mp.warm_start_normal_impulse)
+
+
+def test_upload_run_download_split_is_repeatable(gpu_ctx):
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(4, 4, 4, brick=True), steps=1, substeps=4)
+    b1, m1 = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, b1, m1)
+    b2, m2 = b.copy(), m.copy()
+    gpu_ctx.solver_upload(prm, b2, m2)
+    gpu_ctx.solver_run(); gpu_ctx.solver_run()      # every run restarts from the uploaded snapshot
+    gpu_ctx.solver_download()
+    assert np.array_equal(b1.position, b2.position) and np.array_equal(m1.normal_impulse, m2.normal_impulse)
+
+
+# ---- joints ---------------------------------------------------------------------------------------------------------
+def test_spherical_chain(gpu_ctx):
+    """X0-X4 on chain_3d: 40 links = 40 dependency levels, kinematic anchor, compliance."""
+    sc = scenes.spherical_chain(40)
+    prm = api.default_step_params(substeps=12)
+    bo, bg, jo, jg = sc.bodies.copy(), sc.bodies.copy(), sc.joints.copy(), sc.joints.copy()
+    bo.linear_velocity[5] = bg.linear_velocity[5] = (0.5, 0.0, 0.2)
+    for _ in range(5):
+        oracle_lib.solver_step(prm, bo, None, jo)
+        _gpu_step(gpu_ctx, prm, bg, None, jg)
+    assert_bodies_close(bg, bo, what="chain: ")
+    assert rel_err(jg.types[api.JOINT_SPHERICAL].force, jo.types[api.JOINT_SPHERICAL].force) <= 1e-4
+    assert gpu_ctx.timings()["joint_levels"] == 40
+
+
+def _all_joint_types_scene(scalar=np.float32, n=30, seed=3):
+    rng = np.random.default_rng(seed)
+    s = np.dtype(scalar)
+    nb = 2 * n * 5 + 1
+    q = rng.normal(size=(nb, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    kind = np.zeros(nb, dtype=np.uint8); kind[0] = api.BODY_STATIC; kind[3::17] = api.BODY_KINEMATIC
+    b = api.Bodies(kind=kind, position=(rng.normal(size=(nb, 3)) * 2).astype(s), rotation=q.astype(s),
+                   linear_velocity=(rng.normal(size=(nb, 3)) * 0.5).astype(s), angular_velocity=rng.normal(size=(nb, 3)).astype(s),
+                   inverse_mass=rng.uniform(0.5, 2, size=nb).astype(s), inverse_inertia_local=np.zeros((nb, 6), dtype=s),
+                   center_of_mass=(rng.normal(size=(nb, 3)) * 0.05).astype(s))
+    b.inverse_inertia_local[:, 0] = rng.uniform(1, 3, nb); b.inverse_inertia_local[:, 3] = rng.uniform(1, 3, nb); b.inverse_inertia_local[:, 5] = rng.uniform(1, 3, nb)
+    b.dominance = np.zeros(nb, dtype=np.int8); b.dominance[7::11] = 2
+    js = api.JointSet()
+    for t in range(api.JOINT_TYPE_COUNT):
+        b1 = rng.integers(0, nb, size=n).astype(np.int32)
+        b2 = ((b1 + rng.integers(1, nb - 1, size=n)) % nb).astype(np.int32)
+        lb = rng.normal(size=(2, n, 4)); lb /= np.linalg.norm(lb, axis=2, keepdims=True)
+        ax = rng.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        j = api.Joints(body1=b1, body2=b2, local_anchor1=(rng.normal(size=(n, 3)) * 0.3).astype(s), local_anchor2=(rng.normal(size=(n, 3)) * 0.3).astype(s),
+                       local_basis1=lb[0].astype(s), local_basis2=lb[1].astype(s), axis=ax.astype(s),
+                       limit_enabled=rng.integers(0, 4, size=n).astype(np.uint8), limit_min=rng.uniform(-1.0, -0.1, n).astype(s),
+                       limit_max=rng.uniform(0.1, 1.0, n).astype(s), limit2_min=rng.uniform(-0.5, -0.1, n).astype(s), limit2_max=rng.uniform(0.1, 0.5, n).astype(s),
+                       compliance0=rng.choice([0, 1e-4], n).astype(s), compliance1=rng.choice([0, 1e-3], n).astype(s), compliance2=rng.choice([0, 1e-3], n).astype(s),
+                       damping_enabled=(rng.random(n) < 0.3).astype(np.uint8), damping_linear=rng.uniform(0, 2, n).astype(s), damping_angular=rng.uniform(0, 2, n).astype(s),
+                       force=np.zeros((n, 3), dtype=s), torque=np.zeros((n, 3), dtype=s))
+        if t == api.JOINT_DISTANCE:
+            j.limit_min = rng.uniform(0.2, 0.8, n).astype(s); j.limit_max = (j.limit_min + rng.uniform(0, 0.5, n)).astype(s)
+        js.types[t] = j
+    return b, js
+
+
+def test_all_joint_types_random_graph(gpu_ctx):
+    """every joint type, limits, compliance, damping, dominance, static and kinematic ends, random connectivity:
+    exercises the order-preserving level schedule against the serial oracle."""
+    b, js = _all_joint_types_scene()
+    prm = api.default_step_params(substeps=4)
+    bo, bg, jo, jg = b.copy(), b.copy(), js.copy(), js.copy()
+    oracle_lib.solver_step(prm, bo, None, jo)
+    _gpu_step(gpu_ctx, prm, bg, None, jg)
+    assert_bodies_close(bg, bo, rtol=2e-5, what="joints: ")
+    for t in range(api.JOINT_TYPE_COUNT):
+        assert rel_err(jg.types[t].force, jo.types[t].force) <= 1e-4, t
+        assert rel_err(jg.types[t].torque, jo.types[t].torque) <= 1e-4, t
+
+
+def test_ragdolls_with_contacts(gpu_ctx):
+    """BASELINE config 4 in miniature: 9 ragdolls falling on the ground, contacts + revolute + spherical joints."""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.ragdoll_field(9, pitch=3.0, drop_height=0.1), steps=25, substeps=8)
+    assert m is not None and m.count > 0 and j.count == 9 * 16
+    bo, mo, jo, bg, mg, jg = b.copy(), m.copy(), j.copy(), b.copy(), m.copy(), j.copy()
+    oracle_lib.solver_step(prm, bo, mo, jo)
+    _gpu_step(gpu_ctx, prm, bg, mg, jg)
+    assert_bodies_close(bg, bo, what="ragdolls: ")
+    assert_manifolds_close(mg, mo, what="ragdolls: ")
+
+
+@pytest.mark.parametrize("scalar", [np.float64])
+def test_f64_contacts_and_joints(scalar):
+    with api.Context(device=0, scalar=scalar) as ctx:
+        _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(4, 4, 4, brick=True, scalar=scalar), steps=2, substeps=4)
+        bo, mo, bg, mg = b.copy(), m.copy(), b.copy(), m.copy()
+        oracle_lib.solver_step(prm, bo, mo)
+        ctx.solver_step(prm, bg, mg)
+        assert_bodies_close(bg, bo, rtol=1e-9, what="f64 contacts: ")
+        bj, js = _all_joint_types_scene(scalar=scalar)
+        bo, bg, jo, jg = bj.copy(), bj.copy(), js.copy(), js.copy()
+        oracle_lib.solver_step(prm, bo, None, jo)
+        ctx.solver_step(prm, bg, None, jg)
+        assert_bodies_close(bg, bo, rtol=1e-9, what="f64 joints: ")
