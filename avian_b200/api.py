@@ -319,6 +319,7 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "broadphase_run": ([_vp], C.c_int),
         "broadphase_download": ([_vp, P(AvnPairList)], C.c_int),
         "get_timings": ([_vp, P(AvnTimings)], C.c_int),
+        "joint_levels": ([P(AvnBodyColumns), P(AvnJointSet), _vp, P(C.c_uint32)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -329,7 +330,19 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
 ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
-    "avn_broadphase_download", "avn_get_timings"]
+    "avn_broadphase_download", "avn_get_timings", "avn_joint_levels"]
+
+
+def joint_levels(bodies: "Bodies", joints: "JointSet"):
+    """avn_joint_levels: (level per joint in the reference's global order, number of levels).  Host-only."""
+    lib = load_library()
+    b, j = bodies.as_struct(), joints.as_struct()
+    out = np.zeros(joints.count, dtype=np.uint32)
+    n = C.c_uint32(0)
+    st = lib.avn_joint_levels(C.byref(b), C.byref(j), _ptr(out), C.byref(n))
+    if st != OK:
+        raise AvianError(st, lib.avn_last_error(None).decode())
+    return out, int(n.value)
 
 _lib = None
 

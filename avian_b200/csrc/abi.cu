@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "context.hpp"
+#include "joint_schedule.hpp"
 
 struct AvnContext {
     int device = 0;
@@ -140,6 +141,18 @@ AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* ou
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {
     if (!ctx || !out) return AVN_ERR_INVALID_ARGUMENT;
     *out = ctx->last;
+    return AVN_OK;
+}
+
+AvnStatus avn_joint_levels(const AvnBodyColumns* bodies, const AvnJointSet* joints, uint32_t* out_level, uint32_t* out_level_count) {
+    if (!bodies || !joints) return AVN_ERR_INVALID_ARGUMENT;
+    avn::JointSchedule sch;
+    std::string error;
+    AvnStatus st = avn::build_joint_schedule(*bodies, *joints, sch, error);
+    if (st != AVN_OK) return create_fail(st, error);
+    if (out_level)
+        for (size_t g = 0; g < sch.level_of_global.size(); ++g) out_level[g] = uint32_t(sch.level_of_global[g]);
+    if (out_level_count) *out_level_count = uint32_t(sch.n_levels);
     return AVN_OK;
 }
 

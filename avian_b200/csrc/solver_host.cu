@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "context.hpp"
+#include "joint_schedule.hpp"
 #include "solver_kernels.cuh"
 
 namespace avn {
@@ -115,64 +116,18 @@ class Solver final : public SolverBase {
 
 template <class S>
 AvnStatus Solver<S>::build_joint_schedule(const AvnBodyColumns& bc, const AvnJointSet& js) {
-    // global joint order = the reference's serial solve order: type order, then table order (xpbd/plugin.rs:58-86)
-    size_t J = 0;
-    for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) J += js.types[t].count;
-    const uint32_t B = bc.count;
-    std::vector<int> type(J), index(J), b1(J), b2(J);
-    std::vector<uint8_t> conflict(B, 0);
-    bool any_damping = false;
-    size_t g = 0;
-    auto dom_of = [&](int b) -> int {
-        uint8_t kind = bc.kind ? bc.kind[b] : uint8_t(AVN_BODY_DYNAMIC);
-        return kind == AVN_BODY_DYNAMIC ? (bc.dominance ? int(bc.dominance[b]) : 0) : 128;
-    };
-    auto has_sb = [&](int b) { return (bc.kind ? bc.kind[b] : uint8_t(AVN_BODY_DYNAMIC)) != AVN_BODY_STATIC; };
-    for (int t = 0; t < AVN_JOINT_TYPE_COUNT; ++t) {
-        const AvnJointColumns& jc = js.types[t];
-        if (jc.count && (!jc.body1 || !jc.body2 || !jc.local_anchor1 || !jc.local_anchor2))
-            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "joint type %d: body1/body2/local_anchor1/local_anchor2 are required", t);
-        for (uint32_t k = 0; k < jc.count; ++k, ++g) {
-            int x = jc.body1[k], y = jc.body2[k];
-            if (x < 0 || y < 0 || uint32_t(x) >= B || uint32_t(y) >= B)
-                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "joint type %d #%u references body %d/%d outside [0,%u)", t, k, x, y, B);
-            type[g] = t; index[g] = int(k); b1[g] = x; b2[g] = y;
-            if (jc.damping_enabled && jc.damping_enabled[k]) any_damping = true;
-        }
-    }
-    // a body orders the joints that touch it iff some joint WRITES it: it has a SolverBody and is not the dominated
-    // side there.  With joint damping every SolverBody is written (solver/plugin.rs:789-803).
-    for (g = 0; g < J; ++g) {
-        int rel = dom_of(b1[g]) - dom_of(b2[g]);
-        if (has_sb(b1[g]) && (any_damping || !(rel > 0))) conflict[b1[g]] = 1;
-        if (has_sb(b2[g]) && (any_damping || !(rel < 0))) conflict[b2[g]] = 1;
-    }
-    std::vector<int> last(B, 0), level(J);
-    int n_levels = 0;
-    for (g = 0; g < J; ++g) {
-        int l = 0;
-        if (conflict[b1[g]]) l = std::max(l, last[b1[g]]);
-        if (conflict[b2[g]]) l = std::max(l, last[b2[g]]);
-        level[g] = l;  // 0-based
-        if (conflict[b1[g]]) last[b1[g]] = l + 1;
-        if (conflict[b2[g]]) last[b2[g]] = l + 1;
-        n_levels = std::max(n_levels, l + 1);
-    }
-    h_level_off_.assign(n_levels + 1, 0);
-    for (g = 0; g < J; ++g) ++h_level_off_[level[g] + 1];
-    for (int l = 0; l < n_levels; ++l) h_level_off_[l + 1] += h_level_off_[l];
-    h_type_.resize(J);
-    h_index_.resize(J);
-    std::vector<int> cursor(h_level_off_.begin(), h_level_off_.end() - 1);
-    for (g = 0; g < J; ++g) {  // stable within a level
-        int s = cursor[level[g]]++;
-        h_type_[s] = type[g];
-        h_index_[s] = index[g];
-    }
+    JointSchedule sch;
+    std::string error;
+    AvnStatus st = avn::build_joint_schedule(bc, js, sch, error);
+    if (st != AVN_OK) return err_->fail(st, "%s", error.c_str());
+    h_type_.swap(sch.type);
+    h_index_.swap(sch.index);
+    h_level_off_.swap(sch.level_off);
+    const size_t J = h_type_.size();
     dev_.J = int(J);
     dev_.Jpad = int((J + 31) & ~size_t(31));
-    dev_.n_levels = n_levels;
-    dev_.any_joint_damping = any_damping ? 1 : 0;
+    dev_.n_levels = sch.n_levels;
+    dev_.any_joint_damping = sch.any_damping ? 1 : 0;
     return AVN_OK;
 }
 

@@ -301,6 +301,14 @@ AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs);
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
+/*
+ * Host-only helper (needs no context and no GPU): the order-preserving level schedule the solver stage uses for
+ * joints.  The reference solves joints serially in type order then table order (xpbd/plugin.rs:58-86, 145-189);
+ * out_level[g] (g = index in that global order) is the parallel phase joint g runs in: joints of one level touch
+ * disjoint written bodies, and every joint runs after all earlier joints it shares a written body with.
+ */
+AvnStatus avn_joint_levels(const AvnBodyColumns* bodies, const AvnJointSet* joints, uint32_t* out_level, uint32_t* out_level_count);
+
 #ifdef __cplusplus
 }
 #endif

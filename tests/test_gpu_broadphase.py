@@ -112,7 +112,7 @@ def test_large_sizes_properties(gpu_ctx):
     mn, mx = w.pipeline.update_aabbs(w.bodies, w.params.dt)
     aabbs = w.pipeline.intervals(w.bodies, mn, mx)
     pairs = gpu_ctx.broadphase(aabbs, capacity=4_000_000)
-    assert pairs.count > 400_000
+    assert pairs.count > 300_000
     rank = np.empty(sc.bodies.count, dtype=np.int64); rank[aabbs.collider[aabbs.order_out]] = np.arange(sc.bodies.count)
     ri, rj = rank[pairs.collider1], rank[pairs.collider2]
     assert (ri < rj).all()
