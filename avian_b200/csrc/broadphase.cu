@@ -10,9 +10,10 @@
 //      stable scatter ranked with warp match/ballot (4 passes for f32 keys, 8 for f64);
 //   3. gather the interval columns into sorted SoA arrays (coalesced for the sweep);
 //   4. per interval i: upper bound of max.x[i] in the sorted min.x = the reference's `break` position;
-//   5. one warp per i strides the candidates j in (i, end_i): y/z overlap (inclusive), inactive/layers/same-body,
-//      existing-pair hash set, joint-disabled hash set — count pass, exclusive scan, emit pass: ballot + popc keep
-//      the j order inside a warp, the scan keeps the i order across warps.
+//   5. tiled sweep: a block owns 64 consecutive i and streams the union of their candidate ranges (i, end_i) through
+//      shared memory; y/z overlap (inclusive), inactive/layers/same-body, existing-pair hash set, joint-disabled hash
+//      set — count pass, exclusive scan, emit pass: ballot + popc keep the j order inside a warp, the scan keeps the
+//      i order across intervals.
 #include <algorithm>
 #include <cstring>
 
@@ -227,12 +228,9 @@ __device__ __forceinline__ uint64_t pair_key(uint32_t a, uint32_t b) {  // data_
     return a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a;
 }
 
-// the filters of broad_phase.rs:394-428 for the candidate (i, j); `mi`, `fi` describe i
+// the non-geometric filters of broad_phase.rs:405-428 for a candidate (i, j) that overlaps on all three axes
 template <class S>
-__device__ __forceinline__ bool pair_passes(const Sweep<S>& s, Vec4<S> yi, uint4 mi, uint32_t fi, int j, uint32_t& pair_flags, uint4& mj) {
-    Vec4<S> yj = s.yz[j];
-    if (yi.x > yj.y || yi.y < yj.x) return false;   // aabb1.min.y > aabb2.max.y || aabb1.max.y < aabb2.min.y
-    if (yi.z > yj.w || yi.w < yj.z) return false;   // same on z
+__device__ __forceinline__ bool pair_filters(const Sweep<S>& s, uint4 mi, uint32_t fi, int j, uint32_t& pair_flags, uint4& mj) {
     mj = s.meta[j];
     uint32_t fj = s.flags[j];
     bool interacts = (mi.z & mj.w) != 0 && (mj.z & mi.w) != 0;  // CollisionLayers::interacts_with, layers.rs:423-426
@@ -245,76 +243,155 @@ __device__ __forceinline__ bool pair_passes(const Sweep<S>& s, Vec4<S> yi, uint4
     return true;
 }
 
-// one warp per interval i.  EMIT = false: counts[i]; EMIT = true: writes pairs at offsets[i] + running index.
+// Tiled sweep.  A block owns SW_TILE consecutive intervals i (consecutive in the sorted order, so their candidate
+// ranges (i, end[i]) overlap almost completely) and streams the union of the ranges through shared memory in chunks of
+// SW_CHUNK candidates: every candidate's {min.y,max.y,min.z,max.z} is read from L2 once per block instead of once per i
+// (the 100k-cube stack has ~2 000 x-overlap candidates per interval, ~4 of which survive the y/z test).
+// Warp w handles intervals w*SW_PER_WARP .. +SW_PER_WARP-1 of the tile; for one i the lanes take 32 consecutive
+// candidates per round, chunks / rounds / lanes all advance in j order, so ballot + popc give the reference's (i, j)
+// emission order.  EMIT = false: counts[i]; EMIT = true: writes pairs at offsets[i] + running index.
+constexpr int SW_THREADS = 256, SW_WARPS = SW_THREADS / 32, SW_PER_WARP = 8, SW_TILE = SW_WARPS * SW_PER_WARP, SW_CHUNK = 256;
+
 template <class S, bool EMIT>
-__global__ void __launch_bounds__(256) sweep_kernel(const __grid_constant__ Sweep<S> s, uint32_t* __restrict__ counts,
-                                                    const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
-                                                    uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
-                                                    uint8_t* __restrict__ out_flags) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < s.n; i += warps_per_grid) {
-        const int e = s.end[i];
-        const Vec4<S> yi = s.yz[i];
-        const uint4 mi = s.meta[i];
-        const uint32_t fi = s.flags[i];
-        uint64_t running = EMIT ? offsets[i] : 0ull;
-        uint32_t total = 0;
-        for (int j0 = i + 1; j0 < e; j0 += 32) {
-            const int j = j0 + lane;
-            uint32_t pf = 0;
-            uint4 mj = make_uint4(0, 0, 0, 0);
-            bool ok = j < e && pair_passes(s, yi, mi, fi, j, pf, mj);
-            uint32_t bal = __ballot_sync(0xffffffffu, ok);
-            if (EMIT) {
-                if (ok) {
-                    uint64_t pos = running + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < capacity) {
-                        out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
+__global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant__ Sweep<S> s, uint32_t* __restrict__ counts,
+                                                           const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
+                                                           uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
+                                                           uint8_t* __restrict__ out_flags) {
+    __shared__ Vec4<S> s_yz[SW_CHUNK];
+    __shared__ int s_jend;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile0 = blockIdx.x * SW_TILE; tile0 < s.n; tile0 += gridDim.x * SW_TILE) {
+        const int tile_n = min(SW_TILE, s.n - tile0);
+        // union of the candidate ranges of the tile
+        if (threadIdx.x == 0) s_jend = 0;
+        __syncthreads();
+        if (threadIdx.x < tile_n) atomicMax(&s_jend, s.end[tile0 + threadIdx.x]);
+        __syncthreads();
+        const int j_begin = tile0 + 1, j_end = s_jend;
+        // per-warp state of its SW_PER_WARP intervals (lane-uniform)
+        int my_end[SW_PER_WARP];
+        Vec4<S> my_yz[SW_PER_WARP];
+        uint64_t running[SW_PER_WARP];
+        uint32_t total[SW_PER_WARP];
+#pragma unroll
+        for (int q = 0; q < SW_PER_WARP; ++q) {
+            const int i = tile0 + warp * SW_PER_WARP + q;
+            const bool live = i < s.n;
+            my_end[q] = live ? s.end[i] : 0;
+            my_yz[q] = live ? s.yz[i] : mk4<S>(0, 0, 0, 0);
+            running[q] = (EMIT && live) ? offsets[i] : 0ull;
+            total[q] = 0;
+        }
+        for (int c0 = j_begin; c0 < j_end; c0 += SW_CHUNK) {
+            __syncthreads();  // previous chunk fully consumed
+            {
+                const int j = c0 + threadIdx.x;
+                if (j < j_end) s_yz[threadIdx.x] = s.yz[j];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < SW_PER_WARP; ++q) {
+                const int i = tile0 + warp * SW_PER_WARP + q;
+                const int e = my_end[q];
+                if (c0 >= e || c0 + SW_CHUNK <= i + 1) continue;  // chunk outside (i, end_i): warp-uniform
+                const Vec4<S> yi = my_yz[q];
+#pragma unroll 2
+                for (int r = 0; r < SW_CHUNK / 32; ++r) {
+                    const int j = c0 + r * 32 + lane;
+                    bool ok = j > i && j < e;
+                    if (ok) {
+                        const Vec4<S> yj = s_yz[r * 32 + lane];
+                        // broad_phase.rs:394-403 (inclusive tests)
+                        ok = !(yi.x > yj.y || yi.y < yj.x) && !(yi.z > yj.w || yi.w < yj.z);
+                    }
+                    uint32_t pf = 0;
+                    uint4 mi = make_uint4(0, 0, 0, 0), mj = mi;
+                    if (ok) {
+                        mi = s.meta[i];
+                        ok = pair_filters(s, mi, s.flags[i], j, pf, mj);
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                    if (bal == 0) continue;
+                    if (EMIT) {
+                        if (ok) {
+                            const uint64_t pos = running[q] + __popc(bal & ((1u << lane) - 1u));
+                            if (pos < capacity) {
+                                out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
+                            }
+                        }
+                        running[q] += __popc(bal);
+                    } else {
+                        total[q] += __popc(bal);
                     }
                 }
-                running += __popc(bal);
-            } else {
-                total += __popc(bal);
             }
         }
-        if (!EMIT && lane == 0) counts[i] = total;
+        if (!EMIT && lane == 0) {
+#pragma unroll
+            for (int q = 0; q < SW_PER_WARP; ++q) {
+                const int i = tile0 + warp * SW_PER_WARP + q;
+                if (i < s.n) counts[i] = total[q];
+            }
+        }
+        __syncthreads();
     }
 }
 
-// exclusive scan of n 32-bit counts into 64-bit offsets (single block; n <= a few 10^6), total -> offsets[n]
-__global__ void __launch_bounds__(1024) scan_counts(const uint32_t* __restrict__ counts, int n, uint64_t* __restrict__ offsets) {
-    __shared__ uint64_t warp_sums[32];
+// exclusive scan of n 32-bit counts into 64-bit offsets (offsets[n] = total), three small launches:
+// per-block sums (1024 counts each) -> single-block scan of the <= 1024 block sums -> per-block local scan + base.
+__device__ __forceinline__ uint64_t block_exclusive_scan_1024(uint64_t v, uint64_t* warp_sums, uint64_t& block_total) {
+    uint64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint64_t w = warp_sums[threadIdx.x], z = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, z, o);
+            if (threadIdx.x >= o) z += y;
+        }
+        warp_sums[threadIdx.x] = z - w;
+        if (threadIdx.x == 31) warp_sums[32] = z;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return x - v + warp_sums[threadIdx.x >> 5];
+}
+__global__ void __launch_bounds__(1024) scan_block_sums(const uint32_t* __restrict__ counts, int n, uint64_t* __restrict__ block_sums) {
+    __shared__ uint64_t ws[33];
+    int i = blockIdx.x * 1024 + threadIdx.x;
+    uint64_t total;
+    block_exclusive_scan_1024(i < n ? counts[i] : 0u, ws, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) scan_block_offsets(uint64_t* __restrict__ block_sums, int nblocks, uint64_t* __restrict__ total_out) {
+    __shared__ uint64_t ws[33];
     __shared__ uint64_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
+    for (int base = 0; base < nblocks; base += 1024) {
         int i = base + threadIdx.x;
-        uint64_t v = i < n ? counts[i] : 0u, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        uint64_t v = i < nblocks ? block_sums[i] : 0ull, total;
+        uint64_t excl = block_exclusive_scan_1024(v, ws, total) + carry;
+        if (i < nblocks) block_sums[i] = excl;
         __syncthreads();
-        if (threadIdx.x < 32) {
-            uint64_t w = warp_sums[threadIdx.x], z = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint64_t y = __shfl_up_sync(0xffffffffu, z, o);
-                if (threadIdx.x >= o) z += y;
-            }
-            warp_sums[threadIdx.x] = z - w;
-        }
-        __syncthreads();
-        uint64_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
-        if (i < n) offsets[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 0) carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) offsets[n] = carry;
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(1024) scan_apply(const uint32_t* __restrict__ counts, int n, const uint64_t* __restrict__ block_offsets,
+                                                   uint64_t* __restrict__ offsets) {
+    __shared__ uint64_t ws[33];
+    int i = blockIdx.x * 1024 + threadIdx.x;
+    uint64_t total;
+    uint64_t excl = block_exclusive_scan_1024(i < n ? counts[i] : 0u, ws, total);
+    if (i < n) offsets[i] = excl + block_offsets[blockIdx.x];
 }
 
 template <class S>
@@ -368,7 +445,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -456,10 +533,14 @@ AvnStatus Broadphase<S>::run() {
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
         sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>();
         sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
-        const int grid = std::min((n + 7) / 8, sm_count_ * 8);
-        sweep_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-        scan_counts<<<1, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, offsets_.as<uint64_t>());
-        launches_ += 4;
+        const int grid = std::min((n + SW_TILE - 1) / SW_TILE, sm_count_ * 16);
+        sweep_kernel<S, false><<<grid, SW_THREADS, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+        const int sblocks = (n + 1023) / 1024;
+        AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
+        scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
+        scan_block_offsets<<<1, 1024, 0, stream_>>>(block_sums_.as<uint64_t>(), sblocks, offsets_.as<uint64_t>() + n);
+        scan_apply<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>(), offsets_.as<uint64_t>());
+        launches_ += 6;
         // the pair count decides the size of the output buffers: one 8-byte readback
         AVN_CUDA(cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaStreamSynchronize(stream_));
@@ -468,7 +549,7 @@ AvnStatus Broadphase<S>::run() {
         if (total > 0) {
             AVN_CUDA(o_c1_.ensure(total * 4)); AVN_CUDA(o_c2_.ensure(total * 4)); AVN_CUDA(o_b1_.ensure(total * 4)); AVN_CUDA(o_b2_.ensure(total * 4));
             AVN_CUDA(o_fl_.ensure(total));
-            sweep_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
+            sweep_kernel<S, true><<<grid, SW_THREADS, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
                                                             o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
             ++launches_;
         }

@@ -60,7 +60,9 @@ struct DevSolver {
     // raw manifold columns
     const int* m_body1; const int* m_body2; const S* m_normal; const S* m_friction; const S* m_restitution; const S* m_tanvel;
     const uint32_t* m_point_off; const S* p_anchor1; const S* p_anchor2; const S* p_penetration; const S* p_normal_speed;
-    S* p_ws_normal; S* p_ws_tangent; S* p_normal_impulse;
+    const S* p_ws_normal; const S* p_ws_tangent;               // warm-start inputs (never written: every run restarts from them)
+    const S* p_in_normal_impulse;
+    S* p_out_ws_normal; S* p_out_ws_tangent; S* p_normal_impulse;  // store_contact_impulses outputs
     Vec4<S>* cst;
     int* any_restitution;
     // joints
@@ -517,11 +519,20 @@ __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m)
     const Vec4<S>* c = d.cst + m;
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
     int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = as_int(hidx.w);
+    if (np == 0) {  // skipped by prepare (both bodies non-dynamic): the reference leaves the ContactPoints untouched
+        for (uint32_t p = d.m_point_off[m]; p < d.m_point_off[m + 1]; ++p) {
+            d.p_out_ws_normal[p] = d.p_ws_normal[p];
+            d.p_out_ws_tangent[2 * p] = d.p_ws_tangent[2 * p];
+            d.p_out_ws_tangent[2 * p + 1] = d.p_ws_tangent[2 * p + 1];
+            d.p_normal_impulse[p] = d.p_in_normal_impulse ? d.p_in_normal_impulse[p] : S(0);
+        }
+        return;
+    }
     for (int k = 0; k < np; ++k) {
         Vec4<S> pc = ld4(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
-        d.p_ws_normal[p0 + k] = pc.x;
-        d.p_ws_tangent[2 * (p0 + k)] = (info & CI_TANGENT) ? pc.z : S(0);
-        d.p_ws_tangent[2 * (p0 + k) + 1] = (info & CI_TANGENT) ? pc.w : S(0);
+        d.p_out_ws_normal[p0 + k] = pc.x;
+        d.p_out_ws_tangent[2 * (p0 + k)] = (info & CI_TANGENT) ? pc.z : S(0);
+        d.p_out_ws_tangent[2 * (p0 + k) + 1] = (info & CI_TANGENT) ? pc.w : S(0);
         d.p_normal_impulse[p0 + k] = pc.y;
     }
 }

@@ -106,7 +106,7 @@ class Solver final : public SolverBase {
     DevBuf b_kind_, b_locked_, b_dom_, b_iflags_, b_pos_, b_rot_, b_lv_, b_av_, b_im_, b_iil_, b_com_, b_ld_, b_ad_, b_gs_, b_la_, b_aa_, b_ml_, b_ma_;
     DevBuf o_pos_, o_rot_, o_lv_, o_av_;
     DevBuf s_vel_, s_dlt_, s_inr_, s_itg_, s_pre_;
-    DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_;
+    DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_, p_nin_, p_own_, p_owt_;
     DevBuf c_planes_, c_flag_;
     DevBuf j_type_, j_index_, j_level_, j_planes_;
     DevBuf jcol_[AVN_JOINT_TYPE_COUNT][12], jb1_[AVN_JOINT_TYPE_COUNT], jb2_[AVN_JOINT_TYPE_COUNT], jle_[AVN_JOINT_TYPE_COUNT],
@@ -228,14 +228,12 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
         UP(p_pen_, mc->penetration, P, S, p_penetration);
         UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
-        // the two in/out columns are uploaded into buffers the kernels also write
-        AVN_CUDA(p_wn_.ensure(P * sizeof(S) + 16));
-        AVN_CUDA(cudaMemcpyAsync(p_wn_.p, mc->warm_start_normal_impulse, P * sizeof(S), cudaMemcpyHostToDevice, stream_));
-        d.p_ws_normal = p_wn_.as<S>();
-        AVN_CUDA(p_wt_.ensure(2 * P * sizeof(S) + 16));
-        AVN_CUDA(cudaMemcpyAsync(p_wt_.p, mc->warm_start_tangent_impulse, 2 * P * sizeof(S), cudaMemcpyHostToDevice, stream_));
-        d.p_ws_tangent = p_wt_.as<S>();
-        h2d_bytes_ += 3 * P * sizeof(S);
+        // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
+        UP(p_wn_, mc->warm_start_normal_impulse, P, S, p_ws_normal);
+        UP(p_wt_, mc->warm_start_tangent_impulse, 2 * P, S, p_ws_tangent);
+        UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
+        AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
+        AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
         AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
         d.p_normal_impulse = p_ni_.as<S>();
         AVN_CUDA(c_planes_.ensure(size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>)));
@@ -355,8 +353,8 @@ AvnStatus Solver<S>::download() {
     }
     if (have_m_) {
         const size_t P = hm_.point_count;
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_normal_impulse, dev_.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_tangent_impulse, dev_.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_normal_impulse, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_tangent_impulse, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hm_.normal_impulse, dev_.p_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
     if (have_j_) {
