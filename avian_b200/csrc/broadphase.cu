@@ -186,8 +186,12 @@ __global__ void gather_sorted(const uint32_t* __restrict__ order, int n, const S
 }
 
 // end[i] = first j > i with min.x[j] > max.x[i]  (the `break` of broad_phase.rs:390-392)
+// Intervals with more than SW_WIDE candidates (a ground slab spanning the whole scene) would serialise one warp of the
+// tiled sweep for the whole array; they go to a list that sweep_wide_kernel handles with one block per interval.
+constexpr int SW_WIDE = 4096;
 template <class S>
-__global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, int n, int* __restrict__ end) {
+__global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, int n, int* __restrict__ end, int* __restrict__ wide_list,
+                             int* __restrict__ wide_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     S m = maxx[i];
@@ -197,6 +201,7 @@ __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ m
         if (minx[mid] > m) hi = mid; else lo = mid + 1;
     }
     end[i] = lo;
+    if (lo - i - 1 > SW_WIDE) wide_list[atomicAdd(wide_count, 1)] = i;
 }
 
 __device__ __forceinline__ uint64_t hash64(uint64_t x) {
@@ -265,7 +270,10 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
         // union of the candidate ranges of the tile
         if (threadIdx.x == 0) s_jend = 0;
         __syncthreads();
-        if (threadIdx.x < tile_n) atomicMax(&s_jend, s.end[tile0 + threadIdx.x]);
+        if (threadIdx.x < tile_n) {
+            const int e = s.end[tile0 + threadIdx.x];
+            if (e - (tile0 + threadIdx.x) - 1 <= SW_WIDE) atomicMax(&s_jend, e);
+        }
         __syncthreads();
         const int j_begin = tile0 + 1, j_end = s_jend;
         // per-warp state of its SW_PER_WARP intervals (lane-uniform)
@@ -276,8 +284,9 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
 #pragma unroll
         for (int q = 0; q < SW_PER_WARP; ++q) {
             const int i = tile0 + warp * SW_PER_WARP + q;
-            const bool live = i < s.n;
+            bool live = i < s.n;
             my_end[q] = live ? s.end[i] : 0;
+            if (live && my_end[q] - i - 1 > SW_WIDE) { live = false; my_end[q] = 0; }  // wide: sweep_wide_kernel
             my_yz[q] = live ? s.yz[i] : mk4<S>(0, 0, 0, 0);
             running[q] = (EMIT && live) ? offsets[i] : 0ull;
             total[q] = 0;
@@ -330,10 +339,62 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
 #pragma unroll
             for (int q = 0; q < SW_PER_WARP; ++q) {
                 const int i = tile0 + warp * SW_PER_WARP + q;
-                if (i < s.n) counts[i] = total[q];
+                if (i < s.n && !(s.end[i] - i - 1 > SW_WIDE)) counts[i] = total[q];
             }
         }
         __syncthreads();
+    }
+}
+
+// one block per wide interval: 256 lanes stride its candidates; per round the 8 warp ballots are combined through
+// shared memory so positions stay in j order.
+template <class S, bool EMIT>
+__global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_constant__ Sweep<S> s, const int* __restrict__ wide_list,
+                                                                const int* __restrict__ wide_count, uint32_t* __restrict__ counts,
+                                                                const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
+                                                                uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
+                                                                uint8_t* __restrict__ out_flags) {
+    __shared__ uint32_t s_warp_cnt[SW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = *wide_count;
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const int i = wide_list[w], e = s.end[i];
+        const Vec4<S> yi = s.yz[i];
+        const uint4 mi = s.meta[i];
+        const uint32_t fi = s.flags[i];
+        uint64_t running = EMIT ? offsets[i] : 0ull;
+        uint32_t total = 0;
+        for (int j0 = i + 1; j0 < e; j0 += SW_THREADS) {
+            const int j = j0 + threadIdx.x;
+            bool ok = j < e;
+            if (ok) {
+                const Vec4<S> yj = s.yz[j];
+                ok = !(yi.x > yj.y || yi.y < yj.x) && !(yi.z > yj.w || yi.w < yj.z);
+            }
+            uint32_t pf = 0;
+            uint4 mj = make_uint4(0, 0, 0, 0);
+            if (ok) ok = pair_filters(s, mi, fi, j, pf, mj);
+            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t before = 0, round_total = 0;
+#pragma unroll
+            for (int k = 0; k < SW_WARPS; ++k) {
+                const uint32_t c = s_warp_cnt[k];
+                if (k < warp) before += c;
+                round_total += c;
+            }
+            if (EMIT && ok) {
+                const uint64_t pos = running + before + __popc(bal & ((1u << lane) - 1u));
+                if (pos < capacity) {
+                    out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
+                }
+            }
+            running += round_total;
+            total += round_total;
+            __syncthreads();
+        }
+        if (!EMIT && threadIdx.x == 0) counts[i] = total;
     }
 }
 
@@ -445,7 +506,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -528,19 +589,25 @@ AvnStatus Broadphase<S>::run() {
         gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
                                                                s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
                                                                s_flags_.as<uint8_t>());
-        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>());
+        AVN_CUDA(wide_.ensure((size_t(n) + 1) * 4));
+        int* wide_count = wide_.as<int>();
+        int* wide_list = wide_.as<int>() + 1;
+        AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
+        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>(), wide_list, wide_count);
         Sweep<S> sw;
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
         sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>();
         sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
         const int grid = std::min((n + SW_TILE - 1) / SW_TILE, sm_count_ * 16);
         sweep_kernel<S, false><<<grid, SW_THREADS, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+        sweep_wide_kernel<S, false><<<32, SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr,
+                                                                    nullptr, nullptr);
         const int sblocks = (n + 1023) / 1024;
         AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
         scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
         scan_block_offsets<<<1, 1024, 0, stream_>>>(block_sums_.as<uint64_t>(), sblocks, offsets_.as<uint64_t>() + n);
         scan_apply<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>(), offsets_.as<uint64_t>());
-        launches_ += 6;
+        launches_ += 7;
         // the pair count decides the size of the output buffers: one 8-byte readback
         AVN_CUDA(cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaStreamSynchronize(stream_));
@@ -551,7 +618,9 @@ AvnStatus Broadphase<S>::run() {
             AVN_CUDA(o_fl_.ensure(total));
             sweep_kernel<S, true><<<grid, SW_THREADS, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
                                                             o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
-            ++launches_;
+            sweep_wide_kernel<S, true><<<32, SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(),
+                                                                       o_c2_.as<uint32_t>(), o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+            launches_ += 2;
         }
     }
     cudaEventRecord(ev1_, stream_);

@@ -6,8 +6,10 @@
 //            inr[2*(B+1)]  = {inv_mass, flags, m00, m01}{m02, m11, m12, m22}   SolverBodyInertia (mod.rs:218-261)
 //            itg[2*B]      = {linear_increment.xyz, linear_damping_rhs}{angular_increment.xyz, angular_damping_rhs}
 //            slot B is SolverBody::DUMMY / SolverBodyInertia::DUMMY (static bodies, AVN_NO_BODY).
-//   contacts cst[20][Mpad] planes, manifold-major inside a plane so that a warp reads 32 consecutive Vec4:
-//            0 {n.xyz, friction} 1 {t1.xyz, restitution} 2 {tangent_velocity.xyz,-} 3 {body1, body2, info, first_point}
+//   contacts cst[20][Mpad] planes, slot-major inside a plane so that a warp reads 32 consecutive Vec4.  Manifold m of
+//            graph colour c lives in slot color_off[c] + (m - m_color_off[c]); every colour starts at a multiple of 32 so
+//            a warp never straddles two colours (padding slots have info = 0 = no points):
+//            0 {n.xyz, friction} 1 {t1.xyz, restitution} 2 {tangent_velocity.xyz,-} 3 {body1, body2, info, ranks}
 //            4+4k {anchor1.xyz, initial_separation} 5+4k {anchor2.xyz, normal effective_mass}
 //            6+4k {normal impulse, total normal impulse, tangent impulse.x, .y}   <- the only plane written in the loop
 //            7+4k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
@@ -20,7 +22,8 @@ namespace avn {
 
 enum { CP_N = 0, CP_T1 = 1, CP_TV = 2, CP_IDX = 3, CP_PT0 = 4, CP_PLANES = 4 + 4 * AVN_MAX_MANIFOLD_POINTS };
 // info lane of plane CP_IDX
-enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7 };
+enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7,
+       CI_VER1 = 1 << 8, CI_VER2 = 1 << 9 };  // VERx: side x is a versioned body (has a SolverBody) in wavefront mode
 // flags lane of inr[2*i]
 enum { BF_LOCK_MASK = 0x3f, BF_HAS_SOLVER_BODY = 1 << 8, BF_KINEMATIC = 1 << 9, BF_GYRO = 1 << 10, BF_DYNAMIC = 1 << 11,
        BF_CUSTOM_VEL = 1 << 12, BF_CUSTOM_POS = 1 << 13, BF_DOMINANCE_SHIFT = 16 };
@@ -45,7 +48,12 @@ struct Soft { S bias, mass_scale, impulse_scale; };
 template <class S>
 struct DevSolver {
     int B, M, P, Mpad, J, Jpad, n_levels;
-    int color_off[AVN_GRAPH_COLOR_COUNT + 1];
+    int m_color_off[AVN_GRAPH_COLOR_COUNT + 1];  // manifold index ranges per colour (ABI order)
+    int color_off[AVN_GRAPH_COLOR_COUNT + 1];    // SLOT ranges per colour, each start a multiple of 32; [24] = Mpad
+    int color_len[AVN_GRAPH_COLOR_COUNT];        // manifolds in the colour
+    int wave;                                    // 1: wavefront (dependency-counter) substep loop, 0: grid barriers
+    unsigned int* ver;                           // [B+1] per-body event counter (wavefront mode)
+    int* deg;                                    // [B+1] contact constraints touching the body (wavefront mode)
     int substeps, iters, rest_iters, fast_trig, match_contacts;
     S h, dt, max_overlap_speed, warm_coeff, rest_threshold, joint_force_rhs;
     S gx, gy, gz;
@@ -171,6 +179,13 @@ __device__ void prepare_body_item(const DevSolver<S>& d, int i) {
 // prepare_contact_constraints -> ContactConstraint::generate (solver/plugin.rs:363-448, contact/mod.rs:110-220,
 // normal_part.rs:39-112, tangent_part.rs:35-151)
 // ---------------------------------------------------------------------------------------------------------
+// manifold index (ABI order, grouped by colour) -> slot in the padded colour-major plane layout
+template <class S> __device__ __forceinline__ int slot_of_manifold(const DevSolver<S>& d, int m) {
+    int c = 0;
+    while (c < AVN_GRAPH_COLOR_COUNT - 1 && m >= d.m_color_off[c + 1]) ++c;
+    return d.color_off[c] + (m - d.m_color_off[c]);
+}
+
 template <class S>
 __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     int rb1 = d.m_body1[m], rb2 = d.m_body2[m];
@@ -180,11 +195,11 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     int f1 = as_int(i1a.y), f2 = as_int(i2a.y);
     uint32_t p0 = d.m_point_off[m], p1 = d.m_point_off[m + 1];
     int np = int(p1 - p0);
-    Vec4<S>* c = d.cst + m;
+    Vec4<S>* c = d.cst + slot_of_manifold(d, m);
     const size_t MP = size_t(d.Mpad);
     // skip contacts between two non-dynamic bodies (plugin.rs:415-418) and empty manifolds (:434)
     if ((!(f1 & BF_DYNAMIC) && !(f2 & BF_DYNAMIC)) || np <= 0) {
-        st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), 0), int_as(S(0), int(p0))));
+        st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), 0), int_as(S(0), 0)));
         return;
     }
     int dom1 = (f1 >> BF_DOMINANCE_SHIFT) << 16 >> 16, dom2 = (f2 >> BF_DOMINANCE_SHIFT) << 16 >> 16;  // sign-extend i16
@@ -195,6 +210,8 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     if (rel > 0 || !(f1 & BF_HAS_SOLVER_BODY)) info |= CI_ZERO1;
     if (rel < 0 || !(f2 & BF_HAS_SOLVER_BODY)) info |= CI_ZERO2;
     if (rel != 0) info |= CI_NONDYN;
+    if (f1 & BF_HAS_SOLVER_BODY) info |= CI_VER1;
+    if (f2 & BF_HAS_SOLVER_BODY) info |= CI_VER2;
     V3<S> mass_sum = in1.inv_mass + in2.inv_mass;
     V3<S> n = ldv3(d.m_normal, m);
     // compute_tangent_directions (contact/mod.rs:427-449): LinearVelocity components of the rigid bodies
@@ -216,7 +233,7 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     st4(&c[CP_N * MP], mk4<S>(n.x, n.y, n.z, friction));
     st4(&c[CP_T1 * MP], mk4<S>(t1.x, t1.y, t1.z, restitution));
     st4(&c[CP_TV * MP], mk4<S>(tv.x, tv.y, tv.z, S(0)));
-    st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), info), int_as(S(0), int(p0))));
+    st4(&c[CP_IDX * MP], mk4<S>(int_as(S(0), b1), int_as(S(0), b2), int_as(S(0), info), int_as(S(0), 0)));
     bool warm = d.match_contacts != 0;
     for (int k = 0; k < np; ++k) {
         uint32_t p = p0 + k;
@@ -259,41 +276,116 @@ __device__ __forceinline__ void apply_impulse(V3<S>& v1, V3<S>& w1, V3<S>& v2, V
     w2 = w2 + smul(in2.ii, cross(r2, imp));
 }
 
-template <class S, int PASS>
-__device__ __forceinline__ void contact_item(const DevSolver<S>& d, int m) {
+// ---- wavefront mode: per-body event counters replace the grid barriers between colours ---------------------------
+// Every body with a SolverBody owns a counter ver[b] that counts the work items that have touched it, in the exact order
+// the reference's schedule touches it.  Within one substep that order is (k = number of contact constraints on the body,
+// r = rank of a constraint among them in colour-major order):
+//     integrate_velocities | warm_start r=0..k-1 | (biased solve r=0..k-1) x iters | integrate_positions | relax r=0..k-1
+// An item may run when the counters of its bodies equal its position in their sequences, and bumps them when done.
+// Items are handed to warps in the global schedule order, all warps are co-resident (cooperative launch), and an item
+// only ever waits for items that precede it in that order, so the earliest unfinished item can always run: no deadlock.
+struct WaveStep { int substep, iters; };
+__device__ __forceinline__ unsigned events_per_substep(int k, int iters) { return 2u + unsigned(2 + iters) * unsigned(k); }
+enum { WV_IV = 0, WV_WARM = 1, WV_SOLVE = 2, WV_IP = 3, WV_RELAX = 4 };
+// position of an item in its body's event sequence
+__device__ __forceinline__ unsigned wave_event(int kind, int it, int s, int iters, int k, int r) {
+    unsigned base = unsigned(s) * events_per_substep(k, iters);
+    switch (kind) {
+        case WV_IV: return base;
+        case WV_WARM: return base + 1u + r;
+        case WV_SOLVE: return base + 1u + unsigned(1 + it) * k + r;
+        case WV_IP: return base + 1u + unsigned(1 + iters) * k;
+        default: return base + 2u + unsigned(1 + iters) * k + r;
+    }
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned* p, unsigned v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// mutable body / impulse data is read through L2 only in wavefront mode (other SMs write it while this kernel runs)
+__device__ __forceinline__ Vec4<float> ld4_cg(const Vec4<float>* p) {
+    float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    return mk4<float>(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ Vec4<double> ld4_cg(const Vec4<double>* p) {
+    double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return mk4<double>(a.x, a.y, b.x, b.y);
+}
+template <bool WAVE, class S> __device__ __forceinline__ Vec4<S> ldm(const Vec4<S>* p) { return WAVE ? ld4_cg(p) : ld4(p); }
+
+// warp-synchronous wait: all 32 lanes of the warp wait until every lane's two counters have reached their targets
+// A watchdog bounds the spin (a schedule bug must not hang the device): after ~4M polls the warp gives up and raises
+// *watchdog, which the host turns into an error.
+__device__ __forceinline__ void wave_wait(const unsigned* ver, bool need1, int b1, unsigned e1, bool need2, int b2, unsigned e2, int* watchdog) {
+    for (unsigned spins = 0;; ++spins) {
+        bool ok = (!need1 || ld_relaxed(ver + b1) == e1) && (!need2 || ld_relaxed(ver + b2) == e2);
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (spins > (1u << 22)) { *watchdog = 1; break; }
+    }
+    __threadfence();  // acquire: the loads below must observe what the publishers wrote before bumping the counters
+}
+__device__ __forceinline__ void wave_publish(unsigned* ver, bool need1, int b1, unsigned e1, bool need2, int b2, unsigned e2) {
+    __threadfence();  // release: this item's stores are visible before the counters move
+    if (need1) st_relaxed(ver + b1, e1 + 1u);
+    if (need2) st_relaxed(ver + b2, e2 + 1u);
+}
+
+// `slot` indexes the padded colour-major planes.  WAVE = false: barrier mode (a padding slot returns at once).
+// WAVE = true: every lane of the warp must call this (warp-collective wait); `ws` carries the position in the schedule.
+template <class S, int PASS, bool WAVE = false>
+__device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, int wave_substep = 0, int wave_it = 0) {
     const size_t MP = size_t(d.Mpad);
-    Vec4<S>* c = d.cst + m;
+    Vec4<S>* c = d.cst + slot;
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
     const int info = as_int(hidx.z);
     const int np = info & CI_NP_MASK;
-    if (np == 0) return;
+    if (!WAVE && np == 0) return;
     const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
-    // ---- issue every load up front (independent 128-bit loads -> memory-level parallelism)
-    Vec4<S> hn = ld4(&c[CP_N * MP]);
-    Vec4<S> ht1 = ld4(&c[CP_T1 * MP]);
-    Vec4<S> htv = mk4<S>(0, 0, 0, 0);
-    if (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) htv = ld4(&c[CP_TV * MP]);
-    Vec4<S> l1 = ld4(&d.vel[2 * b1]), a1 = ld4(&d.vel[2 * b1 + 1]);
-    Vec4<S> l2 = ld4(&d.vel[2 * b2]), a2 = ld4(&d.vel[2 * b2 + 1]);
+    // ---- issue every load up front (independent 128-bit loads -> memory-level parallelism).  In wavefront mode the
+    //      immutable part (planes written by prepare only, inertia) is fetched BEFORE waiting on the counters.
+    Vec4<S> hn = mk4<S>(0, 0, 0, 0), ht1 = hn, htv = hn;
     BodyInertia<S> in1 = zero_inertia<S>(), in2 = zero_inertia<S>();
-    if (!(info & CI_ZERO1)) in1 = unpack_inertia(ld4(&d.inr[2 * b1]), ld4(&d.inr[2 * b1 + 1]));
-    if (!(info & CI_ZERO2)) in2 = unpack_inertia(ld4(&d.inr[2 * b2]), ld4(&d.inr[2 * b2 + 1]));
-    Vec4<S> dp1, dq1, dp2, dq2;
-    if (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) {
-        dp1 = ld4(&d.dlt[2 * b1]); dq1 = ld4(&d.dlt[2 * b1 + 1]);
-        dp2 = ld4(&d.dlt[2 * b2]); dq2 = ld4(&d.dlt[2 * b2 + 1]);
-    }
     Vec4<S> PA[AVN_MAX_MANIFOLD_POINTS], PB[AVN_MAX_MANIFOLD_POINTS], PC[AVN_MAX_MANIFOLD_POINTS], PD[AVN_MAX_MANIFOLD_POINTS];
+    constexpr bool SOLVE = (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX);
+    if (np != 0) {
+        hn = ld4(&c[CP_N * MP]);
+        ht1 = ld4(&c[CP_T1 * MP]);
+        if (SOLVE) htv = ld4(&c[CP_TV * MP]);
+        if (!(info & CI_ZERO1)) in1 = unpack_inertia(ld4(&d.inr[2 * b1]), ld4(&d.inr[2 * b1 + 1]));
+        if (!(info & CI_ZERO2)) in2 = unpack_inertia(ld4(&d.inr[2 * b2]), ld4(&d.inr[2 * b2 + 1]));
 #pragma unroll
-    for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
-        if (k < np) {
-            Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
-            PA[k] = ld4(&cp[0]);
-            PB[k] = ld4(&cp[MP]);
-            PC[k] = ld4(&cp[2 * MP]);
-            if (PASS == PASS_RESTITUTION || ((PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX) && (info & CI_TANGENT))) PD[k] = ld4(&cp[3 * MP]);
+        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+            if (k < np) {
+                Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
+                PA[k] = ld4(&cp[0]);
+                PB[k] = ld4(&cp[MP]);
+                if (PASS == PASS_RESTITUTION || (SOLVE && (info & CI_TANGENT))) PD[k] = ld4(&cp[3 * MP]);
+            }
         }
     }
+    unsigned e1 = 0, e2 = 0;
+    const bool ver1 = WAVE && np != 0 && (info & CI_VER1), ver2 = WAVE && np != 0 && (info & CI_VER2);
+    if (WAVE) {
+        const int rk = as_int(hidx.w);
+        const int kind = PASS == PASS_WARM ? WV_WARM : (PASS == PASS_SOLVE_BIAS ? WV_SOLVE : WV_RELAX);
+        e1 = wave_event(kind, wave_it, wave_substep, d.iters, (rk >> 8) & 0xff, rk & 0xff);
+        e2 = wave_event(kind, wave_it, wave_substep, d.iters, (rk >> 24) & 0xff, (rk >> 16) & 0xff);
+        wave_wait(d.ver, ver1, b1, e1, ver2, b2, e2, d.any_restitution + 1);
+        if (np == 0) return;  // padding slot: nothing to do (after the warp-collective wait)
+    }
+    // ---- mutable state: body velocities / deltas and the accumulated impulses
+    Vec4<S> l1 = ldm<WAVE>(&d.vel[2 * b1]), a1 = ldm<WAVE>(&d.vel[2 * b1 + 1]);
+    Vec4<S> l2 = ldm<WAVE>(&d.vel[2 * b2]), a2 = ldm<WAVE>(&d.vel[2 * b2 + 1]);
+    Vec4<S> dp1, dq1, dp2, dq2;
+    if (SOLVE) {
+        dp1 = ldm<WAVE>(&d.dlt[2 * b1]); dq1 = ldm<WAVE>(&d.dlt[2 * b1 + 1]);
+        dp2 = ldm<WAVE>(&d.dlt[2 * b2]); dq2 = ldm<WAVE>(&d.dlt[2 * b2 + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
+        if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
     V3<S> v1 = xyz(l1), w1 = xyz(a1), v2 = xyz(l2), w2 = xyz(a2);
     const V3<S> n = xyz(hn), t1 = xyz(ht1);
     const V3<S> t2 = cross(t1, n);  // tangent_directions(): [tangent1, tangent1 x normal] (contact/mod.rs:411-421)
@@ -414,17 +506,26 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int m) {
         st4(&d.vel[2 * b2], mk4<S>(v2.x, v2.y, v2.z, S(0)));
         st4(&d.vel[2 * b2 + 1], mk4<S>(w2.x, w2.y, w2.z, S(0)));
     }
+    if (WAVE) wave_publish(d.ver, ver1, b1, e1, ver2, b2, e2);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // integrate_velocities + clamp_velocities (integrator/mod.rs:343-391, 467-500)
 // ---------------------------------------------------------------------------------------------------------
-template <class S>
-__device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, int i) {
-    Vec4<S> ia = ld4(&d.inr[2 * i]);
-    int f = as_int(ia.y);
-    if (!(f & BF_HAS_SOLVER_BODY)) return;
-    Vec4<S> l = ld4(&d.vel[2 * i]), a = ld4(&d.vel[2 * i + 1]);
+// WAVE: every lane of the warp calls this (i may be >= B: padding); `s` = substep index
+template <class S, bool WAVE = false>
+__device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, int i, int s = 0) {
+    const bool in_range = i < d.B;
+    int f = 0;
+    if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
+    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    unsigned e = 0;
+    if (WAVE) {
+        if (live) e = wave_event(WV_IV, 0, s, d.iters, d.deg[i], 0);
+        wave_wait(d.ver, live, i, e, false, 0, 0u, d.any_restitution + 1);
+    }
+    if (!live) return;
+    Vec4<S> l = ldm<WAVE>(&d.vel[2 * i]), a = ldm<WAVE>(&d.vel[2 * i + 1]);
     V3<S> v = xyz(l), w = xyz(a);
     bool touched = false;
     if (!(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC)) {
@@ -435,7 +536,7 @@ __device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, i
         w = w + xyz(ai);
         if (f & BF_GYRO) {
             // solve_gyroscopic_torque (integrator/mod.rs:403-460)
-            Vec4<S> dq4 = ld4(&d.dlt[2 * i + 1]);
+            Vec4<S> dq4 = ldm<WAVE>(&d.dlt[2 * i + 1]);
             Q4<S> dq; dq.x = dq4.x; dq.y = dq4.y; dq.z = dq4.z; dq.w = dq4.w;
             Q4<S> rot = qmul(dq, ldq(d.rotation, i));
             Sym3<S> il;
@@ -469,21 +570,65 @@ __device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, i
         st4(&d.vel[2 * i], mk4<S>(v.x, v.y, v.z, S(0)));
         st4(&d.vel[2 * i + 1], mk4<S>(w.x, w.y, w.z, S(0)));
     }
+    if (WAVE) wave_publish(d.ver, true, i, e, false, 0, 0u);
 }
 
 // integrate_positions (integrator/mod.rs:503-535)
-template <class S>
-__device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, int i) {
-    Vec4<S> ia = ld4(&d.inr[2 * i]);
-    int f = as_int(ia.y);
-    if (!(f & BF_HAS_SOLVER_BODY) || (f & BF_CUSTOM_POS)) return;
-    Vec4<S> l = ld4(&d.vel[2 * i]), a = ld4(&d.vel[2 * i + 1]);
-    Vec4<S> dp = ld4(&d.dlt[2 * i]), dq4 = ld4(&d.dlt[2 * i + 1]);
+template <class S, bool WAVE = false>
+__device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, int i, int s = 0) {
+    const bool in_range = i < d.B;
+    int f = 0;
+    if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
+    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    unsigned e = 0;
+    if (WAVE) {
+        if (live) e = wave_event(WV_IP, 0, s, d.iters, d.deg[i], 0);
+        wave_wait(d.ver, live, i, e, false, 0, 0u, d.any_restitution + 1);
+    }
+    if (!live) return;
+    if (f & BF_CUSTOM_POS) {
+        if (WAVE) wave_publish(d.ver, true, i, e, false, 0, 0u);
+        return;
+    }
+    Vec4<S> l = ldm<WAVE>(&d.vel[2 * i]), a = ldm<WAVE>(&d.vel[2 * i + 1]);
+    Vec4<S> dp = ldm<WAVE>(&d.dlt[2 * i]), dq4 = ldm<WAVE>(&d.dlt[2 * i + 1]);
     V3<S> ndp = xyz(dp) + xyz(l) * d.h;
     Q4<S> dq; dq.x = dq4.x; dq.y = dq4.y; dq.z = dq4.z; dq.w = dq4.w;
     Q4<S> nq = qmul(q_from_scaled_axis(xyz(a) * d.h, d.fast_trig != 0), dq);
     st4(&d.dlt[2 * i], mk4<S>(ndp.x, ndp.y, ndp.z, S(0)));
     st4(&d.dlt[2 * i + 1], mk4<S>(nq.x, nq.y, nq.z, nq.w));
+    if (WAVE) wave_publish(d.ver, true, i, e, false, 0, 0u);
+}
+
+// ---- wavefront prologue: ranks of every constraint on its two bodies (colour by colour), then pack {r1,k1,r2,k2} ------
+// Within one colour a versioned body appears at most once (constraint_graph.rs:4-6), so the per-colour pass is race-free.
+template <class S>
+__device__ __forceinline__ void wave_rank_item(const DevSolver<S>& d, int slot) {
+    const size_t MP = size_t(d.Mpad);
+    Vec4<S>* c = d.cst + slot;
+    Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
+    const int info = as_int(hidx.z);
+    if ((info & CI_NP_MASK) == 0) return;
+    const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
+    int r1 = 0, r2 = 0;
+    if (info & CI_VER1) { r1 = d.deg[b1]; d.deg[b1] = r1 + 1; }
+    if (info & CI_VER2) { r2 = d.deg[b2]; d.deg[b2] = r2 + 1; }
+    hidx.w = int_as(S(0), (r1 & 0xff) | ((r2 & 0xff) << 16));
+    st4(&c[CP_IDX * MP], hidx);
+}
+template <class S>
+__device__ __forceinline__ void wave_pack_item(const DevSolver<S>& d, int slot) {
+    const size_t MP = size_t(d.Mpad);
+    Vec4<S>* c = d.cst + slot;
+    Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
+    const int info = as_int(hidx.z);
+    if ((info & CI_NP_MASK) == 0) return;
+    const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
+    int rk = as_int(hidx.w);
+    if (info & CI_VER1) rk |= (d.deg[b1] & 0xff) << 8;
+    if (info & CI_VER2) rk |= (d.deg[b2] & 0xff) << 24;
+    hidx.w = int_as(S(0), rk);
+    st4(&c[CP_IDX * MP], hidx);
 }
 
 // writeback_solver_bodies (solver_body/plugin.rs:255-284)
@@ -516,9 +661,9 @@ __device__ __forceinline__ void writeback_body_item(const DevSolver<S>& d, int i
 template <class S>
 __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m) {
     const size_t MP = size_t(d.Mpad);
-    const Vec4<S>* c = d.cst + m;
+    const Vec4<S>* c = d.cst + slot_of_manifold(d, m);
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
-    int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = as_int(hidx.w);
+    int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = int(d.m_point_off[m]);
     if (np == 0) {  // skipped by prepare (both bodies non-dynamic): the reference leaves the ContactPoints untouched
         for (uint32_t p = d.m_point_off[m]; p < d.m_point_off[m + 1]; ++p) {
             d.p_out_ws_normal[p] = d.p_ws_normal[p];

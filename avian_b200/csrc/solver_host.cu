@@ -39,6 +39,7 @@ class Solver final : public SolverBase {
         }
         const char* mode = getenv("AVN_LAUNCH_MODE");
         if (mode && !strcmp(mode, "phases")) use_mega_ = false;
+        if (mode && !strcmp(mode, "barrier")) use_wave_ = false;   // megakernel with grid barriers between colours
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_megakernel<S>, MEGA_BLOCK, 0) == cudaSuccess && per_sm > 0)
             mega_grid_ = per_sm * sm_count_;
@@ -79,15 +80,15 @@ class Solver final : public SolverBase {
     }
     template <int OP> void launch_contact_pass() {
         const int* off = dev_.color_off;
-        launch_phase<OP>(off[AVN_COLOR_OVERFLOW], off[AVN_COLOR_OVERFLOW + 1] - off[AVN_COLOR_OVERFLOW], true);
-        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) launch_phase<OP>(off[c], off[c + 1] - off[c]);
+        launch_phase<OP>(off[AVN_COLOR_OVERFLOW], dev_.color_len[AVN_COLOR_OVERFLOW], true);
+        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) launch_phase<OP>(off[c], dev_.color_len[c]);
     }
 
     cudaStream_t stream_;
     ErrorSink* err_;
     uint32_t cfg_flags_;
     int sm_count_ = 148;
-    bool coop_ok_ = false, use_mega_ = true;
+    bool coop_ok_ = false, use_mega_ = true, use_wave_ = true;
     int mega_grid_ = 0;
     cudaEvent_t ev_[EV_COUNT];
     AvnTimings tm_{};
@@ -107,7 +108,7 @@ class Solver final : public SolverBase {
     DevBuf o_pos_, o_rot_, o_lv_, o_av_;
     DevBuf s_vel_, s_dlt_, s_inr_, s_itg_, s_pre_;
     DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_, p_nin_, p_own_, p_owt_;
-    DevBuf c_planes_, c_flag_;
+    DevBuf c_planes_, c_flag_, w_ver_, w_deg_;
     DevBuf j_type_, j_index_, j_level_, j_planes_;
     DevBuf jcol_[AVN_JOINT_TYPE_COUNT][12], jb1_[AVN_JOINT_TYPE_COUNT], jb2_[AVN_JOINT_TYPE_COUNT], jle_[AVN_JOINT_TYPE_COUNT],
         jde_[AVN_JOINT_TYPE_COUNT], jdl_[AVN_JOINT_TYPE_COUNT], jda_[AVN_JOINT_TYPE_COUNT], jfo_[AVN_JOINT_TYPE_COUNT], jto_[AVN_JOINT_TYPE_COUNT];
@@ -198,10 +199,12 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     AVN_CUDA(s_inr_.ensure(state_bytes)); d.inr = s_inr_.as<Vec4<S>>();
     AVN_CUDA(s_itg_.ensure(state_bytes)); d.itg = s_itg_.as<Vec4<S>>();
     AVN_CUDA(s_pre_.ensure(state_bytes)); d.pre = s_pre_.as<Vec4<S>>();
+    AVN_CUDA(w_ver_.ensure((B + 1) * sizeof(unsigned))); d.ver = w_ver_.as<unsigned>();
+    AVN_CUDA(w_deg_.ensure((B + 1) * sizeof(int))); d.deg = w_deg_.as<int>();
     hb_ = *bc;
     // ---- manifolds
     have_m_ = mc && mc->count > 0;
-    AVN_CUDA(c_flag_.ensure(sizeof(int)));
+    AVN_CUDA(c_flag_.ensure(2 * sizeof(int)));  // [0] any restitution, [1] wavefront watchdog
     d.any_restitution = c_flag_.as<int>();
     if (have_m_) {
         const size_t M = mc->count, P = mc->point_count;
@@ -215,8 +218,18 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         if (mc->point_offsets[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
         d.M = int(M);
         d.P = int(P);
-        d.Mpad = int((M + 31) & ~size_t(31));
-        for (int c = 0; c <= AVN_GRAPH_COLOR_COUNT; ++c) d.color_off[c] = int(mc->color_offsets[c]);
+        {   // padded slot layout: every colour starts at a multiple of 32
+            int slot = 0;
+            for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) {
+                d.m_color_off[c] = int(mc->color_offsets[c]);
+                d.color_off[c] = slot;
+                d.color_len[c] = int(mc->color_offsets[c + 1] - mc->color_offsets[c]);
+                slot += (d.color_len[c] + 31) & ~31;
+            }
+            d.m_color_off[AVN_GRAPH_COLOR_COUNT] = int(M);
+            d.color_off[AVN_GRAPH_COLOR_COUNT] = slot;
+            d.Mpad = std::max(slot, 32);
+        }
         UP(m_b1_, mc->body1, M, int, m_body1);
         UP(m_b2_, mc->body2, M, int, m_body2);
         UP(m_n_, mc->normal, 3 * M, S, m_normal);
@@ -291,15 +304,26 @@ AvnStatus Solver<S>::run() {
     if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run before avn_solver_upload");
     launches_ = 0;
     cudaEventRecord(ev_[EV_RUN0], stream_);
-    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, sizeof(int), stream_));
-    const DevSolver<S>& d = dev_;
+    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int), stream_));
     bool mega = use_mega_ && coop_ok_;
+    // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour
+    dev_.wave = (mega && use_wave_ && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
+    if (dev_.M > 0) {
+        // padding slots must read as "no points": clear the index plane before prepare fills the live slots
+        AVN_CUDA(cudaMemsetAsync(dev_.cst + size_t(CP_IDX) * dev_.Mpad, 0, size_t(dev_.Mpad) * sizeof(Vec4<S>), stream_));
+    }
+    if (dev_.wave) {
+        AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
+        AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, (size_t(dev_.B) + 1) * sizeof(int), stream_));
+    }
+    const DevSolver<S>& d = dev_;
     if (mega) {
         void* args[] = {(void*)&dev_};
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_megakernel<S>, dim3(mega_grid_), dim3(MEGA_BLOCK), args, 0, stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             mega = false;  // fall through to phase launches (still the same CUDA arithmetic)
+            dev_.wave = 0;
         } else {
             ++launches_;
             cudaEventRecord(ev_[EV_PREP], stream_);
@@ -364,8 +388,11 @@ AvnStatus Solver<S>::download() {
             if (n && dev_.jtorque[t]) AVN_CUDA(cudaMemcpyAsync(hj_.types[t].torque, dev_.jtorque[t], 3 * n * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         }
     }
+    int flags_host[2] = {0, 0};
+    AVN_CUDA(cudaMemcpyAsync(flags_host, dev_.any_restitution, sizeof flags_host, cudaMemcpyDeviceToHost, stream_));
     cudaEventRecord(ev_[EV_D2H1], stream_);
     AVN_CUDA(cudaStreamSynchronize(stream_));
+    if (flags_host[1]) return err_->fail(AVN_ERR_CUDA, "wavefront scheduler watchdog fired: results are invalid (set AVN_LAUNCH_MODE=barrier)");
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ev_[EV_H2D0], ev_[EV_H2D1]) == cudaSuccess) tm_.h2d_ms = ms;
     if (cudaEventElapsedTime(&ms, ev_[EV_RUN0], ev_[EV_PREP]) == cudaSuccess) tm_.prepare_ms = ms;
@@ -377,7 +404,7 @@ AvnStatus Solver<S>::download() {
     tm_.contact_constraint_count = uint32_t(dev_.M);
     tm_.joint_levels = uint32_t(dev_.n_levels);
     uint32_t ac = 0;
-    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) ac += dev_.color_off[c + 1] > dev_.color_off[c];
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) ac += dev_.color_len[c] > 0;
     tm_.active_colors = ac;
     return AVN_OK;
 }

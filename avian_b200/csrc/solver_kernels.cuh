@@ -22,7 +22,8 @@ constexpr int MEGA_BLOCK = 128, MEGA_BLOCKS_PER_SM = 3;
 
 enum PhaseOp {
     OP_PREPARE_BODY = 0, OP_PREPARE_CONSTRAINT, OP_PREPARE_JOINT, OP_INTEGRATE_VEL, OP_INTEGRATE_POS, OP_WARM, OP_SOLVE_BIAS,
-    OP_RELAX, OP_RESTITUTION, OP_SOLVE_JOINT, OP_PROJECT_VEL, OP_DAMP_JOINT, OP_WRITEBACK_BODY, OP_STORE_IMPULSE, OP_JOINT_FORCE
+    OP_RELAX, OP_RESTITUTION, OP_SOLVE_JOINT, OP_PROJECT_VEL, OP_DAMP_JOINT, OP_WRITEBACK_BODY, OP_STORE_IMPULSE, OP_JOINT_FORCE,
+    OP_WAVE_RANK, OP_WAVE_PACK
 };
 
 template <class S, int OP>
@@ -42,6 +43,8 @@ __device__ __forceinline__ void run_item(const DevSolver<S>& d, int i) {
     else if (OP == OP_WRITEBACK_BODY) writeback_body_item(d, i);
     else if (OP == OP_STORE_IMPULSE) store_impulse_item(d, i);
     else if (OP == OP_JOINT_FORCE) joint_force_item(d, i);
+    else if (OP == OP_WAVE_RANK) wave_rank_item(d, i);
+    else if (OP == OP_WAVE_PACK) wave_pack_item(d, i);
 }
 
 // one launch per phase: items [begin, begin+count).  `serial` = the overflow colour: one thread, list order.
@@ -70,16 +73,54 @@ __device__ __noinline__ void grid_serial(const DevSolver<S>& d, int begin, int c
 // (solver/plugin.rs:461-479, 553-572, 643-668)
 template <class S, int OP>
 __device__ __forceinline__ void grid_contact_pass(const DevSolver<S>& d, cg::grid_group& grid) {
-    const int ov = d.color_off[AVN_COLOR_OVERFLOW], ovn = d.color_off[AVN_COLOR_OVERFLOW + 1] - ov;
+    const int ov = d.color_off[AVN_COLOR_OVERFLOW], ovn = d.color_len[AVN_COLOR_OVERFLOW];
     if (ovn > 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) grid_serial<S, OP>(d, ov, ovn);
         grid.sync();
     }
     for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) {
-        const int b = d.color_off[c], n = d.color_off[c + 1] - b;
+        const int b = d.color_off[c], n = d.color_len[c];
         if (n <= 0) continue;
         grid_phase<S, OP>(d, b, n);
         grid.sync();
+    }
+}
+
+// ---- wavefront substep loop ------------------------------------------------------------------------------------------
+// The whole substep schedule as ONE sequence of 32-item chunks; warp w takes chunks w, w + W, w + 2W, ... in order and
+// every item waits on its bodies' event counters instead of a grid barrier (solver_dev.cuh "wavefront mode").  Chunks
+// never straddle two phases or two colours because body ranges and colour slot ranges are padded to multiples of 32.
+template <class S, int PASS>
+__device__ __noinline__ void wave_contact_chunk(const DevSolver<S>& d, int slot, int s, int it) { contact_item<S, PASS, true>(d, slot, s, it); }
+template <class S>
+__device__ __noinline__ void wave_iv_chunk(const DevSolver<S>& d, int i, int s) { integrate_velocity_item<S, true>(d, i, s); }
+template <class S>
+__device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s) { integrate_position_item<S, true>(d, i, s); }
+
+template <class S>
+__device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int body_chunks = (d.B + 31) >> 5, slot_chunks = d.Mpad >> 5;
+    const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
+    const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
+    const long long total = per_substep * d.substeps;
+    for (long long g = warp_id; g < total; g += warps) {
+        const int s = int(g / per_substep);
+        long long r = g - (long long)s * per_substep;
+        if (r < body_chunks) { wave_iv_chunk<S>(d, int(r) * 32 + lane, s); continue; }
+        r -= body_chunks;
+        if (r < (long long)(1 + d.iters) * slot_chunks) {
+            const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * 32 + lane;
+            if (pass == 0) wave_contact_chunk<S, PASS_WARM>(d, slot, s, 0);
+            else wave_contact_chunk<S, PASS_SOLVE_BIAS>(d, slot, s, pass - 1);
+            continue;
+        }
+        r -= (long long)(1 + d.iters) * slot_chunks;
+        if (r < body_chunks) { wave_ip_chunk<S>(d, int(r) * 32 + lane, s); continue; }
+        r -= body_chunks;
+        wave_contact_chunk<S, PASS_RELAX>(d, int(r) * 32 + lane, s, 0);
     }
 }
 
@@ -93,7 +134,19 @@ __global__ void __launch_bounds__(MEGA_BLOCK, MEGA_BLOCKS_PER_SM) step_megakerne
     grid_phase<S, OP_PREPARE_JOINT>(d, 0, d.J);
     grid.sync();
     // ---- run_substep_schedule (solver/schedule.rs:194-213)
-    for (int sub = 0; sub < d.substeps; ++sub) {
+    if (d.wave) {
+        // ranks of every constraint on its bodies, colour by colour in schedule order (deg[] was zeroed by the host)
+        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) {
+            if (d.color_len[c] <= 0) continue;
+            grid_phase<S, OP_WAVE_RANK>(d, d.color_off[c], d.color_len[c]);
+            grid.sync();
+        }
+        grid_phase<S, OP_WAVE_PACK>(d, 0, d.Mpad);
+        grid.sync();
+        wave_substep_loop<S>(d);
+        grid.sync();
+    }
+    for (int sub = 0; sub < (d.wave ? 0 : d.substeps); ++sub) {
         grid_phase<S, OP_INTEGRATE_VEL>(d, 0, d.B);
         grid.sync();
         if (d.M > 0) {

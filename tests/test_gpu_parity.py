@@ -133,23 +133,61 @@ def test_dominance_kinematic_and_overflow_colour(gpu_ctx):
     assert_manifolds_close(mg, mo, what="dominance: ")
 
 
-def test_launch_modes_agree(gpu_ctx):
-    """the persistent megakernel and the one-launch-per-phase path are the same arithmetic: bit-identical results"""
-    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(5, 5, 5, brick=True), steps=2, substeps=4)
-    bg, mg = b.copy(), m.copy()
-    _gpu_step(gpu_ctx, prm, bg, mg)
-    assert gpu_ctx.timings()["kernel_launches"] == 1, "the megakernel path should be ONE launch per step"
-    os.environ["AVN_LAUNCH_MODE"] = "phases"
+def _run_in_mode(mode, prm, b, m, j=None):
+    """a fresh context with AVN_LAUNCH_MODE=mode ('' = default: megakernel + wavefront scheduling)"""
+    if mode:
+        os.environ["AVN_LAUNCH_MODE"] = mode
     try:
-        with api.Context(device=0) as ctx2:
-            bp, mp = b.copy(), m.copy()
-            ctx2.solver_step(prm, bp, mp)
-            assert ctx2.timings()["kernel_launches"] > 10
+        with api.Context(device=0) as ctx:
+            bb, mm = b.copy(), m.copy()
+            ctx.solver_step(prm, bb, mm, j)
+            return bb, mm, ctx.timings()
     finally:
-        del os.environ["AVN_LAUNCH_MODE"]
+        os.environ.pop("AVN_LAUNCH_MODE", None)
+
+
+@pytest.mark.parametrize("iters", [1, 2])
+def test_launch_modes_agree(gpu_ctx, iters):
+    """wavefront megakernel == barrier megakernel == one launch per phase: the same arithmetic in the same per-body
+    order, so the results must be BIT-identical"""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(7, 6, 7, brick=True), steps=2, substeps=4)
+    prm.solver_iterations = iters
+    bw, mw, tw = _run_in_mode("", prm, b, m)
+    bb, mb, tb = _run_in_mode("barrier", prm, b, m)
+    bp, mp, tp = _run_in_mode("phases", prm, b, m)
+    assert tw["kernel_launches"] == 1 and tb["kernel_launches"] == 1, "megakernel paths are ONE launch per step"
+    assert tp["kernel_launches"] > 10
+    for other, what in ((bb, "barrier"), (bp, "phases")):
+        for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
+            assert np.array_equal(getattr(bw, name), getattr(other, name)), (what, name)
+    assert np.array_equal(mw.warm_start_normal_impulse, mb.warm_start_normal_impulse)
+    assert np.array_equal(mw.warm_start_tangent_impulse, mp.warm_start_tangent_impulse)
+    assert np.array_equal(mw.normal_impulse, mp.normal_impulse)
+    bo, mo = b.copy(), m.copy()
+    oracle_lib.solver_step(prm, bo, mo)
+    assert_bodies_close(bw, bo, what=f"iters={iters}: ")
+
+
+def test_wavefront_equals_barrier_at_headline_size(gpu_ctx):
+    """BASELINE-size property: on the 100k-cube stack (no oracle at this size in seconds) the wavefront schedule and the
+    barrier schedule give bit-identical bodies and impulses, and the step stays finite with non-negative normal impulses
+    inside the friction cone."""
+    sc = scenes.cube_stack(51, 40, 50, brick=True)
+    w = plugins.World(sc, plugins.PhysicsPlugins(gpu_ctx), substeps=8)
+    w.step()
+    w.broad_phase(); m = w.narrow_phase()
+    prm, b = w.params, w.bodies
+    assert m.count > 300_000
+    bw, mw, _ = _run_in_mode("", prm, b, m)
+    bb, mb, _ = _run_in_mode("barrier", prm, b, m)
     for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
-        assert np.array_equal(getattr(bg, name), getattr(bp, name)), name
-    assert np.array_equal(mg.warm_start_normal_impulse, mp.warm_start_normal_impulse)
+        assert np.isfinite(getattr(bw, name)).all()
+        assert np.array_equal(getattr(bw, name), getattr(bb, name)), name
+    assert np.array_equal(mw.normal_impulse, mb.normal_impulse)
+    lam_n = mw.warm_start_normal_impulse
+    lam_t = np.linalg.norm(mw.warm_start_tangent_impulse, axis=1)
+    mu = np.repeat(mw.friction, np.diff(mw.point_offsets))
+    assert (lam_n >= 0).all() and (lam_t <= mu * lam_n * (1 + 1e-5) + 1e-7).all()
 
 
 def test_upload_run_download_split_is_repeatable(gpu_ctx):
