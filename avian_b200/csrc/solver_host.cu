@@ -40,8 +40,18 @@ class Solver final : public SolverBase {
         const char* mode = getenv("AVN_LAUNCH_MODE");
         if (mode && !strcmp(mode, "phases")) use_mega_ = false;
         if (mode && !strcmp(mode, "barrier")) use_wave_ = false;   // megakernel with grid barriers between colours
+        // register budget of the persistent kernel: 65536 / (128 threads * blocks per SM); more resident warps hide more
+        // latency, fewer registers spill more.  AVN_MEGA_BPS overrides the default for experiments.
+        const char* bps = getenv("AVN_MEGA_BPS");
+        mega_bps_ = bps ? atoi(bps) : 3;
+        switch (mega_bps_) {
+            case 4: mega_fn_ = (const void*)step_megakernel<S, 4>; break;
+            case 5: mega_fn_ = (const void*)step_megakernel<S, 5>; break;
+            case 6: mega_fn_ = (const void*)step_megakernel<S, 6>; break;
+            default: mega_bps_ = 3; mega_fn_ = (const void*)step_megakernel<S, 3>; break;
+        }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_megakernel<S>, MEGA_BLOCK, 0) == cudaSuccess && per_sm > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_fn_, MEGA_BLOCK, 0) == cudaSuccess && per_sm > 0)
             mega_grid_ = per_sm * sm_count_;
         else
             coop_ok_ = false;
@@ -89,7 +99,8 @@ class Solver final : public SolverBase {
     uint32_t cfg_flags_;
     int sm_count_ = 148;
     bool coop_ok_ = false, use_mega_ = true, use_wave_ = true;
-    int mega_grid_ = 0;
+    int mega_grid_ = 0, mega_bps_ = 3;
+    const void* mega_fn_ = nullptr;
     cudaEvent_t ev_[EV_COUNT];
     AvnTimings tm_{};
     uint32_t launches_ = 0;
@@ -319,7 +330,7 @@ AvnStatus Solver<S>::run() {
     const DevSolver<S>& d = dev_;
     if (mega) {
         void* args[] = {(void*)&dev_};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)step_megakernel<S>, dim3(mega_grid_), dim3(MEGA_BLOCK), args, 0, stream_);
+        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, 0, stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             mega = false;  // fall through to phase launches (still the same CUDA arithmetic)

@@ -18,7 +18,7 @@
 namespace avn {
 namespace cg = cooperative_groups;
 
-constexpr int MEGA_BLOCK = 128, MEGA_BLOCKS_PER_SM = 3;
+constexpr int MEGA_BLOCK = 128;  // blocks per SM is a template parameter of the megakernel (register budget = 65536 / (128 * BPS))
 
 enum PhaseOp {
     OP_PREPARE_BODY = 0, OP_PREPARE_CONSTRAINT, OP_PREPARE_JOINT, OP_INTEGRATE_VEL, OP_INTEGRATE_POS, OP_WARM, OP_SOLVE_BIAS,
@@ -124,8 +124,8 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     }
 }
 
-template <class S>
-__global__ void __launch_bounds__(MEGA_BLOCK, MEGA_BLOCKS_PER_SM) step_megakernel(const __grid_constant__ DevSolver<S> d) {
+template <class S, int BPS>
+__global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_constant__ DevSolver<S> d) {
     cg::grid_group grid = cg::this_grid();
     // ---- prepare
     grid_phase<S, OP_PREPARE_BODY>(d, 0, d.B + 1);

@@ -116,9 +116,10 @@ def pin_columns(ctx, obj):
     return obj
 
 
-def run_gpu(args, rank: int, world: int, local_rank: int):
+def run_gpu(args, info):
     import torch
-    from avian_b200 import api
+    from avian_b200 import api, parallel
+    rank, world, local_rank = info.rank, info.world, info.local_rank
     torch.cuda.set_device(local_rank)
     ctx = api.Context(device=local_rank)
     sc, prm, bodies, man, aabbs = build_snapshot(args.scene, args.settle, ctx)
@@ -128,8 +129,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     b0, m0 = bodies.copy(), man.copy()     # the frozen snapshot (the step writes results into bodies/man in place)
 
     def barrier():
-        if world > 1:
-            torch.distributed.barrier()
+        parallel.barrier(info)
         torch.cuda.synchronize()
 
     def restore():
@@ -186,10 +186,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     restore()
 
     # max over ranks
-    times = torch.tensor([dev_ms, wall_resident * 1e3, wall_e2e * 1e3, mega_ms, bp_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
-    dev_ms, wall_res_ms, wall_e2e_ms, mega_ms, bp_ms = [float(x) for x in times.tolist()]
+    dev_ms, wall_res_ms, wall_e2e_ms, mega_ms, bp_ms = parallel.reduce_max(
+        [dev_ms, wall_resident * 1e3, wall_e2e * 1e3, mega_ms, bp_ms], info, device="cuda")
     if rank != 0:
         ctx.close()
         return None
@@ -288,19 +286,17 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from avian_b200 import parallel
+    info = parallel.rank_info()
     if args.impl == "reference":
-        res = run_reference(args, rank, world)
+        res = run_reference(args, info.rank, info.world)
     else:
-        if world > 1:
+        if info.world > 1:
             import torch
-            import torch.distributed as dist
-            torch.cuda.set_device(local_rank)
-            dist.init_process_group(backend="nccl")
-        res = run_gpu(args, rank, world, local_rank)
-        if world > 1:
+            torch.cuda.set_device(info.local_rank)
+            parallel.init(backend="nccl")
+        res = run_gpu(args, info)
+        if info.world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
     if res is not None:
