@@ -15,6 +15,8 @@
 //            7+4k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
 //   joints   jnt[14][Jpad] planes in level-schedule order (see JP_* below).
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "../../include/avian_b200.h"
 #include "avn_math.cuh"
 
@@ -332,6 +334,24 @@ __device__ __forceinline__ void wave_publish(unsigned* ver, bool need1, int b1, 
     if (need2) st_relaxed(ver + b2, e2 + 1u);
 }
 
+// ---- shared-memory staging of the immutable per-point constraint rows -------------------------------------------------
+// Each thread copies its manifold's {anchor1|sep0}, {anchor2|m_eff}, {K|normal_speed} rows (up to 12 x 16 B) from the planes
+// into its own column of a dynamic shared-memory tile with cp.async (LDGSTS: no registers, no local-memory spills), waits
+// for its own copies only, and reads a row right where a point needs it.  Layout: row r of thread t at stage[r * T + t]
+// (consecutive threads -> consecutive 16-byte words: conflict-free).  The copies fly while the thread waits on its
+// dependency counters (wavefront mode) or on the body gathers (barrier mode).
+constexpr int STAGE_ROWS = 3 * AVN_MAX_MANIFOLD_POINTS;
+template <class S> __device__ __forceinline__ Vec4<S>* stage_base() {
+    extern __shared__ __align__(32) unsigned char avn_stage_raw[];
+    return reinterpret_cast<Vec4<S>*>(avn_stage_raw);
+}
+__device__ __forceinline__ void stage_copy(Vec4<float>* dst, const Vec4<float>* src) { __pipeline_memcpy_async(dst, src, 16); }
+__device__ __forceinline__ void stage_copy(Vec4<double>* dst, const Vec4<double>* src) {
+    __pipeline_memcpy_async(dst, src, 16);
+    __pipeline_memcpy_async(reinterpret_cast<char*>(dst) + 16, reinterpret_cast<const char*>(src) + 16, 16);
+}
+template <class S> __host__ __device__ constexpr size_t stage_bytes(int threads) { return size_t(STAGE_ROWS) * threads * sizeof(Vec4<S>); }
+
 // `slot` indexes the padded colour-major planes.  WAVE = false: barrier mode (a padding slot returns at once).
 // WAVE = true: every lane of the warp must call this (warp-collective wait); `ws` carries the position in the schedule.
 template <class S, int PASS, bool WAVE = false>
@@ -347,8 +367,13 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     //      immutable part (planes written by prepare only, inertia) is fetched BEFORE waiting on the counters.
     Vec4<S> hn = mk4<S>(0, 0, 0, 0), ht1 = hn, htv = hn;
     BodyInertia<S> in1 = zero_inertia<S>(), in2 = zero_inertia<S>();
-    Vec4<S> PA[AVN_MAX_MANIFOLD_POINTS], PB[AVN_MAX_MANIFOLD_POINTS], PC[AVN_MAX_MANIFOLD_POINTS], PD[AVN_MAX_MANIFOLD_POINTS];
+    Vec4<S> PC[AVN_MAX_MANIFOLD_POINTS];
     constexpr bool SOLVE = (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX);
+    Vec4<S>* const stage = stage_base<S>() + threadIdx.x;   // this thread's column; row r at stage[r * T]
+    const int T = blockDim.x;
+#define ROW_A(k) stage[(3 * (k) + 0) * T]
+#define ROW_B(k) stage[(3 * (k) + 1) * T]
+#define ROW_D(k) stage[(3 * (k) + 2) * T]
     if (np != 0) {
         hn = ld4(&c[CP_N * MP]);
         ht1 = ld4(&c[CP_T1 * MP]);
@@ -359,12 +384,13 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
             if (k < np) {
                 Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
-                PA[k] = ld4(&cp[0]);
-                PB[k] = ld4(&cp[MP]);
-                if (PASS == PASS_RESTITUTION || (SOLVE && (info & CI_TANGENT))) PD[k] = ld4(&cp[3 * MP]);
+                stage_copy(&ROW_A(k), &cp[0]);
+                stage_copy(&ROW_B(k), &cp[MP]);
+                if (PASS == PASS_RESTITUTION || (SOLVE && (info & CI_TANGENT))) stage_copy(&ROW_D(k), &cp[3 * MP]);
             }
         }
     }
+    __pipeline_commit();
     unsigned e1 = 0, e2 = 0;
     const bool ver1 = WAVE && np != 0 && (info & CI_VER1), ver2 = WAVE && np != 0 && (info & CI_VER2);
     if (WAVE) {
@@ -386,6 +412,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
     for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
         if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
+    __pipeline_wait_prior(0);  // this thread's staged rows have landed (only the issuing thread reads them)
     V3<S> v1 = xyz(l1), w1 = xyz(a1), v2 = xyz(l2), w2 = xyz(a2);
     const V3<S> n = xyz(hn), t1 = xyz(ht1);
     const V3<S> t2 = cross(t1, n);  // tangent_directions(): [tangent1, tangent1 x normal] (contact/mod.rs:411-421)
@@ -395,7 +422,8 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
             if (k < np) {
-                V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
+                V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
                 S tx = (info & CI_TANGENT) ? PC[k].z : S(0), ty = (info & CI_TANGENT) ? PC[k].w : S(0);
                 V3<S> p = d.warm_coeff * ((PC[k].x * n + tx * t1) + ty * t2);
                 apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, p);
@@ -410,14 +438,15 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
             if (k < np) {
-                V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
+                V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
                 V3<S> rr1 = qrot(q1, r1), rr2 = qrot(q2, r2);
                 V3<S> dsep = delta_translation + (rr2 - rr1);
-                S separation = dot(dsep, n) + PA[k].w;
+                S separation = dot(dsep, n) + PAk.w;
                 V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
                 // ContactNormalPart::solve_impulse (normal_part.rs:116-166)
                 S vn = dot(relv, n);
-                S meff = PB[k].w, acc = PC[k].x;
+                S meff = PBk.w, acc = PC[k].x;
                 S impulse;
                 if (separation > S(0)) {
                     impulse = -meff * (vn + separation / d.h);
@@ -442,14 +471,15 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
             for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
                 if (k < np) {
-                    V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                    const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), PDk = ROW_D(k);
+                    V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
                     V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
                     // ContactTangentPart::solve_impulse (tangent_part.rs:155-244)
                     S limit = friction * PC[k].x;
                     relv = relv + surf;
                     S ts1 = dot(relv, t1), ts2 = dot(relv, t2);
                     S t11 = ts1 * ts1, t22 = ts2 * ts2, t12 = ts1 * ts2;
-                    S inv = (t11 * PD[k].x + t22 * PD[k].y) + t12 * PD[k].z;
+                    S inv = (t11 * PDk.x + t22 * PDk.y) + t12 * PDk.z;
                     S em = (t11 + t22) * (S(1) / inv);
                     V3<S> imp = zero3<S>();
                     if (avn_finite(em)) {
@@ -478,11 +508,12 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
             for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
                 if (k < np) {
-                    if (PD[k].w > -d.rest_threshold || PC[k].y == S(0)) continue;
-                    V3<S> r1 = xyz(PA[k]), r2 = xyz(PB[k]);
+                    const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), PDk = ROW_D(k);
+                    if (PDk.w > -d.rest_threshold || PC[k].y == S(0)) continue;
+                    V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
                     V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
                     S vn = dot(relv, n);
-                    S impulse = -PB[k].w * (vn + e * PD[k].w);
+                    S impulse = -PBk.w * (vn + e * PDk.w);
                     S new_impulse = avn_max(PC[k].x + impulse, S(0));
                     impulse = new_impulse - PC[k].x;
                     PC[k].x = new_impulse;
@@ -507,6 +538,9 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         st4(&d.vel[2 * b2 + 1], mk4<S>(w2.x, w2.y, w2.z, S(0)));
     }
     if (WAVE) wave_publish(d.ver, ver1, b1, e1, ver2, b2, e2);
+#undef ROW_A
+#undef ROW_B
+#undef ROW_D
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -51,7 +51,8 @@ class Solver final : public SolverBase {
             default: mega_bps_ = 3; mega_fn_ = (const void*)step_megakernel<S, 3>; break;
         }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_fn_, MEGA_BLOCK, 0) == cudaSuccess && per_sm > 0)
+        if (cudaFuncSetAttribute(mega_fn_, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stage_bytes<S>(MEGA_BLOCK))) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_fn_, MEGA_BLOCK, stage_bytes<S>(MEGA_BLOCK)) == cudaSuccess && per_sm > 0)
             mega_grid_ = per_sm * sm_count_;
         else
             coop_ok_ = false;
@@ -85,7 +86,10 @@ class Solver final : public SolverBase {
     template <int OP> void launch_phase(int begin, int count, bool serial = false) {
         if (count <= 0) return;
         int grid = serial ? 1 : std::min((count + kBlock - 1) / kBlock, sm_count_ * 8);
-        phase_kernel<S, OP><<<grid, kBlock, 0, stream_>>>(dev_, begin, count, serial ? 1 : 0);
+        const bool contact_op = OP == OP_WARM || OP == OP_SOLVE_BIAS || OP == OP_RELAX || OP == OP_RESTITUTION;
+        const size_t smem = contact_op ? stage_bytes<S>(kBlock) : 0;   // staging tile of contact_item
+        if (smem > 48 * 1024) cudaFuncSetAttribute(phase_kernel<S, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        phase_kernel<S, OP><<<grid, kBlock, smem, stream_>>>(dev_, begin, count, serial ? 1 : 0);
         ++launches_;
     }
     template <int OP> void launch_contact_pass() {
@@ -330,7 +334,7 @@ AvnStatus Solver<S>::run() {
     const DevSolver<S>& d = dev_;
     if (mega) {
         void* args[] = {(void*)&dev_};
-        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, 0, stream_);
+        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, stage_bytes<S>(MEGA_BLOCK), stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             mega = false;  // fall through to phase launches (still the same CUDA arithmetic)
