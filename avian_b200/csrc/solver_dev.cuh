@@ -287,6 +287,16 @@ __device__ __forceinline__ void apply_impulse(V3<S>& v1, V3<S>& w1, V3<S>& v2, V
 // Items are handed to warps in the global schedule order, all warps are co-resident (cooperative launch), and an item
 // only ever waits for items that precede it in that order, so the earliest unfinished item can always run: no deadlock.
 struct WaveStep { int substep, iters; };
+// Optional latency trace of the wavefront items (build with -DAVN_WAVE_TRACE; scripts/wave_trace.py): per-warp SM-cycle sums of
+// [0] dependency wait  [1] acquire fence + mutable loads + staged rows  [2] arithmetic  [3] stores + release fence + publish,
+// [4] item count.  The buffer is 8 unsigned long long counters behind the two int flags of any_restitution.
+#ifdef AVN_WAVE_TRACE
+#define AVN_TRACE_T(var) const long long var = clock64()
+#define AVN_TRACE_ADD(d, i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>((d).any_restitution + 2) + (i), (unsigned long long)(v)); } while (0)
+#else
+#define AVN_TRACE_T(var)
+#define AVN_TRACE_ADD(d, i, v)
+#endif
 __device__ __forceinline__ unsigned events_per_substep(int k, int iters) { return 2u + unsigned(2 + iters) * unsigned(k); }
 enum { WV_IV = 0, WV_WARM = 1, WV_SOLVE = 2, WV_IP = 3, WV_RELAX = 4 };
 // position of an item in its body's event sequence
@@ -398,10 +408,13 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         const int kind = PASS == PASS_WARM ? WV_WARM : (PASS == PASS_SOLVE_BIAS ? WV_SOLVE : WV_RELAX);
         e1 = wave_event(kind, wave_it, wave_substep, d.iters, (rk >> 8) & 0xff, rk & 0xff);
         e2 = wave_event(kind, wave_it, wave_substep, d.iters, (rk >> 24) & 0xff, (rk >> 16) & 0xff);
+        AVN_TRACE_T(t_w0);
         wave_wait(d.ver, ver1, b1, e1, ver2, b2, e2, d.any_restitution + 1);
+        AVN_TRACE_ADD(d, 0, clock64() - t_w0);
         if (np == 0) return;  // padding slot: nothing to do (after the warp-collective wait)
     }
     // ---- mutable state: body velocities / deltas and the accumulated impulses
+    AVN_TRACE_T(t_l0);
     Vec4<S> l1 = ldm<WAVE>(&d.vel[2 * b1]), a1 = ldm<WAVE>(&d.vel[2 * b1 + 1]);
     Vec4<S> l2 = ldm<WAVE>(&d.vel[2 * b2]), a2 = ldm<WAVE>(&d.vel[2 * b2 + 1]);
     Vec4<S> dp1, dq1, dp2, dq2;
@@ -413,6 +426,15 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
         if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
     __pipeline_wait_prior(0);  // this thread's staged rows have landed (only the issuing thread reads them)
+#ifdef AVN_WAVE_TRACE
+    if (WAVE) {  // force the loads to complete here so the segments separate cleanly
+        S sink = l1.x + a1.x + l2.x + a2.x + PC[0].x;
+        if (SOLVE) sink += dq1.x + dq2.x;
+        if (sink == S(1.2345e33)) d.any_restitution[1] = 2;
+    }
+    AVN_TRACE_T(t_c0);
+    if (WAVE) AVN_TRACE_ADD(d, 1, t_c0 - t_l0);
+#endif
     V3<S> v1 = xyz(l1), w1 = xyz(a1), v2 = xyz(l2), w2 = xyz(a2);
     const V3<S> n = xyz(hn), t1 = xyz(ht1);
     const V3<S> t2 = cross(t1, n);  // tangent_directions(): [tangent1, tangent1 x normal] (contact/mod.rs:411-421)
@@ -524,6 +546,11 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         }
     }
     // ---- write back: impulses (plane 6+4k) and the velocities of the non-dominant sides
+#ifdef AVN_WAVE_TRACE
+    if (WAVE && (v1.x + v2.x + w1.x + w2.x) == S(1.2345e33)) d.any_restitution[1] = 2;
+    AVN_TRACE_T(t_s0);
+    if (WAVE) AVN_TRACE_ADD(d, 2, t_s0 - t_c0);
+#endif
     if (PASS != PASS_WARM) {
 #pragma unroll
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
@@ -538,6 +565,9 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         st4(&d.vel[2 * b2 + 1], mk4<S>(w2.x, w2.y, w2.z, S(0)));
     }
     if (WAVE) wave_publish(d.ver, ver1, b1, e1, ver2, b2, e2);
+#ifdef AVN_WAVE_TRACE
+    if (WAVE) { AVN_TRACE_ADD(d, 3, clock64() - t_s0); AVN_TRACE_ADD(d, 4, 1); }
+#endif
 #undef ROW_A
 #undef ROW_B
 #undef ROW_D

@@ -219,7 +219,7 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     hb_ = *bc;
     // ---- manifolds
     have_m_ = mc && mc->count > 0;
-    AVN_CUDA(c_flag_.ensure(2 * sizeof(int)));  // [0] any restitution, [1] wavefront watchdog
+    AVN_CUDA(c_flag_.ensure(2 * sizeof(int) + 8 * sizeof(unsigned long long)));  // [0] any restitution, [1] wavefront watchdog, then the optional trace counters
     d.any_restitution = c_flag_.as<int>();
     if (have_m_) {
         const size_t M = mc->count, P = mc->point_count;
@@ -319,7 +319,7 @@ AvnStatus Solver<S>::run() {
     if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run before avn_solver_upload");
     launches_ = 0;
     cudaEventRecord(ev_[EV_RUN0], stream_);
-    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int), stream_));
+    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
     bool mega = use_mega_ && coop_ok_;
     // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour
     dev_.wave = (mega && use_wave_ && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
@@ -407,7 +407,15 @@ AvnStatus Solver<S>::download() {
     AVN_CUDA(cudaMemcpyAsync(flags_host, dev_.any_restitution, sizeof flags_host, cudaMemcpyDeviceToHost, stream_));
     cudaEventRecord(ev_[EV_D2H1], stream_);
     AVN_CUDA(cudaStreamSynchronize(stream_));
-    if (flags_host[1]) return err_->fail(AVN_ERR_CUDA, "wavefront scheduler watchdog fired: results are invalid (set AVN_LAUNCH_MODE=barrier)");
+#ifdef AVN_WAVE_TRACE
+    {
+        unsigned long long tr[8];
+        cudaMemcpy(tr, dev_.any_restitution + 2, sizeof tr, cudaMemcpyDeviceToHost);
+        if (tr[4]) fprintf(stderr, "[avn wave trace] item-warps %llu  avg cycles: wait %.0f  load %.0f  compute %.0f  store+publish %.0f\n", tr[4],
+                           double(tr[0]) / tr[4], double(tr[1]) / tr[4], double(tr[2]) / tr[4], double(tr[3]) / tr[4]);
+    }
+#endif
+    if (flags_host[1] == 1) return err_->fail(AVN_ERR_CUDA, "wavefront scheduler watchdog fired: results are invalid (set AVN_LAUNCH_MODE=barrier)");
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ev_[EV_H2D0], ev_[EV_H2D1]) == cudaSuccess) tm_.h2d_ms = ms;
     if (cudaEventElapsedTime(&ms, ev_[EV_RUN0], ev_[EV_PREP]) == cudaSuccess) tm_.prepare_ms = ms;

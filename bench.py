@@ -35,11 +35,19 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 SCENES = {
-    # name: (nx, ny, nz, substeps)
-    "stack100k": (51, 40, 50, 8),   # BASELINE configs[2] (headline): exactly 100 000 cubes
-    "stack10k": (23, 20, 22, 8),    # BASELINE configs[1]-sized: 10 000 cubes
-    "stack1k": (11, 10, 10, 8),
+    # name: (builder, substeps, default settle steps)
+    "stack100k": (lambda sc: sc.cube_stack(51, 40, 50, brick=True), 8, 2),   # BASELINE configs[2] (headline): exactly 100 000 cubes
+    "stack10k": (lambda sc: sc.cube_stack(23, 20, 22, brick=True), 8, 2),    # BASELINE configs[1]-sized: ~10 000 cubes
+    "stack1k": (lambda sc: sc.cube_stack(11, 10, 10, brick=True), 8, 2),
+    "ragdolls5k": (lambda sc: sc.ragdoll_field(5000, pitch=3.0, drop_height=0.2), 8, 30),  # BASELINE configs[3]: 85 000 bodies, 80 000 joints
+    "ragdolls500": (lambda sc: sc.ragdoll_field(500, pitch=3.0, drop_height=0.2), 8, 30),
 }
+
+
+def metric_name(scene: str) -> str:
+    label = {"stack100k": "100k-cube stack", "stack10k": "10k-cube stack", "stack1k": "1k-cube stack", "ragdolls5k": "5k-ragdoll field",
+             "ragdolls500": "500-ragdoll field"}[scene]
+    return f"physics steps/sec on {label} (broad phase + solver stage per step)"
 
 
 def algorithmic_bytes(B: int, M: int, P: int, substeps: int, scalar_bytes: int = 4) -> dict:
@@ -90,8 +98,8 @@ def build_snapshot(scene_name: str, settle: int, ctx=None):
     With ctx (GPU arm) the pipeline's hot path runs on the GPU; without it the snapshot is built from the scene's
     initial state only (settle must be 0) so that the CPU arm never needs the GPU."""
     from avian_b200 import plugins, scenes
-    nx, ny, nz, substeps = SCENES[scene_name]
-    sc = scenes.cube_stack(nx, ny, nz, brick=True)
+    builder, substeps, _ = SCENES[scene_name]
+    sc = builder(scenes)
     if ctx is not None:
         w = plugins.World(sc, plugins.PhysicsPlugins(ctx), substeps=substeps)
     else:
@@ -105,7 +113,7 @@ def build_snapshot(scene_name: str, settle: int, ctx=None):
     # the steady-state broad-phase input: every current pair is already in the contact graph
     mn, mx = w.aabb_min, w.aabb_max
     aabbs = w.pipeline.intervals(w.bodies, mn, mx, with_existing=True)
-    return sc, w.params, w.bodies, man, aabbs
+    return sc, w.params, w.bodies, man, aabbs, w.joints
 
 
 def pin_columns(ctx, obj):
@@ -122,8 +130,10 @@ def run_gpu(args, info):
     rank, world, local_rank = info.rank, info.world, info.local_rank
     torch.cuda.set_device(local_rank)
     ctx = api.Context(device=local_rank)
-    sc, prm, bodies, man, aabbs = build_snapshot(args.scene, args.settle, ctx)
+    sc, prm, bodies, man, aabbs, joints = build_snapshot(args.scene, args.settle, ctx)
+    prm.solver_iterations = args.solver_iterations
     B, M, P = bodies.count, man.count, int(man.penetration.shape[0])
+    J = 0 if joints is None else joints.count
     pin_columns(ctx, bodies); pin_columns(ctx, man); pin_columns(ctx, aabbs)
     pairs_out = api.PairList.empty(1 << 16)
     b0, m0 = bodies.copy(), man.copy()     # the frozen snapshot (the step writes results into bodies/man in place)
@@ -140,7 +150,7 @@ def run_gpu(args, info):
 
     # ---- resident arm: upload once, run K times ---------------------------------------------------------------------
     sampler = ClockSampler(local_rank); sampler.start()
-    ctx.solver_upload(prm, bodies, man)
+    ctx.solver_upload(prm, bodies, man, joints)
     ctx.broadphase_upload(aabbs)
     for _ in range(args.warmup):
         ctx.broadphase_run(); ctx.solver_run()
@@ -164,13 +174,13 @@ def run_gpu(args, info):
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step ------------------------------------------------
     for _ in range(max(1, args.warmup // 2)):
-        ctx.broadphase(aabbs); ctx.solver_step(prm, bodies, man); restore()
+        ctx.broadphase(aabbs); ctx.solver_step(prm, bodies, man, joints); restore()
     barrier()
     t0 = time.perf_counter()
     e2e_dev_ms = 0.0
     for _ in range(args.steps):
         ctx.broadphase_upload(aabbs); ctx.broadphase_run(); ctx.broadphase_download(pairs_out)
-        ctx.solver_step(prm, bodies, man)
+        ctx.solver_step(prm, bodies, man, joints)
     barrier()
     wall_e2e = time.perf_counter() - t0
     # keep the GPU under the same load until the sampler has a few readings (nvidia-smi takes ~100 ms per call)
@@ -196,6 +206,8 @@ def run_gpu(args, info):
     value = world * K / (dev_ms / 1e3)
     e2e_value = world * K / (wall_e2e_ms / 1e3)
     alg = algorithmic_bytes(B, M, P, int(prm.substeps), sb)
+    if J:
+        alg["step"] += int(prm.substeps) * (300 * J + 100 * B) * (sb / 4.0)   # XPBD joint pass + velocity projection, SURVEY 8d
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -210,12 +222,12 @@ def run_gpu(args, info):
         except Exception:
             traffic = None
     result = {
-        "metric": "physics steps/sec on 100k-cube stack (broad phase + solver stage per step)", "value": value, "unit": "steps/s",
+        "metric": metric_name(args.scene), "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sc.name}: {B - 1} unit cubes on a ground slab, one coupled pile per GPU, f32, {int(prm.substeps)} substeps, "
-                               f"reference solver semantics (1 biased + 1 relax pass per substep)",
-                   "bodies": B, "manifolds": M, "contact_points": P, "colliders": int(aabbs.collider.shape[0]),
+        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, one scene per GPU, f32, {int(prm.substeps)} substeps, "
+                               f"reference solver semantics (1 warm start + {int(prm.solver_iterations)} biased + 1 relax pass per substep)",
+                   "bodies": B, "manifolds": M, "contact_points": P, "joints": J, "solver_iterations": int(prm.solver_iterations), "colliders": int(aabbs.collider.shape[0]),
                    "existing_pairs": 0 if aabbs.existing_pairs is None else int(aabbs.existing_pairs.shape[0]), "new_pairs_per_step": new_pairs,
                    "parallelism": "1 pile per GPU (island sharding), no data-path collective", "settle_steps": args.settle,
                    "l2": "inputs larger than L2: constraint planes + columns > 126 MB per step", "timing": "CUDA events on the library stream, max over ranks"},
@@ -228,12 +240,12 @@ def run_gpu(args, info):
         "breakdown_ms": {"broad_phase": bp_ms / K, "solver_stage": mega_ms / K, "resident_wall": wall_res_ms / K},
     }
     if not args.no_cpu and world >= 1:
-        result["cpu_baseline"] = cpu_arm(args, prm, b0, m0, aabbs, sample_steps=args.cpu_steps)
+        result["cpu_baseline"] = cpu_arm(args, prm, b0, m0, aabbs, sample_steps=args.cpu_steps, joints=joints)
     ctx.close()
     return result
 
 
-def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int) -> dict:
+def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int, joints=None) -> dict:
     """The oracle (restated reference path, colour-parallel like the reference) on the host cores."""
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib
@@ -245,7 +257,7 @@ def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int) -> dict:
         a = api.Aabbs(**{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in aabbs.__dict__.items()})
         t0 = time.perf_counter()
         oracle_lib.broadphase(a, capacity=1 << 16)
-        oracle_lib.solver_step(prm, b, m, None, threads=threads)
+        oracle_lib.solver_step(prm, b, m, None if joints is None else joints.copy(), threads=threads)
         t_total += time.perf_counter() - t0
     return {"value": sample_steps / t_total, "unit": "steps/s", "cores": threads, "kind": "port",
             "sample": f"{sample_steps} full steps of the same snapshot (SAP single-threaded + solver stage colour-parallel on {threads} threads)",
@@ -256,17 +268,19 @@ def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (Rust cannot be built here)."""
     if rank != 0:
         return None
-    sc, prm, bodies, man, aabbs = build_snapshot(args.scene, 0, None)
+    sc, prm, bodies, man, aabbs, joints = build_snapshot(args.scene, args.settle if args.settle <= 4 else 0, None)
+    prm.solver_iterations = args.solver_iterations
     for _ in range(min(args.warmup, 1)):
-        cpu_arm(args, prm, bodies, man, aabbs, 1)
+        cpu_arm(args, prm, bodies, man, aabbs, 1, joints)
     steps = max(1, min(args.steps, args.cpu_steps_max))
-    cb = cpu_arm(args, prm, bodies, man, aabbs, steps)
+    cb = cpu_arm(args, prm, bodies, man, aabbs, steps, joints)
     B, M, P = bodies.count, man.count, int(man.penetration.shape[0])
     return {
-        "impl": "reference", "metric": "physics steps/sec on 100k-cube stack (broad phase + solver stage per step)", "value": cb["value"], "unit": "steps/s",
+        "impl": "reference", "metric": metric_name(args.scene), "value": cb["value"], "unit": "steps/s",
         "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sc.name}: {B - 1} unit cubes, f32, {int(prm.substeps)} substeps", "bodies": B, "manifolds": M, "contact_points": P,
+        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, f32, {int(prm.substeps)} substeps", "bodies": B, "manifolds": M, "contact_points": P,
+                   "joints": 0 if joints is None else joints.count, "settle_steps": args.settle,
                    "note": "restated Avian CPU path (C++ oracle), not Avian itself: no Rust toolchain in this image"},
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -279,12 +293,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="stack100k", choices=sorted(SCENES))
-    ap.add_argument("--settle", type=int, default=2, help="full pipeline steps before the snapshot is frozen")
+    ap.add_argument("--settle", type=int, default=None, help="full pipeline steps before the snapshot is frozen (default: per scene)")
+    ap.add_argument("--solver-iterations", type=int, default=1, help="EXTENSION: biased solve passes per substep (reference semantics = 1)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="bounded CPU sample (full steps) for cpu_baseline")
     ap.add_argument("--cpu-steps-max", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.settle is None:
+        args.settle = SCENES[args.scene][2]
 
     from avian_b200 import parallel
     info = parallel.rank_info()

@@ -18,14 +18,14 @@ variants = [("wave bps3", {}), ("wave bps4", {"AVN_MEGA_BPS": "4"}), ("wave bps5
             ("barrier bps3", {"AVN_LAUNCH_MODE": "barrier"}), ("barrier bps5", {"AVN_LAUNCH_MODE": "barrier", "AVN_MEGA_BPS": "5"}),
             ("phases", {"AVN_LAUNCH_MODE": "phases"})]
 with api.Context(device=0) as ctx0:
-    sc, prm, bodies, man, aabbs = bench.build_snapshot(scene, 2, ctx0)
+    sc, prm, bodies, man, aabbs, joints = bench.build_snapshot(scene, bench.SCENES[scene][2], ctx0)
 ref = None
 for name, env in variants:
     os.environ.update(env)
     try:
         with api.Context(device=0) as ctx:
             b, m = bodies.copy(), man.copy()
-            ctx.solver_upload(prm, b, m)
+            ctx.solver_upload(prm, b, m, joints)
             for _ in range(3):
                 ctx.solver_run()
             ms = []
