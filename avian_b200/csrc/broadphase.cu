@@ -166,6 +166,7 @@ struct Sweep {
     const uint4* meta;                     // [n] {collider, body, memberships, filters}
     const uint8_t* flags;                  // [n]
     const int* end;                        // [n] first j with min.x[j] > max.x[i]
+    const uint8_t* is_wide;                // [n] 1: handled by sweep_wide_kernel (more than SW_WIDE candidates)
     const uint64_t* existing; uint64_t existing_mask;   // open-addressing hash set of PairKey (0 = empty; keys stored +1)
     const uint64_t* jdis; uint64_t jdis_mask;
 };
@@ -189,9 +190,10 @@ __global__ void gather_sorted(const uint32_t* __restrict__ order, int n, const S
 // Intervals with more than SW_WIDE candidates (a ground slab spanning the whole scene) would serialise one warp of the
 // tiled sweep for the whole array; they go to a list that sweep_wide_kernel handles with one block per interval.
 constexpr int SW_WIDE = 4096;
+constexpr int SW_WIDE_CAP = 1 << 14;   // intervals beyond the cap stay in the tiled sweep (correct, only slower)
 template <class S>
 __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, int n, int* __restrict__ end, int* __restrict__ wide_list,
-                             int* __restrict__ wide_count) {
+                             int* __restrict__ wide_count, uint8_t* __restrict__ is_wide) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     S m = maxx[i];
@@ -201,7 +203,12 @@ __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ m
         if (minx[mid] > m) hi = mid; else lo = mid + 1;
     }
     end[i] = lo;
-    if (lo - i - 1 > SW_WIDE) wide_list[atomicAdd(wide_count, 1)] = i;
+    uint8_t wide = 0;
+    if (lo - i - 1 > SW_WIDE) {
+        int slot = atomicAdd(wide_count, 1);
+        if (slot < SW_WIDE_CAP) { wide_list[slot] = i; wide = 1; }
+    }
+    is_wide[i] = wide;
 }
 
 __device__ __forceinline__ uint64_t hash64(uint64_t x) {
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
                                                            uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
                                                            uint8_t* __restrict__ out_flags) {
     __shared__ Vec4<S> s_yz[SW_CHUNK];
+    __shared__ Vec4<S> s_env[SW_CHUNK / 32];   // y/z envelope of each group of 32 staged candidates
     __shared__ int s_jend;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int tile0 = blockIdx.x * SW_TILE; tile0 < s.n; tile0 += gridDim.x * SW_TILE) {
@@ -271,8 +279,7 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
         if (threadIdx.x == 0) s_jend = 0;
         __syncthreads();
         if (threadIdx.x < tile_n) {
-            const int e = s.end[tile0 + threadIdx.x];
-            if (e - (tile0 + threadIdx.x) - 1 <= SW_WIDE) atomicMax(&s_jend, e);
+            if (!s.is_wide[tile0 + threadIdx.x]) atomicMax(&s_jend, s.end[tile0 + threadIdx.x]);
         }
         __syncthreads();
         const int j_begin = tile0 + 1, j_end = s_jend;
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
             const int i = tile0 + warp * SW_PER_WARP + q;
             bool live = i < s.n;
             my_end[q] = live ? s.end[i] : 0;
-            if (live && my_end[q] - i - 1 > SW_WIDE) { live = false; my_end[q] = 0; }  // wide: sweep_wide_kernel
+            if (live && s.is_wide[i]) { live = false; my_end[q] = 0; }  // wide: sweep_wide_kernel
             my_yz[q] = live ? s.yz[i] : mk4<S>(0, 0, 0, 0);
             running[q] = (EMIT && live) ? offsets[i] : 0ull;
             total[q] = 0;
@@ -294,8 +301,21 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
         for (int c0 = j_begin; c0 < j_end; c0 += SW_CHUNK) {
             __syncthreads();  // previous chunk fully consumed
             {
+                // stage the chunk; warp w also reduces the envelope {min min.y, max max.y, min min.z, max max.z} of its 32
+                // candidates, so that an interval can reject a whole group with one test (sorted order is spatially coherent:
+                // ties on min.x keep spawn order, swept stacks have ~1 500 x-candidates per box and ~4 real overlaps)
                 const int j = c0 + threadIdx.x;
-                if (j < j_end) s_yz[threadIdx.x] = s.yz[j];
+                Vec4<S> v = mk4<S>(S(INFINITY), S(-INFINITY), S(INFINITY), S(-INFINITY));
+                if (j < j_end) { v = s.yz[j]; s_yz[threadIdx.x] = v; }
+                Vec4<S> e = v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    e.x = avn_min(e.x, __shfl_xor_sync(0xffffffffu, e.x, o));
+                    e.y = avn_max(e.y, __shfl_xor_sync(0xffffffffu, e.y, o));
+                    e.z = avn_min(e.z, __shfl_xor_sync(0xffffffffu, e.z, o));
+                    e.w = avn_max(e.w, __shfl_xor_sync(0xffffffffu, e.w, o));
+                }
+                if (lane == 0) s_env[warp] = e;
             }
             __syncthreads();
 #pragma unroll
@@ -306,6 +326,8 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
                 const Vec4<S> yi = my_yz[q];
 #pragma unroll 2
                 for (int r = 0; r < SW_CHUNK / 32; ++r) {
+                    const Vec4<S> env = s_env[r];
+                    if (yi.x > env.y || yi.y < env.x || yi.z > env.w || yi.w < env.z) continue;  // no candidate of the group can overlap i
                     const int j = c0 + r * 32 + lane;
                     bool ok = j > i && j < e;
                     if (ok) {
@@ -339,34 +361,41 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant
 #pragma unroll
             for (int q = 0; q < SW_PER_WARP; ++q) {
                 const int i = tile0 + warp * SW_PER_WARP + q;
-                if (i < s.n && !(s.end[i] - i - 1 > SW_WIDE)) counts[i] = total[q];
+                if (i < s.n && !s.is_wide[i]) counts[i] = total[q];
             }
         }
         __syncthreads();
     }
 }
 
-// one block per wide interval: 256 lanes stride its candidates; per round the 8 warp ballots are combined through
-// shared memory so positions stay in j order.
+// Wide intervals: the candidate range of interval i is cut into sub-ranges of SW_SUB candidates, one block each
+// (blockIdx.x = sub-range, blockIdx.y strides the wide list).  Count pass: sub_counts[w * nsub + s]; wide_finish turns them
+// into per-sub-range offsets and counts[i]; the emit pass starts each block at offsets[i] + sub_off.  Inside a block the 256
+// lanes take 256 consecutive candidates per round and the 8 warp ballots are combined through shared memory, so the j order
+// is kept.
+constexpr int SW_SUB = 4096;
 template <class S, bool EMIT>
 __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_constant__ Sweep<S> s, const int* __restrict__ wide_list,
-                                                                const int* __restrict__ wide_count, uint32_t* __restrict__ counts,
+                                                                const int* __restrict__ wide_count, uint32_t* __restrict__ sub_counts, int nsub,
                                                                 const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
                                                                 uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
                                                                 uint8_t* __restrict__ out_flags) {
     __shared__ uint32_t s_warp_cnt[SW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nw = *wide_count;
-    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int nw = min(*wide_count, SW_WIDE_CAP);
+    for (int w = blockIdx.y; w < nw; w += gridDim.y) {
         const int i = wide_list[w], e = s.end[i];
+        const int sub = blockIdx.x;
+        const int jb = i + 1 + sub * SW_SUB, je = min(e, jb + SW_SUB);
+        if (jb >= e) { if (!EMIT && threadIdx.x == 0) sub_counts[w * nsub + sub] = 0; continue; }
         const Vec4<S> yi = s.yz[i];
         const uint4 mi = s.meta[i];
         const uint32_t fi = s.flags[i];
-        uint64_t running = EMIT ? offsets[i] : 0ull;
+        uint64_t running = EMIT ? offsets[i] + sub_counts[w * nsub + sub] : 0ull;   // (emit pass: sub_counts holds exclusive offsets)
         uint32_t total = 0;
-        for (int j0 = i + 1; j0 < e; j0 += SW_THREADS) {
+        for (int j0 = jb; j0 < je; j0 += SW_THREADS) {
             const int j = j0 + threadIdx.x;
-            bool ok = j < e;
+            bool ok = j < je;
             if (ok) {
                 const Vec4<S> yj = s.yz[j];
                 ok = !(yi.x > yj.y || yi.y < yj.x) && !(yi.z > yj.w || yi.w < yj.z);
@@ -394,7 +423,21 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_con
             total += round_total;
             __syncthreads();
         }
-        if (!EMIT && threadIdx.x == 0) counts[i] = total;
+        if (!EMIT && threadIdx.x == 0) sub_counts[w * nsub + sub] = total;
+    }
+}
+// per wide interval: exclusive scan of its sub-range counts (in place) and its total into counts[i]
+__global__ void wide_finish(const int* __restrict__ wide_list, const int* __restrict__ wide_count, uint32_t* __restrict__ sub_counts, int nsub,
+                            uint32_t* __restrict__ counts) {
+    const int nw = min(*wide_count, SW_WIDE_CAP);
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
+        uint32_t run = 0;
+        for (int k = 0; k < nsub; ++k) {
+            uint32_t c = sub_counts[w * nsub + k];
+            sub_counts[w * nsub + k] = run;
+            run += c;
+        }
+        counts[wide_list[w]] = run;
     }
 }
 
@@ -506,7 +549,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -589,19 +632,26 @@ AvnStatus Broadphase<S>::run() {
         gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
                                                                s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
                                                                s_flags_.as<uint8_t>());
-        AVN_CUDA(wide_.ensure((size_t(n) + 1) * 4));
+        AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
+        AVN_CUDA(wide_flag_.ensure(size_t(n)));
         int* wide_count = wide_.as<int>();
         int* wide_list = wide_.as<int>() + 1;
         AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
-        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>(), wide_list, wide_count);
+        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>(), wide_list, wide_count, wide_flag_.as<uint8_t>());
         Sweep<S> sw;
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
-        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>();
+        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
         sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
         const int grid = std::min((n + SW_TILE - 1) / SW_TILE, sm_count_ * 16);
         sweep_kernel<S, false><<<grid, SW_THREADS, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-        sweep_wide_kernel<S, false><<<32, SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr,
-                                                                    nullptr, nullptr);
+        // wide intervals: at most n / SW_WIDE of them can exist per "layer" of overlap; the grid's y dimension strides the list
+        const int nsub = (n + SW_SUB - 1) / SW_SUB;
+        const int wide_rows = 64;
+        AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
+        sweep_wide_kernel<S, false><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, 0,
+                                                                                       nullptr, nullptr, nullptr, nullptr, nullptr);
+        wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
+        ++launches_;
         const int sblocks = (n + 1023) / 1024;
         AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
         scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
@@ -618,8 +668,9 @@ AvnStatus Broadphase<S>::run() {
             AVN_CUDA(o_fl_.ensure(total));
             sweep_kernel<S, true><<<grid, SW_THREADS, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
                                                             o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
-            sweep_wide_kernel<S, true><<<32, SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(),
-                                                                       o_c2_.as<uint32_t>(), o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+            sweep_wide_kernel<S, true><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
+                                                                                          offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
+                                                                                          o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
             launches_ += 2;
         }
     }

@@ -48,6 +48,24 @@ def test_random_aabbs(gpu_ctx, n, seed):
         assert o.count > 0
 
 
+def test_wide_intervals(gpu_ctx):
+    """every interval overlaps every other one along x (a tower / a ground slab): the wide-interval path, multi-block per i"""
+    n = 9000
+    a, ao = random_aabbs(n, 41, extent=8.0, size=0.6, with_filters=False), random_aabbs(n, 41, extent=8.0, size=0.6, with_filters=False)
+    rng = np.random.default_rng(1)
+    for x in (a, ao):
+        x.aabb_min[:, 0] = (-1.0 + 0.001 * np.arange(n)).astype(np.float32)
+        x.aabb_max[:, 0] = 50.0
+        x.aabb_min[::7, 0] = 20.0          # some narrow ones mixed in
+        x.aabb_max[::7, 0] = 20.5
+        x.flags[:] = 4
+    o = oracle_lib.broadphase(ao)
+    g = gpu_ctx.broadphase(a)
+    assert o.count > 10000
+    assert_pairs_equal(g, o)
+    assert np.array_equal(a.order_out, ao.order_out)
+
+
 def test_existing_pairs_and_joint_disabled(gpu_ctx):
     a, ao = random_aabbs(4000, 11), random_aabbs(4000, 11)
     full = oracle_lib.broadphase(random_aabbs(4000, 11))
