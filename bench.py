@@ -113,6 +113,7 @@ def build_snapshot(scene_name: str, settle: int, ctx=None):
     # the steady-state broad-phase input: every current pair is already in the contact graph
     mn, mx = w.aabb_min, w.aabb_max
     aabbs = w.pipeline.intervals(w.bodies, mn, mx, with_existing=True)
+    aabbs.joint_disabled_body_pairs = sc.joint_disabled_body_pairs
     return sc, w.params, w.bodies, man, aabbs, w.joints
 
 
@@ -135,7 +136,7 @@ def run_gpu(args, info):
     B, M, P = bodies.count, man.count, int(man.penetration.shape[0])
     J = 0 if joints is None else joints.count
     pin_columns(ctx, bodies); pin_columns(ctx, man); pin_columns(ctx, aabbs)
-    pairs_out = api.PairList.empty(1 << 16)
+    pairs_out = api.PairList.empty(1 << 20)
     b0, m0 = bodies.copy(), man.copy()     # the frozen snapshot (the step writes results into bodies/man in place)
 
     def barrier():
@@ -256,7 +257,7 @@ def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int, joints=None) -> di
         b, m = bodies.copy(), man.copy()
         a = api.Aabbs(**{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in aabbs.__dict__.items()})
         t0 = time.perf_counter()
-        oracle_lib.broadphase(a, capacity=1 << 16)
+        oracle_lib.broadphase(a, capacity=1 << 20)
         oracle_lib.solver_step(prm, b, m, None if joints is None else joints.copy(), threads=threads)
         t_total += time.perf_counter() - t0
     return {"value": sample_steps / t_total, "unit": "steps/s", "cores": threads, "kind": "port",
