@@ -9,10 +9,10 @@
 //   contacts cst[20][Mpad] planes, slot-major inside a plane so that a warp reads 32 consecutive Vec4.  Manifold m of
 //            graph colour c lives in slot color_off[c] + (m - m_color_off[c]); every colour starts at a multiple of 32 so
 //            a warp never straddles two colours (padding slots have info = 0 = no points):
-//            0 {n.xyz, friction} 1 {t1.xyz, restitution} 2 {tangent_velocity.xyz,-} 3 {body1, body2, info, ranks}
-//            4+4k {anchor1.xyz, initial_separation} 5+4k {anchor2.xyz, normal effective_mass}
-//            6+4k {normal impulse, total normal impulse, tangent impulse.x, .y}   <- the only plane written in the loop
-//            7+4k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
+//            k (k = 0..3)  {normal impulse, total normal impulse, tangent impulse.x, .y} of point k  <- the only planes written in the loop
+//            4 {n.xyz, friction} 5 {t1.xyz, restitution} 6 {tangent_velocity.xyz,-} 7 {body1, body2, info, ranks}
+//            8+3k {anchor1.xyz, initial_separation} 9+3k {anchor2.xyz, normal effective_mass}
+//            10+3k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
 //   joints   jnt[14][Jpad] planes in level-schedule order (see JP_* below).
 #pragma once
 #include <cuda_pipeline.h>
@@ -22,7 +22,13 @@
 
 namespace avn {
 
-enum { CP_N = 0, CP_T1 = 1, CP_TV = 2, CP_IDX = 3, CP_PT0 = 4, CP_PLANES = 4 + 4 * AVN_MAX_MANIFOLD_POINTS };
+// plane numbering: the four MUTABLE impulse planes come first so that, together with the body state that precedes them in the
+// same allocation, they form one contiguous "hot" range that is pinned in L2 (access-policy window); the immutable rows follow.
+enum { CP_PC0 = 0, CP_N = AVN_MAX_MANIFOLD_POINTS, CP_T1 = CP_N + 1, CP_TV = CP_N + 2, CP_IDX = CP_N + 3, CP_PT0 = CP_N + 4,
+       CP_PLANES = CP_PT0 + 3 * AVN_MAX_MANIFOLD_POINTS };
+// rows of point k: impulses {lambda_n, sum lambda_n, lambda_t.x, lambda_t.y} in plane CP_PC0 + k; immutable rows in CP_PT0 + 3k + {0: A, 1: B, 2: D}
+#define CP_PC(k) (CP_PC0 + (k))
+#define CP_ROW(k, r) (CP_PT0 + 3 * (k) + (r))
 // info lane of plane CP_IDX
 enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7,
        CI_VER1 = 1 << 8, CI_VER2 = 1 << 9 };  // VERx: side x is a versioned body (has a SolverBody) in wavefront mode
@@ -256,11 +262,10 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
             K2 = kl2 + dot(rt21, i1_rt21) + dot(rt22, i2_rt22);
             K3 = S(2) * (dot(rt11, i1_rt21) + dot(rt12, i2_rt22));
         }
-        Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
-        st4(&cp[0], mk4<S>(r1.x, r1.y, r1.z, sep0));
-        st4(&cp[MP], mk4<S>(r2.x, r2.y, r2.z, meff));
-        st4(&cp[2 * MP], mk4<S>(imp_n, S(0), itx, ity));
-        st4(&cp[3 * MP], mk4<S>(K1, K2, K3, d.p_normal_speed[p]));
+        st4(&c[size_t(CP_ROW(k, 0)) * MP], mk4<S>(r1.x, r1.y, r1.z, sep0));
+        st4(&c[size_t(CP_ROW(k, 1)) * MP], mk4<S>(r2.x, r2.y, r2.z, meff));
+        st4(&c[size_t(CP_PC(k)) * MP], mk4<S>(imp_n, S(0), itx, ity));
+        st4(&c[size_t(CP_ROW(k, 2)) * MP], mk4<S>(K1, K2, K3, d.p_normal_speed[p]));
     }
 }
 
@@ -393,10 +398,9 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #pragma unroll
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
             if (k < np) {
-                Vec4<S>* cp = c + size_t(CP_PT0 + 4 * k) * MP;
-                stage_copy(&ROW_A(k), &cp[0]);
-                stage_copy(&ROW_B(k), &cp[MP]);
-                if (PASS == PASS_RESTITUTION || (SOLVE && (info & CI_TANGENT))) stage_copy(&ROW_D(k), &cp[3 * MP]);
+                stage_copy(&ROW_A(k), &c[size_t(CP_ROW(k, 0)) * MP]);
+                stage_copy(&ROW_B(k), &c[size_t(CP_ROW(k, 1)) * MP]);
+                if (PASS == PASS_RESTITUTION || (SOLVE && (info & CI_TANGENT))) stage_copy(&ROW_D(k), &c[size_t(CP_ROW(k, 2)) * MP]);
             }
         }
     }
@@ -424,7 +428,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     }
 #pragma unroll
     for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
-        if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
+        if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PC(k)) * MP]);
     __pipeline_wait_prior(0);  // this thread's staged rows have landed (only the issuing thread reads them)
 #ifdef AVN_WAVE_TRACE
     if (WAVE) {  // force the loads to complete here so the segments separate cleanly
@@ -554,7 +558,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     if (PASS != PASS_WARM) {
 #pragma unroll
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
-            if (k < np) st4(&c[size_t(CP_PT0 + 4 * k + 2) * MP], PC[k]);
+            if (k < np) st4(&c[size_t(CP_PC(k)) * MP], PC[k]);
     }
     if (!(info & CI_ZERO1)) {
         st4(&d.vel[2 * b1], mk4<S>(v1.x, v1.y, v1.z, S(0)));
@@ -738,7 +742,7 @@ __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m)
         return;
     }
     for (int k = 0; k < np; ++k) {
-        Vec4<S> pc = ld4(&c[size_t(CP_PT0 + 4 * k + 2) * MP]);
+        Vec4<S> pc = ld4(&c[size_t(CP_PC(k)) * MP]);
         d.p_out_ws_normal[p0 + k] = pc.x;
         d.p_out_ws_tangent[2 * (p0 + k)] = (info & CI_TANGENT) ? pc.z : S(0);
         d.p_out_ws_tangent[2 * (p0 + k) + 1] = (info & CI_TANGENT) ? pc.w : S(0);

@@ -37,6 +37,16 @@ class Solver final : public SolverBase {
             sm_count_ = prop.multiProcessorCount;
             coop_ok_ = prop.cooperativeLaunch != 0;
         }
+        {
+            // L2 persistence for the hot range (AVN_L2_PERSIST=0 disables it)
+            const char* lp = getenv("AVN_L2_PERSIST");
+            l2_persist_ = !(lp && !strcmp(lp, "0")) && prop.persistingL2CacheMaxSize > 0;
+            if (l2_persist_) {
+                l2_persist_bytes_ = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), size_t(64) << 20);
+                l2_window_max_ = size_t(prop.accessPolicyMaxWindowSize);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_bytes_) != cudaSuccess) { (void)cudaGetLastError(); l2_persist_ = false; }
+            }
+        }
         const char* mode = getenv("AVN_LAUNCH_MODE");
         if (mode && !strcmp(mode, "phases")) use_mega_ = false;
         if (mode && !strcmp(mode, "barrier")) use_wave_ = false;   // megakernel with grid barriers between colours
@@ -102,7 +112,8 @@ class Solver final : public SolverBase {
     ErrorSink* err_;
     uint32_t cfg_flags_;
     int sm_count_ = 148;
-    bool coop_ok_ = false, use_mega_ = true, use_wave_ = true;
+    bool coop_ok_ = false, use_mega_ = true, use_wave_ = true, l2_persist_ = false;
+    size_t l2_persist_bytes_ = 0, l2_window_max_ = 0;
     int mega_grid_ = 0, mega_bps_ = 3;
     const void* mega_fn_ = nullptr;
     cudaEvent_t ev_[EV_COUNT];
@@ -121,9 +132,10 @@ class Solver final : public SolverBase {
     // device storage
     DevBuf b_kind_, b_locked_, b_dom_, b_iflags_, b_pos_, b_rot_, b_lv_, b_av_, b_im_, b_iil_, b_com_, b_ld_, b_ad_, b_gs_, b_la_, b_aa_, b_ml_, b_ma_;
     DevBuf o_pos_, o_rot_, o_lv_, o_av_;
-    DevBuf s_vel_, s_dlt_, s_inr_, s_itg_, s_pre_;
+    DevBuf s_inr_, s_itg_, s_pre_;
     DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_, p_nin_, p_own_, p_owt_;
-    DevBuf c_planes_, c_flag_, w_ver_, w_deg_;
+    DevBuf hot_, c_flag_;
+    size_t hot_bytes_ = 0;
     DevBuf j_type_, j_index_, j_level_, j_planes_;
     DevBuf jcol_[AVN_JOINT_TYPE_COUNT][12], jb1_[AVN_JOINT_TYPE_COUNT], jb2_[AVN_JOINT_TYPE_COUNT], jle_[AVN_JOINT_TYPE_COUNT],
         jde_[AVN_JOINT_TYPE_COUNT], jdl_[AVN_JOINT_TYPE_COUNT], jda_[AVN_JOINT_TYPE_COUNT], jfo_[AVN_JOINT_TYPE_COUNT], jto_[AVN_JOINT_TYPE_COUNT];
@@ -209,13 +221,11 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     AVN_CUDA(o_lv_.ensure(3 * B * sizeof(S) + 16)); d.out_linvel = o_lv_.as<S>();
     AVN_CUDA(o_av_.ensure(3 * B * sizeof(S) + 16)); d.out_angvel = o_av_.as<S>();
     const size_t state_bytes = 2 * (B + 1) * sizeof(Vec4<S>);
-    AVN_CUDA(s_vel_.ensure(state_bytes)); d.vel = s_vel_.as<Vec4<S>>();
-    AVN_CUDA(s_dlt_.ensure(state_bytes)); d.dlt = s_dlt_.as<Vec4<S>>();
     AVN_CUDA(s_inr_.ensure(state_bytes)); d.inr = s_inr_.as<Vec4<S>>();
     AVN_CUDA(s_itg_.ensure(state_bytes)); d.itg = s_itg_.as<Vec4<S>>();
     AVN_CUDA(s_pre_.ensure(state_bytes)); d.pre = s_pre_.as<Vec4<S>>();
-    AVN_CUDA(w_ver_.ensure((B + 1) * sizeof(unsigned))); d.ver = w_ver_.as<unsigned>();
-    AVN_CUDA(w_deg_.ensure((B + 1) * sizeof(int))); d.deg = w_deg_.as<int>();
+    // vel | dlt | ver | deg | contact planes are carved out of ONE allocation (after the manifold count is known, below): the
+    // mutable front of it (vel, dlt, ver, deg, the four impulse planes) is the L2-persisting window.
     hb_ = *bc;
     // ---- manifolds
     have_m_ = mc && mc->count > 0;
@@ -264,14 +274,26 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
         AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
         d.p_normal_impulse = p_ni_.as<S>();
-        AVN_CUDA(c_planes_.ensure(size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>)));
-        d.cst = c_planes_.as<Vec4<S>>();
+
         hm_ = *mc;
         host_any_restitution_ = false;
         {
             const S* r = static_cast<const S*>(mc->restitution);
             for (size_t i = 0; i < M; ++i) host_any_restitution_ |= (r[i] != S(0));
         }
+    }
+    {
+        auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+        const size_t vel_b = up256(state_bytes), dlt_b = up256(state_bytes), ver_b = up256((B + 1) * sizeof(unsigned)), deg_b = up256((B + 1) * sizeof(int));
+        const size_t planes_b = have_m_ ? size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>) : 0;
+        AVN_CUDA(hot_.ensure(vel_b + dlt_b + ver_b + deg_b + planes_b + 256));
+        char* base = hot_.as<char>();
+        d.vel = reinterpret_cast<Vec4<S>*>(base); base += vel_b;
+        d.dlt = reinterpret_cast<Vec4<S>*>(base); base += dlt_b;
+        d.ver = reinterpret_cast<unsigned*>(base); base += ver_b;
+        d.deg = reinterpret_cast<int*>(base); base += deg_b;
+        d.cst = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr;
+        hot_bytes_ = vel_b + dlt_b + ver_b + deg_b + (have_m_ ? size_t(AVN_MAX_MANIFOLD_POINTS) * d.Mpad * sizeof(Vec4<S>) : 0);
     }
     // ---- joints
     have_j_ = false;
@@ -330,6 +352,17 @@ AvnStatus Solver<S>::run() {
     if (dev_.wave) {
         AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
         AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, (size_t(dev_.B) + 1) * sizeof(int), stream_));
+    }
+    if (l2_persist_ && hot_bytes_ > 0) {
+        // pin the mutable state (body velocities/deltas, event counters, impulse planes) in L2: it sits on the critical dependency
+        // chain, while the immutable constraint rows only stream through
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = hot_.p;
+        attr.accessPolicyWindow.num_bytes = std::min(hot_bytes_, l2_window_max_);
+        attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(l2_persist_bytes_) / double(attr.accessPolicyWindow.num_bytes)));
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
     const DevSolver<S>& d = dev_;
     if (mega) {

@@ -14,9 +14,8 @@ from avian_b200 import api  # noqa: E402
 
 scene = sys.argv[1] if len(sys.argv) > 1 else "stack100k"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-variants = [("wave bps3", {}), ("wave bps4", {"AVN_MEGA_BPS": "4"}), ("wave bps5", {"AVN_MEGA_BPS": "5"}), ("wave bps6", {"AVN_MEGA_BPS": "6"}),
-            ("barrier bps3", {"AVN_LAUNCH_MODE": "barrier"}), ("barrier bps5", {"AVN_LAUNCH_MODE": "barrier", "AVN_MEGA_BPS": "5"}),
-            ("phases", {"AVN_LAUNCH_MODE": "phases"})]
+variants = [("wave bps3", {}), ("wave no-l2persist", {"AVN_L2_PERSIST": "0"}), ("wave bps4", {"AVN_MEGA_BPS": "4"}),
+            ("barrier bps3", {"AVN_LAUNCH_MODE": "barrier"}), ("phases", {"AVN_LAUNCH_MODE": "phases"})]
 with api.Context(device=0) as ctx0:
     sc, prm, bodies, man, aabbs, joints = bench.build_snapshot(scene, bench.SCENES[scene][2], ctx0)
 ref = None
