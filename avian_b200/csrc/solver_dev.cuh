@@ -31,10 +31,14 @@ enum { CP_PC0 = 0, CP_N = AVN_MAX_MANIFOLD_POINTS, CP_T1 = CP_N + 1, CP_TV = CP_
 #define CP_ROW(k, r) (CP_PT0 + 3 * (k) + (r))
 // info lane of plane CP_IDX
 enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7,
-       CI_VER1 = 1 << 8, CI_VER2 = 1 << 9 };  // VERx: side x is a versioned body (has a SolverBody) in wavefront mode
+       CI_VER1 = 1 << 8, CI_VER2 = 1 << 9,     // VERx: side x is a versioned body (has a SolverBody) in wavefront mode
+       CI_FIV1 = 1 << 10, CI_FIV2 = 1 << 11,  // this constraint is the LAST relax event of body x: it also integrates its velocity
+       CI_FIP1 = 1 << 12, CI_FIP2 = 1 << 13 }; // this constraint is the LAST solve event of body x: it also integrates its position
 // flags lane of inr[2*i]
 enum { BF_LOCK_MASK = 0x3f, BF_HAS_SOLVER_BODY = 1 << 8, BF_KINEMATIC = 1 << 9, BF_GYRO = 1 << 10, BF_DYNAMIC = 1 << 11,
-       BF_CUSTOM_VEL = 1 << 12, BF_CUSTOM_POS = 1 << 13, BF_DOMINANCE_SHIFT = 16 };
+       BF_CUSTOM_VEL = 1 << 12, BF_CUSTOM_POS = 1 << 13, BF_FUSE_IV = 1 << 14, BF_FUSE_IP = 1 << 15, BF_DOMINANCE_SHIFT = 16 };
+// BF_FUSE_IV / BF_FUSE_IP (wavefront mode): the body's integrate_velocities / integrate_positions step is plain enough (no gyroscopic
+// torque, no speed clamp, no custom-integration marker) to be executed by the contact item that holds the body's state right before it.
 
 enum { JP_IDX = 0,   // {body1, body2, type | limit_enabled<<8 | damping<<16 | zero1<<24 | zero2<<25, original index}
        JP_R1 = 1,    // {world_r1.xyz, compliance0}
@@ -155,6 +159,9 @@ __device__ void prepare_body_item(const DevSolver<S>& d, int i) {
         bool iso = !(avn_abs(il.m00 - il.m11) > eps || avn_abs(il.m11 - il.m22) > eps) && avn_abs(il.m01) < eps &&
                    avn_abs(il.m02) < eps && avn_abs(il.m12) < eps;
         if (!rot_locked && !iso) flags |= BF_GYRO;
+        const bool clamped = (d.max_lin && avn_finite(d.max_lin[i])) || (d.max_ang && avn_finite(d.max_ang[i]));
+        if (kind == AVN_BODY_DYNAMIC && !(flags & (BF_CUSTOM_VEL | BF_GYRO)) && !clamped) flags |= BF_FUSE_IV;
+        if (!(flags & BF_CUSTOM_POS)) flags |= BF_FUSE_IP;
         ia = mk4<S>(inv_mass, int_as(S(0), flags), iw.m00, iw.m01);
         ib = mk4<S>(iw.m02, iw.m11, iw.m12, iw.m22);
     }
@@ -343,10 +350,12 @@ __device__ __forceinline__ void wave_wait(const unsigned* ver, bool need1, int b
     }
     __threadfence();  // acquire: the loads below must observe what the publishers wrote before bumping the counters
 }
-__device__ __forceinline__ void wave_publish(unsigned* ver, bool need1, int b1, unsigned e1, bool need2, int b2, unsigned e2) {
+// n1 / n2 = events this item consumed on each body (2 when it also ran the body's integrate step)
+__device__ __forceinline__ void wave_publish(unsigned* ver, bool need1, int b1, unsigned e1, bool need2, int b2, unsigned e2, unsigned n1 = 1u,
+                                             unsigned n2 = 1u) {
     __threadfence();  // release: this item's stores are visible before the counters move
-    if (need1) st_relaxed(ver + b1, e1 + 1u);
-    if (need2) st_relaxed(ver + b2, e2 + 1u);
+    if (need1) st_relaxed(ver + b1, e1 + n1);
+    if (need2) st_relaxed(ver + b2, e2 + n2);
 }
 
 // ---- shared-memory staging of the immutable per-point constraint rows -------------------------------------------------
@@ -407,6 +416,15 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     __pipeline_commit();
     unsigned e1 = 0, e2 = 0;
     const bool ver1 = WAVE && np != 0 && (info & CI_VER1), ver2 = WAVE && np != 0 && (info & CI_VER2);
+    // fused integrate steps (wavefront mode): the last relax event of a body also runs its next integrate_velocities, the last
+    // biased-solve event also runs its integrate_positions — same arithmetic on the same registers, one dependency level less each
+    const bool fiv1 = WAVE && PASS == PASS_RELAX && (info & CI_FIV1) && wave_substep + 1 < d.substeps;
+    const bool fiv2 = WAVE && PASS == PASS_RELAX && (info & CI_FIV2) && wave_substep + 1 < d.substeps;
+    const bool fip1 = WAVE && PASS == PASS_SOLVE_BIAS && (info & CI_FIP1) && wave_it + 1 == d.iters;
+    const bool fip2 = WAVE && PASS == PASS_SOLVE_BIAS && (info & CI_FIP2) && wave_it + 1 == d.iters;
+    Vec4<S> il1, ia1, il2, ia2;   // VelocityIntegrationData rows (immutable): fetched before the wait
+    if (fiv1) { il1 = ld4(&d.itg[2 * b1]); ia1 = ld4(&d.itg[2 * b1 + 1]); }
+    if (fiv2) { il2 = ld4(&d.itg[2 * b2]); ia2 = ld4(&d.itg[2 * b2 + 1]); }
     if (WAVE) {
         const int rk = as_int(hidx.w);
         const int kind = PASS == PASS_WARM ? WV_WARM : (PASS == PASS_SOLVE_BIAS ? WV_SOLVE : WV_RELAX);
@@ -560,15 +578,35 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
             if (k < np) st4(&c[size_t(CP_PC(k)) * MP], PC[k]);
     }
-    if (!(info & CI_ZERO1)) {
+    if (WAVE && SOLVE) {
+        // integrate_positions of a body whose last solve event this is (integrator/mod.rs:503-535): dp += v h, dq = exp(w h) dq
+        if (fip1) {
+            V3<S> ndp = xyz(dp1) + v1 * d.h;
+            Q4<S> q; q.x = dq1.x; q.y = dq1.y; q.z = dq1.z; q.w = dq1.w;
+            Q4<S> nq = qmul(q_from_scaled_axis(w1 * d.h, d.fast_trig != 0), q);
+            st4(&d.dlt[2 * b1], mk4<S>(ndp.x, ndp.y, ndp.z, S(0)));
+            st4(&d.dlt[2 * b1 + 1], mk4<S>(nq.x, nq.y, nq.z, nq.w));
+        }
+        if (fip2) {
+            V3<S> ndp = xyz(dp2) + v2 * d.h;
+            Q4<S> q; q.x = dq2.x; q.y = dq2.y; q.z = dq2.z; q.w = dq2.w;
+            Q4<S> nq = qmul(q_from_scaled_axis(w2 * d.h, d.fast_trig != 0), q);
+            st4(&d.dlt[2 * b2], mk4<S>(ndp.x, ndp.y, ndp.z, S(0)));
+            st4(&d.dlt[2 * b2 + 1], mk4<S>(nq.x, nq.y, nq.z, nq.w));
+        }
+        // integrate_velocities of the NEXT substep for a body whose last relax event this is (integrator/mod.rs:362-368)
+        if (fiv1) { v1 = v1 * il1.w; w1 = w1 * ia1.w; v1 = v1 + xyz(il1); w1 = w1 + xyz(ia1); }
+        if (fiv2) { v2 = v2 * il2.w; w2 = w2 * ia2.w; v2 = v2 + xyz(il2); w2 = w2 + xyz(ia2); }
+    }
+    if (!(info & CI_ZERO1) || fiv1) {
         st4(&d.vel[2 * b1], mk4<S>(v1.x, v1.y, v1.z, S(0)));
         st4(&d.vel[2 * b1 + 1], mk4<S>(w1.x, w1.y, w1.z, S(0)));
     }
-    if (!(info & CI_ZERO2)) {
+    if (!(info & CI_ZERO2) || fiv2) {
         st4(&d.vel[2 * b2], mk4<S>(v2.x, v2.y, v2.z, S(0)));
         st4(&d.vel[2 * b2 + 1], mk4<S>(w2.x, w2.y, w2.z, S(0)));
     }
-    if (WAVE) wave_publish(d.ver, ver1, b1, e1, ver2, b2, e2);
+    if (WAVE) wave_publish(d.ver, ver1, b1, e1, ver2, b2, e2, (fiv1 || fip1) ? 2u : 1u, (fiv2 || fip2) ? 2u : 1u);
 #ifdef AVN_WAVE_TRACE
     if (WAVE) { AVN_TRACE_ADD(d, 3, clock64() - t_s0); AVN_TRACE_ADD(d, 4, 1); }
 #endif
@@ -586,7 +624,9 @@ __device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, i
     const bool in_range = i < d.B;
     int f = 0;
     if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
-    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    // wavefront mode: from the second substep on, a fusable body's step was already run by its last relax item
+    if (WAVE && live && (f & BF_FUSE_IV) && s >= 1 && d.deg[i] > 0) live = false;
     unsigned e = 0;
     if (WAVE) {
         if (live) e = wave_event(WV_IV, 0, s, d.iters, d.deg[i], 0);
@@ -647,7 +687,8 @@ __device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, i
     const bool in_range = i < d.B;
     int f = 0;
     if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
-    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    if (WAVE && live && (f & BF_FUSE_IP) && d.deg[i] > 0) live = false;   // run by the body's last biased-solve item
     unsigned e = 0;
     if (WAVE) {
         if (live) e = wave_event(WV_IP, 0, s, d.iters, d.deg[i], 0);
@@ -692,9 +733,18 @@ __device__ __forceinline__ void wave_pack_item(const DevSolver<S>& d, int slot) 
     const int info = as_int(hidx.z);
     if ((info & CI_NP_MASK) == 0) return;
     const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
-    int rk = as_int(hidx.w);
-    if (info & CI_VER1) rk |= (d.deg[b1] & 0xff) << 8;
-    if (info & CI_VER2) rk |= (d.deg[b2] & 0xff) << 24;
+    int rk = as_int(hidx.w), ninfo = info;
+    if (info & CI_VER1) {
+        const int k1 = d.deg[b1], f1 = as_int(ld4(&d.inr[2 * b1]).y);
+        rk |= (k1 & 0xff) << 8;
+        if ((rk & 0xff) == k1 - 1) ninfo |= ((f1 & BF_FUSE_IV) ? CI_FIV1 : 0) | ((f1 & BF_FUSE_IP) ? CI_FIP1 : 0);
+    }
+    if (info & CI_VER2) {
+        const int k2 = d.deg[b2], f2 = as_int(ld4(&d.inr[2 * b2]).y);
+        rk |= (k2 & 0xff) << 24;
+        if (((rk >> 16) & 0xff) == k2 - 1) ninfo |= ((f2 & BF_FUSE_IV) ? CI_FIV2 : 0) | ((f2 & BF_FUSE_IP) ? CI_FIP2 : 0);
+    }
+    hidx.z = int_as(S(0), ninfo);
     hidx.w = int_as(S(0), rk);
     st4(&c[CP_IDX * MP], hidx);
 }
