@@ -160,8 +160,18 @@ __device__ void prepare_body_item(const DevSolver<S>& d, int i) {
                    avn_abs(il.m02) < eps && avn_abs(il.m12) < eps;
         if (!rot_locked && !iso) flags |= BF_GYRO;
         const bool clamped = (d.max_lin && avn_finite(d.max_lin[i])) || (d.max_ang && avn_finite(d.max_ang[i]));
+        // (measured: fusing even the 12-flop velocity step into the contact item costs more than the dependency level it saves,
+        //  1.66 -> 1.77 ms — the contact item's own latency is the critical resource; kept behind AVN_FUSE_IV for reference)
+#ifdef AVN_FUSE_IV
         if (kind == AVN_BODY_DYNAMIC && !(flags & (BF_CUSTOM_VEL | BF_GYRO)) && !clamped) flags |= BF_FUSE_IV;
+#else
+        (void)clamped;
+#endif
+        // (fusing integrate_positions the same way was measured SLOWER, 1.66 -> 1.85 ms: its double-precision sincos diverges the
+        //  warps of every late colour of the solve pass instead of costing one cheap level; kept behind AVN_FUSE_IP for reference)
+#ifdef AVN_FUSE_IP
         if (!(flags & BF_CUSTOM_POS)) flags |= BF_FUSE_IP;
+#endif
         ia = mk4<S>(inv_mass, int_as(S(0), flags), iw.m00, iw.m01);
         ib = mk4<S>(iw.m02, iw.m11, iw.m12, iw.m22);
     }
@@ -322,6 +332,8 @@ __device__ __forceinline__ unsigned wave_event(int kind, int it, int s, int iter
         default: return base + 2u + unsigned(1 + iters) * k + r;
     }
 }
+// counters: relaxed gpu-scope accesses bracketed by __threadfence() (message passing).  ld.acquire.gpu / st.release.gpu on the
+// counters instead of the fences was measured and is not faster (1.69 vs 1.66 ms per 100k-cube step).
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -418,10 +430,18 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     const bool ver1 = WAVE && np != 0 && (info & CI_VER1), ver2 = WAVE && np != 0 && (info & CI_VER2);
     // fused integrate steps (wavefront mode): the last relax event of a body also runs its next integrate_velocities, the last
     // biased-solve event also runs its integrate_positions — same arithmetic on the same registers, one dependency level less each
+#ifdef AVN_FUSE_IV
     const bool fiv1 = WAVE && PASS == PASS_RELAX && (info & CI_FIV1) && wave_substep + 1 < d.substeps;
     const bool fiv2 = WAVE && PASS == PASS_RELAX && (info & CI_FIV2) && wave_substep + 1 < d.substeps;
+#else
+    constexpr bool fiv1 = false, fiv2 = false;
+#endif
+#ifdef AVN_FUSE_IP
     const bool fip1 = WAVE && PASS == PASS_SOLVE_BIAS && (info & CI_FIP1) && wave_it + 1 == d.iters;
     const bool fip2 = WAVE && PASS == PASS_SOLVE_BIAS && (info & CI_FIP2) && wave_it + 1 == d.iters;
+#else
+    constexpr bool fip1 = false, fip2 = false;
+#endif
     Vec4<S> il1, ia1, il2, ia2;   // VelocityIntegrationData rows (immutable): fetched before the wait
     if (fiv1) { il1 = ld4(&d.itg[2 * b1]); ia1 = ld4(&d.itg[2 * b1 + 1]); }
     if (fiv2) { il2 = ld4(&d.itg[2 * b2]); ia2 = ld4(&d.itg[2 * b2 + 1]); }
