@@ -41,12 +41,16 @@ SCENES = {
     "stack1k": (lambda sc: sc.cube_stack(11, 10, 10, brick=True), 8, 2),
     "ragdolls5k": (lambda sc: sc.ragdoll_field(5000, pitch=3.0, drop_height=0.2), 8, 30),  # BASELINE configs[3]: 85 000 bodies, 80 000 joints
     "ragdolls500": (lambda sc: sc.ragdoll_field(500, pitch=3.0, drop_height=0.2), 8, 30),
+    # BASELINE configs[4]: 1M spheres r=0.5, f64, uniform in a 200x50x200 box (seed 42); broad-phase heavy.  One GPU holds the whole scene
+    # here (the x-slab partition over 8 GPUs is not built).
+    "spheres1m": (lambda sc: sc.falling_spheres(1_000_000, seed=42, scalar=np.float64), 8, 2),
+    "spheres100k": (lambda sc: sc.falling_spheres(100_000, seed=42, box=(93.0, 50.0, 93.0), scalar=np.float64), 8, 2),
 }
 
 
 def metric_name(scene: str) -> str:
     label = {"stack100k": "100k-cube stack", "stack10k": "10k-cube stack", "stack1k": "1k-cube stack", "ragdolls5k": "5k-ragdoll field",
-             "ragdolls500": "500-ragdoll field"}[scene]
+             "ragdolls500": "500-ragdoll field", "spheres1m": "1M falling spheres (f64)", "spheres100k": "100k falling spheres (f64)"}[scene]
     return f"physics steps/sec on {label} (broad phase + solver stage per step)"
 
 
@@ -130,7 +134,8 @@ def run_gpu(args, info):
     from avian_b200 import api, parallel
     rank, world, local_rank = info.rank, info.world, info.local_rank
     torch.cuda.set_device(local_rank)
-    ctx = api.Context(device=local_rank)
+    scalar = np.float64 if args.scene.startswith("spheres") else np.float32
+    ctx = api.Context(device=local_rank, scalar=scalar)
     sc, prm, bodies, man, aabbs, joints = build_snapshot(args.scene, args.settle, ctx)
     prm.solver_iterations = args.solver_iterations
     B, M, P = bodies.count, man.count, int(man.penetration.shape[0])
@@ -225,8 +230,8 @@ def run_gpu(args, info):
     result = {
         "metric": metric_name(args.scene), "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, one scene per GPU, f32, {int(prm.substeps)} substeps, "
+        "vs_baseline": None, "dtype": "f64" if sb == 8 else "f32", "data": "synthetic",
+        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, one scene per GPU, {'f64' if sb == 8 else 'f32'}, {int(prm.substeps)} substeps, "
                                f"reference solver semantics (1 warm start + {int(prm.solver_iterations)} biased + 1 relax pass per substep)",
                    "bodies": B, "manifolds": M, "contact_points": P, "joints": J, "solver_iterations": int(prm.solver_iterations), "colliders": int(aabbs.collider.shape[0]),
                    "existing_pairs": 0 if aabbs.existing_pairs is None else int(aabbs.existing_pairs.shape[0]), "new_pairs_per_step": new_pairs,
@@ -235,7 +240,7 @@ def run_gpu(args, info):
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e_ms / K},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "step_megakernel<float> (whole solver stage, one launch per step)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"step_megakernel<{'double' if sb == 8 else 'float'}> (whole solver stage, one launch per step)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["step"],
                      "kernel_ms": mega_ms / K, "solve_pass_bytes": alg["solve_pass"]},
         "breakdown_ms": {"broad_phase": bp_ms / K, "solver_stage": mega_ms / K, "resident_wall": wall_res_ms / K},
@@ -279,8 +284,8 @@ def run_reference(args, rank: int, world: int):
     return {
         "impl": "reference", "metric": metric_name(args.scene), "value": cb["value"], "unit": "steps/s",
         "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, f32, {int(prm.substeps)} substeps", "bodies": B, "manifolds": M, "contact_points": P,
+        "vs_baseline": None, "dtype": "f64" if bodies.position.dtype == np.float64 else "f32", "data": "synthetic",
+        "config": {"workload": f"{sc.name}: {B - 1} dynamic bodies on a ground slab, {bodies.position.dtype.name}, {int(prm.substeps)} substeps", "bodies": B, "manifolds": M, "contact_points": P,
                    "joints": 0 if joints is None else joints.count, "settle_steps": args.settle,
                    "note": "restated Avian CPU path (C++ oracle), not Avian itself: no Rust toolchain in this image"},
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
