@@ -10,10 +10,9 @@
 //      stable scatter ranked with warp match/ballot (4 passes for f32 keys, 8 for f64);
 //   3. gather the interval columns into sorted SoA arrays (coalesced for the sweep);
 //   4. per interval i: upper bound of max.x[i] in the sorted min.x = the reference's `break` position;
-//   5. tiled sweep: a block owns 64 consecutive i and streams the union of their candidate ranges (i, end_i) through
-//      shared memory; y/z overlap (inclusive), inactive/layers/same-body, existing-pair hash set, joint-disabled hash
-//      set — count pass, exclusive scan, emit pass: ballot + popc keep the j order inside a warp, the scan keeps the
-//      i order across intervals.
+//   5. candidate search through a (y, z) cell grid under the x-sorted ranks (broadphase_cells.cuh): count pass, exclusive scan,
+//      emit pass into a (rank i, rank j) buffer, per-interval segment sort by j, materialisation of the ABI columns.  Intervals
+//      with a huge x-window (a ground slab) are swept brute force by sweep_wide_kernel, one block per 4 096 candidates.
 #include <algorithm>
 #include <cstring>
 
@@ -255,118 +254,7 @@ __device__ __forceinline__ bool pair_filters(const Sweep<S>& s, uint4 mi, uint32
     return true;
 }
 
-// Tiled sweep.  A block owns SW_TILE consecutive intervals i (consecutive in the sorted order, so their candidate
-// ranges (i, end[i]) overlap almost completely) and streams the union of the ranges through shared memory in chunks of
-// SW_CHUNK candidates: every candidate's {min.y,max.y,min.z,max.z} is read from L2 once per block instead of once per i
-// (the 100k-cube stack has ~2 000 x-overlap candidates per interval, ~4 of which survive the y/z test).
-// Warp w handles intervals w*SW_PER_WARP .. +SW_PER_WARP-1 of the tile; for one i the lanes take 32 consecutive
-// candidates per round, chunks / rounds / lanes all advance in j order, so ballot + popc give the reference's (i, j)
-// emission order.  EMIT = false: counts[i]; EMIT = true: writes pairs at offsets[i] + running index.
-constexpr int SW_THREADS = 256, SW_WARPS = SW_THREADS / 32, SW_PER_WARP = 8, SW_TILE = SW_WARPS * SW_PER_WARP, SW_CHUNK = 256;
-
-template <class S, bool EMIT>
-__global__ void __launch_bounds__(SW_THREADS) sweep_kernel(const __grid_constant__ Sweep<S> s, uint32_t* __restrict__ counts,
-                                                           const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
-                                                           uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
-                                                           uint8_t* __restrict__ out_flags) {
-    __shared__ Vec4<S> s_yz[SW_CHUNK];
-    __shared__ Vec4<S> s_env[SW_CHUNK / 32];   // y/z envelope of each group of 32 staged candidates
-    __shared__ int s_jend;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int tile0 = blockIdx.x * SW_TILE; tile0 < s.n; tile0 += gridDim.x * SW_TILE) {
-        const int tile_n = min(SW_TILE, s.n - tile0);
-        // union of the candidate ranges of the tile
-        if (threadIdx.x == 0) s_jend = 0;
-        __syncthreads();
-        if (threadIdx.x < tile_n) {
-            if (!s.is_wide[tile0 + threadIdx.x]) atomicMax(&s_jend, s.end[tile0 + threadIdx.x]);
-        }
-        __syncthreads();
-        const int j_begin = tile0 + 1, j_end = s_jend;
-        // per-warp state of its SW_PER_WARP intervals (lane-uniform)
-        int my_end[SW_PER_WARP];
-        Vec4<S> my_yz[SW_PER_WARP];
-        uint64_t running[SW_PER_WARP];
-        uint32_t total[SW_PER_WARP];
-#pragma unroll
-        for (int q = 0; q < SW_PER_WARP; ++q) {
-            const int i = tile0 + warp * SW_PER_WARP + q;
-            bool live = i < s.n;
-            my_end[q] = live ? s.end[i] : 0;
-            if (live && s.is_wide[i]) { live = false; my_end[q] = 0; }  // wide: sweep_wide_kernel
-            my_yz[q] = live ? s.yz[i] : mk4<S>(0, 0, 0, 0);
-            running[q] = (EMIT && live) ? offsets[i] : 0ull;
-            total[q] = 0;
-        }
-        for (int c0 = j_begin; c0 < j_end; c0 += SW_CHUNK) {
-            __syncthreads();  // previous chunk fully consumed
-            {
-                // stage the chunk; warp w also reduces the envelope {min min.y, max max.y, min min.z, max max.z} of its 32
-                // candidates, so that an interval can reject a whole group with one test (sorted order is spatially coherent:
-                // ties on min.x keep spawn order, swept stacks have ~1 500 x-candidates per box and ~4 real overlaps)
-                const int j = c0 + threadIdx.x;
-                Vec4<S> v = mk4<S>(S(INFINITY), S(-INFINITY), S(INFINITY), S(-INFINITY));
-                if (j < j_end) { v = s.yz[j]; s_yz[threadIdx.x] = v; }
-                Vec4<S> e = v;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    e.x = avn_min(e.x, __shfl_xor_sync(0xffffffffu, e.x, o));
-                    e.y = avn_max(e.y, __shfl_xor_sync(0xffffffffu, e.y, o));
-                    e.z = avn_min(e.z, __shfl_xor_sync(0xffffffffu, e.z, o));
-                    e.w = avn_max(e.w, __shfl_xor_sync(0xffffffffu, e.w, o));
-                }
-                if (lane == 0) s_env[warp] = e;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < SW_PER_WARP; ++q) {
-                const int i = tile0 + warp * SW_PER_WARP + q;
-                const int e = my_end[q];
-                if (c0 >= e || c0 + SW_CHUNK <= i + 1) continue;  // chunk outside (i, end_i): warp-uniform
-                const Vec4<S> yi = my_yz[q];
-#pragma unroll 2
-                for (int r = 0; r < SW_CHUNK / 32; ++r) {
-                    const Vec4<S> env = s_env[r];
-                    if (yi.x > env.y || yi.y < env.x || yi.z > env.w || yi.w < env.z) continue;  // no candidate of the group can overlap i
-                    const int j = c0 + r * 32 + lane;
-                    bool ok = j > i && j < e;
-                    if (ok) {
-                        const Vec4<S> yj = s_yz[r * 32 + lane];
-                        // broad_phase.rs:394-403 (inclusive tests)
-                        ok = !(yi.x > yj.y || yi.y < yj.x) && !(yi.z > yj.w || yi.w < yj.z);
-                    }
-                    uint32_t pf = 0;
-                    uint4 mi = make_uint4(0, 0, 0, 0), mj = mi;
-                    if (ok) {
-                        mi = s.meta[i];
-                        ok = pair_filters(s, mi, s.flags[i], j, pf, mj);
-                    }
-                    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                    if (bal == 0) continue;
-                    if (EMIT) {
-                        if (ok) {
-                            const uint64_t pos = running[q] + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < capacity) {
-                                out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
-                            }
-                        }
-                        running[q] += __popc(bal);
-                    } else {
-                        total[q] += __popc(bal);
-                    }
-                }
-            }
-        }
-        if (!EMIT && lane == 0) {
-#pragma unroll
-            for (int q = 0; q < SW_PER_WARP; ++q) {
-                const int i = tile0 + warp * SW_PER_WARP + q;
-                if (i < s.n && !s.is_wide[i]) counts[i] = total[q];
-            }
-        }
-        __syncthreads();
-    }
-}
+constexpr int SW_THREADS = 256, SW_WARPS = SW_THREADS / 32;
 
 // Wide intervals: the candidate range of interval i is cut into sub-ranges of SW_SUB candidates, one block each
 // (blockIdx.x = sub-range, blockIdx.y strides the wide list).  Count pass: sub_counts[w * nsub + s]; wide_finish turns them
@@ -377,9 +265,7 @@ constexpr int SW_SUB = 4096;
 template <class S, bool EMIT>
 __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_constant__ Sweep<S> s, const int* __restrict__ wide_list,
                                                                 const int* __restrict__ wide_count, uint32_t* __restrict__ sub_counts, int nsub,
-                                                                const uint64_t* __restrict__ offsets, uint64_t capacity, uint32_t* __restrict__ out_c1,
-                                                                uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1, uint32_t* __restrict__ out_b2,
-                                                                uint8_t* __restrict__ out_flags) {
+                                                                const uint64_t* __restrict__ offsets, uint2* __restrict__ pairs) {
     __shared__ uint32_t s_warp_cnt[SW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nw = min(*wide_count, SW_WIDE_CAP);
@@ -413,12 +299,7 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_con
                 if (k < warp) before += c;
                 round_total += c;
             }
-            if (EMIT && ok) {
-                const uint64_t pos = running + before + __popc(bal & ((1u << lane) - 1u));
-                if (pos < capacity) {
-                    out_c1[pos] = mi.x; out_c2[pos] = mj.x; out_b1[pos] = mi.y; out_b2[pos] = mj.y; out_flags[pos] = uint8_t(pf);
-                }
-            }
+            if (EMIT && ok) pairs[running + before + __popc(bal & ((1u << lane) - 1u))] = make_uint2(uint32_t(i), uint32_t(j));
             running += round_total;
             total += round_total;
             __syncthreads();
@@ -498,6 +379,12 @@ __global__ void __launch_bounds__(1024) scan_apply(const uint32_t* __restrict__ 
     if (i < n) offsets[i] = excl + block_offsets[blockIdx.x];
 }
 
+}  // namespace
+}  // namespace avn
+#include "broadphase_cells.cuh"
+namespace avn {
+namespace {
+
 template <class S>
 class Broadphase final : public BroadphaseBase {
     using K = typename KeyOf<S>::type;
@@ -549,7 +436,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_, grid_, ck0_, ck1_, cv0_, cv1_, cbounds_, pairs_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -642,16 +529,40 @@ AvnStatus Broadphase<S>::run() {
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
         sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
         sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
-        const int grid = std::min((n + SW_TILE - 1) / SW_TILE, sm_count_ * 16);
-        sweep_kernel<S, false><<<grid, SW_THREADS, 0, stream_>>>(sw, counts_.as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-        // wide intervals: at most n / SW_WIDE of them can exist per "layer" of overlap; the grid's y dimension strides the list
+        // (y, z) cell grid under the x-sorted ranks: stats -> cell ids -> stable 2-pass radix sort of the ranks by cell id -> cell bounds
+        AVN_CUDA(grid_.ensure(sizeof(CellGrid<S>)));
+        AVN_CUDA(ck0_.ensure(size_t(n) * 4)); AVN_CUDA(ck1_.ensure(size_t(n) * 4)); AVN_CUDA(cv0_.ensure(size_t(n) * 4)); AVN_CUDA(cv1_.ensure(size_t(n) * 4));
+        AVN_CUDA(cbounds_.ensure(size_t(2) * 0x10000 * 4));
+        CellGrid<S>* d_grid = grid_.as<CellGrid<S>>();
+        int* cstart = cbounds_.as<int>();
+        int* cend = cbounds_.as<int>() + 0x10000;
+        yz_stats<S><<<1, 1024, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid);
+        cell_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, ck0_.as<uint32_t>(), cv0_.as<uint32_t>());
+        {
+            uint32_t* cka = ck0_.as<uint32_t>(); uint32_t* ckb = ck1_.as<uint32_t>();
+            uint32_t* cva = cv0_.as<uint32_t>(); uint32_t* cvb = cv1_.as<uint32_t>();
+            for (int pass = 0; pass < 2; ++pass) {
+                rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, n, 8 * pass, hist_.as<uint32_t>(), nblocks);
+                rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+                rs_scatter<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+                std::swap(cka, ckb);
+                std::swap(cva, cvb);
+            }
+        }
+        AVN_CUDA(cudaMemsetAsync(cstart, 0x7f, size_t(0x10000) * 4, stream_));
+        AVN_CUDA(cudaMemsetAsync(cend, 0, size_t(0x10000) * 4, stream_));
+        cell_bounds<<<(n + 255) / 256, 256, 0, stream_>>>(ck0_.as<uint32_t>(), n, cstart, cend);
+        CellSweep<S> cs;
+        cs.grid = d_grid; cs.cranks = cv0_.as<uint32_t>(); cs.cstart = cstart; cs.cend = cend;
+        const int grid = std::min((n + (256 / CG_GROUP) - 1) / (256 / CG_GROUP), sm_count_ * 32);
+        sweep_cells_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, cs, counts_.as<uint32_t>(), nullptr, nullptr);
+        // intervals with a huge x-window: brute force, one block per SW_SUB candidates; the grid's y dimension strides the wide list
         const int nsub = (n + SW_SUB - 1) / SW_SUB;
         const int wide_rows = 64;
         AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
-        sweep_wide_kernel<S, false><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, 0,
-                                                                                       nullptr, nullptr, nullptr, nullptr, nullptr);
+        sweep_wide_kernel<S, false><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr);
         wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
-        ++launches_;
+        launches_ += 13;
         const int sblocks = (n + 1023) / 1024;
         AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
         scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
@@ -666,11 +577,15 @@ AvnStatus Broadphase<S>::run() {
         if (total > 0) {
             AVN_CUDA(o_c1_.ensure(total * 4)); AVN_CUDA(o_c2_.ensure(total * 4)); AVN_CUDA(o_b1_.ensure(total * 4)); AVN_CUDA(o_b2_.ensure(total * 4));
             AVN_CUDA(o_fl_.ensure(total));
-            sweep_kernel<S, true><<<grid, SW_THREADS, 0, stream_>>>(sw, nullptr, offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
-                                                            o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+            AVN_CUDA(pairs_.ensure(total * sizeof(uint2)));
+            uint2* pairs = pairs_.as<uint2>();
+            sweep_cells_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, cs, nullptr, offsets_.as<uint64_t>(), pairs);
             sweep_wide_kernel<S, true><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
-                                                                                          offsets_.as<uint64_t>(), total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
-                                                                                          o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+                                                                                          offsets_.as<uint64_t>(), pairs);
+            segment_sort<<<(n + 255) / 256, 256, 0, stream_>>>(offsets_.as<uint64_t>(), wide_flag_.as<uint8_t>(), n, pairs);
+            materialize_pairs<S><<<unsigned((total + 255) / 256), 256, 0, stream_>>>(sw, pairs, total, total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
+                                                                                  o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+            launches_ += 2;
             launches_ += 2;
         }
     }
