@@ -67,15 +67,23 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
     hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// exclusive scan of `len` counters by one block (len = 256 * nblocks, a few 10^4 at most)
+// exclusive scan of `len` counters by one block (len = 256 * nblocks: 12 544 for 100k keys, 125 184 for 1M).  Each thread owns
+// RS_SCAN_ITEMS consecutive counters per iteration (serial sum, block scan of the sums, serial write-back), so 1M keys take 8 iterations.
+constexpr int RS_SCAN_ITEMS = 16;
 __global__ void __launch_bounds__(1024) rs_scan(uint32_t* data, int len) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < len; base += 1024) {
-        int i = base + threadIdx.x;
-        uint32_t v = i < len ? data[i] : 0u;
+    for (int base = 0; base < len; base += 1024 * RS_SCAN_ITEMS) {
+        const int i0 = base + threadIdx.x * RS_SCAN_ITEMS;
+        uint32_t item[RS_SCAN_ITEMS];
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < RS_SCAN_ITEMS; ++k) {
+            item[k] = (i0 + k < len) ? data[i0 + k] : 0u;
+            v += item[k];
+        }
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -94,10 +102,14 @@ __global__ void __launch_bounds__(1024) rs_scan(uint32_t* data, int len) {
             warp_sums[threadIdx.x] = z - w;  // exclusive prefix of the warp totals
         }
         __syncthreads();
-        uint32_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
-        if (i < len) data[i] = excl;
+        uint32_t run = x - v + warp_sums[threadIdx.x >> 5] + carry;
+#pragma unroll
+        for (int k = 0; k < RS_SCAN_ITEMS; ++k) {
+            if (i0 + k < len) data[i0 + k] = run;
+            run += item[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 1023) carry = run;
         __syncthreads();
     }
 }
@@ -186,13 +198,15 @@ __global__ void gather_sorted(const uint32_t* __restrict__ order, int n, const S
 }
 
 // end[i] = first j > i with min.x[j] > max.x[i]  (the `break` of broad_phase.rs:390-392)
-// Intervals with more than SW_WIDE candidates (a ground slab spanning the whole scene) would serialise one warp of the
-// tiled sweep for the whole array; they go to a list that sweep_wide_kernel handles with one block per interval.
+// Intervals with more than SW_WIDE x-candidates whose (y, z) footprint also covers more than SW_WIDE cells (a ground slab under the
+// whole scene) go to a list that sweep_wide_kernel sweeps brute force, one block per SW_SUB candidates.
 constexpr int SW_WIDE = 4096;
 constexpr int SW_WIDE_CAP = 1 << 14;   // intervals beyond the cap stay in the tiled sweep (correct, only slower)
+template <class S> struct CellGrid;
+template <class S> __device__ __forceinline__ long long query_cell_count(const CellGrid<S>& g, Vec4<S> yi);
 template <class S>
-__global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, int n, int* __restrict__ end, int* __restrict__ wide_list,
-                             int* __restrict__ wide_count, uint8_t* __restrict__ is_wide) {
+__global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, const Vec4<S>* __restrict__ yz, const CellGrid<S>* __restrict__ grid,
+                             int n, int* __restrict__ end, int* __restrict__ wide_list, int* __restrict__ wide_count, uint8_t* __restrict__ is_wide) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     S m = maxx[i];
@@ -203,7 +217,8 @@ __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ m
     }
     end[i] = lo;
     uint8_t wide = 0;
-    if (lo - i - 1 > SW_WIDE) {
+    // wide = a large x-window AND a (y, z) footprint over many cells: neither the cell lookup nor one 16-lane group can serve it
+    if (lo - i - 1 > SW_WIDE && query_cell_count(*grid, yz[i]) > SW_WIDE) {
         int slot = atomicAdd(wide_count, 1);
         if (slot < SW_WIDE_CAP) { wide_list[slot] = i; wide = 1; }
     }
@@ -436,7 +451,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_, grid_, ck0_, ck1_, cv0_, cv1_, cbounds_, pairs_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_, grid_, ck0_, ck1_, cv0_, cv1_, cbounds_, pairs_, stats_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -519,12 +534,6 @@ AvnStatus Broadphase<S>::run() {
         gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
                                                                s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
                                                                s_flags_.as<uint8_t>());
-        AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
-        AVN_CUDA(wide_flag_.ensure(size_t(n)));
-        int* wide_count = wide_.as<int>();
-        int* wide_list = wide_.as<int>() + 1;
-        AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
-        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), n, s_end_.as<int>(), wide_list, wide_count, wide_flag_.as<uint8_t>());
         Sweep<S> sw;
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
         sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
@@ -536,7 +545,16 @@ AvnStatus Broadphase<S>::run() {
         CellGrid<S>* d_grid = grid_.as<CellGrid<S>>();
         int* cstart = cbounds_.as<int>();
         int* cend = cbounds_.as<int>() + 0x10000;
-        yz_stats<S><<<1, 1024, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid);
+        AVN_CUDA(stats_.ensure(size_t(YZ_BLOCKS) * sizeof(YzPartial<S>)));
+        yz_stats<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, stats_.as<YzPartial<S>>());
+        yz_grid<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), YZ_BLOCKS, n, d_grid);
+        AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
+        AVN_CUDA(wide_flag_.ensure(size_t(n)));
+        int* wide_count = wide_.as<int>();
+        int* wide_list = wide_.as<int>() + 1;
+        AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
+        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), d_grid, n, s_end_.as<int>(), wide_list, wide_count,
+                                                              wide_flag_.as<uint8_t>());
         cell_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, ck0_.as<uint32_t>(), cv0_.as<uint32_t>());
         {
             uint32_t* cka = ck0_.as<uint32_t>(); uint32_t* ckb = ck1_.as<uint32_t>();

@@ -28,19 +28,18 @@ struct CellGrid {
     int ny, nz;
 };
 
-struct GridStats {   // raw reductions, filled by yz_stats
-    double sum_ey, sum_ez;
-    float _pad;
-};
-
-// min/max of the min corners, sum and max of the extents (one block; n is at most a few 10^6)
+// per-block partial reductions of yz_stats
 template <class S>
-__global__ void __launch_bounds__(1024) yz_stats(const Vec4<S>* __restrict__ yz, int n, CellGrid<S>* __restrict__ grid) {
-    __shared__ S s_min_y[32], s_max_y[32], s_min_z[32], s_max_z[32], s_max_ey[32], s_max_ez[32];
-    __shared__ double s_sum_ey[32], s_sum_ez[32];
+struct YzPartial { S min_y, max_y, min_z, max_z, max_ey, max_ez; double sum_ey, sum_ez; };
+constexpr int YZ_BLOCKS = 296;
+
+// min/max of the min corners, sum and max of the extents: one partial per block ...
+template <class S>
+__global__ void __launch_bounds__(256) yz_stats(const Vec4<S>* __restrict__ yz, int n, YzPartial<S>* __restrict__ partial) {
+    __shared__ YzPartial<S> s_part[8];
     S mny = S(INFINITY), mxy = S(-INFINITY), mnz = S(INFINITY), mxz = S(-INFINITY), mey = 0, mez = 0;
     double sey = 0, sez = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Vec4<S> v = yz[i];
         S ey = v.y - v.x, ez = v.w - v.z;
         mny = avn_min(mny, v.x); mxy = avn_max(mxy, v.x); mnz = avn_min(mnz, v.z); mxz = avn_max(mxz, v.z);
@@ -54,38 +53,59 @@ __global__ void __launch_bounds__(1024) yz_stats(const Vec4<S>* __restrict__ yz,
         mey = avn_max(mey, __shfl_xor_sync(0xffffffffu, mey, o)); mez = avn_max(mez, __shfl_xor_sync(0xffffffffu, mez, o));
         sey += __shfl_xor_sync(0xffffffffu, sey, o); sez += __shfl_xor_sync(0xffffffffu, sez, o);
     }
-    const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        s_min_y[w] = mny; s_max_y[w] = mxy; s_min_z[w] = mnz; s_max_z[w] = mxz; s_max_ey[w] = mey; s_max_ez[w] = mez; s_sum_ey[w] = sey; s_sum_ez[w] = sez;
+        YzPartial<S> p; p.min_y = mny; p.max_y = mxy; p.min_z = mnz; p.max_z = mxz; p.max_ey = mey; p.max_ez = mez; p.sum_ey = sey; p.sum_ez = sez;
+        s_part[threadIdx.x >> 5] = p;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 32; ++k) {
-            mny = avn_min(mny, s_min_y[k]); mxy = avn_max(mxy, s_max_y[k]); mnz = avn_min(mnz, s_min_z[k]); mxz = avn_max(mxz, s_max_z[k]);
-            mey = avn_max(mey, s_max_ey[k]); mez = avn_max(mez, s_max_ez[k]); sey += s_sum_ey[k]; sez += s_sum_ez[k];
+        YzPartial<S> p = s_part[0];
+        for (int k = 1; k < 8; ++k) {
+            const YzPartial<S>& q = s_part[k];
+            p.min_y = avn_min(p.min_y, q.min_y); p.max_y = avn_max(p.max_y, q.max_y); p.min_z = avn_min(p.min_z, q.min_z); p.max_z = avn_max(p.max_z, q.max_z);
+            p.max_ey = avn_max(p.max_ey, q.max_ey); p.max_ez = avn_max(p.max_ez, q.max_ez); p.sum_ey += q.sum_ey; p.sum_ez += q.sum_ez;
         }
-        // "small" bound per axis: the largest extent, unless it exceeds 4x the mean — then 4x the mean (larger ones become "large")
-        S mean_y = S(sey / n), mean_z = S(sez / n);
-        S edge_y = mey <= S(4) * mean_y ? mey : S(4) * mean_y;
-        S edge_z = mez <= S(4) * mean_z ? mez : S(4) * mean_z;
-        S range_y = mxy - mny, range_z = mxz - mnz;
-        S cy = avn_max(edge_y, range_y / S(CG_MAX_AXIS)), cz = avn_max(edge_z, range_z / S(CG_MAX_AXIS));
-        int ny = cy > S(0) ? int(range_y / cy) + 1 : 1, nz = cz > S(0) ? int(range_z / cz) + 1 : 1;
-        ny = max(1, min(ny, CG_MAX_AXIS)); nz = max(1, min(nz, CG_MAX_AXIS));
-        while ((long long)ny * nz > CG_MAX_CELLS) {   // coarsen the finer axis until the ids fit 16 bits (cells only get larger: still exact)
-            if (ny >= nz) { ny = (ny + 1) / 2; cy = cy * S(2); } else { nz = (nz + 1) / 2; cz = cz * S(2); }
-        }
-        CellGrid<S> g;
-        g.y0 = mny; g.z0 = mnz; g.inv_cy = cy > S(0) ? S(1) / cy : S(0); g.inv_cz = cz > S(0) ? S(1) / cz : S(0);
-        g.edge_y = edge_y; g.edge_z = edge_z; g.ny = ny; g.nz = nz;
-        *grid = g;
+        partial[blockIdx.x] = p;
     }
+}
+// ... and one thread turns the partials into the grid parameters
+template <class S>
+__global__ void yz_grid(const YzPartial<S>* __restrict__ partial, int nparts, int n, CellGrid<S>* __restrict__ grid) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    YzPartial<S> p = partial[0];
+    for (int k = 1; k < nparts; ++k) {
+        const YzPartial<S>& q = partial[k];
+        p.min_y = avn_min(p.min_y, q.min_y); p.max_y = avn_max(p.max_y, q.max_y); p.min_z = avn_min(p.min_z, q.min_z); p.max_z = avn_max(p.max_z, q.max_z);
+        p.max_ey = avn_max(p.max_ey, q.max_ey); p.max_ez = avn_max(p.max_ez, q.max_ez); p.sum_ey += q.sum_ey; p.sum_ez += q.sum_ez;
+    }
+    // "small" bound per axis: the largest extent, unless it exceeds 4x the mean — then 4x the mean (larger ones become "large")
+    S mean_y = S(p.sum_ey / n), mean_z = S(p.sum_ez / n);
+    S edge_y = p.max_ey <= S(4) * mean_y ? p.max_ey : S(4) * mean_y;
+    S edge_z = p.max_ez <= S(4) * mean_z ? p.max_ez : S(4) * mean_z;
+    S range_y = p.max_y - p.min_y, range_z = p.max_z - p.min_z;
+    S cy = avn_max(edge_y, range_y / S(CG_MAX_AXIS)), cz = avn_max(edge_z, range_z / S(CG_MAX_AXIS));
+    int ny = cy > S(0) ? int(range_y / cy) + 1 : 1, nz = cz > S(0) ? int(range_z / cz) + 1 : 1;
+    ny = max(1, min(ny, CG_MAX_AXIS)); nz = max(1, min(nz, CG_MAX_AXIS));
+    while ((long long)ny * nz > CG_MAX_CELLS) {   // coarsen the finer axis until the ids fit 16 bits (cells only get larger: still exact)
+        if (ny >= nz) { ny = (ny + 1) / 2; cy = cy * S(2); } else { nz = (nz + 1) / 2; cz = cz * S(2); }
+    }
+    CellGrid<S> g;
+    g.y0 = p.min_y; g.z0 = p.min_z; g.inv_cy = cy > S(0) ? S(1) / cy : S(0); g.inv_cz = cz > S(0) ? S(1) / cz : S(0);
+    g.edge_y = edge_y; g.edge_z = edge_z; g.ny = ny; g.nz = nz;
+    *grid = g;
 }
 
 template <class S> __device__ __forceinline__ int cell_coord(S v, S v0, S inv_c, int n) {
     S t = (v - v0) * inv_c;
     int c = t > S(0) ? (t < S(n) ? int(t) : n - 1) : 0;   // clamps; NaN cannot occur (non-finite AABBs never reach the intervals)
     return c;
+}
+
+// number of cells in the query range of an interval with y/z bounds yi (the cells a small overlapping j can live in)
+template <class S> __device__ __forceinline__ long long query_cell_count(const CellGrid<S>& g, Vec4<S> yi) {
+    const int cy_lo = cell_coord(yi.x - g.edge_y, g.y0, g.inv_cy, g.ny), cy_hi = cell_coord(yi.y, g.y0, g.inv_cy, g.ny);
+    const int cz_lo = cell_coord(yi.z - g.edge_z, g.z0, g.inv_cz, g.nz), cz_hi = cell_coord(yi.w, g.z0, g.inv_cz, g.nz);
+    return (long long)(cy_hi - cy_lo + 1) * (cz_hi - cz_lo + 1);
 }
 
 template <class S>
@@ -163,6 +183,17 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
                 const int cy_lo = cell_coord(yi.x - g.edge_y, g.y0, g.inv_cy, g.ny), cy_hi = cell_coord(yi.y, g.y0, g.inv_cy, g.ny);
                 const int cz_lo = cell_coord(yi.z - g.edge_z, g.z0, g.inv_cz, g.nz), cz_hi = cell_coord(yi.w, g.z0, g.inv_cz, g.nz);
                 const int wz = cz_hi - cz_lo + 1, ncell = (cy_hi - cy_lo + 1) * wz;
+                if (ncell > e - i - 1) {
+                    // more cells than x-candidates (a big footprint with a short window): test the window directly, lane-strided
+                    for (int j = i + 1 + lane; j < e; j += CG_GROUP) {
+                        const Vec4<S> yj = s.yz[j];
+                        if ((yi.x > yj.y || yi.y < yj.x) || (yi.z > yj.w || yi.w < yj.z)) continue;
+                        uint32_t pf; uint4 mj;
+                        if (!pair_filters(s, mi, fi, j, pf, mj)) continue;
+                        if (EMIT && pass == 1) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
+                        ++wr;
+                    }
+                } else {
                 for (int q = lane; q < ncell; q += CG_GROUP) {
                     const int cell = (cy_lo + q / wz) * g.nz + (cz_lo + q % wz);
                     int lo = cs.cstart[cell], hi = cs.cend[cell];
@@ -194,6 +225,7 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
                             ++wr;
                         }
                     }
+                }
                 }
             }
             if (pass == 0) mine = wr;
