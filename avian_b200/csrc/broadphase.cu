@@ -534,10 +534,6 @@ AvnStatus Broadphase<S>::run() {
         gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
                                                                s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
                                                                s_flags_.as<uint8_t>());
-        Sweep<S> sw;
-        sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
-        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
-        sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
         // (y, z) cell grid under the x-sorted ranks: stats -> cell ids -> stable 2-pass radix sort of the ranks by cell id -> cell bounds
         AVN_CUDA(grid_.ensure(sizeof(CellGrid<S>)));
         AVN_CUDA(ck0_.ensure(size_t(n) * 4)); AVN_CUDA(ck1_.ensure(size_t(n) * 4)); AVN_CUDA(cv0_.ensure(size_t(n) * 4)); AVN_CUDA(cv1_.ensure(size_t(n) * 4));
@@ -555,6 +551,10 @@ AvnStatus Broadphase<S>::run() {
         AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
         sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), d_grid, n, s_end_.as<int>(), wide_list, wide_count,
                                                               wide_flag_.as<uint8_t>());
+        Sweep<S> sw;
+        sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
+        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
+        sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
         cell_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, ck0_.as<uint32_t>(), cv0_.as<uint32_t>());
         {
             uint32_t* cka = ck0_.as<uint32_t>(); uint32_t* ckb = ck1_.as<uint32_t>();
