@@ -198,7 +198,7 @@ __global__ void gather_sorted(const uint32_t* __restrict__ order, int n, const S
 }
 
 // end[i] = first j > i with min.x[j] > max.x[i]  (the `break` of broad_phase.rs:390-392)
-// Intervals with more than SW_WIDE x-candidates whose (y, z) footprint also covers more than SW_WIDE cells (a ground slab under the
+// Intervals with more than SW_WIDE x-candidates whose (y, z) footprint also covers more than 32 cells (a ground slab under the
 // whole scene) go to a list that sweep_wide_kernel sweeps brute force, one block per SW_SUB candidates.
 constexpr int SW_WIDE = 4096;
 constexpr int SW_WIDE_CAP = 1 << 14;   // intervals beyond the cap stay in the tiled sweep (correct, only slower)
@@ -217,8 +217,9 @@ __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ m
     }
     end[i] = lo;
     uint8_t wide = 0;
-    // wide = a large x-window AND a (y, z) footprint over many cells: neither the cell lookup nor one 16-lane group can serve it
-    if (lo - i - 1 > SW_WIDE && query_cell_count(*grid, yz[i]) > SW_WIDE) {
+    // wide = a large x-window AND a (y, z) footprint well beyond the 3x3 cells of a small interval: one 16-lane group would have to
+    // walk a large part of the window through many cell lists, so the interval is swept brute force by whole blocks instead
+    if (lo - i - 1 > SW_WIDE && query_cell_count(*grid, yz[i]) > 32) {
         int slot = atomicAdd(wide_count, 1);
         if (slot < SW_WIDE_CAP) { wide_list[slot] = i; wide = 1; }
     }
