@@ -452,7 +452,7 @@ class Broadphase final : public BroadphaseBase {
     const uint64_t* d_jdis_ = nullptr; uint64_t jdis_mask_ = 0;
     DevBuf b_min_, b_max_, b_col_, b_body_, b_memb_, b_filt_, b_flags_, b_exk_, b_ext_, b_jdk_, b_jdt_;
     DevBuf k0_, k1_, v0_, v1_, hist_;
-    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_, grid_, ck0_, ck1_, cv0_, cv1_, cbounds_, pairs_, stats_;
+    DevBuf s_minx_, s_maxx_, s_yz_, s_meta_, s_flags_, s_end_, counts_, offsets_, block_sums_, wide_, wide_sub_, wide_flag_, grid_, ck0_, ck1_, cv0_, cv1_, cbounds_, pairs_, stats_, stats2_;
     DevBuf o_c1_, o_c2_, o_b1_, o_b2_, o_fl_;
     uint32_t* d_order_ = nullptr;
 };
@@ -543,8 +543,11 @@ AvnStatus Broadphase<S>::run() {
         int* cstart = cbounds_.as<int>();
         int* cend = cbounds_.as<int>() + 0x10000;
         AVN_CUDA(stats_.ensure(size_t(YZ_BLOCKS) * sizeof(YzPartial<S>)));
+        AVN_CUDA(stats2_.ensure(size_t(2) * YZ_BLOCKS * sizeof(S)));
         yz_stats<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, stats_.as<YzPartial<S>>());
-        yz_grid<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), YZ_BLOCKS, n, d_grid);
+        yz_fold<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), YZ_BLOCKS, n, d_grid);
+        yz_small_max<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, stats2_.as<S>());
+        yz_grid<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), stats2_.as<S>(), YZ_BLOCKS, n, d_grid);
         AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
         AVN_CUDA(wide_flag_.ensure(size_t(n)));
         int* wide_count = wide_.as<int>();

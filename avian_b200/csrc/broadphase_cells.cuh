@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(256) yz_stats(const Vec4<S>* __restrict__ yz, 
         partial[blockIdx.x] = p;
     }
 }
-// ... and one thread turns the partials into the grid parameters
+// ... one thread folds the partials (into partial[0]) and derives the "large" thresholds 4 x mean extent (stored in grid->edge_*) ...
 template <class S>
-__global__ void yz_grid(const YzPartial<S>* __restrict__ partial, int nparts, int n, CellGrid<S>* __restrict__ grid) {
+__global__ void yz_fold(YzPartial<S>* __restrict__ partial, int nparts, int n, CellGrid<S>* __restrict__ grid) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     YzPartial<S> p = partial[0];
     for (int k = 1; k < nparts; ++k) {
@@ -78,10 +78,39 @@ __global__ void yz_grid(const YzPartial<S>* __restrict__ partial, int nparts, in
         p.min_y = avn_min(p.min_y, q.min_y); p.max_y = avn_max(p.max_y, q.max_y); p.min_z = avn_min(p.min_z, q.min_z); p.max_z = avn_max(p.max_z, q.max_z);
         p.max_ey = avn_max(p.max_ey, q.max_ey); p.max_ez = avn_max(p.max_ez, q.max_ez); p.sum_ey += q.sum_ey; p.sum_ez += q.sum_ez;
     }
-    // "small" bound per axis: the largest extent, unless it exceeds 4x the mean — then 4x the mean (larger ones become "large")
-    S mean_y = S(p.sum_ey / n), mean_z = S(p.sum_ez / n);
-    S edge_y = p.max_ey <= S(4) * mean_y ? p.max_ey : S(4) * mean_y;
-    S edge_z = p.max_ez <= S(4) * mean_z ? p.max_ez : S(4) * mean_z;
+    partial[0] = p;
+    grid->edge_y = S(4) * S(p.sum_ey / n);
+    grid->edge_z = S(4) * S(p.sum_ez / n);
+}
+// ... a second pass finds the largest extent that is still "small" (<= the threshold) on each axis: that is the cell edge ...
+template <class S>
+__global__ void __launch_bounds__(256) yz_small_max(const Vec4<S>* __restrict__ yz, int n, const CellGrid<S>* __restrict__ grid, S* __restrict__ out /*[2*gridDim.x]*/) {
+    __shared__ S s_y[8], s_z[8];
+    const S thr_y = grid->edge_y, thr_z = grid->edge_z;
+    S my = 0, mz = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Vec4<S> v = yz[i];
+        S ey = v.y - v.x, ez = v.w - v.z;
+        if (ey <= thr_y) my = avn_max(my, ey);
+        if (ez <= thr_z) mz = avn_max(mz, ez);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { my = avn_max(my, __shfl_xor_sync(0xffffffffu, my, o)); mz = avn_max(mz, __shfl_xor_sync(0xffffffffu, mz, o)); }
+    if ((threadIdx.x & 31) == 0) { s_y[threadIdx.x >> 5] = my; s_z[threadIdx.x >> 5] = mz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { my = avn_max(my, s_y[k]); mz = avn_max(mz, s_z[k]); }
+        out[2 * blockIdx.x] = my; out[2 * blockIdx.x + 1] = mz;
+    }
+}
+// ... and one thread turns everything into the grid parameters
+template <class S>
+__global__ void yz_grid(const YzPartial<S>* __restrict__ partial, const S* __restrict__ small_max, int nparts, int n, CellGrid<S>* __restrict__ grid) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const YzPartial<S> p = partial[0];
+    S edge_y = 0, edge_z = 0;
+    for (int k = 0; k < nparts; ++k) { edge_y = avn_max(edge_y, small_max[2 * k]); edge_z = avn_max(edge_z, small_max[2 * k + 1]); }
+    // extents above 4 x mean are "large"; when every interval exceeds its axis threshold (impossible for a mean) edge stays 0 = all large
     S range_y = p.max_y - p.min_y, range_z = p.max_z - p.min_z;
     S cy = avn_max(edge_y, range_y / S(CG_MAX_AXIS)), cz = avn_max(edge_z, range_z / S(CG_MAX_AXIS));
     int ny = cy > S(0) ? int(range_y / cy) + 1 : 1, nz = cz > S(0) ? int(range_z / cz) + 1 : 1;
