@@ -78,6 +78,16 @@ class AvnPairList(C.Structure):
     _fields_ = [("capacity", C.c_uint64), ("count", C.c_uint64)] + [(n, _vp) for n in ("collider1", "collider2", "body1", "body2", "flags")]
 
 
+class AvnAabbParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("contact_tolerance", C.c_double), ("default_speculative_margin", C.c_double)]
+
+
+class AvnColliderColumns(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in ("shape", "dims", "position", "rotation", "linear_velocity", "angular_velocity", "collision_margin", "speculative_margin",
+                           "aabb_min", "aabb_max")]
+
+
 class AvnTimings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "prepare_ms", "substep_loop_ms", "finalize_ms", "d2h_ms", "broad_phase_ms", "total_ms")] + [
         (n, C.c_uint32) for n in ("kernel_launches", "contact_constraint_count", "joint_levels", "active_colors", "_pad")]
@@ -320,6 +330,7 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "broadphase_download": ([_vp, P(AvnPairList)], C.c_int),
         "get_timings": ([_vp, P(AvnTimings)], C.c_int),
         "joint_levels": ([P(AvnBodyColumns), P(AvnJointSet), _vp, P(C.c_uint32)], C.c_int),
+        "update_aabbs": ([_vp, P(AvnAabbParams), P(AvnColliderColumns)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -330,7 +341,38 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
 ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
-    "avn_broadphase_download", "avn_get_timings", "avn_joint_levels"]
+    "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs"]
+
+
+@dataclass
+class Colliders:
+    """Collider columns of avn_update_aabbs (AvnColliderColumns)."""
+    shape: np.ndarray            # uint8[C]
+    dims: np.ndarray             # [C,3]
+    position: np.ndarray
+    rotation: np.ndarray
+    linear_velocity: np.ndarray | None = None
+    angular_velocity: np.ndarray | None = None
+    collision_margin: np.ndarray | None = None
+    speculative_margin: np.ndarray | None = None
+    aabb_min: np.ndarray | None = None
+    aabb_max: np.ndarray | None = None
+
+    def as_struct(self) -> "AvnColliderColumns":
+        n = int(self.position.shape[0])
+        if self.aabb_min is None:
+            self.aabb_min = np.zeros((n, 3), dtype=self.position.dtype)
+            self.aabb_max = np.zeros((n, 3), dtype=self.position.dtype)
+        s = AvnColliderColumns()
+        s.count = n
+        for name, _ in AvnColliderColumns._fields_[2:]:
+            setattr(s, name, _ptr(getattr(self, name)))
+        return s
+
+
+def aabb_params(dt: float, contact_tolerance: float = 0.005, default_speculative_margin: float = float("inf")) -> "AvnAabbParams":
+    """NarrowPhaseConfig defaults (narrow_phase/mod.rs:247-255) times PhysicsLengthUnit = 1."""
+    return AvnAabbParams(dt, contact_tolerance, default_speculative_margin)
 
 
 def joint_levels(bodies: "Bodies", joints: "JointSet"):
@@ -466,6 +508,11 @@ class Context:
         self._check(self.lib.avn_broadphase_download(self.handle, C.byref(s)))
         out.count = int(s.count)
         return out
+
+    def update_aabbs(self, params: "AvnAabbParams", colliders: "Colliders") -> None:
+        c = colliders.as_struct()
+        self._keep_aabb = (params, colliders, c)
+        self._check(self.lib.avn_update_aabbs(self.handle, C.byref(params), C.byref(c)))
 
     def timings(self) -> dict:
         t = AvnTimings()

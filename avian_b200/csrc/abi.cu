@@ -12,6 +12,7 @@ struct AvnContext {
     avn::ErrorSink err;
     std::unique_ptr<avn::SolverBase> solver;
     std::unique_ptr<avn::BroadphaseBase> broadphase;
+    std::unique_ptr<avn::AabbBase> aabbs;
     AvnTimings last{};
 };
 
@@ -53,7 +54,8 @@ AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
     ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
     ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
-    if (!ctx->solver || !ctx->broadphase) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
+    ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
+    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
     *out_ctx = ctx.release();
     return AVN_OK;
 }
@@ -64,6 +66,7 @@ void avn_destroy(AvnContext* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->solver.reset();
     ctx->broadphase.reset();
+    ctx->aabbs.reset();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -136,6 +139,12 @@ AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* ou
     if (st != AVN_OK) return st;
     if ((st = avn_broadphase_run(ctx)) != AVN_OK) return st;
     return avn_broadphase_download(ctx, out_pairs);
+}
+
+AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColliderColumns* colliders) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->aabbs->update(params, colliders);
 }
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {

@@ -68,6 +68,12 @@ struct BroadphaseBase {
     virtual void timings(AvnTimings* t) const = 0;
 };
 
+struct AabbBase {
+    virtual ~AabbBase() {}
+    virtual AvnStatus update(const AvnAabbParams* prm, AvnColliderColumns* colliders) = 0;
+};
+AabbBase* make_aabb_updater(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
+
 SolverBase* make_solver(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device);
 BroadphaseBase* make_broadphase(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, int device);
 

@@ -299,6 +299,38 @@ AvnStatus avn_broadphase_upload(AvnContext* ctx, AvnAabbColumns* aabbs);
 AvnStatus avn_broadphase_run(AvnContext* ctx);
 AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs);
 
+/* ---- collider AABBs (SURVEY.md 8f "next #2"): update_aabb for the shapes the device knows ------------------------------- */
+typedef enum AvnShape { AVN_SHAPE_CUBOID = 0, AVN_SHAPE_SPHERE = 1 } AvnShape;
+
+typedef struct AvnAabbParams {
+    double dt;                         /* Time::delta (full step, collider/backend.rs:536) */
+    double contact_tolerance;          /* PhysicsLengthUnit * NarrowPhaseConfig::contact_tolerance (default 0.005) */
+    double default_speculative_margin; /* PhysicsLengthUnit * NarrowPhaseConfig::default_speculative_margin (default Scalar::MAX: pass +inf) */
+} AvnAabbParams;
+
+typedef struct AvnColliderColumns {
+    uint32_t count;
+    uint32_t _pad;
+    const uint8_t* shape;              /* [C] AvnShape */
+    const void* dims;                  /* [C][3] cuboid half extents / sphere radius in [0] (scaled shape) */
+    const void* position;              /* [C][3] collider Position */
+    const void* rotation;              /* [C][4] collider Rotation */
+    const void* linear_velocity;       /* [C][3] the velocity update_aabb uses: the collider's own LinearVelocity, or its body's velocity at
+                                          the collider offset (backend.rs:560-580); NULL = 0 */
+    const void* angular_velocity;      /* [C][3] NULL = 0 */
+    const void* collision_margin;      /* [C] CollisionMargin; NULL = 0 */
+    const void* speculative_margin;    /* [C] SpeculativeMargin (+inf for SweptCcd); NULL = the default */
+    void* aabb_min;                    /* [C][3] out: ColliderAabb::min */
+    void* aabb_max;                    /* [C][3] out */
+} AvnColliderColumns;
+
+/*
+ * Replaces update_aabb::<Collider> (src/collision/collider/backend.rs:498-625) for cuboid and sphere colliders: swept AABB from the
+ * current pose to the pose after dt (rotation advanced by Quat::from_scaled_axis + fast_renormalize, translation clamped to the
+ * speculative margin), grown by contact_tolerance + collision margin.
+ */
+AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColliderColumns* colliders);
+
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
 /*

@@ -20,6 +20,8 @@ def lib():
         l.orc_solver_step.restype = C.c_int
         l.orc_broadphase.argtypes = [C.c_uint32, P(api.AvnAabbColumns), P(api.AvnPairList)]
         l.orc_broadphase.restype = C.c_int
+        l.orc_update_aabbs.argtypes = [C.c_uint32, P(api.AvnAabbParams), P(api.AvnColliderColumns)]
+        l.orc_update_aabbs.restype = C.c_int
         _lib = l
     return _lib
 
@@ -50,6 +52,12 @@ def broadphase(aabbs: api.Aabbs, capacity: int | None = None) -> api.PairList:
     assert st == 0, f"oracle broadphase failed: {st}"
     out.count = int(s.count)
     return out.trimmed()
+
+
+def update_aabbs(params, colliders: api.Colliders) -> None:
+    c = colliders.as_struct()
+    st = lib().orc_update_aabbs(_bits(colliders.position.dtype), C.byref(params), C.byref(c))
+    assert st == 0, f"oracle update_aabbs failed: {st}"
 
 
 class OracleBroadPhasePlugin(plugins.BroadPhasePlugin):
