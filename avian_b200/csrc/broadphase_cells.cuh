@@ -71,13 +71,22 @@ __global__ void __launch_bounds__(256) yz_stats(const Vec4<S>* __restrict__ yz, 
 // ... one thread folds the partials (into partial[0]) and derives the "large" thresholds 4 x mean extent (stored in grid->edge_*) ...
 template <class S>
 __global__ void yz_fold(YzPartial<S>* __restrict__ partial, int nparts, int n, CellGrid<S>* __restrict__ grid) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    YzPartial<S> p = partial[0];
-    for (int k = 1; k < nparts; ++k) {
+    // one warp: lanes stride the partials, then a shuffle reduction
+    YzPartial<S> p = partial[threadIdx.x < nparts ? threadIdx.x : 0];
+    for (int k = threadIdx.x + 32; k < nparts; k += 32) {
         const YzPartial<S>& q = partial[k];
         p.min_y = avn_min(p.min_y, q.min_y); p.max_y = avn_max(p.max_y, q.max_y); p.min_z = avn_min(p.min_z, q.min_z); p.max_z = avn_max(p.max_z, q.max_z);
         p.max_ey = avn_max(p.max_ey, q.max_ey); p.max_ez = avn_max(p.max_ez, q.max_ez); p.sum_ey += q.sum_ey; p.sum_ez += q.sum_ez;
     }
+    if (threadIdx.x >= nparts) { p.sum_ey = 0; p.sum_ez = 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p.min_y = avn_min(p.min_y, __shfl_xor_sync(0xffffffffu, p.min_y, o)); p.max_y = avn_max(p.max_y, __shfl_xor_sync(0xffffffffu, p.max_y, o));
+        p.min_z = avn_min(p.min_z, __shfl_xor_sync(0xffffffffu, p.min_z, o)); p.max_z = avn_max(p.max_z, __shfl_xor_sync(0xffffffffu, p.max_z, o));
+        p.max_ey = avn_max(p.max_ey, __shfl_xor_sync(0xffffffffu, p.max_ey, o)); p.max_ez = avn_max(p.max_ez, __shfl_xor_sync(0xffffffffu, p.max_ez, o));
+        p.sum_ey += __shfl_xor_sync(0xffffffffu, p.sum_ey, o); p.sum_ez += __shfl_xor_sync(0xffffffffu, p.sum_ez, o);
+    }
+    if (threadIdx.x != 0) return;
     partial[0] = p;
     grid->edge_y = S(4) * S(p.sum_ey / n);
     grid->edge_z = S(4) * S(p.sum_ez / n);
@@ -106,10 +115,12 @@ __global__ void __launch_bounds__(256) yz_small_max(const Vec4<S>* __restrict__ 
 // ... and one thread turns everything into the grid parameters
 template <class S>
 __global__ void yz_grid(const YzPartial<S>* __restrict__ partial, const S* __restrict__ small_max, int nparts, int n, CellGrid<S>* __restrict__ grid) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const YzPartial<S> p = partial[0];
     S edge_y = 0, edge_z = 0;
-    for (int k = 0; k < nparts; ++k) { edge_y = avn_max(edge_y, small_max[2 * k]); edge_z = avn_max(edge_z, small_max[2 * k + 1]); }
+    for (int k = threadIdx.x; k < nparts; k += 32) { edge_y = avn_max(edge_y, small_max[2 * k]); edge_z = avn_max(edge_z, small_max[2 * k + 1]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { edge_y = avn_max(edge_y, __shfl_xor_sync(0xffffffffu, edge_y, o)); edge_z = avn_max(edge_z, __shfl_xor_sync(0xffffffffu, edge_z, o)); }
+    if (threadIdx.x != 0) return;
     // extents above 4 x mean are "large"; when every interval exceeds its axis threshold (impossible for a mean) edge stays 0 = all large
     S range_y = p.max_y - p.min_y, range_z = p.max_z - p.min_z;
     S cy = avn_max(edge_y, range_y / S(CG_MAX_AXIS)), cz = avn_max(edge_z, range_z / S(CG_MAX_AXIS));
