@@ -386,16 +386,21 @@ __device__ __forceinline__ void stage_copy(Vec4<double>* dst, const Vec4<double>
     __pipeline_memcpy_async(dst, src, 16);
     __pipeline_memcpy_async(reinterpret_cast<char*>(dst) + 16, reinterpret_cast<const char*>(src) + 16, 16);
 }
-template <class S> __host__ __device__ constexpr size_t stage_bytes(int threads) { return size_t(STAGE_ROWS) * threads * sizeof(Vec4<S>); }
+// the tile only needs the rows of the widest manifold of the upload (single-point sphere contacts: a quarter of the tile, the rest
+// of the SM's shared-memory / L1 array stays L1)
+template <class S> __host__ __device__ constexpr size_t stage_bytes(int threads, int max_points = AVN_MAX_MANIFOLD_POINTS) {
+    return size_t(3 * max_points) * threads * sizeof(Vec4<S>);
+}
 
 // `slot` indexes the padded colour-major planes.  WAVE = false: barrier mode (a padding slot returns at once).
 // WAVE = true: every lane of the warp must call this (warp-collective wait); `ws` carries the position in the schedule.
-template <class S, int PASS, bool WAVE = false>
-__device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, int wave_substep = 0, int wave_it = 0) {
+// MAXP: compile-time bound on the points of a manifold (1 for sphere-only scenes: a quarter of the registers and no dead unrolled code)
+template <class S, int PASS, bool WAVE = false, int MAXP = AVN_MAX_MANIFOLD_POINTS>
+__device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, int wave_substep = 0, int wave_it = 0, bool lane_active = true) {
     const size_t MP = size_t(d.Mpad);
-    Vec4<S>* c = d.cst + slot;
+    Vec4<S>* c = d.cst + (lane_active ? slot : 0);
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
-    const int info = as_int(hidx.z);
+    const int info = lane_active ? as_int(hidx.z) : 0;   // an inactive lane of a partial chunk behaves like a padding slot
     const int np = info & CI_NP_MASK;
     if (!WAVE && np == 0) return;
     const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
@@ -403,7 +408,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     //      immutable part (planes written by prepare only, inertia) is fetched BEFORE waiting on the counters.
     Vec4<S> hn = mk4<S>(0, 0, 0, 0), ht1 = hn, htv = hn;
     BodyInertia<S> in1 = zero_inertia<S>(), in2 = zero_inertia<S>();
-    Vec4<S> PC[AVN_MAX_MANIFOLD_POINTS];
+    Vec4<S> PC[MAXP];
     constexpr bool SOLVE = (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX);
     Vec4<S>* const stage = stage_base<S>() + threadIdx.x;   // this thread's column; row r at stage[r * T]
     const int T = blockDim.x;
@@ -417,7 +422,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         if (!(info & CI_ZERO1)) in1 = unpack_inertia(ld4(&d.inr[2 * b1]), ld4(&d.inr[2 * b1 + 1]));
         if (!(info & CI_ZERO2)) in2 = unpack_inertia(ld4(&d.inr[2 * b2]), ld4(&d.inr[2 * b2 + 1]));
 #pragma unroll
-        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+        for (int k = 0; k < MAXP; ++k) {
             if (k < np) {
                 stage_copy(&ROW_A(k), &c[size_t(CP_ROW(k, 0)) * MP]);
                 stage_copy(&ROW_B(k), &c[size_t(CP_ROW(k, 1)) * MP]);
@@ -465,7 +470,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         dp2 = ldm<WAVE>(&d.dlt[2 * b2]); dq2 = ldm<WAVE>(&d.dlt[2 * b2 + 1]);
     }
 #pragma unroll
-    for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
+    for (int k = 0; k < MAXP; ++k)
         if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PC(k)) * MP]);
     __pipeline_wait_prior(0);  // this thread's staged rows have landed (only the issuing thread reads them)
 #ifdef AVN_WAVE_TRACE
@@ -484,7 +489,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     if (PASS == PASS_WARM) {
         // ContactConstraint::warm_start (contact/mod.rs:223-264)
 #pragma unroll
-        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+        for (int k = 0; k < MAXP; ++k) {
             if (k < np) {
                 const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
                 V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
@@ -500,7 +505,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         Q4<S> q2; q2.x = dq2.x; q2.y = dq2.y; q2.z = dq2.z; q2.w = dq2.w;
         const V3<S> delta_translation = xyz(dp2) - xyz(dp1);
 #pragma unroll
-        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+        for (int k = 0; k < MAXP; ++k) {
             if (k < np) {
                 const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
                 V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
@@ -533,7 +538,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
             const S friction = hn.w;
             const V3<S> surf = xyz(htv);
 #pragma unroll
-            for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+            for (int k = 0; k < MAXP; ++k) {
                 if (k < np) {
                     const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), PDk = ROW_D(k);
                     V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
@@ -570,7 +575,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
         const int iterations = np > 1 ? d.rest_iters : 1;
         for (int it = 0; it < iterations; ++it) {
 #pragma unroll
-            for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k) {
+            for (int k = 0; k < MAXP; ++k) {
                 if (k < np) {
                     const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), PDk = ROW_D(k);
                     if (PDk.w > -d.rest_threshold || PC[k].y == S(0)) continue;
@@ -595,7 +600,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 #endif
     if (PASS != PASS_WARM) {
 #pragma unroll
-        for (int k = 0; k < AVN_MAX_MANIFOLD_POINTS; ++k)
+        for (int k = 0; k < MAXP; ++k)
             if (k < np) st4(&c[size_t(CP_PC(k)) * MP], PC[k]);
     }
     if (WAVE && SOLVE) {
@@ -640,8 +645,8 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
 // ---------------------------------------------------------------------------------------------------------
 // WAVE: every lane of the warp calls this (i may be >= B: padding); `s` = substep index
 template <class S, bool WAVE = false>
-__device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, int i, int s = 0) {
-    const bool in_range = i < d.B;
+__device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, int i, int s = 0, bool lane_active = true) {
+    const bool in_range = lane_active && i < d.B;
     int f = 0;
     if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
     bool live = in_range && (f & BF_HAS_SOLVER_BODY);
@@ -703,8 +708,8 @@ __device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, i
 
 // integrate_positions (integrator/mod.rs:503-535)
 template <class S, bool WAVE = false>
-__device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, int i, int s = 0) {
-    const bool in_range = i < d.B;
+__device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, int i, int s = 0, bool lane_active = true) {
+    const bool in_range = lane_active && i < d.B;
     int f = 0;
     if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
     bool live = in_range && (f & BF_HAS_SOLVER_BODY);

@@ -51,21 +51,13 @@ class Solver final : public SolverBase {
         if (mode && !strcmp(mode, "phases")) use_mega_ = false;
         if (mode && !strcmp(mode, "barrier")) use_wave_ = false;   // megakernel with grid barriers between colours
         // register budget of the persistent kernel: 65536 / (128 threads * blocks per SM); more resident warps hide more
-        // latency, fewer registers spill more.  AVN_MEGA_BPS overrides the default for experiments.
+        // latency, fewer registers spill more.  Measured best (scripts/solver_timing.py): 3 blocks/SM for f32, 2 for f64 (whose
+        // state is twice as wide).  AVN_MEGA_BPS = 2|3|4 overrides the default for experiments.
         const char* bps = getenv("AVN_MEGA_BPS");
-        mega_bps_ = bps ? atoi(bps) : 3;
-        switch (mega_bps_) {
-            case 4: mega_fn_ = (const void*)step_megakernel<S, 4>; break;
-            case 5: mega_fn_ = (const void*)step_megakernel<S, 5>; break;
-            case 6: mega_fn_ = (const void*)step_megakernel<S, 6>; break;
-            default: mega_bps_ = 3; mega_fn_ = (const void*)step_megakernel<S, 3>; break;
-        }
-        int per_sm = 0;
-        if (cudaFuncSetAttribute(mega_fn_, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stage_bytes<S>(MEGA_BLOCK))) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_fn_, MEGA_BLOCK, stage_bytes<S>(MEGA_BLOCK)) == cudaSuccess && per_sm > 0)
-            mega_grid_ = per_sm * sm_count_;
-        else
-            coop_ok_ = false;
+        mega_bps_ = bps ? atoi(bps) : (sizeof(S) == 8 ? 2 : 3);
+        if (mega_bps_ < 2 || mega_bps_ > 4) mega_bps_ = 3;
+        if (mode && !strcmp(mode, "wave")) force_wave_ = true;
+        coop_ok_ = coop_ok_ && select_megakernel(AVN_MAX_MANIFOLD_POINTS);
         for (auto& e : ev_) cudaEventCreate(&e);
     }
     ~Solver() override {
@@ -114,7 +106,34 @@ class Solver final : public SolverBase {
     int sm_count_ = 148;
     bool coop_ok_ = false, use_mega_ = true, use_wave_ = true, l2_persist_ = false;
     size_t l2_persist_bytes_ = 0, l2_window_max_ = 0;
-    int mega_grid_ = 0, mega_bps_ = 3;
+    int mega_grid_ = 0, mega_bps_ = 3, mega_maxp_ = 0;
+    bool force_wave_ = false;
+
+    // The persistent kernel is compiled per (blocks/SM, widest manifold): MAXP = 1 (sphere-only scenes) drops the unrolled code and the
+    // registers of points 2..4.  Returns false when the cooperative grid cannot be sized.
+    template <int MAXP> const void* mega_variant() const {
+        switch (mega_bps_) {
+            case 2: return (const void*)step_megakernel<S, 2, MAXP>;
+            case 4: return (const void*)step_megakernel<S, 4, MAXP>;
+            default: return (const void*)step_megakernel<S, 3, MAXP>;
+        }
+    }
+    bool select_megakernel(int max_points) {
+        const int maxp = max_points <= 1 ? 1 : AVN_MAX_MANIFOLD_POINTS;
+        if (maxp == mega_maxp_) return mega_grid_ > 0;
+        mega_maxp_ = maxp;
+        mega_fn_ = maxp == 1 ? mega_variant<1>() : mega_variant<AVN_MAX_MANIFOLD_POINTS>();
+        const size_t smem = stage_bytes<S>(MEGA_BLOCK, maxp);
+        int per_sm = 0;
+        mega_grid_ = 0;
+        if (cudaFuncSetAttribute(mega_fn_, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_fn_, MEGA_BLOCK, smem) == cudaSuccess && per_sm > 0)
+            mega_grid_ = per_sm * sm_count_;
+        else
+            (void)cudaGetLastError();
+        return mega_grid_ > 0;
+    }
+    int max_np_ = AVN_MAX_MANIFOLD_POINTS;  // widest manifold of the current upload
     const void* mega_fn_ = nullptr;
     cudaEvent_t ev_[EV_COUNT];
     AvnTimings tm_{};
@@ -241,6 +260,18 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
             if (mc->color_offsets[c] > mc->color_offsets[c + 1]) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must be non-decreasing");
         if (mc->point_offsets[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
+        {   // widest manifold: sizes the shared-memory staging tile (3 rows per point) and validates the CSR
+            uint32_t widest = 0, bad = 0;
+            const uint32_t* po = mc->point_offsets;
+            for (size_t i = 0; i < M; ++i) {
+                bad |= uint32_t(po[i + 1] < po[i]);
+                const uint32_t n = po[i + 1] - po[i];
+                widest = n > widest ? n : widest;
+            }
+            if (bad || widest > AVN_MAX_MANIFOLD_POINTS)
+                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets must be non-decreasing with at most %d points per manifold", AVN_MAX_MANIFOLD_POINTS);
+            max_np_ = int(std::max<uint32_t>(widest, 1));
+        }
         d.M = int(M);
         d.P = int(P);
         {   // padded slot layout: every colour starts at a multiple of 32
@@ -342,9 +373,14 @@ AvnStatus Solver<S>::run() {
     launches_ = 0;
     cudaEventRecord(ev_[EV_RUN0], stream_);
     AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
-    bool mega = use_mega_ && coop_ok_;
-    // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour
-    dev_.wave = (mega && use_wave_ && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
+    bool mega = use_mega_ && coop_ok_ && select_megakernel(max_np_);
+    // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour.  It wins when the step
+    // is bound by the per-body dependency chain, i.e. when a colour does not fill the machine; with colours several times the
+    // resident thread count (1M-sphere scene) the barriers are cheap and the counters are pure overhead.
+    int widest_colour = 0;
+    for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) widest_colour = std::max(widest_colour, dev_.color_len[c]);
+    const bool chain_bound = force_wave_ || widest_colour <= 2 * mega_grid_ * MEGA_BLOCK;
+    dev_.wave = (mega && use_wave_ && chain_bound && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
     if (dev_.M > 0) {
         // padding slots must read as "no points": clear the index plane before prepare fills the live slots
         AVN_CUDA(cudaMemsetAsync(dev_.cst + size_t(CP_IDX) * dev_.Mpad, 0, size_t(dev_.Mpad) * sizeof(Vec4<S>), stream_));
@@ -367,7 +403,7 @@ AvnStatus Solver<S>::run() {
     const DevSolver<S>& d = dev_;
     if (mega) {
         void* args[] = {(void*)&dev_};
-        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, stage_bytes<S>(MEGA_BLOCK), stream_);
+        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, stage_bytes<S>(MEGA_BLOCK, mega_maxp_), stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             mega = false;  // fall through to phase launches (still the same CUDA arithmetic)

@@ -26,17 +26,17 @@ enum PhaseOp {
     OP_WAVE_RANK, OP_WAVE_PACK
 };
 
-template <class S, int OP>
+template <class S, int OP, int MAXP = AVN_MAX_MANIFOLD_POINTS>
 __device__ __forceinline__ void run_item(const DevSolver<S>& d, int i) {
     if (OP == OP_PREPARE_BODY) prepare_body_item(d, i);
     else if (OP == OP_PREPARE_CONSTRAINT) prepare_constraint_item(d, i);
     else if (OP == OP_PREPARE_JOINT) prepare_joint_item(d, i);
     else if (OP == OP_INTEGRATE_VEL) integrate_velocity_item(d, i);
     else if (OP == OP_INTEGRATE_POS) { integrate_position_item(d, i); if (d.J > 0) store_pre_solve_item(d, i); }
-    else if (OP == OP_WARM) contact_item<S, PASS_WARM>(d, i);
-    else if (OP == OP_SOLVE_BIAS) contact_item<S, PASS_SOLVE_BIAS>(d, i);
-    else if (OP == OP_RELAX) contact_item<S, PASS_RELAX>(d, i);
-    else if (OP == OP_RESTITUTION) contact_item<S, PASS_RESTITUTION>(d, i);
+    else if (OP == OP_WARM) contact_item<S, PASS_WARM, false, MAXP>(d, i);
+    else if (OP == OP_SOLVE_BIAS) contact_item<S, PASS_SOLVE_BIAS, false, MAXP>(d, i);
+    else if (OP == OP_RELAX) contact_item<S, PASS_RELAX, false, MAXP>(d, i);
+    else if (OP == OP_RESTITUTION) contact_item<S, PASS_RESTITUTION, false, MAXP>(d, i);
     else if (OP == OP_SOLVE_JOINT) solve_joint_item(d, i);
     else if (OP == OP_PROJECT_VEL) project_velocity_item(d, i);
     else if (OP == OP_DAMP_JOINT) damp_joint_item(d, i);
@@ -59,29 +59,29 @@ __global__ void __launch_bounds__(256) phase_kernel(const __grid_constant__ DevS
 }
 
 // __noinline__: each phase keeps its own register allocation instead of the union of all phases
-template <class S, int OP>
+template <class S, int OP, int MAXP = AVN_MAX_MANIFOLD_POINTS>
 __device__ __noinline__ void grid_phase(const DevSolver<S>& d, int begin, int count) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) run_item<S, OP>(d, begin + i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) run_item<S, OP, MAXP>(d, begin + i);
 }
 
-template <class S, int OP>
+template <class S, int OP, int MAXP = AVN_MAX_MANIFOLD_POINTS>
 __device__ __noinline__ void grid_serial(const DevSolver<S>& d, int begin, int count) {
-    for (int i = 0; i < count; ++i) run_item<S, OP>(d, begin + i);
+    for (int i = 0; i < count; ++i) run_item<S, OP, MAXP>(d, begin + i);
 }
 
 // all graph colours of one contact pass, reference order: overflow colour serially first, then colours 0..22
 // (solver/plugin.rs:461-479, 553-572, 643-668)
-template <class S, int OP>
+template <class S, int OP, int MAXP = AVN_MAX_MANIFOLD_POINTS>
 __device__ __forceinline__ void grid_contact_pass(const DevSolver<S>& d, cg::grid_group& grid) {
     const int ov = d.color_off[AVN_COLOR_OVERFLOW], ovn = d.color_len[AVN_COLOR_OVERFLOW];
     if (ovn > 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) grid_serial<S, OP>(d, ov, ovn);
+        if (blockIdx.x == 0 && threadIdx.x == 0) grid_serial<S, OP, MAXP>(d, ov, ovn);
         grid.sync();
     }
     for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) {
         const int b = d.color_off[c], n = d.color_len[c];
         if (n <= 0) continue;
-        grid_phase<S, OP>(d, b, n);
+        grid_phase<S, OP, MAXP>(d, b, n);
         grid.sync();
     }
 }
@@ -90,41 +90,51 @@ __device__ __forceinline__ void grid_contact_pass(const DevSolver<S>& d, cg::gri
 // The whole substep schedule as ONE sequence of 32-item chunks; warp w takes chunks w, w + W, w + 2W, ... in order and
 // every item waits on its bodies' event counters instead of a grid barrier (solver_dev.cuh "wavefront mode").  Chunks
 // never straddle two phases or two colours because body ranges and colour slot ranges are padded to multiples of 32.
-template <class S, int PASS>
-__device__ __noinline__ void wave_contact_chunk(const DevSolver<S>& d, int slot, int s, int it) { contact_item<S, PASS, true>(d, slot, s, it); }
+// WAVE_CHUNK items per warp (lanes >= WAVE_CHUNK idle).  A warp waits for the slowest of its items' predecessors, so a smaller chunk
+// shortens the per-level latency (fewer predecessors per warp) at the cost of idle lanes — the machine has lanes to spare
+// (DESIGN.md 3.1).  Must divide 32; colour slot ranges are padded to multiples of 32, so chunks never straddle colours either way.
+#ifndef AVN_WAVE_CHUNK
+#define AVN_WAVE_CHUNK 32
+#endif
+constexpr int WAVE_CHUNK = AVN_WAVE_CHUNK;
+template <class S, int PASS, int MAXP>
+__device__ __noinline__ void wave_contact_chunk(const DevSolver<S>& d, int slot, int s, int it, bool active) {
+    contact_item<S, PASS, true, MAXP>(d, slot, s, it, active);
+}
 template <class S>
-__device__ __noinline__ void wave_iv_chunk(const DevSolver<S>& d, int i, int s) { integrate_velocity_item<S, true>(d, i, s); }
+__device__ __noinline__ void wave_iv_chunk(const DevSolver<S>& d, int i, int s, bool active) { integrate_velocity_item<S, true>(d, i, s, active); }
 template <class S>
-__device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s) { integrate_position_item<S, true>(d, i, s); }
+__device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s, bool active) { integrate_position_item<S, true>(d, i, s, active); }
 
-template <class S>
+template <class S, int MAXP>
 __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int lane = threadIdx.x & 31;
+    const bool active = lane < WAVE_CHUNK;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int body_chunks = (d.B + 31) >> 5, slot_chunks = d.Mpad >> 5;
+    const int body_chunks = (d.B + WAVE_CHUNK - 1) / WAVE_CHUNK, slot_chunks = d.Mpad / WAVE_CHUNK;
     const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
     const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
     const long long total = per_substep * d.substeps;
     for (long long g = warp_id; g < total; g += warps) {
         const int s = int(g / per_substep);
         long long r = g - (long long)s * per_substep;
-        if (r < body_chunks) { wave_iv_chunk<S>(d, int(r) * 32 + lane, s); continue; }
+        if (r < body_chunks) { wave_iv_chunk<S>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
         r -= body_chunks;
         if (r < (long long)(1 + d.iters) * slot_chunks) {
-            const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * 32 + lane;
-            if (pass == 0) wave_contact_chunk<S, PASS_WARM>(d, slot, s, 0);
-            else wave_contact_chunk<S, PASS_SOLVE_BIAS>(d, slot, s, pass - 1);
+            const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * WAVE_CHUNK + lane;
+            if (pass == 0) wave_contact_chunk<S, PASS_WARM, MAXP>(d, slot, s, 0, active);
+            else wave_contact_chunk<S, PASS_SOLVE_BIAS, MAXP>(d, slot, s, pass - 1, active);
             continue;
         }
         r -= (long long)(1 + d.iters) * slot_chunks;
-        if (r < body_chunks) { wave_ip_chunk<S>(d, int(r) * 32 + lane, s); continue; }
+        if (r < body_chunks) { wave_ip_chunk<S>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
         r -= body_chunks;
-        wave_contact_chunk<S, PASS_RELAX>(d, int(r) * 32 + lane, s, 0);
+        wave_contact_chunk<S, PASS_RELAX, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, 0, active);
     }
 }
 
-template <class S, int BPS>
+template <class S, int BPS, int MAXP>
 __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_constant__ DevSolver<S> d) {
     cg::grid_group grid = cg::this_grid();
     // ---- prepare
@@ -143,19 +153,19 @@ __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_
         }
         grid_phase<S, OP_WAVE_PACK>(d, 0, d.Mpad);
         grid.sync();
-        wave_substep_loop<S>(d);
+        wave_substep_loop<S, MAXP>(d);
         grid.sync();
     }
     for (int sub = 0; sub < (d.wave ? 0 : d.substeps); ++sub) {
         grid_phase<S, OP_INTEGRATE_VEL>(d, 0, d.B);
         grid.sync();
         if (d.M > 0) {
-            grid_contact_pass<S, OP_WARM>(d, grid);
-            for (int it = 0; it < d.iters; ++it) grid_contact_pass<S, OP_SOLVE_BIAS>(d, grid);
+            grid_contact_pass<S, OP_WARM, MAXP>(d, grid);
+            for (int it = 0; it < d.iters; ++it) grid_contact_pass<S, OP_SOLVE_BIAS, MAXP>(d, grid);
         }
         grid_phase<S, OP_INTEGRATE_POS>(d, 0, d.B);
         grid.sync();
-        if (d.M > 0) grid_contact_pass<S, OP_RELAX>(d, grid);
+        if (d.M > 0) grid_contact_pass<S, OP_RELAX, MAXP>(d, grid);
         if (d.J > 0) {
             for (int l = 0; l < d.n_levels; ++l) {
                 const int b = d.level_off[l], n = d.level_off[l + 1] - b;
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_
         }
     }
     // ---- restitution, writeback, store impulses
-    if (d.M > 0 && *d.any_restitution) grid_contact_pass<S, OP_RESTITUTION>(d, grid);
+    if (d.M > 0 && *d.any_restitution) grid_contact_pass<S, OP_RESTITUTION, MAXP>(d, grid);
     grid_phase<S, OP_WRITEBACK_BODY>(d, 0, d.B);
     grid_phase<S, OP_STORE_IMPULSE>(d, 0, d.M);
     grid_phase<S, OP_JOINT_FORCE>(d, 0, d.J);
