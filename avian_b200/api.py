@@ -310,6 +310,11 @@ class PairList:
         return PairList(self.collider1[:n], self.collider2[:n], self.body1[:n], self.body2[:n], self.flags[:n], n)
 
 
+class AvnBoundary(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("slot_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("body", _vp), ("slot", _vp), ("owner_rank", _vp)]
+
+
 def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
     """Declare argument/return types of every entry point of include/avian_b200.h on `lib`."""
     P = C.POINTER
@@ -331,6 +336,13 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "get_timings": ([_vp, P(AvnTimings)], C.c_int),
         "joint_levels": ([P(AvnBodyColumns), P(AvnJointSet), _vp, P(C.c_uint32)], C.c_int),
         "update_aabbs": ([_vp, P(AvnAabbParams), P(AvnColliderColumns)], C.c_int),
+        "solver_run_range": ([_vp, C.c_uint32, C.c_uint32, C.c_uint32], C.c_int),
+        "solver_set_boundary": ([_vp, P(AvnBoundary)], C.c_int),
+        "solver_boundary_snapshot": ([_vp], C.c_int),
+        "solver_boundary_pack": ([_vp, _vp], C.c_int),
+        "solver_boundary_apply": ([_vp, _vp], C.c_int),
+        "solver_needs_restitution": ([_vp, P(C.c_int)], C.c_int),
+        "get_stream": ([_vp, P(_vp)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -341,7 +353,11 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
 ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
-    "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs"]
+    "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream"]
+
+RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
+BOUNDARY_RECORD_SCALARS = 16
 
 
 @dataclass
@@ -508,6 +524,35 @@ class Context:
         self._check(self.lib.avn_broadphase_download(self.handle, C.byref(s)))
         out.count = int(s.count)
         return out
+
+    # ---- x-slab partition (include/avian_b200.h "one coupled scene over several GPUs")
+    def solver_run_range(self, first: int, count: int, flags: int) -> None:
+        self._check(self.lib.avn_solver_run_range(self.handle, first, count, flags))
+
+    def solver_set_boundary(self, body: np.ndarray, slot: np.ndarray, owner_rank: np.ndarray, slot_count: int, rank: int, world: int) -> None:
+        body, slot, owner_rank = (np.ascontiguousarray(x, dtype=np.int32) for x in (body, slot, owner_rank))
+        b = AvnBoundary(int(body.shape[0]), int(slot_count), int(rank), int(world), _ptr(body), _ptr(slot), _ptr(owner_rank))
+        self._check(self.lib.avn_solver_set_boundary(self.handle, C.byref(b)))
+
+    def solver_boundary_snapshot(self) -> None:
+        self._check(self.lib.avn_solver_boundary_snapshot(self.handle))
+
+    def solver_boundary_pack(self, device_ptr: int) -> None:
+        self._check(self.lib.avn_solver_boundary_pack(self.handle, _vp(device_ptr)))
+
+    def solver_boundary_apply(self, device_ptr: int) -> None:
+        self._check(self.lib.avn_solver_boundary_apply(self.handle, _vp(device_ptr)))
+
+    def solver_needs_restitution(self) -> bool:
+        out = C.c_int(0)
+        self._check(self.lib.avn_solver_needs_restitution(self.handle, C.byref(out)))
+        return bool(out.value)
+
+    def stream(self) -> int:
+        """The context's cudaStream_t as an integer (torch.cuda.ExternalStream(ptr) orders a collective with the launches)."""
+        out = _vp()
+        self._check(self.lib.avn_get_stream(self.handle, C.byref(out)))
+        return int(out.value or 0)
 
     def update_aabbs(self, params: "AvnAabbParams", colliders: "Colliders") -> None:
         c = colliders.as_struct()

@@ -103,6 +103,41 @@ AvnStatus avn_solver_run(AvnContext* ctx) {
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
     return ctx->solver->run();
 }
+AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->run_range(first_substep, substep_count, run_flags);
+}
+AvnStatus avn_solver_set_boundary(AvnContext* ctx, const AvnBoundary* boundary) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->set_boundary(boundary);
+}
+AvnStatus avn_solver_boundary_snapshot(AvnContext* ctx) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->boundary_snapshot();
+}
+AvnStatus avn_solver_boundary_pack(AvnContext* ctx, void* device_table) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->boundary_pack(device_table);
+}
+AvnStatus avn_solver_boundary_apply(AvnContext* ctx, const void* device_gathered) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->boundary_apply(device_gathered);
+}
+AvnStatus avn_solver_needs_restitution(AvnContext* ctx, int* out_nonzero) {
+    if (!ctx || !out_nonzero) return AVN_ERR_INVALID_ARGUMENT;
+    *out_nonzero = ctx->solver->needs_restitution();
+    return AVN_OK;
+}
+AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream) {
+    if (!ctx || !out_stream) return AVN_ERR_INVALID_ARGUMENT;
+    *out_stream = (void*)ctx->stream;
+    return AVN_OK;
+}
 AvnStatus avn_solver_download(AvnContext* ctx) {
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");

@@ -206,9 +206,15 @@ template <class S> struct CellGrid;
 template <class S> __device__ __forceinline__ long long query_cell_count(const CellGrid<S>& g, Vec4<S> yi);
 template <class S>
 __global__ void sweep_bounds(const S* __restrict__ minx, const S* __restrict__ maxx, const Vec4<S>* __restrict__ yz, const CellGrid<S>* __restrict__ grid,
-                             int n, int* __restrict__ end, int* __restrict__ wide_list, int* __restrict__ wide_count, uint8_t* __restrict__ is_wide) {
+                             int n, int* __restrict__ end, int* __restrict__ wide_list, int* __restrict__ wide_count, uint8_t* __restrict__ is_wide,
+                             const uint8_t* __restrict__ sflags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (sflags[i] & AVN_AABB_HALO) {  // a halo interval never starts a sweep: empty window
+        end[i] = i + 1;
+        is_wide[i] = 0;
+        return;
+    }
     S m = maxx[i];
     int lo = i + 1, hi = n;
     while (lo < hi) {
@@ -554,7 +560,7 @@ AvnStatus Broadphase<S>::run() {
         int* wide_list = wide_.as<int>() + 1;
         AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
         sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), d_grid, n, s_end_.as<int>(), wide_list, wide_count,
-                                                              wide_flag_.as<uint8_t>());
+                                                              wide_flag_.as<uint8_t>(), s_flags_.as<uint8_t>());
         Sweep<S> sw;
         sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
         sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();

@@ -57,6 +57,12 @@ struct SolverBase {
     virtual ~SolverBase() {}
     virtual AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) = 0;
     virtual AvnStatus run() = 0;
+    virtual AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) = 0;
+    virtual AvnStatus set_boundary(const AvnBoundary* bnd) = 0;
+    virtual AvnStatus boundary_snapshot() = 0;
+    virtual AvnStatus boundary_pack(void* device_table) = 0;
+    virtual AvnStatus boundary_apply(const void* device_gathered) = 0;
+    virtual int needs_restitution() const = 0;
     virtual AvnStatus download() = 0;
     virtual void timings(AvnTimings* t) const = 0;
 };

@@ -95,6 +95,12 @@ struct DevSolver {
     const int* jbody1[AVN_JOINT_TYPE_COUNT]; const int* jbody2[AVN_JOINT_TYPE_COUNT];
     S* jforce[AVN_JOINT_TYPE_COUNT]; S* jtorque[AVN_JOINT_TYPE_COUNT];
     int any_joint_damping;
+    // launch range (avn_solver_run_range): which parts of the step this launch runs.  A plain avn_solver_run does everything.
+    int do_prepare, sub_begin, sub_end, do_restitution, do_finalize;
+    // x-slab partition (multi-GPU, include/avian_b200.h "boundary bodies"): bnd_of[b] = index into the boundary list or -1 (NULL when
+    // the step is not partitioned); vel_ref = the boundary bodies' velocities right after integrate_velocities (2 rows per body)
+    const int* bnd_of;
+    Vec4<S>* vel_ref;
 };
 
 template <class S> __device__ __forceinline__ V3<S> ldv3(const S* p, int i) { return mk3<S>(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
@@ -702,6 +708,13 @@ __device__ __forceinline__ void integrate_velocity_item(const DevSolver<S>& d, i
     if (touched) {
         st4(&d.vel[2 * i], mk4<S>(v.x, v.y, v.z, S(0)));
         st4(&d.vel[2 * i + 1], mk4<S>(w.x, w.y, w.z, S(0)));
+    }
+    if (d.bnd_of) {  // partitioned step: the reference point of this substep's constraint impulses on a boundary body
+        const int k = d.bnd_of[i];
+        if (k >= 0) {
+            st4(&d.vel_ref[2 * k], mk4<S>(v.x, v.y, v.z, S(0)));
+            st4(&d.vel_ref[2 * k + 1], mk4<S>(w.x, w.y, w.z, S(0)));
+        }
     }
     if (WAVE) wave_publish(d.ver, true, i, e, false, 0, 0u);
 }

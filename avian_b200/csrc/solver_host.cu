@@ -65,6 +65,12 @@ class Solver final : public SolverBase {
     }
 
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
+    AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) override;
+    AvnStatus set_boundary(const AvnBoundary* bnd) override;
+    AvnStatus boundary_snapshot() override;
+    AvnStatus boundary_pack(void* device_table) override;
+    AvnStatus boundary_apply(const void* device_gathered) override;
+    int needs_restitution() const override { return host_any_restitution_ ? 1 : 0; }
     AvnStatus run() override;
     AvnStatus download() override;
     void timings(AvnTimings* t) const override { *t = tm_; }
@@ -139,7 +145,10 @@ class Solver final : public SolverBase {
     AvnTimings tm_{};
     uint32_t launches_ = 0;
     size_t h2d_bytes_ = 0;
-    bool uploaded_ = false, ran_ = false, host_any_restitution_ = false;
+    bool uploaded_ = false, ran_ = false, host_any_restitution_ = false, prepared_ = false, mega_step_ = false;
+    DevBuf bnd_of_, bnd_body_, bnd_slot_, bnd_owner_, vel_ref_;
+    int bnd_n_ = 0, bnd_rank_ = 0, bnd_world_ = 1;
+    size_t bnd_slots_ = 0;
 
     DevSolver<S> dev_{};
     // host pointers for download
@@ -363,31 +372,57 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
 #undef UP
     cudaEventRecord(ev_[EV_H2D1], stream_);
     uploaded_ = true;
+    prepared_ = false;
+    ran_ = false;
+    dev_.bnd_of = nullptr;   // a new upload renumbers the bodies: the boundary list must be set again
+    dev_.vel_ref = nullptr;
+    bnd_n_ = 0;
+    bnd_slots_ = 0;
     tm_ = AvnTimings{};
     return AVN_OK;
 }
 
 template <class S>
 AvnStatus Solver<S>::run() {
+    return run_range(0, dev_.substeps, AVN_RUN_PREPARE | AVN_RUN_RESTITUTION | AVN_RUN_FINALIZE);
+}
+
+// One launch covering: prepare (flags & AVN_RUN_PREPARE), substeps [first, first + count), the restitution pass, the finalize phases.
+// avn_solver_run is the whole step in one launch; the x-slab partition launches substep by substep with a boundary exchange in between.
+template <class S>
+AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
     if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run before avn_solver_upload");
-    launches_ = 0;
-    cudaEventRecord(ev_[EV_RUN0], stream_);
-    AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
+    const bool prepare = (flags & AVN_RUN_PREPARE) != 0;
+    if (!prepare && !prepared_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run_range: the first launch after an upload must include AVN_RUN_PREPARE");
+    if (uint64_t(first) + count > uint64_t(dev_.substeps)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_run_range: substeps [%u, %u) exceed %d", first, first + count, dev_.substeps);
+    dev_.do_prepare = prepare ? 1 : 0;
+    dev_.sub_begin = int(first);
+    dev_.sub_end = int(first + count);
+    dev_.do_restitution = (flags & AVN_RUN_RESTITUTION) ? 1 : 0;
+    dev_.do_finalize = (flags & AVN_RUN_FINALIZE) ? 1 : 0;
     bool mega = use_mega_ && coop_ok_ && select_megakernel(max_np_);
-    // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour.  It wins when the step
-    // is bound by the per-body dependency chain, i.e. when a colour does not fill the machine; with colours several times the
-    // resident thread count (1M-sphere scene) the barriers are cheap and the counters are pure overhead.
-    int widest_colour = 0;
-    for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) widest_colour = std::max(widest_colour, dev_.color_len[c]);
-    const bool chain_bound = force_wave_ || widest_colour <= 2 * mega_grid_ * MEGA_BLOCK;
-    dev_.wave = (mega && use_wave_ && chain_bound && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
-    if (dev_.M > 0) {
-        // padding slots must read as "no points": clear the index plane before prepare fills the live slots
-        AVN_CUDA(cudaMemsetAsync(dev_.cst + size_t(CP_IDX) * dev_.Mpad, 0, size_t(dev_.Mpad) * sizeof(Vec4<S>), stream_));
-    }
-    if (dev_.wave) {
-        AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
-        AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, (size_t(dev_.B) + 1) * sizeof(int), stream_));
+    if (prepare) {
+        launches_ = 0;
+        cudaEventRecord(ev_[EV_RUN0], stream_);
+        AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
+        // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour.  It wins when the step
+        // is bound by the per-body dependency chain, i.e. when a colour does not fill the machine; with colours several times the
+        // resident thread count (1M-sphere scene) the barriers are cheap and the counters are pure overhead.
+        int widest_colour = 0;
+        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) widest_colour = std::max(widest_colour, dev_.color_len[c]);
+        const bool chain_bound = force_wave_ || widest_colour <= 2 * mega_grid_ * MEGA_BLOCK;
+        dev_.wave = (mega && use_wave_ && chain_bound && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
+        if (dev_.M > 0) {
+            // padding slots must read as "no points": clear the index plane before prepare fills the live slots
+            AVN_CUDA(cudaMemsetAsync(dev_.cst + size_t(CP_IDX) * dev_.Mpad, 0, size_t(dev_.Mpad) * sizeof(Vec4<S>), stream_));
+        }
+        if (dev_.wave) {
+            AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
+            AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, (size_t(dev_.B) + 1) * sizeof(int), stream_));
+        }
+        mega_step_ = mega;
+    } else {
+        mega = mega && mega_step_;   // a step keeps the launch mode its prepare launch chose
     }
     if (l2_persist_ && hot_bytes_ > 0) {
         // pin the mutable state (body velocities/deltas, event counters, impulse planes) in L2: it sits on the critical dependency
@@ -406,20 +441,25 @@ AvnStatus Solver<S>::run() {
         cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, stage_bytes<S>(MEGA_BLOCK, mega_maxp_), stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
+            if (!prepare && dev_.wave)
+                return err_->fail(AVN_ERR_CUDA, "cooperative launch refused in the middle of a wavefront-scheduled step: %s", cudaGetErrorString(e));
             mega = false;  // fall through to phase launches (still the same CUDA arithmetic)
+            mega_step_ = false;
             dev_.wave = 0;
         } else {
             ++launches_;
-            cudaEventRecord(ev_[EV_PREP], stream_);
-            cudaEventRecord(ev_[EV_LOOP], stream_);
+            if (prepare) cudaEventRecord(ev_[EV_PREP], stream_);
+            if (dev_.do_finalize) cudaEventRecord(ev_[EV_LOOP], stream_);
         }
     }
     if (!mega) {
-        launch_phase<OP_PREPARE_BODY>(0, d.B + 1);
-        launch_phase<OP_PREPARE_CONSTRAINT>(0, d.M);
-        launch_phase<OP_PREPARE_JOINT>(0, d.J);
-        cudaEventRecord(ev_[EV_PREP], stream_);
-        for (int sub = 0; sub < d.substeps; ++sub) {
+        if (prepare) {
+            launch_phase<OP_PREPARE_BODY>(0, d.B + 1);
+            launch_phase<OP_PREPARE_CONSTRAINT>(0, d.M);
+            launch_phase<OP_PREPARE_JOINT>(0, d.J);
+            cudaEventRecord(ev_[EV_PREP], stream_);
+        }
+        for (int sub = d.sub_begin; sub < d.sub_end; ++sub) {
             launch_phase<OP_INTEGRATE_VEL>(0, d.B);
             if (d.M > 0) {
                 launch_contact_pass<OP_WARM>();
@@ -434,17 +474,150 @@ AvnStatus Solver<S>::run() {
                     for (int l = 0; l < d.n_levels; ++l) launch_phase<OP_DAMP_JOINT>(h_level_off_[l], h_level_off_[l + 1] - h_level_off_[l]);
             }
         }
-        cudaEventRecord(ev_[EV_LOOP], stream_);
+        if (d.do_finalize) cudaEventRecord(ev_[EV_LOOP], stream_);
         // restitution kernels early-out per manifold when e == 0; skipping the launches needs the device flag, which
         // would cost a sync, so in phase mode they are launched only when the host saw a non-zero coefficient
-        if (d.M > 0 && host_any_restitution_) launch_contact_pass<OP_RESTITUTION>();
-        launch_phase<OP_WRITEBACK_BODY>(0, d.B);
-        launch_phase<OP_STORE_IMPULSE>(0, d.M);
-        launch_phase<OP_JOINT_FORCE>(0, d.J);
+        if (d.do_restitution && d.M > 0 && host_any_restitution_) launch_contact_pass<OP_RESTITUTION>();
+        if (d.do_finalize) {
+            launch_phase<OP_WRITEBACK_BODY>(0, d.B);
+            launch_phase<OP_STORE_IMPULSE>(0, d.M);
+            launch_phase<OP_JOINT_FORCE>(0, d.J);
+        }
     }
-    cudaEventRecord(ev_[EV_RUN1], stream_);
     AVN_CUDA(cudaGetLastError());
-    ran_ = true;
+    prepared_ = true;
+    if (dev_.do_finalize) {
+        cudaEventRecord(ev_[EV_RUN1], stream_);
+        ran_ = true;
+    }
+    return AVN_OK;
+}
+
+// ---- x-slab partition: boundary bodies (include/avian_b200.h) -------------------------------------------------------------
+// record of one boundary slot in the exchange table: 4 rows of Vec4<S>:
+//   row 0 = (dv.xyz, holder marker 1)   row 1 = (dw.xyz, owner marker 1)   row 2 = (delta_position.xyz, 0)   row 3 = delta_rotation
+template <class S>
+__global__ void boundary_snapshot_kernel(DevSolver<S> d, const int* __restrict__ body, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int b = body[k];
+    st4(&d.vel_ref[2 * k], ld4(&d.vel[2 * b]));
+    st4(&d.vel_ref[2 * k + 1], ld4(&d.vel[2 * b + 1]));
+}
+template <class S>
+__global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
+                                     int n, int rank, Vec4<S>* __restrict__ table) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int b = body[k];
+    Vec4<S>* rec = table + size_t(4) * slot[k];
+    const Vec4<S> l = ld4(&d.vel[2 * b]), a = ld4(&d.vel[2 * b + 1]), l0 = ld4(&d.vel_ref[2 * k]), a0 = ld4(&d.vel_ref[2 * k + 1]);
+    const bool owner = owner_rank[k] == rank;
+    st4(&rec[0], mk4<S>(l.x - l0.x, l.y - l0.y, l.z - l0.z, S(1)));
+    st4(&rec[1], mk4<S>(a.x - a0.x, a.y - a0.y, a.z - a0.z, owner ? S(1) : S(0)));
+    if (owner) {
+        st4(&rec[2], ld4(&d.dlt[2 * b]));
+        st4(&rec[3], ld4(&d.dlt[2 * b + 1]));
+    }
+}
+template <class S>
+__global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
+                                      int n, int world, size_t slots, const Vec4<S>* __restrict__ gathered) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int b = body[k];
+    Vec4<S> l = ld4(&d.vel_ref[2 * k]), a = ld4(&d.vel_ref[2 * k + 1]);
+    // every holder's constraint impulses of this substep, summed in rank order (the same order on every rank: identical bits)
+    for (int r = 0; r < world; ++r) {
+        const Vec4<S>* rec = gathered + (size_t(r) * slots + size_t(slot[k])) * 4;
+        const Vec4<S> dl = ld4(&rec[0]), da = ld4(&rec[1]);
+        if (dl.w == S(0)) continue;  // rank r does not hold this body
+        l.x = l.x + dl.x; l.y = l.y + dl.y; l.z = l.z + dl.z;
+        a.x = a.x + da.x; a.y = a.y + da.y; a.z = a.z + da.z;
+    }
+    st4(&d.vel[2 * b], mk4<S>(l.x, l.y, l.z, S(0)));
+    st4(&d.vel[2 * b + 1], mk4<S>(a.x, a.y, a.z, S(0)));
+    const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * slots + size_t(slot[k])) * 4;
+    st4(&d.dlt[2 * b], ld4(&own[2]));
+    st4(&d.dlt[2 * b + 1], ld4(&own[3]));
+}
+
+template <class S>
+AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
+    if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_set_boundary before avn_solver_upload");
+    if (!bnd || bnd->count == 0) {
+        dev_.bnd_of = nullptr;
+        dev_.vel_ref = nullptr;
+        bnd_n_ = 0;
+        return AVN_OK;
+    }
+    if (!bnd->body || !bnd->slot || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, slot and owner_rank are required");
+    if (bnd->rank >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: rank %u >= world %u", bnd->rank, bnd->world);
+    if (dev_.J > 0) return err_->fail(AVN_ERR_UNSUPPORTED, "boundary exchange covers contact constraints only (joints shard by island)");
+    const size_t n = bnd->count, B = size_t(dev_.B);
+    std::vector<int> of(B + 1, -1);
+    for (size_t k = 0; k < n; ++k) {
+        const int b = bnd->body[k];
+        if (b < 0 || size_t(b) >= B) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body[%zu] = %d out of range", k, b);
+        if (bnd->slot[k] < 0 || uint32_t(bnd->slot[k]) >= bnd->slot_count) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: slot[%zu] out of range", k);
+        if (bnd->owner_rank[k] < 0 || uint32_t(bnd->owner_rank[k]) >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: owner_rank[%zu] out of range", k);
+        if (of[b] != -1) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body %d listed twice", b);
+        of[b] = int(k);
+    }
+    AVN_CUDA(bnd_of_.ensure((B + 1) * sizeof(int)));
+    AVN_CUDA(bnd_body_.ensure(n * sizeof(int)));
+    AVN_CUDA(bnd_slot_.ensure(n * sizeof(int)));
+    AVN_CUDA(bnd_owner_.ensure(n * sizeof(int)));
+    AVN_CUDA(vel_ref_.ensure(2 * n * sizeof(Vec4<S>)));
+    AVN_CUDA(cudaMemcpyAsync(bnd_of_.p, of.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaMemcpyAsync(bnd_body_.p, bnd->body, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaMemcpyAsync(bnd_slot_.p, bnd->slot, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaMemcpyAsync(bnd_owner_.p, bnd->owner_rank, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaStreamSynchronize(stream_));   // `of` is a temporary
+    dev_.bnd_of = bnd_of_.as<int>();
+    dev_.vel_ref = vel_ref_.as<Vec4<S>>();
+    bnd_n_ = int(n);
+    bnd_rank_ = int(bnd->rank);
+    bnd_world_ = int(bnd->world);
+    bnd_slots_ = size_t(bnd->slot_count);
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::boundary_snapshot() {
+    if (!prepared_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_boundary_snapshot before the prepare launch");
+    if (bnd_n_ > 0) {
+        boundary_snapshot_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_n_);
+        ++launches_;
+    }
+    AVN_CUDA(cudaGetLastError());
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::boundary_pack(void* device_table) {
+    if (!prepared_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_boundary_pack before the prepare launch");
+    if (bnd_slots_ == 0) return AVN_OK;
+    if (!device_table) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary table is required");
+    AVN_CUDA(cudaMemsetAsync(device_table, 0, bnd_slots_ * 4 * sizeof(Vec4<S>), stream_));
+    if (bnd_n_ > 0) {
+        boundary_pack_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_slot_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_rank_,
+                                                                            static_cast<Vec4<S>*>(device_table));
+        ++launches_;
+    }
+    AVN_CUDA(cudaGetLastError());
+    return AVN_OK;
+}
+
+template <class S>
+AvnStatus Solver<S>::boundary_apply(const void* device_gathered) {
+    if (!prepared_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_boundary_apply before the prepare launch");
+    if (bnd_n_ == 0) return AVN_OK;
+    if (!device_gathered) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "gathered boundary tables are required");
+    boundary_apply_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_slot_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_world_,
+                                                                         bnd_slots_, static_cast<const Vec4<S>*>(device_gathered));
+    ++launches_;
+    AVN_CUDA(cudaGetLastError());
     return AVN_OK;
 }
 

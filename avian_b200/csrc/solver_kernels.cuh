@@ -115,8 +115,8 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int body_chunks = (d.B + WAVE_CHUNK - 1) / WAVE_CHUNK, slot_chunks = d.Mpad / WAVE_CHUNK;
     const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
     const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
-    const long long total = per_substep * d.substeps;
-    for (long long g = warp_id; g < total; g += warps) {
+    const long long total = per_substep * d.sub_end;
+    for (long long g = per_substep * d.sub_begin + warp_id; g < total; g += warps) {
         const int s = int(g / per_substep);
         long long r = g - (long long)s * per_substep;
         if (r < body_chunks) { wave_iv_chunk<S>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
@@ -138,25 +138,29 @@ template <class S, int BPS, int MAXP>
 __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_constant__ DevSolver<S> d) {
     cg::grid_group grid = cg::this_grid();
     // ---- prepare
-    grid_phase<S, OP_PREPARE_BODY>(d, 0, d.B + 1);
-    grid.sync();
-    grid_phase<S, OP_PREPARE_CONSTRAINT>(d, 0, d.M);
-    grid_phase<S, OP_PREPARE_JOINT>(d, 0, d.J);
-    grid.sync();
-    // ---- run_substep_schedule (solver/schedule.rs:194-213)
-    if (d.wave) {
-        // ranks of every constraint on its bodies, colour by colour in schedule order (deg[] was zeroed by the host)
-        for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) {
-            if (d.color_len[c] <= 0) continue;
-            grid_phase<S, OP_WAVE_RANK>(d, d.color_off[c], d.color_len[c]);
+    if (d.do_prepare) {
+        grid_phase<S, OP_PREPARE_BODY>(d, 0, d.B + 1);
+        grid.sync();
+        grid_phase<S, OP_PREPARE_CONSTRAINT>(d, 0, d.M);
+        grid_phase<S, OP_PREPARE_JOINT>(d, 0, d.J);
+        grid.sync();
+        if (d.wave) {
+            // ranks of every constraint on its bodies, colour by colour in schedule order (deg[] was zeroed by the host)
+            for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) {
+                if (d.color_len[c] <= 0) continue;
+                grid_phase<S, OP_WAVE_RANK>(d, d.color_off[c], d.color_len[c]);
+                grid.sync();
+            }
+            grid_phase<S, OP_WAVE_PACK>(d, 0, d.Mpad);
             grid.sync();
         }
-        grid_phase<S, OP_WAVE_PACK>(d, 0, d.Mpad);
-        grid.sync();
+    }
+    // ---- run_substep_schedule (solver/schedule.rs:194-213), substeps [sub_begin, sub_end)
+    if (d.wave && d.sub_end > d.sub_begin) {
         wave_substep_loop<S, MAXP>(d);
         grid.sync();
     }
-    for (int sub = 0; sub < (d.wave ? 0 : d.substeps); ++sub) {
+    for (int sub = d.sub_begin; sub < (d.wave ? 0 : d.sub_end); ++sub) {
         grid_phase<S, OP_INTEGRATE_VEL>(d, 0, d.B);
         grid.sync();
         if (d.M > 0) {
@@ -184,10 +188,12 @@ __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_
         }
     }
     // ---- restitution, writeback, store impulses
-    if (d.M > 0 && *d.any_restitution) grid_contact_pass<S, OP_RESTITUTION, MAXP>(d, grid);
-    grid_phase<S, OP_WRITEBACK_BODY>(d, 0, d.B);
-    grid_phase<S, OP_STORE_IMPULSE>(d, 0, d.M);
-    grid_phase<S, OP_JOINT_FORCE>(d, 0, d.J);
+    if (d.do_restitution && d.M > 0 && *d.any_restitution) grid_contact_pass<S, OP_RESTITUTION, MAXP>(d, grid);
+    if (d.do_finalize) {
+        grid_phase<S, OP_WRITEBACK_BODY>(d, 0, d.B);
+        grid_phase<S, OP_STORE_IMPULSE>(d, 0, d.M);
+        grid_phase<S, OP_JOINT_FORCE>(d, 0, d.J);
+    }
 }
 
 }  // namespace avn

@@ -74,6 +74,10 @@ typedef enum AvnBodyKind { AVN_BODY_DYNAMIC = 0, AVN_BODY_KINEMATIC = 1, AVN_BOD
 #define AVN_AABB_GENERATE_CONSTRAINTS 0x04u
 #define AVN_AABB_CUSTOM_FILTER 0x08u
 #define AVN_AABB_MODIFY_CONTACTS 0x10u
+/* Multi-GPU x-slab partition: the interval is a copy of one owned by the next slab ("halo").  It is only ever the LATER
+ * element of a pair: the sweep never starts from it, so pairs between two halo intervals are left to the slab that owns them.  Not a
+ * reference flag; single-GPU callers never set it. */
+#define AVN_AABB_HALO 0x80u
 
 /* Flag bits of an emitted pair (what collect_collision_pairs stores on ContactEdge / ContactPair,
  * broad_phase.rs:443-468) plus NEEDS_HOOK: the shim must still call CollisionHooks::filter_pairs for it
@@ -287,6 +291,41 @@ AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBod
                             AvnManifoldColumns* manifolds, AvnJointSet* joints);
 AvnStatus avn_solver_run(AvnContext* ctx);
 AvnStatus avn_solver_download(AvnContext* ctx);
+
+/* ---- one coupled scene over several GPUs: the x-slab partition (BASELINE north_star "single all-gather of boundary
+ *      state per substep where the scene spans GPUs").  Not a reference interface: the reference is single-process. -------------
+ * Each rank uploads its own bodies and constraints plus copies ("ghosts") of the remote bodies its constraints touch.  A body held
+ * by more than one rank is a BOUNDARY body; it has one slot in a table every rank agrees on.  Per substep each rank launches
+ * avn_solver_run_range for that substep, packs for every boundary body it holds the velocity change its own constraints caused
+ * (relative to the velocity right after integrate_velocities, which every holder computes identically) and, if it owns the body,
+ * the body's delta_position / delta_rotation; the tables are all-gathered (NCCL, by the caller, on the stream avn_get_stream
+ * returns); avn_solver_boundary_apply sets v = v_ref + sum over ranks in rank order of their changes and takes the owner's deltas.
+ * Impulses therefore cross a cut once per substep instead of once per constraint: results match the single-GPU step to solver
+ * tolerance, not to 1e-5; a scene whose constraints do not cross a cut is reproduced bit for bit. */
+#define AVN_RUN_PREPARE 0x1u      /* prepare bodies / constraints: must be part of the first launch after an upload */
+#define AVN_RUN_RESTITUTION 0x2u  /* solve_restitution after the substeps of this launch */
+#define AVN_RUN_FINALIZE 0x4u     /* writeback_solver_bodies + store_contact_impulses: must be part of the last launch */
+
+typedef struct AvnBoundary {
+    uint32_t count;               /* boundary bodies held by this rank */
+    uint32_t slot_count;          /* slots of the global boundary table */
+    uint32_t rank, world;
+    const int32_t* body;          /* [count] index into the uploaded AvnBodyColumns */
+    const int32_t* slot;          /* [count] slot of the body in the global table */
+    const int32_t* owner_rank;    /* [count] the rank whose delta_position / delta_rotation are authoritative */
+} AvnBoundary;
+/* scalars per slot of the exchange table (4 rows of 4): the table is slot_count * AVN_BOUNDARY_RECORD_SCALARS scalars,
+ * the gathered tables world times that, rank-major */
+#define AVN_BOUNDARY_RECORD_SCALARS 16
+
+AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags);
+AvnStatus avn_solver_set_boundary(AvnContext* ctx, const AvnBoundary* boundary);   /* after upload; NULL / count 0 clears it */
+AvnStatus avn_solver_boundary_snapshot(AvnContext* ctx);                           /* v_ref = current velocity (before a restitution launch) */
+AvnStatus avn_solver_boundary_pack(AvnContext* ctx, void* device_table);           /* DEVICE pointer */
+AvnStatus avn_solver_boundary_apply(AvnContext* ctx, const void* device_gathered); /* DEVICE pointer */
+AvnStatus avn_solver_needs_restitution(AvnContext* ctx, int* out_nonzero);         /* any uploaded restitution coefficient != 0 */
+/* the context's CUDA stream (a cudaStream_t) so that the caller's collective can be ordered with the launches above */
+AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream);
 
 /*
  * Sweep-and-prune pair generation.  Replaces collect_collision_pairs / sweep_and_prune (broad_phase.rs:343-474)

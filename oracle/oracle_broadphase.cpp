@@ -53,6 +53,7 @@ int broadphase(AvnAabbColumns& ac, AvnPairList& out) {
     for (uint32_t ii = 0; ii < n; ++ii) {
         const uint32_t a = order[ii];
         const uint8_t f1 = ac.flags ? ac.flags[a] : uint8_t(AVN_AABB_GENERATE_CONSTRAINTS);
+        if (f1 & AVN_AABB_HALO) continue;  // x-slab partition: a halo copy never starts a sweep (include/avian_b200.h)
         const uint32_t m1 = ac.memberships ? ac.memberships[a] : 1u, fl1 = ac.filters ? ac.filters[a] : 0xFFFFFFFFu;
         for (uint32_t jj = ii + 1; jj < n; ++jj) {
             const uint32_t b = order[jj];

@@ -102,20 +102,53 @@ static void for_each_color(SolverWorld<S>& w, Pool& pool, const std::vector<uint
     }
 }
 
+// The stage as a resumable object: prepare -> substep x N -> restitution -> finalize.  orc_solver_step runs them back to back; the
+// orc_step_* entry points expose them one by one for the x-slab partition tests (include/avian_b200.h, "one coupled scene over
+// several GPUs"), where a boundary exchange happens between substeps.
 template <class S>
-int solver_step(const AvnStepParams& prm, AvnBodyColumns& bc, AvnManifoldColumns* mc, AvnJointSet* js, int threads) {
+struct StepState {
     using C = Columns<S>;
-    Pool pool(std::max(1, threads));
-    const size_t B = bc.count;
+    AvnStepParams prm;
+    AvnBodyColumns bc;
+    AvnManifoldColumns mc_store;
+    AvnManifoldColumns* mc = nullptr;
+    AvnJointSet js_store;
+    AvnJointSet* js = nullptr;
+    Pool pool;
+    size_t B = 0;
     SolverWorld<S> w;
-    w.bodies.assign(B, SolverBody<S>());
-    w.inertias.assign(B, SolverBodyInertia<S>());
-    w.integ.assign(B, VelocityIntegrationData<S>());
-    std::vector<uint8_t> has_sb(B, 0);  // has SolverBody (dynamic or kinematic)
-    std::vector<Quat<S>> rot0(B);
-    std::vector<V3<S>> pos0(B), linvel0(B);
-    const S dt = S(prm.dt), h = S(prm.h);
+    std::vector<uint8_t> has_sb;  // has SolverBody (dynamic or kinematic)
+    std::vector<Quat<S>> rot0;
+    std::vector<V3<S>> pos0, linvel0;
+    S dt = 0, h = 0, max_overlap_solve_speed = 0, warm_coeff = 0;
+    std::vector<V3<S>> pre_dp;
+    std::vector<Quat<S>> pre_dq;
+    bool have_joints = false;
+    const SolverBodyInertia<S> dummy_inertia{};
+    uint32_t iters = 1;
+    // boundary bodies of the x-slab partition (AvnBoundary)
+    std::vector<int> bnd_body, bnd_slot, bnd_owner;
+    std::vector<V3<S>> ref_lin, ref_ang;
+    int bnd_rank = 0, bnd_world = 1;
+    size_t bnd_slots = 0;
 
+    StepState(const AvnStepParams& p, const AvnBodyColumns& b, const AvnManifoldColumns* m, const AvnJointSet* j, int threads)
+        : prm(p), bc(b), pool(std::max(1, threads)) {
+        if (m) { mc_store = *m; mc = &mc_store; }
+        if (j) { js_store = *j; js = &js_store; }
+    }
+
+    int prepare() {
+        B = bc.count;
+        w.bodies.assign(B, SolverBody<S>());
+        w.inertias.assign(B, SolverBodyInertia<S>());
+        w.integ.assign(B, VelocityIntegrationData<S>());
+        has_sb.assign(B, 0);
+        rot0.resize(B);
+        pos0.resize(B);
+        linvel0.resize(B);
+        dt = S(prm.dt);
+        h = S(prm.h);
     // ---- prepare_solver_bodies (solver_body/plugin.rs:173-251)
     pool.par_for(B, 1, [&](size_t a, size_t e) {
         for (size_t i = a; i < e; ++i) {
@@ -257,117 +290,124 @@ int solver_step(const AvnStepParams& prm, AvnBodyColumns& bc, AvnManifoldColumns
         }
     });
 
-    const S max_overlap_solve_speed = S(prm.max_overlap_solve_speed) * S(prm.length_unit);
-    const S warm_coeff = S(prm.warm_start_coefficient);
-    std::vector<V3<S>> pre_dp(B);
-    std::vector<Quat<S>> pre_dq(B);
-    const bool have_joints = !w.joints.empty();
-    const SolverBodyInertia<S> dummy_inertia;
-    const uint32_t iters = prm.solver_iterations ? prm.solver_iterations : 1;
-
-    // ---- run_substep_schedule (solver/schedule.rs:194-213)
-    for (uint32_t sub = 0; sub < prm.substeps; ++sub) {
-        // integrate_velocities (integrator/mod.rs:343-391)
-        pool.par_for(B, 1, [&](size_t a, size_t e) {
-            for (size_t i = a; i < e; ++i) {
-                if (!has_sb[i]) continue;
-                if (bc.integration_flags && (bc.integration_flags[i] & AVN_CUSTOM_VELOCITY_INTEGRATION)) continue;
-                SolverBody<S>& sb = w.bodies[i];
-                if (sb.is_kinematic()) continue;
-                const VelocityIntegrationData<S>& vi = w.integ[i];
-                sb.linear_velocity *= vi.linear_damping_rhs;
-                sb.angular_velocity *= vi.angular_damping_rhs;
-                sb.linear_velocity += vi.linear_increment;
-                sb.angular_velocity += vi.angular_increment;
-                if (sb.is_gyroscopic()) {
-                    Quat<S> rotation = mul(sb.delta_rotation, rot0[i]);
-                    solve_gyroscopic_torque(sb.angular_velocity, rotation, C::sym3(bc.inverse_inertia_local, i), h);
-                }
-            }
-        });
-        // clamp_velocities (integrator/mod.rs:467-500)
-        if (bc.max_linear_speed)
-            for (size_t i = 0; i < B; ++i) {
-                S ms = C::scalar(bc.max_linear_speed, i);
-                if (!has_sb[i] || !std::isfinite(ms)) continue;
-                S l2 = length_squared(w.bodies[i].linear_velocity);
-                if (l2 > ms * ms) w.bodies[i].linear_velocity *= ms / std::sqrt(l2);
-            }
-        if (bc.max_angular_speed)
-            for (size_t i = 0; i < B; ++i) {
-                S ms = C::scalar(bc.max_angular_speed, i);
-                if (!has_sb[i] || !std::isfinite(ms)) continue;
-                S l2 = length_squared(w.bodies[i].angular_velocity);
-                if (l2 > ms * ms) w.bodies[i].angular_velocity *= ms / std::sqrt(l2);
-            }
-        // warm_start (solver/plugin.rs:453-482)
-        for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
-                                               const SolverBodyInertia<S>& i2) { warm_start_constraint(c, b1, b2, i1, i2, warm_coeff); });
-        // solve_contacts::<true> (solver/plugin.rs:531-581)
-        for (uint32_t it = 0; it < iters; ++it)
-            for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
-                                                   const SolverBodyInertia<S>& i2) { solve_constraint(c, b1, b2, i1, i2, h, true, max_overlap_solve_speed); });
-        // integrate_positions (integrator/mod.rs:503-535)
-        pool.par_for(B, 1, [&](size_t a, size_t e) {
-            for (size_t i = a; i < e; ++i) {
-                if (!has_sb[i]) continue;
-                if (bc.integration_flags && (bc.integration_flags[i] & AVN_CUSTOM_POSITION_INTEGRATION)) continue;
-                SolverBody<S>& sb = w.bodies[i];
-                sb.delta_position += sb.linear_velocity * h;
-                sb.delta_rotation = mul(quat_from_scaled_axis(sb.angular_velocity * h), sb.delta_rotation);
-            }
-        });
-        // update_solver_body_angular_inertia recomputes the same value — nothing to do.
-        // solve_contacts::<false> (relax)
-        for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
-                                               const SolverBodyInertia<S>& i2) { solve_constraint(c, b1, b2, i1, i2, h, false, max_overlap_solve_speed); });
-        // XPBD (xpbd/plugin.rs:58-94). With no joints the projection is an exact no-op.
-        if (have_joints) {
-            for (size_t i = 0; i < B; ++i) { pre_dp[i] = w.bodies[i].delta_position; pre_dq[i] = w.bodies[i].delta_rotation; }
-            for (JointData<S>& j : w.joints) {
-                SolverBody<S> d1, d2;  // SolverBody::default()
-                SolverBody<S>* b1 = &d1; SolverBody<S>* b2 = &d2;
-                const SolverBodyInertia<S>* i1 = &dummy_inertia; const SolverBodyInertia<S>* i2 = &dummy_inertia;
-                if (has_sb[j.body1]) { b1 = &w.bodies[j.body1]; i1 = &w.inertias[j.body1]; }
-                if (has_sb[j.body2]) { b2 = &w.bodies[j.body2]; i2 = &w.inertias[j.body2]; }
-                int rel = int(i1->dominance) - int(i2->dominance);
-                if (rel > 0) i1 = &dummy_inertia; else if (rel < 0) i2 = &dummy_inertia;
-                solve_joint(j, *b1, *b2, *i1, *i2, h);
-            }
-            // project_linear_velocity / project_angular_velocity (xpbd/plugin.rs:192-240)
-            for (size_t i = 0; i < B; ++i) {
-                if (!has_sb[i]) continue;
-                SolverBody<S>& sb = w.bodies[i];
-                sb.linear_velocity += (sb.delta_position - pre_dp[i]) / h;
-            }
-            for (size_t i = 0; i < B; ++i) {
-                if (!has_sb[i]) continue;
-                SolverBody<S>& sb = w.bodies[i];
-                Quat<S> dr = mul(sb.delta_rotation, inverse(pre_dq[i]));
-                V3<S> nav = S(2) * xyz(dr) / h;
-                if (dr.w < S(0)) nav = -nav;
-                sb.angular_velocity += nav;
-            }
-            // joint_damping<T> (solver/plugin.rs:759-806)
-            for (JointData<S>& j : w.joints) {
-                if (!j.damping) continue;
-                SolverBody<S> d1, d2;
-                SolverBody<S>* b1 = &d1; SolverBody<S>* b2 = &d2;
-                const SolverBodyInertia<S>* i1 = &dummy_inertia; const SolverBodyInertia<S>* i2 = &dummy_inertia;
-                if (has_sb[j.body1]) { b1 = &w.bodies[j.body1]; i1 = &w.inertias[j.body1]; }
-                if (has_sb[j.body2]) { b2 = &w.bodies[j.body2]; i2 = &w.inertias[j.body2]; }
-                V3<S> delta_omega = (b2->angular_velocity - b1->angular_velocity) * std::fmin(j.damping_angular * h, S(1));
-                if (!b1->is_kinematic()) b1->angular_velocity += delta_omega;
-                if (!b2->is_kinematic()) b2->angular_velocity -= delta_omega;
-                V3<S> delta_v = (b2->linear_velocity - b1->linear_velocity) * std::fmin(j.damping_linear * h, S(1));
-                V3<S> w1 = i1->effective_inv_mass(), w2 = i2->effective_inv_mass();
-                V3<S> p = delta_v * recip_or_zero(w1 + w2);
-                b1->linear_velocity += p * w1;
-                b2->linear_velocity -= p * w2;
-            }
-        }
+        max_overlap_solve_speed = S(prm.max_overlap_solve_speed) * S(prm.length_unit);
+        warm_coeff = S(prm.warm_start_coefficient);
+        pre_dp.resize(B);
+        pre_dq.resize(B);
+        have_joints = !w.joints.empty();
+        iters = prm.solver_iterations ? prm.solver_iterations : 1;
+        return AVN_OK;
     }
 
+    // one iteration of run_substep_schedule (solver/schedule.rs:194-213)
+    void substep() {
+    // integrate_velocities (integrator/mod.rs:343-391)
+    pool.par_for(B, 1, [&](size_t a, size_t e) {
+        for (size_t i = a; i < e; ++i) {
+            if (!has_sb[i]) continue;
+            if (bc.integration_flags && (bc.integration_flags[i] & AVN_CUSTOM_VELOCITY_INTEGRATION)) continue;
+            SolverBody<S>& sb = w.bodies[i];
+            if (sb.is_kinematic()) continue;
+            const VelocityIntegrationData<S>& vi = w.integ[i];
+            sb.linear_velocity *= vi.linear_damping_rhs;
+            sb.angular_velocity *= vi.angular_damping_rhs;
+            sb.linear_velocity += vi.linear_increment;
+            sb.angular_velocity += vi.angular_increment;
+            if (sb.is_gyroscopic()) {
+                Quat<S> rotation = mul(sb.delta_rotation, rot0[i]);
+                solve_gyroscopic_torque(sb.angular_velocity, rotation, C::sym3(bc.inverse_inertia_local, i), h);
+            }
+        }
+    });
+    // clamp_velocities (integrator/mod.rs:467-500)
+    if (bc.max_linear_speed)
+        for (size_t i = 0; i < B; ++i) {
+            S ms = C::scalar(bc.max_linear_speed, i);
+            if (!has_sb[i] || !std::isfinite(ms)) continue;
+            S l2 = length_squared(w.bodies[i].linear_velocity);
+            if (l2 > ms * ms) w.bodies[i].linear_velocity *= ms / std::sqrt(l2);
+        }
+    if (bc.max_angular_speed)
+        for (size_t i = 0; i < B; ++i) {
+            S ms = C::scalar(bc.max_angular_speed, i);
+            if (!has_sb[i] || !std::isfinite(ms)) continue;
+            S l2 = length_squared(w.bodies[i].angular_velocity);
+            if (l2 > ms * ms) w.bodies[i].angular_velocity *= ms / std::sqrt(l2);
+        }
+    // x-slab partition: the reference point of this substep's constraint impulses on the boundary bodies
+    for (size_t k = 0; k < bnd_body.size(); ++k) {
+        ref_lin[k] = w.bodies[bnd_body[k]].linear_velocity;
+        ref_ang[k] = w.bodies[bnd_body[k]].angular_velocity;
+    }
+    // warm_start (solver/plugin.rs:453-482)
+    for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
+                                           const SolverBodyInertia<S>& i2) { warm_start_constraint(c, b1, b2, i1, i2, warm_coeff); });
+    // solve_contacts::<true> (solver/plugin.rs:531-581)
+    for (uint32_t it = 0; it < iters; ++it)
+        for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
+                                               const SolverBodyInertia<S>& i2) { solve_constraint(c, b1, b2, i1, i2, h, true, max_overlap_solve_speed); });
+    // integrate_positions (integrator/mod.rs:503-535)
+    pool.par_for(B, 1, [&](size_t a, size_t e) {
+        for (size_t i = a; i < e; ++i) {
+            if (!has_sb[i]) continue;
+            if (bc.integration_flags && (bc.integration_flags[i] & AVN_CUSTOM_POSITION_INTEGRATION)) continue;
+            SolverBody<S>& sb = w.bodies[i];
+            sb.delta_position += sb.linear_velocity * h;
+            sb.delta_rotation = mul(quat_from_scaled_axis(sb.angular_velocity * h), sb.delta_rotation);
+        }
+    });
+    // update_solver_body_angular_inertia recomputes the same value — nothing to do.
+    // solve_contacts::<false> (relax)
+    for_each_color<S>(w, pool, has_sb, [&](ContactConstraint<S>& c, SolverBody<S>& b1, SolverBody<S>& b2, const SolverBodyInertia<S>& i1,
+                                           const SolverBodyInertia<S>& i2) { solve_constraint(c, b1, b2, i1, i2, h, false, max_overlap_solve_speed); });
+    // XPBD (xpbd/plugin.rs:58-94). With no joints the projection is an exact no-op.
+    if (have_joints) {
+        for (size_t i = 0; i < B; ++i) { pre_dp[i] = w.bodies[i].delta_position; pre_dq[i] = w.bodies[i].delta_rotation; }
+        for (JointData<S>& j : w.joints) {
+            SolverBody<S> d1, d2;  // SolverBody::default()
+            SolverBody<S>* b1 = &d1; SolverBody<S>* b2 = &d2;
+            const SolverBodyInertia<S>* i1 = &dummy_inertia; const SolverBodyInertia<S>* i2 = &dummy_inertia;
+            if (has_sb[j.body1]) { b1 = &w.bodies[j.body1]; i1 = &w.inertias[j.body1]; }
+            if (has_sb[j.body2]) { b2 = &w.bodies[j.body2]; i2 = &w.inertias[j.body2]; }
+            int rel = int(i1->dominance) - int(i2->dominance);
+            if (rel > 0) i1 = &dummy_inertia; else if (rel < 0) i2 = &dummy_inertia;
+            solve_joint(j, *b1, *b2, *i1, *i2, h);
+        }
+        // project_linear_velocity / project_angular_velocity (xpbd/plugin.rs:192-240)
+        for (size_t i = 0; i < B; ++i) {
+            if (!has_sb[i]) continue;
+            SolverBody<S>& sb = w.bodies[i];
+            sb.linear_velocity += (sb.delta_position - pre_dp[i]) / h;
+        }
+        for (size_t i = 0; i < B; ++i) {
+            if (!has_sb[i]) continue;
+            SolverBody<S>& sb = w.bodies[i];
+            Quat<S> dr = mul(sb.delta_rotation, inverse(pre_dq[i]));
+            V3<S> nav = S(2) * xyz(dr) / h;
+            if (dr.w < S(0)) nav = -nav;
+            sb.angular_velocity += nav;
+        }
+        // joint_damping<T> (solver/plugin.rs:759-806)
+        for (JointData<S>& j : w.joints) {
+            if (!j.damping) continue;
+            SolverBody<S> d1, d2;
+            SolverBody<S>* b1 = &d1; SolverBody<S>* b2 = &d2;
+            const SolverBodyInertia<S>* i1 = &dummy_inertia; const SolverBodyInertia<S>* i2 = &dummy_inertia;
+            if (has_sb[j.body1]) { b1 = &w.bodies[j.body1]; i1 = &w.inertias[j.body1]; }
+            if (has_sb[j.body2]) { b2 = &w.bodies[j.body2]; i2 = &w.inertias[j.body2]; }
+            V3<S> delta_omega = (b2->angular_velocity - b1->angular_velocity) * std::fmin(j.damping_angular * h, S(1));
+            if (!b1->is_kinematic()) b1->angular_velocity += delta_omega;
+            if (!b2->is_kinematic()) b2->angular_velocity -= delta_omega;
+            V3<S> delta_v = (b2->linear_velocity - b1->linear_velocity) * std::fmin(j.damping_linear * h, S(1));
+            V3<S> w1 = i1->effective_inv_mass(), w2 = i2->effective_inv_mass();
+            V3<S> p = delta_v * recip_or_zero(w1 + w2);
+            b1->linear_velocity += p * w1;
+            b2->linear_velocity -= p * w2;
+        }
+    }
+    }
+
+    void restitution() {
     // ---- solve_restitution (solver/plugin.rs:630-718)
     {
         S threshold = S(prm.restitution_threshold) * S(prm.length_unit);
@@ -378,7 +418,9 @@ int solver_step(const AvnStepParams& prm, AvnBodyColumns& bc, AvnManifoldColumns
             for (uint32_t k = 0; k < n; ++k) apply_restitution(c, b1, b2, i1, i2, threshold);
         });
     }
+    }
 
+    int finalize() {
     // ---- writeback_solver_bodies (solver_body/plugin.rs:255-284)
     pool.par_for(B, 1, [&](size_t a, size_t e) {
         for (size_t i = a; i < e; ++i) {
@@ -420,10 +462,89 @@ int solver_step(const AvnStepParams& prm, AvnBodyColumns& bc, AvnManifoldColumns
                 }
     }
     return AVN_OK;
+    }
+
+    // ---- boundary exchange of the x-slab partition: the same record layout and arithmetic as boundary_*_kernel (solver_host.cu)
+    int set_boundary(const AvnBoundary& b) {
+        bnd_body.assign(b.body, b.body + b.count);
+        bnd_slot.assign(b.slot, b.slot + b.count);
+        bnd_owner.assign(b.owner_rank, b.owner_rank + b.count);
+        for (int x : bnd_body)
+            if (x < 0 || size_t(x) >= B) return AVN_ERR_INVALID_ARGUMENT;
+        ref_lin.assign(b.count, V3<S>{0, 0, 0});
+        ref_ang.assign(b.count, V3<S>{0, 0, 0});
+        bnd_rank = int(b.rank);
+        bnd_world = int(b.world);
+        bnd_slots = b.slot_count;
+        return AVN_OK;
+    }
+    void boundary_snapshot() {
+        for (size_t k = 0; k < bnd_body.size(); ++k) {
+            ref_lin[k] = w.bodies[bnd_body[k]].linear_velocity;
+            ref_ang[k] = w.bodies[bnd_body[k]].angular_velocity;
+        }
+    }
+    void boundary_pack(S* table) const {
+        std::fill(table, table + bnd_slots * AVN_BOUNDARY_RECORD_SCALARS, S(0));
+        for (size_t k = 0; k < bnd_body.size(); ++k) {
+            const SolverBody<S>& sb = w.bodies[bnd_body[k]];
+            S* r = table + size_t(bnd_slot[k]) * AVN_BOUNDARY_RECORD_SCALARS;
+            const bool owner = bnd_owner[k] == bnd_rank;
+            r[0] = sb.linear_velocity.x - ref_lin[k].x; r[1] = sb.linear_velocity.y - ref_lin[k].y; r[2] = sb.linear_velocity.z - ref_lin[k].z; r[3] = S(1);
+            r[4] = sb.angular_velocity.x - ref_ang[k].x; r[5] = sb.angular_velocity.y - ref_ang[k].y; r[6] = sb.angular_velocity.z - ref_ang[k].z;
+            r[7] = owner ? S(1) : S(0);
+            if (owner) {
+                r[8] = sb.delta_position.x; r[9] = sb.delta_position.y; r[10] = sb.delta_position.z; r[11] = S(0);
+                r[12] = sb.delta_rotation.x; r[13] = sb.delta_rotation.y; r[14] = sb.delta_rotation.z; r[15] = sb.delta_rotation.w;
+            }
+        }
+    }
+    void boundary_apply(const S* gathered) {
+        for (size_t k = 0; k < bnd_body.size(); ++k) {
+            SolverBody<S>& sb = w.bodies[bnd_body[k]];
+            V3<S> l = ref_lin[k], a = ref_ang[k];
+            for (int r = 0; r < bnd_world; ++r) {
+                const S* rec = gathered + (size_t(r) * bnd_slots + size_t(bnd_slot[k])) * AVN_BOUNDARY_RECORD_SCALARS;
+                if (rec[3] == S(0)) continue;
+                l.x = l.x + rec[0]; l.y = l.y + rec[1]; l.z = l.z + rec[2];
+                a.x = a.x + rec[4]; a.y = a.y + rec[5]; a.z = a.z + rec[6];
+            }
+            sb.linear_velocity = l;
+            sb.angular_velocity = a;
+            const S* own = gathered + (size_t(bnd_owner[k]) * bnd_slots + size_t(bnd_slot[k])) * AVN_BOUNDARY_RECORD_SCALARS;
+            sb.delta_position = V3<S>{own[8], own[9], own[10]};
+            sb.delta_rotation = Quat<S>{own[12], own[13], own[14], own[15]};
+        }
+    }
+    bool needs_restitution() const {
+        for (int col = 0; col < AVN_GRAPH_COLOR_COUNT; ++col)
+            for (const ContactConstraint<S>& c : w.constraints[col])
+                if (c.restitution != S(0)) return true;
+        return false;
+    }
+};
+
+template <class S>
+int solver_step(const AvnStepParams& prm, AvnBodyColumns& bc, AvnManifoldColumns* mc, AvnJointSet* js, int threads) {
+    StepState<S> st(prm, bc, mc, js, threads);
+    int rc = st.prepare();
+    if (rc != AVN_OK) return rc;
+    for (uint32_t sub = 0; sub < prm.substeps; ++sub) st.substep();
+    st.restitution();
+    return st.finalize();
 }
 
 template int solver_step<float>(const AvnStepParams&, AvnBodyColumns&, AvnManifoldColumns*, AvnJointSet*, int);
 template int solver_step<double>(const AvnStepParams&, AvnBodyColumns&, AvnManifoldColumns*, AvnJointSet*, int);
+
+// type-erased handle for the resumable entry points
+struct StepHandle {
+    uint32_t bits;
+    void* state;
+};
+template <class F32, class F64> static auto dispatch(StepHandle* h, F32 f32, F64 f64) {
+    return h->bits == 32 ? f32(static_cast<StepState<float>*>(h->state)) : f64(static_cast<StepState<double>*>(h->state));
+}
 
 }  // namespace orc
 
@@ -434,5 +555,58 @@ int orc_solver_step(uint32_t scalar_bits, const AvnStepParams* prm, AvnBodyColum
     if (scalar_bits == 32) return orc::solver_step<float>(*prm, *bodies, manifolds, joints, threads);
     if (scalar_bits == 64) return orc::solver_step<double>(*prm, *bodies, manifolds, joints, threads);
     return AVN_ERR_INVALID_ARGUMENT;
+}
+
+// ---- the stage in pieces (tests of the x-slab partition): the column buffers must stay alive until orc_step_finish
+#define ORC_EACH(h, expr) orc::dispatch((h), [&](auto* st) { return (expr); }, [&](auto* st) { return (expr); })
+void* orc_step_begin(uint32_t scalar_bits, const AvnStepParams* prm, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints,
+                     int threads) {
+    if (!prm || !bodies || (scalar_bits != 32 && scalar_bits != 64)) return nullptr;
+    auto* h = new orc::StepHandle{scalar_bits, nullptr};
+    int rc;
+    if (scalar_bits == 32) {
+        auto* st = new orc::StepState<float>(*prm, *bodies, manifolds, joints, threads);
+        h->state = st;
+        rc = st->prepare();
+    } else {
+        auto* st = new orc::StepState<double>(*prm, *bodies, manifolds, joints, threads);
+        h->state = st;
+        rc = st->prepare();
+    }
+    if (rc != AVN_OK) {
+        ORC_EACH(h, (delete st, 0));
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+int orc_step_substeps(void* handle, uint32_t count) {
+    auto* h = static_cast<orc::StepHandle*>(handle);
+    for (uint32_t i = 0; i < count; ++i) ORC_EACH(h, (st->substep(), 0));
+    return AVN_OK;
+}
+int orc_step_restitution(void* handle) { return ORC_EACH(static_cast<orc::StepHandle*>(handle), (st->restitution(), int(AVN_OK))); }
+int orc_step_needs_restitution(void* handle) { return ORC_EACH(static_cast<orc::StepHandle*>(handle), int(st->needs_restitution())); }
+int orc_step_set_boundary(void* handle, const AvnBoundary* b) { return ORC_EACH(static_cast<orc::StepHandle*>(handle), st->set_boundary(*b)); }
+int orc_step_boundary_snapshot(void* handle) { return ORC_EACH(static_cast<orc::StepHandle*>(handle), (st->boundary_snapshot(), int(AVN_OK))); }
+int orc_step_boundary_pack(void* handle, void* table) {
+    auto* h = static_cast<orc::StepHandle*>(handle);
+    if (h->bits == 32) static_cast<orc::StepState<float>*>(h->state)->boundary_pack(static_cast<float*>(table));
+    else static_cast<orc::StepState<double>*>(h->state)->boundary_pack(static_cast<double*>(table));
+    return AVN_OK;
+}
+int orc_step_boundary_apply(void* handle, const void* gathered) {
+    auto* h = static_cast<orc::StepHandle*>(handle);
+    if (h->bits == 32) static_cast<orc::StepState<float>*>(h->state)->boundary_apply(static_cast<const float*>(gathered));
+    else static_cast<orc::StepState<double>*>(h->state)->boundary_apply(static_cast<const double*>(gathered));
+    return AVN_OK;
+}
+// writeback + store impulses into the column buffers given to orc_step_begin, then frees the handle
+int orc_step_finish(void* handle) {
+    auto* h = static_cast<orc::StepHandle*>(handle);
+    int rc = ORC_EACH(h, st->finalize());
+    ORC_EACH(h, (delete st, 0));
+    delete h;
+    return rc;
 }
 }

@@ -285,3 +285,46 @@ def test_f64_contacts_and_joints(scalar):
         oracle_lib.solver_step(prm, bo, None, jo)
         ctx.solver_step(prm, bg, None, jg)
         assert_bodies_close(bg, bo, rtol=1e-9, what="f64 joints: ")
+
+
+@pytest.mark.parametrize("scalar,rtol", [(np.float32, RTOL), (np.float64, 1e-9)])
+def test_sphere_only_scene_single_point_kernels(scalar, rtol, monkeypatch):
+    """BASELINE config 5 in miniature: every manifold has one point, which selects the MAXP = 1 build of the step kernel and the
+    quarter-size staging tile; wavefront, barrier and per-phase launches must agree bit for bit, and with the oracle to rtol."""
+    sc = scenes.falling_spheres(3000, seed=7, box=(14.0, 6.0, 14.0), scalar=scalar)
+    _, (prm, b, m, j) = advance_to_solver_input(sc, steps=2, substeps=4)
+    assert m.count > 1000 and m.penetration.shape[0] == m.count
+    bo, mo = b.copy(), m.copy()
+    oracle_lib.solver_step(prm, bo, mo)
+    results = []
+    for mode in (None, "barrier", "phases"):
+        if mode:
+            monkeypatch.setenv("AVN_LAUNCH_MODE", mode)
+        with api.Context(device=0, scalar=scalar) as ctx:
+            bg, mg = b.copy(), m.copy()
+            ctx.solver_step(prm, bg, mg)
+        assert_bodies_close(bg, bo, rtol=rtol, what=f"spheres {mode}: ")
+        assert_manifolds_close(mg, mo, rtol=rtol, what=f"spheres {mode}: ")
+        results.append((bg, mg))
+    for bg, mg in results[1:]:
+        assert np.array_equal(bg.position, results[0][0].position) and np.array_equal(bg.linear_velocity, results[0][0].linear_velocity)
+        assert np.array_equal(mg.warm_start_normal_impulse, results[0][1].warm_start_normal_impulse)
+
+
+def test_manifold_csr_is_validated(gpu_ctx):
+    """More than 4 points in a manifold, or decreasing offsets, is an INVALID_ARGUMENT error, not undefined behaviour."""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cubes_example(3), steps=45, substeps=1)
+    assert m.penetration.shape[0] > 4 and m.count > 2
+    wide = m.copy()
+    po = wide.point_offsets.copy()
+    po[1:-1] = po[-1]        # manifold 0 owns every point
+    wide.point_offsets = po
+    with pytest.raises(api.AvianError):
+        gpu_ctx.solver_step(prm, b.copy(), wide)
+    decreasing = m.copy()
+    po = decreasing.point_offsets.copy()
+    po[1] = po[2] + 1
+    decreasing.point_offsets = po
+    with pytest.raises(api.AvianError):
+        gpu_ctx.solver_step(prm, b.copy(), decreasing)
+    gpu_ctx.solver_step(prm, b.copy(), m.copy())   # the context stays usable after a rejected upload
