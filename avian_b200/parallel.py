@@ -187,3 +187,240 @@ def slab_broadphase(broadphase, aabbs, info: RankInfo, cuts: np.ndarray | None =
     parts = [({c: (gathered[c][r].view(np.uint32) if c != "flags" else gathered[c][r]) for c in PAIR_COLUMNS}, orders[r].view(np.uint32))
              for r in range(info.world)]
     return merge_slab_results(parts)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# x-slab partition of ONE coupled scene: the solver stage (include/avian_b200.h "one coupled scene over several GPUs")
+# ---------------------------------------------------------------------------------------------------------------------------
+# Bodies are owned by the slab of their position.x; a contact constraint by the owner of its first non-static body.  A rank
+# holds its own bodies plus copies of the remote bodies its constraints touch; a body held by more than one rank is a boundary
+# body.  Per substep: every rank runs the substep on what it holds, the boundary tables are all-gathered (the one collective),
+# every holder rebuilds the same velocity (v_ref + every holder's impulses, summed in rank order) and takes the owner's position
+# deltas.  Impulses cross a cut once per substep: the result equals the single-GPU step to solver tolerance (bit for bit when no
+# constraint crosses a cut).
+@dataclass
+class SolverShard:
+    bodies: object               # api.Bodies held by this rank, ascending global index
+    manifolds: object            # api.Manifolds owned by this rank (colour-major, reference order kept) or None
+    body_index: np.ndarray       # local body -> global body
+    owned_body: np.ndarray       # bool per local body
+    manifold_index: np.ndarray   # local manifold -> global manifold
+    point_index: np.ndarray      # local contact point -> global contact point
+    bnd_body: np.ndarray         # boundary bodies held here: local body index,
+    bnd_slot: np.ndarray         # slot in the global boundary table,
+    bnd_owner: np.ndarray        # owning rank
+    slot_count: int
+
+
+def body_slab_cuts(bodies, world: int) -> np.ndarray:
+    from avian_b200 import api
+    return slab_cuts(bodies.position[bodies.kind != api.BODY_STATIC, 0], world)
+
+
+def _take(obj, rows, skip=()):
+    out = {}
+    for k, v in obj.__dict__.items():
+        out[k] = v if (v is None or k in skip) else np.ascontiguousarray(v[rows])
+    return out
+
+
+def shard_solver(bodies, manifolds, cuts: np.ndarray, rank: int, world: int) -> SolverShard:
+    from avian_b200 import api
+    B = bodies.count
+    static = bodies.kind == api.BODY_STATIC
+    owner = slab_of(bodies.position[:, 0], cuts)
+    owner[static] = -1
+    held = np.zeros((world, B), dtype=bool)
+    dyn = np.nonzero(~static)[0]
+    held[owner[dyn], dyn] = True
+    M = 0 if manifolds is None else manifolds.count
+    referenced = np.zeros(B, dtype=bool)
+    if M:
+        b1, b2 = manifolds.body1.astype(np.int64), manifolds.body2.astype(np.int64)
+        o1 = np.where(b1 >= 0, owner[np.maximum(b1, 0)], -1)
+        o2 = np.where(b2 >= 0, owner[np.maximum(b2, 0)], -1)
+        m_owner = np.where(o1 >= 0, o1, o2)
+        m_owner[m_owner < 0] = 0                      # static-static: never solved, parked on rank 0
+        for b in (b1, b2):
+            ok = (b >= 0) & ~static[np.maximum(b, 0)]
+            held[m_owner[ok], b[ok]] = True
+        mine = np.nonzero(m_owner == rank)[0]
+        for b in (b1, b2):
+            bb = b[mine]
+            referenced[bb[bb >= 0]] = True
+    holders = held.sum(axis=0)
+    boundary = np.nonzero(holders > 1)[0]             # ascending global index = slot order
+    slot_of_body = np.full(B, -1, dtype=np.int32)
+    slot_of_body[boundary] = np.arange(boundary.size, dtype=np.int32)
+    local = held[rank] | (referenced & static)
+    body_index = np.nonzero(local)[0]
+    to_local = np.full(B, -1, dtype=np.int32)
+    to_local[body_index] = np.arange(body_index.size, dtype=np.int32)
+    lb = api.Bodies(**_take(bodies, body_index))
+    lm, point_index, manifold_index = None, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    if M and mine.size:
+        manifold_index = mine
+        po = manifolds.point_offsets.astype(np.int64)
+        n = po[mine + 1] - po[mine]
+        new_po = np.concatenate([[0], np.cumsum(n)])
+        point_index = np.repeat(po[mine] - new_po[:-1], n) + np.arange(new_po[-1])
+        per_m = ("body1", "body2", "normal", "friction", "restitution", "tangent_velocity")
+        per_p = ("anchor1", "anchor2", "penetration", "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")
+        cols = {k: (None if getattr(manifolds, k) is None else np.ascontiguousarray(getattr(manifolds, k)[mine])) for k in per_m}
+        cols.update({k: np.ascontiguousarray(getattr(manifolds, k)[point_index]) for k in per_p})
+        for k in ("body1", "body2"):
+            g = cols[k]
+            cols[k] = np.where(g >= 0, to_local[np.maximum(g, 0)], g).astype(np.int32)
+        cols["point_offsets"] = new_po.astype(np.uint32)
+        cols["color_offsets"] = np.searchsorted(mine, np.asarray(manifolds.color_offsets, dtype=np.int64), side="left").astype(np.uint32)
+        lm = api.Manifolds(**cols)
+    mine_bnd = boundary[held[rank, boundary]]
+    return SolverShard(lb, lm, body_index, (owner[body_index] == rank), manifold_index, point_index,
+                       to_local[mine_bnd].astype(np.int32), slot_of_body[mine_bnd].astype(np.int32), owner[mine_bnd].astype(np.int32), int(boundary.size))
+
+
+class GpuSlabEngine:
+    """One rank's solver stage on its api.Context, launched substep by substep; the exchange tables are torch CUDA tensors so the
+    all-gather runs on device memory, ordered with the launches on the context's own stream."""
+
+    def __init__(self, ctx):
+        import torch
+        self.ctx = ctx
+        self.torch = torch
+        self.device = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=self.device)
+        self.dtype = torch.float32 if ctx.scalar == np.float32 else torch.float64
+
+    def begin(self, prm, shard: SolverShard, rank: int, world: int):
+        self.ctx.solver_upload(prm, shard.bodies, shard.manifolds, None)
+        self.ctx.solver_set_boundary(shard.bnd_body, shard.bnd_slot, shard.bnd_owner, shard.slot_count, rank, world)
+
+    def tables(self, slot_count: int, world: int):
+        from avian_b200 import api
+        n = max(slot_count, 1) * api.BOUNDARY_RECORD_SCALARS
+        return (self.torch.zeros(n, dtype=self.dtype, device=self.device), self.torch.zeros(world * n, dtype=self.dtype, device=self.device))
+
+    def run(self, first: int, count: int, flags: int): self.ctx.solver_run_range(first, count, flags)
+    def snapshot(self): self.ctx.solver_boundary_snapshot()
+    def pack(self, table): self.ctx.solver_boundary_pack(table.data_ptr())
+    def apply(self, gathered): self.ctx.solver_boundary_apply(gathered.data_ptr())
+    def needs_restitution(self) -> bool: return self.ctx.solver_needs_restitution()
+    def finish(self): self.ctx.solver_download()
+
+    def all_gather(self, gathered, table):
+        import torch.distributed as dist
+        with self.torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(gathered, table)
+
+    def copy_table(self, gathered, r: int, table):   # in-process stand-in for the collective (several engines on one device)
+        with self.torch.cuda.stream(self.stream):
+            gathered[r * table.numel():(r + 1) * table.numel()].copy_(table, non_blocking=True)
+
+    def sync(self): self.stream.synchronize()
+
+
+def run_slab_step(engines, shards, prm, ranks, world: int, gather, agree_any):
+    """The partitioned solver stage in lockstep over the (engine, shard) pairs this process drives: all `world` of them in the
+    in-process tests (gather = copies), exactly one under torch.distributed (gather = the NCCL / gloo all-gather)."""
+    from avian_b200 import api
+    slot_count = shards[0].slot_count
+    for e, sh, r in zip(engines, shards, ranks):
+        e.begin(prm, sh, r, world)
+    tabs = [e.tables(slot_count, world) for e in engines]
+
+    def exchange():
+        if slot_count == 0:
+            return
+        for e, (t, g) in zip(engines, tabs):
+            e.pack(t)
+        gather(engines, tabs)
+        for e, (t, g) in zip(engines, tabs):
+            e.apply(g)
+
+    substeps = int(prm.substeps)
+    for s in range(substeps):
+        for e in engines:
+            e.run(s, 1, api.RUN_PREPARE if s == 0 else 0)
+        exchange()
+    if substeps == 0:
+        for e in engines:
+            e.run(0, 0, api.RUN_PREPARE)
+    if agree_any(any(e.needs_restitution() for e in engines)):
+        for e in engines:
+            e.snapshot()
+            e.run(substeps, 0, api.RUN_RESTITUTION)
+        exchange()
+    for e in engines:
+        e.run(substeps, 0, api.RUN_FINALIZE)
+        e.finish()
+
+
+BODY_OUTPUTS = ("position", "rotation", "linear_velocity", "angular_velocity")
+POINT_OUTPUTS = ("warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")
+
+
+def scatter_results(bodies, manifolds, shard: SolverShard) -> None:
+    """Write one rank's results (owned bodies, owned constraints' impulses) back into the global columns."""
+    rows = shard.body_index[shard.owned_body]
+    for k in BODY_OUTPUTS:
+        getattr(bodies, k)[rows] = getattr(shard.bodies, k)[shard.owned_body]
+    if shard.manifolds is not None:
+        for k in POINT_OUTPUTS:
+            getattr(manifolds, k)[shard.point_index] = getattr(shard.manifolds, k)
+
+
+def slab_solver_step_local(make_engine, prm, bodies, manifolds, world: int, cuts: np.ndarray | None = None):
+    """All `world` slabs in this process (tests, single-GPU dry runs).  Results are written into bodies / manifolds."""
+    if cuts is None:
+        cuts = body_slab_cuts(bodies, world)
+    shards = [shard_solver(bodies, manifolds, cuts, r, world) for r in range(world)]
+    engines = [make_engine(r) for r in range(world)]
+
+    def gather(engines_, tabs):
+        for e in engines_:
+            e.sync()            # every table is packed before anyone copies it (the engines have their own streams)
+        for e, (t, g) in zip(engines_, tabs):
+            for r, (tr, _) in enumerate(tabs):
+                e.copy_table(g, r, tr)
+        for e in engines_:
+            e.sync()
+
+    run_slab_step(engines, shards, prm, list(range(world)), world, gather, lambda flag: flag)
+    for sh in shards:
+        scatter_results(bodies, manifolds, sh)
+    return shards
+
+
+def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.ndarray | None = None, device: str = "cpu") -> SolverShard:
+    """One rank of the partitioned stage under torch.distributed.  Every rank ends with the full result in bodies / manifolds
+    (one gather of results per step)."""
+    if cuts is None:
+        cuts = body_slab_cuts(bodies, info.world)
+    sh = shard_solver(bodies, manifolds, cuts, info.rank, info.world)
+
+    def gather(engines_, tabs):
+        engines_[0].all_gather(tabs[0][1], tabs[0][0])
+
+    def agree_any(flag: bool) -> bool:
+        return reduce_max([1.0 if flag else 0.0], info, device)[0] > 0.0
+
+    run_slab_step([engine], [sh], prm, [info.rank], info.world, gather, agree_any)
+    # results: every rank contributes its owned rows
+    rows = sh.body_index[sh.owned_body].astype(np.int64)
+    all_rows = allgather_ragged(rows, info, device)
+    for k in BODY_OUTPUTS:
+        col = getattr(sh.bodies, k)[sh.owned_body]
+        parts = allgather_ragged(np.ascontiguousarray(col).reshape(-1), info, device)
+        width = col.shape[1] if col.ndim > 1 else 1
+        for r in range(info.world):
+            getattr(bodies, k)[all_rows[r]] = parts[r].reshape(-1, width) if col.ndim > 1 else parts[r]
+    if manifolds is not None and manifolds.count:
+        all_pts = allgather_ragged(sh.point_index.astype(np.int64), info, device)
+        for k in POINT_OUTPUTS:
+            glob = getattr(manifolds, k)
+            col = getattr(sh.manifolds, k) if sh.manifolds is not None else glob[:0]
+            parts = allgather_ragged(np.ascontiguousarray(col).reshape(-1), info, device)
+            width = glob.shape[1] if glob.ndim > 1 else 1
+            for r in range(info.world):
+                glob[all_pts[r]] = parts[r].reshape(-1, width) if glob.ndim > 1 else parts[r]
+    return sh

@@ -79,3 +79,71 @@ class OracleSolverPlugin(plugins.SolverPlugin):
 
 def oracle_plugins(threads: int = 1, gravity=None) -> plugins.PhysicsPlugins:
     return plugins.PhysicsPlugins().add(plugins.IntegratorPlugin(gravity)).add(OracleBroadPhasePlugin()).add(OracleSolverPlugin(threads=threads))
+
+
+class OracleSlabEngine:
+    """TEST INFRASTRUCTURE: the x-slab partition's per-rank engine backed by the oracle's resumable stage (orc_step_*): the same
+    interface as parallel.GpuSlabEngine with numpy tables, so the orchestration and the collective can be tested without a GPU."""
+
+    def __init__(self, threads: int = 1):
+        l = lib()
+        P = C.POINTER
+        if not hasattr(l, "_slab_bound"):
+            l.orc_step_begin.argtypes = [C.c_uint32, P(api.AvnStepParams), P(api.AvnBodyColumns), P(api.AvnManifoldColumns), P(api.AvnJointSet), C.c_int]
+            l.orc_step_begin.restype = C.c_void_p
+            for name, args in (("substeps", [C.c_void_p, C.c_uint32]), ("restitution", [C.c_void_p]), ("needs_restitution", [C.c_void_p]),
+                               ("set_boundary", [C.c_void_p, P(api.AvnBoundary)]), ("boundary_snapshot", [C.c_void_p]),
+                               ("boundary_pack", [C.c_void_p, C.c_void_p]), ("boundary_apply", [C.c_void_p, C.c_void_p]), ("finish", [C.c_void_p])):
+                fn = getattr(l, f"orc_step_{name}")
+                fn.argtypes, fn.restype = args, C.c_int
+            l._slab_bound = True
+        self.l, self.threads, self.h = l, threads, None
+
+    def begin(self, prm, shard, rank: int, world: int):
+        self.prm, self.shard = prm, shard
+        self.dtype = shard.bodies.position.dtype
+        self._b = shard.bodies.as_struct()
+        self._m = shard.manifolds.as_struct() if shard.manifolds is not None and shard.manifolds.count else None
+        self.rank, self.world = rank, world
+        self.h = None
+
+    def _ensure(self):
+        if self.h is None:
+            self.h = self.l.orc_step_begin(_bits(self.dtype), C.byref(self.prm), C.byref(self._b), C.byref(self._m) if self._m is not None else None, None,
+                                           self.threads)
+            assert self.h, "oracle step_begin failed"
+            sh = self.shard
+            self._bnd = tuple(np.ascontiguousarray(x, dtype=np.int32) for x in (sh.bnd_body, sh.bnd_slot, sh.bnd_owner))
+            b = api.AvnBoundary(int(self._bnd[0].shape[0]), int(sh.slot_count), self.rank, self.world, *(x.ctypes.data for x in self._bnd))
+            assert self.l.orc_step_set_boundary(self.h, C.byref(b)) == 0
+
+    def tables(self, slot_count: int, world: int):
+        n = max(slot_count, 1) * api.BOUNDARY_RECORD_SCALARS
+        return np.zeros(n, dtype=self.dtype), np.zeros(world * n, dtype=self.dtype)
+
+    def run(self, first: int, count: int, flags: int):
+        if flags & api.RUN_PREPARE:
+            self._ensure()
+        if count:
+            assert self.l.orc_step_substeps(self.h, count) == 0
+        if flags & api.RUN_RESTITUTION:
+            assert self.l.orc_step_restitution(self.h) == 0
+        self._finalize = bool(flags & api.RUN_FINALIZE)
+
+    def snapshot(self): assert self.l.orc_step_boundary_snapshot(self.h) == 0
+    def pack(self, table): assert self.l.orc_step_boundary_pack(self.h, table.ctypes.data) == 0
+    def apply(self, gathered): assert self.l.orc_step_boundary_apply(self.h, gathered.ctypes.data) == 0
+    def needs_restitution(self) -> bool: return bool(self.l.orc_step_needs_restitution(self.h))
+
+    def finish(self):
+        assert self._finalize
+        assert self.l.orc_step_finish(self.h) == 0
+        self.h = None
+
+    def all_gather(self, gathered, table):
+        import torch
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(torch.from_numpy(gathered), torch.from_numpy(table))
+
+    def copy_table(self, gathered, r: int, table): gathered[r * table.size:(r + 1) * table.size] = table
+    def sync(self): pass

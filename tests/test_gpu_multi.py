@@ -85,3 +85,113 @@ def test_two_gpu_nccl_slab_broadphase():
         for c in parallel.PAIR_COLUMNS:
             assert np.array_equal(cols[c], getattr(want, c)[:want.count]), (rank, c)
         assert np.array_equal(order, a.order_out)
+
+
+# ---- the solver stage cut into slabs ---------------------------------------------------------------------------------------
+from helpers import RTOL, advance_to_solver_input, assert_bodies_close, assert_manifolds_close  # noqa: E402
+from test_slab_solver_cpu import stack_input, two_piles_input  # noqa: E402
+
+
+def _gpu_lockstep(prm, b, m, world, scalar=np.float32, cuts=None):
+    ctxs = [api.Context(device=0, scalar=scalar) for _ in range(world)]
+    try:
+        return parallel.slab_solver_step_local(lambda r: parallel.GpuSlabEngine(ctxs[r]), prm, b, m, world, cuts)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("mode", [None, "barrier", "phases"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_solver_on_one_device_matches_the_oracle_partition(world, mode, monkeypatch):
+    """The same partition, the same exchange arithmetic: CUDA engines vs oracle engines, 1e-5 like every solver parity test."""
+    if mode:
+        monkeypatch.setenv("AVN_LAUNCH_MODE", mode)
+    prm, b, m = stack_input(nx=10, ny=4, nz=4, steps=3, substeps=6)
+    bo, mo = b.copy(), m.copy()
+    so = parallel.slab_solver_step_local(lambda r: oracle_lib.OracleSlabEngine(), prm, bo, mo, world)
+    bg, mg = b.copy(), m.copy()
+    sg = _gpu_lockstep(prm, bg, mg, world)
+    assert so[0].slot_count == sg[0].slot_count > 0
+    assert_bodies_close(bg, bo, what=f"slabs {world} {mode}: ")
+    assert_manifolds_close(mg, mo, what=f"slabs {world} {mode}: ")
+
+
+def test_slab_solver_uncoupled_piles_bit_for_bit(gpu_ctx):
+    prm, b, m = two_piles_input()
+    bs, ms = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, bs, ms)
+    bg, mg = b.copy(), m.copy()
+    shards = _gpu_lockstep(prm, bg, mg, 2, cuts=np.array([15.0], dtype=np.float32))
+    assert shards[0].slot_count == 0
+    for k in parallel.BODY_OUTPUTS:
+        assert np.array_equal(getattr(bg, k), getattr(bs, k)), k
+    for k in parallel.POINT_OUTPUTS:
+        assert np.array_equal(getattr(mg, k), getattr(ms, k)), k
+
+
+def test_slab_solver_restitution_and_f64():
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(6, 3, 3, brick=True, restitution=0.5, scalar=np.float64), steps=2, substeps=3)
+    b.linear_velocity[:, 1] -= 2.0
+    bo, mo = b.copy(), m.copy()
+    parallel.slab_solver_step_local(lambda r: oracle_lib.OracleSlabEngine(), prm, bo, mo, 2)
+    bg, mg = b.copy(), m.copy()
+    _gpu_lockstep(prm, bg, mg, 2, scalar=np.float64)
+    assert_bodies_close(bg, bo, rtol=1e-9, what="slabs f64 restitution: ")
+
+
+def test_run_range_equals_one_launch(gpu_ctx):
+    """avn_solver_run_range substep by substep (no boundary) is the same arithmetic as avn_solver_run."""
+    prm, b, m = stack_input()
+    b1, m1 = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, b1, m1)
+    b2, m2 = b.copy(), m.copy()
+    gpu_ctx.solver_upload(prm, b2, m2, None)
+    n = int(prm.substeps)
+    for s in range(n):
+        gpu_ctx.solver_run_range(s, 1, api.RUN_PREPARE if s == 0 else 0)
+    gpu_ctx.solver_run_range(n, 0, api.RUN_RESTITUTION)
+    gpu_ctx.solver_run_range(n, 0, api.RUN_FINALIZE)
+    gpu_ctx.solver_download()
+    assert np.array_equal(b1.position, b2.position) and np.array_equal(b1.linear_velocity, b2.linear_velocity)
+    assert np.array_equal(m1.warm_start_normal_impulse, m2.warm_start_normal_impulse)
+    with pytest.raises(api.AvianError):
+        gpu_ctx.solver_upload(prm, b2, m2, None)
+        gpu_ctx.solver_run_range(1, 1, 0)          # the first launch after an upload must prepare
+
+
+def _nccl_solver_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    info = parallel.init(backend="nccl")
+    prm, b, m = stack_input(nx=10, ny=4, nz=4, steps=3, substeps=6)
+    with api.Context(device=rank) as ctx:
+        parallel.slab_solver_step(parallel.GpuSlabEngine(ctx), prm, b, m, info, device=f"cuda:{rank}")
+    q.put((rank, {k: getattr(b, k).copy() for k in parallel.BODY_OUTPUTS}, {k: getattr(m, k).copy() for k in parallel.POINT_OUTPUTS}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_nccl_slab_solver():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_nccl_solver_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=300) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    prm, b, m = stack_input(nx=10, ny=4, nz=4, steps=3, substeps=6)
+    parallel.slab_solver_step_local(lambda r: oracle_lib.OracleSlabEngine(), prm, b, m, world)
+    from helpers import rel_err
+    for rank, bodies, points in results:
+        for k in parallel.BODY_OUTPUTS:
+            assert rel_err(bodies[k], getattr(b, k)) <= RTOL, (rank, k)
+    for k in parallel.BODY_OUTPUTS:      # both ranks hold the same bits
+        assert np.array_equal(results[0][1][k], results[1][1][k]), k
