@@ -421,6 +421,7 @@ class Context:
 
     def __init__(self, device: int = 0, scalar=np.float32, flags: int = 0):
         self.lib = load_library()
+        self.device = int(device)
         self.scalar = np.dtype(scalar)
         cfg = AvnConfig(self.lib.avn_abi_version(), device, 32 if self.scalar == np.float32 else 64, flags)
         h = _vp()

@@ -319,14 +319,18 @@ class GpuSlabEngine:
     def sync(self): self.stream.synchronize()
 
 
-def run_slab_step(engines, shards, prm, ranks, world: int, gather, agree_any):
+def run_slab_step(engines, shards, prm, ranks, world: int, gather, agree_any, upload: bool = True, finish: bool = True, tabs=None):
     """The partitioned solver stage in lockstep over the (engine, shard) pairs this process drives: all `world` of them in the
-    in-process tests (gather = copies), exactly one under torch.distributed (gather = the NCCL / gloo all-gather)."""
+    in-process tests (gather = copies), exactly one under torch.distributed (gather = the NCCL / gloo all-gather).
+    upload=False re-runs the snapshot already resident on the engines (a PREPARE launch restarts from it); finish=False leaves the
+    results on the device."""
     from avian_b200 import api
     slot_count = shards[0].slot_count
-    for e, sh, r in zip(engines, shards, ranks):
-        e.begin(prm, sh, r, world)
-    tabs = [e.tables(slot_count, world) for e in engines]
+    if upload:
+        for e, sh, r in zip(engines, shards, ranks):
+            e.begin(prm, sh, r, world)
+    if tabs is None:
+        tabs = [e.tables(slot_count, world) for e in engines]
 
     def exchange():
         if slot_count == 0:
@@ -352,7 +356,9 @@ def run_slab_step(engines, shards, prm, ranks, world: int, gather, agree_any):
         exchange()
     for e in engines:
         e.run(substeps, 0, api.RUN_FINALIZE)
-        e.finish()
+        if finish:
+            e.finish()
+    return tabs
 
 
 BODY_OUTPUTS = ("position", "rotation", "linear_velocity", "angular_velocity")
@@ -391,20 +397,25 @@ def slab_solver_step_local(make_engine, prm, bodies, manifolds, world: int, cuts
     return shards
 
 
-def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.ndarray | None = None, device: str = "cpu") -> SolverShard:
-    """One rank of the partitioned stage under torch.distributed.  Every rank ends with the full result in bodies / manifolds
-    (one gather of results per step)."""
-    if cuts is None:
-        cuts = body_slab_cuts(bodies, info.world)
-    sh = shard_solver(bodies, manifolds, cuts, info.rank, info.world)
+def dist_gather(engines_, tabs) -> None:
+    engines_[0].all_gather(tabs[0][1], tabs[0][0])
 
-    def gather(engines_, tabs):
-        engines_[0].all_gather(tabs[0][1], tabs[0][0])
+
+def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.ndarray | None = None, device: str = "cpu",
+                     shard: SolverShard | None = None) -> SolverShard:
+    """One rank of the partitioned stage under torch.distributed.  Every rank ends with the full result in bodies / manifolds
+    (one gather of results per step).  `shard` = this rank's share when the caller already holds it (a host application keeps its
+    partition between steps)."""
+    if shard is None:
+        if cuts is None:
+            cuts = body_slab_cuts(bodies, info.world)
+        shard = shard_solver(bodies, manifolds, cuts, info.rank, info.world)
+    sh = shard
 
     def agree_any(flag: bool) -> bool:
         return reduce_max([1.0 if flag else 0.0], info, device)[0] > 0.0
 
-    run_slab_step([engine], [sh], prm, [info.rank], info.world, gather, agree_any)
+    run_slab_step([engine], [sh], prm, [info.rank], info.world, dist_gather, agree_any)
     # results: every rank contributes its owned rows
     rows = sh.body_index[sh.owned_body].astype(np.int64)
     all_rows = allgather_ragged(rows, info, device)
