@@ -5,8 +5,8 @@ the boundary tables per substep (avian_b200/parallel.py, include/avian_b200.h). 
         --scene spheres1m --steps 10 --warmup 3
 bench.py's contract (N independent scenes, weak scaling, no collective) is unchanged; this is the other multi-GPU mode of SURVEY §8e.
 Resident arm: every rank's share is uploaded once; a step = local broad phase + the partitioned solver stage (device timed, CUDA
-events on the library stream, max over ranks).  End-to-end arm: host columns in, full host results on every rank out, every step
-(H2D of the share, launches, exchanges, D2H, the result gathers).  Prints one JSON line on rank 0."""
+events on the library stream, max over ranks).  End-to-end arm: every rank's host feeds its own slab, every step (H2D of the share,
+launches, exchanges, D2H of the share's results; no gather of results).  Prints one JSON line on rank 0."""
 import argparse
 import json
 import sys
@@ -76,13 +76,15 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     engine.finish()
 
-    # ---- end-to-end arm: host in, full host results on every rank out
+    # ---- end-to-end arm: every rank's host feeds its own slab: H2D of the share, launches + exchanges, D2H of the share's results
+    #      (pairs whose first interval the slab owns; owned bodies; owned constraints' impulses).  No gather of results.
     b, m = bodies.copy(), man.copy()
+    pairs_out = api.PairList.empty(max(1 << 20, 4 * int(ashard.index.size)))
     sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pairs, order = parallel.slab_broadphase(ctx.broadphase, aabbs, info, acuts, dev) if world > 1 else (ctx.broadphase(aabbs), None)
-        parallel.slab_solver_step(engine, prm, b, m, info, device=dev, shard=shard)
+        ctx.broadphase_upload(ashard.aabbs); ctx.broadphase_run(); ctx.broadphase_download(pairs_out)
+        parallel.slab_solver_step(engine, prm, b, m, info, device=dev, shard=shard, gather_results=False)
     sync()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     dev_ms, e2e_ms = parallel.reduce_max([dev_ms, e2e_ms], info, dev)
