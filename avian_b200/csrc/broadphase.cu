@@ -268,6 +268,7 @@ __device__ __forceinline__ bool pair_filters(const Sweep<S>& s, uint4 mi, uint32
     uint32_t fj = s.flags[j];
     bool interacts = (mi.z & mj.w) != 0 && (mj.z & mi.w) != 0;  // CollisionLayers::interacts_with, layers.rs:423-426
     if ((fi & fj & AVN_AABB_IS_INACTIVE) || !interacts || mi.y == mj.y) return false;
+    if ((fj & AVN_AABB_NOT_J) || ((fi & AVN_AABB_SPLIT_I) && (fj & AVN_AABB_HALO))) return false;  // x-slab partition (include/avian_b200.h)
     if (s.existing && hash_contains(s.existing, s.existing_mask, pair_key(mi.x, mj.x))) return false;
     if (s.jdis && hash_contains(s.jdis, s.jdis_mask, pair_key(mi.y, mj.y))) return false;
     uint32_t u = fi | fj;

@@ -82,7 +82,7 @@ def aggregate_throughput(units_per_rank: float, seconds_per_rank: float, info: R
 # tests/test_gpu_multi.py).  The only collective is the all-gather of the per-slab pair lists.
 import numpy as np  # noqa: E402
 
-AABB_HALO = 0x80
+AABB_HALO, AABB_SPLIT_I, AABB_NOT_J = 0x80, 0x40, 0x20
 
 
 def slab_cuts(min_x: np.ndarray, world: int) -> np.ndarray:
@@ -100,24 +100,45 @@ def slab_of(x: np.ndarray, cuts: np.ndarray) -> np.ndarray:
 
 @dataclass
 class AabbShard:
-    aabbs: object            # api.Aabbs of the local intervals (owned + halo), in the persistent order
+    aabbs: object            # api.Aabbs of the local intervals (left halo + owned + right halo), in the persistent order
     index: np.ndarray        # local interval -> global interval
     owned: np.ndarray        # bool per local interval
+    left: np.ndarray         # bool per local interval: a far-reaching interval owned by an earlier slab (AVN_AABB_SPLIT_I | NOT_J)
+
+
+def wide_intervals(aabbs, cuts: np.ndarray, slab: np.ndarray) -> np.ndarray:
+    """Intervals that reach past the middle of the slab after their own (a ground slab, a long wall).  Their sweep is split: every
+    slab they reach pairs them with the intervals it owns, so no slab has to see the whole scene.  Any choice is exact; this one
+    keeps ordinary bodies that merely straddle a cut out of it."""
+    world = cuts.size + 1
+    if world == 1:
+        return np.zeros(slab.shape, dtype=bool)
+    min_x, max_x = aabbs.aabb_min[:, 0], aabbs.aabb_max[:, 0]
+    hi = np.concatenate([cuts, [min_x.max()]]).astype(np.float64)       # upper end of every slab's min.x range
+    nxt = np.minimum(slab + 1, world - 1)
+    mid_next = 0.5 * (hi[np.minimum(slab, world - 2)] + hi[nxt])
+    return (slab < world - 1) & (max_x.astype(np.float64) >= mid_next)
 
 
 def shard_aabbs(aabbs, cuts: np.ndarray, rank: int) -> AabbShard:
     from avian_b200 import api
-    min_x = aabbs.aabb_min[:, 0]
+    min_x, max_x = aabbs.aabb_min[:, 0], aabbs.aabb_max[:, 0]
     slab = slab_of(min_x, cuts)
+    wide = wide_intervals(aabbs, cuts, slab)
     owned = slab == rank
     halo = np.zeros_like(owned)
-    if owned.any():
-        reach = aabbs.aabb_max[owned, 0].max()
+    narrow = owned & ~wide
+    if narrow.any():
+        reach = max_x[narrow].max()
         halo = (slab > rank) & (min_x <= reach)
-    local = owned | halo
+    lo = cuts[rank - 1] if rank > 0 else None
+    left = wide & (slab < rank) & (max_x >= lo) if rank > 0 else np.zeros_like(owned)
+    local = owned | halo | left
     index = np.nonzero(local)[0]
     flags = aabbs.flags[index].copy()
     flags[halo[index]] |= AABB_HALO
+    flags[(wide & owned)[index]] |= AABB_SPLIT_I
+    flags[left[index]] |= AABB_SPLIT_I | AABB_NOT_J
     existing = aabbs.existing_pairs
     if existing is not None and existing.size:
         top = int(max(int(aabbs.collider.max()), int((existing >> np.uint64(32)).max()), int((existing & np.uint64(0xFFFFFFFF)).max())))
@@ -128,32 +149,54 @@ def shard_aabbs(aabbs, cuts: np.ndarray, rank: int) -> AabbShard:
     sub = api.Aabbs(collider=take(aabbs.collider), body=take(aabbs.body), aabb_min=take(aabbs.aabb_min), aabb_max=take(aabbs.aabb_max), flags=flags,
                     memberships=take(aabbs.memberships), filters=take(aabbs.filters), order_out=np.zeros(index.size, dtype=np.uint32),
                     existing_pairs=existing, joint_disabled_body_pairs=aabbs.joint_disabled_body_pairs)
-    return AabbShard(sub, index, owned[index])
+    return AabbShard(sub, index, owned[index], left[index])
 
 
 PAIR_COLUMNS = ("collider1", "collider2", "body1", "body2", "flags")
 
 
-def slab_broadphase_local(broadphase, aabbs, cuts: np.ndarray, rank: int):
-    """One slab's share: (pair columns, the owned part of the new persistent order as GLOBAL interval indices)."""
-    sh = shard_aabbs(aabbs, cuts, rank)
+def _empty_cols():
+    return {c: np.zeros(0, dtype=np.uint8 if c == "flags" else np.uint32) for c in PAIR_COLUMNS}
+
+
+def slab_broadphase_local(broadphase, aabbs, cuts: np.ndarray, rank: int, shard: AabbShard | None = None):
+    """One slab's share: (pair columns, the owned part of the new persistent order as GLOBAL interval indices, n_foreign).  The first
+    n_foreign pairs start from a far-reaching interval another slab owns (they sort first: its min.x is left of the slab)."""
+    sh = shard_aabbs(aabbs, cuts, rank) if shard is None else shard
     if sh.index.size == 0:
-        return {c: np.zeros(0, dtype=np.uint8 if c == "flags" else np.uint32) for c in PAIR_COLUMNS}, np.zeros(0, dtype=np.uint32)
+        return _empty_cols(), np.zeros(0, dtype=np.uint32), 0
     pairs = broadphase(sh.aabbs)
     n = int(pairs.count)
     order_local = sh.aabbs.order_out
-    n_owned = int(sh.owned.sum())
-    # owned intervals sort before every halo interval (their min.x is strictly smaller)
-    assert sh.owned[order_local[:n_owned]].all(), "slab order: owned intervals must precede the halo"
-    return {c: getattr(pairs, c)[:n].copy() for c in PAIR_COLUMNS}, sh.index[order_local[:n_owned]].astype(np.uint32)
+    n_left, n_owned = int(sh.left.sum()), int(sh.owned.sum())
+    # left-halo intervals sort before every owned one, owned ones before the right halo (strictly smaller min.x each time)
+    assert sh.left[order_local[:n_left]].all() and sh.owned[order_local[n_left:n_left + n_owned]].all(), "slab order: left halo, owned, right halo"
+    cols = {c: getattr(pairs, c)[:n].copy() for c in PAIR_COLUMNS}
+    n_foreign = 0
+    if n_left and n:
+        n_foreign = int(np.isin(cols["collider1"], sh.aabbs.collider[sh.left]).sum())
+        assert np.isin(cols["collider1"][:n_foreign], sh.aabbs.collider[sh.left]).all(), "foreign pairs must lead the slab's list"
+    return cols, sh.index[order_local[n_left:n_left + n_owned]].astype(np.uint32), n_foreign
 
 
-def merge_slab_results(parts):
-    """Concatenate the per-slab (columns, order) results in slab order -> (api.PairList, global order)."""
+def merge_slab_results(parts, collider: np.ndarray | None = None):
+    """Per-slab (columns, order, n_foreign) in slab order -> (api.PairList, global order), the single-GPU list bit for bit: the slabs'
+    own sections concatenated, then every foreign section (pairs starting from a far-reaching interval of an earlier slab) inserted
+    right behind the pairs its interval already has.  `collider` = the global collider column (needed only when a section is foreign)."""
     from avian_b200 import api
-    cols = {c: np.concatenate([p[0][c] for p in parts]) for c in PAIR_COLUMNS}
-    out = api.PairList(cols["collider1"], cols["collider2"], cols["body1"], cols["body2"], cols["flags"], count=int(cols["collider1"].shape[0]))
-    return out, np.concatenate([p[1] for p in parts])
+    order = np.concatenate([p[1] for p in parts])
+    own = {c: np.concatenate([p[0][c][p[2]:] for p in parts]) for c in PAIR_COLUMNS}
+    foreign = {c: np.concatenate([p[0][c][:p[2]] for p in parts]) for c in PAIR_COLUMNS}
+    if foreign["collider1"].size:
+        assert collider is not None, "merging a split interval's pairs needs the global collider column"
+        rank_of = np.zeros(int(collider.max()) + 1, dtype=np.int64)
+        rank_of[collider[order]] = np.arange(order.size)                   # collider id -> position in the sorted order
+        fkey = rank_of[foreign["collider1"]]
+        keep = np.argsort(fkey, kind="stable")                              # by interval; slab order (= j order) kept within one interval
+        at = np.searchsorted(rank_of[own["collider1"]], fkey[keep], side="right")
+        own = {c: np.insert(own[c], at, foreign[c][keep]) for c in PAIR_COLUMNS}
+    out = api.PairList(own["collider1"], own["collider2"], own["body1"], own["body2"], own["flags"], count=int(own["collider1"].shape[0]))
+    return out, order
 
 
 def allgather_ragged(arr: np.ndarray, info: RankInfo, device: str = "cpu") -> list[np.ndarray]:
@@ -180,13 +223,14 @@ def slab_broadphase(broadphase, aabbs, info: RankInfo, cuts: np.ndarray | None =
     persistent order, identical to the single-GPU result.  `broadphase` is the local engine (Context.broadphase)."""
     if cuts is None:
         cuts = slab_cuts(aabbs.aabb_min[:, 0], info.world)
-    cols, order = slab_broadphase_local(broadphase, aabbs, cuts, info.rank)
+    cols, order, n_foreign = slab_broadphase_local(broadphase, aabbs, cuts, info.rank)
     # uint32 columns travel as int32 bit patterns (NCCL / gloo have no unsigned 32-bit type)
     gathered = {c: allgather_ragged(cols[c].view(np.int32) if cols[c].dtype == np.uint32 else cols[c], info, device) for c in PAIR_COLUMNS}
     orders = allgather_ragged(order.view(np.int32), info, device)
-    parts = [({c: (gathered[c][r].view(np.uint32) if c != "flags" else gathered[c][r]) for c in PAIR_COLUMNS}, orders[r].view(np.uint32))
+    foreign = allgather_ragged(np.array([n_foreign], dtype=np.int64), info, device)
+    parts = [({c: (gathered[c][r].view(np.uint32) if c != "flags" else gathered[c][r]) for c in PAIR_COLUMNS}, orders[r].view(np.uint32), int(foreign[r][0]))
              for r in range(info.world)]
-    return merge_slab_results(parts)
+    return merge_slab_results(parts, aabbs.collider)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------

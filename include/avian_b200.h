@@ -78,6 +78,11 @@ typedef enum AvnBodyKind { AVN_BODY_DYNAMIC = 0, AVN_BODY_KINEMATIC = 1, AVN_BOD
  * element of a pair: the sweep never starts from it, so pairs between two halo intervals are left to the slab that owns them.  Not a
  * reference flag; single-GPU callers never set it. */
 #define AVN_AABB_HALO 0x80u
+/* An interval that reaches far beyond its own slab (a ground slab) is not swept by its owner alone: it carries AVN_AABB_SPLIT_I in
+ * every slab it reaches and pairs, as the earlier element, only with intervals that slab owns (never with AVN_AABB_HALO ones).  In
+ * the slabs that do not own it it also carries AVN_AABB_NOT_J: it is never the later element there. */
+#define AVN_AABB_SPLIT_I 0x40u
+#define AVN_AABB_NOT_J 0x20u
 
 /* Flag bits of an emitted pair (what collect_collision_pairs stores on ContactEdge / ContactPair,
  * broad_phase.rs:443-468) plus NEEDS_HOOK: the shim must still call CollisionHooks::filter_pairs for it

@@ -64,6 +64,7 @@ int broadphase(AvnAabbColumns& ac, AvnPairList& out) {
             const uint32_t m2 = ac.memberships ? ac.memberships[b] : 1u, fl2 = ac.filters ? ac.filters[b] : 0xFFFFFFFFu;
             const bool interacts = (m1 & fl2) != 0 && (m2 & fl1) != 0;  // layers.rs:423-426
             if ((f1 & f2 & AVN_AABB_IS_INACTIVE) || !interacts || ac.body[a] == ac.body[b]) continue;
+            if ((f2 & AVN_AABB_NOT_J) || ((f1 & AVN_AABB_SPLIT_I) && (f2 & AVN_AABB_HALO))) continue;  // x-slab partition
             if (existing.count(pair_key(ac.collider[a], ac.collider[b]))) continue;
             if (!jdis.empty() && jdis.count(pair_key(ac.body[a], ac.body[b]))) continue;
             const uint8_t u = f1 | f2;

@@ -28,7 +28,7 @@ def test_slabs_on_one_device_concatenate_to_the_single_list(world, scalar):
         assert_same_pairs(single, want)
         cuts = parallel.slab_cuts(a.aabb_min[:, 0], world)
         parts = [parallel.slab_broadphase_local(ctx.broadphase, a, cuts, r) for r in range(world)]
-    got, order = parallel.merge_slab_results(parts)
+    got, order = parallel.merge_slab_results(parts, a.collider)
     assert_same_pairs(got, want)
     assert np.array_equal(order, want_order)
     assert max(p[0]["collider1"].shape[0] for p in parts) < want.count
@@ -46,7 +46,7 @@ def test_stack_scene_slabs_on_one_device(gpu_ctx):
     want_order = a.order_out.copy()
     cuts = parallel.slab_cuts(a.aabb_min[:, 0], 4)
     parts = [parallel.slab_broadphase_local(gpu_ctx.broadphase, a, cuts, r) for r in range(4)]
-    got, order = parallel.merge_slab_results(parts)
+    got, order = parallel.merge_slab_results(parts, a.collider)
     assert_same_pairs(got, want)
     assert np.array_equal(order, want_order)
 

@@ -65,13 +65,17 @@ def test_slabs_concatenate_to_the_single_list(world, scalar):
     cuts = parallel.slab_cuts(a.aabb_min[:, 0], world)
     assert cuts.shape == (world - 1,) and np.all(np.diff(cuts) >= 0)
     parts = [parallel.slab_broadphase_local(oracle_lib.broadphase, a, cuts, r) for r in range(world)]
-    got, order = parallel.merge_slab_results(parts)
+    got, order = parallel.merge_slab_results(parts, a.collider)
     assert_same_pairs(got, want)
     assert np.array_equal(order, want_order)
     if world > 1:   # the work really is split: no slab emits everything, halos carry the flag and never start a pair
         assert max(p[0]["collider1"].shape[0] for p in parts) < want.count
         sh = parallel.shard_aabbs(a, cuts, 0)
         assert (sh.aabbs.flags[~sh.owned] & parallel.AABB_HALO).all() and not (sh.aabbs.flags[sh.owned] & parallel.AABB_HALO).any()
+        # the ground reaches across every cut: its sweep is split, so no slab holds (nearly) the whole scene
+        assert (sh.aabbs.flags[sh.owned] & parallel.AABB_SPLIT_I).sum() >= 1
+        assert max(parallel.shard_aabbs(a, cuts, r).index.size for r in range(world)) < 0.85 * a.collider.shape[0]
+        assert sum(p[2] for p in parts) > 0
 
 
 def test_every_interval_is_owned_once_and_ties_stay_together():
@@ -95,7 +99,7 @@ def test_empty_and_degenerate_slabs():
     want = oracle_lib.broadphase(a)
     cuts = parallel.slab_cuts(a.aabb_min[:, 0], 3)
     parts = [parallel.slab_broadphase_local(oracle_lib.broadphase, a, cuts, r) for r in range(3)]
-    got, order = parallel.merge_slab_results(parts)
+    got, order = parallel.merge_slab_results(parts, a.collider)
     assert_same_pairs(got, want)
     assert sorted(p[1].shape[0] for p in parts) == [0, 0, 40]
 
