@@ -446,10 +446,10 @@ def dist_gather(engines_, tabs) -> None:
 
 
 def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.ndarray | None = None, device: str = "cpu",
-                     shard: SolverShard | None = None, gather_results: bool = True) -> SolverShard:
+                     shard: SolverShard | None = None, gather_results: bool | None = True) -> SolverShard:
     """One rank of the partitioned stage under torch.distributed.  With gather_results every rank ends with the full result in
-    bodies / manifolds (one gather of results per step); without, a rank writes back only the rows it owns (each rank's host feeds
-    its own slab of the application).  `shard` = this rank's share when the caller already holds it (a host application keeps its
+    bodies / manifolds (one gather of results per step); with False a rank writes back only the rows it owns; with None the results
+    stay in the share's own columns (shard.bodies / shard.manifolds: each rank's host feeds its own slab of the application).  `shard` = this rank's share when the caller already holds it (a host application keeps its
     partition between steps)."""
     if shard is None:
         if cuts is None:
@@ -462,7 +462,8 @@ def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.nd
 
     run_slab_step([engine], [sh], prm, [info.rank], info.world, dist_gather, agree_any)
     if not gather_results:
-        scatter_results(bodies, manifolds, sh)
+        if gather_results is not None:
+            scatter_results(bodies, manifolds, sh)
         return sh
     # results: every rank contributes its owned rows
     rows = sh.body_index[sh.owned_body].astype(np.int64)

@@ -44,6 +44,10 @@ def main():
     shard = parallel.shard_solver(bodies, man, cuts, rank, world)
     acuts = parallel.slab_cuts(aabbs.aabb_min[:, 0], world)
     ashard = parallel.shard_aabbs(aabbs, acuts, rank)
+    bench.pin_columns(ctx, shard.bodies)                     # the share lives in pinned host memory, like bench.py's columns
+    if shard.manifolds is not None:
+        bench.pin_columns(ctx, shard.manifolds)
+    bench.pin_columns(ctx, ashard.aabbs)
     engine = parallel.GpuSlabEngine(ctx)
     gather = parallel.dist_gather if world > 1 else (lambda e, t: None)
     if world == 1:
@@ -78,13 +82,15 @@ def main():
 
     # ---- end-to-end arm: every rank's host feeds its own slab: H2D of the share, launches + exchanges, D2H of the share's results
     #      (pairs whose first interval the slab owns; owned bodies; owned constraints' impulses).  No gather of results.
-    b, m = bodies.copy(), man.copy()
+    b0 = {k: getattr(shard.bodies, k).copy() for k in parallel.BODY_OUTPUTS}
     pairs_out = api.PairList.empty(max(1 << 20, 4 * int(ashard.index.size)))
     sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.broadphase_upload(ashard.aabbs); ctx.broadphase_run(); ctx.broadphase_download(pairs_out)
-        parallel.slab_solver_step(engine, prm, b, m, info, device=dev, shard=shard, gather_results=False)
+        for k, v in b0.items():
+            getattr(shard.bodies, k)[...] = v               # every step starts from the same snapshot
+        parallel.slab_solver_step(engine, prm, None, None, info, device=dev, shard=shard, gather_results=None)
     sync()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     dev_ms, e2e_ms = parallel.reduce_max([dev_ms, e2e_ms], info, dev)
