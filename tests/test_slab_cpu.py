@@ -132,3 +132,31 @@ def test_two_rank_gloo_all_gather_gives_every_rank_the_full_list():
         for c in parallel.PAIR_COLUMNS:
             assert np.array_equal(cols[c], getattr(want, c)[:want.count]), (rank, c)
         assert np.array_equal(order, a.order_out)
+
+
+@pytest.mark.parametrize("world", [2, 4, 7])
+def test_several_far_reaching_intervals_owned_by_different_slabs(world):
+    """Walls that start in different slabs and reach over several cuts, overlapping each other and the ground: every one is swept
+    piecewise, wide-wide pairs included, and the merge still reproduces the single list."""
+    a = random_aabbs(900, seed=40 + world, existing_frac=0.2)
+    n = a.collider.shape[0]
+    xs = np.sort(a.aabb_min[:, 0])
+    rng = np.random.default_rng(world)
+    walls = rng.choice(np.arange(1, n), size=6, replace=False)
+    for k, w in enumerate(walls):
+        start = xs[(k * n) // 7]
+        a.aabb_min[w] = (start, -1.0, -1.0)
+        a.aabb_max[w] = (start + rng.uniform(6, 14), 13.0, 13.0 if k % 2 else 2.0)
+        a.flags[w] = api.AABB_GENERATE_CONSTRAINTS
+    a.existing_pairs = None
+    want = oracle_lib.broadphase(a)
+    want_order = a.order_out.copy()
+    cuts = parallel.slab_cuts(a.aabb_min[:, 0], world)
+    slab = parallel.slab_of(a.aabb_min[:, 0], cuts)
+    wide = parallel.wide_intervals(a, cuts, slab)
+    assert wide.sum() >= 3 and np.unique(slab[wide]).size >= min(2, world - 1)          # far-reaching intervals with different owners
+    parts = [parallel.slab_broadphase_local(oracle_lib.broadphase, a, cuts, r) for r in range(world)]
+    assert sum(p[2] for p in parts) > 0
+    got, order = parallel.merge_slab_results(parts, a.collider)
+    assert_same_pairs(got, want)
+    assert np.array_equal(order, want_order)
