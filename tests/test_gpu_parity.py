@@ -328,3 +328,17 @@ def test_manifold_csr_is_validated(gpu_ctx):
     with pytest.raises(api.AvianError):
         gpu_ctx.solver_step(prm, b.copy(), decreasing)
     gpu_ctx.solver_step(prm, b.copy(), m.copy())   # the context stays usable after a rejected upload
+
+
+def test_cubes_simulation_is_locally_deterministic_on_gpu(gpu_ctx):
+    """src/tests/mod.rs:149-183 on the device: the 4x4x4 cubes scene stepped twice through the GPU plugins gives identical transforms
+    (the wavefront schedule orders every body's events, so the result does not depend on warp timing)."""
+    def run():
+        w = plugins.World(scenes.cubes_example(4), plugins.PhysicsPlugins(gpu_ctx), substeps=6)
+        for _ in range(90):
+            w.step()
+        return w.bodies.position.copy(), w.bodies.rotation.copy(), w.bodies.linear_velocity.copy()
+    a, b = run(), run()
+    assert a[0][1:, 1].min() > -1.0                       # nothing fell through the ground
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

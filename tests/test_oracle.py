@@ -196,3 +196,31 @@ def test_spherical_chain_hangs():
     assert np.allclose(gaps, gaps[0], atol=5e-3)       # links keep their spacing
     assert np.allclose(p[0], 0.0)                      # the kinematic anchor does not move
     assert np.isfinite(p).all()
+
+
+def test_body_with_velocity_moves_reference_test():
+    """src/tests/mod.rs:103-147: a sphere (r = 0.5, density 1) moving at 1 m/s in x without gravity, 500 updates at 60 Hz:
+    y = z = 0 exactly, x = 500/60 within 0.03."""
+    b = _one_body(angvel=(0, 0, 0), inv_inertia=(19.098593, 0, 0, 19.098593, 0, 19.098593))   # 1 / (2/5 m r^2), m = 4/3 pi r^3
+    b.inverse_mass[:] = 1.0 / (4.0 / 3.0 * np.pi * 0.125)
+    b.linear_velocity[:] = (1.0, 0.0, 0.0)
+    prm = api.default_step_params(dt=1.0 / 60.0, substeps=6, gravity=(0, 0, 0))
+    for _ in range(500):
+        oracle_lib.solver_step(prm, b)
+    assert b.position[0, 1] == 0.0 and b.position[0, 2] == 0.0
+    assert abs(b.position[0, 0] - 500.0 / 60.0) < 0.03
+
+
+def test_cubes_simulation_is_locally_deterministic_reference_test():
+    """src/tests/mod.rs:149-183: the 4x4x4 cubes scene run several times gives identical transforms (5 s in the reference; 1.5 s here:
+    the cubes have landed and are in contact).  Restated for the oracle with a different thread count per run, which is the way
+    the reference's run-to-run scheduling differs."""
+    def run(threads):
+        w = oracle_world(scenes.cubes_example(4), substeps=6, threads=threads)
+        for _ in range(90):
+            w.step()
+        return w.bodies.position.copy(), w.bodies.rotation.copy()
+    runs = [run(t) for t in (1, 3, 8, 3)]
+    assert np.abs(runs[0][0][1:, 1]).max() < 12.0 and runs[0][0][1:, 1].min() > -1.0      # the pile is on the ground, nothing fell through
+    for p, q in runs[1:]:
+        assert np.array_equal(p, runs[0][0]) and np.array_equal(q, runs[0][1])
