@@ -165,3 +165,20 @@ def test_two_rank_gloo_equals_the_lockstep_run():
             assert np.array_equal(bodies[k], getattr(b, k)), (rank, k)
         for k in parallel.POINT_OUTPUTS:
             assert np.array_equal(points[k], getattr(m, k)), (rank, k)
+
+
+def test_empty_slab_and_constraint_free_rank():
+    """Cuts that leave a slab without bodies (nothing between the two piles) and more slabs than piles: the empty ranks go through the
+    same launch sequence with nothing to do, and the result is still the unpartitioned one bit for bit."""
+    prm, b, m = two_piles_input()
+    bo, mo = b.copy(), m.copy()
+    oracle_lib.solver_step(prm, bo, mo)
+    bs, ms = b.copy(), m.copy()
+    cuts = np.array([10.0, 20.0, 100.0], dtype=np.float32)      # slabs: pile 1 | empty | pile 2 | empty
+    shards = parallel.slab_solver_step_local(lambda r: oracle_lib.OracleSlabEngine(), prm, bs, ms, 4, cuts)
+    assert [sh.bodies.count for sh in shards][1] == 0 and shards[3].bodies.count == 0
+    assert shards[1].manifolds is None and shards[0].slot_count == 0
+    for k in parallel.BODY_OUTPUTS:
+        assert np.array_equal(getattr(bs, k), getattr(bo, k)), k
+    for k in parallel.POINT_OUTPUTS:
+        assert np.array_equal(getattr(ms, k), getattr(mo, k)), k
