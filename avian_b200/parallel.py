@@ -484,3 +484,226 @@ def slab_solver_step(engine, prm, bodies, manifolds, info: RankInfo, cuts: np.nd
             for r in range(info.world):
                 glob[all_pts[r]] = parts[r].reshape(-1, width) if glob.ndim > 1 else parts[r]
     return sh
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# island sharding of ONE scene: exact, no collective in the data path
+# ---------------------------------------------------------------------------------------------------------------------------
+# Constraints only carry data between DYNAMIC bodies (static and kinematic bodies are never written by a constraint: dominance,
+# solver/contact/mod.rs:129-154), so the connected components of the graph "dynamic bodies joined by contacts and joints" never
+# exchange anything within a step.  Restricting the colour-major manifold list and the typed joint arrays to one component keeps the
+# relative order of its constraints, which is all the Gauss-Seidel result of that component depends on: solving the components on
+# different GPUs reproduces the single-GPU step bit for bit (tests/test_island_cpu.py, tests/test_gpu_multi.py).
+@dataclass
+class IslandShard:
+    bodies: object
+    manifolds: object            # api.Manifolds or None
+    joints: object               # api.JointSet or None
+    body_index: np.ndarray       # local body -> global body
+    owned_body: np.ndarray       # bool per local body: results are taken from this rank
+    manifold_index: np.ndarray
+    point_index: np.ndarray
+    joint_index: dict            # joint type -> local joint -> global joint of that type
+
+
+def find_islands(bodies, manifolds=None, joints=None):
+    """labels[B]: island id of every dynamic body (numbered by their smallest body index), -1 for static / kinematic bodies."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from avian_b200 import api
+    B = bodies.count
+    dyn = bodies.kind == api.BODY_DYNAMIC
+    src, dst = [], []
+
+    def add(b1, b2):
+        b1, b2 = np.asarray(b1, dtype=np.int64), np.asarray(b2, dtype=np.int64)
+        ok = (b1 >= 0) & (b2 >= 0)
+        ok &= dyn[np.maximum(b1, 0)] & dyn[np.maximum(b2, 0)]
+        src.append(b1[ok]); dst.append(b2[ok])
+
+    if manifolds is not None and manifolds.count:
+        add(manifolds.body1, manifolds.body2)
+    if joints is not None:
+        for j in joints.types.values():
+            if j.count:
+                add(j.body1, j.body2)
+    s = np.concatenate(src) if src else np.zeros(0, dtype=np.int64)
+    d = np.concatenate(dst) if dst else np.zeros(0, dtype=np.int64)
+    n, comp = connected_components(coo_matrix((np.ones(s.size, dtype=np.int8), (s, d)), shape=(B, B)), directed=False)
+    labels = np.full(B, -1, dtype=np.int64)
+    idx = np.nonzero(dyn)[0]
+    # renumber by first appearance so that the numbering does not depend on the component search
+    _, first = np.unique(comp[idx], return_index=True)
+    order = np.argsort(first, kind="stable")
+    remap = np.empty(order.size, dtype=np.int64)
+    remap[order] = np.arange(order.size)
+    uniq = np.unique(comp[idx])
+    labels[idx] = remap[np.searchsorted(uniq, comp[idx])]
+    return labels, int(order.size)
+
+
+def assign_islands(labels: np.ndarray, weights: np.ndarray, world: int) -> np.ndarray:
+    """rank of every island: heaviest first onto the least loaded rank (ties: lower island id, lower rank) — deterministic."""
+    n = int(labels.max()) + 1 if labels.size and labels.max() >= 0 else 0
+    w = np.bincount(labels[labels >= 0], weights=weights[labels >= 0], minlength=n) if n else np.zeros(0)
+    rank_of = np.zeros(n, dtype=np.int64)
+    load = np.zeros(world)
+    for isl in np.lexsort((np.arange(n), -w)):
+        r = int(np.argmin(load))
+        rank_of[isl] = r
+        load[r] += w[isl] + 1.0
+    return rank_of
+
+
+def shard_by_island(bodies, manifolds, joints, world: int, rank: int, labels: np.ndarray | None = None) -> IslandShard:
+    from avian_b200 import api
+    B = bodies.count
+    if labels is None:
+        labels, _ = find_islands(bodies, manifolds, joints)
+    M = 0 if manifolds is None else manifolds.count
+    # weight of a body = the constraints it carries (the solver's work), so that the ranks get similar loads
+    weight = np.ones(B)
+    cons = []   # (b1, b2) index arrays of every constraint list, manifolds first then joints by type
+    if M:
+        cons.append(("m", None, manifolds.body1.astype(np.int64), manifolds.body2.astype(np.int64)))
+    if joints is not None:
+        for t in sorted(joints.types):
+            j = joints.types[t]
+            if j.count:
+                cons.append(("j", t, j.body1.astype(np.int64), j.body2.astype(np.int64)))
+    for _, _, b1, b2 in cons:
+        for b in (b1, b2):
+            np.add.at(weight, b[b >= 0], 1.0)
+    rank_of_island = assign_islands(labels, weight, world)
+    body_rank = np.where(labels >= 0, rank_of_island[np.maximum(labels, 0)] if rank_of_island.size else 0, -1)
+
+    def owner(b1, b2):   # rank of a constraint: the island of its dynamic body; none dynamic (never solved) -> rank 0
+        r1 = np.where(b1 >= 0, body_rank[np.maximum(b1, 0)], -1)
+        r2 = np.where(b2 >= 0, body_rank[np.maximum(b2, 0)], -1)
+        r = np.where(r1 >= 0, r1, r2)
+        return np.where(r >= 0, r, 0)
+
+    local = body_rank == rank
+    picks = {}
+    for kind, t, b1, b2 in cons:
+        mine = np.nonzero(owner(b1, b2) == rank)[0]
+        picks[(kind, t)] = mine
+        for b in (b1[mine], b2[mine]):
+            local[b[b >= 0]] = True
+    # non-dynamic bodies nobody references still have to be stepped by someone (kinematic motion): rank 0
+    if rank == 0:
+        ref = np.zeros(B, dtype=bool)
+        for _, _, b1, b2 in cons:
+            for b in (b1, b2):
+                ref[b[b >= 0]] = True
+        local |= (labels < 0) & ~ref
+    body_index = np.nonzero(local)[0]
+    to_local = np.full(B, -1, dtype=np.int32)
+    to_local[body_index] = np.arange(body_index.size, dtype=np.int32)
+    owned = body_rank[body_index] == rank
+    if rank == 0:
+        owned |= labels[body_index] < 0          # replicated non-dynamic bodies: every holder computes the same motion, rank 0 reports it
+    lb = api.Bodies(**_take(bodies, body_index))
+    remap = lambda g: np.where(g >= 0, to_local[np.maximum(g, 0)], g).astype(np.int32)
+    lm, point_index, manifold_index = None, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    mine = picks.get(("m", None))
+    if mine is not None and mine.size:
+        manifold_index = mine
+        po = manifolds.point_offsets.astype(np.int64)
+        n = po[mine + 1] - po[mine]
+        new_po = np.concatenate([[0], np.cumsum(n)])
+        point_index = np.repeat(po[mine] - new_po[:-1], n) + np.arange(new_po[-1])
+        per_m = ("normal", "friction", "restitution", "tangent_velocity")
+        per_p = ("anchor1", "anchor2", "penetration", "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")
+        cols = {k: (None if getattr(manifolds, k) is None else np.ascontiguousarray(getattr(manifolds, k)[mine])) for k in per_m}
+        cols.update({k: np.ascontiguousarray(getattr(manifolds, k)[point_index]) for k in per_p})
+        cols["body1"], cols["body2"] = remap(manifolds.body1[mine]), remap(manifolds.body2[mine])
+        cols["point_offsets"] = new_po.astype(np.uint32)
+        cols["color_offsets"] = np.searchsorted(mine, np.asarray(manifolds.color_offsets, dtype=np.int64), side="left").astype(np.uint32)
+        lm = api.Manifolds(**cols)
+    lj, joint_index = None, {}
+    if joints is not None:
+        types = {}
+        for t in sorted(joints.types):
+            mine_j = picks.get(("j", t))
+            if mine_j is None or mine_j.size == 0:
+                continue
+            j = joints.types[t]
+            cols = _take(j, mine_j)
+            cols["body1"], cols["body2"] = remap(j.body1[mine_j]), remap(j.body2[mine_j])
+            types[t] = api.Joints(**cols)
+            joint_index[t] = mine_j
+        if types:
+            lj = api.JointSet(types)
+    return IslandShard(lb, lm, lj, body_index, owned, manifold_index, point_index, joint_index)
+
+
+JOINT_OUTPUTS = ("force", "torque")
+
+
+def scatter_island_results(bodies, manifolds, joints, shard: IslandShard) -> None:
+    rows = shard.body_index[shard.owned_body]
+    for k in BODY_OUTPUTS:
+        getattr(bodies, k)[rows] = getattr(shard.bodies, k)[shard.owned_body]
+    if shard.manifolds is not None:
+        for k in POINT_OUTPUTS:
+            getattr(manifolds, k)[shard.point_index] = getattr(shard.manifolds, k)
+    if shard.joints is not None:
+        for t, idx in shard.joint_index.items():
+            for k in JOINT_OUTPUTS:
+                dst, src = getattr(joints.types[t], k), getattr(shard.joints.types[t], k)
+                if dst is not None and src is not None:
+                    dst[idx] = src
+
+
+def island_solver_step_local(solver_step, prm, bodies, manifolds, joints, world: int):
+    """Every rank's share solved one after the other in this process (tests, single-GPU dry runs): solver_step(prm, bodies,
+    manifolds, joints) is the engine (Context.solver_step).  Results are written back into the global columns."""
+    labels, _ = find_islands(bodies, manifolds, joints)
+    shards = [shard_by_island(bodies, manifolds, joints, world, r, labels) for r in range(world)]
+    for sh in shards:
+        if sh.bodies.count:
+            solver_step(prm, sh.bodies, sh.manifolds, sh.joints)
+    for sh in shards:
+        scatter_island_results(bodies, manifolds, joints, sh)
+    return shards
+
+
+def island_solver_step(solver_step, prm, bodies, manifolds, joints, info: RankInfo, device: str = "cpu", gather_results: bool = True) -> IslandShard:
+    """One rank of the island-sharded stage: no collective while solving; with gather_results one all-gather of the owned rows at
+    the end so that every rank holds the full result."""
+    labels, _ = find_islands(bodies, manifolds, joints)
+    sh = shard_by_island(bodies, manifolds, joints, info.world, info.rank, labels)
+    if sh.bodies.count:
+        solver_step(prm, sh.bodies, sh.manifolds, sh.joints)
+    scatter_island_results(bodies, manifolds, joints, sh)
+    if not gather_results or info.world == 1:
+        return sh
+    rows = sh.body_index[sh.owned_body].astype(np.int64)
+    all_rows = allgather_ragged(rows, info, device)
+    for k in BODY_OUTPUTS:
+        col = getattr(sh.bodies, k)[sh.owned_body]
+        parts = allgather_ragged(np.ascontiguousarray(col).reshape(-1), info, device)
+        for r in range(info.world):
+            getattr(bodies, k)[all_rows[r]] = parts[r].reshape(-1, col.shape[1]) if col.ndim > 1 else parts[r]
+    if manifolds is not None and manifolds.count:
+        all_pts = allgather_ragged(sh.point_index.astype(np.int64), info, device)
+        for k in POINT_OUTPUTS:
+            glob = getattr(manifolds, k)
+            col = getattr(sh.manifolds, k) if sh.manifolds is not None else glob[:0]
+            parts = allgather_ragged(np.ascontiguousarray(col).reshape(-1), info, device)
+            for r in range(info.world):
+                glob[all_pts[r]] = parts[r].reshape(-1, glob.shape[1]) if glob.ndim > 1 else parts[r]
+    if joints is not None:
+        for t in sorted(joints.types):
+            idx = sh.joint_index.get(t, np.zeros(0, dtype=np.int64)).astype(np.int64)
+            all_idx = allgather_ragged(idx, info, device)
+            for k in JOINT_OUTPUTS:
+                glob = getattr(joints.types[t], k)
+                if glob is None:
+                    continue
+                col = getattr(sh.joints.types[t], k) if (sh.joints is not None and t in sh.joints.types) else glob[:0]
+                parts = allgather_ragged(np.ascontiguousarray(col).reshape(-1), info, device)
+                for r in range(info.world):
+                    glob[all_idx[r]] = parts[r].reshape(-1, glob.shape[1]) if glob.ndim > 1 else parts[r]
+    return sh

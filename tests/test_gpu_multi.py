@@ -195,3 +195,17 @@ def test_two_gpu_nccl_slab_solver():
             assert rel_err(bodies[k], getattr(b, k)) <= RTOL, (rank, k)
     for k in parallel.BODY_OUTPUTS:      # both ranks hold the same bits
         assert np.array_equal(results[0][1][k], results[1][1][k]), k
+
+
+# ---- island sharding of one scene: exact ------------------------------------------------------------------------------------
+def test_island_sharded_step_on_device_is_bit_identical(gpu_ctx):
+    """the ragdoll field dealt island by island to 3 ranks' worth of avn_solver_step calls (one after the other on this
+    device) is the single call bit for bit — contacts, joints, joint forces."""
+    from test_island_cpu import assert_same_step, ragdoll_input
+    prm, b, m, j = ragdoll_input()
+    bs, ms, js = b.copy(), m.copy(), j.copy()
+    gpu_ctx.solver_step(prm, bs, ms, js)
+    bg, mg, jg = b.copy(), m.copy(), j.copy()
+    shards = parallel.island_solver_step_local(gpu_ctx.solver_step, prm, bg, mg, jg, 3)
+    assert min(sh.bodies.count for sh in shards) > 17
+    assert_same_step(bg, mg, jg, bs, ms, js)
