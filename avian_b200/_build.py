@@ -60,7 +60,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
 def build_host(force: bool = False) -> Path:
     src = ROOT / "host"
-    deps = [p for p in src.glob("*.[ch]pp")] + [REPO / "include" / "avian_b200.h"]
+    deps = [p for p in src.glob("*.[ch]pp")] + [REPO / "include" / "avian_b200.h", ROOT / "csrc" / "narrow_math.hpp"]
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
     cxx = os.environ.get("CXX") or shutil.which("g++")

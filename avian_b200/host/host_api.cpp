@@ -18,26 +18,12 @@
 #include <vector>
 
 #include "../../include/avian_b200.h"
+#include "../csrc/narrow_math.hpp"
 
 namespace {
 
-using S = double;  // fixture geometry is evaluated in double and rounded to the column scalar type on export
+using namespace nm;  // S = double, V3, Q, M3, Box, Contacts: the manifold geometry shared with the device (csrc/narrow_math.hpp)
 
-struct V3 { S x, y, z; };
-inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
-inline V3 operator*(V3 a, S s) { return {a.x * s, a.y * s, a.z * s}; }
-inline S dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-inline S len(V3 a) { return std::sqrt(dot(a, a)); }
-inline S comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
-struct Q { S x, y, z, w; };
-inline V3 rot(Q q, V3 v) {
-    V3 b{q.x, q.y, q.z};
-    S b2 = dot(b, b);
-    return v * (q.w * q.w - b2) + b * (dot(v, b) * 2) + cross(b, v) * (q.w * 2);
-}
 inline Q qmul(Q a, Q b) {
     return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
             a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
@@ -48,9 +34,6 @@ inline Q q_from_scaled_axis(V3 v) {
     S s = std::sin(l * 0.5) / l;
     return {v.x * s, v.y * s, v.z * s, std::cos(l * 0.5)};
 }
-struct M3 { V3 c[3]; };  // columns = world directions of the local axes
-inline M3 to_mat(Q q) { return {{rot(q, {1, 0, 0}), rot(q, {0, 1, 0}), rot(q, {0, 0, 1})}}; }
-
 template <class T> struct ColR {  // typed reader over a void* column of float or double
     const void* p; bool f64;
     S at(size_t i) const { return f64 ? static_cast<const double*>(p)[i] : S(static_cast<const float*>(p)[i]); }
@@ -64,7 +47,6 @@ struct ColW {
     void set3(size_t i, V3 v) const { set(3 * i, v.x); set(3 * i + 1, v.y); set(3 * i + 2, v.z); }
 };
 
-enum ShapeType { SHAPE_CUBOID = 0, SHAPE_SPHERE = 1 };
 struct Shape { int type; V3 he; S friction, restitution; };
 
 struct Point {
@@ -151,176 +133,6 @@ void pop_manifold(Pipeline& P, uint32_t id) {
         auto mh = c.handles[h.local];
         P.pairs[mh.first].handles[mh.second].local = h.local;
     }
-}
-
-// ---- manifold generation (fixture) -----------------------------------------------------------------------------
-struct Box { V3 c; M3 r; V3 he; };
-
-// support face of `b` most aligned with direction d: returns 4 corners (world) and the face normal
-void box_face(const Box& b, int axis, S sign, V3 out[4]) {
-    int u = (axis + 1) % 3, v = (axis + 2) % 3;
-    V3 n = b.r.c[axis] * (sign * comp(b.he, axis));
-    V3 eu = b.r.c[u] * comp(b.he, u), ev = b.r.c[v] * comp(b.he, v);
-    V3 fc = b.c + n;
-    out[0] = fc + eu + ev; out[1] = fc - eu + ev; out[2] = fc - eu - ev; out[3] = fc + eu - ev;
-}
-
-int clip_poly(const V3* in, int n, V3 plane_n, S plane_d, V3* out) {  // keep dot(n,p) <= d
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
-        V3 a = in[i], b = in[(i + 1) % n];
-        S da = dot(plane_n, a) - plane_d, db = dot(plane_n, b) - plane_d;
-        if (da <= 0) out[m++] = a;
-        if ((da < 0 && db > 0) || (da > 0 && db < 0)) out[m++] = a + (b - a) * (da / (da - db));
-    }
-    return m;
-}
-
-// returns false when the boxes are farther apart than max_dist. normal points from A to B.
-bool box_box(const Box& A, const Box& B, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts /* (on A, on B) */) {
-    pts.clear();
-    V3 d = B.c - A.c;
-    S best_sep = -1e300;
-    int best_kind = -1, best_i = 0, best_j = 0;
-    V3 best_n{0, 1, 0};
-    auto radius = [](const Box& b, V3 n) {
-        return std::fabs(dot(b.r.c[0], n)) * b.he.x + std::fabs(dot(b.r.c[1], n)) * b.he.y + std::fabs(dot(b.r.c[2], n)) * b.he.z;
-    };
-    auto consider = [&](V3 n, int kind, int i, int j, S bias) {
-        S l = len(n);
-        if (l < 1e-9) return;
-        n = n * (1 / l);
-        if (dot(n, d) < 0) n = -n;
-        S sep = dot(n, d) - radius(A, n) - radius(B, n);
-        // face axes are preferred over edge axes by a small bias, earlier axes win ties: stable feature choice
-        if (sep - bias > best_sep + 1e-9) { best_sep = sep - bias; best_kind = kind; best_i = i; best_j = j; best_n = n; }
-    };
-    for (int i = 0; i < 3; ++i) consider(A.r.c[i], 0, i, 0, 0);
-    for (int i = 0; i < 3; ++i) consider(B.r.c[i], 1, i, 0, 0);
-    S face_sep = best_sep;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) consider(cross(A.r.c[i], B.r.c[j]), 2, i, j, 1e-4);
-    (void)face_sep;
-    S sep = best_kind == 2 ? best_sep + 1e-4 : best_sep;
-    if (sep > max_dist) return false;
-    normal = best_n;
-    if (best_kind == 2) {
-        // edge-edge: closest points of the two supporting edges
-        V3 ea = A.r.c[best_i], eb = B.r.c[best_j];
-        V3 pa = A.c, pb = B.c;
-        for (int k = 0; k < 3; ++k) {
-            if (k != best_i) pa = pa + A.r.c[k] * (comp(A.he, k) * (dot(A.r.c[k], normal) > 0 ? 1 : -1));
-            if (k != best_j) pb = pb + B.r.c[k] * (comp(B.he, k) * (dot(B.r.c[k], normal) < 0 ? 1 : -1));
-        }
-        V3 r = pa - pb;
-        S a = dot(ea, ea), e = dot(eb, eb), f = dot(eb, r), c = dot(ea, r), b = dot(ea, eb);
-        S den = a * e - b * b;
-        S s = den > 1e-12 ? (b * f - c * e) / den : 0;
-        S t = (b * s + f) / e;
-        S ha = comp(A.he, best_i), hb = comp(B.he, best_j);
-        s = std::max(-ha, std::min(ha, s));
-        t = std::max(-hb, std::min(hb, t));
-        pts.push_back({pa + ea * s, pb + eb * t});
-        return true;
-    }
-    // face contact: reference box R (face axis), incident box I
-    const bool ref_is_a = best_kind == 0;
-    const Box& R = ref_is_a ? A : B;
-    const Box& I = ref_is_a ? B : A;
-    V3 rn = ref_is_a ? normal : -normal;  // outward normal of the reference face
-    S rsign = dot(R.r.c[best_i], rn) > 0 ? 1 : -1;
-    // incident face: the face of I most anti-parallel to rn
-    int inc_axis = 0;
-    S inc_best = -1;
-    for (int k = 0; k < 3; ++k) {
-        S v = std::fabs(dot(I.r.c[k], rn));
-        if (v > inc_best) { inc_best = v; inc_axis = k; }
-    }
-    S isign = dot(I.r.c[inc_axis], rn) > 0 ? -1 : 1;
-    V3 poly[16], tmp[16];
-    box_face(I, inc_axis, isign, poly);
-    int np = 4;
-    int u = (best_i + 1) % 3, v = (best_i + 2) % 3;
-    const int axes[2] = {u, v};
-    for (int a = 0; a < 2 && np > 0; ++a) {
-        V3 sn = R.r.c[axes[a]];
-        S he = comp(R.he, axes[a]);
-        np = clip_poly(poly, np, sn, dot(sn, R.c) + he, tmp);
-        np = clip_poly(tmp, np, -sn, -dot(sn, R.c) + he, poly);
-    }
-    S face_d = dot(rn, R.c) + comp(R.he, best_i) * 1.0;
-    (void)rsign;
-    for (int k = 0; k < np; ++k) {
-        S dist = dot(rn, poly[k]) - face_d;  // signed distance of the incident point above the reference face
-        if (dist > max_dist) continue;
-        V3 on_ref = poly[k] - rn * dist;
-        // drop near-duplicates
-        bool dup = false;
-        for (auto& q : pts) {
-            V3 e = (ref_is_a ? q.second : q.first) - poly[k];
-            if (dot(e, e) < 1e-12) { dup = true; break; }
-        }
-        if (dup) continue;
-        if (ref_is_a) pts.push_back({on_ref, poly[k]}); else pts.push_back({poly[k], on_ref});
-    }
-    return !pts.empty();
-}
-
-// keep at most 4 points: deepest, farthest from it, farthest from that segment on each side (cf. prune_points,
-// contact_types/mod.rs:478-566, itself after Jolt's PruneContactPoints)
-void prune4(std::vector<std::pair<V3, V3>>& pts, V3 n) {
-    if (pts.size() <= 4) return;
-    auto depth = [&](size_t i) { return dot(pts[i].first - pts[i].second, n); };
-    size_t p0 = 0;
-    for (size_t i = 1; i < pts.size(); ++i) if (depth(i) > depth(p0) + 1e-12) p0 = i;
-    size_t p1 = p0;
-    S best = -1;
-    for (size_t i = 0; i < pts.size(); ++i) { V3 e = pts[i].first - pts[p0].first; S v = dot(e, e); if (v > best) { best = v; p1 = i; } }
-    V3 dir = cross(pts[p1].first - pts[p0].first, n);
-    size_t p2 = p0, p3 = p0;
-    S mx = 0, mn = 0;
-    for (size_t i = 0; i < pts.size(); ++i) {
-        S v = dot(pts[i].first - pts[p0].first, dir);
-        if (v > mx) { mx = v; p2 = i; }
-        if (v < mn) { mn = v; p3 = i; }
-    }
-    std::vector<size_t> keep{p0};
-    for (size_t c : {p1, p2, p3}) if (std::find(keep.begin(), keep.end(), c) == keep.end()) keep.push_back(c);
-    std::sort(keep.begin(), keep.end());
-    std::vector<std::pair<V3, V3>> out;
-    for (size_t k : keep) out.push_back(pts[k]);
-    pts.swap(out);
-}
-
-bool sphere_sphere(V3 ca, S ra, V3 cb, S rb, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts) {
-    pts.clear();
-    V3 d = cb - ca;
-    S l = len(d);
-    if (l - ra - rb > max_dist) return false;
-    normal = l > 1e-12 ? d * (1 / l) : V3{0, 1, 0};
-    pts.push_back({ca + normal * ra, cb - normal * rb});
-    return true;
-}
-bool box_sphere(const Box& A, V3 cs, S rs, S max_dist, V3& normal, std::vector<std::pair<V3, V3>>& pts) {  // normal from box to sphere
-    pts.clear();
-    V3 d = cs - A.c;
-    V3 local{dot(d, A.r.c[0]), dot(d, A.r.c[1]), dot(d, A.r.c[2])};
-    V3 cl{std::max(-A.he.x, std::min(A.he.x, local.x)), std::max(-A.he.y, std::min(A.he.y, local.y)), std::max(-A.he.z, std::min(A.he.z, local.z))};
-    V3 on_box = A.c + A.r.c[0] * cl.x + A.r.c[1] * cl.y + A.r.c[2] * cl.z;
-    V3 e = cs - on_box;
-    S l = len(e);
-    if (l > 1e-9) {
-        if (l - rs > max_dist) return false;
-        normal = e * (1 / l);
-    } else {  // centre inside the box: push out through the nearest face
-        int ax = 0; S best = 1e300;
-        for (int k = 0; k < 3; ++k) { S v = comp(A.he, k) - std::fabs(comp(local, k)); if (v < best) { best = v; ax = k; } }
-        S sgn = comp(local, ax) >= 0 ? 1 : -1;
-        normal = A.r.c[ax] * sgn;
-        on_box = cs + normal * best;
-    }
-    pts.push_back({on_box, cs - normal * rs});
-    return true;
 }
 
 }  // namespace
@@ -434,7 +246,7 @@ uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* k
     std::vector<uint32_t> changed;  // contact ids whose status changed
     std::vector<uint8_t> disjoint(P.pairs.size(), 0), started(P.pairs.size(), 0), stopped(P.pairs.size(), 0);
     std::vector<int> count_change(P.pairs.size(), 0);
-    std::vector<std::pair<V3, V3>> pts;
+    Contacts pts;
     for (uint32_t id : P.active) {
         Pair& pr = P.pairs[id];
         const uint32_t a = pr.collider1, b = pr.collider2;
@@ -452,38 +264,24 @@ uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* k
         std::vector<Manifold> old = std::move(pr.manifolds);
         pr.manifolds.clear();
         V3 normal;
-        bool hit = false;
         V3 pa = pos.v3(a), pb = pos.v3(b);
-        if (sa.type == SHAPE_CUBOID && sb.type == SHAPE_CUBOID) {
-            Box A{pa, to_mat(rt.q(a)), sa.he}, B{pb, to_mat(rt.q(b)), sb.he};
-            hit = box_box(A, B, max_dist, normal, pts);
-            if (hit) prune4(pts, normal);
-        } else if (sa.type == SHAPE_SPHERE && sb.type == SHAPE_SPHERE) {
-            hit = sphere_sphere(pa, sa.he.x, pb, sb.he.x, max_dist, normal, pts);
-        } else if (sa.type == SHAPE_CUBOID) {
-            Box A{pa, to_mat(rt.q(a)), sa.he};
-            hit = box_sphere(A, pb, sb.he.x, max_dist, normal, pts);
-        } else {
-            Box B{pb, to_mat(rt.q(b)), sb.he};
-            hit = box_sphere(B, pa, sa.he.x, max_dist, normal, pts);
-            if (hit) { normal = -normal; for (auto& q : pts) std::swap(q.first, q.second); }
-        }
+        const bool hit = collide(sa.type, sa.he, pa, rt.q(a), sb.type, sb.he, pb, rt.q(b), max_dist, normal, pts);
         if (hit) {
-            Manifold m;
-            m.normal = normal;
-            for (auto& q : pts) {
-                Point pt;
-                pt.anchor1 = q.first - pa;   // collider at the body origin, centre of mass at the origin
-                pt.anchor2 = q.second - pb;
-                pt.penetration = dot(q.first - q.second, normal);
-                V3 rv = rel + cross(w2, pt.anchor2) - cross(w1, pt.anchor1);
-                pt.normal_speed = dot(rv, normal);
-                // keep rule of system_param.rs:748-756
-                bool keep = -pt.penetration < eff_margin || (pt.normal_speed * dt - pt.penetration < eff_margin);
-                if (!keep) continue;
-                m.pts.push_back(pt);
+            PointOut out[4];
+            const int np = manifold_points(pts, normal, pa, pb, rel, w1, w2, dt, eff_margin, out);
+            if (np > 0) {
+                Manifold m;
+                m.normal = normal;
+                for (int k = 0; k < np; ++k) {
+                    Point pt;
+                    pt.anchor1 = out[k].anchor1;
+                    pt.anchor2 = out[k].anchor2;
+                    pt.penetration = out[k].penetration;
+                    pt.normal_speed = out[k].normal_speed;
+                    m.pts.push_back(pt);
+                }
+                pr.manifolds.push_back(std::move(m));
             }
-            if (!m.pts.empty()) pr.manifolds.push_back(std::move(m));
         }
         bool touching = !pr.manifolds.empty();
         if (touching && match_contacts && pr.manifolds.size() <= 4) {
