@@ -310,6 +310,20 @@ class PairList:
         return PairList(self.collider1[:n], self.collider2[:n], self.body1[:n], self.body2[:n], self.flags[:n], n)
 
 
+class AvnNarrowParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("contact_tolerance", C.c_double)]
+
+
+class AvnNarrowInput(C.Structure):
+    _fields_ = [("pair_count", C.c_uint32), ("collider_count", C.c_uint32), ("body_count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in ("collider1", "collider2", "body1", "body2", "shape", "dims", "position", "rotation", "linear_velocity", "angular_velocity",
+                           "aabb_min", "aabb_max")]
+
+
+class AvnRawManifolds(C.Structure):
+    _fields_ = [(n, _vp) for n in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")]
+
+
 class AvnBoundary(C.Structure):
     _fields_ = [("count", C.c_uint32), ("slot_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
                 ("body", _vp), ("slot", _vp), ("owner_rank", _vp)]
@@ -343,6 +357,7 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "solver_boundary_apply": ([_vp, _vp], C.c_int),
         "solver_needs_restitution": ([_vp, P(C.c_int)], C.c_int),
         "get_stream": ([_vp, P(_vp)], C.c_int),
+        "narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), P(AvnRawManifolds)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -354,7 +369,7 @@ ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
-    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream"]
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 BOUNDARY_RECORD_SCALARS = 16
@@ -554,6 +569,25 @@ class Context:
         out = _vp()
         self._check(self.lib.avn_get_stream(self.handle, C.byref(out)))
         return int(out.value or 0)
+
+    def narrow_phase(self, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray) -> dict:
+        """avn_narrow_phase: pairs = (collider1, collider2, body1, body2) uint32 arrays; colliders = dict(shape, dims, position, rotation,
+        aabb_min=None, aabb_max=None).  Returns the raw manifold columns (4 point slots per pair)."""
+        c1, c2, b1, b2 = (np.ascontiguousarray(x, dtype=np.uint32) for x in pairs)
+        n, dt_ = int(c1.shape[0]), self.scalar
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+        inp = AvnNarrowInput(n, int(cols["position"].shape[0]), int(lv.shape[0]), 0, _ptr(c1), _ptr(c2), _ptr(b1), _ptr(b2), _ptr(cols["shape"]),
+                             _ptr(cols["dims"]), _ptr(cols["position"]), _ptr(cols["rotation"]), _ptr(lv), _ptr(av), _ptr(cols["aabb_min"]),
+                             _ptr(cols["aabb_max"]))
+        out = {"point_count": np.zeros(n, dtype=np.uint8), "disjoint": np.zeros(n, dtype=np.uint8), "normal": np.zeros((n, 3), dtype=dt_),
+               "anchor1": np.zeros((n, 4, 3), dtype=dt_), "anchor2": np.zeros((n, 4, 3), dtype=dt_), "penetration": np.zeros((n, 4), dtype=dt_),
+               "normal_speed": np.zeros((n, 4), dtype=dt_)}
+        raw = AvnRawManifolds(*(_ptr(out[k]) for k in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")))
+        prm = AvnNarrowParams(float(dt), float(contact_tolerance))
+        self._check(self.lib.avn_narrow_phase(self.handle, C.byref(prm), C.byref(inp), C.byref(raw)))
+        return out
 
     def update_aabbs(self, params: "AvnAabbParams", colliders: "Colliders") -> None:
         c = colliders.as_struct()

@@ -13,6 +13,7 @@ struct AvnContext {
     std::unique_ptr<avn::SolverBase> solver;
     std::unique_ptr<avn::BroadphaseBase> broadphase;
     std::unique_ptr<avn::AabbBase> aabbs;
+    std::unique_ptr<avn::NarrowBase> narrow;
     AvnTimings last{};
 };
 
@@ -55,7 +56,8 @@ AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
     ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
     ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
     ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
-    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
+    ctx->narrow.reset(avn::make_narrow(config->scalar_bits, ctx->stream, &ctx->err));
+    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs || !ctx->narrow) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
     *out_ctx = ctx.release();
     return AVN_OK;
 }
@@ -67,6 +69,7 @@ void avn_destroy(AvnContext* ctx) {
     ctx->solver.reset();
     ctx->broadphase.reset();
     ctx->aabbs.reset();
+    ctx->narrow.reset();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -180,6 +183,12 @@ AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColl
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
     return ctx->aabbs->update(params, colliders);
+}
+
+AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->narrow->run(params, input, out);
 }
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {

@@ -80,6 +80,12 @@ struct AabbBase {
 };
 AabbBase* make_aabb_updater(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
 
+struct NarrowBase {
+    virtual ~NarrowBase() {}
+    virtual AvnStatus run(const AvnNarrowParams* prm, const AvnNarrowInput* in, AvnRawManifolds* out) = 0;
+};
+NarrowBase* make_narrow(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
+
 SolverBase* make_solver(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device);
 BroadphaseBase* make_broadphase(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, int device);
 

@@ -34,6 +34,8 @@ def _load():
         lib.avh_narrow_phase.restype = C.c_uint32
         lib.avh_export_manifolds.argtypes = [_vp, C.c_uint32] + [_vp] * 13
         lib.avh_store_impulses.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp]
+        lib.avh_raw_manifolds.argtypes = [C.c_uint32, C.c_uint32] + [_vp] * 12 + [C.c_double, C.c_double] + [_vp] * 7
+        lib.avh_raw_manifolds.restype = None
         lib.avh_pair_count.argtypes = [_vp]
         lib.avh_pair_count.restype = C.c_uint32
         _lib = lib
@@ -42,6 +44,24 @@ def _load():
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+def raw_manifolds(scalar, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray) -> dict:
+    """The geometry stage of the fixture's narrow phase for an explicit pair list (same columns as Context.narrow_phase)."""
+    lib = _load()
+    dt_ = np.dtype(scalar)
+    c1, c2, b1, b2 = (np.ascontiguousarray(x, dtype=np.uint32) for x in pairs)
+    n = int(c1.shape[0])
+    cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+            for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+    lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+    out = {"point_count": np.zeros(n, dtype=np.uint8), "disjoint": np.zeros(n, dtype=np.uint8), "normal": np.zeros((n, 3), dtype=dt_),
+           "anchor1": np.zeros((n, 4, 3), dtype=dt_), "anchor2": np.zeros((n, 4, 3), dtype=dt_), "penetration": np.zeros((n, 4), dtype=dt_),
+           "normal_speed": np.zeros((n, 4), dtype=dt_)}
+    lib.avh_raw_manifolds(32 if dt_ == np.float32 else 64, n, _p(c1), _p(c2), _p(b1), _p(b2), _p(cols["shape"]), _p(cols["dims"]), _p(cols["position"]),
+                          _p(cols["rotation"]), _p(lv), _p(av), _p(cols["aabb_min"]), _p(cols["aabb_max"]), float(dt), float(contact_tolerance),
+                          *(_p(out[k]) for k in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")))
+    return out
 
 
 class HostPipeline:

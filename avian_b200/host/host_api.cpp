@@ -384,6 +384,50 @@ void avh_store_impulses(AvhPipeline* h, uint32_t scalar_bits, const void* ws_nor
     }
 }
 
+// The geometry stage alone for an explicit list of pairs, in the layout of AvnRawManifolds (4 point slots per pair): the CPU side of the
+// device narrow-phase test.  scalar_bits selects the column type; evaluation is in double either way (csrc/narrow_math.hpp).
+void avh_raw_manifolds(uint32_t scalar_bits, uint32_t pair_count, const uint32_t* c1, const uint32_t* c2, const uint32_t* b1, const uint32_t* b2,
+                       const uint8_t* shape, const void* dims, const void* position, const void* rotation, const void* linvel, const void* angvel,
+                       const void* aabb_min, const void* aabb_max, double dt, double tol, uint8_t* point_count, uint8_t* disjoint, void* normal,
+                       void* anchor1, void* anchor2, void* penetration, void* normal_speed) {
+    const bool f64 = scalar_bits == 64;
+    Col dm{dims, f64}, pos{position, f64}, rt{rotation, f64}, lv{linvel, f64}, av{angvel, f64}, amin{aabb_min, f64}, amax{aabb_max, f64};
+    ColW on{normal, f64}, oa1{anchor1, f64}, oa2{anchor2, f64}, op{penetration, f64}, os{normal_speed, f64};
+    for (uint32_t k = 0; k < pair_count; ++k) {
+        const uint32_t a = c1[k], b = c2[k];
+        point_count[k] = 0;
+        on.set3(k, V3{0, 0, 0});
+        for (int p = 0; p < 4; ++p) { oa1.set3(4 * size_t(k) + p, V3{0, 0, 0}); oa2.set3(4 * size_t(k) + p, V3{0, 0, 0}); op.set(4 * size_t(k) + p, 0); os.set(4 * size_t(k) + p, 0); }
+        if (aabb_min) {
+            V3 mina = amin.v3(a), maxa = amax.v3(a), minb = amin.v3(b), maxb = amax.v3(b);
+            bool overlap = !(mina.x > maxb.x || maxa.x < minb.x || mina.y > maxb.y || maxa.y < minb.y || mina.z > maxb.z || maxa.z < minb.z);
+            if (disjoint) disjoint[k] = overlap ? 0 : 1;
+            if (!overlap) continue;
+        } else if (disjoint) {
+            disjoint[k] = 0;
+        }
+        V3 pa = pos.v3(a), pb = pos.v3(b);
+        V3 v1 = lv.v3(b1[k]), v2 = lv.v3(b2[k]), w1 = av.v3(b1[k]), w2 = av.v3(b2[k]);
+        V3 rel = v2 - v1;
+        S eff_margin = dt * len(rel);
+        S max_dist = smax(eff_margin, tol);
+        V3 nrm;
+        Contacts pts;
+        int ta = shape ? shape[a] : SHAPE_CUBOID, tb = shape ? shape[b] : SHAPE_CUBOID;
+        if (!collide(ta, dm.v3(a), pa, rt.q(a), tb, dm.v3(b), pb, rt.q(b), max_dist, nrm, pts)) continue;
+        PointOut out[4];
+        int np = manifold_points(pts, nrm, pa, pb, rel, w1, w2, dt, eff_margin, out);
+        point_count[k] = uint8_t(np);
+        on.set3(k, nrm);
+        for (int p = 0; p < np; ++p) {
+            oa1.set3(4 * size_t(k) + p, out[p].anchor1);
+            oa2.set3(4 * size_t(k) + p, out[p].anchor2);
+            op.set(4 * size_t(k) + p, out[p].penetration);
+            os.set(4 * size_t(k) + p, out[p].normal_speed);
+        }
+    }
+}
+
 uint32_t avh_pair_count(AvhPipeline* h) { return uint32_t(reinterpret_cast<Pipeline*>(h)->active.size()); }
 
 }  // extern "C"

@@ -375,6 +375,43 @@ typedef struct AvnColliderColumns {
  */
 AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColliderColumns* colliders);
 
+/* ---- contact manifolds (SURVEY.md 8f "next #1", geometry stage): one manifold of at most 4 points per contact pair of cuboid / sphere
+ *      colliders.  Stands where NarrowPhase::update calls contact_manifolds (narrow_phase/system_param.rs:437-830,
+ *      collider/parry/contact_query.rs:156-261); the arithmetic is this repository's generator (csrc/narrow_math.hpp — parry3d is not
+ *      vendored), shared with the host fixture.  Matching, the touching state machine and the constraint graph stay on the host. -------- */
+typedef struct AvnNarrowParams {
+    double dt;                         /* Time::delta (narrow_phase/mod.rs:289) */
+    double contact_tolerance;          /* PhysicsLengthUnit * NarrowPhaseConfig::contact_tolerance */
+} AvnNarrowParams;
+
+typedef struct AvnNarrowInput {
+    uint32_t pair_count, collider_count, body_count, _pad;
+    const uint32_t* collider1;         /* [pairs] row of the collider columns below (ascending ContactId order is the caller's business) */
+    const uint32_t* collider2;
+    const uint32_t* body1;             /* [pairs] row of the body velocity columns */
+    const uint32_t* body2;
+    const uint8_t* shape;              /* [C] AvnShape; NULL = cuboid */
+    const void* dims;                  /* [C][3] cuboid half extents / sphere radius in [0] */
+    const void* position;              /* [C][3] collider Position (collider at the body origin, centre of mass at the origin) */
+    const void* rotation;              /* [C][4] */
+    const void* linear_velocity;       /* [B][3] */
+    const void* angular_velocity;      /* [B][3] */
+    const void* aabb_min;              /* [C][3] optional: pairs whose AABBs are disjoint are reported in `disjoint` and skipped */
+    const void* aabb_max;
+} AvnNarrowInput;
+
+typedef struct AvnRawManifolds {      /* fixed stride: 4 point slots per pair, unused slots zero */
+    uint8_t* point_count;              /* [pairs] 0..4 (0 = not touching within the speculative margin) */
+    uint8_t* disjoint;                 /* [pairs] optional */
+    void* normal;                      /* [pairs][3] from collider1 to collider2 */
+    void* anchor1;                     /* [pairs][4][3] */
+    void* anchor2;
+    void* penetration;                 /* [pairs][4] */
+    void* normal_speed;                /* [pairs][4] */
+} AvnRawManifolds;
+
+AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out);
+
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
 /*
