@@ -325,8 +325,8 @@ class AvnRawManifolds(C.Structure):
 
 
 class AvnBoundary(C.Structure):
-    _fields_ = [("count", C.c_uint32), ("slot_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
-                ("body", _vp), ("slot", _vp), ("owner_rank", _vp)]
+    _fields_ = [("count", C.c_uint32), ("record_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("body", _vp), ("source", _vp), ("owner_rank", _vp)]
 
 
 def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
@@ -545,9 +545,10 @@ class Context:
     def solver_run_range(self, first: int, count: int, flags: int) -> None:
         self._check(self.lib.avn_solver_run_range(self.handle, first, count, flags))
 
-    def solver_set_boundary(self, body: np.ndarray, slot: np.ndarray, owner_rank: np.ndarray, slot_count: int, rank: int, world: int) -> None:
-        body, slot, owner_rank = (np.ascontiguousarray(x, dtype=np.int32) for x in (body, slot, owner_rank))
-        b = AvnBoundary(int(body.shape[0]), int(slot_count), int(rank), int(world), _ptr(body), _ptr(slot), _ptr(owner_rank))
+    def solver_set_boundary(self, body: np.ndarray, source: np.ndarray, owner_rank: np.ndarray, record_count: int, rank: int, world: int) -> None:
+        body, source, owner_rank = (np.ascontiguousarray(x, dtype=np.int32) for x in (body, source, owner_rank))
+        assert source.size == body.shape[0] * world
+        b = AvnBoundary(int(body.shape[0]), int(record_count), int(rank), int(world), _ptr(body), _ptr(source), _ptr(owner_rank))
         self._check(self.lib.avn_solver_set_boundary(self.handle, C.byref(b)))
 
     def solver_boundary_snapshot(self) -> None:

@@ -505,12 +505,12 @@ __global__ void boundary_snapshot_kernel(DevSolver<S> d, const int* __restrict__
     st4(&d.vel_ref[2 * k + 1], ld4(&d.vel[2 * b + 1]));
 }
 template <class S>
-__global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
-                                     int n, int rank, Vec4<S>* __restrict__ table) {
+__global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ owner_rank, int n, int rank,
+                                     Vec4<S>* __restrict__ table) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int b = body[k];
-    Vec4<S>* rec = table + size_t(4) * slot[k];
+    Vec4<S>* rec = table + size_t(4) * k;
     const Vec4<S> l = ld4(&d.vel[2 * b]), a = ld4(&d.vel[2 * b + 1]), l0 = ld4(&d.vel_ref[2 * k]), a0 = ld4(&d.vel_ref[2 * k + 1]);
     const bool owner = owner_rank[k] == rank;
     st4(&rec[0], mk4<S>(l.x - l0.x, l.y - l0.y, l.z - l0.z, S(1)));
@@ -521,23 +521,24 @@ __global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ bod
     }
 }
 template <class S>
-__global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
-                                      int n, int world, size_t slots, const Vec4<S>* __restrict__ gathered) {
+__global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ source, const int* __restrict__ owner_rank,
+                                      int n, int world, size_t records, const Vec4<S>* __restrict__ gathered) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int b = body[k];
     Vec4<S> l = ld4(&d.vel_ref[2 * k]), a = ld4(&d.vel_ref[2 * k + 1]);
     // every holder's constraint impulses of this substep, summed in rank order (the same order on every rank: identical bits)
     for (int r = 0; r < world; ++r) {
-        const Vec4<S>* rec = gathered + (size_t(r) * slots + size_t(slot[k])) * 4;
+        const int idx = source[size_t(k) * world + r];
+        if (idx < 0) continue;  // rank r does not hold this body
+        const Vec4<S>* rec = gathered + (size_t(r) * records + size_t(idx)) * 4;
         const Vec4<S> dl = ld4(&rec[0]), da = ld4(&rec[1]);
-        if (dl.w == S(0)) continue;  // rank r does not hold this body
         l.x = l.x + dl.x; l.y = l.y + dl.y; l.z = l.z + dl.z;
         a.x = a.x + da.x; a.y = a.y + da.y; a.z = a.z + da.z;
     }
     st4(&d.vel[2 * b], mk4<S>(l.x, l.y, l.z, S(0)));
     st4(&d.vel[2 * b + 1], mk4<S>(a.x, a.y, a.z, S(0)));
-    const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * slots + size_t(slot[k])) * 4;
+    const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * records + size_t(source[size_t(k) * world + owner_rank[k]])) * 4;
     st4(&d.dlt[2 * b], ld4(&own[2]));
     st4(&d.dlt[2 * b + 1], ld4(&own[3]));
 }
@@ -551,7 +552,8 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
         bnd_n_ = 0;
         return AVN_OK;
     }
-    if (!bnd->body || !bnd->slot || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, slot and owner_rank are required");
+    if (!bnd->body || !bnd->source || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, source and owner_rank are required");
+    if (bnd->count > bnd->record_count) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: count %u exceeds record_count %u", bnd->count, bnd->record_count);
     if (bnd->rank >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: rank %u >= world %u", bnd->rank, bnd->world);
     if (dev_.J > 0) return err_->fail(AVN_ERR_UNSUPPORTED, "boundary exchange covers contact constraints only (joints shard by island)");
     const size_t n = bnd->count, B = size_t(dev_.B);
@@ -559,19 +561,24 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
     for (size_t k = 0; k < n; ++k) {
         const int b = bnd->body[k];
         if (b < 0 || size_t(b) >= B) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body[%zu] = %d out of range", k, b);
-        if (bnd->slot[k] < 0 || uint32_t(bnd->slot[k]) >= bnd->slot_count) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: slot[%zu] out of range", k);
         if (bnd->owner_rank[k] < 0 || uint32_t(bnd->owner_rank[k]) >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: owner_rank[%zu] out of range", k);
+        for (uint32_t r = 0; r < bnd->world; ++r) {
+            const int idx = bnd->source[k * bnd->world + r];
+            if (idx >= int(bnd->record_count)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: source[%zu][%u] out of range", k, r);
+        }
+        if (bnd->source[k * bnd->world + bnd->rank] != int(k)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: source[%zu][rank] must be %zu", k, k);
+        if (bnd->source[k * bnd->world + bnd->owner_rank[k]] < 0) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: the owner of body[%zu] must hold it", k);
         if (of[b] != -1) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body %d listed twice", b);
         of[b] = int(k);
     }
     AVN_CUDA(bnd_of_.ensure((B + 1) * sizeof(int)));
     AVN_CUDA(bnd_body_.ensure(n * sizeof(int)));
-    AVN_CUDA(bnd_slot_.ensure(n * sizeof(int)));
+    AVN_CUDA(bnd_slot_.ensure(n * bnd->world * sizeof(int)));
     AVN_CUDA(bnd_owner_.ensure(n * sizeof(int)));
     AVN_CUDA(vel_ref_.ensure(2 * n * sizeof(Vec4<S>)));
     AVN_CUDA(cudaMemcpyAsync(bnd_of_.p, of.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaMemcpyAsync(bnd_body_.p, bnd->body, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    AVN_CUDA(cudaMemcpyAsync(bnd_slot_.p, bnd->slot, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaMemcpyAsync(bnd_slot_.p, bnd->source, n * bnd->world * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaMemcpyAsync(bnd_owner_.p, bnd->owner_rank, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaStreamSynchronize(stream_));   // `of` is a temporary
     dev_.bnd_of = bnd_of_.as<int>();
@@ -579,7 +586,7 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
     bnd_n_ = int(n);
     bnd_rank_ = int(bnd->rank);
     bnd_world_ = int(bnd->world);
-    bnd_slots_ = size_t(bnd->slot_count);
+    bnd_slots_ = size_t(bnd->record_count);
     return AVN_OK;
 }
 
@@ -601,7 +608,7 @@ AvnStatus Solver<S>::boundary_pack(void* device_table) {
     if (!device_table) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary table is required");
     AVN_CUDA(cudaMemsetAsync(device_table, 0, bnd_slots_ * 4 * sizeof(Vec4<S>), stream_));
     if (bnd_n_ > 0) {
-        boundary_pack_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_slot_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_rank_,
+        boundary_pack_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_rank_,
                                                                             static_cast<Vec4<S>*>(device_table));
         ++launches_;
     }

@@ -303,7 +303,7 @@ AvnStatus avn_solver_download(AvnContext* ctx);
  * by more than one rank is a BOUNDARY body; it has one slot in a table every rank agrees on.  Per substep each rank launches
  * avn_solver_run_range for that substep, packs for every boundary body it holds the velocity change its own constraints caused
  * (relative to the velocity right after integrate_velocities, which every holder computes identically) and, if it owns the body,
- * the body's delta_position / delta_rotation; the tables are all-gathered (NCCL, by the caller, on the stream avn_get_stream
+ * the body's delta_position / delta_rotation, into its own packed table (one record per held boundary body); the tables are all-gathered (NCCL, by the caller, on the stream avn_get_stream
  * returns); avn_solver_boundary_apply sets v = v_ref + sum over ranks in rank order of their changes and takes the owner's deltas.
  * Impulses therefore cross a cut once per substep instead of once per constraint: results match the single-GPU step to solver
  * tolerance, not to 1e-5; a scene whose constraints do not cross a cut is reproduced bit for bit. */
@@ -312,15 +312,15 @@ AvnStatus avn_solver_download(AvnContext* ctx);
 #define AVN_RUN_FINALIZE 0x4u     /* writeback_solver_bodies + store_contact_impulses: must be part of the last launch */
 
 typedef struct AvnBoundary {
-    uint32_t count;               /* boundary bodies held by this rank */
-    uint32_t slot_count;          /* slots of the global boundary table */
+    uint32_t count;               /* boundary bodies held by this rank: record k of this rank's table belongs to body[k] */
+    uint32_t record_count;        /* records per rank's table = the largest `count` of any rank (all-gather needs equal sizes) */
     uint32_t rank, world;
     const int32_t* body;          /* [count] index into the uploaded AvnBodyColumns */
-    const int32_t* slot;          /* [count] slot of the body in the global table */
+    const int32_t* source;        /* [count][world] record of body[k] in rank r's table, or -1 when rank r does not hold it */
     const int32_t* owner_rank;    /* [count] the rank whose delta_position / delta_rotation are authoritative */
 } AvnBoundary;
-/* scalars per slot of the exchange table (4 rows of 4): the table is slot_count * AVN_BOUNDARY_RECORD_SCALARS scalars,
- * the gathered tables world times that, rank-major */
+/* scalars per record of the exchange table (4 rows of 4): a table is record_count * AVN_BOUNDARY_RECORD_SCALARS scalars,
+ * the gathered tables world times that, rank-major.  Only held bodies travel: the table is as large as the busiest rank's list. */
 #define AVN_BOUNDARY_RECORD_SCALARS 16
 
 AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags);
