@@ -266,4 +266,15 @@ NM_HD inline int manifold_points(const Contacts& pts, V3 normal, V3 pa, V3 pb, V
     return m;
 }
 
+// ContactManifold::match_contacts with unknown feature ids (contact_types/mod.rs:426-470): a new point inherits the warm-start impulses
+// of the first old point whose two anchors both lie within the distance threshold (squared: thr2) of its own, in either body order.
+// Returns the index of that old point or -1.
+NM_HD inline int match_point(V3 anchor1, V3 anchor2, const V3* old_anchor1, const V3* old_anchor2, int n_old, S thr2) {
+    for (int k = 0; k < n_old; ++k) {
+        V3 e11 = anchor1 - old_anchor1[k], e22 = anchor2 - old_anchor2[k], e12 = anchor1 - old_anchor2[k], e21 = anchor2 - old_anchor1[k];
+        if ((dot(e11, e11) < thr2 && dot(e22, e22) < thr2) || (dot(e12, e12) < thr2 && dot(e21, e21) < thr2)) return k;
+    }
+    return -1;
+}
+
 }  // namespace nm

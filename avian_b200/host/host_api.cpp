@@ -287,17 +287,16 @@ uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* k
         if (touching && match_contacts && pr.manifolds.size() <= 4) {
             // ContactManifold::match_contacts with unknown feature ids (contact_types/mod.rs:426-470)
             const S thr2 = (0.1 * P.length_unit) * (0.1 * P.length_unit);
-            auto d2 = [](V3 x, V3 y) { V3 e = x - y; return dot(e, e); };
             for (Manifold& m : pr.manifolds)
-                for (const Manifold& om : old)
-                    for (Point& c : m.pts)
-                        for (const Point& pc : om.pts) {
-                            if ((d2(c.anchor1, pc.anchor1) < thr2 && d2(c.anchor2, pc.anchor2) < thr2) ||
-                                (d2(c.anchor1, pc.anchor2) < thr2 && d2(c.anchor2, pc.anchor1) < thr2)) {
-                                c.ws_normal = pc.ws_normal; c.ws_tx = pc.ws_tx; c.ws_ty = pc.ws_ty;
-                                break;
-                            }
-                        }
+                for (const Manifold& om : old) {
+                    V3 oa1[8], oa2[8];
+                    const int n_old = int(std::min<size_t>(om.pts.size(), 8));
+                    for (int k = 0; k < n_old; ++k) { oa1[k] = om.pts[k].anchor1; oa2[k] = om.pts[k].anchor2; }
+                    for (Point& c : m.pts) {
+                        const int k = match_point(c.anchor1, c.anchor2, oa1, oa2, n_old, thr2);
+                        if (k >= 0) { c.ws_normal = om.pts[k].ws_normal; c.ws_tx = om.pts[k].ws_tx; c.ws_ty = om.pts[k].ws_ty; }
+                    }
+                }
         }
         count_change[id] = int(pr.manifolds.size()) - int(old.size());
         if (touching && !pr.touching) { started[id] = 1; changed.push_back(id); }

@@ -160,3 +160,36 @@ def test_several_far_reaching_intervals_owned_by_different_slabs(world):
     got, order = parallel.merge_slab_results(parts, a.collider)
     assert_same_pairs(got, want)
     assert np.array_equal(order, want_order)
+
+
+def _worker_degenerate(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    info = parallel.init(backend="gloo")
+    a = random_aabbs(60, seed=4, ground=False, existing_frac=0)
+    a.aabb_min[:, 0] = 1.0            # one slab owns everything: the other rank contributes zero-length columns to every gather
+    a.aabb_max[:, 0] = 2.0
+    got, order = parallel.slab_broadphase(oracle_lib.broadphase, a, info)
+    q.put((rank, got.count, got.collider1.copy(), got.collider2.copy(), order))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_with_an_empty_slab():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker_degenerate, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=180) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a = random_aabbs(60, seed=4, ground=False, existing_frac=0)
+    a.aabb_min[:, 0] = 1.0
+    a.aabb_max[:, 0] = 2.0
+    want = oracle_lib.broadphase(a)
+    assert want.count > 20
+    for rank, count, c1, c2, order in results:
+        assert count == want.count and np.array_equal(c1, want.collider1[:count]) and np.array_equal(c2, want.collider2[:count])
+        assert np.array_equal(order, a.order_out)
