@@ -235,6 +235,40 @@ void avh_add_pairs(AvhPipeline* h, const uint32_t* c1, const uint32_t* c2, const
     }
 }
 
+// The second half of NarrowPhase::update: status changes in ascending ContactId (system_param.rs:136-389) -> ContactGraph removals and
+// ConstraintGraph push / pop.  Returns the number of manifolds in the constraint graph; *out_points = their points.
+static uint32_t apply_status_changes(Pipeline& P, std::vector<uint32_t>& changed, const std::vector<uint8_t>& disjoint, const std::vector<uint8_t>& started,
+                                     const std::vector<uint8_t>& stopped, const std::vector<int>& count_change, uint32_t* out_points) {
+    std::sort(changed.begin(), changed.end());
+    for (uint32_t id : changed) {
+        Pair& pr = P.pairs[id];
+        const bool gen = pr.flags & AVN_PAIR_GENERATE_CONSTRAINTS;
+        if (disjoint[id]) {
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+            P.pair_set.erase(pair_key(pr.collider1, pr.collider2));
+            auto it = std::find(P.active.begin(), P.active.end(), id);  // remove_edge_by_id: swap_remove (contact_graph.rs:615-628)
+            if (it != P.active.end()) { *it = P.active.back(); P.active.pop_back(); }
+            pr = Pair{};
+            P.free_ids.push(id);
+        } else if (started[id]) {
+            pr.touching = true;
+            if (gen) for (size_t k = 0; k < pr.manifolds.size(); ++k) push_manifold(P, id);
+        } else if (stopped[id]) {
+            pr.touching = false;
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] > 0) {
+            for (int k = 0; k < count_change[id]; ++k) push_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] < 0) {
+            for (int k = 0; k < -count_change[id]; ++k) pop_manifold(P, id);
+        }
+    }
+    uint32_t M = 0, Pn = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
+        for (auto& hnd : P.colors[c].handles) { ++M; Pn += uint32_t(P.pairs[hnd.first].manifolds[hnd.second].pts.size()); }
+    if (out_points) *out_points = Pn;
+    return M;
+}
+
 // NarrowPhase::update (narrow_phase/system_param.rs:114-400) with the fixture manifold generator.
 // kind[n] = AvnBodyKind.  Returns the number of exported manifolds; *out_points = number of points.
 uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* kind, const void* position, const void* rotation, const void* linvel,
@@ -303,35 +337,7 @@ uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* k
         else if (!touching && pr.touching) { stopped[id] = 1; changed.push_back(id); }
         else if (count_change[id] != 0) changed.push_back(id);
     }
-    // status changes in ascending ContactId (system_param.rs:136-389)
-    std::sort(changed.begin(), changed.end());
-    for (uint32_t id : changed) {
-        Pair& pr = P.pairs[id];
-        const bool gen = pr.flags & AVN_PAIR_GENERATE_CONSTRAINTS;
-        if (disjoint[id]) {
-            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
-            P.pair_set.erase(pair_key(pr.collider1, pr.collider2));
-            auto it = std::find(P.active.begin(), P.active.end(), id);  // remove_edge_by_id: swap_remove (contact_graph.rs:615-628)
-            if (it != P.active.end()) { *it = P.active.back(); P.active.pop_back(); }
-            pr = Pair{};
-            P.free_ids.push(id);
-        } else if (started[id]) {
-            pr.touching = true;
-            if (gen) for (size_t k = 0; k < pr.manifolds.size(); ++k) push_manifold(P, id);
-        } else if (stopped[id]) {
-            pr.touching = false;
-            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
-        } else if (pr.touching && gen && count_change[id] > 0) {
-            for (int k = 0; k < count_change[id]; ++k) push_manifold(P, id);
-        } else if (pr.touching && gen && count_change[id] < 0) {
-            for (int k = 0; k < -count_change[id]; ++k) pop_manifold(P, id);
-        }
-    }
-    uint32_t M = 0, Pn = 0;
-    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
-        for (auto& hnd : P.colors[c].handles) { ++M; Pn += uint32_t(P.pairs[hnd.first].manifolds[hnd.second].pts.size()); }
-    if (out_points) *out_points = Pn;
-    return M;
+    return apply_status_changes(P, changed, disjoint, started, stopped, count_change, out_points);
 }
 
 // Export the manifolds grouped by colour in manifold_handles order (what prepare_contact_constraints walks,
@@ -388,7 +394,7 @@ void avh_store_impulses(AvhPipeline* h, uint32_t scalar_bits, const void* ws_nor
 void avh_raw_manifolds(uint32_t scalar_bits, uint32_t pair_count, const uint32_t* c1, const uint32_t* c2, const uint32_t* b1, const uint32_t* b2,
                        const uint8_t* shape, const void* dims, const void* position, const void* rotation, const void* linvel, const void* angvel,
                        const void* aabb_min, const void* aabb_max, double dt, double tol, uint8_t* point_count, uint8_t* disjoint, void* normal,
-                       void* anchor1, void* anchor2, void* penetration, void* normal_speed) {
+                       void* anchor1, void* anchor2, void* penetration, void* normal_speed, double* anchor1_f64, double* anchor2_f64) {
     const bool f64 = scalar_bits == 64;
     Col dm{dims, f64}, pos{position, f64}, rt{rotation, f64}, lv{linvel, f64}, av{angvel, f64}, amin{aabb_min, f64}, amax{aabb_max, f64};
     ColW on{normal, f64}, oa1{anchor1, f64}, oa2{anchor2, f64}, op{penetration, f64}, os{normal_speed, f64};
@@ -421,9 +427,114 @@ void avh_raw_manifolds(uint32_t scalar_bits, uint32_t pair_count, const uint32_t
         for (int p = 0; p < np; ++p) {
             oa1.set3(4 * size_t(k) + p, out[p].anchor1);
             oa2.set3(4 * size_t(k) + p, out[p].anchor2);
+            if (anchor1_f64)   // unrounded anchors: what the next step's match_contacts compares (the fixture matches in double)
+                for (int c = 0; c < 3; ++c) {
+                    anchor1_f64[(4 * size_t(k) + p) * 3 + c] = comp(out[p].anchor1, c);
+                    anchor2_f64[(4 * size_t(k) + p) * 3 + c] = comp(out[p].anchor2, c);
+                }
             op.set(4 * size_t(k) + p, out[p].penetration);
             os.set(4 * size_t(k) + p, out[p].normal_speed);
         }
+    }
+}
+
+// ---- resident mode: the geometry runs elsewhere (avn_narrow_phase), the host keeps only the graphs -------------
+// The active contact edges in ContactGraph order: edge id (ContactId), colliders, bodies.  Arrays sized avh_pair_count().
+uint32_t avh_active_edges(AvhPipeline* h, uint32_t* ids, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    uint32_t n = 0;
+    for (uint32_t id : P.active) {
+        const Pair& pr = P.pairs[id];
+        ids[n] = id; c1[n] = pr.collider1; c2[n] = pr.collider2; b1[n] = pr.body1; b2[n] = pr.body2;
+        ++n;
+    }
+    return n;
+}
+
+// The host half of the narrow phase from the per-edge results computed elsewhere: point_count[i] (0 = not touching) and disjoint[i] for
+// edge ids[i].  Same status machine, same graph updates as avh_narrow_phase; the manifolds only remember how many points they have.
+uint32_t avh_apply_counts(AvhPipeline* h, const uint8_t* kind, const uint32_t* ids, const uint8_t* point_count, const uint8_t* disjoint_in, uint32_t n,
+                          uint32_t* out_points) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    std::vector<uint32_t> changed;
+    std::vector<uint8_t> disjoint(P.pairs.size(), 0), started(P.pairs.size(), 0), stopped(P.pairs.size(), 0);
+    std::vector<int> count_change(P.pairs.size(), 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t id = ids[i];
+        Pair& pr = P.pairs[id];
+        if (disjoint_in[i]) { disjoint[id] = 1; changed.push_back(id); continue; }
+        pr.static1 = kind[pr.body1] == AVN_BODY_STATIC;
+        pr.static2 = kind[pr.body2] == AVN_BODY_STATIC;
+        const size_t old_count = pr.manifolds.size();
+        pr.manifolds.clear();
+        if (point_count[i] > 0) {
+            Manifold m;
+            m.normal = V3{0, 0, 0};
+            m.pts.resize(point_count[i]);
+            pr.manifolds.push_back(std::move(m));
+        }
+        const bool touching = !pr.manifolds.empty();
+        count_change[id] = int(pr.manifolds.size()) - int(old_count);
+        if (touching && !pr.touching) { started[id] = 1; changed.push_back(id); }
+        else if (!touching && pr.touching) { stopped[id] = 1; changed.push_back(id); }
+        else if (count_change[id] != 0) changed.push_back(id);
+    }
+    return apply_status_changes(P, changed, disjoint, started, stopped, count_change, out_points);
+}
+
+// The constraint graph as a colour-major list of edge ids (manifold_handles order) with the per-edge material (what the solver's prepare
+// needs besides the geometry).  Arrays sized from avh_apply_counts' return value.
+void avh_export_edges(AvhPipeline* h, uint32_t* color_offsets /*[25]*/, uint32_t* edge, int32_t* body1, int32_t* body2, double* friction, double* restitution) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    uint32_t m = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) {
+        color_offsets[c] = m;
+        for (auto& hnd : P.colors[c].handles) {
+            const Pair& pr = P.pairs[hnd.first];
+            edge[m] = hnd.first;
+            body1[m] = int32_t(pr.body1);
+            body2[m] = int32_t(pr.body2);
+            friction[m] = (P.shapes[pr.collider1].friction + P.shapes[pr.collider2].friction) * 0.5;
+            restitution[m] = (P.shapes[pr.collider1].restitution + P.shapes[pr.collider2].restitution) * 0.5;
+            ++m;
+        }
+    }
+    color_offsets[AVN_GRAPH_COLOR_COUNT] = m;
+}
+
+// match_contacts on edge-indexed resident state (what the device keeps between steps): for edge ids[i] with new_count[i] points whose anchors
+// (double, unrounded: the fixture matches in double) are new_a1/new_a2[i][4][3], carry the warm-start impulses over from the matching old
+// points and make the new points the resident ones.  ws_n[E][4], ws_t[E][4][2] in the column scalar type.
+void avh_match_raw(uint32_t scalar_bits, uint32_t n, const uint32_t* ids, const uint8_t* new_count, const double* new_a1, const double* new_a2,
+                   double length_unit, uint32_t match_contacts, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n, void* ws_t) {
+    const bool f64 = scalar_bits == 64;
+    Col rn{ws_n, f64}, rtg{ws_t, f64};
+    ColW wn{ws_n, f64}, wt{ws_t, f64};
+    const S thr2 = (0.1 * length_unit) * (0.1 * length_unit);
+    for (uint32_t i = 0; i < n; ++i) {
+        const size_t e = ids[i];
+        const int nc = new_count[i], oc = prev_count[e];
+        V3 oa1[4], oa2[4];
+        S on[4], otx[4], oty[4];
+        for (int k = 0; k < oc; ++k) {
+            oa1[k] = V3{prev_a1[(e * 4 + k) * 3], prev_a1[(e * 4 + k) * 3 + 1], prev_a1[(e * 4 + k) * 3 + 2]};
+            oa2[k] = V3{prev_a2[(e * 4 + k) * 3], prev_a2[(e * 4 + k) * 3 + 1], prev_a2[(e * 4 + k) * 3 + 2]};
+            on[k] = rn.at(e * 4 + k); otx[k] = rtg.at((e * 4 + k) * 2); oty[k] = rtg.at((e * 4 + k) * 2 + 1);
+        }
+        for (int k = 0; k < 4; ++k) {
+            S vn = 0, vx = 0, vy = 0;
+            if (k < nc) {
+                const V3 a1{new_a1[(size_t(i) * 4 + k) * 3], new_a1[(size_t(i) * 4 + k) * 3 + 1], new_a1[(size_t(i) * 4 + k) * 3 + 2]};
+                const V3 a2{new_a2[(size_t(i) * 4 + k) * 3], new_a2[(size_t(i) * 4 + k) * 3 + 1], new_a2[(size_t(i) * 4 + k) * 3 + 2]};
+                const int j = match_contacts ? match_point(a1, a2, oa1, oa2, oc, thr2) : -1;
+                if (j >= 0) { vn = on[j]; vx = otx[j]; vy = oty[j]; }
+                for (int c = 0; c < 3; ++c) { prev_a1[(e * 4 + k) * 3 + c] = comp(a1, c); prev_a2[(e * 4 + k) * 3 + c] = comp(a2, c); }
+            }
+            wn.set(e * 4 + k, vn);
+            wt.set((e * 4 + k) * 2, vx);
+            wt.set((e * 4 + k) * 2 + 1, vy);
+        }
+        prev_count[e] = uint8_t(nc);
     }
 }
 
