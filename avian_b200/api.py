@@ -310,6 +310,12 @@ class PairList:
         return PairList(self.collider1[:n], self.collider2[:n], self.body1[:n], self.body2[:n], self.flags[:n], n)
 
 
+class AvnEdgeManifolds(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("edge_capacity", C.c_uint32), ("color_offsets", C.c_uint32 * (GRAPH_COLOR_COUNT + 1))] + [
+        (n, _vp) for n in ("edge", "body1", "body2", "friction", "restitution", "point_count", "normal", "anchor1", "anchor2", "penetration",
+                           "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")]
+
+
 class AvnNarrowParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("contact_tolerance", C.c_double)]
 
@@ -358,6 +364,7 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "solver_needs_restitution": ([_vp, P(C.c_int)], C.c_int),
         "get_stream": ([_vp, P(_vp)], C.c_int),
         "narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), P(AvnRawManifolds)], C.c_int),
+        "solver_upload_edges": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -369,7 +376,7 @@ ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
-    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase"]
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase", "avn_solver_upload_edges"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 BOUNDARY_RECORD_SCALARS = 16
@@ -570,6 +577,35 @@ class Context:
         out = _vp()
         self._check(self.lib.avn_get_stream(self.handle, C.byref(out)))
         return int(out.value or 0)
+
+    def solver_step_edges(self, params, bodies: Bodies, graph: dict, edges: dict, joints: JointSet | None = None) -> None:
+        """avn_solver_upload_edges + run + download.  graph = dict(color_offsets, edge, body1, body2, friction, restitution) (per manifold);
+        edges = dict(point_count, normal, anchor1, anchor2, penetration, normal_speed, warm_start_normal_impulse,
+        warm_start_tangent_impulse, normal_impulse) (edge-indexed, 4 slots per edge; the three impulse columns are updated in place)."""
+        b = bodies.as_struct()
+        j = joints.as_struct() if joints is not None and joints.count else None
+        em = AvnEdgeManifolds()
+        em.count = int(graph["edge"].shape[0])
+        em.edge_capacity = int(edges["point_count"].shape[0])
+        for i in range(GRAPH_COLOR_COUNT + 1):
+            em.color_offsets[i] = int(graph["color_offsets"][i])
+        keep = []
+        def col(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+        em.edge = col(graph["edge"], np.uint32); em.body1 = col(graph["body1"], np.int32); em.body2 = col(graph["body2"], np.int32)
+        em.friction = col(graph["friction"], self.scalar); em.restitution = col(graph["restitution"], self.scalar)
+        em.point_count = col(edges["point_count"], np.uint8)
+        for k in ("normal", "anchor1", "anchor2", "penetration", "normal_speed"):
+            setattr(em, k, col(edges[k], self.scalar))
+        for k in ("warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse"):
+            assert edges[k].flags["C_CONTIGUOUS"] and edges[k].dtype == self.scalar
+            setattr(em, k, edges[k].ctypes.data)
+        self._keep = (params, bodies, graph, edges, joints, b, em, j, keep)
+        self._check(self.lib.avn_solver_upload_edges(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
+        self._check(self.lib.avn_solver_run(self.handle))
+        self._check(self.lib.avn_solver_download(self.handle))
 
     def narrow_phase(self, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray) -> dict:
         """avn_narrow_phase: pairs = (collider1, collider2, body1, body2) uint32 arrays; colliders = dict(shape, dims, position, rotation,

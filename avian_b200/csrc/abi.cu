@@ -106,6 +106,11 @@ AvnStatus avn_solver_run(AvnContext* ctx) {
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
     return ctx->solver->run();
 }
+AvnStatus avn_solver_upload_edges(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->upload_edges(params, bodies, manifolds, joints);
+}
 AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags) {
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");

@@ -56,6 +56,7 @@ struct DevBuf {
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) = 0;
+    virtual AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) = 0;
     virtual AvnStatus run() = 0;
     virtual AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) = 0;
     virtual AvnStatus set_boundary(const AvnBoundary* bnd) = 0;

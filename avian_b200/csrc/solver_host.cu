@@ -65,6 +65,7 @@ class Solver final : public SolverBase {
     }
 
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
+    AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) override;
     AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) override;
     AvnStatus set_boundary(const AvnBoundary* bnd) override;
     AvnStatus boundary_snapshot() override;
@@ -153,7 +154,20 @@ class Solver final : public SolverBase {
     DevSolver<S> dev_{};
     // host pointers for download
     AvnBodyColumns hb_{};
-    AvnManifoldColumns hm_{};
+    // where the manifolds of an upload come from: the CSR columns of AvnManifoldColumns or the edge-indexed columns of AvnEdgeManifolds
+    struct ManifoldSource {
+        size_t M = 0, P = 0, normal_rows = 0;             // manifolds, rows of the point columns, rows of the normal column
+        const uint32_t* color_offsets = nullptr;
+        const int32_t* body1 = nullptr; const int32_t* body2 = nullptr;
+        const void* friction = nullptr; const void* restitution = nullptr; const void* tangent_velocity = nullptr; const void* normal = nullptr;
+        const uint32_t* point_offsets = nullptr;           // CSR
+        const uint32_t* edge = nullptr; const uint8_t* edge_point_count = nullptr;   // edge-indexed
+        const void* anchor1 = nullptr; const void* anchor2 = nullptr; const void* penetration = nullptr; const void* normal_speed = nullptr;
+        void* ws_normal = nullptr; void* ws_tangent = nullptr; void* normal_impulse = nullptr;
+    };
+    AvnStatus upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* src, AvnJointSet* js);
+    ManifoldSource hm_{};
+    DevBuf m_edge_, m_pbegin_, m_pend_, e_cnt_;
     AvnJointSet hj_{};
     bool have_m_ = false, have_j_ = false;
 
@@ -189,6 +203,48 @@ AvnStatus Solver<S>::build_joint_schedule(const AvnBodyColumns& bc, const AvnJoi
 
 template <class S>
 AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) {
+    if (!mc || mc->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
+        !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+    ManifoldSource src;
+    src.M = mc->count; src.P = mc->point_count; src.normal_rows = mc->count;
+    src.color_offsets = mc->color_offsets; src.body1 = mc->body1; src.body2 = mc->body2; src.friction = mc->friction; src.restitution = mc->restitution;
+    src.tangent_velocity = mc->tangent_velocity; src.normal = mc->normal; src.point_offsets = mc->point_offsets;
+    src.anchor1 = mc->anchor1; src.anchor2 = mc->anchor2; src.penetration = mc->penetration; src.normal_speed = mc->normal_speed;
+    src.ws_normal = mc->warm_start_normal_impulse; src.ws_tangent = mc->warm_start_tangent_impulse; src.normal_impulse = mc->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) {
+    if (!em || em->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!em->edge || !em->body1 || !em->body2 || !em->friction || !em->restitution || !em->point_count || !em->normal || !em->anchor1 || !em->anchor2 ||
+        !em->penetration || !em->normal_speed || !em->warm_start_normal_impulse || !em->warm_start_tangent_impulse || !em->normal_impulse)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: every column is required");
+    for (size_t m = 0; m < em->count; ++m)
+        if (em->edge[m] >= em->edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: edge[%zu] = %u >= edge_capacity %u", m, em->edge[m], em->edge_capacity);
+    ManifoldSource src;
+    src.M = em->count; src.P = size_t(4) * em->edge_capacity; src.normal_rows = em->edge_capacity;
+    src.color_offsets = em->color_offsets; src.body1 = em->body1; src.body2 = em->body2; src.friction = em->friction; src.restitution = em->restitution;
+    src.normal = em->normal; src.edge = em->edge; src.edge_point_count = em->point_count;
+    src.anchor1 = em->anchor1; src.anchor2 = em->anchor2; src.penetration = em->penetration; src.normal_speed = em->normal_speed;
+    src.ws_normal = em->warm_start_normal_impulse; src.ws_tangent = em->warm_start_tangent_impulse; src.normal_impulse = em->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+// fills the point ranges of the manifolds of an edge-indexed upload: 4 slots per edge, the first point_count[edge] of them live
+__global__ void edge_ranges_kernel(const uint32_t* __restrict__ edge, const uint8_t* __restrict__ count, int M, uint32_t* __restrict__ begin,
+                                   uint32_t* __restrict__ end) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const uint32_t e = edge[m];
+    begin[m] = 4u * e;
+    end[m] = 4u * e + count[e];
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* mc, AvnJointSet* js) {
     if (!prm || !bc) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "params and bodies are required");
     if (bc->count && (!bc->position || !bc->rotation || !bc->linear_velocity || !bc->angular_velocity || !bc->inverse_mass || !bc->inverse_inertia_local))
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "bodies: position, rotation, velocities, inverse_mass and inverse_inertia_local are required");
@@ -256,29 +312,33 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     // mutable front of it (vel, dlt, ver, deg, the four impulse planes) is the L2-persisting window.
     hb_ = *bc;
     // ---- manifolds
-    have_m_ = mc && mc->count > 0;
+    have_m_ = mc != nullptr && mc->M > 0;
     AVN_CUDA(c_flag_.ensure(2 * sizeof(int) + 8 * sizeof(unsigned long long)));  // [0] any restitution, [1] wavefront watchdog, then the optional trace counters
     d.any_restitution = c_flag_.as<int>();
     if (have_m_) {
-        const size_t M = mc->count, P = mc->point_count;
-        if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
-            !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
-            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+        const size_t M = mc->M, P = mc->P;
         if (mc->color_offsets[0] != 0 || mc->color_offsets[AVN_GRAPH_COLOR_COUNT] != M)
             return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must span [0, count]");
         for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
             if (mc->color_offsets[c] > mc->color_offsets[c + 1]) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must be non-decreasing");
-        if (mc->point_offsets[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
-        {   // widest manifold: sizes the shared-memory staging tile (3 rows per point) and validates the CSR
+        {   // widest manifold: sizes the shared-memory staging tile (3 rows per point) and validates the point ranges
             uint32_t widest = 0, bad = 0;
-            const uint32_t* po = mc->point_offsets;
-            for (size_t i = 0; i < M; ++i) {
-                bad |= uint32_t(po[i + 1] < po[i]);
-                const uint32_t n = po[i + 1] - po[i];
-                widest = n > widest ? n : widest;
+            if (mc->point_offsets) {
+                const uint32_t* po = mc->point_offsets;
+                if (po[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
+                for (size_t i = 0; i < M; ++i) {
+                    bad |= uint32_t(po[i + 1] < po[i]);
+                    const uint32_t n = po[i + 1] - po[i];
+                    widest = n > widest ? n : widest;
+                }
+            } else {
+                for (size_t i = 0; i < M; ++i) {
+                    const uint32_t n = mc->edge_point_count[mc->edge[i]];
+                    widest = n > widest ? n : widest;
+                }
             }
             if (bad || widest > AVN_MAX_MANIFOLD_POINTS)
-                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets must be non-decreasing with at most %d points per manifold", AVN_MAX_MANIFOLD_POINTS);
+                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: at most %d points per manifold, point ranges must not decrease", AVN_MAX_MANIFOLD_POINTS);
             max_np_ = int(std::max<uint32_t>(widest, 1));
         }
         d.M = int(M);
@@ -297,29 +357,50 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         }
         UP(m_b1_, mc->body1, M, int, m_body1);
         UP(m_b2_, mc->body2, M, int, m_body2);
-        UP(m_n_, mc->normal, 3 * M, S, m_normal);
+        UP(m_n_, mc->normal, 3 * mc->normal_rows, S, m_normal);
         UP(m_f_, mc->friction, M, S, m_friction);
         UP(m_r_, mc->restitution, M, S, m_restitution);
         UP(m_tv_, mc->tangent_velocity, 3 * M, S, m_tanvel);
-        UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_off);
+        if (mc->point_offsets) {
+            UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_begin);
+            d.m_point_end = d.m_point_begin + 1;
+            d.m_src = nullptr;
+        } else {
+            const uint8_t* d_count = nullptr;
+            UP(m_edge_, mc->edge, M, uint32_t, m_src);
+            if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
+            AVN_CUDA(m_pbegin_.ensure(M * sizeof(uint32_t)));
+            AVN_CUDA(m_pend_.ensure(M * sizeof(uint32_t)));
+            edge_ranges_kernel<<<unsigned((M + 255) / 256), 256, 0, stream_>>>(d.m_src, d_count, int(M), m_pbegin_.as<uint32_t>(), m_pend_.as<uint32_t>());
+            AVN_CUDA(cudaGetLastError());
+            d.m_point_begin = m_pbegin_.as<uint32_t>();
+            d.m_point_end = m_pend_.as<uint32_t>();
+        }
         UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
         UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
         UP(p_pen_, mc->penetration, P, S, p_penetration);
         UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
         // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
-        UP(p_wn_, mc->warm_start_normal_impulse, P, S, p_ws_normal);
-        UP(p_wt_, mc->warm_start_tangent_impulse, 2 * P, S, p_ws_tangent);
+        UP(p_wn_, mc->ws_normal, P, S, p_ws_normal);
+        UP(p_wt_, mc->ws_tangent, 2 * P, S, p_ws_tangent);
         UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
         AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
         AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
         AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
         d.p_normal_impulse = p_ni_.as<S>();
+        if (!mc->point_offsets) {
+            // edge-indexed: rows of edges that are not in the constraint graph are not written by store_contact_impulses; they keep their
+            // input values (the reference leaves such ContactPoints untouched)
+            AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_normal, d.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+            AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_tangent, d.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+            AVN_CUDA(cudaMemcpyAsync(d.p_normal_impulse, d.p_in_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+        }
 
         hm_ = *mc;
         host_any_restitution_ = false;
         {
             const S* r = static_cast<const S*>(mc->restitution);
-            for (size_t i = 0; i < M; ++i) host_any_restitution_ |= (r[i] != S(0));
+            for (size_t i = 0; i < mc->M; ++i) host_any_restitution_ |= (r[i] != S(0));
         }
     }
     {
@@ -640,9 +721,9 @@ AvnStatus Solver<S>::download() {
         AVN_CUDA(cudaMemcpyAsync(hb_.angular_velocity, dev_.out_angvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
     if (have_m_) {
-        const size_t P = hm_.point_count;
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_normal_impulse, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_tangent_impulse, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        const size_t P = hm_.P;
+        AVN_CUDA(cudaMemcpyAsync(hm_.ws_normal, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.ws_tangent, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hm_.normal_impulse, dev_.p_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
     if (have_j_) {

@@ -297,6 +297,31 @@ AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBod
 AvnStatus avn_solver_run(AvnContext* ctx);
 AvnStatus avn_solver_download(AvnContext* ctx);
 
+/* The same stage fed from EDGE-INDEXED manifold storage: the layout avn_narrow_phase writes (4 point slots per contact edge, indexed by
+ * ContactId) plus the constraint graph as a colour-major list of edge ids.  prepare_contact_constraints reads manifold m through
+ * edge[m]; store_contact_impulses writes the impulses back to the edge's slots.  This is the input form of a device-resident pipeline:
+ * the geometry never has to be compacted or sent through the host, only the edge list changes hands. */
+typedef struct AvnEdgeManifolds {
+    uint32_t count;                                     /* M: manifolds in the constraint graph */
+    uint32_t edge_capacity;                             /* E: rows of the edge-indexed columns */
+    uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];  /* colour c owns edge[off[c], off[c+1]) */
+    const uint32_t* edge;             /* [M] ContactId of manifold m */
+    const int32_t* body1;             /* [M] */
+    const int32_t* body2;
+    const void* friction;             /* [M] */
+    const void* restitution;          /* [M] */
+    const uint8_t* point_count;       /* [E] 0..4 */
+    const void* normal;               /* [E][3] */
+    const void* anchor1;              /* [E][4][3] */
+    const void* anchor2;
+    const void* penetration;          /* [E][4] */
+    const void* normal_speed;         /* [E][4] */
+    void* warm_start_normal_impulse;  /* [E][4]    in/out */
+    void* warm_start_tangent_impulse; /* [E][4][2] in/out */
+    void* normal_impulse;             /* [E][4]    out */
+} AvnEdgeManifolds;
+AvnStatus avn_solver_upload_edges(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints);
+
 /* ---- one coupled scene over several GPUs: the x-slab partition (BASELINE north_star "single all-gather of boundary
  *      state per substep where the scene spans GPUs").  Not a reference interface: the reference is single-process. -------------
  * Each rank uploads its own bodies and constraints plus copies ("ghosts") of the remote bodies its constraints touch.  A body held

@@ -59,3 +59,41 @@ def test_without_aabbs_and_empty_input(gpu_ctx):
     bad = (np.array([1000], dtype=np.uint32),) * 4
     with pytest.raises(api.AvianError):
         gpu_ctx.narrow_phase(1.0 / 60.0, 0.005, bad, cols, lv, av)
+
+
+# ---- the solver fed from edge-indexed storage --------------------------------------------------------------------------------
+def test_solver_from_edge_indexed_manifolds_equals_the_csr_input(gpu_ctx):
+    """avn_solver_upload_edges: the same manifolds scattered over ContactId-indexed rows (4 slots per edge, gaps, arbitrary ids) and
+    listed colour by colour give the step of the CSR input bit for bit; impulses come back in the edges' slots, rows of edges that are
+    not in the graph keep their values."""
+    from avian_b200 import scenes
+    from helpers import advance_to_solver_input
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(6, 4, 5, brick=True), steps=3, substeps=4)
+    bs, ms = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, bs, ms)
+    M = m.count
+    rng = np.random.default_rng(0)
+    E = 3 * M + 17
+    edge = rng.permutation(E)[:M].astype(np.uint32)            # arbitrary ContactIds with gaps
+    s = b.position.dtype
+    cnt = np.diff(m.point_offsets.astype(np.int64))
+    slot = np.arange(4)[None, :] < cnt[:, None]
+    edges = {"point_count": np.zeros(E, dtype=np.uint8), "normal": np.zeros((E, 3), dtype=s), "anchor1": np.zeros((E, 4, 3), dtype=s),
+             "anchor2": np.zeros((E, 4, 3), dtype=s), "penetration": np.zeros((E, 4), dtype=s), "normal_speed": np.zeros((E, 4), dtype=s),
+             "warm_start_normal_impulse": np.full((E, 4), 7.0, dtype=s), "warm_start_tangent_impulse": np.full((E, 4, 2), 7.0, dtype=s),
+             "normal_impulse": np.full((E, 4), 7.0, dtype=s)}
+    edges["point_count"][edge] = cnt
+    edges["normal"][edge] = m.normal
+    for k in ("anchor1", "anchor2", "penetration", "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse"):
+        rows = edges[k][edge]
+        rows[slot] = getattr(m, k)
+        edges[k][edge] = rows
+    graph = {"color_offsets": m.color_offsets, "edge": edge, "body1": m.body1, "body2": m.body2, "friction": m.friction, "restitution": m.restitution}
+    be = b.copy()
+    gpu_ctx.solver_step_edges(prm, be, graph, edges)
+    for k in ("position", "rotation", "linear_velocity", "angular_velocity"):
+        assert np.array_equal(getattr(be, k), getattr(bs, k)), k
+    for k in ("warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse"):
+        assert np.array_equal(edges[k][edge][slot], getattr(ms, k)), k
+    untouched = np.ones(E, dtype=bool); untouched[edge] = False
+    assert (edges["warm_start_normal_impulse"][untouched] == 7.0).all() and (edges["normal_impulse"][untouched] == 7.0).all()
