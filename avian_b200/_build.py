@@ -16,7 +16,7 @@ LIB_DIR = ROOT / "lib"
 CUDA_LIB = LIB_DIR / "libavian_b200.so"
 HOST_LIB = LIB_DIR / "libavian_host.so"
 
-CUDA_SOURCES = ["abi.cu", "solver_host.cu", "broadphase.cu", "aabb.cu", "narrow.cu"]
+CUDA_SOURCES = ["abi.cu", "solver_host.cu", "broadphase.cu", "aabb.cu", "narrow.cu", "contacts.cu"]
 CUDA_HEADERS = ["avn_math.cuh", "solver_dev.cuh", "joints_dev.cuh", "solver_kernels.cuh", "context.hpp", "joint_schedule.hpp", "broadphase_cells.cuh", "narrow_math.hpp"]
 # -fmad=false: the reference (Rust) never contracts a*b+c; parity at 1e-5 on contact dynamics needs the same
 # rounding.  Division and sqrt stay IEEE (nvcc defaults -prec-div=true -prec-sqrt=true).

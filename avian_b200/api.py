@@ -365,6 +365,12 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "get_stream": ([_vp, P(_vp)], C.c_int),
         "narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), P(AvnRawManifolds)], C.c_int),
         "solver_upload_edges": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
+        "solver_upload_graph": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
+        "contacts_reserve": ([_vp, C.c_uint32], C.c_int),
+        "contacts_add": ([_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp], C.c_int),
+        "contacts_remove": ([_vp, C.c_uint32, _vp], C.c_int),
+        "contacts_narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), C.c_uint32, C.c_double, _vp, _vp], C.c_int),
+        "contacts_download_impulses": ([_vp, _vp, _vp, _vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -376,7 +382,8 @@ ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
-    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase", "avn_solver_upload_edges"]
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
+    "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 BOUNDARY_RECORD_SCALARS = 16
@@ -606,6 +613,56 @@ class Context:
         self._check(self.lib.avn_solver_upload_edges(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
         self._check(self.lib.avn_solver_run(self.handle))
         self._check(self.lib.avn_solver_download(self.handle))
+
+    # ---- device-resident contact edges (include/avian_b200.h)
+    def contacts_reserve(self, capacity: int) -> None:
+        self._check(self.lib.avn_contacts_reserve(self.handle, int(capacity)))
+
+    def contacts_add(self, ids, c1, c2, b1, b2) -> None:
+        a = [np.ascontiguousarray(x, dtype=np.uint32) for x in (ids, c1, c2, b1, b2)]
+        self._check(self.lib.avn_contacts_add(self.handle, int(a[0].shape[0]), *(x.ctypes.data for x in a)))
+
+    def contacts_remove(self, ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self.lib.avn_contacts_remove(self.handle, int(ids.shape[0]), ids.ctypes.data))
+
+    def contacts_narrow_phase(self, dt: float, contact_tolerance: float, colliders: dict, lin_vel, ang_vel, capacity: int, match_contacts: bool = True,
+                              length_unit: float = 1.0):
+        """Geometry + match_contacts for every live row.  Returns (point_count[capacity], disjoint[capacity])."""
+        dt_ = self.scalar
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+        inp = AvnNarrowInput(0, int(cols["position"].shape[0]), int(lv.shape[0]), 0, None, None, None, None, _ptr(cols["shape"]), _ptr(cols["dims"]),
+                             _ptr(cols["position"]), _ptr(cols["rotation"]), _ptr(lv), _ptr(av), _ptr(cols["aabb_min"]), _ptr(cols["aabb_max"]))
+        count, disjoint = np.zeros(capacity, dtype=np.uint8), np.zeros(capacity, dtype=np.uint8)
+        prm = AvnNarrowParams(float(dt), float(contact_tolerance))
+        self._check(self.lib.avn_contacts_narrow_phase(self.handle, C.byref(prm), C.byref(inp), 1 if match_contacts else 0, float(length_unit),
+                                                       count.ctypes.data, disjoint.ctypes.data))
+        return count, disjoint
+
+    def solver_step_graph(self, params, bodies: Bodies, graph: dict, joints: JointSet | None = None) -> None:
+        """avn_solver_upload_graph + run + download: the manifolds come from the resident rows, graph = dict(color_offsets, edge, body1, body2,
+        friction, restitution)."""
+        b = bodies.as_struct()
+        j = joints.as_struct() if joints is not None and joints.count else None
+        em = AvnEdgeManifolds()
+        em.count = int(graph["edge"].shape[0])
+        for i in range(GRAPH_COLOR_COUNT + 1):
+            em.color_offsets[i] = int(graph["color_offsets"][i])
+        keep = [np.ascontiguousarray(graph["edge"], dtype=np.uint32), np.ascontiguousarray(graph["body1"], dtype=np.int32),
+                np.ascontiguousarray(graph["body2"], dtype=np.int32), np.ascontiguousarray(graph["friction"], dtype=self.scalar),
+                np.ascontiguousarray(graph["restitution"], dtype=self.scalar)]
+        em.edge, em.body1, em.body2, em.friction, em.restitution = (x.ctypes.data for x in keep)
+        self._keep = (params, bodies, graph, joints, b, em, j, keep)
+        self._check(self.lib.avn_solver_upload_graph(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
+        self._check(self.lib.avn_solver_run(self.handle))
+        self._check(self.lib.avn_solver_download(self.handle))
+
+    def contacts_download_impulses(self, capacity: int):
+        wn, wt, ni = (np.zeros((capacity, 4), dtype=self.scalar), np.zeros((capacity, 4, 2), dtype=self.scalar), np.zeros((capacity, 4), dtype=self.scalar))
+        self._check(self.lib.avn_contacts_download_impulses(self.handle, wn.ctypes.data, wt.ctypes.data, ni.ctypes.data))
+        return wn, wt, ni
 
     def narrow_phase(self, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray) -> dict:
         """avn_narrow_phase: pairs = (collider1, collider2, body1, body2) uint32 arrays; colliders = dict(shape, dims, position, rotation,

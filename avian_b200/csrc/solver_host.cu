@@ -66,6 +66,7 @@ class Solver final : public SolverBase {
 
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
     AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) override;
+    AvnStatus upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* graph, ContactsBase* contacts, AvnJointSet* js) override;
     AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) override;
     AvnStatus set_boundary(const AvnBoundary* bnd) override;
     AvnStatus boundary_snapshot() override;
@@ -164,6 +165,10 @@ class Solver final : public SolverBase {
         const uint32_t* edge = nullptr; const uint8_t* edge_point_count = nullptr;   // edge-indexed
         const void* anchor1 = nullptr; const void* anchor2 = nullptr; const void* penetration = nullptr; const void* normal_speed = nullptr;
         void* ws_normal = nullptr; void* ws_tangent = nullptr; void* normal_impulse = nullptr;
+        // device == true: the edge-indexed columns above (point counts, normal, point columns, impulse inputs) are DEVICE pointers owned by the
+        // contact store, and store_contact_impulses writes to out_* (device) instead of buffers of this solver; nothing of them is copied
+        bool device = false;
+        void* out_ws_normal = nullptr; void* out_ws_tangent = nullptr; void* out_normal_impulse = nullptr;
     };
     AvnStatus upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* src, AvnJointSet* js);
     ManifoldSource hm_{};
@@ -230,6 +235,29 @@ AvnStatus Solver<S>::upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, 
     src.normal = em->normal; src.edge = em->edge; src.edge_point_count = em->point_count;
     src.anchor1 = em->anchor1; src.anchor2 = em->anchor2; src.penetration = em->penetration; src.normal_speed = em->normal_speed;
     src.ws_normal = em->warm_start_normal_impulse; src.ws_tangent = em->warm_start_tangent_impulse; src.normal_impulse = em->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* g, ContactsBase* contacts, AvnJointSet* js) {
+    if (!g || g->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!contacts) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "upload_graph: no contact store");
+    if (!g->edge || !g->body1 || !g->body2 || !g->friction || !g->restitution)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge, body1, body2, friction and restitution are required");
+    AvnEdgeManifolds v{};
+    AvnStatus st = contacts->view(&v);
+    if (st != AVN_OK) return st;
+    for (size_t m = 0; m < g->count; ++m)
+        if (g->edge[m] >= v.edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge[%zu] = %u >= capacity %u", m, g->edge[m], v.edge_capacity);
+    ManifoldSource src;
+    src.M = g->count; src.P = size_t(4) * v.edge_capacity; src.normal_rows = v.edge_capacity;
+    src.color_offsets = g->color_offsets; src.body1 = g->body1; src.body2 = g->body2; src.friction = g->friction; src.restitution = g->restitution;
+    src.edge = g->edge;
+    src.device = true;
+    src.normal = v.normal; src.edge_point_count = v.point_count;
+    src.anchor1 = v.anchor1; src.anchor2 = v.anchor2; src.penetration = v.penetration; src.normal_speed = v.normal_speed;
+    src.ws_normal = v.warm_start_normal_impulse; src.ws_tangent = v.warm_start_tangent_impulse; src.normal_impulse = v.normal_impulse;
+    contacts->outputs(&src.out_ws_normal, &src.out_ws_tangent, &src.out_normal_impulse);
     return upload_impl(prm, bc, &src, js);
 }
 
@@ -331,6 +359,8 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
                     const uint32_t n = po[i + 1] - po[i];
                     widest = n > widest ? n : widest;
                 }
+            } else if (mc->device) {
+                widest = AVN_MAX_MANIFOLD_POINTS;   // the counts live on the device: take the general kernel build
             } else {
                 for (size_t i = 0; i < M; ++i) {
                     const uint32_t n = mc->edge_point_count[mc->edge[i]];
@@ -357,7 +387,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         }
         UP(m_b1_, mc->body1, M, int, m_body1);
         UP(m_b2_, mc->body2, M, int, m_body2);
-        UP(m_n_, mc->normal, 3 * mc->normal_rows, S, m_normal);
+        if (mc->device) d.m_normal = static_cast<const S*>(mc->normal); else UP(m_n_, mc->normal, 3 * mc->normal_rows, S, m_normal);
         UP(m_f_, mc->friction, M, S, m_friction);
         UP(m_r_, mc->restitution, M, S, m_restitution);
         UP(m_tv_, mc->tangent_velocity, 3 * M, S, m_tanvel);
@@ -368,7 +398,8 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         } else {
             const uint8_t* d_count = nullptr;
             UP(m_edge_, mc->edge, M, uint32_t, m_src);
-            if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
+            if (mc->device) d_count = mc->edge_point_count;
+            else if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
             AVN_CUDA(m_pbegin_.ensure(M * sizeof(uint32_t)));
             AVN_CUDA(m_pend_.ensure(M * sizeof(uint32_t)));
             edge_ranges_kernel<<<unsigned((M + 255) / 256), 256, 0, stream_>>>(d.m_src, d_count, int(M), m_pbegin_.as<uint32_t>(), m_pend_.as<uint32_t>());
@@ -376,24 +407,33 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             d.m_point_begin = m_pbegin_.as<uint32_t>();
             d.m_point_end = m_pend_.as<uint32_t>();
         }
-        UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
-        UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
-        UP(p_pen_, mc->penetration, P, S, p_penetration);
-        UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
-        // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
-        UP(p_wn_, mc->ws_normal, P, S, p_ws_normal);
-        UP(p_wt_, mc->ws_tangent, 2 * P, S, p_ws_tangent);
-        UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
-        AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
-        AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
-        AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
-        d.p_normal_impulse = p_ni_.as<S>();
-        if (!mc->point_offsets) {
-            // edge-indexed: rows of edges that are not in the constraint graph are not written by store_contact_impulses; they keep their
-            // input values (the reference leaves such ContactPoints untouched)
-            AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_normal, d.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
-            AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_tangent, d.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
-            AVN_CUDA(cudaMemcpyAsync(d.p_normal_impulse, d.p_in_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+        if (mc->device) {
+            d.p_anchor1 = static_cast<const S*>(mc->anchor1); d.p_anchor2 = static_cast<const S*>(mc->anchor2);
+            d.p_penetration = static_cast<const S*>(mc->penetration); d.p_normal_speed = static_cast<const S*>(mc->normal_speed);
+            d.p_ws_normal = static_cast<const S*>(mc->ws_normal); d.p_ws_tangent = static_cast<const S*>(mc->ws_tangent);
+            d.p_in_normal_impulse = static_cast<const S*>(mc->normal_impulse);
+            d.p_out_ws_normal = static_cast<S*>(mc->out_ws_normal); d.p_out_ws_tangent = static_cast<S*>(mc->out_ws_tangent);
+            d.p_normal_impulse = static_cast<S*>(mc->out_normal_impulse);
+        } else {
+            UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
+            UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
+            UP(p_pen_, mc->penetration, P, S, p_penetration);
+            UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
+            // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
+            UP(p_wn_, mc->ws_normal, P, S, p_ws_normal);
+            UP(p_wt_, mc->ws_tangent, 2 * P, S, p_ws_tangent);
+            UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
+            AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
+            AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
+            AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
+            d.p_normal_impulse = p_ni_.as<S>();
+            if (!mc->point_offsets) {
+                // edge-indexed: rows of edges that are not in the constraint graph are not written by store_contact_impulses; they keep their
+                // input values (the reference leaves such ContactPoints untouched)
+                AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_normal, d.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+                AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_tangent, d.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+                AVN_CUDA(cudaMemcpyAsync(d.p_normal_impulse, d.p_in_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+            }
         }
 
         hm_ = *mc;
@@ -720,7 +760,7 @@ AvnStatus Solver<S>::download() {
         AVN_CUDA(cudaMemcpyAsync(hb_.linear_velocity, dev_.out_linvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hb_.angular_velocity, dev_.out_angvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
-    if (have_m_) {
+    if (have_m_ && !hm_.device) {
         const size_t P = hm_.P;
         AVN_CUDA(cudaMemcpyAsync(hm_.ws_normal, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hm_.ws_tangent, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));

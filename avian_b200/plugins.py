@@ -257,3 +257,51 @@ class ResidentWorld(World):
             wt[self._slot] = m.warm_start_tangent_impulse
             self.e_ws_n[self._edges] = wn
             self.e_ws_t[self._edges] = wt
+
+
+class DeviceResidentWorld(World):
+    """The resident protocol with the device doing its part (ResidentWorld is the CPU specification): contact rows, manifolds and warm-start
+    impulses live in the library's contact store; per step the host sends the contact-graph changes (new / removed edges), receives one
+    point count and one disjoint flag per row, updates its graphs and sends the colour-major edge list; avn_solver_upload_graph reads the
+    manifolds where avn_contacts_narrow_phase left them."""
+
+    def __init__(self, scene: Scene, plugins: PhysicsPlugins, ctx: "api.Context", **kw):
+        super().__init__(scene, plugins, **kw)
+        self.ctx = ctx
+        self.capacity = 0
+        self.known = {}          # ContactId -> pair key of the row on the device
+        self.bytes_to_host = self.bytes_to_device = 0
+
+    def narrow_phase(self):
+        p, b, s = self.pipeline, self.bodies, self.scalar
+        ids, c1, c2, b1, b2 = p.active_edges()
+        need = int(ids.max()) + 1 if ids.size else 0
+        if need > self.capacity:
+            self.capacity = max(1024, 2 * need)
+            self.ctx.contacts_reserve(self.capacity)
+        # contact-graph changes since the last step
+        key = (c1.astype(np.uint64) << np.uint64(32)) | c2.astype(np.uint64)
+        now = dict(zip(ids.tolist(), key.tolist()))
+        gone = [e for e in self.known if e not in now]
+        fresh = np.array([i for i, (e, k) in enumerate(now.items()) if self.known.get(e) != k], dtype=np.int64)
+        if gone:
+            self.ctx.contacts_remove(np.array(gone, dtype=np.uint32))
+        if fresh.size:
+            self.ctx.contacts_add(ids[fresh], c1[fresh], c2[fresh], b1[fresh], b2[fresh])
+        self.known = now
+        colliders = {"shape": self.scene.shape_type.astype(np.uint8), "dims": np.asarray(self.scene.dims, dtype=s), "position": b.position,
+                     "rotation": b.rotation, "aabb_min": self.aabb_min, "aabb_max": self.aabb_max}
+        count, disjoint = self.ctx.contacts_narrow_phase(self.params.dt, 0.005, colliders, b.linear_velocity, b.angular_velocity, self.capacity,
+                                                         bool(self.params.match_contacts))
+        self.bytes_to_host = 2 * self.capacity
+        self.bytes_to_device = 20 * int(fresh.size) + 4 * len(gone)
+        m, npts = p.apply_counts(b, ids, count[ids], disjoint[ids])
+        co, edge, eb1, eb2, fr, re = p.export_edges(m)
+        self.bytes_to_device += 4 * m
+        self.graph = {"color_offsets": co, "edge": edge, "body1": eb1, "body2": eb2, "friction": fr.astype(s), "restitution": re.astype(s)}
+        self.last_counts = count
+        self.last_manifolds = None
+        return self.graph
+
+    def solve(self) -> None:
+        self.ctx.solver_step_graph(self.params, self.bodies, self.graph, self.joints)

@@ -437,6 +437,23 @@ typedef struct AvnRawManifolds {      /* fixed stride: 4 point slots per pair, u
 
 AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out);
 
+/* ---- device-resident contact edges: the contact pairs, their manifolds and warm-start impulses stay on the device between steps; the host
+ *      keeps the ContactGraph and the ConstraintGraph (contact_graph.rs, constraint_graph.rs) and exchanges a few bytes per edge with the
+ *      device (protocol and its CPU specification: avian_b200/plugins.py ResidentWorld).  Row = ContactId. ---------------------------------- */
+AvnStatus avn_contacts_reserve(AvnContext* ctx, uint32_t capacity);                  /* rows; grows, keeps the existing rows */
+AvnStatus avn_contacts_add(AvnContext* ctx, uint32_t n, const uint32_t* ids, const uint32_t* collider1, const uint32_t* collider2,
+                           const uint32_t* body1, const uint32_t* body2);            /* ContactGraph::add_edge: the row starts without history */
+AvnStatus avn_contacts_remove(AvnContext* ctx, uint32_t n, const uint32_t* ids);     /* ContactGraph::remove_edge */
+/* Geometry + match_contacts for every live row (input: only the collider / body columns of AvnNarrowInput; the pair arrays are ignored).
+ * out_point_count / out_disjoint: [capacity] host arrays — all the host needs for the touching state machine and the graphs. */
+AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts,
+                                    double length_unit, uint8_t* out_point_count, uint8_t* out_disjoint);
+/* The solver stage reading its manifolds from the resident rows: `graph` carries only count, color_offsets, edge, body1, body2, friction,
+ * restitution (host); store_contact_impulses writes into the rows.  Then avn_solver_run / avn_solver_download (bodies only) as usual. */
+AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints);
+/* the impulses of the rows as the last solve left them (tests, tools): [capacity][4], [capacity][4][2], [capacity][4]; any may be NULL */
+AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse);
+
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
 /*

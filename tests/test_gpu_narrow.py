@@ -97,3 +97,41 @@ def test_solver_from_edge_indexed_manifolds_equals_the_csr_input(gpu_ctx):
         assert np.array_equal(edges[k][edge][slot], getattr(ms, k)), k
     untouched = np.ones(E, dtype=bool); untouched[edge] = False
     assert (edges["warm_start_normal_impulse"][untouched] == 7.0).all() and (edges["normal_impulse"][untouched] == 7.0).all()
+
+
+# ---- the whole resident protocol on the device -----------------------------------------------------------------------------------
+def _tumble(w):
+    rng = np.random.default_rng(5)
+    w.bodies.angular_velocity[1:] = rng.normal(0, 3.0, size=(w.bodies.count - 1, 3)).astype(w.bodies.angular_velocity.dtype)
+    w.bodies.linear_velocity[1:] = rng.normal(0, 1.5, size=(w.bodies.count - 1, 3)).astype(w.bodies.linear_velocity.dtype)
+
+
+@pytest.mark.parametrize("scene_fn,steps,substeps,kick", [
+    (lambda: __import__("avian_b200.scenes", fromlist=["x"]).cubes_example(4), 120, 6, True),          # pairs come and go, ContactIds are reused
+    (lambda: __import__("avian_b200.scenes", fromlist=["x"]).cube_stack(6, 5, 5, brick=True), 25, 4, False),
+    (lambda: __import__("avian_b200.scenes", fromlist=["x"]).ragdoll_field(9, pitch=1.2, drop_height=0.5), 40, 4, False),
+])
+def test_device_resident_world_equals_the_ordinary_world(gpu_ctx, scene_fn, steps, substeps, kick):
+    """Bodies of the device-resident pipeline vs the ordinary GPU world (host narrow phase, CSR upload), step after step, bit for bit;
+    the resident rows' impulses equal the ordinary world's manifold columns; a few bytes per edge cross the bus."""
+    from avian_b200 import plugins
+    wa = plugins.World(scene_fn(), plugins.PhysicsPlugins(gpu_ctx), substeps=substeps)
+    with api.Context(device=0, scalar=wa.scalar) as ctx_b:
+        wb = plugins.DeviceResidentWorld(scene_fn(), plugins.PhysicsPlugins(ctx_b), ctx_b, substeps=substeps)
+        if kick:
+            _tumble(wa); _tumble(wb)
+        for i in range(steps):
+            wa.broad_phase(); wb.broad_phase()
+            ma, gb = wa.narrow_phase(), wb.narrow_phase()
+            assert ma.count == gb["edge"].shape[0], f"step {i}: manifold count"
+            assert np.array_equal(ma.color_offsets, gb["color_offsets"]) and np.array_equal(ma.body1, gb["body1"]), f"step {i}: graph"
+            wa.solve(); wb.solve()
+            for k in ("position", "rotation", "linear_velocity", "angular_velocity"):
+                assert np.array_equal(getattr(wa.bodies, k), getattr(wb.bodies, k)), f"step {i}: {k}"
+            if ma.count:
+                wn, wt, ni = ctx_b.contacts_download_impulses(wb.capacity)
+                cnt = np.diff(ma.point_offsets.astype(np.int64))
+                slot = np.arange(4)[None, :] < cnt[:, None]
+                assert np.array_equal(wn[gb["edge"]][slot], ma.warm_start_normal_impulse), f"step {i}: impulses"
+                assert np.array_equal(ni[gb["edge"]][slot], ma.normal_impulse), f"step {i}: total impulses"
+        assert wb.bytes_to_host <= 2 * wb.capacity
