@@ -62,3 +62,95 @@ def test_spheres(scalar):
 
 def test_ragdolls_with_joints():
     run_both(lambda: scenes.ragdoll_field(9, pitch=1.2, drop_height=0.5), 50)
+
+
+class MockContactStore:
+    """CPU stand-in for the library's contact store + avn_solver_upload_graph (same calls as api.Context): numpy rows, the fixture's
+    geometry and matching, the oracle as the solver.  It lets DeviceResidentWorld's host logic (edge deltas, capacity growth, graph
+    hand-over) run on the CPU against the ordinary World."""
+
+    def __init__(self, scalar):
+        from avian_b200 import fixture
+        self.fixture, self.scalar, self.E = fixture, np.dtype(scalar), 0
+        self.rows = {}
+
+    def contacts_reserve(self, capacity):
+        s = self.scalar
+        shapes = {"c1": ((), np.uint32), "c2": ((), np.uint32), "b1": ((), np.uint32), "b2": ((), np.uint32), "live": ((), np.uint8), "count": ((), np.uint8),
+                  "normal": ((3,), s), "anchor1": ((4, 3), s), "anchor2": ((4, 3), s), "penetration": ((4,), s), "normal_speed": ((4,), s),
+                  "prev_count": ((), np.uint8), "prev_a1": ((4, 3), np.float64), "prev_a2": ((4, 3), np.float64), "ws_n": ((4,), s), "ws_t": ((4, 2), s),
+                  "nimp": ((4,), s)}
+        for k, (shape, dt) in shapes.items():
+            new = np.zeros((capacity,) + shape, dtype=dt)
+            if k in self.rows:
+                new[:self.E] = self.rows[k]
+            self.rows[k] = new
+        self.E = capacity
+
+    def contacts_add(self, ids, c1, c2, b1, b2):
+        r = self.rows
+        r["c1"][ids], r["c2"][ids], r["b1"][ids], r["b2"][ids] = c1, c2, b1, b2
+        r["live"][ids] = 1; r["count"][ids] = 0; r["prev_count"][ids] = 0
+
+    def contacts_remove(self, ids):
+        r = self.rows
+        r["live"][ids] = 0; r["count"][ids] = 0; r["prev_count"][ids] = 0
+
+    def contacts_narrow_phase(self, dt, tol, colliders, lv, av, capacity, match_contacts=True, length_unit=1.0):
+        r = self.rows
+        live = np.nonzero(r["live"])[0].astype(np.uint32)
+        raw = self.fixture.raw_manifolds(self.scalar, dt, tol, (r["c1"][live], r["c2"][live], r["b1"][live], r["b2"][live]), colliders, lv, av, f64_anchors=True)
+        count, disjoint = np.zeros(capacity, dtype=np.uint8), np.zeros(capacity, dtype=np.uint8)
+        count[live], disjoint[live] = raw["point_count"], raw["disjoint"]
+        r["count"][:] = 0
+        r["count"][live] = raw["point_count"]
+        for k in ("normal", "anchor1", "anchor2", "penetration", "normal_speed"):
+            r[k][live] = raw[k]
+        lib = self.fixture._load()
+        lib.avh_match_raw(32 if self.scalar == np.float32 else 64, int(live.shape[0]), live.ctypes.data, raw["point_count"].ctypes.data,
+                          raw["anchor1_f64"].ctypes.data, raw["anchor2_f64"].ctypes.data, float(length_unit), 1 if match_contacts else 0,
+                          r["prev_count"].ctypes.data, r["prev_a1"].ctypes.data, r["prev_a2"].ctypes.data, r["ws_n"].ctypes.data, r["ws_t"].ctypes.data)
+        return count, disjoint
+
+    def solver_step_graph(self, params, bodies, graph, joints=None):
+        from avian_b200 import api
+        r, s, edge = self.rows, self.scalar, graph["edge"]
+        cnt = r["count"][edge].astype(np.int64)
+        slot = np.arange(4)[None, :] < cnt[:, None]
+        take = lambda a: np.ascontiguousarray(a[edge][slot])
+        po = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
+        man = api.Manifolds(color_offsets=graph["color_offsets"], body1=graph["body1"], body2=graph["body2"], normal=np.ascontiguousarray(r["normal"][edge]),
+                            friction=graph["friction"], restitution=graph["restitution"], point_offsets=po, anchor1=take(r["anchor1"]), anchor2=take(r["anchor2"]),
+                            penetration=take(r["penetration"]), normal_speed=take(r["normal_speed"]), warm_start_normal_impulse=take(r["ws_n"]),
+                            warm_start_tangent_impulse=take(r["ws_t"]), normal_impulse=np.zeros(int(po[-1]), dtype=s)) if edge.size else None
+        oracle_lib.solver_step(params, bodies, man, joints, threads=2)
+        if man is not None:
+            for name, col in (("ws_n", man.warm_start_normal_impulse), ("ws_t", man.warm_start_tangent_impulse), ("nimp", man.normal_impulse)):
+                rows = r[name][edge]
+                rows[slot] = col
+                r[name][edge] = rows
+
+
+@pytest.mark.parametrize("scene_fn,steps,substeps,kick", [
+    (lambda: scenes.cubes_example(4), 120, 6, _tumble),
+    (lambda: scenes.cube_stack(5, 4, 4, brick=True), 20, 4, None),
+    (lambda: scenes.ragdoll_field(6, pitch=1.2, drop_height=0.5), 40, 4, None),
+])
+def test_device_resident_world_host_logic_with_a_cpu_contact_store(scene_fn, steps, substeps, kick):
+    wa = plugins.World(scene_fn(), oracle_lib.oracle_plugins(threads=2), substeps=substeps)
+    wb = plugins.DeviceResidentWorld(scene_fn(), oracle_lib.oracle_plugins(threads=2), MockContactStore(wa.scalar), substeps=substeps)
+    if kick:
+        kick(wa); kick(wb)
+    added = removed = 0
+    for i in range(steps):
+        wa.broad_phase(); wb.broad_phase()
+        before = dict(wb.known)
+        ma, gb = wa.narrow_phase(), wb.narrow_phase()
+        added += sum(1 for e, k in wb.known.items() if before.get(e) != k)
+        removed += sum(1 for e in before if e not in wb.known)
+        assert ma.count == gb["edge"].shape[0] and np.array_equal(ma.color_offsets, gb["color_offsets"]), f"step {i}"
+        wa.solve(); wb.solve()
+        assert np.array_equal(wa.bodies.position, wb.bodies.position) and np.array_equal(wa.bodies.linear_velocity, wb.bodies.linear_velocity), f"step {i}"
+    assert added > 0
+    if kick:
+        assert removed > 0          # pairs really were dropped and ContactIds reused
