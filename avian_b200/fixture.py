@@ -43,6 +43,8 @@ def _load():
         lib.avh_export_edges.restype = None
         lib.avh_match_raw.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.c_double, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
         lib.avh_match_raw.restype = None
+        lib.avh_rows_narrow.argtypes = [C.c_uint32, C.c_uint32] + [_vp] * 27 + [C.c_double, C.c_double, C.c_double, C.c_uint32]
+        lib.avh_rows_narrow.restype = None
         lib.avh_raw_manifolds.restype = None
         lib.avh_pair_count.argtypes = [_vp]
         lib.avh_pair_count.restype = C.c_uint32

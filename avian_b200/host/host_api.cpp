@@ -19,6 +19,7 @@
 
 #include "../../include/avian_b200.h"
 #include "../csrc/narrow_math.hpp"
+#include "../csrc/contact_rows.hpp"
 
 namespace {
 
@@ -133,6 +134,26 @@ void pop_manifold(Pipeline& P, uint32_t id) {
         auto mh = c.handles[h.local];
         P.pairs[mh.first].handles[mh.second].local = h.local;
     }
+}
+
+// The row function of the device-resident contact store (csrc/contact_rows.hpp, what csrc/contacts.cu runs one thread per row) over host
+// arrays: every live row gets its manifold, matched impulses and history exactly as on the device.  Column layouts as in contacts.cu.
+template <class T>
+static void rows_narrow(uint32_t E, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2, uint8_t* live, uint8_t* count, uint8_t* disjoint, void* normal, void* a1,
+                        void* a2, void* pen, void* ns, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n_in, void* ws_t_in, void* ws_n_out,
+                        void* ws_t_out, const uint8_t* shape, const void* dims, const void* pos, const void* rot, const void* lv, const void* av,
+                        const void* amin, const void* amax, double dt, double tol, double length_unit, uint32_t match) {
+    avn::NarrowEdgeArgs<T> a{};
+    a.r.E = int(E);
+    a.r.c1 = c1; a.r.c2 = c2; a.r.b1 = b1; a.r.b2 = b2; a.r.live = live; a.r.count = count; a.r.disjoint = disjoint;
+    a.r.normal = static_cast<T*>(normal); a.r.a1 = static_cast<T*>(a1); a.r.a2 = static_cast<T*>(a2); a.r.pen = static_cast<T*>(pen); a.r.ns = static_cast<T*>(ns);
+    a.r.prev_count = prev_count; a.r.prev_a1 = prev_a1; a.r.prev_a2 = prev_a2;
+    a.r.ws_n_in = static_cast<T*>(ws_n_in); a.r.ws_t_in = static_cast<T*>(ws_t_in); a.r.ws_n_out = static_cast<T*>(ws_n_out); a.r.ws_t_out = static_cast<T*>(ws_t_out);
+    a.r.nimp_in = nullptr; a.r.nimp_out = nullptr;
+    a.shape = shape; a.dims = static_cast<const T*>(dims); a.pos = static_cast<const T*>(pos); a.rot = static_cast<const T*>(rot);
+    a.lv = static_cast<const T*>(lv); a.av = static_cast<const T*>(av); a.amin = static_cast<const T*>(amin); a.amax = static_cast<const T*>(amax);
+    a.dt = dt; a.tol = tol; a.thr2 = (0.1 * length_unit) * (0.1 * length_unit); a.match = match ? 1 : 0;
+    for (uint32_t e = 0; e < E; ++e) avn::narrow_edge_row<T>(a, int(e));
 }
 
 }  // namespace
@@ -536,6 +557,19 @@ void avh_match_raw(uint32_t scalar_bits, uint32_t n, const uint32_t* ids, const 
         }
         prev_count[e] = uint8_t(nc);
     }
+}
+
+// csrc/contact_rows.hpp over host arrays (see rows_narrow above)
+void avh_rows_narrow(uint32_t scalar_bits, uint32_t E, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2, uint8_t* live, uint8_t* count, uint8_t* disjoint,
+                     void* normal, void* a1, void* a2, void* pen, void* ns, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n_in, void* ws_t_in,
+                     void* ws_n_out, void* ws_t_out, const uint8_t* shape, const void* dims, const void* pos, const void* rot, const void* lv, const void* av,
+                     const void* amin, const void* amax, double dt, double tol, double length_unit, uint32_t match) {
+    if (scalar_bits == 64)
+        rows_narrow<double>(E, c1, c2, b1, b2, live, count, disjoint, normal, a1, a2, pen, ns, prev_count, prev_a1, prev_a2, ws_n_in, ws_t_in, ws_n_out, ws_t_out,
+                            shape, dims, pos, rot, lv, av, amin, amax, dt, tol, length_unit, match);
+    else
+        rows_narrow<float>(E, c1, c2, b1, b2, live, count, disjoint, normal, a1, a2, pen, ns, prev_count, prev_a1, prev_a2, ws_n_in, ws_t_in, ws_n_out, ws_t_out,
+                           shape, dims, pos, rot, lv, av, amin, amax, dt, tol, length_unit, match);
 }
 
 uint32_t avh_pair_count(AvhPipeline* h) { return uint32_t(reinterpret_cast<Pipeline*>(h)->active.size()); }

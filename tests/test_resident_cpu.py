@@ -65,9 +65,15 @@ def test_ragdolls_with_joints():
 
 
 class MockContactStore:
-    """CPU stand-in for the library's contact store + avn_solver_upload_graph (same calls as api.Context): numpy rows, the fixture's
-    geometry and matching, the oracle as the solver.  It lets DeviceResidentWorld's host logic (edge deltas, capacity growth, graph
-    hand-over) run on the CPU against the ordinary World."""
+    """CPU stand-in for the library's contact store + avn_solver_upload_graph (same calls as api.Context).  The rows are numpy arrays with
+    the device's column layout, and the per-row work is the DEVICE's row function (csrc/contact_rows.hpp through avh_rows_narrow): what the
+    kernel of csrc/contacts.cu runs one thread per row runs here in a loop.  The oracle stands in for the solver; like the device it reads the
+    rows' `in` impulses and writes the `out` ones.  It lets DeviceResidentWorld run on the CPU against the ordinary World."""
+
+    COLUMNS = {"c1": ((), np.uint32), "c2": ((), np.uint32), "b1": ((), np.uint32), "b2": ((), np.uint32), "live": ((), np.uint8), "count": ((), np.uint8),
+               "disjoint": ((), np.uint8), "normal": ((3,), None), "anchor1": ((4, 3), None), "anchor2": ((4, 3), None), "penetration": ((4,), None),
+               "normal_speed": ((4,), None), "prev_count": ((), np.uint8), "prev_a1": ((4, 3), np.float64), "prev_a2": ((4, 3), np.float64),
+               "ws_n_in": ((4,), None), "ws_t_in": ((4, 2), None), "ws_n_out": ((4,), None), "ws_t_out": ((4, 2), None), "nimp_out": ((4,), None)}
 
     def __init__(self, scalar):
         from avian_b200 import fixture
@@ -75,42 +81,35 @@ class MockContactStore:
         self.rows = {}
 
     def contacts_reserve(self, capacity):
-        s = self.scalar
-        shapes = {"c1": ((), np.uint32), "c2": ((), np.uint32), "b1": ((), np.uint32), "b2": ((), np.uint32), "live": ((), np.uint8), "count": ((), np.uint8),
-                  "normal": ((3,), s), "anchor1": ((4, 3), s), "anchor2": ((4, 3), s), "penetration": ((4,), s), "normal_speed": ((4,), s),
-                  "prev_count": ((), np.uint8), "prev_a1": ((4, 3), np.float64), "prev_a2": ((4, 3), np.float64), "ws_n": ((4,), s), "ws_t": ((4, 2), s),
-                  "nimp": ((4,), s)}
-        for k, (shape, dt) in shapes.items():
-            new = np.zeros((capacity,) + shape, dtype=dt)
+        for k, (shape, dt) in self.COLUMNS.items():
+            new = np.zeros((capacity,) + shape, dtype=dt or self.scalar)
             if k in self.rows:
                 new[:self.E] = self.rows[k]
             self.rows[k] = new
         self.E = capacity
 
-    def contacts_add(self, ids, c1, c2, b1, b2):
+    def contacts_add(self, ids, c1, c2, b1, b2):        # edge_add_kernel
         r = self.rows
         r["c1"][ids], r["c2"][ids], r["b1"][ids], r["b2"][ids] = c1, c2, b1, b2
         r["live"][ids] = 1; r["count"][ids] = 0; r["prev_count"][ids] = 0
 
-    def contacts_remove(self, ids):
+    def contacts_remove(self, ids):                      # edge_remove_kernel
         r = self.rows
         r["live"][ids] = 0; r["count"][ids] = 0; r["prev_count"][ids] = 0
 
     def contacts_narrow_phase(self, dt, tol, colliders, lv, av, capacity, match_contacts=True, length_unit=1.0):
-        r = self.rows
-        live = np.nonzero(r["live"])[0].astype(np.uint32)
-        raw = self.fixture.raw_manifolds(self.scalar, dt, tol, (r["c1"][live], r["c2"][live], r["b1"][live], r["b2"][live]), colliders, lv, av, f64_anchors=True)
-        count, disjoint = np.zeros(capacity, dtype=np.uint8), np.zeros(capacity, dtype=np.uint8)
-        count[live], disjoint[live] = raw["point_count"], raw["disjoint"]
-        r["count"][:] = 0
-        r["count"][live] = raw["point_count"]
-        for k in ("normal", "anchor1", "anchor2", "penetration", "normal_speed"):
-            r[k][live] = raw[k]
-        lib = self.fixture._load()
-        lib.avh_match_raw(32 if self.scalar == np.float32 else 64, int(live.shape[0]), live.ctypes.data, raw["point_count"].ctypes.data,
-                          raw["anchor1_f64"].ctypes.data, raw["anchor2_f64"].ctypes.data, float(length_unit), 1 if match_contacts else 0,
-                          r["prev_count"].ctypes.data, r["prev_a1"].ctypes.data, r["prev_a2"].ctypes.data, r["ws_n"].ctypes.data, r["ws_t"].ctypes.data)
-        return count, disjoint
+        r, s = self.rows, self.scalar
+        assert capacity == self.E
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else s)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lv, dtype=s), np.ascontiguousarray(av, dtype=s)
+        p = lambda a: None if a is None else a.ctypes.data
+        self.fixture._load().avh_rows_narrow(
+            32 if s == np.float32 else 64, self.E, p(r["c1"]), p(r["c2"]), p(r["b1"]), p(r["b2"]), p(r["live"]), p(r["count"]), p(r["disjoint"]), p(r["normal"]),
+            p(r["anchor1"]), p(r["anchor2"]), p(r["penetration"]), p(r["normal_speed"]), p(r["prev_count"]), p(r["prev_a1"]), p(r["prev_a2"]), p(r["ws_n_in"]),
+            p(r["ws_t_in"]), p(r["ws_n_out"]), p(r["ws_t_out"]), p(cols["shape"]), p(cols["dims"]), p(cols["position"]), p(cols["rotation"]), p(lv), p(av),
+            p(cols["aabb_min"]), p(cols["aabb_max"]), float(dt), float(tol), float(length_unit), 1 if match_contacts else 0)
+        return r["count"].copy(), r["disjoint"].copy()
 
     def solver_step_graph(self, params, bodies, graph, joints=None):
         from avian_b200 import api
@@ -121,11 +120,11 @@ class MockContactStore:
         po = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
         man = api.Manifolds(color_offsets=graph["color_offsets"], body1=graph["body1"], body2=graph["body2"], normal=np.ascontiguousarray(r["normal"][edge]),
                             friction=graph["friction"], restitution=graph["restitution"], point_offsets=po, anchor1=take(r["anchor1"]), anchor2=take(r["anchor2"]),
-                            penetration=take(r["penetration"]), normal_speed=take(r["normal_speed"]), warm_start_normal_impulse=take(r["ws_n"]),
-                            warm_start_tangent_impulse=take(r["ws_t"]), normal_impulse=np.zeros(int(po[-1]), dtype=s)) if edge.size else None
+                            penetration=take(r["penetration"]), normal_speed=take(r["normal_speed"]), warm_start_normal_impulse=take(r["ws_n_in"]),
+                            warm_start_tangent_impulse=take(r["ws_t_in"]), normal_impulse=np.zeros(int(po[-1]), dtype=s)) if edge.size else None
         oracle_lib.solver_step(params, bodies, man, joints, threads=2)
-        if man is not None:
-            for name, col in (("ws_n", man.warm_start_normal_impulse), ("ws_t", man.warm_start_tangent_impulse), ("nimp", man.normal_impulse)):
+        if man is not None:          # store_contact_impulses: the rows' `out` columns
+            for name, col in (("ws_n_out", man.warm_start_normal_impulse), ("ws_t_out", man.warm_start_tangent_impulse), ("nimp_out", man.normal_impulse)):
                 rows = r[name][edge]
                 rows[slot] = col
                 r[name][edge] = rows
