@@ -224,3 +224,39 @@ def test_cubes_simulation_is_locally_deterministic_reference_test():
     assert np.abs(runs[0][0][1:, 1]).max() < 12.0 and runs[0][0][1:, 1].min() > -1.0      # the pile is on the ground, nothing fell through
     for p, q in runs[1:]:
         assert np.array_equal(p, runs[0][0]) and np.array_equal(q, runs[0][1])
+
+
+def _two_bodies(mass=(1.0, 0.5), inertia=(1.0, 0.5)):
+    s = np.float32
+    n = len(mass)
+    inv_i = np.array([[1.0 / i, 0, 0, 1.0 / i, 0, 1.0 / i] for i in inertia], dtype=s)
+    return api.Bodies(kind=np.full(n, api.BODY_DYNAMIC, dtype=np.uint8), position=np.zeros((n, 3), dtype=s), rotation=np.tile(np.array([[0, 0, 0, 1]], dtype=s), (n, 1)),
+                      linear_velocity=np.zeros((n, 3), dtype=s), angular_velocity=np.zeros((n, 3), dtype=s), inverse_mass=np.array([1.0 / m for m in mass], dtype=s),
+                      inverse_inertia_local=inv_i)
+
+
+def test_apply_force_reference_test():
+    """rigid_body/forces/tests.rs:53-96: 9.81 N upwards against gravity, 20 substeps, 5 s at 64 Hz (TIMESTEP = 1/64): the 1 kg body stays (1e-6), the 0.5 kg body
+    rises by 1/2 * 9.81 * 25 (eps 0.05).  The ForcePlugin turns the force into the acceleration column F / m (forces/plugin.rs:207-241)."""
+    b = _two_bodies()
+    b.linear_acceleration = np.array([[0, 9.81 * 1.0, 0], [0, 9.81 * 2.0, 0]], dtype=np.float32)
+    prm = api.default_step_params(dt=1.0 / 64.0, substeps=20, gravity=(0, -9.81, 0))
+    for _ in range(int(5.0 * 64.0)):
+        oracle_lib.solver_step(prm, b)
+    assert abs(b.position[0, 1]) < 1e-6
+    assert abs(b.position[1, 1] - 0.5 * 9.81 * 25.0) < 0.05
+
+
+def test_apply_torque_reference_test():
+    """rigid_body/forces/tests.rs:346-394: 1.5 N m about Z for 1.5 s: the body with unit inertia turns by 1/2 * 1.5 * t^2 (0.1 rad), the one
+    with inertia 0.5 by 1.5 * t^2 (0.15 rad)."""
+    b = _two_bodies()
+    b.angular_acceleration = np.array([[0, 0, 1.5 / 1.0], [0, 0, 1.5 / 0.5]], dtype=np.float32)
+    prm = api.default_step_params(dt=1.0 / 64.0, substeps=20, gravity=(0, 0, 0))
+    for _ in range(int(1.5 * 64.0)):
+        oracle_lib.solver_step(prm, b)
+    def angle_to_z(q, theta):
+        want = np.array([0, 0, np.sin(theta / 2), np.cos(theta / 2)])
+        return 2.0 * np.arccos(min(1.0, abs(float(np.dot(q.astype(np.float64), want)))))
+    assert angle_to_z(b.rotation[0], 0.5 * 1.5 * 1.5 ** 2) < 0.1
+    assert angle_to_z(b.rotation[1], 1.5 * 1.5 ** 2) < 0.15
