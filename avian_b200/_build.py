@@ -16,8 +16,8 @@ LIB_DIR = ROOT / "lib"
 CUDA_LIB = LIB_DIR / "libavian_b200.so"
 HOST_LIB = LIB_DIR / "libavian_host.so"
 
-CUDA_SOURCES = ["abi.cu", "solver_host.cu", "broadphase.cu", "aabb.cu"]
-CUDA_HEADERS = ["avn_math.cuh", "solver_dev.cuh", "joints_dev.cuh", "solver_kernels.cuh", "context.hpp", "joint_schedule.hpp", "broadphase_cells.cuh"]
+CUDA_SOURCES = ["abi.cu", "solver_host.cu", "broadphase.cu", "aabb.cu", "narrow.cu", "contacts.cu"]
+CUDA_HEADERS = ["avn_math.cuh", "solver_dev.cuh", "joints_dev.cuh", "solver_kernels.cuh", "context.hpp", "joint_schedule.hpp", "broadphase_cells.cuh", "narrow_math.hpp", "contact_rows.hpp"]
 # -fmad=false: the reference (Rust) never contracts a*b+c; parity at 1e-5 on contact dynamics needs the same
 # rounding.  Division and sqrt stay IEEE (nvcc defaults -prec-div=true -prec-sqrt=true).
 NVCC_FLAGS = [
@@ -60,7 +60,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
 def build_host(force: bool = False) -> Path:
     src = ROOT / "host"
-    deps = [p for p in src.glob("*.[ch]pp")] + [REPO / "include" / "avian_b200.h", ROOT / "csrc" / "narrow_math.hpp"]
+    deps = [p for p in src.glob("*.[ch]pp")] + [REPO / "include" / "avian_b200.h", ROOT / "csrc" / "narrow_math.hpp", ROOT / "csrc" / "contact_rows.hpp"]
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
     cxx = os.environ.get("CXX") or shutil.which("g++")

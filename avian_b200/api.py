@@ -310,9 +310,29 @@ class PairList:
         return PairList(self.collider1[:n], self.collider2[:n], self.body1[:n], self.body2[:n], self.flags[:n], n)
 
 
+class AvnEdgeManifolds(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("edge_capacity", C.c_uint32), ("color_offsets", C.c_uint32 * (GRAPH_COLOR_COUNT + 1))] + [
+        (n, _vp) for n in ("edge", "body1", "body2", "friction", "restitution", "point_count", "normal", "anchor1", "anchor2", "penetration",
+                           "normal_speed", "warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse")]
+
+
+class AvnNarrowParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("contact_tolerance", C.c_double)]
+
+
+class AvnNarrowInput(C.Structure):
+    _fields_ = [("pair_count", C.c_uint32), ("collider_count", C.c_uint32), ("body_count", C.c_uint32), ("_pad", C.c_uint32)] + [
+        (n, _vp) for n in ("collider1", "collider2", "body1", "body2", "shape", "dims", "position", "rotation", "linear_velocity", "angular_velocity",
+                           "aabb_min", "aabb_max")]
+
+
+class AvnRawManifolds(C.Structure):
+    _fields_ = [(n, _vp) for n in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")]
+
+
 class AvnBoundary(C.Structure):
-    _fields_ = [("count", C.c_uint32), ("slot_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
-                ("body", _vp), ("slot", _vp), ("owner_rank", _vp)]
+    _fields_ = [("count", C.c_uint32), ("record_count", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("body", _vp), ("source", _vp), ("owner_rank", _vp)]
 
 
 def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
@@ -343,6 +363,14 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "solver_boundary_apply": ([_vp, _vp], C.c_int),
         "solver_needs_restitution": ([_vp, P(C.c_int)], C.c_int),
         "get_stream": ([_vp, P(_vp)], C.c_int),
+        "narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), P(AvnRawManifolds)], C.c_int),
+        "solver_upload_edges": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
+        "solver_upload_graph": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
+        "contacts_reserve": ([_vp, C.c_uint32], C.c_int),
+        "contacts_add": ([_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp], C.c_int),
+        "contacts_remove": ([_vp, C.c_uint32, _vp], C.c_int),
+        "contacts_narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), C.c_uint32, C.c_double, _vp, _vp], C.c_int),
+        "contacts_download_impulses": ([_vp, _vp, _vp, _vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -354,7 +382,8 @@ ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
-    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream"]
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
+    "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 BOUNDARY_RECORD_SCALARS = 16
@@ -530,9 +559,10 @@ class Context:
     def solver_run_range(self, first: int, count: int, flags: int) -> None:
         self._check(self.lib.avn_solver_run_range(self.handle, first, count, flags))
 
-    def solver_set_boundary(self, body: np.ndarray, slot: np.ndarray, owner_rank: np.ndarray, slot_count: int, rank: int, world: int) -> None:
-        body, slot, owner_rank = (np.ascontiguousarray(x, dtype=np.int32) for x in (body, slot, owner_rank))
-        b = AvnBoundary(int(body.shape[0]), int(slot_count), int(rank), int(world), _ptr(body), _ptr(slot), _ptr(owner_rank))
+    def solver_set_boundary(self, body: np.ndarray, source: np.ndarray, owner_rank: np.ndarray, record_count: int, rank: int, world: int) -> None:
+        body, source, owner_rank = (np.ascontiguousarray(x, dtype=np.int32) for x in (body, source, owner_rank))
+        assert source.size == body.shape[0] * world
+        b = AvnBoundary(int(body.shape[0]), int(record_count), int(rank), int(world), _ptr(body), _ptr(source), _ptr(owner_rank))
         self._check(self.lib.avn_solver_set_boundary(self.handle, C.byref(b)))
 
     def solver_boundary_snapshot(self) -> None:
@@ -554,6 +584,104 @@ class Context:
         out = _vp()
         self._check(self.lib.avn_get_stream(self.handle, C.byref(out)))
         return int(out.value or 0)
+
+    def solver_step_edges(self, params, bodies: Bodies, graph: dict, edges: dict, joints: JointSet | None = None) -> None:
+        """avn_solver_upload_edges + run + download.  graph = dict(color_offsets, edge, body1, body2, friction, restitution) (per manifold);
+        edges = dict(point_count, normal, anchor1, anchor2, penetration, normal_speed, warm_start_normal_impulse,
+        warm_start_tangent_impulse, normal_impulse) (edge-indexed, 4 slots per edge; the three impulse columns are updated in place)."""
+        b = bodies.as_struct()
+        j = joints.as_struct() if joints is not None and joints.count else None
+        em = AvnEdgeManifolds()
+        em.count = int(graph["edge"].shape[0])
+        em.edge_capacity = int(edges["point_count"].shape[0])
+        for i in range(GRAPH_COLOR_COUNT + 1):
+            em.color_offsets[i] = int(graph["color_offsets"][i])
+        keep = []
+        def col(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+        em.edge = col(graph["edge"], np.uint32); em.body1 = col(graph["body1"], np.int32); em.body2 = col(graph["body2"], np.int32)
+        em.friction = col(graph["friction"], self.scalar); em.restitution = col(graph["restitution"], self.scalar)
+        em.point_count = col(edges["point_count"], np.uint8)
+        for k in ("normal", "anchor1", "anchor2", "penetration", "normal_speed"):
+            setattr(em, k, col(edges[k], self.scalar))
+        for k in ("warm_start_normal_impulse", "warm_start_tangent_impulse", "normal_impulse"):
+            assert edges[k].flags["C_CONTIGUOUS"] and edges[k].dtype == self.scalar
+            setattr(em, k, edges[k].ctypes.data)
+        self._keep = (params, bodies, graph, edges, joints, b, em, j, keep)
+        self._check(self.lib.avn_solver_upload_edges(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
+        self._check(self.lib.avn_solver_run(self.handle))
+        self._check(self.lib.avn_solver_download(self.handle))
+
+    # ---- device-resident contact edges (include/avian_b200.h)
+    def contacts_reserve(self, capacity: int) -> None:
+        self._check(self.lib.avn_contacts_reserve(self.handle, int(capacity)))
+
+    def contacts_add(self, ids, c1, c2, b1, b2) -> None:
+        a = [np.ascontiguousarray(x, dtype=np.uint32) for x in (ids, c1, c2, b1, b2)]
+        self._check(self.lib.avn_contacts_add(self.handle, int(a[0].shape[0]), *(x.ctypes.data for x in a)))
+
+    def contacts_remove(self, ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self.lib.avn_contacts_remove(self.handle, int(ids.shape[0]), ids.ctypes.data))
+
+    def contacts_narrow_phase(self, dt: float, contact_tolerance: float, colliders: dict, lin_vel, ang_vel, capacity: int, match_contacts: bool = True,
+                              length_unit: float = 1.0):
+        """Geometry + match_contacts for every live row.  Returns (point_count[capacity], disjoint[capacity])."""
+        dt_ = self.scalar
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+        inp = AvnNarrowInput(0, int(cols["position"].shape[0]), int(lv.shape[0]), 0, None, None, None, None, _ptr(cols["shape"]), _ptr(cols["dims"]),
+                             _ptr(cols["position"]), _ptr(cols["rotation"]), _ptr(lv), _ptr(av), _ptr(cols["aabb_min"]), _ptr(cols["aabb_max"]))
+        count, disjoint = np.zeros(capacity, dtype=np.uint8), np.zeros(capacity, dtype=np.uint8)
+        prm = AvnNarrowParams(float(dt), float(contact_tolerance))
+        self._check(self.lib.avn_contacts_narrow_phase(self.handle, C.byref(prm), C.byref(inp), 1 if match_contacts else 0, float(length_unit),
+                                                       count.ctypes.data, disjoint.ctypes.data))
+        return count, disjoint
+
+    def solver_step_graph(self, params, bodies: Bodies, graph: dict, joints: JointSet | None = None) -> None:
+        """avn_solver_upload_graph + run + download: the manifolds come from the resident rows, graph = dict(color_offsets, edge, body1, body2,
+        friction, restitution)."""
+        b = bodies.as_struct()
+        j = joints.as_struct() if joints is not None and joints.count else None
+        em = AvnEdgeManifolds()
+        em.count = int(graph["edge"].shape[0])
+        for i in range(GRAPH_COLOR_COUNT + 1):
+            em.color_offsets[i] = int(graph["color_offsets"][i])
+        keep = [np.ascontiguousarray(graph["edge"], dtype=np.uint32), np.ascontiguousarray(graph["body1"], dtype=np.int32),
+                np.ascontiguousarray(graph["body2"], dtype=np.int32), np.ascontiguousarray(graph["friction"], dtype=self.scalar),
+                np.ascontiguousarray(graph["restitution"], dtype=self.scalar)]
+        em.edge, em.body1, em.body2, em.friction, em.restitution = (x.ctypes.data for x in keep)
+        self._keep = (params, bodies, graph, joints, b, em, j, keep)
+        self._check(self.lib.avn_solver_upload_graph(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
+        self._check(self.lib.avn_solver_run(self.handle))
+        self._check(self.lib.avn_solver_download(self.handle))
+
+    def contacts_download_impulses(self, capacity: int):
+        wn, wt, ni = (np.zeros((capacity, 4), dtype=self.scalar), np.zeros((capacity, 4, 2), dtype=self.scalar), np.zeros((capacity, 4), dtype=self.scalar))
+        self._check(self.lib.avn_contacts_download_impulses(self.handle, wn.ctypes.data, wt.ctypes.data, ni.ctypes.data))
+        return wn, wt, ni
+
+    def narrow_phase(self, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray) -> dict:
+        """avn_narrow_phase: pairs = (collider1, collider2, body1, body2) uint32 arrays; colliders = dict(shape, dims, position, rotation,
+        aabb_min=None, aabb_max=None).  Returns the raw manifold columns (4 point slots per pair)."""
+        c1, c2, b1, b2 = (np.ascontiguousarray(x, dtype=np.uint32) for x in pairs)
+        n, dt_ = int(c1.shape[0]), self.scalar
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+        inp = AvnNarrowInput(n, int(cols["position"].shape[0]), int(lv.shape[0]), 0, _ptr(c1), _ptr(c2), _ptr(b1), _ptr(b2), _ptr(cols["shape"]),
+                             _ptr(cols["dims"]), _ptr(cols["position"]), _ptr(cols["rotation"]), _ptr(lv), _ptr(av), _ptr(cols["aabb_min"]),
+                             _ptr(cols["aabb_max"]))
+        out = {"point_count": np.zeros(n, dtype=np.uint8), "disjoint": np.zeros(n, dtype=np.uint8), "normal": np.zeros((n, 3), dtype=dt_),
+               "anchor1": np.zeros((n, 4, 3), dtype=dt_), "anchor2": np.zeros((n, 4, 3), dtype=dt_), "penetration": np.zeros((n, 4), dtype=dt_),
+               "normal_speed": np.zeros((n, 4), dtype=dt_)}
+        raw = AvnRawManifolds(*(_ptr(out[k]) for k in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")))
+        prm = AvnNarrowParams(float(dt), float(contact_tolerance))
+        self._check(self.lib.avn_narrow_phase(self.handle, C.byref(prm), C.byref(inp), C.byref(raw)))
+        return out
 
     def update_aabbs(self, params: "AvnAabbParams", colliders: "Colliders") -> None:
         c = colliders.as_struct()

@@ -13,6 +13,8 @@ struct AvnContext {
     std::unique_ptr<avn::SolverBase> solver;
     std::unique_ptr<avn::BroadphaseBase> broadphase;
     std::unique_ptr<avn::AabbBase> aabbs;
+    std::unique_ptr<avn::NarrowBase> narrow;
+    std::unique_ptr<avn::ContactsBase> contacts;
     AvnTimings last{};
 };
 
@@ -55,7 +57,9 @@ AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
     ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
     ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
     ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
-    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
+    ctx->narrow.reset(avn::make_narrow(config->scalar_bits, ctx->stream, &ctx->err));
+    ctx->contacts.reset(avn::make_contacts(config->scalar_bits, ctx->stream, &ctx->err));
+    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs || !ctx->narrow || !ctx->contacts) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
     *out_ctx = ctx.release();
     return AVN_OK;
 }
@@ -67,6 +71,8 @@ void avn_destroy(AvnContext* ctx) {
     ctx->solver.reset();
     ctx->broadphase.reset();
     ctx->aabbs.reset();
+    ctx->narrow.reset();
+    ctx->contacts.reset();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -102,6 +108,11 @@ AvnStatus avn_solver_run(AvnContext* ctx) {
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
     return ctx->solver->run();
+}
+AvnStatus avn_solver_upload_edges(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->solver->upload_edges(params, bodies, manifolds, joints);
 }
 AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags) {
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
@@ -180,6 +191,36 @@ AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColl
     if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
     if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
     return ctx->aabbs->update(params, colliders);
+}
+
+AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out) {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+    return ctx->narrow->run(params, input, out);
+}
+
+#define AVN_ENTER(ctx)                                                             \
+    if (!(ctx)) return AVN_ERR_INVALID_ARGUMENT;                                   \
+    if (!bind(ctx)) return (ctx)->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed")
+AvnStatus avn_contacts_reserve(AvnContext* ctx, uint32_t capacity) { AVN_ENTER(ctx); return ctx->contacts->reserve(capacity); }
+AvnStatus avn_contacts_add(AvnContext* ctx, uint32_t n, const uint32_t* ids, const uint32_t* collider1, const uint32_t* collider2, const uint32_t* body1,
+                           const uint32_t* body2) {
+    AVN_ENTER(ctx);
+    return ctx->contacts->add(n, ids, collider1, collider2, body1, body2);
+}
+AvnStatus avn_contacts_remove(AvnContext* ctx, uint32_t n, const uint32_t* ids) { AVN_ENTER(ctx); return ctx->contacts->remove(n, ids); }
+AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts, double length_unit,
+                                    uint8_t* out_point_count, uint8_t* out_disjoint) {
+    AVN_ENTER(ctx);
+    return ctx->contacts->narrow_phase(params, input, match_contacts, length_unit, out_point_count, out_disjoint);
+}
+AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints) {
+    AVN_ENTER(ctx);
+    return ctx->solver->upload_graph(params, bodies, graph, ctx->contacts.get(), joints);
+}
+AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse) {
+    AVN_ENTER(ctx);
+    return ctx->contacts->download_impulses(warm_start_normal, warm_start_tangent, normal_impulse);
 }
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {

@@ -116,11 +116,41 @@ __global__ void __launch_bounds__(1024) rs_scan(uint32_t* data, int len) {
 
 // stable scatter of one tile.  Warp w owns the contiguous sub-tile [w*256, (w+1)*256) and walks it in 8 rounds of
 // 32 consecutive keys, so (warp, round, lane) order == input order; ranks come from match_any + popc.
-template <class K>
+// FUSED = the (digit, block) offsets are computed here from the raw per-block histograms instead of by a separate rs_scan launch:
+// offset(d, blk) = sum of all counters of the digits below d + the counters of digit d in the blocks before blk.  Every block redoes the
+// 256 x nblocks row sums (L2-resident, 49 KB at 100k keys), which is cheaper than a 12 us single-block scan kernel and its launch gap as
+// long as nblocks is small; the host keeps the scan kernel above RS_FUSE_MAX_BLOCKS.
+constexpr int RS_FUSE_MAX_BLOCKS = 128;
+template <class K, bool FUSED>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int n, int shift,
                                                          const uint32_t* __restrict__ offsets, int nblocks, K* __restrict__ keys_out,
                                                          uint32_t* __restrict__ vals_out) {
     __shared__ uint32_t wcnt[RS_WARPS][256];
+    __shared__ uint32_t digit_base[256];
+    __shared__ uint32_t scan_warp[8];
+    if (FUSED) {
+        // thread d: total of digit d over all blocks, and the part of it that belongs to earlier blocks
+        const int d = threadIdx.x;
+        uint32_t total = 0, before_blk = 0;
+        const uint32_t* row = offsets + size_t(d) * nblocks;
+        for (int b = 0; b < nblocks; ++b) {
+            const uint32_t c = row[b];
+            total += c;
+            if (b < int(blockIdx.x)) before_blk += c;
+        }
+        // exclusive scan of the 256 totals (8 warps)
+        uint32_t x = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) scan_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t warp_before = 0;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) warp_before += scan_warp[w];
+        digit_base[d] = (x - total) + warp_before + before_blk;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int d = threadIdx.x; d < RS_WARPS * 256; d += RS_THREADS) (&wcnt[0][0])[d] = 0;
     __syncthreads();
@@ -147,7 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
     // per digit (one thread each): exclusive prefix across the 8 warps + global offset of (digit, block)
     {
         const int d = threadIdx.x;
-        uint32_t run = offsets[d * nblocks + blockIdx.x];
+        uint32_t run = FUSED ? digit_base[d] : offsets[d * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             uint32_t c = wcnt[w][d];
@@ -528,9 +558,13 @@ AvnStatus Broadphase<S>::run() {
         for (int pass = 0; pass < KeyOf<S>::passes; ++pass) {
             const int shift = 8 * pass;
             rs_histogram<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, n, shift, hist_.as<uint32_t>(), nblocks);
-            rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
-            rs_scatter<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
-            launches_ += 3;
+            if (nblocks <= RS_FUSE_MAX_BLOCKS) {
+                rs_scatter<K, true><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+            } else {
+                rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+                rs_scatter<K, false><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+            }
+            launches_ += nblocks <= RS_FUSE_MAX_BLOCKS ? 2 : 3;
             std::swap(ka, kb);
             std::swap(va, vb);
         }
@@ -572,8 +606,12 @@ AvnStatus Broadphase<S>::run() {
             uint32_t* cva = cv0_.as<uint32_t>(); uint32_t* cvb = cv1_.as<uint32_t>();
             for (int pass = 0; pass < 2; ++pass) {
                 rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, n, 8 * pass, hist_.as<uint32_t>(), nblocks);
-                rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
-                rs_scatter<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+                if (nblocks <= RS_FUSE_MAX_BLOCKS) {
+                    rs_scatter<uint32_t, true><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+                } else {
+                    rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+                    rs_scatter<uint32_t, false><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+                }
                 std::swap(cka, ckb);
                 std::swap(cva, cvb);
             }
@@ -591,7 +629,7 @@ AvnStatus Broadphase<S>::run() {
         AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
         sweep_wide_kernel<S, false><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr);
         wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
-        launches_ += 13;
+        launches_ += nblocks <= RS_FUSE_MAX_BLOCKS ? 11 : 13;
         const int sblocks = (n + 1023) / 1024;
         AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
         scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());

@@ -53,9 +53,13 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+struct ContactsBase;
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) = 0;
+    virtual AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) = 0;
+    // the same with the edge-indexed columns already on the device (ContactsBase::view / outputs): only the graph columns are uploaded
+    virtual AvnStatus upload_graph(const AvnStepParams* prm, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, ContactsBase* contacts, AvnJointSet* joints) = 0;
     virtual AvnStatus run() = 0;
     virtual AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) = 0;
     virtual AvnStatus set_boundary(const AvnBoundary* bnd) = 0;
@@ -79,6 +83,26 @@ struct AabbBase {
     virtual AvnStatus update(const AvnAabbParams* prm, AvnColliderColumns* colliders) = 0;
 };
 AabbBase* make_aabb_updater(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
+
+struct NarrowBase {
+    virtual ~NarrowBase() {}
+    virtual AvnStatus run(const AvnNarrowParams* prm, const AvnNarrowInput* in, AvnRawManifolds* out) = 0;
+};
+NarrowBase* make_narrow(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
+
+struct ContactsBase {
+    virtual ~ContactsBase() {}
+    virtual AvnStatus reserve(uint32_t capacity) = 0;
+    virtual AvnStatus add(uint32_t n, const uint32_t* ids, const uint32_t* c1, const uint32_t* c2, const uint32_t* b1, const uint32_t* b2) = 0;
+    virtual AvnStatus remove(uint32_t n, const uint32_t* ids) = 0;
+    virtual AvnStatus narrow_phase(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint8_t* out_count,
+                                   uint8_t* out_disjoint) = 0;
+    virtual AvnStatus view(AvnEdgeManifolds* out) = 0;                       // device pointers of the edge-indexed columns
+    virtual void outputs(void** ws_n, void** ws_t, void** nimp) = 0;         // device pointers store_contact_impulses writes
+    virtual uint32_t capacity() const = 0;
+    virtual AvnStatus download_impulses(void* ws_n, void* ws_t, void* nimp) = 0;
+};
+ContactsBase* make_contacts(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
 
 SolverBase* make_solver(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, uint32_t cfg_flags, int device);
 BroadphaseBase* make_broadphase(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err, int device);

@@ -79,7 +79,11 @@ struct DevSolver {
     Vec4<S>* vel; Vec4<S>* dlt; Vec4<S>* inr; Vec4<S>* itg; Vec4<S>* pre;
     // raw manifold columns
     const int* m_body1; const int* m_body2; const S* m_normal; const S* m_friction; const S* m_restitution; const S* m_tanvel;
-    const uint32_t* m_point_off; const S* p_anchor1; const S* p_anchor2; const S* p_penetration; const S* p_normal_speed;
+    // points of manifold m: rows [m_point_begin[m], m_point_end[m]) of the point columns.  CSR input: begin = offsets, end = offsets + 1
+    // (the same buffer).  Edge-indexed input: begin = 4 * edge[m], end = begin + point_count[edge[m]], and the per-manifold normal lives
+    // in row m_src[m] (= edge[m]) of the normal column; m_src == NULL means row m.
+    const uint32_t* m_point_begin; const uint32_t* m_point_end; const uint32_t* m_src;
+    const S* p_anchor1; const S* p_anchor2; const S* p_penetration; const S* p_normal_speed;
     const S* p_ws_normal; const S* p_ws_tangent;               // warm-start inputs (never written: every run restarts from them)
     const S* p_in_normal_impulse;
     S* p_out_ws_normal; S* p_out_ws_tangent; S* p_normal_impulse;  // store_contact_impulses outputs
@@ -224,7 +228,7 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     Vec4<S> i1a = ld4(&d.inr[2 * b1]), i1b = ld4(&d.inr[2 * b1 + 1]);
     Vec4<S> i2a = ld4(&d.inr[2 * b2]), i2b = ld4(&d.inr[2 * b2 + 1]);
     int f1 = as_int(i1a.y), f2 = as_int(i2a.y);
-    uint32_t p0 = d.m_point_off[m], p1 = d.m_point_off[m + 1];
+    uint32_t p0 = d.m_point_begin[m], p1 = d.m_point_end[m];
     int np = int(p1 - p0);
     Vec4<S>* c = d.cst + slot_of_manifold(d, m);
     const size_t MP = size_t(d.Mpad);
@@ -244,7 +248,7 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     if (f1 & BF_HAS_SOLVER_BODY) info |= CI_VER1;
     if (f2 & BF_HAS_SOLVER_BODY) info |= CI_VER2;
     V3<S> mass_sum = in1.inv_mass + in2.inv_mass;
-    V3<S> n = ldv3(d.m_normal, m);
+    V3<S> n = ldv3(d.m_normal, d.m_src ? int(d.m_src[m]) : m);
     // compute_tangent_directions (contact/mod.rs:427-449): LinearVelocity components of the rigid bodies
     V3<S> v1 = rb1 >= 0 ? ldv3(d.linvel, rb1) : zero3<S>();
     V3<S> v2 = rb2 >= 0 ? ldv3(d.linvel, rb2) : zero3<S>();
@@ -819,9 +823,9 @@ __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m)
     const size_t MP = size_t(d.Mpad);
     const Vec4<S>* c = d.cst + slot_of_manifold(d, m);
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
-    int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = int(d.m_point_off[m]);
+    int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = int(d.m_point_begin[m]);
     if (np == 0) {  // skipped by prepare (both bodies non-dynamic): the reference leaves the ContactPoints untouched
-        for (uint32_t p = d.m_point_off[m]; p < d.m_point_off[m + 1]; ++p) {
+        for (uint32_t p = d.m_point_begin[m]; p < d.m_point_end[m]; ++p) {
             d.p_out_ws_normal[p] = d.p_ws_normal[p];
             d.p_out_ws_tangent[2 * p] = d.p_ws_tangent[2 * p];
             d.p_out_ws_tangent[2 * p + 1] = d.p_ws_tangent[2 * p + 1];

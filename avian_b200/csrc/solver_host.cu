@@ -65,6 +65,8 @@ class Solver final : public SolverBase {
     }
 
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
+    AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) override;
+    AvnStatus upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* graph, ContactsBase* contacts, AvnJointSet* js) override;
     AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) override;
     AvnStatus set_boundary(const AvnBoundary* bnd) override;
     AvnStatus boundary_snapshot() override;
@@ -153,7 +155,24 @@ class Solver final : public SolverBase {
     DevSolver<S> dev_{};
     // host pointers for download
     AvnBodyColumns hb_{};
-    AvnManifoldColumns hm_{};
+    // where the manifolds of an upload come from: the CSR columns of AvnManifoldColumns or the edge-indexed columns of AvnEdgeManifolds
+    struct ManifoldSource {
+        size_t M = 0, P = 0, normal_rows = 0;             // manifolds, rows of the point columns, rows of the normal column
+        const uint32_t* color_offsets = nullptr;
+        const int32_t* body1 = nullptr; const int32_t* body2 = nullptr;
+        const void* friction = nullptr; const void* restitution = nullptr; const void* tangent_velocity = nullptr; const void* normal = nullptr;
+        const uint32_t* point_offsets = nullptr;           // CSR
+        const uint32_t* edge = nullptr; const uint8_t* edge_point_count = nullptr;   // edge-indexed
+        const void* anchor1 = nullptr; const void* anchor2 = nullptr; const void* penetration = nullptr; const void* normal_speed = nullptr;
+        void* ws_normal = nullptr; void* ws_tangent = nullptr; void* normal_impulse = nullptr;
+        // device == true: the edge-indexed columns above (point counts, normal, point columns, impulse inputs) are DEVICE pointers owned by the
+        // contact store, and store_contact_impulses writes to out_* (device) instead of buffers of this solver; nothing of them is copied
+        bool device = false;
+        void* out_ws_normal = nullptr; void* out_ws_tangent = nullptr; void* out_normal_impulse = nullptr;
+    };
+    AvnStatus upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* src, AvnJointSet* js);
+    ManifoldSource hm_{};
+    DevBuf m_edge_, m_pbegin_, m_pend_, e_cnt_;
     AvnJointSet hj_{};
     bool have_m_ = false, have_j_ = false;
 
@@ -189,6 +208,71 @@ AvnStatus Solver<S>::build_joint_schedule(const AvnBodyColumns& bc, const AvnJoi
 
 template <class S>
 AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) {
+    if (!mc || mc->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
+        !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+    ManifoldSource src;
+    src.M = mc->count; src.P = mc->point_count; src.normal_rows = mc->count;
+    src.color_offsets = mc->color_offsets; src.body1 = mc->body1; src.body2 = mc->body2; src.friction = mc->friction; src.restitution = mc->restitution;
+    src.tangent_velocity = mc->tangent_velocity; src.normal = mc->normal; src.point_offsets = mc->point_offsets;
+    src.anchor1 = mc->anchor1; src.anchor2 = mc->anchor2; src.penetration = mc->penetration; src.normal_speed = mc->normal_speed;
+    src.ws_normal = mc->warm_start_normal_impulse; src.ws_tangent = mc->warm_start_tangent_impulse; src.normal_impulse = mc->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) {
+    if (!em || em->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!em->edge || !em->body1 || !em->body2 || !em->friction || !em->restitution || !em->point_count || !em->normal || !em->anchor1 || !em->anchor2 ||
+        !em->penetration || !em->normal_speed || !em->warm_start_normal_impulse || !em->warm_start_tangent_impulse || !em->normal_impulse)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: every column is required");
+    for (size_t m = 0; m < em->count; ++m)
+        if (em->edge[m] >= em->edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: edge[%zu] = %u >= edge_capacity %u", m, em->edge[m], em->edge_capacity);
+    ManifoldSource src;
+    src.M = em->count; src.P = size_t(4) * em->edge_capacity; src.normal_rows = em->edge_capacity;
+    src.color_offsets = em->color_offsets; src.body1 = em->body1; src.body2 = em->body2; src.friction = em->friction; src.restitution = em->restitution;
+    src.normal = em->normal; src.edge = em->edge; src.edge_point_count = em->point_count;
+    src.anchor1 = em->anchor1; src.anchor2 = em->anchor2; src.penetration = em->penetration; src.normal_speed = em->normal_speed;
+    src.ws_normal = em->warm_start_normal_impulse; src.ws_tangent = em->warm_start_tangent_impulse; src.normal_impulse = em->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* g, ContactsBase* contacts, AvnJointSet* js) {
+    if (!g || g->count == 0) return upload_impl(prm, bc, nullptr, js);
+    if (!contacts) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "upload_graph: no contact store");
+    if (!g->edge || !g->body1 || !g->body2 || !g->friction || !g->restitution)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge, body1, body2, friction and restitution are required");
+    AvnEdgeManifolds v{};
+    AvnStatus st = contacts->view(&v);
+    if (st != AVN_OK) return st;
+    for (size_t m = 0; m < g->count; ++m)
+        if (g->edge[m] >= v.edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge[%zu] = %u >= capacity %u", m, g->edge[m], v.edge_capacity);
+    ManifoldSource src;
+    src.M = g->count; src.P = size_t(4) * v.edge_capacity; src.normal_rows = v.edge_capacity;
+    src.color_offsets = g->color_offsets; src.body1 = g->body1; src.body2 = g->body2; src.friction = g->friction; src.restitution = g->restitution;
+    src.edge = g->edge;
+    src.device = true;
+    src.normal = v.normal; src.edge_point_count = v.point_count;
+    src.anchor1 = v.anchor1; src.anchor2 = v.anchor2; src.penetration = v.penetration; src.normal_speed = v.normal_speed;
+    src.ws_normal = v.warm_start_normal_impulse; src.ws_tangent = v.warm_start_tangent_impulse; src.normal_impulse = v.normal_impulse;
+    contacts->outputs(&src.out_ws_normal, &src.out_ws_tangent, &src.out_normal_impulse);
+    return upload_impl(prm, bc, &src, js);
+}
+
+// fills the point ranges of the manifolds of an edge-indexed upload: 4 slots per edge, the first point_count[edge] of them live
+__global__ void edge_ranges_kernel(const uint32_t* __restrict__ edge, const uint8_t* __restrict__ count, int M, uint32_t* __restrict__ begin,
+                                   uint32_t* __restrict__ end) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const uint32_t e = edge[m];
+    begin[m] = 4u * e;
+    end[m] = 4u * e + count[e];
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* mc, AvnJointSet* js) {
     if (!prm || !bc) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "params and bodies are required");
     if (bc->count && (!bc->position || !bc->rotation || !bc->linear_velocity || !bc->angular_velocity || !bc->inverse_mass || !bc->inverse_inertia_local))
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "bodies: position, rotation, velocities, inverse_mass and inverse_inertia_local are required");
@@ -256,29 +340,35 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     // mutable front of it (vel, dlt, ver, deg, the four impulse planes) is the L2-persisting window.
     hb_ = *bc;
     // ---- manifolds
-    have_m_ = mc && mc->count > 0;
+    have_m_ = mc != nullptr && mc->M > 0;
     AVN_CUDA(c_flag_.ensure(2 * sizeof(int) + 8 * sizeof(unsigned long long)));  // [0] any restitution, [1] wavefront watchdog, then the optional trace counters
     d.any_restitution = c_flag_.as<int>();
     if (have_m_) {
-        const size_t M = mc->count, P = mc->point_count;
-        if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
-            !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
-            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+        const size_t M = mc->M, P = mc->P;
         if (mc->color_offsets[0] != 0 || mc->color_offsets[AVN_GRAPH_COLOR_COUNT] != M)
             return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must span [0, count]");
         for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
             if (mc->color_offsets[c] > mc->color_offsets[c + 1]) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: color_offsets must be non-decreasing");
-        if (mc->point_offsets[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
-        {   // widest manifold: sizes the shared-memory staging tile (3 rows per point) and validates the CSR
+        {   // widest manifold: sizes the shared-memory staging tile (3 rows per point) and validates the point ranges
             uint32_t widest = 0, bad = 0;
-            const uint32_t* po = mc->point_offsets;
-            for (size_t i = 0; i < M; ++i) {
-                bad |= uint32_t(po[i + 1] < po[i]);
-                const uint32_t n = po[i + 1] - po[i];
-                widest = n > widest ? n : widest;
+            if (mc->point_offsets) {
+                const uint32_t* po = mc->point_offsets;
+                if (po[M] != P) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets[count] != point_count");
+                for (size_t i = 0; i < M; ++i) {
+                    bad |= uint32_t(po[i + 1] < po[i]);
+                    const uint32_t n = po[i + 1] - po[i];
+                    widest = n > widest ? n : widest;
+                }
+            } else if (mc->device) {
+                widest = AVN_MAX_MANIFOLD_POINTS;   // the counts live on the device: take the general kernel build
+            } else {
+                for (size_t i = 0; i < M; ++i) {
+                    const uint32_t n = mc->edge_point_count[mc->edge[i]];
+                    widest = n > widest ? n : widest;
+                }
             }
             if (bad || widest > AVN_MAX_MANIFOLD_POINTS)
-                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: point_offsets must be non-decreasing with at most %d points per manifold", AVN_MAX_MANIFOLD_POINTS);
+                return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: at most %d points per manifold, point ranges must not decrease", AVN_MAX_MANIFOLD_POINTS);
             max_np_ = int(std::max<uint32_t>(widest, 1));
         }
         d.M = int(M);
@@ -297,29 +387,60 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
         }
         UP(m_b1_, mc->body1, M, int, m_body1);
         UP(m_b2_, mc->body2, M, int, m_body2);
-        UP(m_n_, mc->normal, 3 * M, S, m_normal);
+        if (mc->device) d.m_normal = static_cast<const S*>(mc->normal); else UP(m_n_, mc->normal, 3 * mc->normal_rows, S, m_normal);
         UP(m_f_, mc->friction, M, S, m_friction);
         UP(m_r_, mc->restitution, M, S, m_restitution);
         UP(m_tv_, mc->tangent_velocity, 3 * M, S, m_tanvel);
-        UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_off);
-        UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
-        UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
-        UP(p_pen_, mc->penetration, P, S, p_penetration);
-        UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
-        // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
-        UP(p_wn_, mc->warm_start_normal_impulse, P, S, p_ws_normal);
-        UP(p_wt_, mc->warm_start_tangent_impulse, 2 * P, S, p_ws_tangent);
-        UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
-        AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
-        AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
-        AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
-        d.p_normal_impulse = p_ni_.as<S>();
+        if (mc->point_offsets) {
+            UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_begin);
+            d.m_point_end = d.m_point_begin + 1;
+            d.m_src = nullptr;
+        } else {
+            const uint8_t* d_count = nullptr;
+            UP(m_edge_, mc->edge, M, uint32_t, m_src);
+            if (mc->device) d_count = mc->edge_point_count;
+            else if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
+            AVN_CUDA(m_pbegin_.ensure(M * sizeof(uint32_t)));
+            AVN_CUDA(m_pend_.ensure(M * sizeof(uint32_t)));
+            edge_ranges_kernel<<<unsigned((M + 255) / 256), 256, 0, stream_>>>(d.m_src, d_count, int(M), m_pbegin_.as<uint32_t>(), m_pend_.as<uint32_t>());
+            AVN_CUDA(cudaGetLastError());
+            d.m_point_begin = m_pbegin_.as<uint32_t>();
+            d.m_point_end = m_pend_.as<uint32_t>();
+        }
+        if (mc->device) {
+            d.p_anchor1 = static_cast<const S*>(mc->anchor1); d.p_anchor2 = static_cast<const S*>(mc->anchor2);
+            d.p_penetration = static_cast<const S*>(mc->penetration); d.p_normal_speed = static_cast<const S*>(mc->normal_speed);
+            d.p_ws_normal = static_cast<const S*>(mc->ws_normal); d.p_ws_tangent = static_cast<const S*>(mc->ws_tangent);
+            d.p_in_normal_impulse = static_cast<const S*>(mc->normal_impulse);
+            d.p_out_ws_normal = static_cast<S*>(mc->out_ws_normal); d.p_out_ws_tangent = static_cast<S*>(mc->out_ws_tangent);
+            d.p_normal_impulse = static_cast<S*>(mc->out_normal_impulse);
+        } else {
+            UP(p_a1_, mc->anchor1, 3 * P, S, p_anchor1);
+            UP(p_a2_, mc->anchor2, 3 * P, S, p_anchor2);
+            UP(p_pen_, mc->penetration, P, S, p_penetration);
+            UP(p_ns_, mc->normal_speed, P, S, p_normal_speed);
+            // in/out columns: inputs and outputs live in separate device buffers so that avn_solver_run is repeatable
+            UP(p_wn_, mc->ws_normal, P, S, p_ws_normal);
+            UP(p_wt_, mc->ws_tangent, 2 * P, S, p_ws_tangent);
+            UP(p_nin_, mc->normal_impulse, P, S, p_in_normal_impulse);
+            AVN_CUDA(p_own_.ensure(P * sizeof(S) + 16)); d.p_out_ws_normal = p_own_.as<S>();
+            AVN_CUDA(p_owt_.ensure(2 * P * sizeof(S) + 16)); d.p_out_ws_tangent = p_owt_.as<S>();
+            AVN_CUDA(p_ni_.ensure(P * sizeof(S) + 16));
+            d.p_normal_impulse = p_ni_.as<S>();
+            if (!mc->point_offsets) {
+                // edge-indexed: rows of edges that are not in the constraint graph are not written by store_contact_impulses; they keep their
+                // input values (the reference leaves such ContactPoints untouched)
+                AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_normal, d.p_ws_normal, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+                AVN_CUDA(cudaMemcpyAsync(d.p_out_ws_tangent, d.p_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+                AVN_CUDA(cudaMemcpyAsync(d.p_normal_impulse, d.p_in_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToDevice, stream_));
+            }
+        }
 
         hm_ = *mc;
         host_any_restitution_ = false;
         {
             const S* r = static_cast<const S*>(mc->restitution);
-            for (size_t i = 0; i < M; ++i) host_any_restitution_ |= (r[i] != S(0));
+            for (size_t i = 0; i < mc->M; ++i) host_any_restitution_ |= (r[i] != S(0));
         }
     }
     {
@@ -505,12 +626,12 @@ __global__ void boundary_snapshot_kernel(DevSolver<S> d, const int* __restrict__
     st4(&d.vel_ref[2 * k + 1], ld4(&d.vel[2 * b + 1]));
 }
 template <class S>
-__global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
-                                     int n, int rank, Vec4<S>* __restrict__ table) {
+__global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ owner_rank, int n, int rank,
+                                     Vec4<S>* __restrict__ table) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int b = body[k];
-    Vec4<S>* rec = table + size_t(4) * slot[k];
+    Vec4<S>* rec = table + size_t(4) * k;
     const Vec4<S> l = ld4(&d.vel[2 * b]), a = ld4(&d.vel[2 * b + 1]), l0 = ld4(&d.vel_ref[2 * k]), a0 = ld4(&d.vel_ref[2 * k + 1]);
     const bool owner = owner_rank[k] == rank;
     st4(&rec[0], mk4<S>(l.x - l0.x, l.y - l0.y, l.z - l0.z, S(1)));
@@ -521,23 +642,24 @@ __global__ void boundary_pack_kernel(DevSolver<S> d, const int* __restrict__ bod
     }
 }
 template <class S>
-__global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ slot, const int* __restrict__ owner_rank,
-                                      int n, int world, size_t slots, const Vec4<S>* __restrict__ gathered) {
+__global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ body, const int* __restrict__ source, const int* __restrict__ owner_rank,
+                                      int n, int world, size_t records, const Vec4<S>* __restrict__ gathered) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int b = body[k];
     Vec4<S> l = ld4(&d.vel_ref[2 * k]), a = ld4(&d.vel_ref[2 * k + 1]);
     // every holder's constraint impulses of this substep, summed in rank order (the same order on every rank: identical bits)
     for (int r = 0; r < world; ++r) {
-        const Vec4<S>* rec = gathered + (size_t(r) * slots + size_t(slot[k])) * 4;
+        const int idx = source[size_t(k) * world + r];
+        if (idx < 0) continue;  // rank r does not hold this body
+        const Vec4<S>* rec = gathered + (size_t(r) * records + size_t(idx)) * 4;
         const Vec4<S> dl = ld4(&rec[0]), da = ld4(&rec[1]);
-        if (dl.w == S(0)) continue;  // rank r does not hold this body
         l.x = l.x + dl.x; l.y = l.y + dl.y; l.z = l.z + dl.z;
         a.x = a.x + da.x; a.y = a.y + da.y; a.z = a.z + da.z;
     }
     st4(&d.vel[2 * b], mk4<S>(l.x, l.y, l.z, S(0)));
     st4(&d.vel[2 * b + 1], mk4<S>(a.x, a.y, a.z, S(0)));
-    const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * slots + size_t(slot[k])) * 4;
+    const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * records + size_t(source[size_t(k) * world + owner_rank[k]])) * 4;
     st4(&d.dlt[2 * b], ld4(&own[2]));
     st4(&d.dlt[2 * b + 1], ld4(&own[3]));
 }
@@ -551,7 +673,8 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
         bnd_n_ = 0;
         return AVN_OK;
     }
-    if (!bnd->body || !bnd->slot || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, slot and owner_rank are required");
+    if (!bnd->body || !bnd->source || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, source and owner_rank are required");
+    if (bnd->count > bnd->record_count) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: count %u exceeds record_count %u", bnd->count, bnd->record_count);
     if (bnd->rank >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: rank %u >= world %u", bnd->rank, bnd->world);
     if (dev_.J > 0) return err_->fail(AVN_ERR_UNSUPPORTED, "boundary exchange covers contact constraints only (joints shard by island)");
     const size_t n = bnd->count, B = size_t(dev_.B);
@@ -559,19 +682,24 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
     for (size_t k = 0; k < n; ++k) {
         const int b = bnd->body[k];
         if (b < 0 || size_t(b) >= B) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body[%zu] = %d out of range", k, b);
-        if (bnd->slot[k] < 0 || uint32_t(bnd->slot[k]) >= bnd->slot_count) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: slot[%zu] out of range", k);
         if (bnd->owner_rank[k] < 0 || uint32_t(bnd->owner_rank[k]) >= bnd->world) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: owner_rank[%zu] out of range", k);
+        for (uint32_t r = 0; r < bnd->world; ++r) {
+            const int idx = bnd->source[k * bnd->world + r];
+            if (idx >= int(bnd->record_count)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: source[%zu][%u] out of range", k, r);
+        }
+        if (bnd->source[k * bnd->world + bnd->rank] != int(k)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: source[%zu][rank] must be %zu", k, k);
+        if (bnd->source[k * bnd->world + bnd->owner_rank[k]] < 0) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: the owner of body[%zu] must hold it", k);
         if (of[b] != -1) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body %d listed twice", b);
         of[b] = int(k);
     }
     AVN_CUDA(bnd_of_.ensure((B + 1) * sizeof(int)));
     AVN_CUDA(bnd_body_.ensure(n * sizeof(int)));
-    AVN_CUDA(bnd_slot_.ensure(n * sizeof(int)));
+    AVN_CUDA(bnd_slot_.ensure(n * bnd->world * sizeof(int)));
     AVN_CUDA(bnd_owner_.ensure(n * sizeof(int)));
     AVN_CUDA(vel_ref_.ensure(2 * n * sizeof(Vec4<S>)));
     AVN_CUDA(cudaMemcpyAsync(bnd_of_.p, of.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaMemcpyAsync(bnd_body_.p, bnd->body, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    AVN_CUDA(cudaMemcpyAsync(bnd_slot_.p, bnd->slot, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    AVN_CUDA(cudaMemcpyAsync(bnd_slot_.p, bnd->source, n * bnd->world * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaMemcpyAsync(bnd_owner_.p, bnd->owner_rank, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
     AVN_CUDA(cudaStreamSynchronize(stream_));   // `of` is a temporary
     dev_.bnd_of = bnd_of_.as<int>();
@@ -579,7 +707,7 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
     bnd_n_ = int(n);
     bnd_rank_ = int(bnd->rank);
     bnd_world_ = int(bnd->world);
-    bnd_slots_ = size_t(bnd->slot_count);
+    bnd_slots_ = size_t(bnd->record_count);
     return AVN_OK;
 }
 
@@ -601,7 +729,7 @@ AvnStatus Solver<S>::boundary_pack(void* device_table) {
     if (!device_table) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary table is required");
     AVN_CUDA(cudaMemsetAsync(device_table, 0, bnd_slots_ * 4 * sizeof(Vec4<S>), stream_));
     if (bnd_n_ > 0) {
-        boundary_pack_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_slot_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_rank_,
+        boundary_pack_kernel<S><<<(bnd_n_ + 255) / 256, 256, 0, stream_>>>(dev_, bnd_body_.as<int>(), bnd_owner_.as<int>(), bnd_n_, bnd_rank_,
                                                                             static_cast<Vec4<S>*>(device_table));
         ++launches_;
     }
@@ -632,10 +760,10 @@ AvnStatus Solver<S>::download() {
         AVN_CUDA(cudaMemcpyAsync(hb_.linear_velocity, dev_.out_linvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hb_.angular_velocity, dev_.out_angvel, 3 * B * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
-    if (have_m_) {
-        const size_t P = hm_.point_count;
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_normal_impulse, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
-        AVN_CUDA(cudaMemcpyAsync(hm_.warm_start_tangent_impulse, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+    if (have_m_ && !hm_.device) {
+        const size_t P = hm_.P;
+        AVN_CUDA(cudaMemcpyAsync(hm_.ws_normal, dev_.p_out_ws_normal, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaMemcpyAsync(hm_.ws_tangent, dev_.p_out_ws_tangent, 2 * P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(hm_.normal_impulse, dev_.p_normal_impulse, P * sizeof(S), cudaMemcpyDeviceToHost, stream_));
     }
     if (have_j_) {

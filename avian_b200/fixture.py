@@ -34,6 +34,18 @@ def _load():
         lib.avh_narrow_phase.restype = C.c_uint32
         lib.avh_export_manifolds.argtypes = [_vp, C.c_uint32] + [_vp] * 13
         lib.avh_store_impulses.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp]
+        lib.avh_raw_manifolds.argtypes = [C.c_uint32, C.c_uint32] + [_vp] * 12 + [C.c_double, C.c_double] + [_vp] * 9
+        lib.avh_active_edges.argtypes = [_vp] * 6
+        lib.avh_active_edges.restype = C.c_uint32
+        lib.avh_apply_counts.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        lib.avh_apply_counts.restype = C.c_uint32
+        lib.avh_export_edges.argtypes = [_vp] * 7
+        lib.avh_export_edges.restype = None
+        lib.avh_match_raw.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.c_double, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
+        lib.avh_match_raw.restype = None
+        lib.avh_rows_narrow.argtypes = [C.c_uint32, C.c_uint32] + [_vp] * 27 + [C.c_double, C.c_double, C.c_double, C.c_uint32]
+        lib.avh_rows_narrow.restype = None
+        lib.avh_raw_manifolds.restype = None
         lib.avh_pair_count.argtypes = [_vp]
         lib.avh_pair_count.restype = C.c_uint32
         _lib = lib
@@ -42,6 +54,30 @@ def _load():
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+def raw_manifolds(scalar, dt: float, contact_tolerance: float, pairs, colliders: dict, lin_vel: np.ndarray, ang_vel: np.ndarray,
+                  f64_anchors: bool = False) -> dict:
+    """The geometry stage of the fixture's narrow phase for an explicit pair list (same columns as Context.narrow_phase).
+    f64_anchors adds the unrounded anchors (what match_contacts compares on the next step)."""
+    lib = _load()
+    dt_ = np.dtype(scalar)
+    c1, c2, b1, b2 = (np.ascontiguousarray(x, dtype=np.uint32) for x in pairs)
+    n = int(c1.shape[0])
+    cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+            for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+    lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+    out = {"point_count": np.zeros(n, dtype=np.uint8), "disjoint": np.zeros(n, dtype=np.uint8), "normal": np.zeros((n, 3), dtype=dt_),
+           "anchor1": np.zeros((n, 4, 3), dtype=dt_), "anchor2": np.zeros((n, 4, 3), dtype=dt_), "penetration": np.zeros((n, 4), dtype=dt_),
+           "normal_speed": np.zeros((n, 4), dtype=dt_)}
+    a1d = np.zeros((n, 4, 3), dtype=np.float64) if f64_anchors else None
+    a2d = np.zeros((n, 4, 3), dtype=np.float64) if f64_anchors else None
+    lib.avh_raw_manifolds(32 if dt_ == np.float32 else 64, n, _p(c1), _p(c2), _p(b1), _p(b2), _p(cols["shape"]), _p(cols["dims"]), _p(cols["position"]),
+                          _p(cols["rotation"]), _p(lv), _p(av), _p(cols["aabb_min"]), _p(cols["aabb_max"]), float(dt), float(contact_tolerance),
+                          *(_p(out[k]) for k in ("point_count", "disjoint", "normal", "anchor1", "anchor2", "penetration", "normal_speed")), _p(a1d), _p(a2d))
+    if f64_anchors:
+        out["anchor1_f64"], out["anchor2_f64"] = a1d, a2d
+    return out
 
 
 class HostPipeline:
@@ -53,6 +89,7 @@ class HostPipeline:
         self.n = int(shape_type.shape[0])
         self.scalar = np.dtype(scalar)
         self.bits = 32 if self.scalar == np.float32 else 64
+        dims = np.asarray(dims, dtype=self.scalar).astype(np.float64)      # shapes carry the world's scalar type (Collider is f32 in an f32 build)
         self.h = self.lib.avh_create(self.n)
         st = np.ascontiguousarray(shape_type, dtype=np.int32)
         dm = np.ascontiguousarray(dims, dtype=np.float64)
@@ -113,6 +150,29 @@ class HostPipeline:
                                       _p(man.restitution), _p(man.point_offsets), _p(man.anchor1), _p(man.anchor2), _p(man.penetration),
                                       _p(man.normal_speed), _p(man.warm_start_normal_impulse), _p(man.warm_start_tangent_impulse))
         return man
+
+    # ---- resident mode: the geometry runs elsewhere, the host keeps only the graphs
+    def active_edges(self):
+        n = self.pair_count
+        ids, c1, c2, b1, b2 = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+        k = int(self.lib.avh_active_edges(self.h, _p(ids), _p(c1), _p(c2), _p(b1), _p(b2)))
+        return ids[:k], c1[:k], c2[:k], b1[:k], b2[:k]
+
+    def apply_counts(self, bodies: api.Bodies, ids: np.ndarray, point_count: np.ndarray, disjoint: np.ndarray):
+        """Touching state machine + contact / constraint graph updates from per-edge point counts.  Returns (manifolds, points) in the graph."""
+        pts = C.c_uint32(0)
+        kind = np.ascontiguousarray(bodies.kind, dtype=np.uint8)
+        ids, point_count, disjoint = np.ascontiguousarray(ids, dtype=np.uint32), np.ascontiguousarray(point_count, dtype=np.uint8), np.ascontiguousarray(disjoint, dtype=np.uint8)
+        m = int(self.lib.avh_apply_counts(self.h, _p(kind), _p(ids), _p(point_count), _p(disjoint), int(ids.shape[0]), C.byref(pts)))
+        return m, int(pts.value)
+
+    def export_edges(self, m: int):
+        """The constraint graph as a colour-major list of edge ids + per-edge bodies and material."""
+        co = np.zeros(api.GRAPH_COLOR_COUNT + 1, dtype=np.uint32)
+        edge, b1, b2 = np.zeros(m, dtype=np.uint32), np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32)
+        fr, re = np.zeros(m, dtype=np.float64), np.zeros(m, dtype=np.float64)
+        self.lib.avh_export_edges(self.h, _p(co), _p(edge), _p(b1), _p(b2), _p(fr), _p(re))
+        return co, edge, b1, b2, fr, re
 
     def store_impulses(self, man: api.Manifolds) -> None:
         self.lib.avh_store_impulses(self.h, self.bits, _p(man.warm_start_normal_impulse), _p(man.warm_start_tangent_impulse), _p(man.normal_impulse))

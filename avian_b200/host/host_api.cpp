@@ -19,6 +19,7 @@
 
 #include "../../include/avian_b200.h"
 #include "../csrc/narrow_math.hpp"
+#include "../csrc/contact_rows.hpp"
 
 namespace {
 
@@ -135,6 +136,26 @@ void pop_manifold(Pipeline& P, uint32_t id) {
     }
 }
 
+// The row function of the device-resident contact store (csrc/contact_rows.hpp, what csrc/contacts.cu runs one thread per row) over host
+// arrays: every live row gets its manifold, matched impulses and history exactly as on the device.  Column layouts as in contacts.cu.
+template <class T>
+static void rows_narrow(uint32_t E, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2, uint8_t* live, uint8_t* count, uint8_t* disjoint, void* normal, void* a1,
+                        void* a2, void* pen, void* ns, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n_in, void* ws_t_in, void* ws_n_out,
+                        void* ws_t_out, const uint8_t* shape, const void* dims, const void* pos, const void* rot, const void* lv, const void* av,
+                        const void* amin, const void* amax, double dt, double tol, double length_unit, uint32_t match) {
+    avn::NarrowEdgeArgs<T> a{};
+    a.r.E = int(E);
+    a.r.c1 = c1; a.r.c2 = c2; a.r.b1 = b1; a.r.b2 = b2; a.r.live = live; a.r.count = count; a.r.disjoint = disjoint;
+    a.r.normal = static_cast<T*>(normal); a.r.a1 = static_cast<T*>(a1); a.r.a2 = static_cast<T*>(a2); a.r.pen = static_cast<T*>(pen); a.r.ns = static_cast<T*>(ns);
+    a.r.prev_count = prev_count; a.r.prev_a1 = prev_a1; a.r.prev_a2 = prev_a2;
+    a.r.ws_n_in = static_cast<T*>(ws_n_in); a.r.ws_t_in = static_cast<T*>(ws_t_in); a.r.ws_n_out = static_cast<T*>(ws_n_out); a.r.ws_t_out = static_cast<T*>(ws_t_out);
+    a.r.nimp_in = nullptr; a.r.nimp_out = nullptr;
+    a.shape = shape; a.dims = static_cast<const T*>(dims); a.pos = static_cast<const T*>(pos); a.rot = static_cast<const T*>(rot);
+    a.lv = static_cast<const T*>(lv); a.av = static_cast<const T*>(av); a.amin = static_cast<const T*>(amin); a.amax = static_cast<const T*>(amax);
+    a.dt = dt; a.tol = tol; a.thr2 = (0.1 * length_unit) * (0.1 * length_unit); a.match = match ? 1 : 0;
+    for (uint32_t e = 0; e < E; ++e) avn::narrow_edge_row<T>(a, int(e));
+}
+
 }  // namespace
 
 extern "C" {
@@ -235,6 +256,40 @@ void avh_add_pairs(AvhPipeline* h, const uint32_t* c1, const uint32_t* c2, const
     }
 }
 
+// The second half of NarrowPhase::update: status changes in ascending ContactId (system_param.rs:136-389) -> ContactGraph removals and
+// ConstraintGraph push / pop.  Returns the number of manifolds in the constraint graph; *out_points = their points.
+static uint32_t apply_status_changes(Pipeline& P, std::vector<uint32_t>& changed, const std::vector<uint8_t>& disjoint, const std::vector<uint8_t>& started,
+                                     const std::vector<uint8_t>& stopped, const std::vector<int>& count_change, uint32_t* out_points) {
+    std::sort(changed.begin(), changed.end());
+    for (uint32_t id : changed) {
+        Pair& pr = P.pairs[id];
+        const bool gen = pr.flags & AVN_PAIR_GENERATE_CONSTRAINTS;
+        if (disjoint[id]) {
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+            P.pair_set.erase(pair_key(pr.collider1, pr.collider2));
+            auto it = std::find(P.active.begin(), P.active.end(), id);  // remove_edge_by_id: swap_remove (contact_graph.rs:615-628)
+            if (it != P.active.end()) { *it = P.active.back(); P.active.pop_back(); }
+            pr = Pair{};
+            P.free_ids.push(id);
+        } else if (started[id]) {
+            pr.touching = true;
+            if (gen) for (size_t k = 0; k < pr.manifolds.size(); ++k) push_manifold(P, id);
+        } else if (stopped[id]) {
+            pr.touching = false;
+            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] > 0) {
+            for (int k = 0; k < count_change[id]; ++k) push_manifold(P, id);
+        } else if (pr.touching && gen && count_change[id] < 0) {
+            for (int k = 0; k < -count_change[id]; ++k) pop_manifold(P, id);
+        }
+    }
+    uint32_t M = 0, Pn = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
+        for (auto& hnd : P.colors[c].handles) { ++M; Pn += uint32_t(P.pairs[hnd.first].manifolds[hnd.second].pts.size()); }
+    if (out_points) *out_points = Pn;
+    return M;
+}
+
 // NarrowPhase::update (narrow_phase/system_param.rs:114-400) with the fixture manifold generator.
 // kind[n] = AvnBodyKind.  Returns the number of exported manifolds; *out_points = number of points.
 uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* kind, const void* position, const void* rotation, const void* linvel,
@@ -303,35 +358,7 @@ uint32_t avh_narrow_phase(AvhPipeline* h, uint32_t scalar_bits, const uint8_t* k
         else if (!touching && pr.touching) { stopped[id] = 1; changed.push_back(id); }
         else if (count_change[id] != 0) changed.push_back(id);
     }
-    // status changes in ascending ContactId (system_param.rs:136-389)
-    std::sort(changed.begin(), changed.end());
-    for (uint32_t id : changed) {
-        Pair& pr = P.pairs[id];
-        const bool gen = pr.flags & AVN_PAIR_GENERATE_CONSTRAINTS;
-        if (disjoint[id]) {
-            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
-            P.pair_set.erase(pair_key(pr.collider1, pr.collider2));
-            auto it = std::find(P.active.begin(), P.active.end(), id);  // remove_edge_by_id: swap_remove (contact_graph.rs:615-628)
-            if (it != P.active.end()) { *it = P.active.back(); P.active.pop_back(); }
-            pr = Pair{};
-            P.free_ids.push(id);
-        } else if (started[id]) {
-            pr.touching = true;
-            if (gen) for (size_t k = 0; k < pr.manifolds.size(); ++k) push_manifold(P, id);
-        } else if (stopped[id]) {
-            pr.touching = false;
-            if (gen) while (!pr.handles.empty()) pop_manifold(P, id);
-        } else if (pr.touching && gen && count_change[id] > 0) {
-            for (int k = 0; k < count_change[id]; ++k) push_manifold(P, id);
-        } else if (pr.touching && gen && count_change[id] < 0) {
-            for (int k = 0; k < -count_change[id]; ++k) pop_manifold(P, id);
-        }
-    }
-    uint32_t M = 0, Pn = 0;
-    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c)
-        for (auto& hnd : P.colors[c].handles) { ++M; Pn += uint32_t(P.pairs[hnd.first].manifolds[hnd.second].pts.size()); }
-    if (out_points) *out_points = Pn;
-    return M;
+    return apply_status_changes(P, changed, disjoint, started, stopped, count_change, out_points);
 }
 
 // Export the manifolds grouped by colour in manifold_handles order (what prepare_contact_constraints walks,
@@ -381,6 +408,168 @@ void avh_store_impulses(AvhPipeline* h, uint32_t scalar_bits, const void* ws_nor
         Point& pt = P.pairs[r.id].manifolds[r.mi].pts[r.pi];
         pt.ws_normal = n.at(p); pt.ws_tx = t.at(2 * p); pt.ws_ty = t.at(2 * p + 1); pt.normal_impulse = ni.at(p);
     }
+}
+
+// The geometry stage alone for an explicit list of pairs, in the layout of AvnRawManifolds (4 point slots per pair): the CPU side of the
+// device narrow-phase test.  scalar_bits selects the column type; evaluation is in double either way (csrc/narrow_math.hpp).
+void avh_raw_manifolds(uint32_t scalar_bits, uint32_t pair_count, const uint32_t* c1, const uint32_t* c2, const uint32_t* b1, const uint32_t* b2,
+                       const uint8_t* shape, const void* dims, const void* position, const void* rotation, const void* linvel, const void* angvel,
+                       const void* aabb_min, const void* aabb_max, double dt, double tol, uint8_t* point_count, uint8_t* disjoint, void* normal,
+                       void* anchor1, void* anchor2, void* penetration, void* normal_speed, double* anchor1_f64, double* anchor2_f64) {
+    const bool f64 = scalar_bits == 64;
+    Col dm{dims, f64}, pos{position, f64}, rt{rotation, f64}, lv{linvel, f64}, av{angvel, f64}, amin{aabb_min, f64}, amax{aabb_max, f64};
+    ColW on{normal, f64}, oa1{anchor1, f64}, oa2{anchor2, f64}, op{penetration, f64}, os{normal_speed, f64};
+    for (uint32_t k = 0; k < pair_count; ++k) {
+        const uint32_t a = c1[k], b = c2[k];
+        point_count[k] = 0;
+        on.set3(k, V3{0, 0, 0});
+        for (int p = 0; p < 4; ++p) { oa1.set3(4 * size_t(k) + p, V3{0, 0, 0}); oa2.set3(4 * size_t(k) + p, V3{0, 0, 0}); op.set(4 * size_t(k) + p, 0); os.set(4 * size_t(k) + p, 0); }
+        if (aabb_min) {
+            V3 mina = amin.v3(a), maxa = amax.v3(a), minb = amin.v3(b), maxb = amax.v3(b);
+            bool overlap = !(mina.x > maxb.x || maxa.x < minb.x || mina.y > maxb.y || maxa.y < minb.y || mina.z > maxb.z || maxa.z < minb.z);
+            if (disjoint) disjoint[k] = overlap ? 0 : 1;
+            if (!overlap) continue;
+        } else if (disjoint) {
+            disjoint[k] = 0;
+        }
+        V3 pa = pos.v3(a), pb = pos.v3(b);
+        V3 v1 = lv.v3(b1[k]), v2 = lv.v3(b2[k]), w1 = av.v3(b1[k]), w2 = av.v3(b2[k]);
+        V3 rel = v2 - v1;
+        S eff_margin = dt * len(rel);
+        S max_dist = smax(eff_margin, tol);
+        V3 nrm;
+        Contacts pts;
+        int ta = shape ? shape[a] : SHAPE_CUBOID, tb = shape ? shape[b] : SHAPE_CUBOID;
+        if (!collide(ta, dm.v3(a), pa, rt.q(a), tb, dm.v3(b), pb, rt.q(b), max_dist, nrm, pts)) continue;
+        PointOut out[4];
+        int np = manifold_points(pts, nrm, pa, pb, rel, w1, w2, dt, eff_margin, out);
+        point_count[k] = uint8_t(np);
+        on.set3(k, nrm);
+        for (int p = 0; p < np; ++p) {
+            oa1.set3(4 * size_t(k) + p, out[p].anchor1);
+            oa2.set3(4 * size_t(k) + p, out[p].anchor2);
+            if (anchor1_f64)   // unrounded anchors: what the next step's match_contacts compares (the fixture matches in double)
+                for (int c = 0; c < 3; ++c) {
+                    anchor1_f64[(4 * size_t(k) + p) * 3 + c] = comp(out[p].anchor1, c);
+                    anchor2_f64[(4 * size_t(k) + p) * 3 + c] = comp(out[p].anchor2, c);
+                }
+            op.set(4 * size_t(k) + p, out[p].penetration);
+            os.set(4 * size_t(k) + p, out[p].normal_speed);
+        }
+    }
+}
+
+// ---- resident mode: the geometry runs elsewhere (avn_narrow_phase), the host keeps only the graphs -------------
+// The active contact edges in ContactGraph order: edge id (ContactId), colliders, bodies.  Arrays sized avh_pair_count().
+uint32_t avh_active_edges(AvhPipeline* h, uint32_t* ids, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    uint32_t n = 0;
+    for (uint32_t id : P.active) {
+        const Pair& pr = P.pairs[id];
+        ids[n] = id; c1[n] = pr.collider1; c2[n] = pr.collider2; b1[n] = pr.body1; b2[n] = pr.body2;
+        ++n;
+    }
+    return n;
+}
+
+// The host half of the narrow phase from the per-edge results computed elsewhere: point_count[i] (0 = not touching) and disjoint[i] for
+// edge ids[i].  Same status machine, same graph updates as avh_narrow_phase; the manifolds only remember how many points they have.
+uint32_t avh_apply_counts(AvhPipeline* h, const uint8_t* kind, const uint32_t* ids, const uint8_t* point_count, const uint8_t* disjoint_in, uint32_t n,
+                          uint32_t* out_points) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    std::vector<uint32_t> changed;
+    std::vector<uint8_t> disjoint(P.pairs.size(), 0), started(P.pairs.size(), 0), stopped(P.pairs.size(), 0);
+    std::vector<int> count_change(P.pairs.size(), 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t id = ids[i];
+        Pair& pr = P.pairs[id];
+        if (disjoint_in[i]) { disjoint[id] = 1; changed.push_back(id); continue; }
+        pr.static1 = kind[pr.body1] == AVN_BODY_STATIC;
+        pr.static2 = kind[pr.body2] == AVN_BODY_STATIC;
+        const size_t old_count = pr.manifolds.size();
+        pr.manifolds.clear();
+        if (point_count[i] > 0) {
+            Manifold m;
+            m.normal = V3{0, 0, 0};
+            m.pts.resize(point_count[i]);
+            pr.manifolds.push_back(std::move(m));
+        }
+        const bool touching = !pr.manifolds.empty();
+        count_change[id] = int(pr.manifolds.size()) - int(old_count);
+        if (touching && !pr.touching) { started[id] = 1; changed.push_back(id); }
+        else if (!touching && pr.touching) { stopped[id] = 1; changed.push_back(id); }
+        else if (count_change[id] != 0) changed.push_back(id);
+    }
+    return apply_status_changes(P, changed, disjoint, started, stopped, count_change, out_points);
+}
+
+// The constraint graph as a colour-major list of edge ids (manifold_handles order) with the per-edge material (what the solver's prepare
+// needs besides the geometry).  Arrays sized from avh_apply_counts' return value.
+void avh_export_edges(AvhPipeline* h, uint32_t* color_offsets /*[25]*/, uint32_t* edge, int32_t* body1, int32_t* body2, double* friction, double* restitution) {
+    Pipeline& P = *reinterpret_cast<Pipeline*>(h);
+    uint32_t m = 0;
+    for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) {
+        color_offsets[c] = m;
+        for (auto& hnd : P.colors[c].handles) {
+            const Pair& pr = P.pairs[hnd.first];
+            edge[m] = hnd.first;
+            body1[m] = int32_t(pr.body1);
+            body2[m] = int32_t(pr.body2);
+            friction[m] = (P.shapes[pr.collider1].friction + P.shapes[pr.collider2].friction) * 0.5;
+            restitution[m] = (P.shapes[pr.collider1].restitution + P.shapes[pr.collider2].restitution) * 0.5;
+            ++m;
+        }
+    }
+    color_offsets[AVN_GRAPH_COLOR_COUNT] = m;
+}
+
+// match_contacts on edge-indexed resident state (what the device keeps between steps): for edge ids[i] with new_count[i] points whose anchors
+// (double, unrounded: the fixture matches in double) are new_a1/new_a2[i][4][3], carry the warm-start impulses over from the matching old
+// points and make the new points the resident ones.  ws_n[E][4], ws_t[E][4][2] in the column scalar type.
+void avh_match_raw(uint32_t scalar_bits, uint32_t n, const uint32_t* ids, const uint8_t* new_count, const double* new_a1, const double* new_a2,
+                   double length_unit, uint32_t match_contacts, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n, void* ws_t) {
+    const bool f64 = scalar_bits == 64;
+    Col rn{ws_n, f64}, rtg{ws_t, f64};
+    ColW wn{ws_n, f64}, wt{ws_t, f64};
+    const S thr2 = (0.1 * length_unit) * (0.1 * length_unit);
+    for (uint32_t i = 0; i < n; ++i) {
+        const size_t e = ids[i];
+        const int nc = new_count[i], oc = prev_count[e];
+        V3 oa1[4], oa2[4];
+        S on[4], otx[4], oty[4];
+        for (int k = 0; k < oc; ++k) {
+            oa1[k] = V3{prev_a1[(e * 4 + k) * 3], prev_a1[(e * 4 + k) * 3 + 1], prev_a1[(e * 4 + k) * 3 + 2]};
+            oa2[k] = V3{prev_a2[(e * 4 + k) * 3], prev_a2[(e * 4 + k) * 3 + 1], prev_a2[(e * 4 + k) * 3 + 2]};
+            on[k] = rn.at(e * 4 + k); otx[k] = rtg.at((e * 4 + k) * 2); oty[k] = rtg.at((e * 4 + k) * 2 + 1);
+        }
+        for (int k = 0; k < 4; ++k) {
+            S vn = 0, vx = 0, vy = 0;
+            if (k < nc) {
+                const V3 a1{new_a1[(size_t(i) * 4 + k) * 3], new_a1[(size_t(i) * 4 + k) * 3 + 1], new_a1[(size_t(i) * 4 + k) * 3 + 2]};
+                const V3 a2{new_a2[(size_t(i) * 4 + k) * 3], new_a2[(size_t(i) * 4 + k) * 3 + 1], new_a2[(size_t(i) * 4 + k) * 3 + 2]};
+                const int j = match_contacts ? match_point(a1, a2, oa1, oa2, oc, thr2) : -1;
+                if (j >= 0) { vn = on[j]; vx = otx[j]; vy = oty[j]; }
+                for (int c = 0; c < 3; ++c) { prev_a1[(e * 4 + k) * 3 + c] = comp(a1, c); prev_a2[(e * 4 + k) * 3 + c] = comp(a2, c); }
+            }
+            wn.set(e * 4 + k, vn);
+            wt.set((e * 4 + k) * 2, vx);
+            wt.set((e * 4 + k) * 2 + 1, vy);
+        }
+        prev_count[e] = uint8_t(nc);
+    }
+}
+
+// csrc/contact_rows.hpp over host arrays (see rows_narrow above)
+void avh_rows_narrow(uint32_t scalar_bits, uint32_t E, uint32_t* c1, uint32_t* c2, uint32_t* b1, uint32_t* b2, uint8_t* live, uint8_t* count, uint8_t* disjoint,
+                     void* normal, void* a1, void* a2, void* pen, void* ns, uint8_t* prev_count, double* prev_a1, double* prev_a2, void* ws_n_in, void* ws_t_in,
+                     void* ws_n_out, void* ws_t_out, const uint8_t* shape, const void* dims, const void* pos, const void* rot, const void* lv, const void* av,
+                     const void* amin, const void* amax, double dt, double tol, double length_unit, uint32_t match) {
+    if (scalar_bits == 64)
+        rows_narrow<double>(E, c1, c2, b1, b2, live, count, disjoint, normal, a1, a2, pen, ns, prev_count, prev_a1, prev_a2, ws_n_in, ws_t_in, ws_n_out, ws_t_out,
+                            shape, dims, pos, rot, lv, av, amin, amax, dt, tol, length_unit, match);
+    else
+        rows_narrow<float>(E, c1, c2, b1, b2, live, count, disjoint, normal, a1, a2, pen, ns, prev_count, prev_a1, prev_a2, ws_n_in, ws_t_in, ws_n_out, ws_t_out,
+                           shape, dims, pos, rot, lv, av, amin, amax, dt, tol, length_unit, match);
 }
 
 uint32_t avh_pair_count(AvhPipeline* h) { return uint32_t(reinterpret_cast<Pipeline*>(h)->active.size()); }

@@ -251,9 +251,11 @@ class SolverShard:
     manifold_index: np.ndarray   # local manifold -> global manifold
     point_index: np.ndarray      # local contact point -> global contact point
     bnd_body: np.ndarray         # boundary bodies held here: local body index,
-    bnd_slot: np.ndarray         # slot in the global boundary table,
-    bnd_owner: np.ndarray        # owning rank
-    slot_count: int
+    bnd_slot: np.ndarray         # number of the body among all boundary bodies (bookkeeping, tests),
+    bnd_owner: np.ndarray        # owning rank,
+    bnd_source: np.ndarray       # [held, world]: record of the body in rank r's packed table, -1 when rank r does not hold it
+    slot_count: int              # boundary bodies of the whole scene (0: nothing to exchange)
+    record_count: int            # records per rank's table = the busiest rank's list
 
 
 def body_slab_cuts(bodies, world: int) -> np.ndarray:
@@ -318,9 +320,15 @@ def shard_solver(bodies, manifolds, cuts: np.ndarray, rank: int, world: int) -> 
         cols["point_offsets"] = new_po.astype(np.uint32)
         cols["color_offsets"] = np.searchsorted(mine, np.asarray(manifolds.color_offsets, dtype=np.int64), side="left").astype(np.uint32)
         lm = api.Manifolds(**cols)
-    mine_bnd = boundary[held[rank, boundary]]
+    held_b = held[:, boundary]                                  # world x boundary bodies
+    mine_bnd = boundary[held_b[rank]]
+    # every rank packs only what it holds, in slot order: record of a body in rank r's table = its position in r's list
+    pos = np.cumsum(held_b, axis=1) - 1
+    source = np.where(held_b, pos, -1)[:, held_b[rank]].T.astype(np.int32)      # [held here, world]
+    record_count = int(held_b.sum(axis=1).max()) if boundary.size else 0
     return SolverShard(lb, lm, body_index, (owner[body_index] == rank), manifold_index, point_index,
-                       to_local[mine_bnd].astype(np.int32), slot_of_body[mine_bnd].astype(np.int32), owner[mine_bnd].astype(np.int32), int(boundary.size))
+                       to_local[mine_bnd].astype(np.int32), slot_of_body[mine_bnd].astype(np.int32), owner[mine_bnd].astype(np.int32),
+                       np.ascontiguousarray(source), int(boundary.size), record_count)
 
 
 class GpuSlabEngine:
@@ -337,11 +345,11 @@ class GpuSlabEngine:
 
     def begin(self, prm, shard: SolverShard, rank: int, world: int):
         self.ctx.solver_upload(prm, shard.bodies, shard.manifolds, None)
-        self.ctx.solver_set_boundary(shard.bnd_body, shard.bnd_slot, shard.bnd_owner, shard.slot_count, rank, world)
+        self.ctx.solver_set_boundary(shard.bnd_body, shard.bnd_source, shard.bnd_owner, shard.record_count, rank, world)
 
-    def tables(self, slot_count: int, world: int):
+    def tables(self, record_count: int, world: int):
         from avian_b200 import api
-        n = max(slot_count, 1) * api.BOUNDARY_RECORD_SCALARS
+        n = max(record_count, 1) * api.BOUNDARY_RECORD_SCALARS
         return (self.torch.zeros(n, dtype=self.dtype, device=self.device), self.torch.zeros(world * n, dtype=self.dtype, device=self.device))
 
     def run(self, first: int, count: int, flags: int): self.ctx.solver_run_range(first, count, flags)
@@ -374,7 +382,7 @@ def run_slab_step(engines, shards, prm, ranks, world: int, gather, agree_any, up
         for e, sh, r in zip(engines, shards, ranks):
             e.begin(prm, sh, r, world)
     if tabs is None:
-        tabs = [e.tables(slot_count, world) for e in engines]
+        tabs = [e.tables(shards[0].record_count, world) for e in engines]
 
     def exchange():
         if slot_count == 0:

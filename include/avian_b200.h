@@ -297,13 +297,38 @@ AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBod
 AvnStatus avn_solver_run(AvnContext* ctx);
 AvnStatus avn_solver_download(AvnContext* ctx);
 
+/* The same stage fed from EDGE-INDEXED manifold storage: the layout avn_narrow_phase writes (4 point slots per contact edge, indexed by
+ * ContactId) plus the constraint graph as a colour-major list of edge ids.  prepare_contact_constraints reads manifold m through
+ * edge[m]; store_contact_impulses writes the impulses back to the edge's slots.  This is the input form of a device-resident pipeline:
+ * the geometry never has to be compacted or sent through the host, only the edge list changes hands. */
+typedef struct AvnEdgeManifolds {
+    uint32_t count;                                     /* M: manifolds in the constraint graph */
+    uint32_t edge_capacity;                             /* E: rows of the edge-indexed columns */
+    uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];  /* colour c owns edge[off[c], off[c+1]) */
+    const uint32_t* edge;             /* [M] ContactId of manifold m */
+    const int32_t* body1;             /* [M] */
+    const int32_t* body2;
+    const void* friction;             /* [M] */
+    const void* restitution;          /* [M] */
+    const uint8_t* point_count;       /* [E] 0..4 */
+    const void* normal;               /* [E][3] */
+    const void* anchor1;              /* [E][4][3] */
+    const void* anchor2;
+    const void* penetration;          /* [E][4] */
+    const void* normal_speed;         /* [E][4] */
+    void* warm_start_normal_impulse;  /* [E][4]    in/out */
+    void* warm_start_tangent_impulse; /* [E][4][2] in/out */
+    void* normal_impulse;             /* [E][4]    out */
+} AvnEdgeManifolds;
+AvnStatus avn_solver_upload_edges(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints);
+
 /* ---- one coupled scene over several GPUs: the x-slab partition (BASELINE north_star "single all-gather of boundary
  *      state per substep where the scene spans GPUs").  Not a reference interface: the reference is single-process. -------------
  * Each rank uploads its own bodies and constraints plus copies ("ghosts") of the remote bodies its constraints touch.  A body held
  * by more than one rank is a BOUNDARY body; it has one slot in a table every rank agrees on.  Per substep each rank launches
  * avn_solver_run_range for that substep, packs for every boundary body it holds the velocity change its own constraints caused
  * (relative to the velocity right after integrate_velocities, which every holder computes identically) and, if it owns the body,
- * the body's delta_position / delta_rotation; the tables are all-gathered (NCCL, by the caller, on the stream avn_get_stream
+ * the body's delta_position / delta_rotation, into its own packed table (one record per held boundary body); the tables are all-gathered (NCCL, by the caller, on the stream avn_get_stream
  * returns); avn_solver_boundary_apply sets v = v_ref + sum over ranks in rank order of their changes and takes the owner's deltas.
  * Impulses therefore cross a cut once per substep instead of once per constraint: results match the single-GPU step to solver
  * tolerance, not to 1e-5; a scene whose constraints do not cross a cut is reproduced bit for bit. */
@@ -312,15 +337,15 @@ AvnStatus avn_solver_download(AvnContext* ctx);
 #define AVN_RUN_FINALIZE 0x4u     /* writeback_solver_bodies + store_contact_impulses: must be part of the last launch */
 
 typedef struct AvnBoundary {
-    uint32_t count;               /* boundary bodies held by this rank */
-    uint32_t slot_count;          /* slots of the global boundary table */
+    uint32_t count;               /* boundary bodies held by this rank: record k of this rank's table belongs to body[k] */
+    uint32_t record_count;        /* records per rank's table = the largest `count` of any rank (all-gather needs equal sizes) */
     uint32_t rank, world;
     const int32_t* body;          /* [count] index into the uploaded AvnBodyColumns */
-    const int32_t* slot;          /* [count] slot of the body in the global table */
+    const int32_t* source;        /* [count][world] record of body[k] in rank r's table, or -1 when rank r does not hold it */
     const int32_t* owner_rank;    /* [count] the rank whose delta_position / delta_rotation are authoritative */
 } AvnBoundary;
-/* scalars per slot of the exchange table (4 rows of 4): the table is slot_count * AVN_BOUNDARY_RECORD_SCALARS scalars,
- * the gathered tables world times that, rank-major */
+/* scalars per record of the exchange table (4 rows of 4): a table is record_count * AVN_BOUNDARY_RECORD_SCALARS scalars,
+ * the gathered tables world times that, rank-major.  Only held bodies travel: the table is as large as the busiest rank's list. */
 #define AVN_BOUNDARY_RECORD_SCALARS 16
 
 AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags);
@@ -374,6 +399,60 @@ typedef struct AvnColliderColumns {
  * speculative margin), grown by contact_tolerance + collision margin.
  */
 AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColliderColumns* colliders);
+
+/* ---- contact manifolds (SURVEY.md 8f "next #1", geometry stage): one manifold of at most 4 points per contact pair of cuboid / sphere
+ *      colliders.  Stands where NarrowPhase::update calls contact_manifolds (narrow_phase/system_param.rs:437-830,
+ *      collider/parry/contact_query.rs:156-261); the arithmetic is this repository's generator (csrc/narrow_math.hpp — parry3d is not
+ *      vendored), shared with the host fixture.  Matching, the touching state machine and the constraint graph stay on the host. -------- */
+typedef struct AvnNarrowParams {
+    double dt;                         /* Time::delta (narrow_phase/mod.rs:289) */
+    double contact_tolerance;          /* PhysicsLengthUnit * NarrowPhaseConfig::contact_tolerance */
+} AvnNarrowParams;
+
+typedef struct AvnNarrowInput {
+    uint32_t pair_count, collider_count, body_count, _pad;
+    const uint32_t* collider1;         /* [pairs] row of the collider columns below (ascending ContactId order is the caller's business) */
+    const uint32_t* collider2;
+    const uint32_t* body1;             /* [pairs] row of the body velocity columns */
+    const uint32_t* body2;
+    const uint8_t* shape;              /* [C] AvnShape; NULL = cuboid */
+    const void* dims;                  /* [C][3] cuboid half extents / sphere radius in [0] */
+    const void* position;              /* [C][3] collider Position (collider at the body origin, centre of mass at the origin) */
+    const void* rotation;              /* [C][4] */
+    const void* linear_velocity;       /* [B][3] */
+    const void* angular_velocity;      /* [B][3] */
+    const void* aabb_min;              /* [C][3] optional: pairs whose AABBs are disjoint are reported in `disjoint` and skipped */
+    const void* aabb_max;
+} AvnNarrowInput;
+
+typedef struct AvnRawManifolds {      /* fixed stride: 4 point slots per pair, unused slots zero */
+    uint8_t* point_count;              /* [pairs] 0..4 (0 = not touching within the speculative margin) */
+    uint8_t* disjoint;                 /* [pairs] optional */
+    void* normal;                      /* [pairs][3] from collider1 to collider2 */
+    void* anchor1;                     /* [pairs][4][3] */
+    void* anchor2;
+    void* penetration;                 /* [pairs][4] */
+    void* normal_speed;                /* [pairs][4] */
+} AvnRawManifolds;
+
+AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out);
+
+/* ---- device-resident contact edges: the contact pairs, their manifolds and warm-start impulses stay on the device between steps; the host
+ *      keeps the ContactGraph and the ConstraintGraph (contact_graph.rs, constraint_graph.rs) and exchanges a few bytes per edge with the
+ *      device (protocol and its CPU specification: avian_b200/plugins.py ResidentWorld).  Row = ContactId. ---------------------------------- */
+AvnStatus avn_contacts_reserve(AvnContext* ctx, uint32_t capacity);                  /* rows; grows, keeps the existing rows */
+AvnStatus avn_contacts_add(AvnContext* ctx, uint32_t n, const uint32_t* ids, const uint32_t* collider1, const uint32_t* collider2,
+                           const uint32_t* body1, const uint32_t* body2);            /* ContactGraph::add_edge: the row starts without history */
+AvnStatus avn_contacts_remove(AvnContext* ctx, uint32_t n, const uint32_t* ids);     /* ContactGraph::remove_edge */
+/* Geometry + match_contacts for every live row (input: only the collider / body columns of AvnNarrowInput; the pair arrays are ignored).
+ * out_point_count / out_disjoint: [capacity] host arrays — all the host needs for the touching state machine and the graphs. */
+AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts,
+                                    double length_unit, uint8_t* out_point_count, uint8_t* out_disjoint);
+/* The solver stage reading its manifolds from the resident rows: `graph` carries only count, color_offsets, edge, body1, body2, friction,
+ * restitution (host); store_contact_impulses writes into the rows.  Then avn_solver_run / avn_solver_download (bodies only) as usual. */
+AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints);
+/* the impulses of the rows as the last solve left them (tests, tools): [capacity][4], [capacity][4][2], [capacity][4]; any may be NULL */
+AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse);
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 

@@ -127,7 +127,7 @@ struct StepState {
     const SolverBodyInertia<S> dummy_inertia{};
     uint32_t iters = 1;
     // boundary bodies of the x-slab partition (AvnBoundary)
-    std::vector<int> bnd_body, bnd_slot, bnd_owner;
+    std::vector<int> bnd_body, bnd_source, bnd_owner;
     std::vector<V3<S>> ref_lin, ref_ang;
     int bnd_rank = 0, bnd_world = 1;
     size_t bnd_slots = 0;
@@ -467,7 +467,7 @@ struct StepState {
     // ---- boundary exchange of the x-slab partition: the same record layout and arithmetic as boundary_*_kernel (solver_host.cu)
     int set_boundary(const AvnBoundary& b) {
         bnd_body.assign(b.body, b.body + b.count);
-        bnd_slot.assign(b.slot, b.slot + b.count);
+        bnd_source.assign(b.source, b.source + size_t(b.count) * b.world);
         bnd_owner.assign(b.owner_rank, b.owner_rank + b.count);
         for (int x : bnd_body)
             if (x < 0 || size_t(x) >= B) return AVN_ERR_INVALID_ARGUMENT;
@@ -475,7 +475,7 @@ struct StepState {
         ref_ang.assign(b.count, V3<S>{0, 0, 0});
         bnd_rank = int(b.rank);
         bnd_world = int(b.world);
-        bnd_slots = b.slot_count;
+        bnd_slots = b.record_count;
         return AVN_OK;
     }
     void boundary_snapshot() {
@@ -488,7 +488,7 @@ struct StepState {
         std::fill(table, table + bnd_slots * AVN_BOUNDARY_RECORD_SCALARS, S(0));
         for (size_t k = 0; k < bnd_body.size(); ++k) {
             const SolverBody<S>& sb = w.bodies[bnd_body[k]];
-            S* r = table + size_t(bnd_slot[k]) * AVN_BOUNDARY_RECORD_SCALARS;
+            S* r = table + k * AVN_BOUNDARY_RECORD_SCALARS;
             const bool owner = bnd_owner[k] == bnd_rank;
             r[0] = sb.linear_velocity.x - ref_lin[k].x; r[1] = sb.linear_velocity.y - ref_lin[k].y; r[2] = sb.linear_velocity.z - ref_lin[k].z; r[3] = S(1);
             r[4] = sb.angular_velocity.x - ref_ang[k].x; r[5] = sb.angular_velocity.y - ref_ang[k].y; r[6] = sb.angular_velocity.z - ref_ang[k].z;
@@ -504,14 +504,15 @@ struct StepState {
             SolverBody<S>& sb = w.bodies[bnd_body[k]];
             V3<S> l = ref_lin[k], a = ref_ang[k];
             for (int r = 0; r < bnd_world; ++r) {
-                const S* rec = gathered + (size_t(r) * bnd_slots + size_t(bnd_slot[k])) * AVN_BOUNDARY_RECORD_SCALARS;
-                if (rec[3] == S(0)) continue;
+                const int idx = bnd_source[k * size_t(bnd_world) + r];
+                if (idx < 0) continue;
+                const S* rec = gathered + (size_t(r) * bnd_slots + size_t(idx)) * AVN_BOUNDARY_RECORD_SCALARS;
                 l.x = l.x + rec[0]; l.y = l.y + rec[1]; l.z = l.z + rec[2];
                 a.x = a.x + rec[4]; a.y = a.y + rec[5]; a.z = a.z + rec[6];
             }
             sb.linear_velocity = l;
             sb.angular_velocity = a;
-            const S* own = gathered + (size_t(bnd_owner[k]) * bnd_slots + size_t(bnd_slot[k])) * AVN_BOUNDARY_RECORD_SCALARS;
+            const S* own = gathered + (size_t(bnd_owner[k]) * bnd_slots + size_t(bnd_source[k * size_t(bnd_world) + bnd_owner[k]])) * AVN_BOUNDARY_RECORD_SCALARS;
             sb.delta_position = V3<S>{own[8], own[9], own[10]};
             sb.delta_rotation = Quat<S>{own[12], own[13], own[14], own[15]};
         }

@@ -106,7 +106,7 @@ def main():
                        "boundary_bodies": shard.slot_count, "bodies_held_all_ranks": int(held[0]), "manifolds_all_ranks": int(held[1]),
                        "intervals_held_all_ranks": int(held[2]), "colliders": int(aabbs.collider.shape[0]),
                        "collective": "one all-gather of the boundary tables per substep (+ one after the restitution pass)",
-                       "exchange_bytes_per_substep_per_rank": shard.slot_count * api.BOUNDARY_RECORD_SCALARS * bodies.position.dtype.itemsize,
+                       "exchange_bytes_per_substep_per_rank": shard.record_count * api.BOUNDARY_RECORD_SCALARS * bodies.position.dtype.itemsize,
                        "parity": "solver tolerance across cuts (impulses cross a cut once per substep); broad phase bit-exact"},
             "e2e": {"value": K / (e2e_ms / 1e3), "unit": "steps/s", "ms_per_step": e2e_ms / K}}), flush=True)
     ctx.close()

@@ -113,12 +113,12 @@ class OracleSlabEngine:
                                            self.threads)
             assert self.h, "oracle step_begin failed"
             sh = self.shard
-            self._bnd = tuple(np.ascontiguousarray(x, dtype=np.int32) for x in (sh.bnd_body, sh.bnd_slot, sh.bnd_owner))
-            b = api.AvnBoundary(int(self._bnd[0].shape[0]), int(sh.slot_count), self.rank, self.world, *(x.ctypes.data for x in self._bnd))
+            self._bnd = tuple(np.ascontiguousarray(x, dtype=np.int32) for x in (sh.bnd_body, sh.bnd_source, sh.bnd_owner))
+            b = api.AvnBoundary(int(self._bnd[0].shape[0]), int(sh.record_count), self.rank, self.world, *(x.ctypes.data for x in self._bnd))
             assert self.l.orc_step_set_boundary(self.h, C.byref(b)) == 0
 
-    def tables(self, slot_count: int, world: int):
-        n = max(slot_count, 1) * api.BOUNDARY_RECORD_SCALARS
+    def tables(self, record_count: int, world: int):
+        n = max(record_count, 1) * api.BOUNDARY_RECORD_SCALARS
         return np.zeros(n, dtype=self.dtype), np.zeros(world * n, dtype=self.dtype)
 
     def run(self, first: int, count: int, flags: int):
