@@ -69,7 +69,7 @@ class AvnJointSet(C.Structure):
 
 
 class AvnAabbColumns(C.Structure):
-    _fields_ = [("count", C.c_uint32), ("_pad", C.c_uint32)] + [
+    _fields_ = [("count", C.c_uint32), ("retained_count", C.c_uint32)] + [
         (n, _vp) for n in ("collider", "body", "aabb_min", "aabb_max", "memberships", "filters", "flags", "order_out")] + [
         ("existing_pairs", _vp), ("existing_pair_count", C.c_uint64), ("joint_disabled_body_pairs", _vp), ("joint_disabled_pair_count", C.c_uint64)]
 
@@ -90,7 +90,7 @@ class AvnColliderColumns(C.Structure):
 
 class AvnTimings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "prepare_ms", "substep_loop_ms", "finalize_ms", "d2h_ms", "broad_phase_ms", "total_ms")] + [
-        (n, C.c_uint32) for n in ("kernel_launches", "contact_constraint_count", "joint_levels", "active_colors", "_pad")]
+        (n, C.c_uint32) for n in ("kernel_launches", "contact_constraint_count", "joint_levels", "active_colors", "launch_mode")]
 
 
 class AvianError(RuntimeError):
@@ -271,6 +271,7 @@ class Aabbs:
     order_out: np.ndarray | None = None
     existing_pairs: np.ndarray | None = None          # uint64
     joint_disabled_body_pairs: np.ndarray | None = None
+    retained_count: int | None = None                 # out: entries of order_out (intervals with a non-finite AABB are dropped)
 
     def as_struct(self) -> AvnAabbColumns:
         s = AvnAabbColumns()
@@ -539,6 +540,7 @@ class Context:
             st = self.lib.avn_broadphase_download(self.handle, C.byref(s))
         self._check(st)
         out.count = int(s.count)
+        aabbs.retained_count = int(a.retained_count)
         return out.trimmed()
 
     def broadphase_upload(self, aabbs: Aabbs) -> None:
@@ -553,6 +555,7 @@ class Context:
         s = out.as_struct()
         self._check(self.lib.avn_broadphase_download(self.handle, C.byref(s)))
         out.count = int(s.count)
+        self._keep_bp[0].retained_count = int(self._keep_bp[1].retained_count)
         return out
 
     # ---- x-slab partition (include/avian_b200.h "one coupled scene over several GPUs")

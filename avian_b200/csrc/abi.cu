@@ -1,6 +1,8 @@
 // extern "C" surface of libavian_b200.so (declared in include/avian_b200.h).
+#include <cstring>
 #include <memory>
 #include <mutex>
+#include <new>
 
 #include "context.hpp"
 #include "joint_schedule.hpp"
@@ -28,6 +30,24 @@ AvnStatus create_fail(AvnStatus code, const std::string& msg) {
     return code;
 }
 bool bind(AvnContext* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess; }
+
+// "nothing throws or aborts across the ABI": every entry point that reaches C++ code which may allocate (std::vector, std::string, new) runs
+// inside this guard; an exception becomes a status code and a message.
+template <class F>
+AvnStatus guarded(AvnContext* ctx, F&& body) noexcept {
+    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
+    try {
+        if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
+        return body();
+    } catch (const std::bad_alloc&) {
+        try { return ctx->err.fail(AVN_ERR_OUT_OF_MEMORY, "host allocation failed"); } catch (...) { return AVN_ERR_OUT_OF_MEMORY; }
+    } catch (const std::exception& e) {
+        try { return ctx->err.fail(AVN_ERR_INVALID_ARGUMENT, "internal error: %s", e.what()); } catch (...) { return AVN_ERR_INVALID_ARGUMENT; }
+    } catch (...) {
+        return AVN_ERR_INVALID_ARGUMENT;
+    }
+}
+thread_local char t_create_error[512];
 }  // namespace
 
 extern "C" {
@@ -37,31 +57,42 @@ uint32_t avn_abi_version(void) { return AVN_ABI_VERSION; }
 AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
     if (!config || !out_ctx) return create_fail(AVN_ERR_INVALID_ARGUMENT, "config and out_ctx are required");
     *out_ctx = nullptr;
-    if (config->abi_version != AVN_ABI_VERSION) return create_fail(AVN_ERR_INVALID_ARGUMENT, "ABI version mismatch");
-    if (config->scalar_bits != 32 && config->scalar_bits != 64) return create_fail(AVN_ERR_INVALID_ARGUMENT, "scalar_bits must be 32 or 64");
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return create_fail(AVN_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
-    if (config->device < 0 || config->device >= count) return create_fail(AVN_ERR_INVALID_ARGUMENT, "device ordinal out of range");
-    if ((e = cudaSetDevice(config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
-    if (prop.major != 10)
-        return create_fail(AVN_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; device is ") + prop.name + " (sm_" +
-                                                    std::to_string(prop.major) + std::to_string(prop.minor) + ")");
-    auto ctx = std::make_unique<AvnContext>();
-    ctx->device = config->device;
-    ctx->scalar_bits = config->scalar_bits;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
-    ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
-    ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
-    ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
-    ctx->narrow.reset(avn::make_narrow(config->scalar_bits, ctx->stream, &ctx->err));
-    ctx->contacts.reset(avn::make_contacts(config->scalar_bits, ctx->stream, &ctx->err));
-    if (!ctx->solver || !ctx->broadphase || !ctx->aabbs || !ctx->narrow || !ctx->contacts) return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
-    *out_ctx = ctx.release();
-    return AVN_OK;
+    cudaStream_t stream = nullptr;
+    try {
+        if (config->abi_version != AVN_ABI_VERSION) return create_fail(AVN_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+        if (config->scalar_bits != 32 && config->scalar_bits != 64) return create_fail(AVN_ERR_INVALID_ARGUMENT, "scalar_bits must be 32 or 64");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return create_fail(AVN_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+        if (config->device < 0 || config->device >= count) return create_fail(AVN_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+        if ((e = cudaSetDevice(config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, config->device)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+        if (prop.major != 10)
+            return create_fail(AVN_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; device is ") + prop.name + " (sm_" +
+                                                        std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+        auto ctx = std::make_unique<AvnContext>();
+        ctx->device = config->device;
+        ctx->scalar_bits = config->scalar_bits;
+        if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return create_fail(AVN_ERR_CUDA, cudaGetErrorString(e));
+        ctx->stream = stream;
+        ctx->solver.reset(avn::make_solver(config->scalar_bits, ctx->stream, &ctx->err, config->flags, config->device));
+        ctx->broadphase.reset(avn::make_broadphase(config->scalar_bits, ctx->stream, &ctx->err, config->device));
+        ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
+        ctx->narrow.reset(avn::make_narrow(config->scalar_bits, ctx->stream, &ctx->err));
+        ctx->contacts.reset(avn::make_contacts(config->scalar_bits, ctx->stream, &ctx->err));
+        if (!ctx->solver || !ctx->broadphase || !ctx->aabbs || !ctx->narrow || !ctx->contacts) {
+            ctx.reset();   // the members hold the stream: release them before it goes
+            cudaStreamDestroy(stream);
+            return create_fail(AVN_ERR_UNSUPPORTED, "scalar type not available");
+        }
+        *out_ctx = ctx.release();
+        return AVN_OK;
+    } catch (...) {
+        if (stream) cudaStreamDestroy(stream);
+        try { return create_fail(AVN_ERR_OUT_OF_MEMORY, "host allocation failed in avn_create"); } catch (...) { return AVN_ERR_OUT_OF_MEMORY; }
+    }
 }
 
 void avn_destroy(AvnContext* ctx) {
@@ -79,8 +110,10 @@ void avn_destroy(AvnContext* ctx) {
 
 const char* avn_last_error(const AvnContext* ctx) {
     if (ctx) return ctx->err.msg.c_str();
-    std::lock_guard<std::mutex> lk(g_create_mutex);
-    return g_create_error.c_str();
+    std::lock_guard<std::mutex> lk(g_create_mutex);   // copied under the lock: the returned pointer stays valid for this thread
+    std::strncpy(t_create_error, g_create_error.c_str(), sizeof t_create_error - 1);
+    t_create_error[sizeof t_create_error - 1] = 0;
+    return t_create_error;
 }
 
 AvnStatus avn_alloc_pinned(AvnContext* ctx, size_t bytes, void** out_ptr) {
@@ -100,44 +133,28 @@ AvnStatus avn_free_pinned(AvnContext* ctx, void* ptr) {
 }
 
 AvnStatus avn_solver_upload(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->upload(params, bodies, manifolds, joints);
+    return guarded(ctx, [&] { return ctx->solver->upload(params, bodies, manifolds, joints); });
 }
 AvnStatus avn_solver_run(AvnContext* ctx) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->run();
+    return guarded(ctx, [&] { return ctx->solver->run(); });
 }
 AvnStatus avn_solver_upload_edges(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->upload_edges(params, bodies, manifolds, joints);
+    return guarded(ctx, [&] { return ctx->solver->upload_edges(params, bodies, manifolds, joints); });
 }
 AvnStatus avn_solver_run_range(AvnContext* ctx, uint32_t first_substep, uint32_t substep_count, uint32_t run_flags) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->run_range(first_substep, substep_count, run_flags);
+    return guarded(ctx, [&] { return ctx->solver->run_range(first_substep, substep_count, run_flags); });
 }
 AvnStatus avn_solver_set_boundary(AvnContext* ctx, const AvnBoundary* boundary) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->set_boundary(boundary);
+    return guarded(ctx, [&] { return ctx->solver->set_boundary(boundary); });
 }
 AvnStatus avn_solver_boundary_snapshot(AvnContext* ctx) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->boundary_snapshot();
+    return guarded(ctx, [&] { return ctx->solver->boundary_snapshot(); });
 }
 AvnStatus avn_solver_boundary_pack(AvnContext* ctx, void* device_table) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->boundary_pack(device_table);
+    return guarded(ctx, [&] { return ctx->solver->boundary_pack(device_table); });
 }
 AvnStatus avn_solver_boundary_apply(AvnContext* ctx, const void* device_gathered) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->solver->boundary_apply(device_gathered);
+    return guarded(ctx, [&] { return ctx->solver->boundary_apply(device_gathered); });
 }
 AvnStatus avn_solver_needs_restitution(AvnContext* ctx, int* out_nonzero) {
     if (!ctx || !out_nonzero) return AVN_ERR_INVALID_ARGUMENT;
@@ -150,11 +167,11 @@ AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream) {
     return AVN_OK;
 }
 AvnStatus avn_solver_download(AvnContext* ctx) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    AvnStatus st = ctx->solver->download();
-    ctx->solver->timings(&ctx->last);
-    return st;
+    return guarded(ctx, [&] {
+        AvnStatus st = ctx->solver->download();
+        ctx->solver->timings(&ctx->last);
+        return st;
+    });
 }
 AvnStatus avn_solver_step(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnManifoldColumns* manifolds, AvnJointSet* joints) {
     AvnStatus st = avn_solver_upload(ctx, params, bodies, manifolds, joints);
@@ -164,21 +181,17 @@ AvnStatus avn_solver_step(AvnContext* ctx, const AvnStepParams* params, AvnBodyC
 }
 
 AvnStatus avn_broadphase_upload(AvnContext* ctx, AvnAabbColumns* aabbs) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->broadphase->upload(aabbs);
+    return guarded(ctx, [&] { return ctx->broadphase->upload(aabbs); });
 }
 AvnStatus avn_broadphase_run(AvnContext* ctx) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->broadphase->run();
+    return guarded(ctx, [&] { return ctx->broadphase->run(); });
 }
 AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    AvnStatus st = ctx->broadphase->download(out_pairs);
-    ctx->broadphase->timings(&ctx->last);
-    return st;
+    return guarded(ctx, [&] {
+        AvnStatus st = ctx->broadphase->download(out_pairs);
+        ctx->broadphase->timings(&ctx->last);
+        return st;
+    });
 }
 AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* out_pairs) {
     AvnStatus st = avn_broadphase_upload(ctx, aabbs);
@@ -188,39 +201,28 @@ AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* ou
 }
 
 AvnStatus avn_update_aabbs(AvnContext* ctx, const AvnAabbParams* params, AvnColliderColumns* colliders) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->aabbs->update(params, colliders);
+    return guarded(ctx, [&] { return ctx->aabbs->update(params, colliders); });
 }
 
 AvnStatus avn_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, AvnRawManifolds* out) {
-    if (!ctx) return AVN_ERR_INVALID_ARGUMENT;
-    if (!bind(ctx)) return ctx->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed");
-    return ctx->narrow->run(params, input, out);
+    return guarded(ctx, [&] { return ctx->narrow->run(params, input, out); });
 }
 
-#define AVN_ENTER(ctx)                                                             \
-    if (!(ctx)) return AVN_ERR_INVALID_ARGUMENT;                                   \
-    if (!bind(ctx)) return (ctx)->err.fail(AVN_ERR_CUDA, "cudaSetDevice failed")
-AvnStatus avn_contacts_reserve(AvnContext* ctx, uint32_t capacity) { AVN_ENTER(ctx); return ctx->contacts->reserve(capacity); }
+AvnStatus avn_contacts_reserve(AvnContext* ctx, uint32_t capacity) { return guarded(ctx, [&] { return ctx->contacts->reserve(capacity); }); }
 AvnStatus avn_contacts_add(AvnContext* ctx, uint32_t n, const uint32_t* ids, const uint32_t* collider1, const uint32_t* collider2, const uint32_t* body1,
                            const uint32_t* body2) {
-    AVN_ENTER(ctx);
-    return ctx->contacts->add(n, ids, collider1, collider2, body1, body2);
+    return guarded(ctx, [&] { return ctx->contacts->add(n, ids, collider1, collider2, body1, body2); });
 }
-AvnStatus avn_contacts_remove(AvnContext* ctx, uint32_t n, const uint32_t* ids) { AVN_ENTER(ctx); return ctx->contacts->remove(n, ids); }
+AvnStatus avn_contacts_remove(AvnContext* ctx, uint32_t n, const uint32_t* ids) { return guarded(ctx, [&] { return ctx->contacts->remove(n, ids); }); }
 AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts, double length_unit,
                                     uint8_t* out_point_count, uint8_t* out_disjoint) {
-    AVN_ENTER(ctx);
-    return ctx->contacts->narrow_phase(params, input, match_contacts, length_unit, out_point_count, out_disjoint);
+    return guarded(ctx, [&] { return ctx->contacts->narrow_phase(params, input, match_contacts, length_unit, out_point_count, out_disjoint); });
 }
 AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints) {
-    AVN_ENTER(ctx);
-    return ctx->solver->upload_graph(params, bodies, graph, ctx->contacts.get(), joints);
+    return guarded(ctx, [&] { return ctx->solver->upload_graph(params, bodies, graph, ctx->contacts.get(), joints); });
 }
 AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse) {
-    AVN_ENTER(ctx);
-    return ctx->contacts->download_impulses(warm_start_normal, warm_start_tangent, normal_impulse);
+    return guarded(ctx, [&] { return ctx->contacts->download_impulses(warm_start_normal, warm_start_tangent, normal_impulse); });
 }
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {
@@ -231,6 +233,7 @@ AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out) {
 
 AvnStatus avn_joint_levels(const AvnBodyColumns* bodies, const AvnJointSet* joints, uint32_t* out_level, uint32_t* out_level_count) {
     if (!bodies || !joints) return AVN_ERR_INVALID_ARGUMENT;
+    try {
     avn::JointSchedule sch;
     std::string error;
     AvnStatus st = avn::build_joint_schedule(*bodies, *joints, sch, error);
@@ -239,6 +242,9 @@ AvnStatus avn_joint_levels(const AvnBodyColumns* bodies, const AvnJointSet* join
         for (size_t g = 0; g < sch.level_of_global.size(); ++g) out_level[g] = uint32_t(sch.level_of_global[g]);
     if (out_level_count) *out_level_count = uint32_t(sch.n_levels);
     return AVN_OK;
+    } catch (...) {
+        return AVN_ERR_OUT_OF_MEMORY;
+    }
 }
 
 }  // extern "C"

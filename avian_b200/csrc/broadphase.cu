@@ -14,7 +14,10 @@
 //      emit pass into a (rank i, rank j) buffer, per-interval segment sort by j, materialisation of the ABI columns.  Intervals
 //      with a huge x-window (a ground slab) are swept brute force by sweep_wide_kernel, one block per 4 096 candidates.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "avn_math.cuh"
 #include "context.hpp"
@@ -42,11 +45,19 @@ __device__ __forceinline__ uint64_t sortable(double f) {
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// Also raises *nonfinite when any component of an AABB is NaN or infinite: the reference drops such intervals in update_aabb_intervals
+// (broad_phase.rs:243-245); here the host then compacts the columns and runs again (Broadphase::drop_nonfinite), the common case pays one
+// flag per step.
 template <class S>
-__global__ void make_keys(const S* __restrict__ aabb_min, int n, typename KeyOf<S>::type* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void make_keys(const S* __restrict__ aabb_min, const S* __restrict__ aabb_max, int n, typename KeyOf<S>::type* __restrict__ keys,
+                          uint32_t* __restrict__ vals, unsigned long long* __restrict__ nonfinite) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        keys[i] = sortable(aabb_min[3 * i]);
+        const S a = aabb_min[3 * i], b = aabb_min[3 * i + 1], c = aabb_min[3 * i + 2], d = aabb_max[3 * i], e = aabb_max[3 * i + 1], f = aabb_max[3 * i + 2];
+        // x - x is 0 for finite x and NaN for NaN / +-inf
+        const S z = (a - a) + (b - b) + (c - c) + (d - d) + (e - e) + (f - f);
+        if (!(z == S(0))) *nonfinite = 1ull;
+        keys[i] = sortable(a);
         vals[i] = uint32_t(i);
     }
 }
@@ -448,12 +459,15 @@ class Broadphase final : public BroadphaseBase {
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sm_count_ = prop.multiProcessorCount;
         cudaEventCreate(&ev0_);
         cudaEventCreate(&ev1_);
-        cudaHostAlloc(&h_total_, sizeof(uint64_t), cudaHostAllocDefault);
+        cudaHostAlloc(&h_total_, 2 * sizeof(uint64_t), cudaHostAllocDefault);   // [0] pair count, [1] non-finite flag
+        const char* g = getenv("AVN_BP_GRAPH");
+        use_graph_ = !(g && !strcmp(g, "0"));
     }
     ~Broadphase() override {
         cudaEventDestroy(ev0_);
         cudaEventDestroy(ev1_);
         if (h_total_) cudaFreeHost(h_total_);
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
     }
     AvnStatus upload(AvnAabbColumns* a) override;
     AvnStatus run() override;
@@ -470,6 +484,44 @@ class Broadphase final : public BroadphaseBase {
         return AVN_OK;
     }
     AvnStatus build_set(DevBuf& keys_buf, DevBuf& table_buf, const uint64_t* host_keys, uint64_t count, const uint64_t** table, uint64_t* mask);
+    static constexpr int WIDE_ROWS = 64;
+    uint32_t graph_replays_ = 0;
+    Sweep<S> sweep_desc() const {
+        Sweep<S> sw;
+        sw.n = n_; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
+        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
+        sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
+        return sw;
+    }
+    CellSweep<S> cell_desc() const {
+        CellSweep<S> cs;
+        cs.grid = grid_.as<CellGrid<S>>(); cs.cranks = cv0_.as<uint32_t>(); cs.cstart = cbounds_.as<int>(); cs.cend = cbounds_.as<int>() + 0x10000;
+        return cs;
+    }
+    AvnStatus ensure_buffers(int n);
+    void enqueue_front(int n);          // every launch from make_keys to the pair-count readback: no allocation, no synchronisation
+    AvnStatus drop_nonfinite();
+
+    // The front part of a run is a fixed sequence of ~25 small launches (3-15 us each): captured once into a CUDA graph and replayed as long
+    // as the interval count and every buffer address stay the same (buffers are grow-only, so a steady scene replays forever).
+    struct GraphKey {
+        int n = -1;
+        const void* p[24] = {};
+        uint64_t m[2] = {};
+        bool operator==(const GraphKey& o) const { return n == o.n && !memcmp(p, o.p, sizeof p) && !memcmp(m, o.m, sizeof m); }
+    };
+    GraphKey graph_key() const;
+    bool use_graph_ = true;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    GraphKey graph_key_{};
+    uint32_t front_launches_ = 0;
+    DevBuf nf_flag_;
+    // update_aabb_intervals' retain (broad_phase.rs:243-245): set when non-finite intervals were dropped from this upload
+    bool dropped_ = false;
+    std::vector<uint32_t> keep_;        // compacted row -> row of the caller's columns
+    std::vector<unsigned char> c_min_, c_max_;
+    std::vector<uint32_t> c_col_, c_body_, c_memb_, c_filt_;
+    std::vector<uint8_t> c_flags_;
 
     cudaStream_t stream_;
     ErrorSink* err_;
@@ -477,11 +529,12 @@ class Broadphase final : public BroadphaseBase {
     cudaEvent_t ev0_, ev1_;
     uint64_t* h_total_ = nullptr;
     AvnTimings tm_{};
-    uint32_t launches_ = 0;
+    uint32_t launches_ = 0, upload_launches_ = 0;
     bool uploaded_ = false, ran_ = false;
     int n_ = 0;
     uint64_t pair_capacity_ = 0;
     AvnAabbColumns host_{};
+    AvnAabbColumns* caller_ = nullptr;   // retained_count is written back at download
     const S* d_min_ = nullptr; const S* d_max_ = nullptr;
     const uint32_t* d_collider_ = nullptr; const uint32_t* d_body_ = nullptr; const uint32_t* d_memb_ = nullptr; const uint32_t* d_filt_ = nullptr;
     const uint8_t* d_flags_ = nullptr;
@@ -518,11 +571,15 @@ AvnStatus Broadphase<S>::upload(AvnAabbColumns* a) {
     if (!a) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs is required");
     if (a->count && (!a->collider || !a->body || !a->aabb_min || !a->aabb_max))
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs: collider, body, aabb_min and aabb_max are required");
+    a->retained_count = a->count;
     if (a->count > 0x7fffffffu - RS_TILE) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "aabbs: too many intervals");
     uploaded_ = ran_ = false;
     launches_ = 0;
+    upload_launches_ = 0;
+    dropped_ = false;
     n_ = int(a->count);
     host_ = *a;
+    caller_ = a;
     const size_t n = a->count;
     AvnStatus st;
 #define UPB(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
@@ -536,109 +593,172 @@ AvnStatus Broadphase<S>::upload(AvnAabbColumns* a) {
 #undef UPB
     if ((st = build_set(b_exk_, b_ext_, a->existing_pairs, a->existing_pair_count, &d_existing_, &existing_mask_)) != AVN_OK) return st;
     if ((st = build_set(b_jdk_, b_jdt_, a->joint_disabled_body_pairs, a->joint_disabled_pair_count, &d_jdis_, &jdis_mask_)) != AVN_OK) return st;
+    upload_launches_ = launches_;
     uploaded_ = true;
     return AVN_OK;
+}
+
+template <class S>
+AvnStatus Broadphase<S>::ensure_buffers(int n) {
+    const int nblocks = (n + RS_TILE - 1) / RS_TILE;
+    AVN_CUDA(k0_.ensure(size_t(n) * sizeof(K))); AVN_CUDA(k1_.ensure(size_t(n) * sizeof(K)));
+    AVN_CUDA(v0_.ensure(size_t(n) * 4)); AVN_CUDA(v1_.ensure(size_t(n) * 4));
+    AVN_CUDA(hist_.ensure(size_t(256) * nblocks * 4));
+    AVN_CUDA(s_minx_.ensure(size_t(n) * sizeof(S))); AVN_CUDA(s_maxx_.ensure(size_t(n) * sizeof(S)));
+    AVN_CUDA(s_yz_.ensure(size_t(n) * sizeof(Vec4<S>))); AVN_CUDA(s_meta_.ensure(size_t(n) * sizeof(uint4)));
+    AVN_CUDA(s_flags_.ensure(size_t(n))); AVN_CUDA(s_end_.ensure(size_t(n) * 4));
+    AVN_CUDA(counts_.ensure(size_t(n) * 4)); AVN_CUDA(offsets_.ensure((size_t(n) + 1) * 8));
+    AVN_CUDA(grid_.ensure(sizeof(CellGrid<S>)));
+    AVN_CUDA(ck0_.ensure(size_t(n) * 4)); AVN_CUDA(ck1_.ensure(size_t(n) * 4)); AVN_CUDA(cv0_.ensure(size_t(n) * 4)); AVN_CUDA(cv1_.ensure(size_t(n) * 4));
+    AVN_CUDA(cbounds_.ensure(size_t(2) * 0x10000 * 4));
+    AVN_CUDA(stats_.ensure(size_t(YZ_BLOCKS) * sizeof(YzPartial<S>)));
+    AVN_CUDA(stats2_.ensure(size_t(2) * YZ_BLOCKS * sizeof(S)));
+    AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
+    AVN_CUDA(wide_flag_.ensure(size_t(n)));
+    const int nsub = (n + SW_SUB - 1) / SW_SUB;
+    AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
+    AVN_CUDA(block_sums_.ensure(size_t((n + 1023) / 1024) * 8));
+    AVN_CUDA(nf_flag_.ensure(8));
+    return AVN_OK;
+}
+
+template <class S>
+typename Broadphase<S>::GraphKey Broadphase<S>::graph_key() const {
+    GraphKey k;
+    k.n = n_;
+    const void* ptrs[] = {d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_, d_existing_, d_jdis_, k0_.p, k1_.p, v0_.p, v1_.p, hist_.p,
+                          s_minx_.p, s_maxx_.p, s_yz_.p, s_meta_.p, s_flags_.p, s_end_.p, counts_.p, offsets_.p, grid_.p, ck0_.p};
+    static_assert(sizeof ptrs == sizeof k.p, "graph key size");
+    memcpy(k.p, ptrs, sizeof ptrs);
+    // the remaining buffers are allocated together with the ones above (same n): their addresses change only when those do
+    k.m[0] = existing_mask_ ^ (uint64_t(uintptr_t(cv0_.p)) << 1) ^ (uint64_t(uintptr_t(wide_sub_.p)) << 2);
+    k.m[1] = jdis_mask_ ^ (uint64_t(uintptr_t(cbounds_.p)) << 1) ^ (uint64_t(uintptr_t(block_sums_.p)) << 2) ^ (uint64_t(uintptr_t(wide_flag_.p)) << 3);
+    return k;
+}
+
+template <class S>
+void Broadphase<S>::enqueue_front(int n) {
+    const int nblocks = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t launches = 0;
+    K* ka = k0_.as<K>(); K* kb = k1_.as<K>();
+    uint32_t* va = v0_.as<uint32_t>(); uint32_t* vb = v1_.as<uint32_t>();
+    cudaMemsetAsync(nf_flag_.p, 0, 8, stream_);
+    make_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_min_, d_max_, n, ka, va, nf_flag_.as<unsigned long long>());
+    ++launches;
+    for (int pass = 0; pass < KeyOf<S>::passes; ++pass) {
+        const int shift = 8 * pass;
+        rs_histogram<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, n, shift, hist_.as<uint32_t>(), nblocks);
+        if (nblocks <= RS_FUSE_MAX_BLOCKS) {
+            rs_scatter<K, true><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+        } else {
+            rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+            rs_scatter<K, false><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+        }
+        launches += nblocks <= RS_FUSE_MAX_BLOCKS ? 2 : 3;
+        std::swap(ka, kb);
+        std::swap(va, vb);
+    }
+    d_order_ = va;  // even number of passes: back in buffer 0
+    gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
+                                                           s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
+                                                           s_flags_.as<uint8_t>());
+    // (y, z) cell grid under the x-sorted ranks: stats -> cell ids -> stable 2-pass radix sort of the ranks by cell id -> cell bounds
+    CellGrid<S>* d_grid = grid_.as<CellGrid<S>>();
+    int* cstart = cbounds_.as<int>();
+    int* cend = cbounds_.as<int>() + 0x10000;
+    yz_stats<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, stats_.as<YzPartial<S>>());
+    yz_fold<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), YZ_BLOCKS, n, d_grid);
+    yz_small_max<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, stats2_.as<S>());
+    yz_grid<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), stats2_.as<S>(), YZ_BLOCKS, n, d_grid);
+    int* wide_count = wide_.as<int>();
+    int* wide_list = wide_.as<int>() + 1;
+    cudaMemsetAsync(wide_count, 0, 4, stream_);
+    sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), d_grid, n, s_end_.as<int>(), wide_list, wide_count,
+                                                          wide_flag_.as<uint8_t>(), s_flags_.as<uint8_t>());
+    const Sweep<S> sw = sweep_desc();
+    cell_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, ck0_.as<uint32_t>(), cv0_.as<uint32_t>());
+    {
+        uint32_t* cka = ck0_.as<uint32_t>(); uint32_t* ckb = ck1_.as<uint32_t>();
+        uint32_t* cva = cv0_.as<uint32_t>(); uint32_t* cvb = cv1_.as<uint32_t>();
+        for (int pass = 0; pass < 2; ++pass) {
+            rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, n, 8 * pass, hist_.as<uint32_t>(), nblocks);
+            if (nblocks <= RS_FUSE_MAX_BLOCKS) {
+                rs_scatter<uint32_t, true><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+            } else {
+                rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+                rs_scatter<uint32_t, false><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
+            }
+            std::swap(cka, ckb);
+            std::swap(cva, cvb);
+        }
+    }
+    cudaMemsetAsync(cstart, 0x7f, size_t(0x10000) * 4, stream_);
+    cudaMemsetAsync(cend, 0, size_t(0x10000) * 4, stream_);
+    cell_bounds<<<(n + 255) / 256, 256, 0, stream_>>>(ck0_.as<uint32_t>(), n, cstart, cend);
+    const CellSweep<S> cs = cell_desc();
+    const int grid = std::min((n + (256 / CG_GROUP) - 1) / (256 / CG_GROUP), sm_count_ * 32);
+    sweep_cells_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, cs, counts_.as<uint32_t>(), nullptr, nullptr);
+    // intervals with a huge x-window: brute force, one block per SW_SUB candidates; the grid's y dimension strides the wide list
+    const int nsub = (n + SW_SUB - 1) / SW_SUB;
+    sweep_wide_kernel<S, false><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr);
+    wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
+    launches += nblocks <= RS_FUSE_MAX_BLOCKS ? 15 : 17;
+    const int sblocks = (n + 1023) / 1024;
+    scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
+    scan_block_offsets<<<1, 1024, 0, stream_>>>(block_sums_.as<uint64_t>(), sblocks, offsets_.as<uint64_t>() + n);
+    scan_apply<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>(), offsets_.as<uint64_t>());
+    launches += 3;
+    // the pair count decides the size of the output buffers: one 16-byte readback (count + non-finite flag)
+    cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(h_total_ + 1, nf_flag_.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_);
+    front_launches_ = launches;
 }
 
 template <class S>
 AvnStatus Broadphase<S>::run() {
     if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_broadphase_run before avn_broadphase_upload");
     const int n = n_;
+    launches_ = upload_launches_;   // launches of THIS run (+ the hash-set builds of its upload), not of every run since the upload
     cudaEventRecord(ev0_, stream_);
-    *h_total_ = 0;
+    h_total_[0] = 0;
+    h_total_[1] = 0;
     if (n > 0) {
-        const int nblocks = (n + RS_TILE - 1) / RS_TILE;
-        AVN_CUDA(k0_.ensure(size_t(n) * sizeof(K))); AVN_CUDA(k1_.ensure(size_t(n) * sizeof(K)));
-        AVN_CUDA(v0_.ensure(size_t(n) * 4)); AVN_CUDA(v1_.ensure(size_t(n) * 4));
-        AVN_CUDA(hist_.ensure(size_t(256) * nblocks * 4));
-        K* ka = k0_.as<K>(); K* kb = k1_.as<K>();
-        uint32_t* va = v0_.as<uint32_t>(); uint32_t* vb = v1_.as<uint32_t>();
-        make_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_min_, n, ka, va);
-        ++launches_;
-        for (int pass = 0; pass < KeyOf<S>::passes; ++pass) {
-            const int shift = 8 * pass;
-            rs_histogram<K><<<nblocks, RS_THREADS, 0, stream_>>>(ka, n, shift, hist_.as<uint32_t>(), nblocks);
-            if (nblocks <= RS_FUSE_MAX_BLOCKS) {
-                rs_scatter<K, true><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
-            } else {
-                rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
-                rs_scatter<K, false><<<nblocks, RS_THREADS, 0, stream_>>>(ka, va, n, shift, hist_.as<uint32_t>(), nblocks, kb, vb);
+        AvnStatus st = ensure_buffers(n);
+        if (st != AVN_OK) return st;
+        if (use_graph_) {
+            const GraphKey key = graph_key();
+            if (!graph_exec_ || !(key == graph_key_)) {
+                if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+                cudaGraph_t g = nullptr;
+                AVN_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+                enqueue_front(n);
+                cudaError_t ce = cudaStreamEndCapture(stream_, &g);
+                if (ce == cudaSuccess) ce = cudaGraphInstantiate(&graph_exec_, g, 0);
+                if (g) cudaGraphDestroy(g);
+                if (ce != cudaSuccess) {   // capture refused: plain launches from now on (same kernels)
+                    (void)cudaGetLastError();
+                    graph_exec_ = nullptr;
+                    use_graph_ = false;
+                } else {
+                    graph_key_ = key;
+                }
             }
-            launches_ += nblocks <= RS_FUSE_MAX_BLOCKS ? 2 : 3;
-            std::swap(ka, kb);
-            std::swap(va, vb);
         }
-        d_order_ = va;  // even number of passes: back in buffer 0
-        AVN_CUDA(s_minx_.ensure(size_t(n) * sizeof(S))); AVN_CUDA(s_maxx_.ensure(size_t(n) * sizeof(S)));
-        AVN_CUDA(s_yz_.ensure(size_t(n) * sizeof(Vec4<S>))); AVN_CUDA(s_meta_.ensure(size_t(n) * sizeof(uint4)));
-        AVN_CUDA(s_flags_.ensure(size_t(n))); AVN_CUDA(s_end_.ensure(size_t(n) * 4));
-        AVN_CUDA(counts_.ensure(size_t(n) * 4)); AVN_CUDA(offsets_.ensure((size_t(n) + 1) * 8));
-        gather_sorted<S><<<(n + 255) / 256, 256, 0, stream_>>>(d_order_, n, d_min_, d_max_, d_collider_, d_body_, d_memb_, d_filt_, d_flags_,
-                                                               s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), s_meta_.as<uint4>(),
-                                                               s_flags_.as<uint8_t>());
-        // (y, z) cell grid under the x-sorted ranks: stats -> cell ids -> stable 2-pass radix sort of the ranks by cell id -> cell bounds
-        AVN_CUDA(grid_.ensure(sizeof(CellGrid<S>)));
-        AVN_CUDA(ck0_.ensure(size_t(n) * 4)); AVN_CUDA(ck1_.ensure(size_t(n) * 4)); AVN_CUDA(cv0_.ensure(size_t(n) * 4)); AVN_CUDA(cv1_.ensure(size_t(n) * 4));
-        AVN_CUDA(cbounds_.ensure(size_t(2) * 0x10000 * 4));
-        CellGrid<S>* d_grid = grid_.as<CellGrid<S>>();
-        int* cstart = cbounds_.as<int>();
-        int* cend = cbounds_.as<int>() + 0x10000;
-        AVN_CUDA(stats_.ensure(size_t(YZ_BLOCKS) * sizeof(YzPartial<S>)));
-        AVN_CUDA(stats2_.ensure(size_t(2) * YZ_BLOCKS * sizeof(S)));
-        yz_stats<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, stats_.as<YzPartial<S>>());
-        yz_fold<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), YZ_BLOCKS, n, d_grid);
-        yz_small_max<S><<<YZ_BLOCKS, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, stats2_.as<S>());
-        yz_grid<S><<<1, 32, 0, stream_>>>(stats_.as<YzPartial<S>>(), stats2_.as<S>(), YZ_BLOCKS, n, d_grid);
-        AVN_CUDA(wide_.ensure((size_t(SW_WIDE_CAP) + 1) * 4));
-        AVN_CUDA(wide_flag_.ensure(size_t(n)));
+        if (use_graph_ && graph_exec_) {
+            AVN_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+            graph_replays_ += 1;
+        } else {
+            enqueue_front(n);
+        }
+        launches_ += front_launches_;
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        if (h_total_[1] != 0) return drop_nonfinite();
+        const Sweep<S> sw = sweep_desc();
+        const CellSweep<S> cs = cell_desc();
+        const int grid = std::min((n + (256 / CG_GROUP) - 1) / (256 / CG_GROUP), sm_count_ * 32);
+        const int nsub = (n + SW_SUB - 1) / SW_SUB;
         int* wide_count = wide_.as<int>();
         int* wide_list = wide_.as<int>() + 1;
-        AVN_CUDA(cudaMemsetAsync(wide_count, 0, 4, stream_));
-        sweep_bounds<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_minx_.as<S>(), s_maxx_.as<S>(), s_yz_.as<Vec4<S>>(), d_grid, n, s_end_.as<int>(), wide_list, wide_count,
-                                                              wide_flag_.as<uint8_t>(), s_flags_.as<uint8_t>());
-        Sweep<S> sw;
-        sw.n = n; sw.minx = s_minx_.as<S>(); sw.maxx = s_maxx_.as<S>(); sw.yz = s_yz_.as<Vec4<S>>(); sw.meta = s_meta_.as<uint4>();
-        sw.flags = s_flags_.as<uint8_t>(); sw.end = s_end_.as<int>(); sw.is_wide = wide_flag_.as<uint8_t>();
-        sw.existing = d_existing_; sw.existing_mask = existing_mask_; sw.jdis = d_jdis_; sw.jdis_mask = jdis_mask_;
-        cell_keys<S><<<(n + 255) / 256, 256, 0, stream_>>>(s_yz_.as<Vec4<S>>(), n, d_grid, ck0_.as<uint32_t>(), cv0_.as<uint32_t>());
-        {
-            uint32_t* cka = ck0_.as<uint32_t>(); uint32_t* ckb = ck1_.as<uint32_t>();
-            uint32_t* cva = cv0_.as<uint32_t>(); uint32_t* cvb = cv1_.as<uint32_t>();
-            for (int pass = 0; pass < 2; ++pass) {
-                rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(cka, n, 8 * pass, hist_.as<uint32_t>(), nblocks);
-                if (nblocks <= RS_FUSE_MAX_BLOCKS) {
-                    rs_scatter<uint32_t, true><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
-                } else {
-                    rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
-                    rs_scatter<uint32_t, false><<<nblocks, RS_THREADS, 0, stream_>>>(cka, cva, n, 8 * pass, hist_.as<uint32_t>(), nblocks, ckb, cvb);
-                }
-                std::swap(cka, ckb);
-                std::swap(cva, cvb);
-            }
-        }
-        AVN_CUDA(cudaMemsetAsync(cstart, 0x7f, size_t(0x10000) * 4, stream_));
-        AVN_CUDA(cudaMemsetAsync(cend, 0, size_t(0x10000) * 4, stream_));
-        cell_bounds<<<(n + 255) / 256, 256, 0, stream_>>>(ck0_.as<uint32_t>(), n, cstart, cend);
-        CellSweep<S> cs;
-        cs.grid = d_grid; cs.cranks = cv0_.as<uint32_t>(); cs.cstart = cstart; cs.cend = cend;
-        const int grid = std::min((n + (256 / CG_GROUP) - 1) / (256 / CG_GROUP), sm_count_ * 32);
-        sweep_cells_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, cs, counts_.as<uint32_t>(), nullptr, nullptr);
-        // intervals with a huge x-window: brute force, one block per SW_SUB candidates; the grid's y dimension strides the wide list
-        const int nsub = (n + SW_SUB - 1) / SW_SUB;
-        const int wide_rows = 64;
-        AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
-        sweep_wide_kernel<S, false><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr);
-        wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
-        launches_ += nblocks <= RS_FUSE_MAX_BLOCKS ? 11 : 13;
-        const int sblocks = (n + 1023) / 1024;
-        AVN_CUDA(block_sums_.ensure(size_t(sblocks) * 8));
-        scan_block_sums<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>());
-        scan_block_offsets<<<1, 1024, 0, stream_>>>(block_sums_.as<uint64_t>(), sblocks, offsets_.as<uint64_t>() + n);
-        scan_apply<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>(), offsets_.as<uint64_t>());
-        launches_ += 7;
-        // the pair count decides the size of the output buffers: one 8-byte readback
-        AVN_CUDA(cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
-        AVN_CUDA(cudaStreamSynchronize(stream_));
         const uint64_t total = *h_total_;
         pair_capacity_ = total;
         if (total > 0) {
@@ -647,19 +767,66 @@ AvnStatus Broadphase<S>::run() {
             AVN_CUDA(pairs_.ensure(total * sizeof(uint2)));
             uint2* pairs = pairs_.as<uint2>();
             sweep_cells_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, cs, nullptr, offsets_.as<uint64_t>(), pairs);
-            sweep_wide_kernel<S, true><<<dim3(nsub, wide_rows), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
+            sweep_wide_kernel<S, true><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
                                                                                           offsets_.as<uint64_t>(), pairs);
             segment_sort<<<(n + 255) / 256, 256, 0, stream_>>>(offsets_.as<uint64_t>(), wide_flag_.as<uint8_t>(), n, pairs);
             materialize_pairs<S><<<unsigned((total + 255) / 256), 256, 0, stream_>>>(sw, pairs, total, total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
                                                                                   o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
-            launches_ += 2;
-            launches_ += 2;
+            launches_ += 4;
         }
     }
     cudaEventRecord(ev1_, stream_);
     AVN_CUDA(cudaGetLastError());
     ran_ = true;
     return AVN_OK;
+}
+
+// update_aabb_intervals' `retain` (broad_phase.rs:236-246): intervals whose AABB is not finite leave the interval list.  The flag raised by
+// make_keys brings us here (rare): compact the caller's columns on the host, upload the survivors and run again.  order_out then lists the
+// surviving intervals only (retained_count of them, as rows of the CALLER's columns).
+template <class S>
+AvnStatus Broadphase<S>::drop_nonfinite() {
+    const size_t n = host_.count;
+    const S* mn = static_cast<const S*>(host_.aabb_min);
+    const S* mx = static_cast<const S*>(host_.aabb_max);
+    keep_.clear();
+    keep_.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        bool finite = true;
+        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(mn[3 * i + k]) && std::isfinite(mx[3 * i + k]);
+        if (finite) keep_.push_back(uint32_t(i));
+    }
+    const size_t m = keep_.size();
+    c_min_.resize(3 * m * sizeof(S)); c_max_.resize(3 * m * sizeof(S));
+    c_col_.resize(m); c_body_.resize(m);
+    if (host_.memberships) c_memb_.resize(m);
+    if (host_.filters) c_filt_.resize(m);
+    if (host_.flags) c_flags_.resize(m);
+    S* cmn = reinterpret_cast<S*>(c_min_.data());
+    S* cmx = reinterpret_cast<S*>(c_max_.data());
+    for (size_t r = 0; r < m; ++r) {
+        const size_t i = keep_[r];
+        for (int k = 0; k < 3; ++k) { cmn[3 * r + k] = mn[3 * i + k]; cmx[3 * r + k] = mx[3 * i + k]; }
+        c_col_[r] = host_.collider[i];
+        c_body_[r] = host_.body[i];
+        if (host_.memberships) c_memb_[r] = host_.memberships[i];
+        if (host_.filters) c_filt_[r] = host_.filters[i];
+        if (host_.flags) c_flags_[r] = host_.flags[i];
+    }
+    AvnStatus st;
+#define UPB(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
+    UPB(b_min_, cmn, 3 * m, S, d_min_);
+    UPB(b_max_, cmx, 3 * m, S, d_max_);
+    UPB(b_col_, c_col_.data(), m, uint32_t, d_collider_);
+    UPB(b_body_, c_body_.data(), m, uint32_t, d_body_);
+    UPB(b_memb_, host_.memberships ? c_memb_.data() : nullptr, m, uint32_t, d_memb_);
+    UPB(b_filt_, host_.filters ? c_filt_.data() : nullptr, m, uint32_t, d_filt_);
+    UPB(b_flags_, host_.flags ? c_flags_.data() : nullptr, m, uint8_t, d_flags_);
+#undef UPB
+    AVN_CUDA(cudaStreamSynchronize(stream_));   // the compacted columns are pageable host vectors
+    n_ = int(m);
+    dropped_ = true;
+    return run();
 }
 
 template <class S>
@@ -680,6 +847,9 @@ AvnStatus Broadphase<S>::download(AvnPairList* out) {
     }
     if (host_.order_out && n_ > 0) AVN_CUDA(cudaMemcpyAsync(host_.order_out, d_order_, size_t(n_) * 4, cudaMemcpyDeviceToHost, stream_));
     AVN_CUDA(cudaStreamSynchronize(stream_));
+    if (dropped_ && host_.order_out)
+        for (int r = 0; r < n_; ++r) host_.order_out[r] = keep_[host_.order_out[r]];   // compacted rows -> rows of the caller's columns
+    if (caller_) caller_->retained_count = uint32_t(n_);
     float ms = 0;
     tm_ = AvnTimings{};
     if (cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess) { tm_.broad_phase_ms = ms; tm_.total_ms = ms; }

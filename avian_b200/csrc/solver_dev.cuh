@@ -66,6 +66,7 @@ struct DevSolver {
     int wave;                                    // 1: wavefront (dependency-counter) substep loop, 0: grid barriers
     unsigned int* ver;                           // [B+1] per-body event counter (wavefront mode)
     int* deg;                                    // [B+1] contact constraints touching the body (wavefront mode)
+    int* stamp;                                  // [B+1] 1 + last colour that ranked the body: detects a body listed twice in one colour
     int substeps, iters, rest_iters, fast_trig, match_contacts;
     S h, dt, max_overlap_speed, warm_coeff, rest_threshold, joint_force_rhs;
     S gx, gy, gz;
@@ -753,6 +754,11 @@ __device__ __forceinline__ void integrate_position_item(const DevSolver<S>& d, i
 
 // ---- wavefront prologue: ranks of every constraint on its two bodies (colour by colour), then pack {r1,k1,r2,k2} ------
 // Within one colour a versioned body appears at most once (constraint_graph.rs:4-6), so the per-colour pass is race-free.
+// The per-colour pass trusts the colouring only as far as it checks it: every versioned body is stamped with the colour that ranks it
+// (atomicExch); meeting its own colour's stamp again means the caller listed the body twice in one colour — a colouring the wavefront
+// schedule would turn into wrong event numbers and a spin until the watchdog — so the flag WAVE_BAD_COLOURING is raised instead, the kernel
+// falls back to the barrier schedule for this step and avn_solver_download reports AVN_ERR_INVALID_ARGUMENT.
+enum { WAVE_WATCHDOG = 1, WAVE_BAD_COLOURING = 3 };
 template <class S>
 __device__ __forceinline__ void wave_rank_item(const DevSolver<S>& d, int slot) {
     const size_t MP = size_t(d.Mpad);
@@ -761,9 +767,13 @@ __device__ __forceinline__ void wave_rank_item(const DevSolver<S>& d, int slot) 
     const int info = as_int(hidx.z);
     if ((info & CI_NP_MASK) == 0) return;
     const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
+    int colour = 0;
+    while (colour < AVN_GRAPH_COLOR_COUNT - 1 && slot >= d.color_off[colour + 1]) ++colour;
     int r1 = 0, r2 = 0;
-    if (info & CI_VER1) { r1 = d.deg[b1]; d.deg[b1] = r1 + 1; }
-    if (info & CI_VER2) { r2 = d.deg[b2]; d.deg[b2] = r2 + 1; }
+    bool bad = false;
+    if (info & CI_VER1) { bad |= atomicExch(&d.stamp[b1], colour + 1) == colour + 1; r1 = atomicAdd(&d.deg[b1], 1); }
+    if (info & CI_VER2) { bad |= atomicExch(&d.stamp[b2], colour + 1) == colour + 1; r2 = atomicAdd(&d.deg[b2], 1); }
+    if (bad || r1 > 0xfe || r2 > 0xfe) d.any_restitution[1] = WAVE_BAD_COLOURING;
     hidx.w = int_as(S(0), (r1 & 0xff) | ((r2 & 0xff) << 16));
     st4(&c[CP_IDX * MP], hidx);
 }

@@ -303,9 +303,11 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         S hz = S(prm->contact_frequency_factor) * std::min(max_hz, S(0.25) / d.h);
         d.soft_dyn = softness<S>(S(prm->contact_damping_ratio), hz, d.h);
         d.soft_nondyn = softness<S>(S(prm->contact_damping_ratio), S(2) * hz, d.h);
-        // writeback_joint_forces rhs (xpbd/plugin.rs:253): (h*h).recip_or_zero() * substeps
-        S hh = d.h * d.h;
-        d.joint_force_rhs = ((hh != S(0) && std::isfinite(hh)) ? S(1) / hh : S(0)) * S(prm->substeps);
+        // writeback_joint_forces rhs (xpbd/plugin.rs:253): (delta_secs * delta_secs).recip_or_zero() * substeps, where delta_secs is the
+        // FULL step dt — the system runs in SolverSystems::Finalize, after run_substep_schedule has set the generic Time back to
+        // Time<Physics> (solver/schedule.rs:211-212).  (Round 1 used h here, in the oracle too: substeps^2 too large.)
+        S dd = d.dt * d.dt;
+        d.joint_force_rhs = ((dd != S(0) && std::isfinite(dd)) ? S(1) / dd : S(0)) * S(prm->substeps);
     }
     // ---- body columns
     AvnStatus st;
@@ -370,6 +372,18 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             if (bad || widest > AVN_MAX_MANIFOLD_POINTS)
                 return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: at most %d points per manifold, point ranges must not decrease", AVN_MAX_MANIFOLD_POINTS);
             max_np_ = int(std::max<uint32_t>(widest, 1));
+        }
+        {   // body indices are gathered through on the device (inr[2*b], vel[2*b], ver[b] ...): anything outside [AVN_NO_BODY, B) would read and
+            // write out of bounds, so it is rejected here (streaming pass over two int columns)
+            const int32_t* hb1 = mc->body1; const int32_t* hb2 = mc->body2;
+            const int64_t Bi = int64_t(B);
+            uint32_t bad_body = 0;
+            for (size_t i = 0; i < M; ++i) bad_body |= uint32_t(hb1[i] < AVN_NO_BODY) | uint32_t(hb1[i] >= Bi) | uint32_t(hb2[i] < AVN_NO_BODY) | uint32_t(hb2[i] >= Bi);
+            if (bad_body) {
+                for (size_t i = 0; i < M; ++i)
+                    if (hb1[i] < AVN_NO_BODY || hb1[i] >= Bi || hb2[i] < AVN_NO_BODY || hb2[i] >= Bi)
+                        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: body indices (%d, %d) of manifold %zu are outside [-1, %zu)", hb1[i], hb2[i], i, B);
+            }
         }
         d.M = int(M);
         d.P = int(P);
@@ -445,14 +459,14 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
     }
     {
         auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
-        const size_t vel_b = up256(state_bytes), dlt_b = up256(state_bytes), ver_b = up256((B + 1) * sizeof(unsigned)), deg_b = up256((B + 1) * sizeof(int));
+        const size_t vel_b = up256(state_bytes), dlt_b = up256(state_bytes), ver_b = up256((B + 1) * sizeof(unsigned)), deg_b = up256(2 * (B + 1) * sizeof(int));
         const size_t planes_b = have_m_ ? size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>) : 0;
         AVN_CUDA(hot_.ensure(vel_b + dlt_b + ver_b + deg_b + planes_b + 256));
         char* base = hot_.as<char>();
         d.vel = reinterpret_cast<Vec4<S>*>(base); base += vel_b;
         d.dlt = reinterpret_cast<Vec4<S>*>(base); base += dlt_b;
         d.ver = reinterpret_cast<unsigned*>(base); base += ver_b;
-        d.deg = reinterpret_cast<int*>(base); base += deg_b;
+        d.deg = reinterpret_cast<int*>(base); d.stamp = d.deg + (B + 1); base += deg_b;
         d.cst = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr;
         hot_bytes_ = vel_b + dlt_b + ver_b + deg_b + (have_m_ ? size_t(AVN_MAX_MANIFOLD_POINTS) * d.Mpad * sizeof(Vec4<S>) : 0);
     }
@@ -539,7 +553,7 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
         }
         if (dev_.wave) {
             AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
-            AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, (size_t(dev_.B) + 1) * sizeof(int), stream_));
+            AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, 2 * (size_t(dev_.B) + 1) * sizeof(int), stream_));   // deg + stamp
         }
         mega_step_ = mega;
     } else {
@@ -785,7 +799,10 @@ AvnStatus Solver<S>::download() {
                            double(tr[0]) / tr[4], double(tr[1]) / tr[4], double(tr[2]) / tr[4], double(tr[3]) / tr[4]);
     }
 #endif
-    if (flags_host[1] == 1) return err_->fail(AVN_ERR_CUDA, "wavefront scheduler watchdog fired: results are invalid (set AVN_LAUNCH_MODE=barrier)");
+    if (flags_host[1] == WAVE_BAD_COLOURING)
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: invalid colouring — a body with a SolverBody appears twice in one graph colour (or carries more than 254 "
+                                                    "constraints): the colours are not conflict-free, the results of this step are not reliable");
+    if (flags_host[1] == WAVE_WATCHDOG) return err_->fail(AVN_ERR_CUDA, "wavefront scheduler watchdog fired: results are invalid (set AVN_LAUNCH_MODE=barrier)");
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ev_[EV_H2D0], ev_[EV_H2D1]) == cudaSuccess) tm_.h2d_ms = ms;
     if (cudaEventElapsedTime(&ms, ev_[EV_RUN0], ev_[EV_PREP]) == cudaSuccess) tm_.prepare_ms = ms;
@@ -799,6 +816,7 @@ AvnStatus Solver<S>::download() {
     uint32_t ac = 0;
     for (int c = 0; c < AVN_GRAPH_COLOR_COUNT; ++c) ac += dev_.color_len[c] > 0;
     tm_.active_colors = ac;
+    tm_.launch_mode = !mega_step_ ? AVN_LAUNCH_PHASES : (dev_.wave ? AVN_LAUNCH_MEGA_WAVE : AVN_LAUNCH_MEGA_BARRIER);
     return AVN_OK;
 }
 

@@ -156,11 +156,14 @@ __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_
         }
     }
     // ---- run_substep_schedule (solver/schedule.rs:194-213), substeps [sub_begin, sub_end)
-    if (d.wave && d.sub_end > d.sub_begin) {
+    // the wavefront schedule is only entered with a colouring the rank pass found valid (and no watchdog event in an earlier launch of this
+    // step); otherwise the barrier schedule below runs, which terminates on any input (read after a grid barrier: uniform over the grid)
+    const bool wave = d.wave && *reinterpret_cast<volatile int*>(d.any_restitution + 1) == 0;
+    if (wave && d.sub_end > d.sub_begin) {
         wave_substep_loop<S, MAXP>(d);
         grid.sync();
     }
-    for (int sub = d.sub_begin; sub < (d.wave ? 0 : d.sub_end); ++sub) {
+    for (int sub = d.sub_begin; sub < (wave ? 0 : d.sub_end); ++sub) {
         grid_phase<S, OP_INTEGRATE_VEL>(d, 0, d.B);
         grid.sync();
         if (d.M > 0) {

@@ -200,6 +200,11 @@ def run_gpu(args, info):
         sum(v.nbytes for k, v in aabbs.__dict__.items() if isinstance(v, np.ndarray) and k != "order_out")
     d2h = B * (3 + 4 + 3 + 3) * sb + P * 4 * sb + B * 4 + new_pairs * 17
     restore()
+    # one more end-to-end step from the frozen snapshot whose outputs are kept: the parity block compares them with the CPU arm's
+    gpu_pairs = ctx.broadphase(aabbs)
+    ctx.solver_step(prm, bodies, man, joints)
+    gpu_out = (bodies.copy(), man.copy(), gpu_pairs, None if aabbs.order_out is None else aabbs.order_out.copy())
+    restore()
 
     # max over ranks
     dev_ms, wall_res_ms, wall_e2e_ms, mega_ms, bp_ms = parallel.reduce_max(
@@ -246,12 +251,36 @@ def run_gpu(args, info):
         "breakdown_ms": {"broad_phase": bp_ms / K, "solver_stage": mega_ms / K, "resident_wall": wall_res_ms / K},
     }
     if not args.no_cpu and world >= 1:
-        result["cpu_baseline"] = cpu_arm(args, prm, b0, m0, aabbs, sample_steps=args.cpu_steps, joints=joints)
+        keep = {}
+        result["cpu_baseline"] = cpu_arm(args, prm, b0, m0, aabbs, sample_steps=args.cpu_steps, joints=joints, keep=keep)
+        result["parity"] = parity_block(gpu_out, keep)
     ctx.close()
     return result
 
 
-def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int, joints=None) -> dict:
+def parity_block(gpu_out, keep) -> dict:
+    """The GPU step and the CPU oracle step from the SAME full-size snapshot, compared element-wise (tests/helpers.py parity_report):
+    relative error with a floor of one unit, bar 1e-5 (BASELINE.json north_star); the broad phase's pair list and persistent order
+    bit for bit.  The run FAILS (exit code 1) when the bar is missed."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import BODY_OUT, IMPULSE_OUT, parity_report
+    gb, gm, gp, gorder = gpu_out
+    ob, om, op, oorder = keep["bodies"], keep["manifolds"], keep["pairs"], keep["order"]
+    rep = parity_report(gb, ob, BODY_OUT)
+    rep.update(parity_report(gm, om, IMPULSE_OUT))
+    pairs_ok = gp.count == op.count and all(np.array_equal(getattr(gp, k)[:gp.count], getattr(op, k)[:op.count]) for k in ("collider1", "collider2", "body1", "body2", "flags"))
+    order_ok = gorder is None or oorder is None or bool(np.array_equal(gorder, oorder))
+    worst = max(r["max_rel_err"] for r in rep.values())
+    return {"max_rel_err_pos": rep["position"]["max_rel_err"], "max_rel_err_rot": rep["rotation"]["max_rel_err"],
+            "max_rel_err_vel": max(rep["linear_velocity"]["max_rel_err"], rep["angular_velocity"]["max_rel_err"]),
+            "max_rel_err_impulse": max(rep[k]["max_rel_err"] for k in IMPULSE_OUT if k in rep) if any(k in rep for k in IMPULSE_OUT) else 0.0,
+            "pairs_bit_exact": bool(pairs_ok), "order_bit_exact": order_ok, "pairs": int(op.count),
+            "bit_identical_share": min(r["bit_identical"] for r in rep.values()), "max_ulp": max(r["max_ulp"] for r in rep.values()),
+            "definition": "element-wise |gpu - cpu| / max(1, |cpu|) after one full step from the same snapshot; cpu = oracle/ (restated reference)",
+            "bar": 1e-5, "ok": bool(worst <= 1e-5 and pairs_ok and order_ok)}
+
+
+def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int, joints=None, keep: dict | None = None) -> dict:
     """The oracle (restated reference path, colour-parallel like the reference) on the host cores."""
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib
@@ -262,9 +291,11 @@ def cpu_arm(args, prm, bodies, man, aabbs, sample_steps: int, joints=None) -> di
         b, m = bodies.copy(), man.copy()
         a = api.Aabbs(**{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in aabbs.__dict__.items()})
         t0 = time.perf_counter()
-        oracle_lib.broadphase(a, capacity=1 << 20)
+        pairs = oracle_lib.broadphase(a, capacity=1 << 20)
         oracle_lib.solver_step(prm, b, m, None if joints is None else joints.copy(), threads=threads)
         t_total += time.perf_counter() - t0
+        if keep is not None and i == 0:
+            keep.update(bodies=b, manifolds=m, pairs=pairs, order=a.order_out)
     return {"value": sample_steps / t_total, "unit": "steps/s", "cores": threads, "kind": "port",
             "sample": f"{sample_steps} full steps of the same snapshot (SAP single-threaded + solver stage colour-parallel on {threads} threads)",
             "ms_per_step": t_total / sample_steps * 1e3}
@@ -324,6 +355,8 @@ def main():
             dist.destroy_process_group()
     if res is not None:
         print(json.dumps(res))
+        if isinstance(res.get("parity"), dict) and not res["parity"]["ok"]:
+            sys.exit(1)
 
 
 if __name__ == "__main__":

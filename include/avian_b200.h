@@ -220,7 +220,9 @@ typedef struct AvnJointSet {
  *      frame's sorted order, then newly added colliders appended, broad_phase.rs:296-315) -------------- */
 typedef struct AvnAabbColumns {
     uint32_t count;                   /* C */
-    uint32_t _pad;
+    uint32_t retained_count;          /* out (written by upload and again by download): intervals that stay in the list = entries of order_out.
+                                         Intervals whose AABB has a NaN or infinite component are dropped, as update_aabb_intervals' retain
+                                         does (broad_phase.rs:243-245): they form no pairs and are absent from order_out */
     const uint32_t* collider;         /* [C] Entity::index() of the collider */
     const uint32_t* body;             /* [C] Entity::index() of ColliderOf::body */
     const void* aabb_min;             /* [C][3] ColliderAabb::min */
@@ -228,7 +230,7 @@ typedef struct AvnAabbColumns {
     const uint32_t* memberships;      /* [C] CollisionLayers; NULL = 1 (default layer) */
     const uint32_t* filters;          /* [C] NULL = 0xFFFFFFFF */
     const uint8_t* flags;             /* [C] AVN_AABB_* */
-    uint32_t* order_out;              /* [C] out: new persistent order, as indices into these columns; NULL = skip */
+    uint32_t* order_out;              /* [C] out: new persistent order, as indices into these columns (retained_count entries); NULL = skip */
     /* pairs already in ContactGraph::pair_set (contact_graph.rs:95): PairKey u64, any order */
     const uint64_t* existing_pairs;
     uint64_t existing_pair_count;
@@ -261,8 +263,11 @@ typedef struct AvnTimings {
     uint32_t contact_constraint_count;
     uint32_t joint_levels;
     uint32_t active_colors;
-    uint32_t _pad;
+    uint32_t launch_mode;      /* AVN_LAUNCH_*: how the last solver stage was launched (a refused cooperative launch falls back to phases) */
 } AvnTimings;
+#define AVN_LAUNCH_PHASES 0u        /* one kernel launch per phase (~500 per step) */
+#define AVN_LAUNCH_MEGA_BARRIER 1u  /* one persistent cooperative kernel, grid barriers between colours */
+#define AVN_LAUNCH_MEGA_WAVE 2u     /* one persistent cooperative kernel, per-body event counters instead of barriers */
 
 /* lifecycle ------------------------------------------------------------------------------------------- */
 AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx);
@@ -364,6 +369,7 @@ AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream);
  * (same pairs, same order); pairs flagged AVN_PAIR_NEEDS_HOOK still need the host filter_pairs callback.
  */
 AvnStatus avn_broadphase(AvnContext* ctx, AvnAabbColumns* aabbs, AvnPairList* out_pairs);
+/* split form: the AvnAabbColumns struct itself (not only its buffers) must stay valid until avn_broadphase_download returns */
 AvnStatus avn_broadphase_upload(AvnContext* ctx, AvnAabbColumns* aabbs);
 AvnStatus avn_broadphase_run(AvnContext* ctx);
 AvnStatus avn_broadphase_download(AvnContext* ctx, AvnPairList* out_pairs);

@@ -5,6 +5,7 @@
 // Both are integer/compare algorithms restated literally (insertion sort included), so the pair list is the
 // exact sequence of ContactGraph::add_edge_and_key_with calls of the reference.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <unordered_set>
 #include <vector>
@@ -19,12 +20,21 @@ inline uint64_t pair_key(uint32_t a, uint32_t b) {  // data_structures/pair_key.
 
 template <class S>
 int broadphase(AvnAabbColumns& ac, AvnPairList& out) {
-    const uint32_t n = ac.count;
+    const uint32_t n_all = ac.count;
     const S* mn = static_cast<const S*>(ac.aabb_min);
     const S* mx = static_cast<const S*>(ac.aabb_max);
-    // intervals in persistent order; `order` is the permutation being sorted
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    // intervals in persistent order; `order` is the permutation being sorted.  update_aabb_intervals' retain drops the intervals whose AABB
+    // is not finite before the sort ever sees them (broad_phase.rs:243-245)
+    std::vector<uint32_t> order;
+    order.reserve(n_all);
+    for (uint32_t i = 0; i < n_all; ++i) {
+        bool finite = true;
+        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(mn[3 * i + k]) && std::isfinite(mx[3 * i + k]);
+        if (finite) order.push_back(i);
+    }
+    const uint32_t n = uint32_t(order.size());
+    ac.retained_count = n;
+    const std::vector<uint32_t> retained = order;
     // insertion_sort(|a, b| a.min.x > b.min.x)  (broad_phase.rs:383,479-487)
     // The literal O(n^2) loop is kept while it is affordable; past a swap budget the oracle restarts with
     // std::stable_sort, which yields the identical permutation (a strict-'>' adjacent-swap insertion sort is a
@@ -41,7 +51,7 @@ int broadphase(AvnAabbColumns& ac, AvnPairList& out) {
         }
     }
     if (bailed) {
-        for (uint32_t i = 0; i < n; ++i) order[i] = i;
+        order = retained;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return mn[3 * a] < mn[3 * b]; });
     }
     if (ac.order_out) std::memcpy(ac.order_out, order.data(), sizeof(uint32_t) * n);

@@ -124,9 +124,20 @@ template <class S> inline V3<S> rotate(Quat<S> q, V3<S> v) {
     S b2 = dot(b, b);
     return (v * (w * w - b2)) + (b * (dot(v, b) * S(2))) + (cross(b, v) * (w * S(2)));
 }
+// f32 transcendentals: CORRECTLY ROUNDED (evaluated in double, rounded once) — the definition the CUDA path uses (csrc/avn_math.cuh) and the
+// one glibc >= 2.41 implements (CORE-MATH sinf/cosf/asinf).  The reference calls the platform libm through Rust's f32::sin/cos/asin, so its
+// last bit is platform-dependent: glibc 2.39's asinf differs from the correctly rounded value in 7 % of arguments, sinf/cosf in 1.3 %
+// (measured on this image).  Such one-ulp differences in joint angles are amplified by the XPBD velocity projection (x 2/h) to ~1e-4 rad/s,
+// so "1e-5 of Avian" is only meaningful for jointed scenes once the libm is fixed; the oracle fixes it to the correctly rounded one.
+inline float cr_sin(float x) { return float(std::sin(double(x))); }
+inline float cr_cos(float x) { return float(std::cos(double(x))); }
+inline float cr_asin(float x) { return float(std::asin(double(x))); }
+inline double cr_sin(double x) { return std::sin(x); }
+inline double cr_cos(double x) { return std::cos(x); }
+inline double cr_asin(double x) { return std::asin(x); }
 // glam Quat::from_axis_angle / from_scaled_axis
 template <class S> inline Quat<S> quat_from_axis_angle(V3<S> axis, S angle) {
-    S s = std::sin(angle * S(0.5)), c = std::cos(angle * S(0.5));
+    S s = cr_sin(angle * S(0.5)), c = cr_cos(angle * S(0.5));
     V3<S> v = axis * s;
     return {v.x, v.y, v.z, c};
 }

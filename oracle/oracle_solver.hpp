@@ -453,7 +453,7 @@ template <class S>
 inline bool angle_limit_correction(S lim_min, S lim_max, V3<S> limit_axis, V3<S> axis1, V3<S> axis2, S max_correction, V3<S>& out) {
     const S PI = S(3.14159265358979323846264338327950288);
     const S TAU = S(6.28318530717958647692528676655900577);
-    S phi = std::asin(dot(cross(axis1, axis2), limit_axis));
+    S phi = cr_asin(dot(cross(axis1, axis2), limit_axis));
     if (dot(axis1, axis2) < S(0)) phi = PI - phi;
     if (phi > PI) phi -= TAU;
     if (phi < lim_min || phi > lim_max) {

@@ -439,7 +439,9 @@ struct StepState {
 
     // ---- writeback_joint_forces (xpbd/plugin.rs:242-260)
     if (js) {
-        S rhs = recip_or_zero(h * h) * S(prm.substeps);
+        // `time: Res<Time>` in SolverSystems::Finalize is Time<Physics> again (run_substep_schedule restores it, solver/schedule.rs:211-212),
+        // so delta_seconds_adjusted() is the FULL step dt here, not the substep h: f = sum(lambda) * substeps / dt^2.
+        S rhs = recip_or_zero(dt * dt) * S(prm.substeps);
         for (const JointData<S>& j : w.joints) {
             AvnJointColumns& jc = js->types[j.type];
             if (jc.force) C::set_vec3(jc.force, j.index_in_type, j.total_position_lagrange * rhs);

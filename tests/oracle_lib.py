@@ -51,6 +51,7 @@ def broadphase(aabbs: api.Aabbs, capacity: int | None = None) -> api.PairList:
         st = lib().orc_broadphase(_bits(aabbs.aabb_min.dtype), C.byref(a), C.byref(s))
     assert st == 0, f"oracle broadphase failed: {st}"
     out.count = int(s.count)
+    aabbs.retained_count = int(a.retained_count)
     return out.trimmed()
 
 
