@@ -16,7 +16,7 @@ LIB_DIR = ROOT / "lib"
 CUDA_LIB = LIB_DIR / "libavian_b200.so"
 HOST_LIB = LIB_DIR / "libavian_host.so"
 
-CUDA_SOURCES = ["abi.cu", "solver_host.cu", "broadphase.cu", "aabb.cu", "narrow.cu", "contacts.cu"]
+CUDA_SOURCES = ["abi.cu", "comm.cu", "solver_host.cu", "broadphase.cu", "aabb.cu", "narrow.cu", "contacts.cu"]
 CUDA_HEADERS = ["avn_math.cuh", "solver_dev.cuh", "joints_dev.cuh", "solver_kernels.cuh", "context.hpp", "joint_schedule.hpp", "broadphase_cells.cuh", "narrow_math.hpp", "contact_rows.hpp"]
 # -fmad=false: the reference (Rust) never contracts a*b+c; parity at 1e-5 on contact dynamics needs the same
 # rounding.  Division and sqrt stay IEEE (nvcc defaults -prec-div=true -prec-sqrt=true).
@@ -42,9 +42,22 @@ def find_nvcc() -> str | None:
     return None
 
 
+# headers each translation unit depends on (anything not listed: every header)
+_UNIT_HEADERS = {
+    "comm.cu": ["context.hpp"],
+    "aabb.cu": ["avn_math.cuh", "context.hpp"],
+    "broadphase.cu": ["avn_math.cuh", "context.hpp", "broadphase_cells.cuh"],
+    "narrow.cu": ["avn_math.cuh", "context.hpp", "narrow_math.hpp"],
+    "contacts.cu": ["avn_math.cuh", "context.hpp", "narrow_math.hpp", "contact_rows.hpp"],
+}
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    """Every translation unit is compiled on its own (in parallel, only when its sources changed) and linked into one shared library."""
     src = ROOT / "csrc"
-    deps = [src / s for s in CUDA_SOURCES + CUDA_HEADERS] + [REPO / "include" / "avian_b200.h"]
+    header = REPO / "include" / "avian_b200.h"
+    all_headers = sorted(p.name for p in src.glob("*.cuh")) + sorted(p.name for p in src.glob("*.hpp"))
+    deps = [src / s for s in CUDA_SOURCES] + [src / h for h in all_headers] + [header]
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     nvcc = find_nvcc()
@@ -53,9 +66,42 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
             return CUDA_LIB  # prebuilt library shipped with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libavian_b200.so: the CUDA path cannot be built")
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(CUDA_LIB), *[str(src / s) for s in CUDA_SOURCES]]
-    subprocess.run(cmd, check=True, cwd=src)
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    for unit in CUDA_SOURCES:
+        obj = obj_dir / (unit + ".o")
+        unit_deps = [src / unit, header, Path(__file__)] + [src / h for h in _UNIT_HEADERS.get(unit, all_headers)]
+        if force or not _newer(obj, unit_deps):
+            jobs.append((unit, [nvcc, *compile_flags, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src / unit)]))
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 2)) as pool:
+            results = list(pool.map(lambda j: (j[0], subprocess.run(j[1], cwd=src, capture_output=True, text=True)), jobs))
+        for unit, r in results:
+            if verbose or r.returncode != 0:
+                print(f"---- {unit}\n{r.stdout}{r.stderr}")
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {unit}")
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB), *[str(obj_dir / (u + ".o")) for u in CUDA_SOURCES], "-ldl"],
+                   check=True, cwd=src)
     return CUDA_LIB
+
+
+def build_variant(name: str, defines: list[str]) -> Path:
+    """An experimental build of the library (scripts/wave_trace.py, scripts/lib_timing.py): solver_host.cu recompiled with extra -D flags,
+    linked with the other units of the regular build -> avian_b200/lib/libavian_b200_<name>.so"""
+    build_cuda()
+    nvcc = find_nvcc()
+    src, obj_dir = ROOT / "csrc", LIB_DIR / "obj"
+    obj = obj_dir / f"solver_host.{name}.o"
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    subprocess.run([nvcc, *flags, *[f"-D{d}" for d in defines], "-c", "-o", str(obj), str(src / "solver_host.cu")], check=True, cwd=src)
+    out = LIB_DIR / f"libavian_b200_{name}.so"
+    objs = [str(obj if u == "solver_host.cu" else obj_dir / (u + ".o")) for u in CUDA_SOURCES]
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs, "-ldl"], check=True, cwd=src)
+    return out
 
 
 def build_host(force: bool = False) -> Path:

@@ -364,6 +364,11 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "solver_boundary_apply": ([_vp, _vp], C.c_int),
         "solver_needs_restitution": ([_vp, P(C.c_int)], C.c_int),
         "get_stream": ([_vp, P(_vp)], C.c_int),
+        "solver_step_partitioned": ([_vp], C.c_int),
+        "comm_unique_id": ([_vp, _vp], C.c_int),
+        "comm_init": ([_vp, C.c_uint32, C.c_uint32, _vp], C.c_int),
+        "comm_destroy": ([_vp], C.c_int),
+        "comm_all_gather": ([_vp, _vp, _vp, C.c_size_t], C.c_int),
         "narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), P(AvnRawManifolds)], C.c_int),
         "solver_upload_edges": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
         "solver_upload_graph": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnEdgeManifolds), P(AvnJointSet)], C.c_int),
@@ -383,10 +388,12 @@ ABI_SYMBOLS = [
     "avn_create", "avn_destroy", "avn_last_error", "avn_abi_version", "avn_alloc_pinned", "avn_free_pinned", "avn_solver_step",
     "avn_solver_upload", "avn_solver_run", "avn_solver_download", "avn_broadphase", "avn_broadphase_upload", "avn_broadphase_run",
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
-    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
+    "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream",
+    "avn_solver_step_partitioned", "avn_comm_unique_id", "avn_comm_init", "avn_comm_destroy", "avn_comm_all_gather", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
     "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
+COMM_ID_BYTES = 128
 BOUNDARY_RECORD_SCALARS = 16
 
 
@@ -581,6 +588,26 @@ class Context:
         out = C.c_int(0)
         self._check(self.lib.avn_solver_needs_restitution(self.handle, C.byref(out)))
         return bool(out.value)
+
+    # ---- communicator (NCCL inside the library; one process per GPU)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        self._check(self.lib.avn_comm_unique_id(self.handle, C.cast(buf, _vp)))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None = None) -> None:
+        buf = None if unique_id is None else C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self.lib.avn_comm_init(self.handle, rank, world, None if buf is None else C.cast(buf, _vp)))
+
+    def comm_destroy(self) -> None:
+        self._check(self.lib.avn_comm_destroy(self.handle))
+
+    def comm_all_gather(self, send_device_ptr: int, recv_device_ptr: int, bytes_per_rank: int) -> None:
+        self._check(self.lib.avn_comm_all_gather(self.handle, _vp(send_device_ptr), _vp(recv_device_ptr), bytes_per_rank))
+
+    def solver_step_partitioned(self) -> None:
+        """The partitioned solver stage of this rank (after solver_upload + solver_set_boundary); then solver_download."""
+        self._check(self.lib.avn_solver_step_partitioned(self.handle))
 
     def stream(self) -> int:
         """The context's cudaStream_t as an integer (torch.cuda.ExternalStream(ptr) orders a collective with the launches)."""

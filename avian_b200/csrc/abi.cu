@@ -17,6 +17,7 @@ struct AvnContext {
     std::unique_ptr<avn::AabbBase> aabbs;
     std::unique_ptr<avn::NarrowBase> narrow;
     std::unique_ptr<avn::ContactsBase> contacts;
+    std::unique_ptr<avn::CommBase> comm;
     AvnTimings last{};
 };
 
@@ -82,6 +83,7 @@ AvnStatus avn_create(const AvnConfig* config, AvnContext** out_ctx) {
         ctx->aabbs.reset(avn::make_aabb_updater(config->scalar_bits, ctx->stream, &ctx->err));
         ctx->narrow.reset(avn::make_narrow(config->scalar_bits, ctx->stream, &ctx->err));
         ctx->contacts.reset(avn::make_contacts(config->scalar_bits, ctx->stream, &ctx->err));
+        ctx->comm.reset(avn::make_comm(ctx->stream, &ctx->err));
         if (!ctx->solver || !ctx->broadphase || !ctx->aabbs || !ctx->narrow || !ctx->contacts) {
             ctx.reset();   // the members hold the stream: release them before it goes
             cudaStreamDestroy(stream);
@@ -99,6 +101,7 @@ void avn_destroy(AvnContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->comm.reset();
     ctx->solver.reset();
     ctx->broadphase.reset();
     ctx->aabbs.reset();
@@ -160,6 +163,21 @@ AvnStatus avn_solver_needs_restitution(AvnContext* ctx, int* out_nonzero) {
     if (!ctx || !out_nonzero) return AVN_ERR_INVALID_ARGUMENT;
     *out_nonzero = ctx->solver->needs_restitution();
     return AVN_OK;
+}
+AvnStatus avn_solver_step_partitioned(AvnContext* ctx) {
+    return guarded(ctx, [&] { return ctx->solver->step_partitioned(ctx->comm.get()); });
+}
+AvnStatus avn_comm_unique_id(AvnContext* ctx, void* out_id) {
+    return guarded(ctx, [&] { return ctx->comm->unique_id(out_id); });
+}
+AvnStatus avn_comm_init(AvnContext* ctx, uint32_t rank, uint32_t world, const void* unique_id) {
+    return guarded(ctx, [&] { return ctx->comm->init(rank, world, unique_id); });
+}
+AvnStatus avn_comm_destroy(AvnContext* ctx) {
+    return guarded(ctx, [&] { return ctx->comm->shutdown(); });
+}
+AvnStatus avn_comm_all_gather(AvnContext* ctx, const void* send_device, void* recv_device, size_t bytes_per_rank) {
+    return guarded(ctx, [&] { return ctx->comm->all_gather(send_device, recv_device, bytes_per_rank); });
 }
 AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream) {
     if (!ctx || !out_stream) return AVN_ERR_INVALID_ARGUMENT;

@@ -53,6 +53,19 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// the context's communicator (comm.cu): NCCL bound at run time; a communicator of one needs no NCCL at all
+struct CommBase {
+    virtual ~CommBase() {}
+    virtual AvnStatus unique_id(void* out_id) = 0;
+    virtual AvnStatus init(uint32_t rank, uint32_t world, const void* id) = 0;
+    virtual AvnStatus shutdown() = 0;
+    virtual int rank() const = 0;
+    virtual int world() const = 0;
+    virtual AvnStatus all_gather(const void* send_dev, void* recv_dev, size_t bytes_per_rank) = 0;   // on the context's stream
+    virtual AvnStatus all_reduce_max_i32(int* dev, size_t count) = 0;
+};
+CommBase* make_comm(cudaStream_t stream, ErrorSink* err);
+
 struct ContactsBase;
 struct SolverBase {
     virtual ~SolverBase() {}
@@ -66,6 +79,8 @@ struct SolverBase {
     virtual AvnStatus boundary_snapshot() = 0;
     virtual AvnStatus boundary_pack(void* device_table) = 0;
     virtual AvnStatus boundary_apply(const void* device_gathered) = 0;
+    // the whole partitioned stage of one rank: launches substep by substep with the boundary exchange over `comm` in between
+    virtual AvnStatus step_partitioned(CommBase* comm) = 0;
     virtual int needs_restitution() const = 0;
     virtual AvnStatus download() = 0;
     virtual void timings(AvnTimings* t) const = 0;

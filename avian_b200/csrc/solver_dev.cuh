@@ -6,13 +6,13 @@
 //            inr[2*(B+1)]  = {inv_mass, flags, m00, m01}{m02, m11, m12, m22}   SolverBodyInertia (mod.rs:218-261)
 //            itg[2*B]      = {linear_increment.xyz, linear_damping_rhs}{angular_increment.xyz, angular_damping_rhs}
 //            slot B is SolverBody::DUMMY / SolverBodyInertia::DUMMY (static bodies, AVN_NO_BODY).
-//   contacts cst[20][Mpad] planes, slot-major inside a plane so that a warp reads 32 consecutive Vec4.  Manifold m of
+//   contacts cst[16][Mpad] planes, slot-major inside a plane so that a warp reads 32 consecutive Vec4.  Manifold m of
 //            graph colour c lives in slot color_off[c] + (m - m_color_off[c]); every colour starts at a multiple of 32 so
 //            a warp never straddles two colours (padding slots have info = 0 = no points):
-//            k (k = 0..3)  {normal impulse, total normal impulse, tangent impulse.x, .y} of point k  <- the only planes written in the loop
-//            4 {n.xyz, friction} 5 {t1.xyz, restitution} 6 {tangent_velocity.xyz,-} 7 {body1, body2, info, ranks}
-//            8+3k {anchor1.xyz, initial_separation} 9+3k {anchor2.xyz, normal effective_mass}
-//            10+3k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
+//            0 {n.xyz, friction} 1 {t1.xyz, restitution} 2 {tangent_velocity.xyz,-} 3 {body1, body2, info, ranks}
+//            4+3k {anchor1.xyz, initial_separation} 5+3k {anchor2.xyz, normal effective_mass}
+//            6+3k {K1, K2, K3 (tangent effective inverse mass), normal_speed}
+//            pcr[4][Mpad] records {normal impulse, total normal impulse, tangent impulse.x, .y} of point k  <- the only constraint data written in the loop
 //   joints   jnt[14][Jpad] planes in level-schedule order (see JP_* below).
 #pragma once
 #include <cuda_pipeline.h>
@@ -22,13 +22,16 @@
 
 namespace avn {
 
-// plane numbering: the four MUTABLE impulse planes come first so that, together with the body state that precedes them in the
-// same allocation, they form one contiguous "hot" range that is pinned in L2 (access-policy window); the immutable rows follow.
-enum { CP_PC0 = 0, CP_N = AVN_MAX_MANIFOLD_POINTS, CP_T1 = CP_N + 1, CP_TV = CP_N + 2, CP_IDX = CP_N + 3, CP_PT0 = CP_N + 4,
-       CP_PLANES = CP_PT0 + 3 * AVN_MAX_MANIFOLD_POINTS };
-// rows of point k: impulses {lambda_n, sum lambda_n, lambda_t.x, lambda_t.y} in plane CP_PC0 + k; immutable rows in CP_PT0 + 3k + {0: A, 1: B, 2: D}
-#define CP_PC(k) (CP_PC0 + (k))
+// plane numbering of the IMMUTABLE constraint rows (written by prepare, read-only in the substep loop)
+enum { CP_N = 0, CP_T1 = 1, CP_TV = 2, CP_IDX = 3, CP_PT0 = 4, CP_PLANES = CP_PT0 + 3 * AVN_MAX_MANIFOLD_POINTS };
+// immutable rows of point k in CP_PT0 + 3k + {0: A, 1: B, 2: D}
 #define CP_ROW(k, r) (CP_PT0 + 3 * (k) + (r))
+// The MUTABLE impulses {lambda_n, sum lambda_n, lambda_t.x, lambda_t.y} of point k live in their own array of RECORDS, pcr, point-major
+// like a plane: record (k, slot) at pcr[(k * Mpad + slot) * PCW].  f32: PCW = 2 — a record is one 32-byte L2 sector
+// {lambda_n, sum, lt.x, lt.y | tag, -, -, -} so that the wavefront schedule can read and write it with ONE 256-bit access that carries its own
+// sequence tag (wave32_dev.cuh); f64: PCW = 1 (the 32-byte Vec4<double>, no tag).  Together with the body state that precedes it in the same
+// allocation (vel | dlt | counters | pcr) it is the "hot" range pinned in L2 by the access-policy window.
+template <class S> struct PcRec { static constexpr int W = sizeof(S) == 4 ? 2 : 1; };
 // info lane of plane CP_IDX
 enum { CI_NP_MASK = 0x7, CI_ZERO1 = 1 << 4, CI_ZERO2 = 1 << 5, CI_NONDYN = 1 << 6, CI_TANGENT = 1 << 7,
        CI_VER1 = 1 << 8, CI_VER2 = 1 << 9,     // VERx: side x is a versioned body (has a SolverBody) in wavefront mode
@@ -89,6 +92,7 @@ struct DevSolver {
     const S* p_in_normal_impulse;
     S* p_out_ws_normal; S* p_out_ws_tangent; S* p_normal_impulse;  // store_contact_impulses outputs
     Vec4<S>* cst;
+    Vec4<S>* pcr;                                // impulse records, see PcRec
     int* any_restitution;
     // joints
     const int* j_src_type; const int* j_src_index;  // schedule slot -> (type, index in type)
@@ -114,6 +118,11 @@ template <class S> __device__ __forceinline__ Q4<S> ldq(const S* p, int i) {
     Q4<S> q; q.x = p[4 * i]; q.y = p[4 * i + 1]; q.z = p[4 * i + 2]; q.w = p[4 * i + 3]; return q;
 }
 template <class S> __device__ __forceinline__ void stv3(S* p, int i, V3<S> v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+// impulse record of point k of the manifold in `slot`
+template <class S> __device__ __forceinline__ Vec4<S>* pc_ptr(const DevSolver<S>& d, int k, int slot) {
+    return d.pcr + (size_t(k) * size_t(d.Mpad) + size_t(slot)) * PcRec<S>::W;
+}
 
 template <class S> struct BodyInertia {
     V3<S> inv_mass;  // effective (locked axes applied)
@@ -231,7 +240,8 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
     int f1 = as_int(i1a.y), f2 = as_int(i2a.y);
     uint32_t p0 = d.m_point_begin[m], p1 = d.m_point_end[m];
     int np = int(p1 - p0);
-    Vec4<S>* c = d.cst + slot_of_manifold(d, m);
+    const int slot = slot_of_manifold(d, m);
+    Vec4<S>* c = d.cst + slot;
     const size_t MP = size_t(d.Mpad);
     // skip contacts between two non-dynamic bodies (plugin.rs:415-418) and empty manifolds (:434)
     if ((!(f1 & BF_DYNAMIC) && !(f2 & BF_DYNAMIC)) || np <= 0) {
@@ -292,7 +302,9 @@ __device__ void prepare_constraint_item(const DevSolver<S>& d, int m) {
         }
         st4(&c[size_t(CP_ROW(k, 0)) * MP], mk4<S>(r1.x, r1.y, r1.z, sep0));
         st4(&c[size_t(CP_ROW(k, 1)) * MP], mk4<S>(r2.x, r2.y, r2.z, meff));
-        st4(&c[size_t(CP_PC(k)) * MP], mk4<S>(imp_n, S(0), itx, ity));
+        Vec4<S>* pc = pc_ptr(d, k, slot);
+        st4(pc, mk4<S>(imp_n, S(0), itx, ity));
+        if (PcRec<S>::W == 2) st4(pc + 1, mk4<S>(S(0), S(0), S(0), S(0)));   // sequence tag 0
         st4(&c[size_t(CP_ROW(k, 2)) * MP], mk4<S>(K1, K2, K3, d.p_normal_speed[p]));
     }
 }
@@ -482,7 +494,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     }
 #pragma unroll
     for (int k = 0; k < MAXP; ++k)
-        if (k < np) PC[k] = ldm<WAVE>(&c[size_t(CP_PC(k)) * MP]);
+        if (k < np) PC[k] = ldm<WAVE>(pc_ptr(d, k, slot));
     __pipeline_wait_prior(0);  // this thread's staged rows have landed (only the issuing thread reads them)
 #ifdef AVN_WAVE_TRACE
     if (WAVE) {  // force the loads to complete here so the segments separate cleanly
@@ -612,7 +624,7 @@ __device__ __forceinline__ void contact_item(const DevSolver<S>& d, int slot, in
     if (PASS != PASS_WARM) {
 #pragma unroll
         for (int k = 0; k < MAXP; ++k)
-            if (k < np) st4(&c[size_t(CP_PC(k)) * MP], PC[k]);
+            if (k < np) st4(pc_ptr(d, k, slot), PC[k]);
     }
     if (WAVE && SOLVE) {
         // integrate_positions of a body whose last solve event this is (integrator/mod.rs:503-535): dp += v h, dq = exp(w h) dq
@@ -831,7 +843,8 @@ __device__ __forceinline__ void writeback_body_item(const DevSolver<S>& d, int i
 template <class S>
 __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m) {
     const size_t MP = size_t(d.Mpad);
-    const Vec4<S>* c = d.cst + slot_of_manifold(d, m);
+    const int slot = slot_of_manifold(d, m);
+    const Vec4<S>* c = d.cst + slot;
     Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
     int info = as_int(hidx.z), np = info & CI_NP_MASK, p0 = int(d.m_point_begin[m]);
     if (np == 0) {  // skipped by prepare (both bodies non-dynamic): the reference leaves the ContactPoints untouched
@@ -844,7 +857,7 @@ __device__ __forceinline__ void store_impulse_item(const DevSolver<S>& d, int m)
         return;
     }
     for (int k = 0; k < np; ++k) {
-        Vec4<S> pc = ld4(&c[size_t(CP_PC(k)) * MP]);
+        Vec4<S> pc = ld4(pc_ptr(d, k, slot));
         d.p_out_ws_normal[p0 + k] = pc.x;
         d.p_out_ws_tangent[2 * (p0 + k)] = (info & CI_TANGENT) ? pc.z : S(0);
         d.p_out_ws_tangent[2 * (p0 + k) + 1] = (info & CI_TANGENT) ? pc.w : S(0);

@@ -62,6 +62,7 @@ class Solver final : public SolverBase {
     }
     ~Solver() override {
         for (auto& e : ev_) cudaEventDestroy(e);
+        if (h_agree_) cudaFreeHost(h_agree_);
     }
 
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
@@ -72,6 +73,7 @@ class Solver final : public SolverBase {
     AvnStatus boundary_snapshot() override;
     AvnStatus boundary_pack(void* device_table) override;
     AvnStatus boundary_apply(const void* device_gathered) override;
+    AvnStatus step_partitioned(CommBase* comm) override;
     int needs_restitution() const override { return host_any_restitution_ ? 1 : 0; }
     AvnStatus run() override;
     AvnStatus download() override;
@@ -145,10 +147,11 @@ class Solver final : public SolverBase {
     const void* mega_fn_ = nullptr;
     cudaEvent_t ev_[EV_COUNT];
     AvnTimings tm_{};
-    uint32_t launches_ = 0;
+    uint32_t launches_ = 0, exchanges_ = 0;
     size_t h2d_bytes_ = 0;
     bool uploaded_ = false, ran_ = false, host_any_restitution_ = false, prepared_ = false, mega_step_ = false;
-    DevBuf bnd_of_, bnd_body_, bnd_slot_, bnd_owner_, vel_ref_;
+    DevBuf bnd_of_, bnd_body_, bnd_slot_, bnd_owner_, vel_ref_, bnd_table_, bnd_gathered_, bnd_agree_;
+    int* h_agree_ = nullptr;
     int bnd_n_ = 0, bnd_rank_ = 0, bnd_world_ = 1;
     size_t bnd_slots_ = 0;
 
@@ -461,14 +464,16 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
         const size_t vel_b = up256(state_bytes), dlt_b = up256(state_bytes), ver_b = up256((B + 1) * sizeof(unsigned)), deg_b = up256(2 * (B + 1) * sizeof(int));
         const size_t planes_b = have_m_ ? size_t(CP_PLANES) * d.Mpad * sizeof(Vec4<S>) : 0;
-        AVN_CUDA(hot_.ensure(vel_b + dlt_b + ver_b + deg_b + planes_b + 256));
+        const size_t pcr_b = have_m_ ? up256(size_t(AVN_MAX_MANIFOLD_POINTS) * d.Mpad * PcRec<S>::W * sizeof(Vec4<S>)) : 0;
+        AVN_CUDA(hot_.ensure(vel_b + dlt_b + ver_b + deg_b + pcr_b + planes_b + 256));
         char* base = hot_.as<char>();
         d.vel = reinterpret_cast<Vec4<S>*>(base); base += vel_b;
         d.dlt = reinterpret_cast<Vec4<S>*>(base); base += dlt_b;
         d.ver = reinterpret_cast<unsigned*>(base); base += ver_b;
         d.deg = reinterpret_cast<int*>(base); d.stamp = d.deg + (B + 1); base += deg_b;
+        d.pcr = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr; base += pcr_b;
         d.cst = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr;
-        hot_bytes_ = vel_b + dlt_b + ver_b + deg_b + (have_m_ ? size_t(AVN_MAX_MANIFOLD_POINTS) * d.Mpad * sizeof(Vec4<S>) : 0);
+        hot_bytes_ = vel_b + dlt_b + ver_b + deg_b + pcr_b;
     }
     // ---- joints
     have_j_ = false;
@@ -671,10 +676,13 @@ __global__ void boundary_apply_kernel(DevSolver<S> d, const int* __restrict__ bo
         l.x = l.x + dl.x; l.y = l.y + dl.y; l.z = l.z + dl.z;
         a.x = a.x + da.x; a.y = a.y + da.y; a.z = a.z + da.z;
     }
-    st4(&d.vel[2 * b], mk4<S>(l.x, l.y, l.z, S(0)));
+    // the spare lanes of the velocity / delta rows carry the wavefront schedule's sequence tags (wave32_dev.cuh): kept as they are
+    st4(&d.vel[2 * b], mk4<S>(l.x, l.y, l.z, ld4(&d.vel[2 * b]).w));
     st4(&d.vel[2 * b + 1], mk4<S>(a.x, a.y, a.z, S(0)));
     const Vec4<S>* own = gathered + (size_t(owner_rank[k]) * records + size_t(source[size_t(k) * world + owner_rank[k]])) * 4;
-    st4(&d.dlt[2 * b], ld4(&own[2]));
+    Vec4<S> odp = ld4(&own[2]);
+    odp.w = ld4(&d.dlt[2 * b]).w;
+    st4(&d.dlt[2 * b], odp);
     st4(&d.dlt[2 * b + 1], ld4(&own[3]));
 }
 
@@ -685,6 +693,10 @@ AvnStatus Solver<S>::set_boundary(const AvnBoundary* bnd) {
         dev_.bnd_of = nullptr;
         dev_.vel_ref = nullptr;
         bnd_n_ = 0;
+        // a rank that holds no boundary body still takes part in the exchange of the others' tables
+        bnd_slots_ = bnd ? size_t(bnd->record_count) : 0;
+        bnd_rank_ = bnd ? int(bnd->rank) : 0;
+        bnd_world_ = bnd ? int(bnd->world) : 1;
         return AVN_OK;
     }
     if (!bnd->body || !bnd->source || !bnd->owner_rank) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary: body, source and owner_rank are required");
@@ -763,6 +775,59 @@ AvnStatus Solver<S>::boundary_apply(const void* device_gathered) {
     return AVN_OK;
 }
 
+// One rank's share of a scene cut into x-slabs (include/avian_b200.h "one coupled scene over several GPUs"): the step kernel substep by
+// substep (the wavefront counters keep counting across the launches), and after every substep
+//     pack (this rank's records) -> all-gather of the packed tables over the context's communicator -> apply (rank-ordered sums)
+// all on the context's stream, so nothing synchronises with the host inside the step except one agreement per step on whether a
+// restitution pass is needed anywhere.  Protocol and its CPU twin: DESIGN.md 4.2, oracle/oracle_step.cpp orc_step_*.
+template <class S>
+AvnStatus Solver<S>::step_partitioned(CommBase* comm) {
+    if (!uploaded_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_step_partitioned before avn_solver_upload");
+    if (!comm) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "no communicator");
+    const int world = comm->world();
+    if (bnd_slots_ > 0 && (bnd_world_ != world || bnd_rank_ != comm->rank()))
+        return err_->fail(AVN_ERR_INVALID_ARGUMENT, "boundary was set for rank %d of %d, the communicator is rank %d of %d", bnd_rank_, bnd_world_, comm->rank(), world);
+    const size_t table_bytes = bnd_slots_ * 4 * sizeof(Vec4<S>);
+    if (table_bytes) {
+        AVN_CUDA(bnd_table_.ensure(table_bytes));
+        AVN_CUDA(bnd_gathered_.ensure(table_bytes * size_t(world)));
+    }
+    AvnStatus st;
+    auto exchange = [&]() -> AvnStatus {
+        if (table_bytes == 0) return AVN_OK;
+        AvnStatus e = boundary_pack(bnd_table_.p);
+        if (e != AVN_OK) return e;
+        if ((e = comm->all_gather(bnd_table_.p, bnd_gathered_.p, table_bytes)) != AVN_OK) return e;
+        ++exchanges_;
+        return boundary_apply(bnd_gathered_.p);
+    };
+    exchanges_ = 0;
+    // agreement on the restitution pass (every rank must launch it, and exchange after it, or none): max over ranks of the host flag
+    int any_rest = host_any_restitution_ ? 1 : 0;
+    if (world > 1) {
+        AVN_CUDA(bnd_agree_.ensure(sizeof(int)));
+        if (!h_agree_) AVN_CUDA(cudaHostAlloc(&h_agree_, sizeof(int), cudaHostAllocDefault));
+        *h_agree_ = any_rest;
+        AVN_CUDA(cudaMemcpyAsync(bnd_agree_.p, h_agree_, sizeof(int), cudaMemcpyHostToDevice, stream_));
+        if ((st = comm->all_reduce_max_i32(bnd_agree_.as<int>(), 1)) != AVN_OK) return st;
+        AVN_CUDA(cudaMemcpyAsync(h_agree_, bnd_agree_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        any_rest = *h_agree_;
+    }
+    const uint32_t substeps = uint32_t(dev_.substeps);
+    for (uint32_t s = 0; s < substeps; ++s) {
+        if ((st = run_range(s, 1, s == 0 ? AVN_RUN_PREPARE : 0u)) != AVN_OK) return st;
+        if ((st = exchange()) != AVN_OK) return st;
+    }
+    if (substeps == 0 && (st = run_range(0, 0, AVN_RUN_PREPARE)) != AVN_OK) return st;
+    if (any_rest) {
+        if ((st = boundary_snapshot()) != AVN_OK) return st;
+        if ((st = run_range(substeps, 0, AVN_RUN_RESTITUTION)) != AVN_OK) return st;
+        if ((st = exchange()) != AVN_OK) return st;
+    }
+    return run_range(substeps, 0, AVN_RUN_FINALIZE);
+}
+
 template <class S>
 AvnStatus Solver<S>::download() {
     if (!ran_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_solver_download before avn_solver_run");
@@ -795,8 +860,8 @@ AvnStatus Solver<S>::download() {
     {
         unsigned long long tr[8];
         cudaMemcpy(tr, dev_.any_restitution + 2, sizeof tr, cudaMemcpyDeviceToHost);
-        if (tr[4]) fprintf(stderr, "[avn wave trace] item-warps %llu  avg cycles: wait %.0f  load %.0f  compute %.0f  store+publish %.0f\n", tr[4],
-                           double(tr[0]) / tr[4], double(tr[1]) / tr[4], double(tr[2]) / tr[4], double(tr[3]) / tr[4]);
+        if (tr[4]) fprintf(stderr, "[avn wave trace] item-warps %llu  avg cycles: wait(records) %.0f  wait(delta)+staging %.0f  separations/load %.0f  compute %.0f  store+publish %.0f\n", tr[4],
+                           double(tr[0]) / tr[4], double(tr[5]) / tr[4], double(tr[1]) / tr[4], double(tr[2]) / tr[4], double(tr[3]) / tr[4]);
     }
 #endif
     if (flags_host[1] == WAVE_BAD_COLOURING)

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include "joints_dev.cuh"
+#include "wave32_dev.cuh"
 
 namespace avn {
 namespace cg = cooperative_groups;
@@ -97,6 +98,7 @@ __device__ __forceinline__ void grid_contact_pass(const DevSolver<S>& d, cg::gri
 #define AVN_WAVE_CHUNK 32
 #endif
 constexpr int WAVE_CHUNK = AVN_WAVE_CHUNK;
+// f32 runs the sector-record protocol (wave32_dev.cuh), f64 the counter protocol (solver_dev.cuh)
 template <class S, int PASS, int MAXP>
 __device__ __noinline__ void wave_contact_chunk(const DevSolver<S>& d, int slot, int s, int it, bool active) {
     contact_item<S, PASS, true, MAXP>(d, slot, s, it, active);
@@ -105,8 +107,50 @@ template <class S>
 __device__ __noinline__ void wave_iv_chunk(const DevSolver<S>& d, int i, int s, bool active) { integrate_velocity_item<S, true>(d, i, s, active); }
 template <class S>
 __device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s, bool active) { integrate_position_item<S, true>(d, i, s, active); }
+// f32: the sector-record protocol.  (-DAVN_WAVE_COUNTERS_F32 builds the round-1 counter protocol for f32 as well, for A/B timing.)
+// (BPS and MAXP are template parameters of all of them only so that every megakernel variant owns its copies: ptxas 12.9 segfaults when two
+//  kernels share a __noinline__ function that contains the 256-bit accesses)
+template <int PASS, int MAXP, int BPS>
+__device__ __noinline__ void wave32_contact_chunk(const DevSolver<float>& d, int slot, int s, int it, bool active) {
+    w32_contact_item<PASS, MAXP>(d, slot, s, it, active);
+}
+template <int BPS, int MAXP> __device__ __noinline__ void wave32_iv_chunk(const DevSolver<float>& d, int i, int s, bool active) { w32_integrate_velocity_item(d, i, s, active); }
+template <int BPS, int MAXP> __device__ __noinline__ void wave32_ip_chunk(const DevSolver<float>& d, int i, int s, bool active) { w32_integrate_position_item(d, i, s, active); }
+#ifdef AVN_WAVE_COUNTERS_F32
+constexpr bool WAVE_RECORDS_F32 = false;
+#else
+constexpr bool WAVE_RECORDS_F32 = true;
+#endif
+template <class S> struct UseRecords { static constexpr bool value = false; };
+template <> struct UseRecords<float> { static constexpr bool value = WAVE_RECORDS_F32; };
+template <class S, int PASS, int MAXP, int BPS>
+__device__ __forceinline__ void wave_contact(const DevSolver<S>& d, int slot, int s, int it, bool active) {
+    if constexpr (UseRecords<S>::value) wave32_contact_chunk<PASS, MAXP, BPS>(d, slot, s, it, active);
+    else wave_contact_chunk<S, PASS, MAXP>(d, slot, s, it, active);
+}
+template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_iv(const DevSolver<S>& d, int i, int s, bool active) {
+    if constexpr (UseRecords<S>::value) wave32_iv_chunk<BPS, MAXP>(d, i, s, active);
+    else wave_iv_chunk<S>(d, i, s, active);
+}
+template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_ip(const DevSolver<S>& d, int i, int s, bool active) {
+    if constexpr (UseRecords<S>::value) wave32_ip_chunk<BPS, MAXP>(d, i, s, active);
+    else wave_ip_chunk<S>(d, i, s, active);
+}
 
+// L2 prefetch of the immutable constraint rows of a chunk this warp will process one iteration from now: at 100k bodies the planes
+// (>100 MB) stream from HBM every pass, and an item can do nothing before its index row has arrived — the prefetch turns that DRAM
+// latency (and its jitter, which a 64-way dependency wait amplifies) into an L2 hit.
 template <class S, int MAXP>
+__device__ __forceinline__ void wave_prefetch_slot(const DevSolver<S>& d, int slot) {
+#ifndef AVN_NO_WAVE_PREFETCH
+    const char* base = reinterpret_cast<const char*>(d.cst + slot);
+    const size_t stride = size_t(d.Mpad) * sizeof(Vec4<S>);
+#pragma unroll
+    for (int r = 0; r < CP_PT0 + 3 * MAXP; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + size_t(r) * stride));
+#endif
+}
+
+template <class S, int MAXP, int BPS>
 __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int lane = threadIdx.x & 31;
     const bool active = lane < WAVE_CHUNK;
@@ -116,21 +160,37 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
     const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
     const long long total = per_substep * d.sub_end;
+    // position of a chunk inside its substep -> slot of its first item, or -1 for a body chunk
+    auto contact_slot_of = [&](long long r) -> int {
+        if (r < body_chunks) return -1;
+        r -= body_chunks;
+        if (r < (long long)(1 + d.iters) * slot_chunks) return int(r % slot_chunks) * WAVE_CHUNK;
+        r -= (long long)(1 + d.iters) * slot_chunks;
+        if (r < body_chunks) return -1;
+        return int(r - body_chunks) * WAVE_CHUNK;
+    };
     for (long long g = per_substep * d.sub_begin + warp_id; g < total; g += warps) {
         const int s = int(g / per_substep);
         long long r = g - (long long)s * per_substep;
-        if (r < body_chunks) { wave_iv_chunk<S>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
+        {   // the chunk after this one
+            const long long gn = g + warps;
+            if (gn < total) {
+                const int ns = contact_slot_of(gn % per_substep);
+                if (ns >= 0 && active) wave_prefetch_slot<S, MAXP>(d, ns + lane);
+            }
+        }
+        if (r < body_chunks) { wave_iv<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
         r -= body_chunks;
         if (r < (long long)(1 + d.iters) * slot_chunks) {
             const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * WAVE_CHUNK + lane;
-            if (pass == 0) wave_contact_chunk<S, PASS_WARM, MAXP>(d, slot, s, 0, active);
-            else wave_contact_chunk<S, PASS_SOLVE_BIAS, MAXP>(d, slot, s, pass - 1, active);
+            if (pass == 0) wave_contact<S, PASS_WARM, MAXP, BPS>(d, slot, s, 0, active);
+            else wave_contact<S, PASS_SOLVE_BIAS, MAXP, BPS>(d, slot, s, pass - 1, active);
             continue;
         }
         r -= (long long)(1 + d.iters) * slot_chunks;
-        if (r < body_chunks) { wave_ip_chunk<S>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
+        if (r < body_chunks) { wave_ip<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
         r -= body_chunks;
-        wave_contact_chunk<S, PASS_RELAX, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, 0, active);
+        wave_contact<S, PASS_RELAX, MAXP, BPS>(d, int(r) * WAVE_CHUNK + lane, s, 0, active);
     }
 }
 
@@ -160,7 +220,7 @@ __global__ void __launch_bounds__(MEGA_BLOCK, BPS) step_megakernel(const __grid_
     // step); otherwise the barrier schedule below runs, which terminates on any input (read after a grid barrier: uniform over the grid)
     const bool wave = d.wave && *reinterpret_cast<volatile int*>(d.any_restitution + 1) == 0;
     if (wave && d.sub_end > d.sub_begin) {
-        wave_substep_loop<S, MAXP>(d);
+        wave_substep_loop<S, MAXP, BPS>(d);
         grid.sync();
     }
     for (int sub = d.sub_begin; sub < (wave ? 0 : d.sub_end); ++sub) {

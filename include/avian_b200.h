@@ -362,6 +362,26 @@ AvnStatus avn_solver_needs_restitution(AvnContext* ctx, int* out_nonzero);      
 /* the context's CUDA stream (a cudaStream_t) so that the caller's collective can be ordered with the launches above */
 AvnStatus avn_get_stream(AvnContext* ctx, void** out_stream);
 
+/* ---- the communicator: one process per GPU, one AvnContext per process, one NCCL communicator per context.  NCCL is bound
+ *      at run time (dlopen "libnccl.so.2", or the name in AVN_NCCL_LIB): a host that never calls avn_comm_init with world > 1 needs no NCCL.
+ *      One rank calls avn_comm_unique_id and hands the AVN_COMM_ID_BYTES bytes to the others over any channel the host has (a file, a socket,
+ *      MPI, torch.distributed's store); then EVERY rank calls avn_comm_init with the same bytes (collective).  Errors: AVN_ERR_NCCL. */
+#define AVN_COMM_ID_BYTES 128
+AvnStatus avn_comm_unique_id(AvnContext* ctx, void* out_id /* [AVN_COMM_ID_BYTES] */);
+AvnStatus avn_comm_init(AvnContext* ctx, uint32_t rank, uint32_t world, const void* unique_id /* NULL allowed when world == 1 */);
+AvnStatus avn_comm_destroy(AvnContext* ctx);
+/* all-gather of bytes_per_rank bytes of DEVICE memory from every rank into recv_device (world * bytes_per_rank, rank-major), enqueued on the
+ * context's stream (pair lists of the slab broad phase, results of the owned rows) */
+AvnStatus avn_comm_all_gather(AvnContext* ctx, const void* send_device, void* recv_device, size_t bytes_per_rank);
+/*
+ * The whole partitioned solver stage of this rank, inside the library: after avn_solver_upload (this rank's share) and
+ * avn_solver_set_boundary, runs for every substep  avn_solver_run_range -> pack -> ncclAllGather of the packed tables -> apply  on the
+ * context's stream, the restitution launch + one more exchange when any rank uploaded a non-zero coefficient (agreed with one all-reduce),
+ * and the finalize launch.  Follow with avn_solver_download.  With a communicator of one rank (or no boundary) it equals avn_solver_run.
+ * The exchange tables live in the library; nothing crosses the host.
+ */
+AvnStatus avn_solver_step_partitioned(AvnContext* ctx);
+
 /*
  * Sweep-and-prune pair generation.  Replaces collect_collision_pairs / sweep_and_prune (broad_phase.rs:343-474)
  * over the intervals that update_aabb_intervals / add_new_aabb_intervals maintain (broad_phase.rs:214-315).

@@ -10,7 +10,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from avian_b200 import api  # noqa: E402
 
-lib = C.CDLL(str(ROOT / "avian_b200" / "lib" / "libavian_b200_trace.so"))
+from avian_b200 import _build  # noqa: E402
+lib = C.CDLL(str(_build.build_variant("trace", ["AVN_WAVE_TRACE"])))
 api.bind_abi(lib)
 api._lib = lib
 import bench  # noqa: E402

@@ -197,6 +197,87 @@ def test_two_gpu_nccl_slab_solver():
         assert np.array_equal(results[0][1][k], results[1][1][k]), k
 
 
+# ---- the partitioned stage inside the library: NCCL behind the C ABI (avn_comm_init + avn_solver_step_partitioned) -------------------
+def test_step_partitioned_with_a_communicator_of_one_equals_solver_run(gpu_ctx):
+    """world = 1 needs no NCCL: avn_solver_step_partitioned == avn_solver_run bit for bit."""
+    prm, b, m = stack_input()
+    b1, m1 = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, b1, m1)
+    b2, m2 = b.copy(), m.copy()
+    gpu_ctx.comm_init(0, 1, None)
+    gpu_ctx.solver_upload(prm, b2, m2, None)
+    gpu_ctx.solver_step_partitioned()
+    gpu_ctx.solver_download()
+    for k in parallel.BODY_OUTPUTS:
+        assert np.array_equal(getattr(b1, k), getattr(b2, k)), k
+    for k in parallel.POINT_OUTPUTS:
+        assert np.array_equal(getattr(m1, k), getattr(m2, k)), k
+
+
+def _lib_nccl_worker(rank, world, id_path, q):
+    """No torch.distributed anywhere: the unique id travels through a file, the collective lives in libavian_b200.so."""
+    import time
+    torch.cuda.set_device(rank)
+    prm, b, m = stack_input(nx=10, ny=4, nz=4, steps=3, substeps=6)
+    with api.Context(device=rank) as ctx:
+        if rank == 0:
+            tmp = id_path + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(ctx.comm_unique_id())
+            os.replace(tmp, id_path)
+        t0 = time.time()
+        while not os.path.exists(id_path):
+            assert time.time() - t0 < 120, "unique id never arrived"
+            time.sleep(0.05)
+        with open(id_path, "rb") as f:
+            uid = f.read()
+        ctx.comm_init(rank, world, uid)
+        cuts = parallel.body_slab_cuts(b, world)
+        sh = parallel.shard_solver(b, m, cuts, rank, world)
+        ctx.solver_upload(prm, sh.bodies, sh.manifolds, None)
+        ctx.solver_set_boundary(sh.bnd_body, sh.bnd_source, sh.bnd_owner, sh.record_count, rank, world)
+        ctx.solver_step_partitioned()
+        ctx.solver_download()
+        rows = sh.body_index[sh.owned_body]
+        q.put((rank, rows, {k: getattr(sh.bodies, k)[sh.owned_body].copy() for k in parallel.BODY_OUTPUTS}, sh.point_index,
+               {} if sh.manifolds is None else {k: getattr(sh.manifolds, k).copy() for k in parallel.POINT_OUTPUTS}, sh.slot_count))
+        ctx.comm_destroy()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="NCCL refuses two ranks on one device: needs 2 GPUs (run with gpurun --gpus 2; the driver's "
+                                                          "single-GPU test box skips it, scripts/multi_gpu_checks.sh runs it)")
+def test_two_gpu_library_nccl_partitioned_step(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    id_path = str(tmp_path / "nccl_id.bin")
+    procs = [ctx.Process(target=_lib_nccl_worker, args=(r, world, id_path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=300) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    prm, b, m = stack_input(nx=10, ny=4, nz=4, steps=3, substeps=6)
+    bg, mg = b.copy(), m.copy()
+    for rank, rows, bodies, pidx, points, slots in results:
+        assert slots > 0
+        for k in parallel.BODY_OUTPUTS:
+            getattr(bg, k)[rows] = bodies[k]
+        for k, v in points.items():
+            getattr(mg, k)[pidx] = v
+    bo, mo = b.copy(), m.copy()
+    parallel.slab_solver_step_local(lambda r: oracle_lib.OracleSlabEngine(), prm, bo, mo, world)
+    assert_bodies_close(bg, bo, what="library NCCL slabs: ")
+    assert_manifolds_close(mg, mo, what="library NCCL slabs: ")
+    # and the library-driven step is the same arithmetic as the caller-driven one (lockstep engines on one device)
+    bl, ml = b.copy(), m.copy()
+    _gpu_lockstep(prm, bl, ml, world)
+    for k in parallel.BODY_OUTPUTS:
+        assert np.array_equal(getattr(bg, k), getattr(bl, k)), k
+
+
 # ---- island sharding of one scene: exact ------------------------------------------------------------------------------------
 def test_island_sharded_step_on_device_is_bit_identical(gpu_ctx):
     """the ragdoll field dealt island by island to 3 ranks' worth of avn_solver_step calls (one after the other on this
