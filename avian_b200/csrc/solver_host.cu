@@ -54,6 +54,7 @@ class Solver final : public SolverBase {
         // latency, fewer registers spill more.  Measured best (scripts/solver_timing.py): 3 blocks/SM for f32, 2 for f64 (whose
         // state is twice as wide).  AVN_MEGA_BPS = 2|3|4 overrides the default for experiments.
         const char* bps = getenv("AVN_MEGA_BPS");
+        bps_forced_ = bps != nullptr;
         mega_bps_ = bps ? atoi(bps) : (sizeof(S) == 8 ? 2 : 3);
         if (mega_bps_ < 2 || mega_bps_ > 4) mega_bps_ = 3;
         if (mode && !strcmp(mode, "wave")) force_wave_ = true;
@@ -116,23 +117,30 @@ class Solver final : public SolverBase {
     int sm_count_ = 148;
     bool coop_ok_ = false, use_mega_ = true, use_wave_ = true, l2_persist_ = false;
     size_t l2_persist_bytes_ = 0, l2_window_max_ = 0;
-    int mega_grid_ = 0, mega_bps_ = 3, mega_maxp_ = 0;
+    int mega_grid_ = 0, mega_bps_ = 3, mega_maxp_ = 0, mega_sel_bps_ = 0;
+    bool bps_forced_ = false;
     bool force_wave_ = false;
 
     // The persistent kernel is compiled per (blocks/SM, widest manifold): MAXP = 1 (sphere-only scenes) drops the unrolled code and the
     // registers of points 2..4.  Returns false when the cooperative grid cannot be sized.
-    template <int MAXP> const void* mega_variant() const {
-        switch (mega_bps_) {
+    template <int MAXP> const void* mega_variant(int bps) const {
+        switch (bps) {
             case 2: return (const void*)step_megakernel<S, 2, MAXP>;
             case 4: return (const void*)step_megakernel<S, 4, MAXP>;
             default: return (const void*)step_megakernel<S, 3, MAXP>;
         }
     }
-    bool select_megakernel(int max_points) {
+    // blocks per SM of a step: the f32 wavefront routines fit 128 registers without spills (the delta records die before the main loop), so a
+    // wavefront-scheduled f32 step runs 4 blocks = 16 warps per SM (1.618 -> 1.562 ms at 100k cubes); the barrier schedule keeps the
+    // measured best of round 1 (3 for f32, 2 for f64).  AVN_MEGA_BPS overrides both.
+    int bps_for(bool wave_candidate) const { return bps_forced_ ? mega_bps_ : ((sizeof(S) == 4 && wave_candidate) ? 4 : mega_bps_); }
+    bool select_megakernel(int max_points, int bps = 0) {
         const int maxp = max_points <= 1 ? 1 : AVN_MAX_MANIFOLD_POINTS;
-        if (maxp == mega_maxp_) return mega_grid_ > 0;
+        if (bps == 0) bps = mega_bps_;
+        if (maxp == mega_maxp_ && bps == mega_sel_bps_) return mega_grid_ > 0;
         mega_maxp_ = maxp;
-        mega_fn_ = maxp == 1 ? mega_variant<1>() : mega_variant<AVN_MAX_MANIFOLD_POINTS>();
+        mega_sel_bps_ = bps;
+        mega_fn_ = maxp == 1 ? mega_variant<1>(bps) : mega_variant<AVN_MAX_MANIFOLD_POINTS>(bps);
         const size_t smem = stage_bytes<S>(MEGA_BLOCK, maxp);
         int per_sm = 0;
         mega_grid_ = 0;
@@ -152,7 +160,7 @@ class Solver final : public SolverBase {
     bool uploaded_ = false, ran_ = false, host_any_restitution_ = false, prepared_ = false, mega_step_ = false;
     DevBuf bnd_of_, bnd_body_, bnd_slot_, bnd_owner_, vel_ref_, bnd_table_, bnd_gathered_, bnd_agree_;
     int* h_agree_ = nullptr;
-    int bnd_n_ = 0, bnd_rank_ = 0, bnd_world_ = 1;
+    int bnd_n_ = 0, bnd_rank_ = 0, bnd_world_ = 1, step_bps_ = 0;
     size_t bnd_slots_ = 0;
 
     DevSolver<S> dev_{};
@@ -540,7 +548,13 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
     dev_.sub_end = int(first + count);
     dev_.do_restitution = (flags & AVN_RUN_RESTITUTION) ? 1 : 0;
     dev_.do_finalize = (flags & AVN_RUN_FINALIZE) ? 1 : 0;
-    bool mega = use_mega_ && coop_ok_ && select_megakernel(max_np_);
+    bool mega = use_mega_ && coop_ok_;
+    if (prepare) {
+        // the schedule is decided before the kernel variant: a step that can run the wavefront schedule gets the 4-blocks-per-SM build
+        const bool wave_candidate = use_wave_ && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0;
+        step_bps_ = bps_for(wave_candidate);
+    }
+    mega = mega && select_megakernel(max_np_, step_bps_);
     if (prepare) {
         launches_ = 0;
         cudaEventRecord(ev_[EV_RUN0], stream_);

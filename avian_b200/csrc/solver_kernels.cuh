@@ -137,12 +137,12 @@ template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_ip(co
     else wave_ip_chunk<S>(d, i, s, active);
 }
 
-// L2 prefetch of the immutable constraint rows of a chunk this warp will process one iteration from now: at 100k bodies the planes
-// (>100 MB) stream from HBM every pass, and an item can do nothing before its index row has arrived — the prefetch turns that DRAM
-// latency (and its jitter, which a 64-way dependency wait amplifies) into an L2 hit.
+// EXPERIMENT (off): L2 prefetch of the immutable constraint rows of the chunk this warp processes one iteration from now.  The idea: at
+// 100k bodies the planes (>100 MB) stream from HBM every pass and an item can do nothing before its index row has arrived.  The measurement
+// says the 16 extra CCTL per item cost more than the latency they hide.
 template <class S, int MAXP>
 __device__ __forceinline__ void wave_prefetch_slot(const DevSolver<S>& d, int slot) {
-#ifndef AVN_NO_WAVE_PREFETCH
+#ifdef AVN_WAVE_PREFETCH   // measured SLOWER (1.618 -> 1.671 ms at 100k cubes, 1.562 -> 1.774 at 4 blocks/SM): kept as an experiment
     const char* base = reinterpret_cast<const char*>(d.cst + slot);
     const size_t stride = size_t(d.Mpad) * sizeof(Vec4<S>);
 #pragma unroll
@@ -160,8 +160,8 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
     const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
     const long long total = per_substep * d.sub_end;
-    // position of a chunk inside its substep -> slot of its first item, or -1 for a body chunk
-    auto contact_slot_of = [&](long long r) -> int {
+    // position of a chunk inside its substep -> slot of its first item, or -1 for a body chunk (prefetch experiment)
+    [[maybe_unused]] auto contact_slot_of = [&](long long r) -> int {
         if (r < body_chunks) return -1;
         r -= body_chunks;
         if (r < (long long)(1 + d.iters) * slot_chunks) return int(r % slot_chunks) * WAVE_CHUNK;
@@ -172,6 +172,7 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     for (long long g = per_substep * d.sub_begin + warp_id; g < total; g += warps) {
         const int s = int(g / per_substep);
         long long r = g - (long long)s * per_substep;
+#ifdef AVN_WAVE_PREFETCH
         {   // the chunk after this one
             const long long gn = g + warps;
             if (gn < total) {
@@ -179,6 +180,7 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
                 if (ns >= 0 && active) wave_prefetch_slot<S, MAXP>(d, ns + lane);
             }
         }
+#endif
         if (r < body_chunks) { wave_iv<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
         r -= body_chunks;
         if (r < (long long)(1 + d.iters) * slot_chunks) {

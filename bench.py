@@ -235,6 +235,8 @@ def run_gpu(args, info):
         ctx.solver_step(prm, bodies, man, joints)
     barrier()
     wall_e2e = time.perf_counter() - t0
+    te = ctx.timings()     # of the last end-to-end solver call: where its time went
+    e2e_break = {"solver_h2d": te["h2d_ms"], "solver_kernels": te["total_ms"], "solver_d2h": te["d2h_ms"]}
     # keep the GPU under the same load until the sampler has a few readings (nvidia-smi takes ~100 ms per call)
     t_hold = time.perf_counter()
     while rank == 0 and len(sampler.rows) < 3 and time.perf_counter() - t_hold < 3.0:
@@ -312,7 +314,8 @@ def run_gpu(args, info):
         "metric": metric_name(args.scene), "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": span_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": sname, "data": "synthetic", "config": cfg,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e_ms / K},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e_ms / K,
+                "last_step_device_ms": e2e_break},
         "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks, "roofline": roof,
         "breakdown_ms": {"broad_phase": bp_ms, "solver_stage": mega_ms, "resident_span": span_ms / K, "resident_wall": wall_res_ms / K,
                          "kernel_launches_per_step": launches_per_step},
@@ -442,7 +445,7 @@ def partition_islands(args, info) -> dict | None:
     ctx = api.Context(device=info.local_rank, scalar=np.float32)
     try:
         sc, prm, bodies, man, aabbs, joints = build_snapshot(scene, SCENES[scene][2], ctx)
-        labels = parallel.find_islands(bodies, man, joints)
+        labels, n_islands = parallel.find_islands(bodies, man, joints)
         sh = parallel.shard_by_island(bodies, man, joints, world, rank, labels)
         acuts = parallel.slab_cuts(aabbs.aabb_min[:, 0], world)
         ashard = parallel.shard_aabbs(aabbs, acuts, rank)
@@ -461,7 +464,7 @@ def partition_islands(args, info) -> dict | None:
         if rank != 0:
             return None
         return {"scene": sc.name, "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world, "dtype": "f32",
-                "bodies": bodies.count, "joints": 0 if joints is None else joints.count, "manifolds": man.count, "islands": int(labels.max()) + 1,
+                "bodies": bodies.count, "joints": 0 if joints is None else joints.count, "manifolds": man.count, "islands": int(n_islands),
                 "bodies_held_all_ranks": int(held[0]), "joints_all_ranks": int(held[1]), "collective": "none in the data path (islands are independent)",
                 "launch_mode": MODES.get(mode, mode), "parity": "bit-identical to the unsharded step (tests/test_island_cpu.py, tests/test_gpu_multi.py)"}
     finally:

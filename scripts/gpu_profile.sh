@@ -1,19 +1,20 @@
 #!/bin/bash
-# Run on the GPU box (under gpurun).  Produces under gpurun_out/:
-#   launches_phases.csv  per-launch device times of one-launch-per-phase mode (kernel SHARES of a step)
-#   launches_mega.csv    the same for the default megakernel mode
-#   mega_full.ncu-rep    ncu --set full of the step megakernel (1 launch)
-#   solve_full.ncu-rep   ncu --set full of the biased-solve phase kernel (3 launches)
+# Run on the GPU box (under gpurun): ncu evidence for the current tree.  Produces under gpurun_out/ (TAG = first argument, default r02):
+#   TAG_launches_<scene>.csv      per-launch device times of the default mode (kernel SHARES of a step)
+#   TAG_mega_<scene>.ncu-rep      ncu --set full of the step megakernel (1 launch)  + TAG_mega_<scene>_raw.csv (--page raw)
+# Scenes: stack100k (wavefront records, f32) and spheres1m (barrier schedule, f64, MAXP = 1).
 set -u
-SCENE=${1:-stack100k}
+TAG=${1:-r02}
+shift || true
+SCENES=${@:-stack100k spheres1m}
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
-AVN_LAUNCH_MODE=phases timeout 600 $NCU --metrics gpu__time_duration.sum -c 6000 --csv --log-file gpurun_out/launches_phases.csv \
-    python bench.py --scene $SCENE --steps 1 --warmup 3 --settle 0 --no-cpu > gpurun_out/ncu_phases.log 2>&1
-timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/launches_mega.csv \
-    python bench.py --scene $SCENE --steps 1 --warmup 3 --settle 0 --no-cpu > gpurun_out/ncu_mega.log 2>&1
-timeout 900 $NCU --set full --import-source on --kernel-name-base demangled -k regex:step_megakernel -s 2 -c 1 -o gpurun_out/mega_full \
-    python bench.py --scene $SCENE --steps 1 --warmup 3 --settle 0 --no-cpu > gpurun_out/ncu_mega_full.log 2>&1
-AVN_LAUNCH_MODE=phases timeout 900 $NCU --set full --import-source on --kernel-name-base demangled -k 'regex:phase_kernel<float, \(int\)6>' -s 12 -c 3 -o gpurun_out/solve_full \
-    python bench.py --scene $SCENE --steps 1 --warmup 3 --settle 0 --no-cpu > gpurun_out/ncu_solve_full.log 2>&1
-ls -la gpurun_out
+for SCENE in $SCENES; do
+  ARGS="bench.py --scene $SCENE --steps 2 --warmup 3 --no-cpu --no-partition --no-pass"
+  timeout 900 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/${TAG}_launches_${SCENE}.csv python $ARGS > gpurun_out/${TAG}_ncu_launches_${SCENE}.log 2>&1
+  timeout 1200 $NCU --set full --import-source on --kernel-name-base demangled -k regex:step_megakernel -s 3 -c 1 -f -o gpurun_out/${TAG}_mega_${SCENE} \
+      python $ARGS > gpurun_out/${TAG}_ncu_full_${SCENE}.log 2>&1
+  ncu -i gpurun_out/${TAG}_mega_${SCENE}.ncu-rep --page raw --csv > gpurun_out/${TAG}_mega_${SCENE}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/${TAG}_mega_${SCENE}.ncu-rep --page details > gpurun_out/${TAG}_mega_${SCENE}_details.txt 2>/dev/null
+done
+ls -la gpurun_out | tail -20

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Turn the ncu outputs under gpurun_out/ into the small text/CSV summaries committed under profiles/.
-usage: python scripts/summarize_profiles.py <tag>      (e.g. r01a)"""
+"""Turn the ncu outputs scripts/gpu_profile.sh left under gpurun_out/ into the small text summaries committed under profiles/, and
+regenerate profiles/traffic.json (DRAM bytes per launch of the dominant kernel, read by bench.py for `roofline.traffic`) FROM THE SAME CAPTURE.
+usage: python scripts/summarize_profiles.py <tag> [scene ...]      (e.g. r02b stack100k spheres1m)"""
 import collections
 import csv
-import subprocess
+import json
 import sys
 from pathlib import Path
 
@@ -12,10 +13,13 @@ OUT = ROOT / "gpurun_out"
 PROF = ROOT / "profiles"
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"]
+GB = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
 def launch_summary(csv_path: Path, out_path: Path, note: str):
@@ -35,34 +39,46 @@ def launch_summary(csv_path: Path, out_path: Path, note: str):
             f.write(f"{sum(v):12.1f} {sum(v) / total:7.3f} {len(v):6d} {sum(v) / len(v):9.2f} {min(v):9.2f} {max(v):9.2f}  {k[:150]}\n")
 
 
-def full_summary(rep: Path, out_path: Path, note: str):
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+def full_summary(raw_csv: Path, out_path: Path, note: str):
+    """raw_csv = `ncu -i X.ncu-rep --page raw --csv`; returns (kernel name, dram bytes per launch) of the first row"""
+    rows = list(csv.reader(raw_csv.read_text().splitlines()))
     hdr, units = rows[0], rows[1]
+    first = None
     with out_path.open("w") as f:
-        f.write(f"# {note}\n# source: {rep.name} (ncu --set full --clock-control none)\n")
+        f.write(f"# {note}\n# source: {raw_csv.name} (ncu --set full --clock-control none --import-source on, --page raw)\n")
         for r in rows[2:]:
-            f.write(f"\nkernel {r[hdr.index('Kernel Name')][:120]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
+            name = r[hdr.index("Kernel Name")]
+            f.write(f"\nkernel {name[:160]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n")
+            vals = {}
             for i, h in enumerate(hdr):
                 if h in KEYS or ("issue_stalled" in h and "per_issue_active" in h):
                     f.write(f"  {h:88s} {units[i]:16s} {r[i]}\n")
+                    vals[h] = (r[i], units[i])
+            if first is None and "dram__bytes_read.sum" in vals:
+                tot = sum(float(vals[k][0].replace(",", "")) * GB.get(vals[k][1], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                first = (name, int(tot))
+    return first
 
 
 if __name__ == "__main__":
     tag = sys.argv[1]
+    scenes = sys.argv[2:] or ["stack100k", "spheres1m"]
     PROF.mkdir(exist_ok=True)
-    for name, note in (("launches_phases", "one launch per phase (AVN_LAUNCH_MODE=phases), 100k-cube stack"),
-                       ("launches_mega", "default mode: one persistent megakernel per step, 100k-cube stack")):
-        p = OUT / f"{name}.csv"
+    tfile = PROF / "traffic.json"
+    traffic = json.loads(tfile.read_text()) if tfile.exists() else {}
+    traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from one `ncu --set full` capture of the tree "
+                        "named in `capture`; written by scripts/summarize_profiles.py together with the text summary it cites")
+    for scene in scenes:
+        p = OUT / f"{tag}_launches_{scene}.csv"
         if p.exists():
-            launch_summary(p, PROF / f"{tag}_{name}_summary.txt", note)
-    for name, note in (("mega_full", "step_megakernel<float>, 100k-cube stack, one step"),
-                       ("solve_full", "phase_kernel<float, OP_SOLVE_BIAS> (solver-iteration kernel), 100k-cube stack, 3 launches"),
-                       ("sweep_full", "broad-phase sweep kernel, 100k-cube stack")):
-        p = OUT / f"{name}.ncu-rep"
+            launch_summary(p, PROF / f"{tag}_launches_{scene}_summary.txt", f"default mode: one persistent megakernel per step + the broad phase, {scene}")
+        p = OUT / f"{tag}_mega_{scene}_raw.csv"
         if p.exists():
-            full_summary(p, PROF / f"{tag}_{name}_ncu.txt", note)
-    for name in ("bench_100k.log", "bench_100k_phases.log", "pytest_gpu.log", "gpu.txt"):
-        p = OUT / name
+            got = full_summary(p, PROF / f"{tag}_mega_{scene}_ncu.txt", f"step_megakernel, {scene}, one step")
+            if got:
+                traffic[scene] = {"kernel": got[0][:120], "dram_bytes_per_launch": got[1], "capture": f"{tag} (profiles/{tag}_mega_{scene}_ncu.txt)"}
+        p = OUT / f"{tag}_mega_{scene}_details.txt"
         if p.exists():
-            (PROF / f"{tag}_{name}").write_text(p.read_text())
+            (PROF / f"{tag}_mega_{scene}_ncu_details.txt").write_text(p.read_text())
+    tfile.write_text(json.dumps(traffic, indent=1))
+    print(json.dumps(traffic, indent=1))

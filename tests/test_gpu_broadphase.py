@@ -140,3 +140,48 @@ def test_large_sizes_properties(gpu_ctx):
     assert ((mn[a] <= mx[b]) & (mn[b] <= mx[a])).all()
     sx = mn[aabbs.collider[aabbs.order_out], 0]
     assert (np.diff(sx) >= 0).all()
+
+
+def _poison(a, rows):
+    vals = [np.nan, np.inf, -np.inf]
+    for k, r in enumerate(rows):
+        (a.aabb_min if k % 2 else a.aabb_max)[r, k % 3] = vals[k % 3]
+
+
+@pytest.mark.parametrize("scalar", [np.float32, np.float64])
+def test_nonfinite_aabbs_are_dropped(scalar):
+    """update_aabb_intervals' retain (broad_phase.rs:243-245): an interval whose AABB is NaN / infinite leaves the list — no pairs, absent from
+    the new persistent order.  The device flags it, the host compacts and reruns; the result equals the sweep of the finite intervals alone."""
+    n = 3000
+    rows = [5, 17, 400, 401, 2999, 1234]
+    a, ao = random_aabbs(n, 77, scalar=scalar), random_aabbs(n, 77, scalar=scalar)
+    _poison(a, rows); _poison(ao, rows)
+    keep = np.setdiff1d(np.arange(n), rows)
+    clean = random_aabbs(n, 77, scalar=scalar)
+    clean = api.Aabbs(**{k: (v[keep] if isinstance(v, np.ndarray) and v.shape[0] == n else v) for k, v in clean.__dict__.items()})
+    clean.order_out = np.zeros(keep.size, dtype=np.uint32)
+    want = oracle_lib.broadphase(clean)
+    o = oracle_lib.broadphase(ao)
+    assert_pairs_equal(o, want)
+    assert ao.retained_count == keep.size and np.array_equal(ao.order_out[:keep.size], keep[clean.order_out])
+    with api.Context(device=0, scalar=scalar) as ctx:
+        g = ctx.broadphase(a)
+        assert_pairs_equal(g, want)
+        assert a.retained_count == keep.size
+        assert np.array_equal(a.order_out[:keep.size], keep[clean.order_out])
+        # and a finite upload afterwards is untouched by the episode
+        b, bo = random_aabbs(n, 78, scalar=scalar), random_aabbs(n, 78, scalar=scalar)
+        assert_pairs_equal(ctx.broadphase(b), oracle_lib.broadphase(bo))
+        assert b.retained_count == n
+
+
+def test_repeated_runs_report_their_own_launch_count(gpu_ctx):
+    a = random_aabbs(4000, 3)
+    gpu_ctx.broadphase_upload(a)
+    out = api.PairList.empty(1 << 16)
+    counts = []
+    for _ in range(3):
+        gpu_ctx.broadphase_run()
+        gpu_ctx.broadphase_download(out)
+        counts.append(gpu_ctx.timings()["kernel_launches"])
+    assert counts[0] == counts[1] == counts[2] and 0 < counts[0] < 64, counts

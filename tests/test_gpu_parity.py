@@ -342,3 +342,43 @@ def test_cubes_simulation_is_locally_deterministic_on_gpu(gpu_ctx):
     assert a[0][1:, 1].min() > -1.0                       # nothing fell through the ground
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_invalid_inputs_are_refused_not_gathered_through(gpu_ctx):
+    """a manifold body index outside [-1, B) must be an error at upload, not an out-of-bounds gather on the device."""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(4, 3, 4, brick=True), steps=2, substeps=4)
+    for bad in (b.count, b.count + 7, -2):
+        mb = m.copy()
+        mb.body2 = mb.body2.copy()
+        mb.body2[3] = bad
+        with pytest.raises(api.AvianError) as e:
+            gpu_ctx.solver_step(prm, b.copy(), mb)
+        assert e.value.status == api.ERR_INVALID_ARGUMENT
+    # the context stays usable
+    bg, mg, bo, mo = b.copy(), m.copy(), b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, bg, mg)
+    oracle_lib.solver_step(prm, bo, mo)
+    assert_bodies_close(bg, bo)
+
+
+def test_bad_colouring_is_reported_not_spun_on(gpu_ctx, monkeypatch):
+    """the wavefront schedule trusts the colouring only as far as it checks it.  Two constraints of one body in ONE colour would give
+    wrong event numbers and a spin until the watchdog; the rank pass detects it, the step falls back to barriers and the download reports it."""
+    monkeypatch.setenv("AVN_LAUNCH_MODE", "wave")
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(5, 4, 5, brick=True), steps=2, substeps=4)
+    with api.Context(device=0) as ctx:
+        ok_b, ok_m = b.copy(), m.copy()
+        ctx.solver_step(prm, ok_b, ok_m)
+        assert ctx.timings()["launch_mode"] == 2          # AVN_LAUNCH_MEGA_WAVE
+        bad = m.copy()
+        co = bad.color_offsets.copy()
+        c0 = next(c for c in range(23) if co[c + 1] - co[c] > 0)
+        c1 = next(c for c in range(c0 + 1, 23) if co[c + 1] - co[c] > 0)
+        co[c0 + 1:c1 + 1] = co[c1 + 1]                    # merge colour c1 (and the empty ones between) into c0: bodies now repeat inside a colour
+        bad.color_offsets = co
+        with pytest.raises(api.AvianError) as e:
+            ctx.solver_step(prm, b.copy(), bad)
+        assert e.value.status == api.ERR_INVALID_ARGUMENT and "colour" in str(e.value)
+        again_b, again_m = b.copy(), m.copy()
+        ctx.solver_step(prm, again_b, again_m)             # and the context is fine afterwards
+        assert np.array_equal(again_b.position, ok_b.position)

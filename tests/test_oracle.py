@@ -260,3 +260,15 @@ def test_apply_torque_reference_test():
         return 2.0 * np.arccos(min(1.0, abs(float(np.dot(q.astype(np.float64), want)))))
     assert angle_to_z(b.rotation[0], 0.5 * 1.5 * 1.5 ** 2) < 0.1
     assert angle_to_z(b.rotation[1], 1.5 * 1.5 ** 2) < 0.15
+
+
+def test_broadphase_drops_nonfinite_aabbs():
+    """update_aabb_intervals' retain (broad_phase.rs:243-245): an interval with a NaN / infinite AABB leaves the list before the sort."""
+    mn = np.array([[0, 0, 0], [0.5, 0, 0], [np.nan, 0, 0], [0.2, 0, 0], [0.4, 0, 0]], dtype=np.float32)
+    mx = mn + 1.0
+    mx[3, 1] = np.inf
+    a = api.Aabbs(collider=np.arange(5, dtype=np.uint32), body=np.arange(5, dtype=np.uint32), aabb_min=mn, aabb_max=mx,
+                  flags=np.full(5, api.AABB_GENERATE_CONSTRAINTS, dtype=np.uint8), order_out=np.zeros(5, dtype=np.uint32))
+    p = oracle_lib.broadphase(a)
+    assert a.retained_count == 3 and list(a.order_out[:3]) == [0, 4, 1]
+    assert sorted(zip(p.collider1.tolist(), p.collider2.tolist())) == [(0, 1), (0, 4), (4, 1)]
