@@ -14,6 +14,8 @@ Scenes (every branch named is hit at least once, checked by the asserts at the b
   revolute_pair       two dynamic bodies, misaligned hinge axes: align_orientation then the point constraint
   fixed_pair          fixed joint with a rotation error: fixed-angle constraint then the point constraint
   spherical_dominant  spherical joint (point only) where body 1 has higher Dominance: its inertia is treated as infinite
+  revolute_limited    revolute joint bent beyond its angle limit (AngleLimit::compute_correction: asin, clamp, from_axis_angle) + JointDamping
+  spherical_limited   spherical joint beyond its swing AND twist limits
   sap_six             six intervals swept by hand (ties on min.x with -0.0/+0.0, touching y bounds, same body, layer mismatch, both inactive)
 """
 import json
@@ -113,6 +115,23 @@ SCENES["spherical_dominant"] = {
     "joints": [{"type": W.SPHERICAL, "body1": 0, "body2": 1, "local_anchor1": [0.5, 0, 0], "local_anchor2": [-0.5, 0.2, 0], "compliance0": 0.0}],
 }
 
+SCENES["revolute_limited"] = {      # the hinge is bent 1.2 rad, the limit allows [-0.5, 0.5]: align + angle limit + point, with joint damping
+    "params": params(2),
+    "bodies": [body(W.DYNAMIC, (0, 0, 0), inv_mass=1.0, inv_inertia=(4.0, 0, 0, 4.0, 0, 4.0)),
+               body(W.DYNAMIC, (0.9, 0.35, 0), rot=axis_angle((0, 0, 1), 1.2), w=(0, 0, 1.5), inv_mass=1.0, inv_inertia=(5.0, 0, 0, 5.0, 0, 5.0))],
+    "joints": [{"type": W.REVOLUTE, "body1": 0, "body2": 1, "local_anchor1": [0.5, 0, 0], "local_anchor2": [-0.5, 0, 0], "axis": [0, 0, 1],
+                "angle_limit": [-0.5, 0.5], "compliance0": 0.0, "compliance1": 0.0, "compliance2": 0.0, "damping": [0.8, 2.0]}],
+}
+
+SCENES["spherical_limited"] = {     # swing 1.0 rad against a 0.4 limit, twist 0.9 rad against 0.3: point, swing limit, twist limit
+    "params": params(2),
+    "bodies": [body(W.DYNAMIC, (0, 0, 0), inv_mass=0.5, inv_inertia=(3.0, 0, 0, 3.0, 0, 3.0)),
+               body(W.DYNAMIC, (0.3, 0.9, 0.1), rot=tuple(W.quat_mul(np.array(axis_angle((0, 0, 1), 1.0)), np.array(axis_angle((0, 1, 0), 0.9)))),
+                    w=(0.3, 0.0, -0.2), inv_mass=1.0, inv_inertia=(6.0, 0, 0, 6.0, 0, 6.0))],
+    "joints": [{"type": W.SPHERICAL, "body1": 0, "body2": 1, "local_anchor1": [0, 0.5, 0], "local_anchor2": [0, -0.5, 0], "axis": [0, 1, 0],
+                "swing_limit": [-0.4, 0.4], "twist_limit": [-0.3, 0.3], "compliance0": 0.0, "compliance1": 0.0, "compliance2": 0.0}],
+}
+
 SAP = {
     "intervals": [
         {"collider": 10, "body": 10, "min": [2.0, 0.0, 0.0], "max": [3.0, 1.0, 1.0], "memberships": 1, "filters": 0xFFFFFFFF, "inactive": True},
@@ -155,6 +174,9 @@ def main():
     s = vectors["scenes"]["sphere_bounce"]["expected_f32"]
     assert s["linear_velocity"][1][1] > 0, "sphere_bounce: restitution must reverse the approach"
     assert s["normal_impulse"][0] > 0
+    for nm in ("revolute_limited", "spherical_limited"):
+        t = vectors["scenes"][nm]["expected_f32"]["joint_torque"][0]
+        assert sum(abs(x) for x in t) > 1.0, f"{nm}: the limits must act"
     d = vectors["scenes"]["distance_pendulum"]["expected_f32"]
     assert abs(d["joint_force"][0][0]) > 1.0, "distance_pendulum: the joint must pull"
     (HERE / "vectors.json").write_text(json.dumps(vectors, indent=1))

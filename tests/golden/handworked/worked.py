@@ -121,6 +121,33 @@ def rotate_inverse_inertia(il, q):
     return np.array([B[0][0], B[1][0], B[2][0], B[1][1], B[2][1], B[2][2]], dtype=q.dtype)
 
 
+def mat3_mul_vec(M, v):   # glam Mat3 * Vec3: x_axis * v.x + y_axis * v.y + z_axis * v.z
+    return (M[0] * v[0] + M[1] * v[1]) + M[2] * v[2]
+
+
+def clamp_length_max(N, v, m):   # glam Vec3::clamp_length_max
+    l2 = dot(v, v)
+    return m * (v / N.sqrt(l2)) if l2 > m * m else v
+
+
+def angle_limit_correction(N, lo, hi, limit_axis, axis1, axis2, max_correction):
+    """AngleLimit::compute_correction, 3D (dynamics/joints/mod.rs:427-473); None when the limit holds"""
+    T = N.T
+    PI, TAU = T(math.pi), T(2 * math.pi)
+    phi = N.asin(dot(cross(axis1, axis2), limit_axis))
+    if dot(axis1, axis2) < 0:
+        phi = PI - phi
+    if phi > PI:
+        phi = phi - TAU
+    if phi < lo or phi > hi:
+        phi = min(max(phi, lo), hi)
+        half = phi * T(0.5)
+        s_, c_ = N.sin(half), N.cos(half)                  # Quat::from_axis_angle(limit_axis, phi)
+        rot = np.array([limit_axis[0] * s_, limit_axis[1] * s_, limit_axis[2] * s_, c_], dtype=T)
+        return clamp_length_max(N, cross(quat_rotate(rot, axis1), axis2), max_correction)
+    return None
+
+
 def recip_or_zero(x):   # math/mod.rs:248-268
     return (x.dtype.type(1) / x) if (x != 0 and np.isfinite(x)) else x.dtype.type(0)
 
@@ -363,8 +390,23 @@ def step(scene, dtype=np.float32):
                 axis = np.array(j.get("axis", [0, 0, 1]), dtype=T)
                 d["a1"] = quat_rotate(quat_mul(b1["rot"], basis1), axis)
                 d["a2"] = quat_rotate(quat_mul(b2["rot"], basis2), axis)
+                ortho = any_orthonormal_vector(N, axis)            # revolute.rs:86-89
+                d["b1"] = quat_rotate(quat_mul(b1["rot"], basis1), ortho)
+                d["b2"] = quat_rotate(quat_mul(b2["rot"], basis2), ortho)
             else:
                 d["rd"] = quat_mul(quat_mul(b1["rot"], basis1), quat_conj(quat_mul(b2["rot"], basis2)))
+        if j["type"] == SPHERICAL:                            # xpbd/joints/spherical.rs:45-82: through rotation MATRICES here
+            basis1 = np.array(j.get("local_basis1", [0, 0, 0, 1]), dtype=T)
+            basis2 = np.array(j.get("local_basis2", [0, 0, 0, 1]), dtype=T)
+            R1, R2 = mat3_from_quat(b1["rot"]), mat3_from_quat(b2["rot"])
+            d["r1"] = mat3_mul_vec(R1, la1 - b1["com"])
+            d["r2"] = mat3_mul_vec(R2, la2 - b2["com"])
+            twist = np.array(j.get("axis", [0, 1, 0]), dtype=T)
+            swing = any_orthonormal_vector(N, twist)
+            d["sw1"], d["sw2"] = mat3_mul_vec(R1, quat_rotate(basis1, swing)), mat3_mul_vec(R2, quat_rotate(basis2, swing))
+            d["tw1"], d["tw2"] = mat3_mul_vec(R1, quat_rotate(basis1, twist)), mat3_mul_vec(R2, quat_rotate(basis2, twist))
+            d["lam_b"] = N.v(0, 0, 0)
+        d.setdefault("lam_b", N.v(0, 0, 0))
         J.append(d)
 
     def joint_sides(j):
@@ -445,11 +487,44 @@ def step(scene, dtype=np.float32):
             imp = dl * dirn
             j["lam_p"] = j["lam_p"] + imp
             positional_impulse(b1, b2, in1, in2, imp, wr1, wr2)
-        elif j["type"] == SPHERICAL:                          # xpbd/joints/spherical.rs:84-110 without limits: the point constraint
+        elif j["type"] == SPHERICAL:                          # xpbd/joints/spherical.rs:84-207: point, swing limit, twist limit
+            c2 = T(j.get("compliance2", 0.0))
             point_constraint(j, b1, b2, in1, in2, c0)
-        elif j["type"] == REVOLUTE:                           # xpbd/joints/revolute.rs:92-141 without limits: align, then point
+            PI = T(math.pi)
+            if j.get("swing_limit") is not None:
+                a1, a2 = quat_rotate(b1["dq"], j["sw1"]), quat_rotate(b2["dq"], j["sw2"])
+                n = cross(a1, a2)
+                nm = length(N, n)
+                if nm > N.eps:
+                    n = n / nm
+                    corr = angle_limit_correction(N, T(j["swing_limit"][0]), T(j["swing_limit"][1]), n, a1, a2, PI)
+                    if corr is not None:
+                        j["lam_a"] = j["lam_a"] + align_orientation(j, b1, b2, in1, in2, corr, c1)
+            if j.get("twist_limit") is not None:
+                a1, a2 = quat_rotate(b1["dq"], j["sw1"]), quat_rotate(b2["dq"], j["sw2"])
+                n = a1 + a2
+                nm = length(N, n)
+                if nm > N.eps:
+                    tb1, tb2 = quat_rotate(b1["dq"], j["tw1"]), quat_rotate(b2["dq"], j["tw2"])
+                    n = n / nm
+                    n1 = tb1 - dot(n, tb1) * n
+                    n2 = tb2 - dot(n, tb2) * n
+                    m1, m2 = length(N, n1), length(N, n2)
+                    if not (m1 <= N.eps or m2 <= N.eps):
+                        n1, n2 = n1 / m1, n2 / m2
+                        max_corr = T(2) * PI if dot(a1, a2) > T(-0.5) else h
+                        corr = angle_limit_correction(N, T(j["twist_limit"][0]), T(j["twist_limit"][1]), n, n1, n2, max_corr)
+                        if corr is not None:
+                            j["lam_b"] = j["lam_b"] + align_orientation(j, b1, b2, in1, in2, corr, c2)
+        elif j["type"] == REVOLUTE:                           # xpbd/joints/revolute.rs:92-187: align, angle limit, then point
             a1, a2 = quat_rotate(b1["dq"], j["a1"]), quat_rotate(b2["dq"], j["a2"])
             j["lam_a"] = j["lam_a"] + align_orientation(j, b1, b2, in1, in2, cross(a1, a2), c1)
+            if j.get("angle_limit") is not None:
+                a1 = quat_rotate(b1["dq"], j["a1"])
+                lb1, lb2 = quat_rotate(b1["dq"], j["b1"]), quat_rotate(b2["dq"], j["b2"])
+                corr = angle_limit_correction(N, T(j["angle_limit"][0]), T(j["angle_limit"][1]), a1, lb1, lb2, T(math.pi))
+                if corr is not None:
+                    j["lam_b"] = j["lam_b"] + align_orientation(j, b1, b2, in1, in2, corr, T(j.get("compliance2", 0.0)))
             point_constraint(j, b1, b2, in1, in2, c0)
         elif j["type"] == FIXED:                              # xpbd/joints/fixed.rs:73-89, shared/fixed_angle_constraint.rs:59-96
             q = quat_mul(quat_mul(j["rd"], b1["dq"]), quat_conj(b2["dq"]))
@@ -507,6 +582,24 @@ def step(scene, dtype=np.float32):
                 if dr[3] < 0:
                     nw = -nw
                 b["w"] = b["w"] + nw
+            for jt in (FIXED, REVOLUTE, SPHERICAL, PRISMATIC, DISTANCE):   # joint_damping::<T> (solver/plugin.rs:759-806), same order
+                for j in J:
+                    if j["type"] != jt or j.get("damping") is None:
+                        continue
+                    i1, i2 = j["body1"], j["body2"]
+                    jb1, jb2 = body(i1), body(i2)
+                    dl, da = T(j["damping"][0]), T(j["damping"][1])
+                    d_omega = (jb2["w"] - jb1["w"]) * min(da * h, T(1))
+                    if jb1["kind"] != KINEMATIC:
+                        jb1["w"] = jb1["w"] + d_omega
+                    if jb2["kind"] != KINEMATIC:
+                        jb2["w"] = jb2["w"] - d_omega
+                    d_v = (jb2["v"] - jb1["v"]) * min(dl * h, T(1))
+                    w1, w2 = inertia_of(i1, False)[0], inertia_of(i2, False)[0]
+                    ws = w1 + w2
+                    pimp = d_v * np.array([recip_or_zero(ws[0]), recip_or_zero(ws[1]), recip_or_zero(ws[2])], dtype=T)
+                    jb1["v"] = jb1["v"] + pimp * w1
+                    jb2["v"] = jb2["v"] - pimp * w2
 
     for k in order:
         restitution(C[k])
@@ -529,7 +622,7 @@ def step(scene, dtype=np.float32):
     # Res<Time> in SolverSystems::Finalize is Time<Physics> again (solver/schedule.rs:211-212): delta_secs = dt, not h
     rhs = recip_or_zero(dt * dt) * T(substeps)
     out["joint_force"] = [[float(x) for x in j["lam_p"] * rhs] for j in J]
-    out["joint_torque"] = [[float(x) for x in j["lam_a"] * rhs] for j in J]
+    out["joint_torque"] = [[float(x) for x in (j["lam_a"] + j["lam_b"]) * rhs] for j in J]
     out["normal_impulse"], out["warm_start_normal_impulse"], out["warm_start_tangent_impulse"] = [], [], []
     for k, c in enumerate(C):
         for pi, p in enumerate(scene["manifolds"][k]["points"]):

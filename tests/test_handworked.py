@@ -64,12 +64,25 @@ def _build(sc, dtype):
                 continue
             n = len(js)
             g = lambda key, default, width: np.array([j.get(key, default) for _, j in js], dtype=s).reshape((n,) + ((width,) if width > 1 else ()))
+            def lim(key):   # (enabled, min, max) columns of an optional limit
+                en = np.array([j.get(key) is not None for _, j in js])
+                lo = np.array([(j.get(key) or [0.0, 0.0])[0] for _, j in js], dtype=s)
+                hi = np.array([(j.get(key) or [0.0, 0.0])[1] for _, j in js], dtype=s)
+                return en, lo, hi
+            if t == api.JOINT_DISTANCE:
+                en1, lo1, hi1 = np.zeros(n, dtype=bool), g("limit_min", 0.0, 1), g("limit_max", 0.0, 1)
+            else:
+                en1, lo1, hi1 = lim("angle_limit" if t == api.JOINT_REVOLUTE else "swing_limit")
+            en2, lo2, hi2 = lim("twist_limit")
+            damp = np.array([j.get("damping") is not None for _, j in js])
             joints.types[t] = api.Joints(
                 body1=np.array([j["body1"] for _, j in js], dtype=np.int32), body2=np.array([j["body2"] for _, j in js], dtype=np.int32),
                 local_anchor1=g("local_anchor1", None, 3), local_anchor2=g("local_anchor2", None, 3), local_basis1=g("local_basis1", [0, 0, 0, 1], 4),
                 local_basis2=g("local_basis2", [0, 0, 0, 1], 4), axis=g("axis", [[0, 0, 1], [0, 0, 1], [0, 1, 0], [1, 0, 0], [0, 0, 1]][t], 3),
-                limit_enabled=np.zeros(n, dtype=np.uint8), limit_min=g("limit_min", 0.0, 1), limit_max=g("limit_max", 0.0, 1),
+                limit_enabled=(en1.astype(np.uint8) | (en2.astype(np.uint8) << 1)), limit_min=lo1, limit_max=hi1, limit2_min=lo2, limit2_max=hi2,
                 compliance0=g("compliance0", 0.0, 1), compliance1=g("compliance1", 0.0, 1), compliance2=g("compliance2", 0.0, 1),
+                damping_enabled=damp.astype(np.uint8), damping_linear=np.array([(j.get("damping") or [0.0, 0.0])[0] for _, j in js], dtype=s),
+                damping_angular=np.array([(j.get("damping") or [0.0, 0.0])[1] for _, j in js], dtype=s),
                 force=np.zeros((n, 3), dtype=s), torque=np.zeros((n, 3), dtype=s))
             where += [(k, t, i) for i, (k, _) in enumerate(js)]
     return prm, bodies, man, joints, where
