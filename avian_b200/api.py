@@ -671,7 +671,7 @@ class Context:
                                                        count.ctypes.data, disjoint.ctypes.data))
         return count, disjoint
 
-    def solver_step_graph(self, params, bodies: Bodies, graph: dict, joints: JointSet | None = None) -> None:
+    def solver_step_graph(self, params, bodies: Bodies, graph: dict, joints: JointSet | None = None, reuse_graph: bool = False) -> None:
         """avn_solver_upload_graph + run + download: the manifolds come from the resident rows, graph = dict(color_offsets, edge, body1, body2,
         friction, restitution)."""
         b = bodies.as_struct()
@@ -683,7 +683,8 @@ class Context:
         keep = [np.ascontiguousarray(graph["edge"], dtype=np.uint32), np.ascontiguousarray(graph["body1"], dtype=np.int32),
                 np.ascontiguousarray(graph["body2"], dtype=np.int32), np.ascontiguousarray(graph["friction"], dtype=self.scalar),
                 np.ascontiguousarray(graph["restitution"], dtype=self.scalar)]
-        em.edge, em.body1, em.body2, em.friction, em.restitution = (x.ctypes.data for x in keep)
+        if not reuse_graph:     # reuse: edge stays NULL = "the list of the previous call is still resident"
+            em.edge, em.body1, em.body2, em.friction, em.restitution = (x.ctypes.data for x in keep)
         self._keep = (params, bodies, graph, joints, b, em, j, keep)
         self._check(self.lib.avn_solver_upload_graph(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
         self._check(self.lib.avn_solver_run(self.handle))

@@ -329,12 +329,13 @@ constexpr int SW_SUB = 4096;
 template <class S, bool EMIT>
 __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_constant__ Sweep<S> s, const int* __restrict__ wide_list,
                                                                 const int* __restrict__ wide_count, uint32_t* __restrict__ sub_counts, int nsub,
-                                                                const uint64_t* __restrict__ offsets, uint2* __restrict__ pairs) {
+                                                                const uint64_t* __restrict__ offsets, uint2* __restrict__ pairs, uint64_t capacity) {
     __shared__ uint32_t s_warp_cnt[SW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nw = min(*wide_count, SW_WIDE_CAP);
     for (int w = blockIdx.y; w < nw; w += gridDim.y) {
         const int i = wide_list[w], e = s.end[i];
+        if (EMIT && offsets[i + 1] == offsets[i]) continue;   // block-uniform: the count pass found nothing for this interval
         const int sub = blockIdx.x;
         const int jb = i + 1 + sub * SW_SUB, je = min(e, jb + SW_SUB);
         if (jb >= e) { if (!EMIT && threadIdx.x == 0) sub_counts[w * nsub + sub] = 0; continue; }
@@ -363,7 +364,10 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_wide_kernel(const __grid_con
                 if (k < warp) before += c;
                 round_total += c;
             }
-            if (EMIT && ok) pairs[running + before + __popc(bal & ((1u << lane) - 1u))] = make_uint2(uint32_t(i), uint32_t(j));
+            if (EMIT && ok) {
+                const uint64_t at = running + before + __popc(bal & ((1u << lane) - 1u));
+                if (at < capacity) pairs[at] = make_uint2(uint32_t(i), uint32_t(j));
+            }
             running += round_total;
             total += round_total;
             __syncthreads();
@@ -496,6 +500,7 @@ class Broadphase final : public BroadphaseBase {
     CellSweep<S> cell_desc() const {
         CellSweep<S> cs;
         cs.grid = grid_.as<CellGrid<S>>(); cs.cranks = cv0_.as<uint32_t>(); cs.cstart = cbounds_.as<int>(); cs.cend = cbounds_.as<int>() + 0x10000;
+        cs.capacity = pair_capacity_;
         return cs;
     }
     AvnStatus ensure_buffers(int n);
@@ -619,6 +624,10 @@ AvnStatus Broadphase<S>::ensure_buffers(int n) {
     AVN_CUDA(wide_sub_.ensure(size_t(nsub) * size_t(std::min(n, SW_WIDE_CAP)) * 4));
     AVN_CUDA(block_sums_.ensure(size_t((n + 1023) / 1024) * 8));
     AVN_CUDA(nf_flag_.ensure(8));
+    pair_capacity_ = std::max<uint64_t>(pair_capacity_, uint64_t(4) * uint64_t(n) + 1024);
+    AVN_CUDA(o_c1_.ensure(pair_capacity_ * 4)); AVN_CUDA(o_c2_.ensure(pair_capacity_ * 4)); AVN_CUDA(o_b1_.ensure(pair_capacity_ * 4)); AVN_CUDA(o_b2_.ensure(pair_capacity_ * 4));
+    AVN_CUDA(o_fl_.ensure(pair_capacity_));
+    AVN_CUDA(pairs_.ensure(pair_capacity_ * sizeof(uint2)));
     return AVN_OK;
 }
 
@@ -632,6 +641,7 @@ typename Broadphase<S>::GraphKey Broadphase<S>::graph_key() const {
     memcpy(k.p, ptrs, sizeof ptrs);
     // the remaining buffers are allocated together with the ones above (same n): their addresses change only when those do
     k.m[0] = existing_mask_ ^ (uint64_t(uintptr_t(cv0_.p)) << 1) ^ (uint64_t(uintptr_t(wide_sub_.p)) << 2);
+    k.m[0] ^= (pair_capacity_ * 0x9e3779b97f4a7c15ull) ^ (uint64_t(uintptr_t(pairs_.p)) << 3) ^ (uint64_t(uintptr_t(o_c1_.p)) << 4) ^ (uint64_t(uintptr_t(o_fl_.p)) << 5);
     k.m[1] = jdis_mask_ ^ (uint64_t(uintptr_t(cbounds_.p)) << 1) ^ (uint64_t(uintptr_t(block_sums_.p)) << 2) ^ (uint64_t(uintptr_t(wide_flag_.p)) << 3);
     return k;
 }
@@ -700,7 +710,7 @@ void Broadphase<S>::enqueue_front(int n) {
     sweep_cells_kernel<S, false><<<grid, 256, 0, stream_>>>(sw, cs, counts_.as<uint32_t>(), nullptr, nullptr);
     // intervals with a huge x-window: brute force, one block per SW_SUB candidates; the grid's y dimension strides the wide list
     const int nsub = (n + SW_SUB - 1) / SW_SUB;
-    sweep_wide_kernel<S, false><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr);
+    sweep_wide_kernel<S, false><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, nullptr, nullptr, 0);
     wide_finish<<<1, 256, 0, stream_>>>(wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub, counts_.as<uint32_t>());
     launches += nblocks <= RS_FUSE_MAX_BLOCKS ? 15 : 17;
     const int sblocks = (n + 1023) / 1024;
@@ -708,7 +718,20 @@ void Broadphase<S>::enqueue_front(int n) {
     scan_block_offsets<<<1, 1024, 0, stream_>>>(block_sums_.as<uint64_t>(), sblocks, offsets_.as<uint64_t>() + n);
     scan_apply<<<sblocks, 1024, 0, stream_>>>(counts_.as<uint32_t>(), n, block_sums_.as<uint64_t>(), offsets_.as<uint64_t>());
     launches += 3;
-    // the pair count decides the size of the output buffers: one 16-byte readback (count + non-finite flag)
+    // emit pass straight after the count pass, into buffers of pair_capacity_ entries (grown by download() when the count says so): the count
+    // never visits the host in between, so a run is ONE graph launch with no synchronisation
+    {
+        uint2* pairs = pairs_.as<uint2>();
+        sweep_cells_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, cs, nullptr, offsets_.as<uint64_t>(), pairs);
+        sweep_wide_kernel<S, true><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
+                                                                                      offsets_.as<uint64_t>(), pairs, pair_capacity_);
+        segment_sort<<<(n + 255) / 256, 256, 0, stream_>>>(offsets_.as<uint64_t>(), wide_flag_.as<uint8_t>(), n, pairs, pair_capacity_);
+        const unsigned mblocks = unsigned(std::min<uint64_t>((pair_capacity_ + 255) / 256, uint64_t(sm_count_) * 16));
+        materialize_pairs<S><<<mblocks, 256, 0, stream_>>>(sw, pairs, offsets_.as<uint64_t>() + n, pair_capacity_, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
+                                                           o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
+        launches += 4;
+    }
+    // count + non-finite flag for download(): one 16-byte readback, not waited for here
     cudaMemcpyAsync(h_total_, offsets_.as<uint64_t>() + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_);
     cudaMemcpyAsync(h_total_ + 1, nf_flag_.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_);
     front_launches_ = launches;
@@ -751,29 +774,6 @@ AvnStatus Broadphase<S>::run() {
             enqueue_front(n);
         }
         launches_ += front_launches_;
-        AVN_CUDA(cudaStreamSynchronize(stream_));
-        if (h_total_[1] != 0) return drop_nonfinite();
-        const Sweep<S> sw = sweep_desc();
-        const CellSweep<S> cs = cell_desc();
-        const int grid = std::min((n + (256 / CG_GROUP) - 1) / (256 / CG_GROUP), sm_count_ * 32);
-        const int nsub = (n + SW_SUB - 1) / SW_SUB;
-        int* wide_count = wide_.as<int>();
-        int* wide_list = wide_.as<int>() + 1;
-        const uint64_t total = *h_total_;
-        pair_capacity_ = total;
-        if (total > 0) {
-            AVN_CUDA(o_c1_.ensure(total * 4)); AVN_CUDA(o_c2_.ensure(total * 4)); AVN_CUDA(o_b1_.ensure(total * 4)); AVN_CUDA(o_b2_.ensure(total * 4));
-            AVN_CUDA(o_fl_.ensure(total));
-            AVN_CUDA(pairs_.ensure(total * sizeof(uint2)));
-            uint2* pairs = pairs_.as<uint2>();
-            sweep_cells_kernel<S, true><<<grid, 256, 0, stream_>>>(sw, cs, nullptr, offsets_.as<uint64_t>(), pairs);
-            sweep_wide_kernel<S, true><<<dim3(nsub, WIDE_ROWS), SW_THREADS, 0, stream_>>>(sw, wide_list, wide_count, wide_sub_.as<uint32_t>(), nsub,
-                                                                                          offsets_.as<uint64_t>(), pairs);
-            segment_sort<<<(n + 255) / 256, 256, 0, stream_>>>(offsets_.as<uint64_t>(), wide_flag_.as<uint8_t>(), n, pairs);
-            materialize_pairs<S><<<unsigned((total + 255) / 256), 256, 0, stream_>>>(sw, pairs, total, total, o_c1_.as<uint32_t>(), o_c2_.as<uint32_t>(),
-                                                                                  o_b1_.as<uint32_t>(), o_b2_.as<uint32_t>(), o_fl_.as<uint8_t>());
-            launches_ += 4;
-        }
     }
     cudaEventRecord(ev1_, stream_);
     AVN_CUDA(cudaGetLastError());
@@ -833,6 +833,24 @@ template <class S>
 AvnStatus Broadphase<S>::download(AvnPairList* out) {
     if (!ran_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_broadphase_download before avn_broadphase_run");
     if (!out) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "out_pairs is required");
+    // the run left its pair count and the non-finite flag in pinned memory; this is where the host first looks at them
+    AVN_CUDA(cudaStreamSynchronize(stream_));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (h_total_[1] != 0) {                       // a NaN / infinite AABB: drop those intervals and run again (drop_nonfinite reruns)
+            AvnStatus st = drop_nonfinite();
+            if (st != AVN_OK) return st;
+            AVN_CUDA(cudaStreamSynchronize(stream_));
+            continue;
+        }
+        if (h_total_[0] > pair_capacity_) {           // more pairs than the emit buffers held: grow them and run again
+            pair_capacity_ = h_total_[0] + h_total_[0] / 4 + 1024;
+            AvnStatus st = run();
+            if (st != AVN_OK) return st;
+            AVN_CUDA(cudaStreamSynchronize(stream_));
+            continue;
+        }
+        break;
+    }
     const uint64_t total = *h_total_;
     out->count = total;
     const uint64_t ncopy = std::min<uint64_t>(total, out->capacity);

@@ -184,6 +184,7 @@ struct CellSweep {
     const CellGrid<S>* grid;
     const uint32_t* cranks;   // ranks grouped by cell, ascending inside a cell
     const int* cstart; const int* cend;   // [0x10000]
+    uint64_t capacity;        // entries of the pair buffer the emit pass may write (the count pass runs first; a larger total re-runs)
 };
 
 // CG_GROUP lanes per interval i.  The lanes stride over the cells of i's query range (+ one lane-strided pass over the large list);
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
     for (long long i64 = (long long)blockIdx.x * (blockDim.x / CG_GROUP) + threadIdx.x / CG_GROUP; i64 < s.n; i64 += groups) {
         const int i = int(i64);
         if (s.is_wide[i]) continue;   // group-uniform
+        if (EMIT && offsets[i + 1] == offsets[i]) continue;   // the count pass found nothing for this interval (the usual case in steady state)
         const int e = s.end[i];
         uint32_t mine = 0;            // hits found by this lane
         uint64_t base = 0;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
                         if ((yi.x > yj.y || yi.y < yj.x) || (yi.z > yj.w || yi.w < yj.z)) continue;
                         uint32_t pf; uint4 mj;
                         if (!pair_filters(s, mi, fi, j, pf, mj)) continue;
-                        if (EMIT && pass == 1) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
+                        if (EMIT && pass == 1 && base + wr < cs.capacity) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
                         ++wr;
                     }
                 } else {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
                         if ((yi.x > yj.y || yi.y < yj.x) || (yi.z > yj.w || yi.w < yj.z)) continue;
                         uint32_t pf; uint4 mj;
                         if (!pair_filters(s, mi, fi, j, pf, mj)) continue;
-                        if (EMIT && pass == 1) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
+                        if (EMIT && pass == 1 && base + wr < cs.capacity) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
                         ++wr;
                     }
                 }
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
                             if ((yi.x > yj.y || yi.y < yj.x) || (yi.z > yj.w || yi.w < yj.z)) continue;
                             uint32_t pf; uint4 mj;
                             if (!pair_filters(s, mi, fi, j, pf, mj)) continue;
-                            if (EMIT && pass == 1) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
+                            if (EMIT && pass == 1 && base + wr < cs.capacity) pairs[base + wr] = make_uint2(uint32_t(i), uint32_t(j));
                             ++wr;
                         }
                     }
@@ -280,10 +282,11 @@ __global__ void __launch_bounds__(256) sweep_cells_kernel(const __grid_constant_
 }
 
 // sort every non-wide interval's segment of the pair buffer by rank j (insertion sort: segments are a few entries long)
-__global__ void segment_sort(const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ is_wide, int n, uint2* __restrict__ pairs) {
+__global__ void segment_sort(const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ is_wide, int n, uint2* __restrict__ pairs, uint64_t capacity) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || is_wide[i]) return;
     const uint64_t b = offsets[i], e = offsets[i + 1];
+    if (e > capacity || e - b < 2) return;   // (too small a buffer: the host grows it and runs again) / nothing to sort
     for (uint64_t p = b + 1; p < e; ++p) {
         uint2 v = pairs[p];
         uint64_t q = p;
@@ -294,17 +297,19 @@ __global__ void segment_sort(const uint64_t* __restrict__ offsets, const uint8_t
 
 // (rank i, rank j) -> the ABI columns of the emitted pair (broad_phase.rs:443-468)
 template <class S>
-__global__ void materialize_pairs(const __grid_constant__ Sweep<S> s, const uint2* __restrict__ pairs, uint64_t total, uint64_t capacity,
+__global__ void materialize_pairs(const __grid_constant__ Sweep<S> s, const uint2* __restrict__ pairs, const uint64_t* __restrict__ total_ptr, uint64_t capacity,
                                   uint32_t* __restrict__ out_c1, uint32_t* __restrict__ out_c2, uint32_t* __restrict__ out_b1,
                                   uint32_t* __restrict__ out_b2, uint8_t* __restrict__ out_flags) {
-    uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if (p >= total || p >= capacity) return;
+    const uint64_t total = *total_ptr;   // the count pass's result, still on the device: no host round trip between count and emit
+    if (total > capacity) return;
+    for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < total; p += uint64_t(gridDim.x) * blockDim.x) {
     const uint2 ij = pairs[p];
     const uint4 mi = s.meta[ij.x], mj = s.meta[ij.y];
     const uint32_t u = uint32_t(s.flags[ij.x]) | uint32_t(s.flags[ij.y]);
     out_c1[p] = mi.x; out_c2[p] = mj.x; out_b1[p] = mi.y; out_b2[p] = mj.y;
     out_flags[p] = uint8_t(((u & AVN_AABB_CONTACT_EVENTS) ? AVN_PAIR_CONTACT_EVENTS : 0u) | ((u & AVN_AABB_MODIFY_CONTACTS) ? AVN_PAIR_MODIFY_CONTACTS : 0u) |
                            ((u & AVN_AABB_GENERATE_CONSTRAINTS) ? AVN_PAIR_GENERATE_CONSTRAINTS : 0u) | ((u & AVN_AABB_CUSTOM_FILTER) ? AVN_PAIR_NEEDS_HOOK : 0u));
+    }
 }
 
 }  // namespace

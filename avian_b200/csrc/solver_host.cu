@@ -133,6 +133,8 @@ class Solver final : public SolverBase {
     // blocks per SM of a step: the f32 wavefront routines fit 128 registers without spills (the delta records die before the main loop), so a
     // wavefront-scheduled f32 step runs 4 blocks = 16 warps per SM (1.618 -> 1.562 ms at 100k cubes); the barrier schedule keeps the
     // measured best of round 1 (3 for f32, 2 for f64).  AVN_MEGA_BPS overrides both.
+    // dynamic shared memory of the persistent kernel: the per-thread cp.async tile of the contact routines
+    static size_t mega_smem_bytes(int maxp) { return stage_bytes<S>(MEGA_BLOCK, maxp); }
     int bps_for(bool wave_candidate) const { return bps_forced_ ? mega_bps_ : ((sizeof(S) == 4 && wave_candidate) ? 4 : mega_bps_); }
     bool select_megakernel(int max_points, int bps = 0) {
         const int maxp = max_points <= 1 ? 1 : AVN_MAX_MANIFOLD_POINTS;
@@ -141,7 +143,7 @@ class Solver final : public SolverBase {
         mega_maxp_ = maxp;
         mega_sel_bps_ = bps;
         mega_fn_ = maxp == 1 ? mega_variant<1>(bps) : mega_variant<AVN_MAX_MANIFOLD_POINTS>(bps);
-        const size_t smem = stage_bytes<S>(MEGA_BLOCK, maxp);
+        const size_t smem = mega_smem_bytes(maxp);
         int per_sm = 0;
         mega_grid_ = 0;
         if (cudaFuncSetAttribute(mega_fn_, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) == cudaSuccess &&
@@ -179,10 +181,13 @@ class Solver final : public SolverBase {
         // device == true: the edge-indexed columns above (point counts, normal, point columns, impulse inputs) are DEVICE pointers owned by the
         // contact store, and store_contact_impulses writes to out_* (device) instead of buffers of this solver; nothing of them is copied
         bool device = false;
+        bool reuse_graph = false;   // upload_graph: the colour-major list (edge, body1, body2, friction, restitution) of the previous upload is still valid
         void* out_ws_normal = nullptr; void* out_ws_tangent = nullptr; void* out_normal_impulse = nullptr;
     };
     AvnStatus upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* src, AvnJointSet* js);
     ManifoldSource hm_{};
+    bool graph_on_device_ = false, graph_restitution_ = false;   // avn_solver_upload_graph: the resident colour-major list
+    uint32_t graph_count_ = 0, graph_color_offsets_[AVN_GRAPH_COLOR_COUNT + 1] = {};
     DevBuf m_edge_, m_pbegin_, m_pend_, e_cnt_;
     AvnJointSet hj_{};
     bool have_m_ = false, have_j_ = false;
@@ -223,6 +228,7 @@ AvnStatus Solver<S>::upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnMan
     if (!mc->body1 || !mc->body2 || !mc->normal || !mc->friction || !mc->restitution || !mc->point_offsets || !mc->anchor1 || !mc->anchor2 ||
         !mc->penetration || !mc->normal_speed || !mc->warm_start_normal_impulse || !mc->warm_start_tangent_impulse || !mc->normal_impulse)
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: every column except tangent_velocity is required");
+    graph_on_device_ = false;
     ManifoldSource src;
     src.M = mc->count; src.P = mc->point_count; src.normal_rows = mc->count;
     src.color_offsets = mc->color_offsets; src.body1 = mc->body1; src.body2 = mc->body2; src.friction = mc->friction; src.restitution = mc->restitution;
@@ -240,6 +246,7 @@ AvnStatus Solver<S>::upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, 
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: every column is required");
     for (size_t m = 0; m < em->count; ++m)
         if (em->edge[m] >= em->edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "edge manifolds: edge[%zu] = %u >= edge_capacity %u", m, em->edge[m], em->edge_capacity);
+    graph_on_device_ = false;
     ManifoldSource src;
     src.M = em->count; src.P = size_t(4) * em->edge_capacity; src.normal_rows = em->edge_capacity;
     src.color_offsets = em->color_offsets; src.body1 = em->body1; src.body2 = em->body2; src.friction = em->friction; src.restitution = em->restitution;
@@ -253,23 +260,39 @@ template <class S>
 AvnStatus Solver<S>::upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* g, ContactsBase* contacts, AvnJointSet* js) {
     if (!g || g->count == 0) return upload_impl(prm, bc, nullptr, js);
     if (!contacts) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "upload_graph: no contact store");
-    if (!g->edge || !g->body1 || !g->body2 || !g->friction || !g->restitution)
+    // edge == NULL: "the graph has not changed since the last avn_solver_upload_graph" — the list stays on the device, only count and
+    // color_offsets are read (they must equal the previous upload's)
+    const bool reuse = g->edge == nullptr;
+    if (reuse) {
+        if (!graph_on_device_ || g->count != graph_count_ || memcmp(g->color_offsets, graph_color_offsets_, sizeof graph_color_offsets_) != 0)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge == NULL asks to reuse the previous graph, but none with %u manifolds and these colour offsets is resident", g->count);
+    } else if (!g->body1 || !g->body2 || !g->friction || !g->restitution) {
         return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge, body1, body2, friction and restitution are required");
+    }
     AvnEdgeManifolds v{};
     AvnStatus st = contacts->view(&v);
     if (st != AVN_OK) return st;
-    for (size_t m = 0; m < g->count; ++m)
-        if (g->edge[m] >= v.edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge[%zu] = %u >= capacity %u", m, g->edge[m], v.edge_capacity);
+    if (!reuse)
+        for (size_t m = 0; m < g->count; ++m)
+            if (g->edge[m] >= v.edge_capacity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "graph: edge[%zu] = %u >= capacity %u", m, g->edge[m], v.edge_capacity);
     ManifoldSource src;
     src.M = g->count; src.P = size_t(4) * v.edge_capacity; src.normal_rows = v.edge_capacity;
     src.color_offsets = g->color_offsets; src.body1 = g->body1; src.body2 = g->body2; src.friction = g->friction; src.restitution = g->restitution;
     src.edge = g->edge;
     src.device = true;
+    src.reuse_graph = reuse;
     src.normal = v.normal; src.edge_point_count = v.point_count;
     src.anchor1 = v.anchor1; src.anchor2 = v.anchor2; src.penetration = v.penetration; src.normal_speed = v.normal_speed;
     src.ws_normal = v.warm_start_normal_impulse; src.ws_tangent = v.warm_start_tangent_impulse; src.normal_impulse = v.normal_impulse;
     contacts->outputs(&src.out_ws_normal, &src.out_ws_tangent, &src.out_normal_impulse);
-    return upload_impl(prm, bc, &src, js);
+    graph_on_device_ = false;
+    st = upload_impl(prm, bc, &src, js);
+    if (st == AVN_OK) {
+        graph_on_device_ = true;
+        graph_count_ = g->count;
+        memcpy(graph_color_offsets_, g->color_offsets, sizeof graph_color_offsets_);
+    }
+    return st;
 }
 
 // fills the point ranges of the manifolds of an edge-indexed upload: 4 slots per edge, the first point_count[edge] of them live
@@ -384,7 +407,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
                 return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: at most %d points per manifold, point ranges must not decrease", AVN_MAX_MANIFOLD_POINTS);
             max_np_ = int(std::max<uint32_t>(widest, 1));
         }
-        {   // body indices are gathered through on the device (inr[2*b], vel[2*b], ver[b] ...): anything outside [AVN_NO_BODY, B) would read and
+        if (!mc->reuse_graph) {   // body indices are gathered through on the device (inr[2*b], vel[2*b], ver[b] ...): anything outside [AVN_NO_BODY, B) would read and
             // write out of bounds, so it is rejected here (streaming pass over two int columns)
             const int32_t* hb1 = mc->body1; const int32_t* hb2 = mc->body2;
             const int64_t Bi = int64_t(B);
@@ -410,11 +433,15 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             d.color_off[AVN_GRAPH_COLOR_COUNT] = slot;
             d.Mpad = std::max(slot, 32);
         }
-        UP(m_b1_, mc->body1, M, int, m_body1);
-        UP(m_b2_, mc->body2, M, int, m_body2);
+        if (mc->reuse_graph) {   // the list of the previous avn_solver_upload_graph is still in these buffers
+            d.m_body1 = m_b1_.as<int>(); d.m_body2 = m_b2_.as<int>(); d.m_friction = m_f_.as<S>(); d.m_restitution = m_r_.as<S>();
+        } else {
+            UP(m_b1_, mc->body1, M, int, m_body1);
+            UP(m_b2_, mc->body2, M, int, m_body2);
+            UP(m_f_, mc->friction, M, S, m_friction);
+            UP(m_r_, mc->restitution, M, S, m_restitution);
+        }
         if (mc->device) d.m_normal = static_cast<const S*>(mc->normal); else UP(m_n_, mc->normal, 3 * mc->normal_rows, S, m_normal);
-        UP(m_f_, mc->friction, M, S, m_friction);
-        UP(m_r_, mc->restitution, M, S, m_restitution);
         UP(m_tv_, mc->tangent_velocity, 3 * M, S, m_tanvel);
         if (mc->point_offsets) {
             UP(m_po_, mc->point_offsets, M + 1, uint32_t, m_point_begin);
@@ -422,7 +449,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             d.m_src = nullptr;
         } else {
             const uint8_t* d_count = nullptr;
-            UP(m_edge_, mc->edge, M, uint32_t, m_src);
+            if (mc->reuse_graph) d.m_src = m_edge_.as<uint32_t>(); else UP(m_edge_, mc->edge, M, uint32_t, m_src);
             if (mc->device) d_count = mc->edge_point_count;
             else if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
             AVN_CUDA(m_pbegin_.ensure(M * sizeof(uint32_t)));
@@ -462,10 +489,13 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         }
 
         hm_ = *mc;
-        host_any_restitution_ = false;
-        {
+        if (mc->reuse_graph) {
+            host_any_restitution_ = graph_restitution_;
+        } else {
+            host_any_restitution_ = false;
             const S* r = static_cast<const S*>(mc->restitution);
             for (size_t i = 0; i < mc->M; ++i) host_any_restitution_ |= (r[i] != S(0));
+            graph_restitution_ = host_any_restitution_;
         }
     }
     {
@@ -592,7 +622,7 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
     const DevSolver<S>& d = dev_;
     if (mega) {
         void* args[] = {(void*)&dev_};
-        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, stage_bytes<S>(MEGA_BLOCK, mega_maxp_), stream_);
+        cudaError_t e = cudaLaunchCooperativeKernel(mega_fn_, dim3(mega_grid_), dim3(MEGA_BLOCK), args, mega_smem_bytes(mega_maxp_), stream_);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
             if (!prepare && dev_.wave)

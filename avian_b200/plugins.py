@@ -271,6 +271,8 @@ class DeviceResidentWorld(World):
         self.capacity = 0
         self.known = {}          # ContactId -> pair key of the row on the device
         self.bytes_to_host = self.bytes_to_device = 0
+        self._steady = None      # step_steady's memory: which rows were touching, which ids are live
+        self._colliders = None
 
     def narrow_phase(self):
         p, b, s = self.pipeline, self.bodies, self.scalar
@@ -305,3 +307,55 @@ class DeviceResidentWorld(World):
 
     def solve(self) -> None:
         self.ctx.solver_step_graph(self.params, self.bodies, self.graph, self.joints)
+
+    # ---- the steady-state step, incremental on the host: what an application pays per frame once the contact set has settled ------------
+    def step_steady(self, aabbs: api.Aabbs, pairs_out: api.PairList) -> bool:
+        """One whole step from HOST body columns through the resident protocol: avn_broadphase (host AABB columns in, new pairs out) ->
+        avn_contacts_narrow_phase (collider poses + velocities in, one point count and one disjoint flag per contact row out) ->
+        avn_solver_upload_graph + run + download (body columns in and out).  The host touches its graphs only when the device reports that
+        a pair appeared, separated, or started / stopped touching; otherwise the colour-major edge list of the previous step is still valid and
+        stays on the device.  Returns True when the fast path was taken."""
+        ctx, p, b, s = self.ctx, self.pipeline, self.bodies, self.scalar
+        ctx.broadphase_upload(aabbs)
+        ctx.broadphase_run()
+        ctx.broadphase_download(pairs_out)
+        if pairs_out.count or self._steady is None:
+            # contact-graph changes: the general path (edge deltas, graph update, new edge list)
+            if pairs_out.count:
+                p.commit_broadphase(aabbs, pairs_out.trimmed())
+            self.aabb_min, self.aabb_max = self._aabb_rows(aabbs)
+            self.narrow_phase()
+            self._steady = {"touching": self.last_counts > 0, "ids": p.active_edges()[0]}
+            self.solve()
+            return False
+        colliders = self._colliders
+        colliders["position"], colliders["rotation"] = b.position, b.rotation
+        count, disjoint = ctx.contacts_narrow_phase(self.params.dt, 0.005, colliders, b.linear_velocity, b.angular_velocity, self.capacity,
+                                                    bool(self.params.match_contacts))
+        touching = count > 0
+        reuse = not disjoint.any() and np.array_equal(touching, self._steady["touching"])
+        if not reuse:
+            ids = self._steady["ids"]
+            m, _ = p.apply_counts(b, ids, count[ids], disjoint[ids])
+            co, edge, eb1, eb2, fr, re = p.export_edges(m)
+            self.graph = {"color_offsets": co, "edge": edge, "body1": eb1, "body2": eb2, "friction": fr.astype(s), "restitution": re.astype(s)}
+            self._steady = None if disjoint.any() else {"touching": touching, "ids": ids}   # a separated pair changes the id set: general path next
+        self.last_counts = count
+        ctx.solver_step_graph(self.params, b, self.graph, self.joints, reuse_graph=reuse)
+        return reuse
+
+    def prepare_steady(self, aabbs: api.Aabbs) -> None:
+        """After the settle steps: freeze what does not change per step (shapes, the AABB columns of the broad-phase input in body order)."""
+        s = self.scalar
+        self.aabb_min, self.aabb_max = self._aabb_rows(aabbs)
+        self._colliders = {"shape": self.scene.shape_type.astype(np.uint8), "dims": np.asarray(self.scene.dims, dtype=s), "position": self.bodies.position,
+                           "rotation": self.bodies.rotation, "aabb_min": self.aabb_min, "aabb_max": self.aabb_max}
+        self._steady = None
+
+    @staticmethod
+    def _aabb_rows(aabbs: api.Aabbs):
+        """the interval columns (persistent order) back in collider order (collider index == row of the body columns in this fixture)"""
+        n = int(aabbs.collider.shape[0])
+        mn, mx = np.empty_like(aabbs.aabb_min), np.empty_like(aabbs.aabb_max)
+        mn[aabbs.collider], mx[aabbs.collider] = aabbs.aabb_min, aabbs.aabb_max
+        return mn, mx

@@ -6,8 +6,12 @@ sweep-and-prune broad phase over the 100 001 collider AABBs + the whole solver s
 biased solve, integrate positions, relax], restitution, writeback, store impulses) over the snapshot's bodies and contact manifolds.
 The narrow phase is NOT in the step (outside the hot path); its manifolds are part of the snapshot, identical for every arm.
 
-  e2e          THE HEADLINE: steps/s through the public C-ABI calls avn_broadphase + avn_solver_step with pinned HOST buffers — H2D of every
-               column and D2H of the results inside the timed region (wall clock around K steps, barrier + synchronize on both sides).
+  e2e          THE HEADLINE: steps/s from pinned HOST body / AABB columns to HOST results through the public C-ABI calls of the device-resident
+               pipeline: avn_broadphase -> avn_contacts_narrow_phase (contact rows, manifolds and warm-start impulses live on
+               the device) -> avn_solver_upload_graph + run + download; every step uploads the body and collider columns and reads back the new
+               pairs, one point count + one flag per contact row and the bodies (wall clock around K steps, barrier + synchronize on both
+               sides).  It does MORE than the CPU arm's step (the narrow phase is inside).  `e2e.host_manifolds` is round 1's arm: the manifolds
+               computed by a host narrow phase outside the step and uploaded as columns through avn_solver_step (80 MB up / 24 MB down).
   value        steps/s with the snapshot resident in HBM: K x (avn_broadphase_run + avn_solver_run) back to back, timed as ONE span by two
                CUDA events on the library's stream (host launch gaps included, no copies), max over ranks; N > 1 = N independent piles
                (island sharding of independent scenes, no collective), value = N * K / T.
@@ -254,6 +258,9 @@ def run_gpu(args, info):
     gpu_out = (bodies.copy(), man.copy(), gpu_pairs, None if aabbs.order_out is None else aabbs.order_out.copy())
     restore()
 
+    # ---- end-to-end arm of the device-resident pipeline: its own context and world (the contact rows must have lived through the settle steps)
+    resident = e2e_resident(args, info, barrier) if not args.no_resident else None
+
     # max over ranks
     span_ms, wall_res_ms, wall_e2e_ms, mega_ms, bp_ms = parallel.reduce_max([span_ms, wall_resident * 1e3, wall_e2e * 1e3, mega_ms, bp_ms], info, device="cuda")
     # the pinned columns die with the context: what the CPU arm still needs moves to ordinary memory first
@@ -310,12 +317,20 @@ def run_gpu(args, info):
         pass_gbs = alg["solve_pass"] / (solver_pass["ms_per_pass"] / 1e3) / 1e9
         roof["solver_pass"] = {"kernel": "phase_kernel<OP_SOLVE_BIAS> x active colours (one solver-iteration pass, one launch per colour)",
                                "ms_per_pass": solver_pass["ms_per_pass"], "achieved": pass_gbs, "frac": pass_gbs / peak, "how": solver_pass["how"]}
+    host_arm = {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e_ms / K,
+                "last_step_device_ms": e2e_break, "what": "avn_broadphase + avn_solver_step with the manifold columns of a host narrow phase uploaded every step"}
+    if resident is not None and "error" not in resident:
+        e2e_block = {"value": world * K / (resident["wall_ms"] / 1e3), "unit": "steps/s", "h2d_bytes_per_step": resident["h2d"], "d2h_bytes_per_step": resident["d2h"],
+                     "ms_per_step": resident["wall_ms"] / K, "pipeline": resident["what"], "fast_path_share": resident["fast_share"], "host_manifolds": host_arm}
+    else:
+        e2e_block = dict(host_arm)
+        if resident is not None:
+            e2e_block["resident_error"] = resident["error"]
     result = {
         "metric": metric_name(args.scene), "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": span_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": sname, "data": "synthetic", "config": cfg,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e_ms / K,
-                "last_step_device_ms": e2e_break},
+        "e2e": e2e_block,
         "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks, "roofline": roof,
         "breakdown_ms": {"broad_phase": bp_ms, "solver_stage": mega_ms, "resident_span": span_ms / K, "resident_wall": wall_res_ms / K,
                          "kernel_launches_per_step": launches_per_step},
@@ -327,6 +342,64 @@ def run_gpu(args, info):
         result["cpu_baseline"] = cpu_arm(args, prm, b0, m0, aabbs, sample_steps=args.cpu_steps, joints=joints, keep=keep)
         result["parity"] = parity_block(gpu_out, keep)
     return result
+
+
+def _resident_world(args, ctx):
+    """A DeviceResidentWorld of the scene, settled, with every per-step host column pinned and the snapshot's pair set in the contact graph."""
+    from avian_b200 import api, plugins, scenes
+    builder, substeps, _ = SCENES[args.scene]
+    w = plugins.DeviceResidentWorld(builder(scenes), plugins.PhysicsPlugins(ctx), ctx, substeps=substeps)
+    w.params.solver_iterations = args.solver_iterations
+    for _ in range(args.settle):
+        w.step()
+    pin_columns(ctx, w.bodies)
+    pairs_out = api.PairList.empty(1 << 20)
+    for _ in range(6):                  # until a step reports no new pair: the snapshot's pair set is then in the contact graph (rows on the device)
+        mn, mx = w.pipeline.update_aabbs(w.bodies, w.params.dt)
+        aabbs = pin_columns(ctx, w.pipeline.intervals(w.bodies, mn, mx))
+        aabbs.joint_disabled_body_pairs = w.scene.joint_disabled_body_pairs
+        w.prepare_steady(aabbs)
+        for k in ("shape", "dims", "aabb_min", "aabb_max"):
+            w._colliders[k] = ctx.pin_like(w._colliders[k])
+        w.step_steady(aabbs, pairs_out)
+        if pairs_out.count == 0:
+            break
+    for _ in range(max(2, args.warmup)):
+        w.step_steady(aabbs, pairs_out)
+    return w, aabbs, pairs_out
+
+
+def e2e_resident(args, info, barrier):
+    """K steps of DeviceResidentWorld.step_steady from pinned host columns; returns wall ms (max over ranks) and the bytes that cross the bus."""
+    from avian_b200 import api, parallel
+    scalar = np.float64 if args.scene.startswith("spheres") else np.float32
+    ctx = api.Context(device=info.local_rank, scalar=scalar)
+    try:
+        error = None
+        try:
+            w, aabbs, pairs_out = _resident_world(args, ctx)
+        except Exception as exc:
+            error = f"{type(exc).__name__}: {exc}"
+        if parallel.reduce_max([0.0 if error is None else 1.0], info, device="cuda")[0] > 0:     # every rank agrees before the barriers
+            return {"error": error or "another rank failed to set the resident world up"}
+        barrier()
+        fast = 0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fast += bool(w.step_steady(aabbs, pairs_out))
+        barrier()
+        wall_ms = parallel.reduce_max([(time.perf_counter() - t0) * 1e3], info, device="cuda")[0]
+        b, sb = w.bodies, w.bodies.position.dtype.itemsize
+        C = int(aabbs.collider.shape[0])
+        h2d = sum(v.nbytes for k, v in aabbs.__dict__.items() if isinstance(v, np.ndarray) and k != "order_out") \
+            + C * (1 + 3 * sb + 3 * sb + 4 * sb + 3 * sb + 3 * sb) + 2 * b.count * 3 * sb \
+            + sum(v.nbytes for k, v in b.__dict__.items() if isinstance(v, np.ndarray))
+        d2h = 2 * w.capacity + b.count * (3 + 4 + 3 + 3) * sb + C * 4
+        return {"wall_ms": wall_ms, "h2d": int(h2d), "d2h": int(d2h), "fast_share": fast / max(args.steps, 1),
+                "what": f"avn_broadphase -> avn_contacts_narrow_phase ({w.capacity} resident contact rows) -> avn_solver_upload_graph/run/download; "
+                        "the constraint graph stays on the device while no contact starts or stops touching"}
+    finally:
+        ctx.close()
 
 
 def measure_solver_pass(args, prm, bodies, man, joints, scalar, device):
@@ -549,6 +622,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-partition", action="store_true", help="skip the one-scene-over-N-GPUs arms")
     ap.add_argument("--no-pass", action="store_true", help="skip the single solver-pass roofline measurement")
+    ap.add_argument("--no-resident", action="store_true", help="e2e = round 1's host-manifold arm only")
     ap.add_argument("--partition-steps", type=int, default=10)
     ap.add_argument("--partition-slab-scene", default="spheres1m", choices=sorted(SCENES))
     ap.add_argument("--partition-island-scene", default="ragdolls5k", choices=sorted(SCENES))

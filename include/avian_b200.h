@@ -476,6 +476,8 @@ AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* para
                                     double length_unit, uint8_t* out_point_count, uint8_t* out_disjoint);
 /* The solver stage reading its manifolds from the resident rows: `graph` carries only count, color_offsets, edge, body1, body2, friction,
  * restitution (host); store_contact_impulses writes into the rows.  Then avn_solver_run / avn_solver_download (bodies only) as usual. */
+/* graph->edge == NULL: the constraint graph has not changed since the previous avn_solver_upload_graph (no contact started or stopped
+ * touching) — the list stays on the device and only the bodies are uploaded; count and color_offsets must repeat the previous call's. */
 AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints);
 /* the impulses of the rows as the last solve left them (tests, tools): [capacity][4], [capacity][4][2], [capacity][4]; any may be NULL */
 AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse);

@@ -135,3 +135,32 @@ def test_device_resident_world_equals_the_ordinary_world(gpu_ctx, scene_fn, step
                 assert np.array_equal(wn[gb["edge"]][slot], ma.warm_start_normal_impulse), f"step {i}: impulses"
                 assert np.array_equal(ni[gb["edge"]][slot], ma.normal_impulse), f"step {i}: total impulses"
         assert wb.bytes_to_host <= 2 * wb.capacity
+
+
+@pytest.mark.parametrize("scene_fn,steps,substeps,kick", [
+    (lambda: __import__("avian_b200.scenes", fromlist=["x"]).cubes_example(4), 80, 6, True),
+    (lambda: __import__("avian_b200.scenes", fromlist=["x"]).cube_stack(6, 5, 5, brick=True), 25, 4, False),
+])
+def test_step_steady_on_the_device_equals_the_ordinary_world(gpu_ctx, scene_fn, steps, substeps, kick):
+    """The bench's end-to-end arm: host AABB / body columns -> avn_broadphase -> avn_contacts_narrow_phase -> avn_solver_upload_graph (the resident
+    colour-major list reused while no contact starts or stops touching) -> bodies, against the ordinary GPU world, bit for bit every step."""
+    from avian_b200 import plugins
+    wa = plugins.World(scene_fn(), plugins.PhysicsPlugins(gpu_ctx), substeps=substeps)
+    with api.Context(device=0, scalar=wa.scalar) as ctx_b:
+        wb = plugins.DeviceResidentWorld(scene_fn(), plugins.PhysicsPlugins(ctx_b), ctx_b, substeps=substeps)
+        if kick:
+            _tumble(wa); _tumble(wb)
+        pairs_out = api.PairList.empty(1 << 16)
+        fast = 0
+        for i in range(steps):
+            wa.step()
+            mn, mx = wb.pipeline.update_aabbs(wb.bodies, wb.params.dt)
+            aabbs = wb.pipeline.intervals(wb.bodies, mn, mx)
+            aabbs.joint_disabled_body_pairs = wb.scene.joint_disabled_body_pairs
+            if wb._colliders is None:
+                wb.prepare_steady(aabbs)
+            wb._colliders["aabb_min"], wb._colliders["aabb_max"] = mn, mx
+            fast += bool(wb.step_steady(aabbs, pairs_out))
+            for k in ("position", "rotation", "linear_velocity", "angular_velocity"):
+                assert np.array_equal(getattr(wa.bodies, k), getattr(wb.bodies, k)), f"step {i}: {k}"
+        assert fast > 0, "the graph-reuse path never ran"

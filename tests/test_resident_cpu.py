@@ -9,7 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
-from avian_b200 import plugins, scenes  # noqa: E402
+from avian_b200 import api, plugins, scenes  # noqa: E402
 import oracle_lib  # noqa: E402
 
 COLUMNS = ("color_offsets", "body1", "body2", "normal", "friction", "restitution", "point_offsets", "anchor1", "anchor2", "penetration",
@@ -111,8 +111,21 @@ class MockContactStore:
             p(cols["aabb_min"]), p(cols["aabb_max"]), float(dt), float(tol), float(length_unit), 1 if match_contacts else 0)
         return r["count"].copy(), r["disjoint"].copy()
 
-    def solver_step_graph(self, params, bodies, graph, joints=None):
+    # the broad phase of step_steady (the oracle stands in for the device)
+    def broadphase_upload(self, aabbs): self._aabbs = aabbs
+    def broadphase_run(self): pass
+    def broadphase_download(self, out):
+        p = oracle_lib.broadphase(self._aabbs)
+        for k in ("collider1", "collider2", "body1", "body2", "flags"):
+            getattr(out, k)[:p.count] = getattr(p, k)
+        out.count = p.count
+        return out
+
+    def solver_step_graph(self, params, bodies, graph, joints=None, reuse_graph=False):
         from avian_b200 import api
+        if reuse_graph:      # the library keeps the previous list on the device; so does the mock
+            assert np.array_equal(graph["edge"], self._last_graph["edge"]) and np.array_equal(graph["color_offsets"], self._last_graph["color_offsets"])
+        self._last_graph = {k: np.array(v, copy=True) for k, v in graph.items()}
         r, s, edge = self.rows, self.scalar, graph["edge"]
         cnt = r["count"][edge].astype(np.int64)
         slot = np.arange(4)[None, :] < cnt[:, None]
@@ -153,3 +166,33 @@ def test_device_resident_world_host_logic_with_a_cpu_contact_store(scene_fn, ste
     assert added > 0
     if kick:
         assert removed > 0          # pairs really were dropped and ContactIds reused
+
+
+@pytest.mark.parametrize("scene_fn,steps,substeps,kick", [
+    (lambda: scenes.cube_stack(5, 4, 4, brick=True), 40, 4, None),          # settles: the fast path takes over
+    (lambda: scenes.cubes_example(4), 90, 6, _tumble),                       # pairs come and go: both paths, ContactIds reused
+])
+def test_step_steady_is_the_same_simulation(scene_fn, steps, substeps, kick):
+    """DeviceResidentWorld.step_steady (host AABB columns -> broad phase -> resident narrow phase -> solver from the resident rows, graphs touched
+    only when something started / stopped touching) against the ordinary World, step after step, bit for bit; the fast path must actually be
+    taken once the contact set has settled."""
+    wa = plugins.World(scene_fn(), oracle_lib.oracle_plugins(threads=2), substeps=substeps)
+    wb = plugins.DeviceResidentWorld(scene_fn(), oracle_lib.oracle_plugins(threads=2), MockContactStore(wa.scalar), substeps=substeps)
+    if kick:
+        kick(wa); kick(wb)
+    pairs_out = api.PairList.empty(1 << 16)
+    fast = 0
+    for i in range(steps):
+        wa.step()
+        mn, mx = wb.pipeline.update_aabbs(wb.bodies, wb.params.dt)
+        aabbs = wb.pipeline.intervals(wb.bodies, mn, mx)
+        aabbs.joint_disabled_body_pairs = wb.scene.joint_disabled_body_pairs
+        if wb._colliders is None:
+            wb.prepare_steady(aabbs)
+        wb._colliders["aabb_min"], wb._colliders["aabb_max"] = mn, mx     # a moving scene: this step's AABBs
+        fast += bool(wb.step_steady(aabbs, pairs_out))
+        for k in ("position", "rotation", "linear_velocity", "angular_velocity"):
+            assert np.array_equal(getattr(wa.bodies, k), getattr(wb.bodies, k)), f"step {i}: {k}"
+    assert fast > 0, "the incremental path never ran"
+    if kick is None:
+        assert fast > steps // 2
