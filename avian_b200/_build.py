@@ -46,9 +46,9 @@ def find_nvcc() -> str | None:
 _UNIT_HEADERS = {
     "comm.cu": ["context.hpp"],
     "aabb.cu": ["avn_math.cuh", "context.hpp"],
-    "broadphase.cu": ["avn_math.cuh", "context.hpp", "broadphase_cells.cuh"],
+    "broadphase.cu": ["avn_math.cuh", "context.hpp", "broadphase_cells.cuh", "device_prims.cuh"],
     "narrow.cu": ["avn_math.cuh", "context.hpp", "narrow_math.hpp"],
-    "contacts.cu": ["avn_math.cuh", "context.hpp", "narrow_math.hpp", "contact_rows.hpp"],
+    "contacts.cu": ["avn_math.cuh", "context.hpp", "narrow_math.hpp", "contact_rows.hpp", "device_prims.cuh"],
 }
 
 

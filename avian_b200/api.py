@@ -321,6 +321,18 @@ class AvnNarrowParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("contact_tolerance", C.c_double)]
 
 
+class AvnContactGraphConfig(C.Structure):
+    _fields_ = [("body_count", C.c_uint32), ("collider_count", C.c_uint32), ("body_kind", _vp), ("friction", _vp), ("restitution", _vp)]
+
+
+class AvnContactStep(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("rows_high_water", "rows_live", "pairs_added", "pairs_removed", "started_touching", "stopped_touching",
+                                         "manifold_count", "colouring_rounds", "any_restitution", "_pad")] + [("color_offsets", C.c_uint32 * (GRAPH_COLOR_COUNT + 1))]
+
+
+CONTACTS_TAKE_BROADPHASE_PAIRS = 1
+
+
 class AvnNarrowInput(C.Structure):
     _fields_ = [("pair_count", C.c_uint32), ("collider_count", C.c_uint32), ("body_count", C.c_uint32), ("_pad", C.c_uint32)] + [
         (n, _vp) for n in ("collider1", "collider2", "body1", "body2", "shape", "dims", "position", "rotation", "linear_velocity", "angular_velocity",
@@ -377,6 +389,11 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "contacts_remove": ([_vp, C.c_uint32, _vp], C.c_int),
         "contacts_narrow_phase": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), C.c_uint32, C.c_double, _vp, _vp], C.c_int),
         "contacts_download_impulses": ([_vp, _vp, _vp, _vp], C.c_int),
+        "contacts_configure": ([_vp, P(AvnContactGraphConfig)], C.c_int),
+        "contacts_step": ([_vp, P(AvnNarrowParams), P(AvnNarrowInput), C.c_uint32, C.c_double, C.c_uint32, P(AvnContactStep)], C.c_int),
+        "solver_upload_resident": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnJointSet)], C.c_int),
+        "broadphase_download_order": ([_vp, P(C.c_uint64)], C.c_int),
+        "contacts_download_graph": ([_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -390,7 +407,8 @@ ABI_SYMBOLS = [
     "avn_broadphase_download", "avn_get_timings", "avn_joint_levels", "avn_update_aabbs", "avn_solver_run_range", "avn_solver_set_boundary",
     "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream",
     "avn_solver_step_partitioned", "avn_comm_unique_id", "avn_comm_init", "avn_comm_destroy", "avn_comm_all_gather", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
-    "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses"]
+    "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses",
+    "avn_contacts_configure", "avn_contacts_step", "avn_solver_upload_resident", "avn_broadphase_download_order", "avn_contacts_download_graph"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 COMM_ID_BYTES = 128
@@ -689,6 +707,54 @@ class Context:
         self._check(self.lib.avn_solver_upload_graph(self.handle, C.byref(params), C.byref(b), C.byref(em) if em.count else None, C.byref(j) if j is not None else None))
         self._check(self.lib.avn_solver_run(self.handle))
         self._check(self.lib.avn_solver_download(self.handle))
+
+    # ---- the ContactGraph + ConstraintGraph on the device (include/avian_b200.h avn_contacts_configure / _step)
+    def contacts_configure(self, body_kind, collider_count: int, friction=None, restitution=None) -> None:
+        kind = np.ascontiguousarray(body_kind, dtype=np.uint8)
+        fr = None if friction is None else np.ascontiguousarray(friction, dtype=np.float64)
+        re = None if restitution is None else np.ascontiguousarray(restitution, dtype=np.float64)
+        cfg = AvnContactGraphConfig(int(kind.shape[0]), int(collider_count), _ptr(kind), _ptr(fr), _ptr(re))
+        self._check(self.lib.avn_contacts_configure(self.handle, C.byref(cfg)))
+
+    def contacts_step(self, dt: float, contact_tolerance: float, colliders: dict, lin_vel, ang_vel, match_contacts: bool = True, take_pairs: bool = True,
+                      length_unit: float = 1.0) -> dict:
+        """avn_contacts_step: (the last broad phase's new pairs ->) rows, geometry + matching, status loop, graphs, colour-major list — all on the
+        device.  Returns the step's counters and the colour offsets of the list."""
+        dt_ = self.scalar
+        cols = {k: (None if colliders.get(k) is None else np.ascontiguousarray(colliders[k], dtype=(np.uint8 if k == "shape" else dt_)))
+                for k in ("shape", "dims", "position", "rotation", "aabb_min", "aabb_max")}
+        lv, av = np.ascontiguousarray(lin_vel, dtype=dt_), np.ascontiguousarray(ang_vel, dtype=dt_)
+        inp = AvnNarrowInput(0, int(cols["position"].shape[0]), int(lv.shape[0]), 0, None, None, None, None, _ptr(cols["shape"]), _ptr(cols["dims"]),
+                             _ptr(cols["position"]), _ptr(cols["rotation"]), _ptr(lv), _ptr(av), _ptr(cols["aabb_min"]), _ptr(cols["aabb_max"]))
+        prm = AvnNarrowParams(float(dt), float(contact_tolerance))
+        out = AvnContactStep()
+        self._check(self.lib.avn_contacts_step(self.handle, C.byref(prm), C.byref(inp), 1 if match_contacts else 0, float(length_unit),
+                                               CONTACTS_TAKE_BROADPHASE_PAIRS if take_pairs else 0, C.byref(out)))
+        st = {n: int(getattr(out, n)) for n, _ in AvnContactStep._fields_ if n not in ("_pad", "color_offsets")}
+        st["color_offsets"] = np.array(list(out.color_offsets), dtype=np.uint32)
+        return st
+
+    def solver_step_resident(self, params, bodies: Bodies, joints: JointSet | None = None) -> None:
+        """avn_solver_upload_resident + run + download: manifolds AND constraint graph come from the contact store on the device."""
+        b = bodies.as_struct()
+        j = joints.as_struct() if joints is not None and joints.count else None
+        self._keep = (params, bodies, joints, b, j)
+        self._check(self.lib.avn_solver_upload_resident(self.handle, C.byref(params), C.byref(b), C.byref(j) if j is not None else None))
+        self._check(self.lib.avn_solver_run(self.handle))
+        self._check(self.lib.avn_solver_download(self.handle))
+
+    def broadphase_download_order(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self.lib.avn_broadphase_download_order(self.handle, C.byref(n)))
+        self._keep_bp[0].retained_count = int(self._keep_bp[1].retained_count)
+        return int(n.value)
+
+    def contacts_download_graph(self, capacity: int, manifold_count: int) -> dict:
+        out = {"collider1": np.zeros(capacity, dtype=np.uint32), "collider2": np.zeros(capacity, dtype=np.uint32), "live": np.zeros(capacity, dtype=np.uint8),
+               "touching": np.zeros(capacity, dtype=np.uint8), "colour": np.zeros(capacity, dtype=np.int8), "edge": np.zeros(manifold_count, dtype=np.uint32)}
+        self._check(self.lib.avn_contacts_download_graph(self.handle, int(capacity), *(out[k].ctypes.data for k in ("collider1", "collider2", "live", "touching",
+                                                                                                                   "colour", "edge"))))
+        return out
 
     def contacts_download_impulses(self, capacity: int):
         wn, wt, ni = (np.zeros((capacity, 4), dtype=self.scalar), np.zeros((capacity, 4, 2), dtype=self.scalar), np.zeros((capacity, 4), dtype=self.scalar))

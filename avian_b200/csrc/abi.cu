@@ -239,6 +239,34 @@ AvnStatus avn_contacts_narrow_phase(AvnContext* ctx, const AvnNarrowParams* para
 AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, AvnJointSet* joints) {
     return guarded(ctx, [&] { return ctx->solver->upload_graph(params, bodies, graph, ctx->contacts.get(), joints); });
 }
+AvnStatus avn_contacts_configure(AvnContext* ctx, const AvnContactGraphConfig* config) { return guarded(ctx, [&] { return ctx->contacts->configure(config); }); }
+AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts, double length_unit, uint32_t flags,
+                            AvnContactStep* out) {
+    return guarded(ctx, [&] {
+        avn::DevicePairs pairs;
+        const bool take = (flags & AVN_CONTACTS_TAKE_BROADPHASE_PAIRS) != 0;
+        if (take) {
+            AvnStatus st = ctx->broadphase->device_pairs(&pairs);
+            if (st != AVN_OK) return st;
+        }
+        AvnStatus st = ctx->contacts->step(params, input, match_contacts, length_unit, take ? &pairs : nullptr, out);
+        if (st != AVN_OK) return st;
+        // ContactGraph::pair_set stays on the device: the next broad phase filters against it
+        const uint64_t* table = nullptr;
+        uint64_t mask = 0;
+        ctx->contacts->pair_set(&table, &mask);
+        ctx->broadphase->set_existing_device(table, mask);
+        return AVN_OK;
+    });
+}
+AvnStatus avn_solver_upload_resident(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnJointSet* joints) {
+    return guarded(ctx, [&] { return ctx->solver->upload_resident(params, bodies, ctx->contacts.get(), joints); });
+}
+AvnStatus avn_broadphase_download_order(AvnContext* ctx, uint64_t* out_pair_count) { return guarded(ctx, [&] { return ctx->broadphase->download_order(out_pair_count); }); }
+AvnStatus avn_contacts_download_graph(AvnContext* ctx, uint32_t capacity, uint32_t* collider1, uint32_t* collider2, uint8_t* live, uint8_t* touching, int8_t* colour,
+                                      uint32_t* edge_list) {
+    return guarded(ctx, [&] { return ctx->contacts->download_graph(capacity, collider1, collider2, live, touching, colour, edge_list); });
+}
 AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse) {
     return guarded(ctx, [&] { return ctx->contacts->download_impulses(warm_start_normal, warm_start_tangent, normal_impulse); });
 }

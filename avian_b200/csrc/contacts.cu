@@ -4,11 +4,253 @@
 // unrounded anchors of that manifold (double: what the next step's match_contacts compares) and the warm-start impulses (in = what the
 // next solve starts from, written by the matching; out = what the last solve left, written by store_contact_impulses).
 // Per step only point counts and disjoint flags go to the host (2 B per row) and the edge list of the constraint graph comes back.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "context.hpp"
 #include "contact_rows.hpp"
+#include "device_prims.cuh"
 
 namespace avn {
 namespace {
+namespace cg = cooperative_groups;
+
+// =====================================================================================================================================
+// The ContactGraph and the ConstraintGraph on the device.
+//   ContactGraph::add_edge_and_key_with (contact_graph.rs:521-565): new pairs take the lowest free ContactIds in list order (IdPool,
+//     data_structures/id_pool.rs:43-52) — the k-th new pair gets the k-th smallest free row, rows beyond the free ones are appended.
+//   NarrowPhase::update's status loop (narrow_phase/system_param.rs:136-389) visits the changed contacts in ASCENDING ContactId: a pair
+//     whose AABBs separated leaves the graph (its manifold is popped), a pair that started touching pushes its manifold into the
+//     ConstraintGraph, a pair that stopped touching pops it.
+//   ConstraintGraph::push_manifold (solver/constraint_graph.rs:163-238) is GREEDY: dynamic-dynamic takes the lowest of the first
+//     AVN_DYNAMIC_COLOR_COUNT colours whose body set holds neither body, dynamic-static the highest colour below the overflow colour that does
+//     not hold the dynamic body, anything else lands in the overflow colour; pop_manifold (:240-296) clears the bodies from the set.
+// The colour a push gets depends on every earlier push and pop that shares a body, so the result is order dependent — and the order of
+// the colours IS the Gauss-Seidel order of the solver.  The device reproduces the sequential result exactly with a dependency wavefront:
+// in every round a changed edge runs iff it is the smallest pending ContactId on each of its non-static bodies (64-bit atomicMin tagged
+// with the round: no reset pass); edges of one round share no non-static body, so they commute.  The number of rounds is the longest chain
+// of changed edges linked through shared bodies in ascending id (a few in the steady state, thousands on the first frame of a big pile).
+// Inside a colour the order of the manifolds does not influence the solve (they share no dynamic body), so the colour-major list is built
+// in ascending ContactId by one stable radix pass; only the overflow colour, which the solver walks serially, keeps the reference's
+// push / swap_remove list order, maintained by one thread.
+// =====================================================================================================================================
+enum { CH_NONE = 0, CH_PUSH = 1, CH_POP = 2, CH_REMOVE = 3, CH_MASK = 3, CH_DONE = 0x10 };
+
+struct GraphCounters {          // device block, copied to the host once per step
+    // cleared at the start of every step
+    uint32_t removed, started, stopped, changed, rounds, ovf_dirty, manifolds, any_restitution, aborted;
+    uint32_t round_left[3];
+    uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];
+    // persistent
+    uint32_t ovf_count;
+};
+
+struct GraphRows {
+    int hw;                                       // rows in use: ContactIds [0, hw)
+    uint32_t* c1; uint32_t* c2; uint32_t* b1; uint32_t* b2;
+    uint8_t* live; uint8_t* count; uint8_t* disjoint; uint8_t* prev_count;
+    uint8_t* pflags; uint8_t* touching; uint8_t* colour /* 0 = none, c + 1 */; uint8_t* change; uint8_t* old_colour;
+    uint32_t* ovf_pos; uint32_t* ovf;
+    const uint8_t* body_kind; int n_bodies;
+    uint32_t* body_bits;                          // [B] bit c: the body is in colour c's body set
+    unsigned long long* body_min;                 // [B] round-tagged smallest pending ContactId
+    GraphCounters* ctr;
+};
+
+__global__ void add_rows_kernel(GraphRows g, uint32_t n_new, const uint32_t* __restrict__ pc1, const uint32_t* __restrict__ pc2, const uint32_t* __restrict__ pb1,
+                                const uint32_t* __restrict__ pb2, const uint8_t* __restrict__ pfl, const uint32_t* __restrict__ free_list, uint32_t n_free,
+                                uint32_t old_hw) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_new) return;
+    const uint32_t e = k < n_free ? free_list[k] : old_hw + (k - n_free);
+    g.c1[e] = pc1[k]; g.c2[e] = pc2[k]; g.b1[e] = pb1[k]; g.b2[e] = pb2[k];
+    g.pflags[e] = pfl[k];
+    g.live[e] = 1;            // a ContactId handed to a new pair starts without history
+    g.count[e] = 0; g.prev_count[e] = 0; g.touching[e] = 0; g.colour[e] = 0; g.change[e] = 0;
+}
+
+// key 0 for rows that satisfy the predicate, 1 otherwise: one stable radix pass then lists them in ascending ContactId
+__global__ void free_keys_kernel(const uint8_t* __restrict__ live, int n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    keys[e] = live[e] ? 1u : 0u;
+    vals[e] = uint32_t(e);
+}
+
+// the touching state machine of one row -> its change for the graphs
+__global__ void classify_kernel(GraphRows g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw) return;
+    uint8_t ch = CH_NONE;
+    if (g.live[e]) {
+        const bool gen = (g.pflags[e] & AVN_PAIR_GENERATE_CONSTRAINTS) != 0;
+        if (g.disjoint[e]) {
+            ch = CH_REMOVE | (g.colour[e] ? 0 : CH_DONE);
+            atomicAdd(&g.ctr->removed, 1u);
+        } else {
+            const bool now = g.count[e] > 0, was = g.touching[e] != 0;
+            if (now && !was) {
+                g.touching[e] = 1;
+                atomicAdd(&g.ctr->started, 1u);
+                if (gen) ch = CH_PUSH;
+            } else if (!now && was) {
+                g.touching[e] = 0;
+                atomicAdd(&g.ctr->stopped, 1u);
+                if (gen && g.colour[e]) ch = CH_POP;
+            }
+        }
+    }
+    g.change[e] = ch;
+    if (ch) atomicAdd(&g.ctr->changed, 1u);
+    keys[e] = ch ? 0u : 1u;
+    vals[e] = uint32_t(e);
+}
+
+__device__ __forceinline__ bool graph_static(const GraphRows& g, uint32_t b) { return b >= uint32_t(g.n_bodies) || g.body_kind[b] == AVN_BODY_STATIC; }
+
+// ConstraintGraph::push_manifold / pop_manifold for ONE edge whose turn it is
+__device__ __forceinline__ void graph_apply(const GraphRows& g, uint32_t e, uint8_t ch) {
+    const uint32_t b1 = g.b1[e], b2 = g.b2[e];
+    const bool s1 = graph_static(g, b1), s2 = graph_static(g, b2);
+    if ((ch & CH_MASK) == CH_PUSH) {
+        int c = AVN_COLOR_OVERFLOW;
+        if (!s1 && !s2) {
+            const uint32_t freec = ~(g.body_bits[b1] | g.body_bits[b2]) & ((1u << AVN_DYNAMIC_COLOR_COUNT) - 1u);
+            if (freec) { c = __ffs(int(freec)) - 1; g.body_bits[b1] |= 1u << c; g.body_bits[b2] |= 1u << c; }
+        } else if (!s1 || !s2) {
+            const uint32_t b = s1 ? b2 : b1;
+            const uint32_t freec = ~g.body_bits[b] & (((1u << AVN_COLOR_OVERFLOW) - 1u) & ~1u);   // colours OVERFLOW-1 .. 1, highest first
+            if (freec) { c = 31 - __clz(int(freec)); g.body_bits[b] |= 1u << c; }
+        }
+        g.colour[e] = uint8_t(c + 1);
+        if (c == AVN_COLOR_OVERFLOW) g.ctr->ovf_dirty = 1;
+    } else {
+        const int c = int(g.colour[e]) - 1;
+        g.old_colour[e] = uint8_t(c + 1);
+        if (c >= 0 && c != AVN_COLOR_OVERFLOW) {
+            if (!s1) g.body_bits[b1] &= ~(1u << c);
+            if (!s2) g.body_bits[b2] &= ~(1u << c);
+        }
+        if (c == AVN_COLOR_OVERFLOW) g.ctr->ovf_dirty = 1;
+        g.colour[e] = 0;
+    }
+}
+
+constexpr unsigned GRAPH_MAX_ROUNDS = 1u << 22;
+__global__ void __launch_bounds__(256) colour_rounds_kernel(GraphRows g, const uint32_t* __restrict__ list) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t n = g.ctr->changed;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned round = 0;
+    for (;; ++round) {
+        const unsigned long long tag = (unsigned long long)(GRAPH_MAX_ROUNDS - round) << 32;   // later rounds compare smaller: no reset pass
+        if (tid == 0) g.ctr->round_left[(round + 1) % 3] = 0;   // next round's counter: its last readers left before this round began
+        for (uint32_t i = tid; i < n; i += nth) {
+            const uint32_t e = list[i];
+            const uint8_t ch = g.change[e];
+            if (ch & CH_DONE) continue;
+            const uint32_t b1 = g.b1[e], b2 = g.b2[e];
+            if (!graph_static(g, b1)) atomicMin(&g.body_min[b1], tag | e);
+            if (!graph_static(g, b2)) atomicMin(&g.body_min[b2], tag | e);
+        }
+        grid.sync();
+        uint32_t left = 0;
+        for (uint32_t i = tid; i < n; i += nth) {
+            const uint32_t e = list[i];
+            const uint8_t ch = g.change[e];
+            if (ch & CH_DONE) continue;
+            const uint32_t b1 = g.b1[e], b2 = g.b2[e];
+            const bool mine = (graph_static(g, b1) || g.body_min[b1] == (tag | e)) && (graph_static(g, b2) || g.body_min[b2] == (tag | e));
+            if (mine) { graph_apply(g, e, ch); g.change[e] = ch | CH_DONE; }
+            else ++left;
+        }
+        if (left) atomicAdd(&g.ctr->round_left[round % 3], left);
+        grid.sync();
+        if (*reinterpret_cast<volatile uint32_t*>(&g.ctr->round_left[round % 3]) == 0) break;
+        if (round + 2 >= GRAPH_MAX_ROUNDS) { if (tid == 0) g.ctr->aborted = 1; break; }
+    }
+    if (tid == 0) g.ctr->rounds = round + 1;
+}
+
+// the overflow colour keeps the reference's list order (push at the end, swap_remove): one thread, changed edges in ascending ContactId
+__global__ void overflow_list_kernel(GraphRows g, const uint32_t* __restrict__ list) {
+    if (blockIdx.x || threadIdx.x || !g.ctr->ovf_dirty) return;
+    uint32_t n_ovf = g.ctr->ovf_count;
+    const uint32_t n = g.ctr->changed;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t e = list[i];
+        const uint8_t ch = g.change[e] & CH_MASK;
+        if (ch == CH_PUSH) {
+            if (g.colour[e] == AVN_COLOR_OVERFLOW + 1) { g.ovf[n_ovf] = e; g.ovf_pos[e] = n_ovf++; }
+        } else if (g.old_colour[e] == AVN_COLOR_OVERFLOW + 1) {
+            const uint32_t pos = g.ovf_pos[e], last = g.ovf[n_ovf - 1];
+            g.ovf[pos] = last; g.ovf_pos[last] = pos; --n_ovf;
+        }
+    }
+    g.ctr->ovf_count = n_ovf;
+}
+
+// rows that left the ContactGraph; and the radix key of every row for the colour-major list (255 = not in a coloured list)
+__global__ void finalize_rows_kernel(GraphRows g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw) return;
+    const uint8_t ch = g.change[e];
+    if ((ch & CH_MASK) == CH_REMOVE) { g.live[e] = 0; g.count[e] = 0; g.prev_count[e] = 0; g.touching[e] = 0; g.colour[e] = 0; g.pflags[e] = 0; }
+    g.old_colour[e] = 0;
+    const int c = int(g.colour[e]) - 1;
+    keys[e] = (c >= 0 && c < AVN_COLOR_OVERFLOW) ? uint32_t(c) : 255u;
+    vals[e] = uint32_t(e);
+}
+
+// colour offsets from the sorted keys; the overflow colour's list is appended behind the coloured part
+__global__ void color_offsets_kernel(GraphRows g, const uint32_t* __restrict__ sorted_keys, uint32_t* __restrict__ edge_list) {
+    __shared__ uint32_t off[AVN_GRAPH_COLOR_COUNT + 1];
+    const int c = threadIdx.x;
+    if (c < AVN_GRAPH_COLOR_COUNT) {   // lower bound of key c
+        int lo = 0, hi = g.hw;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_keys[mid] < uint32_t(c)) lo = mid + 1; else hi = mid; }
+        off[c] = uint32_t(lo);
+    }
+    __syncthreads();
+    const uint32_t n_ovf = g.ctr->ovf_count;
+    if (c == 0) off[AVN_GRAPH_COLOR_COUNT] = off[AVN_COLOR_OVERFLOW] + n_ovf;
+    __syncthreads();
+    if (c <= AVN_GRAPH_COLOR_COUNT) g.ctr->color_offsets[c] = off[c];
+    if (c == 0) g.ctr->manifolds = off[AVN_GRAPH_COLOR_COUNT];
+    for (uint32_t k = threadIdx.x; k < n_ovf; k += blockDim.x) edge_list[off[AVN_COLOR_OVERFLOW] + k] = g.ovf[k];
+}
+
+// what prepare_contact_constraints needs per manifold besides the row: the bodies and the pair's material
+template <class S>
+__global__ void gather_graph_kernel(GraphRows g, const uint32_t* __restrict__ edge_list, const double* __restrict__ friction, const double* __restrict__ restitution,
+                                    int32_t* __restrict__ m_b1, int32_t* __restrict__ m_b2, S* __restrict__ m_fr, S* __restrict__ m_re) {
+    const uint32_t M = g.ctr->manifolds;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        const uint32_t e = edge_list[m];
+        m_b1[m] = int32_t(g.b1[e]);
+        m_b2[m] = int32_t(g.b2[e]);
+        const uint32_t ca = g.c1[e], cb = g.c2[e];
+        const double fr = friction ? (friction[ca] + friction[cb]) * 0.5 : 0.5, re = restitution ? (restitution[ca] + restitution[cb]) * 0.5 : 0.0;
+        m_fr[m] = S(fr);
+        m_re[m] = S(re);
+        if (S(re) != S(0)) g.ctr->any_restitution = 1;
+    }
+}
+
+// ContactGraph::pair_set as the broad phase's "existing pairs" hash set, rebuilt from the live rows
+__global__ void pair_set_kernel(GraphRows g, uint64_t* __restrict__ table, uint64_t mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw || !g.live[e]) return;
+    const uint32_t a = g.c1[e], b = g.c2[e];
+    const uint64_t k = (a < b ? (uint64_t(a) << 32) | b : (uint64_t(b) << 32) | a) + 1;
+    uint64_t h = hash64(k) & mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long*)&table[h], 0ull, (unsigned long long)k);
+        if (prev == 0ull || prev == k) return;
+        h = (h + 1) & mask;
+    }
+}
 
 __global__ void edge_add_kernel(int n, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2,
                                 const uint32_t* __restrict__ b1, const uint32_t* __restrict__ b2, uint32_t* rc1, uint32_t* rc2, uint32_t* rb1, uint32_t* rb2,
@@ -37,7 +279,14 @@ __global__ void __launch_bounds__(128) narrow_edges_kernel(const __grid_constant
 template <class S>
 class Contacts final : public ContactsBase {
    public:
-    Contacts(cudaStream_t stream, ErrorSink* err) : stream_(stream), err_(err) {}
+    Contacts(cudaStream_t stream, ErrorSink* err) : stream_(stream), err_(err) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sm_count_ = prop.multiProcessorCount;
+        cudaHostAlloc(&h_ctr_, sizeof(GraphCounters), cudaHostAllocDefault);
+    }
+    ~Contacts() override { if (h_ctr_) cudaFreeHost(h_ctr_); }
 
     AvnStatus reserve(uint32_t capacity) override {
         if (capacity <= E_) return AVN_OK;
@@ -46,7 +295,9 @@ class Contacts final : public ContactsBase {
         Col cols[] = {{&c1_, 4}, {&c2_, 4}, {&b1_, 4}, {&b2_, 4}, {&live_, 1}, {&count_, 1}, {&disjoint_, 1}, {&normal_, 3 * sizeof(S)}, {&a1_, 12 * sizeof(S)},
                       {&a2_, 12 * sizeof(S)}, {&pen_, 4 * sizeof(S)}, {&ns_, 4 * sizeof(S)}, {&prev_count_, 1}, {&prev_a1_, 12 * sizeof(double)},
                       {&prev_a2_, 12 * sizeof(double)}, {&ws_n_in_, 4 * sizeof(S)}, {&ws_t_in_, 8 * sizeof(S)}, {&ws_n_out_, 4 * sizeof(S)},
-                      {&ws_t_out_, 8 * sizeof(S)}, {&nimp_in_, 4 * sizeof(S)}, {&nimp_out_, 4 * sizeof(S)}};
+                      {&ws_t_out_, 8 * sizeof(S)}, {&nimp_in_, 4 * sizeof(S)}, {&nimp_out_, 4 * sizeof(S)},
+                      // graph state per row (zero = no flags, not touching, no colour)
+                      {&pflags_, 1}, {&touching_, 1}, {&colour_, 1}, {&change_, 1}, {&old_colour_, 1}, {&ovf_pos_, 4}, {&ovf_, 4}};
         for (Col& c : cols) {   // grow, keep the old rows, zero the new ones
             void* fresh = nullptr;
             AVN_CUDA(cudaMalloc(&fresh, n * c.bytes_per_row));
@@ -58,6 +309,16 @@ class Contacts final : public ContactsBase {
             c.buf->cap = n * c.bytes_per_row;
         }
         E_ = capacity;
+        // work buffers of the graph step (contents do not outlive a step) and the pair set (rebuilt by the next step)
+        const size_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+        AVN_CUDA(k0_.ensure(n * 4)); AVN_CUDA(k1_.ensure(n * 4)); AVN_CUDA(v0_.ensure(n * 4)); AVN_CUDA(v1_.ensure(n * 4)); AVN_CUDA(list_.ensure(n * 4));
+        AVN_CUDA(hist_.ensure(256 * nblocks * 4));
+        AVN_CUDA(m_b1_.ensure(n * 4)); AVN_CUDA(m_b2_.ensure(n * 4)); AVN_CUDA(m_fr_.ensure(n * sizeof(S))); AVN_CUDA(m_re_.ensure(n * sizeof(S)));
+        uint64_t cap = 1024;
+        while (cap < uint64_t(n) * 2) cap <<= 1;
+        AVN_CUDA(table_.ensure(cap * sizeof(uint64_t)));
+        table_mask_ = cap - 1;
+        table_dirty_ = true;
         return AVN_OK;
     }
 
@@ -74,6 +335,7 @@ class Contacts final : public ContactsBase {
                                                               c2_.as<uint32_t>(), b1_.as<uint32_t>(), b2_.as<uint32_t>(), live_.as<uint8_t>(), count_.as<uint8_t>(),
                                                               prev_count_.as<uint8_t>());
         AVN_CUDA(cudaGetLastError());
+        for (uint32_t k = 0; k < n; ++k) hw_ = std::max(hw_, ids[k] + 1);   // rows managed by the host protocol: the high-water mark follows
         AVN_CUDA(cudaStreamSynchronize(stream_));   // the host arrays may be reused by the caller
         return AVN_OK;
     }
@@ -95,31 +357,137 @@ class Contacts final : public ContactsBase {
                            uint8_t* out_disjoint) override {
         if (!prm || !in || !out_count || !out_disjoint) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_narrow_phase: params, input and outputs are required");
         if (E_ == 0) return AVN_OK;
-        const size_t C = in->collider_count, B = in->body_count;
-        if (!in->dims || !in->position || !in->rotation || !in->linear_velocity || !in->angular_velocity || !in->aabb_min || !in->aabb_max)
-            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_narrow_phase: dims, position, rotation, velocities and AABBs are required");
-        NarrowEdgeArgs<S> a{};
-        a.r = rows();
-        AvnStatus st;
-#define UPC(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
-        UPC(i_shape_, in->shape, C, uint8_t, a.shape);
-        UPC(i_dims_, in->dims, 3 * C, S, a.dims);
-        UPC(i_pos_, in->position, 3 * C, S, a.pos);
-        UPC(i_rot_, in->rotation, 4 * C, S, a.rot);
-        UPC(i_lv_, in->linear_velocity, 3 * B, S, a.lv);
-        UPC(i_av_, in->angular_velocity, 3 * B, S, a.av);
-        UPC(i_amin_, in->aabb_min, 3 * C, S, a.amin);
-        UPC(i_amax_, in->aabb_max, 3 * C, S, a.amax);
-#undef UPC
-        a.dt = prm->dt;
-        a.tol = prm->contact_tolerance;
-        a.thr2 = (0.1 * length_unit) * (0.1 * length_unit);
-        a.match = match_contacts ? 1 : 0;
-        narrow_edges_kernel<S><<<(E_ + 127) / 128, 128, 0, stream_>>>(a);
-        AVN_CUDA(cudaGetLastError());
+        AvnStatus st = launch_narrow(prm, in, match_contacts, length_unit, E_);
+        if (st != AVN_OK) return st;
         AVN_CUDA(cudaMemcpyAsync(out_count, count_.p, E_, cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaMemcpyAsync(out_disjoint, disjoint_.p, E_, cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaStreamSynchronize(stream_));
+        return AVN_OK;
+    }
+
+    // ---- the graphs on the device ---------------------------------------------------------------------------------------------------
+    AvnStatus configure(const AvnContactGraphConfig* cfg) override {
+        if (!cfg || !cfg->body_kind) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_configure: config and body_kind are required");
+        n_bodies_ = cfg->body_count;
+        n_colliders_ = cfg->collider_count;
+        AVN_CUDA(kind_.ensure(std::max<size_t>(n_bodies_, 1)));
+        AVN_CUDA(cudaMemcpyAsync(kind_.p, cfg->body_kind, n_bodies_, cudaMemcpyHostToDevice, stream_));
+        have_fr_ = cfg->friction != nullptr;
+        have_re_ = cfg->restitution != nullptr;
+        if (have_fr_) { AVN_CUDA(fr_.ensure(size_t(n_colliders_) * 8)); AVN_CUDA(cudaMemcpyAsync(fr_.p, cfg->friction, size_t(n_colliders_) * 8, cudaMemcpyHostToDevice, stream_)); }
+        if (have_re_) { AVN_CUDA(re_.ensure(size_t(n_colliders_) * 8)); AVN_CUDA(cudaMemcpyAsync(re_.p, cfg->restitution, size_t(n_colliders_) * 8, cudaMemcpyHostToDevice, stream_)); }
+        // the body sets of the colours and the round-tagged minima; a (re)configuration starts from an empty ConstraintGraph
+        AVN_CUDA(body_bits_.ensure(std::max<size_t>(n_bodies_, 1) * 4));
+        AVN_CUDA(body_min_.ensure(std::max<size_t>(n_bodies_, 1) * 8));
+        AVN_CUDA(cudaMemsetAsync(body_bits_.p, 0, std::max<size_t>(n_bodies_, 1) * 4, stream_));
+        AVN_CUDA(ctr_.ensure(sizeof(GraphCounters)));
+        AVN_CUDA(cudaMemsetAsync(ctr_.p, 0, sizeof(GraphCounters), stream_));
+        if (E_) {
+            AVN_CUDA(cudaMemsetAsync(colour_.p, 0, E_, stream_));
+            AVN_CUDA(cudaMemsetAsync(touching_.p, 0, E_, stream_));
+        }
+        AVN_CUDA(cudaStreamSynchronize(stream_));   // the host arrays may be reused by the caller
+        configured_ = true;
+        graph_ = ResidentGraph{};
+        return AVN_OK;
+    }
+
+    AvnStatus step(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, const DevicePairs* np,
+                   AvnContactStep* out) override {
+        if (!prm || !in || !out) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_step: params, input and out are required");
+        if (!configured_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_contacts_step before avn_contacts_configure");
+        if (in->body_count > n_bodies_ || in->collider_count > n_colliders_)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_step: %u bodies / %u colliders exceed the configured %u / %u", in->body_count, in->collider_count,
+                              n_bodies_, n_colliders_);
+        const uint64_t n_new64 = np ? np->count : 0;
+        if (n_new64 > 0x7fffffffull - hw_) return err_->fail(AVN_ERR_CAPACITY, "contacts_step: too many contact pairs");
+        const uint32_t n_new = uint32_t(n_new64);
+        if (hw_ + n_new > E_ || E_ == 0) {
+            AvnStatus st = reserve(std::max<uint32_t>(1024u, std::max(2 * E_, hw_ + n_new + 1024u)));
+            if (st != AVN_OK) return st;
+        }
+        GraphRows g = graph_rows();
+        const uint32_t added = n_new;
+        if (n_new) {
+            // ContactGraph::add_edge_and_key_with: lowest free ContactIds first, in list order
+            const uint32_t n_free = hw_ - live_n_;
+            const uint32_t* free_list = nullptr;
+            if (n_free) {
+                free_keys_kernel<<<(hw_ + 255) / 256, 256, 0, stream_>>>(live_.as<uint8_t>(), int(hw_), k0_.as<uint32_t>(), v0_.as<uint32_t>());
+                radix_pass(int(hw_));
+                free_list = v1_.as<uint32_t>();
+            }
+            add_rows_kernel<<<(n_new + 255) / 256, 256, 0, stream_>>>(g, n_new, np->c1, np->c2, np->b1, np->b2, np->flags, free_list, n_free, hw_);
+            AVN_CUDA(cudaGetLastError());
+            if (n_new > n_free) hw_ += n_new - n_free;
+            live_n_ += n_new;
+            g.hw = int(hw_);
+        }
+        AVN_CUDA(cudaMemsetAsync(ctr_.p, 0, offsetof(GraphCounters, ovf_count), stream_));   // the per-step counters; ovf_count persists
+        if (hw_) {
+            AvnStatus st = launch_narrow(prm, in, match_contacts, length_unit, hw_);
+            if (st != AVN_OK) return st;
+            const unsigned rb = (hw_ + 255) / 256;
+            classify_kernel<<<rb, 256, 0, stream_>>>(g, k0_.as<uint32_t>(), v0_.as<uint32_t>());
+            radix_pass(int(hw_));
+            AVN_CUDA(cudaMemcpyAsync(list_.p, v1_.p, size_t(hw_) * 4, cudaMemcpyDeviceToDevice, stream_));   // changed rows first, ascending ContactId
+            AVN_CUDA(cudaMemsetAsync(body_min_.p, 0xff, std::max<size_t>(n_bodies_, 1) * 8, stream_));
+            {
+                const uint32_t* list = list_.as<uint32_t>();
+                void* args[] = {(void*)&g, (void*)&list};
+                int per_sm = 0;
+                AVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colour_rounds_kernel, 256, 0));
+                if (per_sm < 1) return err_->fail(AVN_ERR_CUDA, "contacts_step: the colouring kernel does not fit the device");
+                AVN_CUDA(cudaLaunchCooperativeKernel((const void*)colour_rounds_kernel, dim3(sm_count_), dim3(256), args, 0, stream_));
+            }
+            overflow_list_kernel<<<1, 32, 0, stream_>>>(g, list_.as<uint32_t>());
+            finalize_rows_kernel<<<rb, 256, 0, stream_>>>(g, k0_.as<uint32_t>(), v0_.as<uint32_t>());
+            radix_pass(int(hw_));   // -> k1_ sorted colour keys, v1_ = the colour-major list (ascending ContactId inside a colour)
+            color_offsets_kernel<<<1, 64, 0, stream_>>>(g, k1_.as<uint32_t>(), v1_.as<uint32_t>());
+            gather_graph_kernel<S><<<std::min<unsigned>(rb, unsigned(sm_count_) * 8u), 256, 0, stream_>>>(g, v1_.as<uint32_t>(), have_fr_ ? fr_.as<double>() : nullptr,
+                                                                                                        have_re_ ? re_.as<double>() : nullptr, m_b1_.as<int32_t>(),
+                                                                                                        m_b2_.as<int32_t>(), m_fr_.as<S>(), m_re_.as<S>());
+            AVN_CUDA(cudaGetLastError());
+        }
+        AVN_CUDA(cudaMemcpyAsync(h_ctr_, ctr_.p, sizeof(GraphCounters), cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        if (h_ctr_->aborted) return err_->fail(AVN_ERR_CUDA, "contacts_step: the colouring did not converge");
+        live_n_ -= h_ctr_->removed;
+        if (hw_ && (added || h_ctr_->removed || table_dirty_)) {   // ContactGraph::pair_set for the next broad phase
+            AVN_CUDA(cudaMemsetAsync(table_.p, 0, (table_mask_ + 1) * sizeof(uint64_t), stream_));
+            pair_set_kernel<<<(hw_ + 255) / 256, 256, 0, stream_>>>(g, table_.as<uint64_t>(), table_mask_);
+            AVN_CUDA(cudaGetLastError());
+            table_dirty_ = false;
+        }
+        *out = AvnContactStep{};
+        out->rows_high_water = hw_; out->rows_live = live_n_; out->pairs_added = added; out->pairs_removed = h_ctr_->removed;
+        out->started_touching = h_ctr_->started; out->stopped_touching = h_ctr_->stopped; out->manifold_count = h_ctr_->manifolds;
+        out->colouring_rounds = h_ctr_->rounds; out->any_restitution = h_ctr_->any_restitution;
+        memcpy(out->color_offsets, h_ctr_->color_offsets, sizeof out->color_offsets);
+        graph_ = ResidentGraph{};
+        graph_.count = h_ctr_->manifolds; graph_.any_restitution = h_ctr_->any_restitution;
+        memcpy(graph_.color_offsets, h_ctr_->color_offsets, sizeof graph_.color_offsets);
+        graph_.edge = v1_.as<uint32_t>(); graph_.body1 = m_b1_.as<int32_t>(); graph_.body2 = m_b2_.as<int32_t>(); graph_.friction = m_fr_.p; graph_.restitution = m_re_.p;
+        return AVN_OK;
+    }
+
+    AvnStatus graph_view(ResidentGraph* out) override { *out = graph_; return AVN_OK; }
+    void pair_set(const uint64_t** table, uint64_t* mask) override {
+        *table = (configured_ && table_.p && !table_dirty_) ? table_.as<uint64_t>() : nullptr;
+        *mask = table_mask_;
+    }
+    AvnStatus download_graph(uint32_t capacity, uint32_t* c1, uint32_t* c2, uint8_t* live, uint8_t* touching, int8_t* colour, uint32_t* edge_list) override {
+        const size_t n = std::min(capacity, E_);
+        if (n) {
+            if (c1) AVN_CUDA(cudaMemcpyAsync(c1, c1_.p, n * 4, cudaMemcpyDeviceToHost, stream_));
+            if (c2) AVN_CUDA(cudaMemcpyAsync(c2, c2_.p, n * 4, cudaMemcpyDeviceToHost, stream_));
+            if (live) AVN_CUDA(cudaMemcpyAsync(live, live_.p, n, cudaMemcpyDeviceToHost, stream_));
+            if (touching) AVN_CUDA(cudaMemcpyAsync(touching, touching_.p, n, cudaMemcpyDeviceToHost, stream_));
+            if (colour) AVN_CUDA(cudaMemcpyAsync(colour, colour_.p, n, cudaMemcpyDeviceToHost, stream_));
+        }
+        if (edge_list && graph_.count) AVN_CUDA(cudaMemcpyAsync(edge_list, graph_.edge, size_t(graph_.count) * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        if (colour) for (size_t e = 0; e < n; ++e) colour[e] = int8_t(int(uint8_t(colour[e])) - 1);   // stored + 1 (0 = none)
         return AVN_OK;
     }
 
@@ -146,6 +514,58 @@ class Contacts final : public ContactsBase {
     }
 
    private:
+    // geometry + match_contacts over rows [0, n)
+    AvnStatus launch_narrow(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t n) {
+        const size_t C = in->collider_count, B = in->body_count;
+        if (!in->dims || !in->position || !in->rotation || !in->linear_velocity || !in->angular_velocity || !in->aabb_min || !in->aabb_max)
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_narrow_phase: dims, position, rotation, velocities and AABBs are required");
+        NarrowEdgeArgs<S> a{};
+        a.r = rows();
+        a.r.E = int(n);
+        AvnStatus st;
+#define UPC(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
+        UPC(i_shape_, in->shape, C, uint8_t, a.shape);
+        UPC(i_dims_, in->dims, 3 * C, S, a.dims);
+        UPC(i_pos_, in->position, 3 * C, S, a.pos);
+        UPC(i_rot_, in->rotation, 4 * C, S, a.rot);
+        UPC(i_lv_, in->linear_velocity, 3 * B, S, a.lv);
+        UPC(i_av_, in->angular_velocity, 3 * B, S, a.av);
+        UPC(i_amin_, in->aabb_min, 3 * C, S, a.amin);
+        UPC(i_amax_, in->aabb_max, 3 * C, S, a.amax);
+#undef UPC
+        a.dt = prm->dt;
+        a.tol = prm->contact_tolerance;
+        a.thr2 = (0.1 * length_unit) * (0.1 * length_unit);
+        a.match = match_contacts ? 1 : 0;
+        narrow_edges_kernel<S><<<(n + 127) / 128, 128, 0, stream_>>>(a);
+        AVN_CUDA(cudaGetLastError());
+        return AVN_OK;
+    }
+    // one stable 8-bit radix pass (digit = the low byte of the key): (k0_, v0_) -> (k1_, v1_)
+    void radix_pass(int n) {
+        const int nblocks = (n + RS_TILE - 1) / RS_TILE;
+        rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, stream_>>>(k0_.as<uint32_t>(), n, 0, hist_.as<uint32_t>(), nblocks);
+        if (nblocks <= RS_FUSE_MAX_BLOCKS) {
+            rs_scatter<uint32_t, true><<<nblocks, RS_THREADS, 0, stream_>>>(k0_.as<uint32_t>(), v0_.as<uint32_t>(), n, 0, hist_.as<uint32_t>(), nblocks, k1_.as<uint32_t>(),
+                                                                            v1_.as<uint32_t>());
+        } else {
+            rs_scan<<<1, 1024, 0, stream_>>>(hist_.as<uint32_t>(), 256 * nblocks);
+            rs_scatter<uint32_t, false><<<nblocks, RS_THREADS, 0, stream_>>>(k0_.as<uint32_t>(), v0_.as<uint32_t>(), n, 0, hist_.as<uint32_t>(), nblocks, k1_.as<uint32_t>(),
+                                                                             v1_.as<uint32_t>());
+        }
+    }
+    GraphRows graph_rows() {
+        GraphRows g{};
+        g.hw = int(hw_);
+        g.c1 = c1_.as<uint32_t>(); g.c2 = c2_.as<uint32_t>(); g.b1 = b1_.as<uint32_t>(); g.b2 = b2_.as<uint32_t>();
+        g.live = live_.as<uint8_t>(); g.count = count_.as<uint8_t>(); g.disjoint = disjoint_.as<uint8_t>(); g.prev_count = prev_count_.as<uint8_t>();
+        g.pflags = pflags_.as<uint8_t>(); g.touching = touching_.as<uint8_t>(); g.colour = colour_.as<uint8_t>(); g.change = change_.as<uint8_t>();
+        g.old_colour = old_colour_.as<uint8_t>(); g.ovf_pos = ovf_pos_.as<uint32_t>(); g.ovf = ovf_.as<uint32_t>();
+        g.body_kind = kind_.as<uint8_t>(); g.n_bodies = int(n_bodies_);
+        g.body_bits = body_bits_.as<uint32_t>(); g.body_min = body_min_.as<unsigned long long>();
+        g.ctr = ctr_.as<GraphCounters>();
+        return g;
+    }
     EdgeRows<S> rows() {
         EdgeRows<S> r{};
         r.E = int(E_);
@@ -170,6 +590,16 @@ class Contacts final : public ContactsBase {
     DevBuf c1_, c2_, b1_, b2_, live_, count_, disjoint_, normal_, a1_, a2_, pen_, ns_, prev_count_, prev_a1_, prev_a2_, ws_n_in_, ws_t_in_, ws_n_out_, ws_t_out_,
         nimp_in_, nimp_out_, stage_;
     DevBuf i_shape_, i_dims_, i_pos_, i_rot_, i_lv_, i_av_, i_amin_, i_amax_;
+    // graphs
+    using ResidentGraph = ContactsBase::ResidentGraph;
+    DevBuf pflags_, touching_, colour_, change_, old_colour_, ovf_pos_, ovf_, kind_, fr_, re_, body_bits_, body_min_, ctr_, k0_, k1_, v0_, v1_, hist_, list_, m_b1_, m_b2_,
+        m_fr_, m_re_, table_;
+    GraphCounters* h_ctr_ = nullptr;
+    ResidentGraph graph_{};
+    uint64_t table_mask_ = 0;
+    uint32_t hw_ = 0, live_n_ = 0, n_bodies_ = 0, n_colliders_ = 0;
+    int sm_count_ = 148;
+    bool configured_ = false, have_fr_ = false, have_re_ = false, table_dirty_ = true;
 };
 
 }  // namespace

@@ -73,6 +73,8 @@ struct SolverBase {
     virtual AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bodies, AvnEdgeManifolds* manifolds, AvnJointSet* joints) = 0;
     // the same with the edge-indexed columns already on the device (ContactsBase::view / outputs): only the graph columns are uploaded
     virtual AvnStatus upload_graph(const AvnStepParams* prm, AvnBodyColumns* bodies, const AvnEdgeManifolds* graph, ContactsBase* contacts, AvnJointSet* joints) = 0;
+    // the same with the colour-major list on the device as well (ContactsBase::graph_view): nothing of the constraints crosses the bus
+    virtual AvnStatus upload_resident(const AvnStepParams* prm, AvnBodyColumns* bodies, ContactsBase* contacts, AvnJointSet* joints) = 0;
     virtual AvnStatus run() = 0;
     virtual AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) = 0;
     virtual AvnStatus set_boundary(const AvnBoundary* bnd) = 0;
@@ -85,11 +87,25 @@ struct SolverBase {
     virtual AvnStatus download() = 0;
     virtual void timings(AvnTimings* t) const = 0;
 };
+// the new pairs of the last broad-phase run where the run left them (device memory); count is known on the host after the run settled
+struct DevicePairs {
+    uint64_t count = 0;
+    const uint32_t* c1 = nullptr; const uint32_t* c2 = nullptr; const uint32_t* b1 = nullptr; const uint32_t* b2 = nullptr;
+    const uint8_t* flags = nullptr;
+};
+
 struct BroadphaseBase {
     virtual ~BroadphaseBase() {}
     virtual AvnStatus upload(AvnAabbColumns* aabbs) = 0;
     virtual AvnStatus run() = 0;
     virtual AvnStatus download(AvnPairList* out) = 0;
+    // device-resident pipeline: the pairs stay on the device (the contact store takes them from there); only the persistent order and the
+    // pair count go to the host
+    virtual AvnStatus device_pairs(DevicePairs* out) = 0;
+    virtual AvnStatus download_order(uint64_t* out_pair_count) = 0;
+    // ContactGraph::pair_set kept by the contact store on the device: used as the "existing pairs" set of every later upload that
+    // brings no host key list (table == NULL switches back)
+    virtual void set_existing_device(const uint64_t* table, uint64_t mask) = 0;
     virtual void timings(AvnTimings* t) const = 0;
 };
 
@@ -116,6 +132,19 @@ struct ContactsBase {
     virtual void outputs(void** ws_n, void** ws_t, void** nimp) = 0;         // device pointers store_contact_impulses writes
     virtual uint32_t capacity() const = 0;
     virtual AvnStatus download_impulses(void* ws_n, void* ws_t, void* nimp) = 0;
+    // ---- the ContactGraph + ConstraintGraph on the device (contacts.cu)
+    virtual AvnStatus configure(const AvnContactGraphConfig* cfg) = 0;
+    virtual AvnStatus step(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, const DevicePairs* new_pairs,
+                           AvnContactStep* out) = 0;
+    struct ResidentGraph {          // device pointers of the colour-major list the last step() built
+        uint32_t count = 0, any_restitution = 0;
+        uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1] = {};
+        const uint32_t* edge = nullptr; const int32_t* body1 = nullptr; const int32_t* body2 = nullptr;
+        const void* friction = nullptr; const void* restitution = nullptr;
+    };
+    virtual AvnStatus graph_view(ResidentGraph* out) = 0;
+    virtual void pair_set(const uint64_t** table, uint64_t* mask) = 0;
+    virtual AvnStatus download_graph(uint32_t capacity, uint32_t* c1, uint32_t* c2, uint8_t* live, uint8_t* touching, int8_t* colour, uint32_t* edge_list) = 0;
 };
 ContactsBase* make_contacts(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
 

@@ -70,6 +70,11 @@ struct DevSolver {
     unsigned int* ver;                           // [B+1] per-body event counter (wavefront mode)
     int* deg;                                    // [B+1] contact constraints touching the body (wavefront mode)
     int* stamp;                                  // [B+1] 1 + last colour that ranked the body: detects a body listed twice in one colour
+    // body-centric warm start (f32 wavefront schedule, wave32_dev.cuh "w32_ivw_item"): per body the constraints that move it, in colour order
+    int* wdeg;                                   // [B+1] adjacency entries of the body (sides whose inertia is not zeroed)
+    int* wpts;                                   // [B+1] contact points over those entries
+    uint2* adj;                                  // [ADJ_MAX][adj_stride] rank-major: {slot, WA_* | first point << 8}; NULL = slot-centric warm start
+    int adj_stride;
     int substeps, iters, rest_iters, fast_trig, match_contacts;
     S h, dt, max_overlap_speed, warm_coeff, rest_threshold, joint_force_rhs;
     S gx, gy, gz;
@@ -332,27 +337,35 @@ __device__ __forceinline__ void apply_impulse(V3<S>& v1, V3<S>& w1, V3<S>& v2, V
 // Items are handed to warps in the global schedule order, all warps are co-resident (cooperative launch), and an item
 // only ever waits for items that precede it in that order, so the earliest unfinished item can always run: no deadlock.
 struct WaveStep { int substep, iters; };
+// flag words behind any_restitution: [0] some restitution coefficient != 0, [1] WAVE_* event, [2] a body has more than ADJ_MAX adjacency
+// entries (the step keeps the slot-centric warm start), [3] spare, then (8-byte aligned) the optional trace counters
+enum { FLAG_RESTITUTION = 0, FLAG_WAVE = 1, FLAG_ADJ_OVERFLOW = 2, FLAG_WORDS = 4 };
+// adjacency of the body-centric warm start: at most ADJ_MAX constraints per body (a cube in a brick stack has 8-10)
+constexpr int ADJ_MAX = 32;
+enum { WA_NP_MASK = 0x7, WA_TANGENT = 1 << 3, WA_SIDE2 = 1 << 4, WA_Q0_SHIFT = 8 };
 // Optional latency trace of the wavefront items (build with -DAVN_WAVE_TRACE; scripts/wave_trace.py): per-warp SM-cycle sums of
 // [0] dependency wait  [1] acquire fence + mutable loads + staged rows  [2] arithmetic  [3] stores + release fence + publish,
-// [4] item count.  The buffer is 8 unsigned long long counters behind the two int flags of any_restitution.
+// [4] item count.  The buffer is 8 unsigned long long counters behind the FLAG_WORDS int flags of any_restitution.
 #ifdef AVN_WAVE_TRACE
 #define AVN_TRACE_T(var) const long long var = clock64()
-#define AVN_TRACE_ADD(d, i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>((d).any_restitution + 2) + (i), (unsigned long long)(v)); } while (0)
+#define AVN_TRACE_ADD(d, i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>((d).any_restitution + FLAG_WORDS) + (i), (unsigned long long)(v)); } while (0)
 #else
 #define AVN_TRACE_T(var)
 #define AVN_TRACE_ADD(d, i, v)
 #endif
-__device__ __forceinline__ unsigned events_per_substep(int k, int iters) { return 2u + unsigned(2 + iters) * unsigned(k); }
+// wf = 1: the warm start is k events of the body (one per constraint, slot-centric warm items); wf = 0: it is part of the body's
+// integrate_velocities event (body-centric warm start, wave32_dev.cuh)
+__device__ __forceinline__ unsigned events_per_substep(int k, int iters, int wf = 1) { return 2u + unsigned(1 + wf + iters) * unsigned(k); }
 enum { WV_IV = 0, WV_WARM = 1, WV_SOLVE = 2, WV_IP = 3, WV_RELAX = 4 };
 // position of an item in its body's event sequence
-__device__ __forceinline__ unsigned wave_event(int kind, int it, int s, int iters, int k, int r) {
-    unsigned base = unsigned(s) * events_per_substep(k, iters);
+__device__ __forceinline__ unsigned wave_event(int kind, int it, int s, int iters, int k, int r, int wf = 1) {
+    unsigned base = unsigned(s) * events_per_substep(k, iters, wf);
     switch (kind) {
         case WV_IV: return base;
         case WV_WARM: return base + 1u + r;
-        case WV_SOLVE: return base + 1u + unsigned(1 + it) * k + r;
-        case WV_IP: return base + 1u + unsigned(1 + iters) * k;
-        default: return base + 2u + unsigned(1 + iters) * k + r;
+        case WV_SOLVE: return base + 1u + unsigned(wf + it) * k + r;
+        case WV_IP: return base + 1u + unsigned(wf + iters) * k;
+        default: return base + 2u + unsigned(wf + iters) * k + r;
     }
 }
 // counters: relaxed gpu-scope accesses bracketed by __threadfence() (message passing).  ld.acquire.gpu / st.release.gpu on the
@@ -786,6 +799,22 @@ __device__ __forceinline__ void wave_rank_item(const DevSolver<S>& d, int slot) 
     if (info & CI_VER1) { bad |= atomicExch(&d.stamp[b1], colour + 1) == colour + 1; r1 = atomicAdd(&d.deg[b1], 1); }
     if (info & CI_VER2) { bad |= atomicExch(&d.stamp[b2], colour + 1) == colour + 1; r2 = atomicAdd(&d.deg[b2], 1); }
     if (bad || r1 > 0xfe || r2 > 0xfe) d.any_restitution[1] = WAVE_BAD_COLOURING;
+    if (d.adj) {
+        // adjacency of the body-centric warm start: one entry per side this constraint moves (a side with zeroed inertia keeps its
+        // velocity bit for bit).  The colours are ranked one after the other, so entry order = colour order = the reference's order.
+        const unsigned meta = unsigned(info & CI_NP_MASK) | ((info & CI_TANGENT) ? WA_TANGENT : 0u);
+        const int np = info & CI_NP_MASK;
+        if ((info & CI_VER1) && !(info & CI_ZERO1)) {
+            const int j = atomicAdd(&d.wdeg[b1], 1), q0 = atomicAdd(&d.wpts[b1], np);
+            if (j < ADJ_MAX) d.adj[size_t(j) * d.adj_stride + b1] = make_uint2(unsigned(slot), meta | (unsigned(q0) << WA_Q0_SHIFT));
+            else d.any_restitution[FLAG_ADJ_OVERFLOW] = 1;
+        }
+        if ((info & CI_VER2) && !(info & CI_ZERO2)) {
+            const int j = atomicAdd(&d.wdeg[b2], 1), q0 = atomicAdd(&d.wpts[b2], np);
+            if (j < ADJ_MAX) d.adj[size_t(j) * d.adj_stride + b2] = make_uint2(unsigned(slot), meta | WA_SIDE2 | (unsigned(q0) << WA_Q0_SHIFT));
+            else d.any_restitution[FLAG_ADJ_OVERFLOW] = 1;
+        }
+    }
     hidx.w = int_as(S(0), (r1 & 0xff) | ((r2 & 0xff) << 16));
     st4(&c[CP_IDX * MP], hidx);
 }

@@ -58,6 +58,7 @@ class Solver final : public SolverBase {
         mega_bps_ = bps ? atoi(bps) : (sizeof(S) == 8 ? 2 : 3);
         if (mega_bps_ < 2 || mega_bps_ > 4) mega_bps_ = 3;
         if (mode && !strcmp(mode, "wave")) force_wave_ = true;
+        if (const char* w = getenv("AVN_WARM_BY_BODY")) warm_by_body_ = atoi(w) != 0;
         coop_ok_ = coop_ok_ && select_megakernel(AVN_MAX_MANIFOLD_POINTS);
         for (auto& e : ev_) cudaEventCreate(&e);
     }
@@ -69,6 +70,7 @@ class Solver final : public SolverBase {
     AvnStatus upload(const AvnStepParams* prm, AvnBodyColumns* bc, AvnManifoldColumns* mc, AvnJointSet* js) override;
     AvnStatus upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, AvnEdgeManifolds* em, AvnJointSet* js) override;
     AvnStatus upload_graph(const AvnStepParams* prm, AvnBodyColumns* bc, const AvnEdgeManifolds* graph, ContactsBase* contacts, AvnJointSet* js) override;
+    AvnStatus upload_resident(const AvnStepParams* prm, AvnBodyColumns* bc, ContactsBase* contacts, AvnJointSet* js) override;
     AvnStatus run_range(uint32_t first, uint32_t count, uint32_t flags) override;
     AvnStatus set_boundary(const AvnBoundary* bnd) override;
     AvnStatus boundary_snapshot() override;
@@ -182,6 +184,8 @@ class Solver final : public SolverBase {
         // contact store, and store_contact_impulses writes to out_* (device) instead of buffers of this solver; nothing of them is copied
         bool device = false;
         bool reuse_graph = false;   // upload_graph: the colour-major list (edge, body1, body2, friction, restitution) of the previous upload is still valid
+        bool device_list = false;   // upload_resident: edge, body1, body2, friction, restitution are DEVICE pointers too (the contact store's list)
+        bool list_restitution = false;
         void* out_ws_normal = nullptr; void* out_ws_tangent = nullptr; void* out_normal_impulse = nullptr;
     };
     AvnStatus upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, const ManifoldSource* src, AvnJointSet* js);
@@ -197,7 +201,11 @@ class Solver final : public SolverBase {
     DevBuf o_pos_, o_rot_, o_lv_, o_av_;
     DevBuf s_inr_, s_itg_, s_pre_;
     DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_, p_nin_, p_own_, p_owt_;
-    DevBuf hot_, c_flag_;
+    DevBuf hot_, c_flag_, adj_;
+    // body-centric warm start (wave32_dev.cuh w32_ivw_item): bit-identical, 26 -> 18 dependency levels per substep, but measured SLOWER where
+    // it matters (100k cubes 1.62 -> 1.98 ms: the item is a chain of dependent gathers, 4x more chunks than integrate_velocities had) and
+    // only 4 % faster on the chain-bound 10k scene (0.739 -> 0.708 ms).  Off by default; AVN_WARM_BY_BODY=1 enables it.
+    bool warm_by_body_ = false;
     size_t hot_bytes_ = 0;
     DevBuf j_type_, j_index_, j_level_, j_planes_;
     DevBuf jcol_[AVN_JOINT_TYPE_COUNT][12], jb1_[AVN_JOINT_TYPE_COUNT], jb2_[AVN_JOINT_TYPE_COUNT], jle_[AVN_JOINT_TYPE_COUNT],
@@ -253,6 +261,30 @@ AvnStatus Solver<S>::upload_edges(const AvnStepParams* prm, AvnBodyColumns* bc, 
     src.normal = em->normal; src.edge = em->edge; src.edge_point_count = em->point_count;
     src.anchor1 = em->anchor1; src.anchor2 = em->anchor2; src.penetration = em->penetration; src.normal_speed = em->normal_speed;
     src.ws_normal = em->warm_start_normal_impulse; src.ws_tangent = em->warm_start_tangent_impulse; src.normal_impulse = em->normal_impulse;
+    return upload_impl(prm, bc, &src, js);
+}
+
+template <class S>
+AvnStatus Solver<S>::upload_resident(const AvnStepParams* prm, AvnBodyColumns* bc, ContactsBase* contacts, AvnJointSet* js) {
+    if (!contacts) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "upload_resident: no contact store");
+    ContactsBase::ResidentGraph g;
+    AvnStatus st = contacts->graph_view(&g);
+    if (st != AVN_OK) return st;
+    graph_on_device_ = false;
+    if (g.count == 0) return upload_impl(prm, bc, nullptr, js);
+    AvnEdgeManifolds v{};
+    if ((st = contacts->view(&v)) != AVN_OK) return st;
+    ManifoldSource src;
+    src.M = g.count; src.P = size_t(4) * v.edge_capacity; src.normal_rows = v.edge_capacity;
+    src.color_offsets = g.color_offsets; src.body1 = g.body1; src.body2 = g.body2; src.friction = g.friction; src.restitution = g.restitution;
+    src.edge = g.edge;
+    src.device = true;
+    src.device_list = true;
+    src.list_restitution = g.any_restitution != 0;
+    src.normal = v.normal; src.edge_point_count = v.point_count;
+    src.anchor1 = v.anchor1; src.anchor2 = v.anchor2; src.penetration = v.penetration; src.normal_speed = v.normal_speed;
+    src.ws_normal = v.warm_start_normal_impulse; src.ws_tangent = v.warm_start_tangent_impulse; src.normal_impulse = v.normal_impulse;
+    contacts->outputs(&src.out_ws_normal, &src.out_ws_tangent, &src.out_normal_impulse);
     return upload_impl(prm, bc, &src, js);
 }
 
@@ -377,7 +409,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
     hb_ = *bc;
     // ---- manifolds
     have_m_ = mc != nullptr && mc->M > 0;
-    AVN_CUDA(c_flag_.ensure(2 * sizeof(int) + 8 * sizeof(unsigned long long)));  // [0] any restitution, [1] wavefront watchdog, then the optional trace counters
+    AVN_CUDA(c_flag_.ensure(FLAG_WORDS * sizeof(int) + 8 * sizeof(unsigned long long)));  // FLAG_* words (solver_dev.cuh), then the optional trace counters
     d.any_restitution = c_flag_.as<int>();
     if (have_m_) {
         const size_t M = mc->M, P = mc->P;
@@ -407,7 +439,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
                 return err_->fail(AVN_ERR_INVALID_ARGUMENT, "manifolds: at most %d points per manifold, point ranges must not decrease", AVN_MAX_MANIFOLD_POINTS);
             max_np_ = int(std::max<uint32_t>(widest, 1));
         }
-        if (!mc->reuse_graph) {   // body indices are gathered through on the device (inr[2*b], vel[2*b], ver[b] ...): anything outside [AVN_NO_BODY, B) would read and
+        if (!mc->reuse_graph && !mc->device_list) {   // body indices are gathered through on the device (inr[2*b], vel[2*b], ver[b] ...): anything outside [AVN_NO_BODY, B) would read and
             // write out of bounds, so it is rejected here (streaming pass over two int columns)
             const int32_t* hb1 = mc->body1; const int32_t* hb2 = mc->body2;
             const int64_t Bi = int64_t(B);
@@ -433,7 +465,10 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             d.color_off[AVN_GRAPH_COLOR_COUNT] = slot;
             d.Mpad = std::max(slot, 32);
         }
-        if (mc->reuse_graph) {   // the list of the previous avn_solver_upload_graph is still in these buffers
+        if (mc->device_list) {   // the contact store's list (its bodies are the rows' bodies, validated when the pairs were formed)
+            d.m_body1 = reinterpret_cast<const int*>(mc->body1); d.m_body2 = reinterpret_cast<const int*>(mc->body2);
+            d.m_friction = static_cast<const S*>(mc->friction); d.m_restitution = static_cast<const S*>(mc->restitution);
+        } else if (mc->reuse_graph) {   // the list of the previous avn_solver_upload_graph is still in these buffers
             d.m_body1 = m_b1_.as<int>(); d.m_body2 = m_b2_.as<int>(); d.m_friction = m_f_.as<S>(); d.m_restitution = m_r_.as<S>();
         } else {
             UP(m_b1_, mc->body1, M, int, m_body1);
@@ -449,7 +484,8 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
             d.m_src = nullptr;
         } else {
             const uint8_t* d_count = nullptr;
-            if (mc->reuse_graph) d.m_src = m_edge_.as<uint32_t>(); else UP(m_edge_, mc->edge, M, uint32_t, m_src);
+            if (mc->device_list) d.m_src = mc->edge;
+            else if (mc->reuse_graph) d.m_src = m_edge_.as<uint32_t>(); else UP(m_edge_, mc->edge, M, uint32_t, m_src);
             if (mc->device) d_count = mc->edge_point_count;
             else if ((st = up<uint8_t>(e_cnt_, mc->edge_point_count, mc->normal_rows, &d_count)) != AVN_OK) return st;
             AVN_CUDA(m_pbegin_.ensure(M * sizeof(uint32_t)));
@@ -489,7 +525,9 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         }
 
         hm_ = *mc;
-        if (mc->reuse_graph) {
+        if (mc->device_list) {
+            host_any_restitution_ = mc->list_restitution;
+        } else if (mc->reuse_graph) {
             host_any_restitution_ = graph_restitution_;
         } else {
             host_any_restitution_ = false;
@@ -512,6 +550,16 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
         d.pcr = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr; base += pcr_b;
         d.cst = have_m_ ? reinterpret_cast<Vec4<S>*>(base) : nullptr;
         hot_bytes_ = vel_b + dlt_b + ver_b + deg_b + pcr_b;
+        // adjacency of the body-centric warm start (f32 wavefront schedule; experiment, AVN_WARM_BY_BODY=1)
+        d.adj = nullptr; d.wdeg = nullptr; d.wpts = nullptr; d.adj_stride = 0;
+        if (sizeof(S) == 4 && have_m_ && warm_by_body_) {
+            const size_t stride = (B + 1 + 31) & ~size_t(31);
+            AVN_CUDA(adj_.ensure(size_t(ADJ_MAX) * stride * sizeof(uint2) + 2 * (B + 1) * sizeof(int)));
+            d.adj = adj_.as<uint2>();
+            d.wdeg = reinterpret_cast<int*>(d.adj + size_t(ADJ_MAX) * stride);
+            d.wpts = d.wdeg + (B + 1);
+            d.adj_stride = int(stride);
+        }
     }
     // ---- joints
     have_j_ = false;
@@ -588,7 +636,7 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
     if (prepare) {
         launches_ = 0;
         cudaEventRecord(ev_[EV_RUN0], stream_);
-        AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, 2 * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
+        AVN_CUDA(cudaMemsetAsync(dev_.any_restitution, 0, FLAG_WORDS * sizeof(int) + 8 * sizeof(unsigned long long), stream_));
         // wavefront substep loop: contacts only (joints keep the level-by-level barriers), empty overflow colour.  It wins when the step
         // is bound by the per-body dependency chain, i.e. when a colour does not fill the machine; with colours several times the
         // resident thread count (1M-sphere scene) the barriers are cheap and the counters are pure overhead.
@@ -603,6 +651,7 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
         if (dev_.wave) {
             AVN_CUDA(cudaMemsetAsync(dev_.ver, 0, (size_t(dev_.B) + 1) * sizeof(unsigned), stream_));
             AVN_CUDA(cudaMemsetAsync(dev_.deg, 0, 2 * (size_t(dev_.B) + 1) * sizeof(int), stream_));   // deg + stamp
+            if (dev_.adj) AVN_CUDA(cudaMemsetAsync(dev_.wdeg, 0, 2 * (size_t(dev_.B) + 1) * sizeof(int), stream_));   // wdeg + wpts
         }
         mega_step_ = mega;
     } else {
@@ -903,7 +952,7 @@ AvnStatus Solver<S>::download() {
 #ifdef AVN_WAVE_TRACE
     {
         unsigned long long tr[8];
-        cudaMemcpy(tr, dev_.any_restitution + 2, sizeof tr, cudaMemcpyDeviceToHost);
+        cudaMemcpy(tr, dev_.any_restitution + FLAG_WORDS, sizeof tr, cudaMemcpyDeviceToHost);
         if (tr[4]) fprintf(stderr, "[avn wave trace] item-warps %llu  avg cycles: wait(records) %.0f  wait(delta)+staging %.0f  separations/load %.0f  compute %.0f  store+publish %.0f\n", tr[4],
                            double(tr[0]) / tr[4], double(tr[5]) / tr[4], double(tr[1]) / tr[4], double(tr[2]) / tr[4], double(tr[3]) / tr[4]);
     }

@@ -111,11 +111,13 @@ __device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s, 
 // (BPS and MAXP are template parameters of all of them only so that every megakernel variant owns its copies: ptxas 12.9 segfaults when two
 //  kernels share a __noinline__ function that contains the 256-bit accesses)
 template <int PASS, int MAXP, int BPS>
-__device__ __noinline__ void wave32_contact_chunk(const DevSolver<float>& d, int slot, int s, int it, bool active) {
-    w32_contact_item<PASS, MAXP>(d, slot, s, it, active);
+__device__ __noinline__ void wave32_contact_chunk(const DevSolver<float>& d, int slot, int s, int it, bool active, int wf) {
+    w32_contact_item<PASS, MAXP>(d, slot, s, it, active, wf);
 }
 template <int BPS, int MAXP> __device__ __noinline__ void wave32_iv_chunk(const DevSolver<float>& d, int i, int s, bool active) { w32_integrate_velocity_item(d, i, s, active); }
-template <int BPS, int MAXP> __device__ __noinline__ void wave32_ip_chunk(const DevSolver<float>& d, int i, int s, bool active) { w32_integrate_position_item(d, i, s, active); }
+template <int BPS, int MAXP> __device__ __noinline__ void wave32_ip_chunk(const DevSolver<float>& d, int i, int s, bool active, int wf) { w32_integrate_position_item(d, i, s, active, wf); }
+// integrate_velocities + the body's warm starts (8 bodies per warp, wave32_dev.cuh)
+template <int BPS, int MAXP> __device__ __noinline__ void wave32_ivw_chunk(const DevSolver<float>& d, int chunk, int s) { w32_ivw_item<MAXP>(d, chunk, s); }
 #ifdef AVN_WAVE_COUNTERS_F32
 constexpr bool WAVE_RECORDS_F32 = false;
 #else
@@ -124,17 +126,20 @@ constexpr bool WAVE_RECORDS_F32 = true;
 template <class S> struct UseRecords { static constexpr bool value = false; };
 template <> struct UseRecords<float> { static constexpr bool value = WAVE_RECORDS_F32; };
 template <class S, int PASS, int MAXP, int BPS>
-__device__ __forceinline__ void wave_contact(const DevSolver<S>& d, int slot, int s, int it, bool active) {
-    if constexpr (UseRecords<S>::value) wave32_contact_chunk<PASS, MAXP, BPS>(d, slot, s, it, active);
+__device__ __forceinline__ void wave_contact(const DevSolver<S>& d, int slot, int s, int it, bool active, int wf) {
+    if constexpr (UseRecords<S>::value) wave32_contact_chunk<PASS, MAXP, BPS>(d, slot, s, it, active, wf);
     else wave_contact_chunk<S, PASS, MAXP>(d, slot, s, it, active);
 }
 template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_iv(const DevSolver<S>& d, int i, int s, bool active) {
     if constexpr (UseRecords<S>::value) wave32_iv_chunk<BPS, MAXP>(d, i, s, active);
     else wave_iv_chunk<S>(d, i, s, active);
 }
-template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_ip(const DevSolver<S>& d, int i, int s, bool active) {
-    if constexpr (UseRecords<S>::value) wave32_ip_chunk<BPS, MAXP>(d, i, s, active);
+template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_ip(const DevSolver<S>& d, int i, int s, bool active, int wf) {
+    if constexpr (UseRecords<S>::value) wave32_ip_chunk<BPS, MAXP>(d, i, s, active, wf);
     else wave_ip_chunk<S>(d, i, s, active);
+}
+template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_ivw(const DevSolver<S>& d, int chunk, int s) {
+    if constexpr (UseRecords<S>::value) wave32_ivw_chunk<BPS, MAXP>(d, chunk, s);
 }
 
 // EXPERIMENT (off): L2 prefetch of the immutable constraint rows of the chunk this warp processes one iteration from now.  The idea: at
@@ -157,15 +162,22 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int body_chunks = (d.B + WAVE_CHUNK - 1) / WAVE_CHUNK, slot_chunks = d.Mpad / WAVE_CHUNK;
-    const int passes = 2 + d.iters;                                  // warm, iters x solve, relax
-    const long long per_substep = 2LL * body_chunks + (long long)passes * slot_chunks;
+    // body-centric warm start (f32 records): the first phase of a substep is integrate_velocities + warm start, 8 bodies per warp, and the
+    // slot-centric warm pass disappears.  The adjacency it needs was built by the rank pass; a body with too many constraints (flag, read
+    // after a grid barrier: uniform over the grid) keeps the slot-centric schedule.
+    const bool wbb = UseRecords<S>::value && WAVE_CHUNK == 32 && d.adj != nullptr &&
+                     *reinterpret_cast<volatile int*>(d.any_restitution + FLAG_ADJ_OVERFLOW) == 0;
+    const int wf = wbb ? 0 : 1;
+    const int first_chunks = wbb ? (d.B + 7) / 8 : body_chunks;
+    const int front_passes = wf + d.iters;                          // (warm,) iters x solve: the slot passes before integrate_positions
+    const long long per_substep = (long long)first_chunks + body_chunks + (long long)(front_passes + 1) * slot_chunks;
     const long long total = per_substep * d.sub_end;
     // position of a chunk inside its substep -> slot of its first item, or -1 for a body chunk (prefetch experiment)
     [[maybe_unused]] auto contact_slot_of = [&](long long r) -> int {
-        if (r < body_chunks) return -1;
-        r -= body_chunks;
-        if (r < (long long)(1 + d.iters) * slot_chunks) return int(r % slot_chunks) * WAVE_CHUNK;
-        r -= (long long)(1 + d.iters) * slot_chunks;
+        if (r < first_chunks) return -1;
+        r -= first_chunks;
+        if (r < (long long)front_passes * slot_chunks) return int(r % slot_chunks) * WAVE_CHUNK;
+        r -= (long long)front_passes * slot_chunks;
         if (r < body_chunks) return -1;
         return int(r - body_chunks) * WAVE_CHUNK;
     };
@@ -181,18 +193,22 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
             }
         }
 #endif
-        if (r < body_chunks) { wave_iv<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
-        r -= body_chunks;
-        if (r < (long long)(1 + d.iters) * slot_chunks) {
-            const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * WAVE_CHUNK + lane;
-            if (pass == 0) wave_contact<S, PASS_WARM, MAXP, BPS>(d, slot, s, 0, active);
-            else wave_contact<S, PASS_SOLVE_BIAS, MAXP, BPS>(d, slot, s, pass - 1, active);
+        if (r < first_chunks) {
+            if (wbb) wave_ivw<S, BPS, MAXP>(d, int(r), s);
+            else wave_iv<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active);
             continue;
         }
-        r -= (long long)(1 + d.iters) * slot_chunks;
-        if (r < body_chunks) { wave_ip<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active); continue; }
+        r -= first_chunks;
+        if (r < (long long)front_passes * slot_chunks) {
+            const int pass = int(r / slot_chunks), slot = int(r - (long long)pass * slot_chunks) * WAVE_CHUNK + lane;
+            if (pass < wf) wave_contact<S, PASS_WARM, MAXP, BPS>(d, slot, s, 0, active, wf);
+            else wave_contact<S, PASS_SOLVE_BIAS, MAXP, BPS>(d, slot, s, pass - wf, active, wf);
+            continue;
+        }
+        r -= (long long)front_passes * slot_chunks;
+        if (r < body_chunks) { wave_ip<S, BPS, MAXP>(d, int(r) * WAVE_CHUNK + lane, s, active, wf); continue; }
         r -= body_chunks;
-        wave_contact<S, PASS_RELAX, MAXP, BPS>(d, int(r) * WAVE_CHUNK + lane, s, 0, active);
+        wave_contact<S, PASS_RELAX, MAXP, BPS>(d, int(r) * WAVE_CHUNK + lane, s, 0, active, wf);
     }
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ unsigned w32_pc_tag(int pass, int s, int it, int iter
 // Every lane of the warp must call this (warp-collective polls).
 // ---------------------------------------------------------------------------------------------------------
 template <int PASS, int MAXP>
-__device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int slot, int s, int it, bool lane_active) {
+__device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int slot, int s, int it, bool lane_active, int wf) {
     using S = float;
     const size_t MP = size_t(d.Mpad);
     const Vec4<S>* c = d.cst + (lane_active ? slot : 0);
@@ -90,8 +90,8 @@ __device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int 
     const bool ver1 = np != 0 && (info & CI_VER1), ver2 = np != 0 && (info & CI_VER2);
     const int rk = as_int(hidx.w);
     constexpr int kind = PASS == PASS_WARM ? WV_WARM : (PASS == PASS_SOLVE_BIAS ? WV_SOLVE : WV_RELAX);
-    const unsigned e1 = wave_event(kind, it, s, d.iters, (rk >> 8) & 0xff, rk & 0xff);
-    const unsigned e2 = wave_event(kind, it, s, d.iters, (rk >> 24) & 0xff, (rk >> 16) & 0xff);
+    const unsigned e1 = wave_event(kind, it, s, d.iters, (rk >> 8) & 0xff, rk & 0xff, wf);
+    const unsigned e2 = wave_event(kind, it, s, d.iters, (rk >> 24) & 0xff, (rk >> 16) & 0xff, wf);
     const unsigned ptag = w32_pc_tag(PASS, s, it, d.iters);
     const V3<S> n = xyz(hn), t1 = xyz(ht1);
     AVN_TRACE_T(t_w0);
@@ -283,32 +283,9 @@ __device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int 
 #undef ROW_D
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// integrate_velocities + clamp_velocities (integrator/mod.rs:343-391, 467-500), wavefront mode
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void w32_integrate_velocity_item(const DevSolver<float>& d, int i, int s, bool lane_active) {
+// the arithmetic of integrate_velocities + clamp_velocities on one body (shared by the two wavefront items that run it)
+__device__ __forceinline__ void w32_integrate_velocity_math(const DevSolver<float>& d, int i, int f, const Rec32& D, V3<float>& v, V3<float>& w) {
     using S = float;
-    const bool in_range = lane_active && i < d.B;
-    int f = 0;
-    if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
-    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
-    const unsigned e = live ? wave_event(WV_IV, 0, s, d.iters, d.deg[i], 0) : 0u;
-    const bool gyro = live && (f & BF_GYRO) && !(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC);
-    Rec32 R, D;
-    R.a = mk4<S>(0, 0, 0, 0); R.b = R.a; D = R;
-    {
-        bool nr = live, nd = gyro;
-        for (unsigned spins = 0;; ++spins) {
-            if (nr) R = ld_rec(&d.vel[2 * i]);
-            if (nd) D = ld_rec(&d.dlt[2 * i]);
-            if (nr) nr = tag_of(R.a.w) != e;
-            if (nd) nd = tag_of(D.a.w) != unsigned(s);
-            if (__all_sync(0xffffffffu, !(nr || nd))) break;
-            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
-        }
-    }
-    if (!live) return;
-    V3<S> v = xyz(R.a), w = xyz(R.b);
     if (!(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC)) {
         Vec4<S> li = ld4(&d.itg[2 * i]), ai = ld4(&d.itg[2 * i + 1]);
         v = v * li.w;
@@ -352,17 +329,192 @@ __device__ __forceinline__ void w32_integrate_velocity_item(const DevSolver<floa
             st4(&d.vel_ref[2 * k + 1], mk4<S>(w.x, w.y, w.z, S(0)));
         }
     }
-    st_rec(&d.vel[2 * i], v.x, v.y, v.z, tag_lane(e + 1u), w.x, w.y, w.z, 0.f);
 }
 
-// integrate_positions (integrator/mod.rs:503-535), wavefront mode
-__device__ __forceinline__ void w32_integrate_position_item(const DevSolver<float>& d, int i, int s, bool lane_active) {
+// ---------------------------------------------------------------------------------------------------------
+// integrate_velocities + clamp_velocities (integrator/mod.rs:343-391, 467-500), wavefront mode
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void w32_integrate_velocity_item(const DevSolver<float>& d, int i, int s, bool lane_active) {
     using S = float;
     const bool in_range = lane_active && i < d.B;
     int f = 0;
     if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
     const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
-    const unsigned e = live ? wave_event(WV_IP, 0, s, d.iters, d.deg[i], 0) : 0u;
+    const unsigned e = live ? wave_event(WV_IV, 0, s, d.iters, d.deg[i], 0) : 0u;
+    const bool gyro = live && (f & BF_GYRO) && !(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC);
+    Rec32 R, D;
+    R.a = mk4<S>(0, 0, 0, 0); R.b = R.a; D = R;
+    {
+        bool nr = live, nd = gyro;
+        for (unsigned spins = 0;; ++spins) {
+            if (nr) R = ld_rec(&d.vel[2 * i]);
+            if (nd) D = ld_rec(&d.dlt[2 * i]);
+            if (nr) nr = tag_of(R.a.w) != e;
+            if (nd) nd = tag_of(D.a.w) != unsigned(s);
+            if (__all_sync(0xffffffffu, !(nr || nd))) break;
+            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+        }
+    }
+    if (!live) return;
+    V3<S> v = xyz(R.a), w = xyz(R.b);
+    w32_integrate_velocity_math(d, i, f, D, v, w);
+    st_rec(&d.vel[2 * i], v.x, v.y, v.z, tag_lane(e + 1u), w.x, w.y, w.z, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BODY-CENTRIC warm start, fused with integrate_velocities: ONE event per body and substep instead of 1 + k.
+//
+// ContactConstraint::warm_start (contact/mod.rs:223-264) changes a body's velocity by a vector that does not depend on any velocity:
+//     v -= P * inv_mass,  w -= I (r x P),   P = coeff * ((ln * n + lt.x * t1) + lt.y * t2)        (body 2: +)
+// so the k warm-start items of a body are not a true dependency chain — only the ORDER of the k * np subtractions is part of the result
+// (floating-point addition does not associate).  Four lanes per body (8 bodies per warp) compute the per-point deltas of the body's
+// constraints as soon as the impulse records of the previous substep's relax pass are there (all of it before the body's own velocity
+// record is final), park them in the warp's slice of the staging tile, and the body's first lane then runs integrate_velocities and adds
+// the deltas in colour order, point order: 6 dependent additions per point are all that is left on the critical path.  x - a == x + (-a)
+// bit for bit, so the deltas are stored with their sign.  26 -> 18 dependency levels per substep at k = 8.
+// Tile slice of a warp: rows x 128 floats; delta c of point q of body g at float (q * 6 + c) * 8 + g (the 8 leader lanes read 8
+// consecutive floats).  Points beyond the slice (8 * MAXP per body) are computed by the leader on the spot.
+// ---------------------------------------------------------------------------------------------------------
+struct W32WarmDelta { V3<float> a, bw; };
+__device__ __forceinline__ W32WarmDelta w32_warm_delta(const DevSolver<float>& d, const BodyInertia<float>& in, V3<float> n, V3<float> t1, V3<float> t2,
+                                                       V3<float> r, Vec4<float> pc, bool tangent, bool side2) {
+    using S = float;
+    const S tx = tangent ? pc.z : S(0), ty = tangent ? pc.w : S(0);
+    const V3<S> p = d.warm_coeff * ((pc.x * n + tx * t1) + ty * t2);
+    W32WarmDelta o;
+    o.a = cmul(p, in.inv_mass);
+    o.bw = smul(in.ii, cross(r, p));
+    if (!side2) { o.a = -o.a; o.bw = -o.bw; }
+    return o;
+}
+template <int MAXP>
+__device__ __forceinline__ float* w32_delta_slot(int q, int c, int g) {
+    const int idx = (q * 6 + c) * 8 + g;
+    float* base = reinterpret_cast<float*>(stage_base<float>());
+    return base + size_t(idx >> 7) * (size_t(blockDim.x) * 4) + (threadIdx.x >> 5) * 128 + (idx & 127);
+}
+
+template <int MAXP>
+__device__ __forceinline__ void w32_ivw_item(const DevSolver<float>& d, int chunk, int s) {
+    using S = float;
+    constexpr int CAPQ = 8 * MAXP;     // points per body that fit the warp's slice of the tile: 3 * MAXP rows * 128 floats / (6 * 8)
+    const int lane = threadIdx.x & 31, g = lane >> 2, l = lane & 3;
+    const int i = chunk * 8 + g;
+    const size_t MP = size_t(d.Mpad);
+    const bool in_range = i < d.B;
+    int f = 0;
+    if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
+    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    const int nw = live ? d.wdeg[i] : 0;
+    const int npts = live ? d.wpts[i] : 0;
+    BodyInertia<S> in = zero_inertia<S>();
+    if (nw > 0) in = unpack_inertia(ld4(&d.inr[2 * i]), ld4(&d.inr[2 * i + 1]));
+    const unsigned ptag = w32_pc_tag(PASS_WARM, s, 0, d.iters);
+    __syncwarp();   // the previous item's reads of its staged rows are done in every lane before the slice is overwritten
+    // ---- phase A: the deltas of entries l, l + 4, ... of body g (no dependence on the body's velocity)
+    for (int j = l;; j += 4) {
+        const bool has = j < nw;
+        if (!__any_sync(0xffffffffu, has)) break;
+        uint2 ent = make_uint2(0u, 0u);
+        if (has) ent = d.adj[size_t(j) * d.adj_stride + i];
+        const int np = int(ent.y & WA_NP_MASK), q0 = int(ent.y >> WA_Q0_SHIFT), slot = int(ent.x);
+        const bool tangent = (ent.y & WA_TANGENT) != 0, side2 = (ent.y & WA_SIDE2) != 0;
+        const Vec4<S>* c = d.cst + slot;
+        Vec4<S> hn = mk4<S>(0, 0, 0, 0), ht1 = hn, row[MAXP], PC[MAXP];
+#pragma unroll
+        for (int k = 0; k < MAXP; ++k) { row[k] = hn; PC[k] = hn; }
+        if (np != 0) {
+            hn = ld4(&c[CP_N * MP]);
+            ht1 = ld4(&c[CP_T1 * MP]);
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k)
+                if (k < np) row[k] = ld4(&c[size_t(CP_ROW(k, side2 ? 1 : 0)) * MP]);
+        }
+        unsigned pend = np != 0 ? ((1u << np) - 1u) : 0u;
+        for (unsigned spins = 0;; ++spins) {
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k) {
+                if (pend & (1u << k)) {
+                    const Rec32 p = ld_rec(pc_ptr(d, k, slot));
+                    PC[k] = p.a;
+                    if (tag_of(p.b.x) == ptag) pend &= ~(1u << k);
+                }
+            }
+            if (__all_sync(0xffffffffu, pend == 0u)) break;
+            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+        }
+        const V3<S> n = xyz(hn), t1 = xyz(ht1), t2 = cross(t1, n);
+#pragma unroll
+        for (int k = 0; k < MAXP; ++k) {
+            if (k < np && q0 + k < CAPQ) {
+                const W32WarmDelta o = w32_warm_delta(d, in, n, t1, t2, xyz(row[k]), PC[k], tangent, side2);
+                *w32_delta_slot<MAXP>(q0 + k, 0, g) = o.a.x;  *w32_delta_slot<MAXP>(q0 + k, 1, g) = o.a.y;  *w32_delta_slot<MAXP>(q0 + k, 2, g) = o.a.z;
+                *w32_delta_slot<MAXP>(q0 + k, 3, g) = o.bw.x; *w32_delta_slot<MAXP>(q0 + k, 4, g) = o.bw.y; *w32_delta_slot<MAXP>(q0 + k, 5, g) = o.bw.z;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- phase B: the leader lane of every body: integrate_velocities, then the deltas in order
+    const bool lead = live && l == 0;
+    const unsigned e = lead ? wave_event(WV_IV, 0, s, d.iters, d.deg[i], 0, 0) : 0u;
+    const bool gyro = lead && (f & BF_GYRO) && !(f & BF_CUSTOM_VEL) && !(f & BF_KINEMATIC);
+    Rec32 R, D;
+    R.a = mk4<S>(0, 0, 0, 0); R.b = R.a; D = R;
+    {
+        bool nr = lead, nd = gyro;
+        for (unsigned spins = 0;; ++spins) {
+            if (nr) R = ld_rec(&d.vel[2 * i]);
+            if (nd) D = ld_rec(&d.dlt[2 * i]);
+            if (nr) nr = tag_of(R.a.w) != e;
+            if (nd) nd = tag_of(D.a.w) != unsigned(s);
+            if (__all_sync(0xffffffffu, !(nr || nd))) break;
+            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+        }
+    }
+    if (lead) {
+        V3<S> v = xyz(R.a), w = xyz(R.b);
+        w32_integrate_velocity_math(d, i, f, D, v, w);
+        const int nq = npts < CAPQ ? npts : CAPQ;
+        for (int q = 0; q < nq; ++q) {
+            v.x = v.x + *w32_delta_slot<MAXP>(q, 0, g); v.y = v.y + *w32_delta_slot<MAXP>(q, 1, g); v.z = v.z + *w32_delta_slot<MAXP>(q, 2, g);
+            w.x = w.x + *w32_delta_slot<MAXP>(q, 3, g); w.y = w.y + *w32_delta_slot<MAXP>(q, 4, g); w.z = w.z + *w32_delta_slot<MAXP>(q, 5, g);
+        }
+        if (npts > CAPQ) {   // more points than the slice holds: the rest on the spot (the body's velocity record is final, so the
+                             // impulse records of its constraints are written; they are still validated, lane by lane)
+            for (int j = 0; j < nw; ++j) {
+                const uint2 ent = d.adj[size_t(j) * d.adj_stride + i];
+                const int np = int(ent.y & WA_NP_MASK), q0 = int(ent.y >> WA_Q0_SHIFT), slot = int(ent.x);
+                if (q0 + np <= CAPQ) continue;
+                const bool tangent = (ent.y & WA_TANGENT) != 0, side2 = (ent.y & WA_SIDE2) != 0;
+                const Vec4<S>* c = d.cst + slot;
+                const V3<S> n = xyz(ld4(&c[CP_N * MP])), t1 = xyz(ld4(&c[CP_T1 * MP])), t2 = cross(t1, n);
+                for (int k = 0; k < np; ++k) {
+                    if (q0 + k < CAPQ) continue;
+                    const V3<S> r = xyz(ld4(&c[size_t(CP_ROW(k, side2 ? 1 : 0)) * MP]));
+                    Rec32 p = ld_rec(pc_ptr(d, k, slot));
+                    for (unsigned spins = 0; tag_of(p.b.x) != ptag; ++spins) {
+                        if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+                        p = ld_rec(pc_ptr(d, k, slot));
+                    }
+                    const W32WarmDelta o = w32_warm_delta(d, in, n, t1, t2, r, p.a, tangent, side2);
+                    v = v + o.a;
+                    w = w + o.bw;
+                }
+            }
+        }
+        st_rec(&d.vel[2 * i], v.x, v.y, v.z, tag_lane(e + 1u), w.x, w.y, w.z, 0.f);
+    }
+    __syncwarp();   // the slice is free again (the next item stages its rows into it)
+}
+
+// integrate_positions (integrator/mod.rs:503-535), wavefront mode
+__device__ __forceinline__ void w32_integrate_position_item(const DevSolver<float>& d, int i, int s, bool lane_active, int wf) {
+    using S = float;
+    const bool in_range = lane_active && i < d.B;
+    int f = 0;
+    if (in_range) f = as_int(ld4(&d.inr[2 * i]).y);
+    const bool live = in_range && (f & BF_HAS_SOLVER_BODY);
+    const unsigned e = live ? wave_event(WV_IP, 0, s, d.iters, d.deg[i], 0, wf) : 0u;
     Rec32 R, D;
     R.a = mk4<S>(0, 0, 0, 0); R.b = R.a; D = R;
     {

@@ -359,3 +359,50 @@ class DeviceResidentWorld(World):
         mn, mx = np.empty_like(aabbs.aabb_min), np.empty_like(aabbs.aabb_max)
         mn[aabbs.collider], mx[aabbs.collider] = aabbs.aabb_min, aabbs.aabb_max
         return mn, mx
+
+
+class DeviceGraphWorld(World):
+    """The whole contact pipeline on the device (SURVEY.md 8f #1 + #3): broad phase -> new pairs taken in device memory by the contact store ->
+    geometry + match_contacts -> touching state machine, ContactGraph, ConstraintGraph colouring, colour-major list -> solver stage reading
+    all of it in place (avn_contacts_step + avn_solver_upload_resident).  The host keeps the body columns and the persistent interval order;
+    per step it sends the AABB and body columns and reads back the order, ~40 counters and the bodies.  Steps bit for bit like World
+    (tests/test_gpu_graph.py): same ContactIds, same colours, same bodies."""
+
+    def __init__(self, scene: Scene, plugins: PhysicsPlugins, ctx: "api.Context", **kw):
+        super().__init__(scene, plugins, **kw)
+        self.ctx = ctx
+        n = int(scene.bodies.count)
+        self.n = n
+        ctx.contacts_configure(scene.bodies.kind if scene.bodies.kind is not None else np.zeros(n, dtype=np.uint8), n, scene.friction, scene.restitution)
+        self.order = np.arange(n, dtype=np.uint32)       # AabbIntervals' persistent order (colliders = bodies in this fixture)
+        self.stats: dict | None = None
+        self.new_pairs = 0
+        self._shape = np.ascontiguousarray(scene.shape_type, dtype=np.uint8)
+        self._dims = np.ascontiguousarray(scene.dims, dtype=self.scalar)
+        self._order_out = np.empty(n, dtype=np.uint32)
+
+    def intervals(self, aabb_min: np.ndarray, aabb_max: np.ndarray) -> api.Aabbs:
+        o, kind = self.order, self.bodies.kind
+        flags = np.where(kind[o] == api.BODY_STATIC, api.AABB_IS_INACTIVE, 0).astype(np.uint8) | np.uint8(api.AABB_GENERATE_CONSTRAINTS)
+        a = api.Aabbs(collider=o.copy(), body=o.copy(), aabb_min=np.ascontiguousarray(aabb_min[o]), aabb_max=np.ascontiguousarray(aabb_max[o]),
+                      flags=np.ascontiguousarray(flags), order_out=self._order_out)
+        a.joint_disabled_body_pairs = self.scene.joint_disabled_body_pairs
+        return a
+
+    def step_from(self, aabbs: api.Aabbs, aabb_min: np.ndarray, aabb_max: np.ndarray) -> dict:
+        """One step from host columns: `aabbs` = the interval columns in the persistent order, aabb_min / aabb_max = the same AABBs in collider order."""
+        ctx, b = self.ctx, self.bodies
+        ctx.broadphase_upload(aabbs)
+        ctx.broadphase_run()
+        self.new_pairs = ctx.broadphase_download_order()
+        kept = int(aabbs.retained_count if aabbs.retained_count is not None else aabbs.collider.shape[0])
+        self.order = np.ascontiguousarray(aabbs.collider[aabbs.order_out[:kept]])
+        colliders = {"shape": self._shape, "dims": self._dims, "position": b.position, "rotation": b.rotation, "aabb_min": aabb_min, "aabb_max": aabb_max}
+        self.stats = ctx.contacts_step(self.params.dt, 0.005, colliders, b.linear_velocity, b.angular_velocity, bool(self.params.match_contacts), take_pairs=True)
+        ctx.solver_step_resident(self.params, b, self.joints)
+        self.step_index += 1
+        return self.stats
+
+    def step(self) -> None:
+        self.aabb_min, self.aabb_max = self.pipeline.update_aabbs(self.bodies, self.params.dt)
+        self.step_from(self.intervals(self.aabb_min, self.aabb_max), self.aabb_min, self.aabb_max)

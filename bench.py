@@ -7,11 +7,13 @@ biased solve, integrate positions, relax], restitution, writeback, store impulse
 The narrow phase is NOT in the step (outside the hot path); its manifolds are part of the snapshot, identical for every arm.
 
   e2e          THE HEADLINE: steps/s from pinned HOST body / AABB columns to HOST results through the public C-ABI calls of the device-resident
-               pipeline: avn_broadphase -> avn_contacts_narrow_phase (contact rows, manifolds and warm-start impulses live on
-               the device) -> avn_solver_upload_graph + run + download; every step uploads the body and collider columns and reads back the new
-               pairs, one point count + one flag per contact row and the bodies (wall clock around K steps, barrier + synchronize on both
-               sides).  It does MORE than the CPU arm's step (the narrow phase is inside).  `e2e.host_manifolds` is round 1's arm: the manifolds
-               computed by a host narrow phase outside the step and uploaded as columns through avn_solver_step (80 MB up / 24 MB down).
+               pipeline (SURVEY 8f #1 + #3): avn_broadphase_upload/run/download_order -> avn_contacts_step (the new pairs are taken in device
+               memory; contact rows, geometry + match_contacts, touching state machine, ContactGraph, ConstraintGraph colouring and the
+               colour-major list all live on the device) -> avn_solver_upload_resident + run + download; every step uploads the body, collider
+               and AABB columns and reads back the persistent order, ~40 counters and the bodies (wall clock around K steps of a LIVE world,
+               barrier + synchronize on both sides).  It does MORE than the CPU arm's step (narrow phase and graph maintenance are inside).
+               `e2e.host_manifolds` is round 1's arm: the manifolds computed by a host narrow phase outside the step and uploaded as columns
+               through avn_solver_step (80 MB up / 24 MB down).
   value        steps/s with the snapshot resident in HBM: K x (avn_broadphase_run + avn_solver_run) back to back, timed as ONE span by two
                CUDA events on the library's stream (host launch gaps included, no copies), max over ranks; N > 1 = N independent piles
                (island sharding of independent scenes, no collective), value = N * K / T.
@@ -321,7 +323,7 @@ def run_gpu(args, info):
                 "last_step_device_ms": e2e_break, "what": "avn_broadphase + avn_solver_step with the manifold columns of a host narrow phase uploaded every step"}
     if resident is not None and "error" not in resident:
         e2e_block = {"value": world * K / (resident["wall_ms"] / 1e3), "unit": "steps/s", "h2d_bytes_per_step": resident["h2d"], "d2h_bytes_per_step": resident["d2h"],
-                     "ms_per_step": resident["wall_ms"] / K, "pipeline": resident["what"], "fast_path_share": resident["fast_share"], "host_manifolds": host_arm}
+                     "ms_per_step": resident["wall_ms"] / K, "pipeline": resident["what"], "graph": resident["graph"], "host_manifolds": host_arm}
     else:
         e2e_block = dict(host_arm)
         if resident is not None:
@@ -345,48 +347,53 @@ def run_gpu(args, info):
 
 
 def _resident_world(args, ctx):
-    """A DeviceResidentWorld of the scene, settled, with every per-step host column pinned and the snapshot's pair set in the contact graph."""
+    """A DeviceGraphWorld of the scene (contact rows, ContactGraph and ConstraintGraph on the device), settled, with every per-step host column
+    pinned.  The AABB columns are frozen after the settle steps (like the snapshot of the other arms: the broad phase runs in full and finds the
+    pairs it already has); the bodies keep evolving, so contacts start and stop touching and the graphs change on the device every step."""
     from avian_b200 import api, plugins, scenes
     builder, substeps, _ = SCENES[args.scene]
-    w = plugins.DeviceResidentWorld(builder(scenes), plugins.PhysicsPlugins(ctx), ctx, substeps=substeps)
+    w = plugins.DeviceGraphWorld(builder(scenes), plugins.PhysicsPlugins(ctx), ctx, substeps=substeps)
     w.params.solver_iterations = args.solver_iterations
-    for _ in range(args.settle):
+    first = None
+    for _ in range(args.settle + 2):
         w.step()
+        first = first or dict(w.stats)
     pin_columns(ctx, w.bodies)
-    pairs_out = api.PairList.empty(1 << 20)
-    for _ in range(6):                  # until a step reports no new pair: the snapshot's pair set is then in the contact graph (rows on the device)
-        mn, mx = w.pipeline.update_aabbs(w.bodies, w.params.dt)
-        aabbs = pin_columns(ctx, w.pipeline.intervals(w.bodies, mn, mx))
-        aabbs.joint_disabled_body_pairs = w.scene.joint_disabled_body_pairs
-        w.prepare_steady(aabbs)
-        for k in ("shape", "dims", "aabb_min", "aabb_max"):
-            w._colliders[k] = ctx.pin_like(w._colliders[k])
-        w.step_steady(aabbs, pairs_out)
-        if pairs_out.count == 0:
+    mn, mx = w.pipeline.update_aabbs(w.bodies, w.params.dt)
+    mn, mx = ctx.pin_like(mn), ctx.pin_like(mx)
+    w._shape, w._dims = ctx.pin_like(w._shape), ctx.pin_like(w._dims)
+    aabbs = None
+    for _ in range(4):                    # until the frozen AABBs bring no new pair; the order is a fixed point then
+        aabbs = pin_columns(ctx, w.intervals(mn, mx))
+        w.step_from(aabbs, mn, mx)
+        if w.new_pairs == 0:
             break
+    aabbs = pin_columns(ctx, w.intervals(mn, mx))
     for _ in range(max(2, args.warmup)):
-        w.step_steady(aabbs, pairs_out)
-    return w, aabbs, pairs_out
+        w.step_from(aabbs, mn, mx)
+    return w, aabbs, mn, mx, first
 
 
 def e2e_resident(args, info, barrier):
-    """K steps of DeviceResidentWorld.step_steady from pinned host columns; returns wall ms (max over ranks) and the bytes that cross the bus."""
+    """K steps of DeviceGraphWorld.step_from from pinned host columns; returns wall ms (max over ranks) and the bytes that cross the bus."""
     from avian_b200 import api, parallel
     scalar = np.float64 if args.scene.startswith("spheres") else np.float32
     ctx = api.Context(device=info.local_rank, scalar=scalar)
     try:
         error = None
         try:
-            w, aabbs, pairs_out = _resident_world(args, ctx)
+            w, aabbs, mn, mx, first = _resident_world(args, ctx)
         except Exception as exc:
             error = f"{type(exc).__name__}: {exc}"
         if parallel.reduce_max([0.0 if error is None else 1.0], info, device="cuda")[0] > 0:     # every rank agrees before the barriers
             return {"error": error or "another rank failed to set the resident world up"}
         barrier()
-        fast = 0
+        changes = rounds = 0
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            fast += bool(w.step_steady(aabbs, pairs_out))
+            st = w.step_from(aabbs, mn, mx)
+            changes += st["started_touching"] + st["stopped_touching"] + st["pairs_added"] + st["pairs_removed"]
+            rounds = max(rounds, st["colouring_rounds"])
         barrier()
         wall_ms = parallel.reduce_max([(time.perf_counter() - t0) * 1e3], info, device="cuda")[0]
         b, sb = w.bodies, w.bodies.position.dtype.itemsize
@@ -394,10 +401,13 @@ def e2e_resident(args, info, barrier):
         h2d = sum(v.nbytes for k, v in aabbs.__dict__.items() if isinstance(v, np.ndarray) and k != "order_out") \
             + C * (1 + 3 * sb + 3 * sb + 4 * sb + 3 * sb + 3 * sb) + 2 * b.count * 3 * sb \
             + sum(v.nbytes for k, v in b.__dict__.items() if isinstance(v, np.ndarray))
-        d2h = 2 * w.capacity + b.count * (3 + 4 + 3 + 3) * sb + C * 4
-        return {"wall_ms": wall_ms, "h2d": int(h2d), "d2h": int(d2h), "fast_share": fast / max(args.steps, 1),
-                "what": f"avn_broadphase -> avn_contacts_narrow_phase ({w.capacity} resident contact rows) -> avn_solver_upload_graph/run/download; "
-                        "the constraint graph stays on the device while no contact starts or stops touching"}
+        d2h = b.count * (3 + 4 + 3 + 3) * sb + C * 4 + 35 * 4 + 16
+        st = w.stats
+        return {"wall_ms": wall_ms, "h2d": int(h2d), "d2h": int(d2h),
+                "graph": {"contact_rows": st["rows_live"], "manifolds": st["manifold_count"], "changes_per_step": changes / max(args.steps, 1),
+                          "max_colouring_rounds": rounds, "first_frame": {k: first[k] for k in ("pairs_added", "started_touching", "colouring_rounds")}},
+                "what": "avn_broadphase (new pairs stay on the device) -> avn_contacts_step (rows, geometry + match_contacts, touching state machine, "
+                        "ContactGraph, ConstraintGraph colouring, colour-major list: all on the device) -> avn_solver_upload_resident/run/download"}
     finally:
         ctx.close()
 

@@ -482,6 +482,51 @@ AvnStatus avn_solver_upload_graph(AvnContext* ctx, const AvnStepParams* params, 
 /* the impulses of the rows as the last solve left them (tests, tools): [capacity][4], [capacity][4][2], [capacity][4]; any may be NULL */
 AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse);
 
+/* ---- the ContactGraph and the ConstraintGraph on the device (SURVEY.md 8f "next #3"): after this nothing of the contact pipeline lives on
+ *      the host.  Replaces, for the pairs the device narrow phase covers,
+ *        ContactGraph::add_edge_and_key_with          (collision/contact_types/contact_graph.rs:521-565; ids: data_structures/id_pool.rs:43-52)
+ *        the status-change loop of NarrowPhase::update (collision/narrow_phase/system_param.rs:136-389: removal of separated pairs,
+ *                                                       started / stopped touching)
+ *        ConstraintGraph::push_manifold / pop_manifold (dynamics/solver/constraint_graph.rs:163-296)
+ *      with the reference's results: the same ContactId for every pair, the same colour for every manifold (the greedy colouring is
+ *      order dependent; the device reproduces the sequential order with a dependency wavefront, csrc/contacts.cu).  The order of the
+ *      manifolds INSIDE a colour is ascending ContactId instead of the reference's swap_remove order — it does not influence the solve;
+ *      the overflow colour, which is solved serially, keeps the reference's list order. ------------------------------------------------ */
+typedef struct AvnContactGraphConfig {
+    uint32_t body_count, collider_count;
+    const uint8_t* body_kind;          /* [B] AvnBodyKind: static bodies never enter a colour's body set */
+    const double* friction;            /* [C] per collider; a pair's coefficient is the mean of its colliders' (NULL = 0.5) */
+    const double* restitution;         /* [C] (NULL = 0) */
+} AvnContactGraphConfig;
+AvnStatus avn_contacts_configure(AvnContext* ctx, const AvnContactGraphConfig* config);
+
+typedef struct AvnContactStep {
+    uint32_t rows_high_water;          /* ContactIds in use: [0, rows_high_water) */
+    uint32_t rows_live;                /* pairs in the ContactGraph after this step */
+    uint32_t pairs_added, pairs_removed, started_touching, stopped_touching;
+    uint32_t manifold_count;           /* manifolds in the ConstraintGraph = length of the colour-major list */
+    uint32_t colouring_rounds;         /* dependency levels the greedy colouring needed this step */
+    uint32_t any_restitution;
+    uint32_t _pad;
+    uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];
+} AvnContactStep;
+#define AVN_CONTACTS_TAKE_BROADPHASE_PAIRS 0x1u   /* add the new pairs of the context's last avn_broadphase_run (read in device memory) */
+/* One step of the contact pipeline on the device: (new pairs ->) rows, geometry + match_contacts for every live row, the status loop, the
+ * graphs, the colour-major list.  input: the collider / body columns of AvnNarrowInput (pair arrays ignored).  From the first call on the
+ * contact store's pair set is the broad phase's "existing pairs" set (AvnAabbColumns::existing_pairs may stay NULL). */
+AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, const AvnNarrowInput* input, uint32_t match_contacts, double length_unit,
+                            uint32_t flags, AvnContactStep* out);
+/* The solver stage fed entirely from the device: manifolds from the contact rows, the constraint graph from the last avn_contacts_step.
+ * Then avn_solver_run / avn_solver_download (bodies only) as usual. */
+AvnStatus avn_solver_upload_resident(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnJointSet* joints);
+/* After avn_broadphase_run in the device-resident pipeline: waits for the run, writes order_out / retained_count of the uploaded columns and
+ * returns the number of new pairs; the pairs themselves stay on the device for avn_contacts_step. */
+AvnStatus avn_broadphase_download_order(AvnContext* ctx, uint64_t* out_pair_count);
+/* the graphs as the device holds them (tests, tools): per row [capacity] colliders, live / touching flags, colour (-1 = not in the
+ * constraint graph); edge_list [manifold_count] = the colour-major list.  Any pointer may be NULL. */
+AvnStatus avn_contacts_download_graph(AvnContext* ctx, uint32_t capacity, uint32_t* collider1, uint32_t* collider2, uint8_t* live, uint8_t* touching,
+                                      int8_t* colour, uint32_t* edge_list);
+
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
 /*

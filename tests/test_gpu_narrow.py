@@ -163,4 +163,5 @@ def test_step_steady_on_the_device_equals_the_ordinary_world(gpu_ctx, scene_fn, 
             fast += bool(wb.step_steady(aabbs, pairs_out))
             for k in ("position", "rotation", "linear_velocity", "angular_velocity"):
                 assert np.array_equal(getattr(wa.bodies, k), getattr(wb.bodies, k)), f"step {i}: {k}"
-        assert fast > 0, "the graph-reuse path never ran"
+        if not kick:   # (a tumbling scene changes its touching set every step: the reuse path is for settled scenes)
+            assert fast > 0, "the graph-reuse path never ran"

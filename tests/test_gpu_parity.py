@@ -133,17 +133,20 @@ def test_dominance_kinematic_and_overflow_colour(gpu_ctx):
     assert_manifolds_close(mg, mo, what="dominance: ")
 
 
-def _run_in_mode(mode, prm, b, m, j=None):
-    """a fresh context with AVN_LAUNCH_MODE=mode ('' = default: megakernel + wavefront scheduling)"""
+def _run_in_mode(mode, prm, b, m, j=None, env=None):
+    """a fresh context with AVN_LAUNCH_MODE=mode ('' = default: megakernel + wavefront scheduling) and extra environment switches"""
+    env = dict(env or {})
     if mode:
-        os.environ["AVN_LAUNCH_MODE"] = mode
+        env["AVN_LAUNCH_MODE"] = mode
+    os.environ.update(env)
     try:
         with api.Context(device=0) as ctx:
             bb, mm = b.copy(), m.copy()
             ctx.solver_step(prm, bb, mm, j)
             return bb, mm, ctx.timings()
     finally:
-        os.environ.pop("AVN_LAUNCH_MODE", None)
+        for k in env:
+            os.environ.pop(k, None)
 
 
 @pytest.mark.parametrize("iters", [1, 2])
@@ -155,9 +158,12 @@ def test_launch_modes_agree(gpu_ctx, iters):
     bw, mw, tw = _run_in_mode("", prm, b, m)
     bb, mb, tb = _run_in_mode("barrier", prm, b, m)
     bp, mp, tp = _run_in_mode("phases", prm, b, m)
+    bs, ms, ts = _run_in_mode("", prm, b, m, env={"AVN_WARM_BY_BODY": "1"})   # wavefront schedule with the body-centric warm start (experiment)
     assert tw["kernel_launches"] == 1 and tb["kernel_launches"] == 1, "megakernel paths are ONE launch per step"
+    assert tw["launch_mode"] == ts["launch_mode"] == 2   # AVN_LAUNCH_MEGA_WAVE
     assert tp["kernel_launches"] > 10
-    for other, what in ((bb, "barrier"), (bp, "phases")):
+    assert np.array_equal(mw.normal_impulse, ms.normal_impulse) and np.array_equal(mw.warm_start_tangent_impulse, ms.warm_start_tangent_impulse)
+    for other, what in ((bb, "barrier"), (bp, "phases"), (bs, "body-centric warm start")):
         for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
             assert np.array_equal(getattr(bw, name), getattr(other, name)), (what, name)
     assert np.array_equal(mw.warm_start_normal_impulse, mb.warm_start_normal_impulse)
@@ -166,6 +172,27 @@ def test_launch_modes_agree(gpu_ctx, iters):
     bo, mo = b.copy(), m.copy()
     oracle_lib.solver_step(prm, bo, mo)
     assert_bodies_close(bw, bo, what=f"iters={iters}: ")
+
+
+def test_body_centric_warm_start_with_many_contacts(gpu_ctx):
+    """a body with more contact points than the warp's slice of the staging tile holds (32): the body-centric warm start computes the
+    rest on the spot; a wide plate resting on a 4 x 4 field of cubes carries 16 manifolds x 4 points.  Bit-identical to the barrier schedule."""
+    cubes = np.array([[1.5 * ix, 0.49, 1.5 * iz] for ix in range(4) for iz in range(4)])
+    pos = np.concatenate([[[2.25, -0.5, 2.25]], cubes, [[2.25, 1.22, 2.25]]])
+    he = np.concatenate([[[20.0, 0.5, 20.0]], np.full((16, 3), 0.5), [[3.5, 0.25, 3.5]]])
+    kind = np.concatenate([[api.BODY_STATIC], np.full(17, api.BODY_DYNAMIC)])
+    rot = np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (18, 1))
+    sc = scenes._assemble("plate_on_cubes", pos, rot, kind, he, np.full(18, scenes.SHAPE_CUBOID), np.float32)
+    _, (prm, b, m, j) = advance_to_solver_input(sc, steps=3, substeps=4)
+    per_body = np.bincount(np.concatenate([m.body1[m.body1 >= 0], m.body2[m.body2 >= 0]]), minlength=b.count)
+    assert per_body.max() >= 16 and m.color_offsets[api.COLOR_OVERFLOW + 1] == m.color_offsets[api.COLOR_OVERFLOW], (per_body.max(), m.color_offsets)
+    bw, mw, tw = _run_in_mode("wave", prm, b, m, env={"AVN_WARM_BY_BODY": "1"})
+    bb, mb, _ = _run_in_mode("barrier", prm, b, m)
+    assert tw["launch_mode"] == 2   # AVN_LAUNCH_MEGA_WAVE
+    for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
+        assert np.array_equal(getattr(bw, name), getattr(bb, name)), name
+    assert np.array_equal(mw.warm_start_normal_impulse, mb.warm_start_normal_impulse)
+    assert np.array_equal(mw.warm_start_tangent_impulse, mb.warm_start_tangent_impulse)
 
 
 def test_wavefront_equals_barrier_at_headline_size(gpu_ctx):
