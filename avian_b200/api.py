@@ -330,7 +330,8 @@ class AvnContactStep(C.Structure):
                                          "manifold_count", "colouring_rounds", "any_restitution", "_pad")] + [("color_offsets", C.c_uint32 * (GRAPH_COLOR_COUNT + 1))]
 
 
-CONTACTS_TAKE_BROADPHASE_PAIRS = 1
+CONTACTS_TAKE_BROADPHASE_PAIRS, CONTACTS_SHAPES_UNCHANGED = 1, 2
+BODIES_STATIC_UNCHANGED = 1
 
 
 class AvnNarrowInput(C.Structure):
@@ -394,6 +395,7 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "solver_upload_resident": ([_vp, P(AvnStepParams), P(AvnBodyColumns), P(AvnJointSet)], C.c_int),
         "broadphase_download_order": ([_vp, P(C.c_uint64)], C.c_int),
         "contacts_download_graph": ([_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+        "solver_prefetch_bodies": ([_vp, P(AvnBodyColumns), C.c_uint32], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -408,7 +410,8 @@ ABI_SYMBOLS = [
     "avn_solver_boundary_snapshot", "avn_solver_boundary_pack", "avn_solver_boundary_apply", "avn_solver_needs_restitution", "avn_get_stream",
     "avn_solver_step_partitioned", "avn_comm_unique_id", "avn_comm_init", "avn_comm_destroy", "avn_comm_all_gather", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
     "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses",
-    "avn_contacts_configure", "avn_contacts_step", "avn_solver_upload_resident", "avn_broadphase_download_order", "avn_contacts_download_graph"]
+    "avn_contacts_configure", "avn_contacts_step", "avn_solver_upload_resident", "avn_broadphase_download_order", "avn_contacts_download_graph",
+    "avn_solver_prefetch_bodies"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 COMM_ID_BYTES = 128
@@ -716,8 +719,14 @@ class Context:
         cfg = AvnContactGraphConfig(int(kind.shape[0]), int(collider_count), _ptr(kind), _ptr(fr), _ptr(re))
         self._check(self.lib.avn_contacts_configure(self.handle, C.byref(cfg)))
 
+    def solver_prefetch_bodies(self, bodies: Bodies, static_unchanged: bool = False) -> None:
+        """avn_solver_prefetch_bodies: the body columns of the next solver upload start moving to the device now (second stream)."""
+        b = bodies.as_struct()
+        self._keep_prefetch = (bodies, b)
+        self._check(self.lib.avn_solver_prefetch_bodies(self.handle, C.byref(b), BODIES_STATIC_UNCHANGED if static_unchanged else 0))
+
     def contacts_step(self, dt: float, contact_tolerance: float, colliders: dict, lin_vel, ang_vel, match_contacts: bool = True, take_pairs: bool = True,
-                      length_unit: float = 1.0) -> dict:
+                      length_unit: float = 1.0, shapes_unchanged: bool = False) -> dict:
         """avn_contacts_step: (the last broad phase's new pairs ->) rows, geometry + matching, status loop, graphs, colour-major list — all on the
         device.  Returns the step's counters and the colour offsets of the list."""
         dt_ = self.scalar
@@ -729,7 +738,8 @@ class Context:
         prm = AvnNarrowParams(float(dt), float(contact_tolerance))
         out = AvnContactStep()
         self._check(self.lib.avn_contacts_step(self.handle, C.byref(prm), C.byref(inp), 1 if match_contacts else 0, float(length_unit),
-                                               CONTACTS_TAKE_BROADPHASE_PAIRS if take_pairs else 0, C.byref(out)))
+                                               (CONTACTS_TAKE_BROADPHASE_PAIRS if take_pairs else 0) | (CONTACTS_SHAPES_UNCHANGED if shapes_unchanged else 0),
+                                               C.byref(out)))
         st = {n: int(getattr(out, n)) for n, _ in AvnContactStep._fields_ if n not in ("_pad", "color_offsets")}
         st["color_offsets"] = np.array(list(out.color_offsets), dtype=np.uint32)
         return st

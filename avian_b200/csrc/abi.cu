@@ -245,6 +245,11 @@ AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, cons
     return guarded(ctx, [&] {
         avn::DevicePairs pairs;
         const bool take = (flags & AVN_CONTACTS_TAKE_BROADPHASE_PAIRS) != 0;
+        // this step's collider / body columns start moving to the device before the broad phase is waited for
+        if (params && input && out) {
+            AvnStatus st = ctx->contacts->prefetch_inputs(input, flags);
+            if (st != AVN_OK) return st;
+        }
         if (take) {
             AvnStatus st = ctx->broadphase->device_pairs(&pairs);
             if (st != AVN_OK) return st;
@@ -261,6 +266,9 @@ AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, cons
 }
 AvnStatus avn_solver_upload_resident(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnJointSet* joints) {
     return guarded(ctx, [&] { return ctx->solver->upload_resident(params, bodies, ctx->contacts.get(), joints); });
+}
+AvnStatus avn_solver_prefetch_bodies(AvnContext* ctx, AvnBodyColumns* bodies, uint32_t flags) {
+    return guarded(ctx, [&] { return ctx->solver->prefetch_bodies(bodies, flags); });
 }
 AvnStatus avn_broadphase_download_order(AvnContext* ctx, uint64_t* out_pair_count) { return guarded(ctx, [&] { return ctx->broadphase->download_order(out_pair_count); }); }
 AvnStatus avn_contacts_download_graph(AvnContext* ctx, uint32_t capacity, uint32_t* collider1, uint32_t* collider2, uint8_t* live, uint8_t* touching, int8_t* colour,

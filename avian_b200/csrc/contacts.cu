@@ -285,8 +285,15 @@ class Contacts final : public ContactsBase {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sm_count_ = prop.multiProcessorCount;
         cudaHostAlloc(&h_ctr_, sizeof(GraphCounters), cudaHostAllocDefault);
+        up_stream_ = stream_;
+        if (cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); copy_stream_ = nullptr; }
+        cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming);
     }
-    ~Contacts() override { if (h_ctr_) cudaFreeHost(h_ctr_); }
+    ~Contacts() override {
+        if (h_ctr_) cudaFreeHost(h_ctr_);
+        if (ev_in_) cudaEventDestroy(ev_in_);
+        if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+    }
 
     AvnStatus reserve(uint32_t capacity) override {
         if (capacity <= E_) return AVN_OK;
@@ -389,6 +396,17 @@ class Contacts final : public ContactsBase {
         AVN_CUDA(cudaStreamSynchronize(stream_));   // the host arrays may be reused by the caller
         configured_ = true;
         graph_ = ResidentGraph{};
+        return AVN_OK;
+    }
+
+    AvnStatus prefetch_inputs(const AvnNarrowInput* in, uint32_t flags) override {
+        prefetched_ = nullptr;
+        if (!copy_stream_ || !in) return AVN_OK;
+        // (the device copies were read by the previous step's narrow phase, which the previous step waited for)
+        AvnStatus st = upload_inputs(in, (flags & AVN_CONTACTS_SHAPES_UNCHANGED) != 0, copy_stream_);
+        if (st != AVN_OK) return st;
+        AVN_CUDA(cudaEventRecord(ev_in_, copy_stream_));
+        prefetched_ = in;
         return AVN_OK;
     }
 
@@ -514,25 +532,44 @@ class Contacts final : public ContactsBase {
     }
 
    private:
-    // geometry + match_contacts over rows [0, n)
-    AvnStatus launch_narrow(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t n) {
+    // the collider / body columns of a step -> device (on `s`); keep_shapes: shape and dims are those of the previous call
+    AvnStatus upload_inputs(const AvnNarrowInput* in, bool keep_shapes, cudaStream_t s) {
         const size_t C = in->collider_count, B = in->body_count;
         if (!in->dims || !in->position || !in->rotation || !in->linear_velocity || !in->angular_velocity || !in->aabb_min || !in->aabb_max)
             return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_narrow_phase: dims, position, rotation, velocities and AABBs are required");
+        keep_shapes = keep_shapes && in_.colliders == C && in_.dims != nullptr;
+        AvnStatus st;
+        up_stream_ = s;
+#define UPC(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) { up_stream_ = stream_; return st; }
+        if (!keep_shapes) {
+            UPC(i_shape_, in->shape, C, uint8_t, in_.shape);
+            UPC(i_dims_, in->dims, 3 * C, S, in_.dims);
+        }
+        UPC(i_pos_, in->position, 3 * C, S, in_.pos);
+        UPC(i_rot_, in->rotation, 4 * C, S, in_.rot);
+        UPC(i_lv_, in->linear_velocity, 3 * B, S, in_.lv);
+        UPC(i_av_, in->angular_velocity, 3 * B, S, in_.av);
+        UPC(i_amin_, in->aabb_min, 3 * C, S, in_.amin);
+        UPC(i_amax_, in->aabb_max, 3 * C, S, in_.amax);
+#undef UPC
+        up_stream_ = stream_;
+        in_.colliders = C;
+        return AVN_OK;
+    }
+    // geometry + match_contacts over rows [0, n)
+    AvnStatus launch_narrow(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t n) {
+        if (prefetched_ == in) {   // prefetch_inputs copied this call's columns on the copy stream
+            AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));
+        } else {
+            if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));
+            AvnStatus st = upload_inputs(in, false, stream_);
+            if (st != AVN_OK) return st;
+        }
+        prefetched_ = nullptr;
         NarrowEdgeArgs<S> a{};
         a.r = rows();
         a.r.E = int(n);
-        AvnStatus st;
-#define UPC(buf, host, cnt, T, dst) if ((st = up<T>(buf, host, cnt, &dst)) != AVN_OK) return st
-        UPC(i_shape_, in->shape, C, uint8_t, a.shape);
-        UPC(i_dims_, in->dims, 3 * C, S, a.dims);
-        UPC(i_pos_, in->position, 3 * C, S, a.pos);
-        UPC(i_rot_, in->rotation, 4 * C, S, a.rot);
-        UPC(i_lv_, in->linear_velocity, 3 * B, S, a.lv);
-        UPC(i_av_, in->angular_velocity, 3 * B, S, a.av);
-        UPC(i_amin_, in->aabb_min, 3 * C, S, a.amin);
-        UPC(i_amax_, in->aabb_max, 3 * C, S, a.amax);
-#undef UPC
+        a.shape = in_.shape; a.dims = in_.dims; a.pos = in_.pos; a.rot = in_.rot; a.lv = in_.lv; a.av = in_.av; a.amin = in_.amin; a.amax = in_.amax;
         a.dt = prm->dt;
         a.tol = prm->contact_tolerance;
         a.thr2 = (0.1 * length_unit) * (0.1 * length_unit);
@@ -580,11 +617,16 @@ class Contacts final : public ContactsBase {
         *dev = nullptr;
         if (!host || count == 0) return AVN_OK;
         AVN_CUDA(buf.ensure(count * sizeof(T)));
-        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, up_stream_));
         *dev = buf.as<T>();
         return AVN_OK;
     }
     cudaStream_t stream_;
+    cudaStream_t copy_stream_ = nullptr, up_stream_ = nullptr;
+    cudaEvent_t ev_in_ = nullptr;
+    const AvnNarrowInput* prefetched_ = nullptr;
+    struct { const uint8_t* shape = nullptr; const S* dims = nullptr; const S* pos = nullptr; const S* rot = nullptr; const S* lv = nullptr; const S* av = nullptr;
+             const S* amin = nullptr; const S* amax = nullptr; size_t colliders = 0; } in_;
     ErrorSink* err_;
     uint32_t E_ = 0;
     DevBuf c1_, c2_, b1_, b2_, live_, count_, disjoint_, normal_, a1_, a2_, pen_, ns_, prev_count_, prev_a1_, prev_a2_, ws_n_in_, ws_t_in_, ws_n_out_, ws_t_out_,

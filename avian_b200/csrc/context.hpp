@@ -84,6 +84,8 @@ struct SolverBase {
     // the whole partitioned stage of one rank: launches substep by substep with the boundary exchange over `comm` in between
     virtual AvnStatus step_partitioned(CommBase* comm) = 0;
     virtual int needs_restitution() const = 0;
+    // start the host-to-device copy of the next upload's body columns on a second stream (overlaps whatever runs before the solver stage)
+    virtual AvnStatus prefetch_bodies(AvnBodyColumns* bodies, uint32_t flags) = 0;
     virtual AvnStatus download() = 0;
     virtual void timings(AvnTimings* t) const = 0;
 };
@@ -134,6 +136,8 @@ struct ContactsBase {
     virtual AvnStatus download_impulses(void* ws_n, void* ws_t, void* nimp) = 0;
     // ---- the ContactGraph + ConstraintGraph on the device (contacts.cu)
     virtual AvnStatus configure(const AvnContactGraphConfig* cfg) = 0;
+    // start the host-to-device copy of step()'s collider / body columns on a second stream (before the broad phase is waited for)
+    virtual AvnStatus prefetch_inputs(const AvnNarrowInput* in, uint32_t flags) = 0;
     virtual AvnStatus step(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, const DevicePairs* new_pairs,
                            AvnContactStep* out) = 0;
     struct ResidentGraph {          // device pointers of the colour-major list the last step() built

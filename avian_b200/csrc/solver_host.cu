@@ -61,9 +61,14 @@ class Solver final : public SolverBase {
         if (const char* w = getenv("AVN_WARM_BY_BODY")) warm_by_body_ = atoi(w) != 0;
         coop_ok_ = coop_ok_ && select_megakernel(AVN_MAX_MANIFOLD_POINTS);
         for (auto& e : ev_) cudaEventCreate(&e);
+        up_stream_ = stream_;
+        if (cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); copy_stream_ = nullptr; }
+        cudaEventCreateWithFlags(&ev_prefetch_, cudaEventDisableTiming);
     }
     ~Solver() override {
         for (auto& e : ev_) cudaEventDestroy(e);
+        if (ev_prefetch_) cudaEventDestroy(ev_prefetch_);
+        if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
         if (h_agree_) cudaFreeHost(h_agree_);
     }
 
@@ -78,6 +83,24 @@ class Solver final : public SolverBase {
     AvnStatus boundary_apply(const void* device_gathered) override;
     AvnStatus step_partitioned(CommBase* comm) override;
     int needs_restitution() const override { return host_any_restitution_ ? 1 : 0; }
+    AvnStatus prefetch_bodies(AvnBodyColumns* bc, uint32_t flags) override {
+        if (!bc) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "bodies are required");
+        if (bc->count && (!bc->position || !bc->rotation || !bc->linear_velocity || !bc->angular_velocity || !bc->inverse_mass || !bc->inverse_inertia_local))
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "bodies: position, rotation, velocities, inverse_mass and inverse_inertia_local are required");
+        prefetched_ = false;
+        if (!copy_stream_) return AVN_OK;    // no second stream: the next upload copies as usual
+        // the device copies are inputs of the previous run: the copy waits for it (not for anything enqueued after it)
+        if (ran_ || prepared_) AVN_CUDA(cudaStreamWaitEvent(copy_stream_, ev_[EV_RUN1], 0));
+        DevSolver<S> tmp{};
+        up_stream_ = copy_stream_;
+        const AvnStatus st = upload_body_columns(*bc, (flags & AVN_BODIES_STATIC_UNCHANGED) != 0, tmp);
+        up_stream_ = stream_;
+        if (st != AVN_OK) return st;
+        AVN_CUDA(cudaEventRecord(ev_prefetch_, copy_stream_));
+        pref_host_ = *bc;
+        prefetched_ = true;
+        return AVN_OK;
+    }
     AvnStatus run() override;
     AvnStatus download() override;
     void timings(AvnTimings* t) const override { *t = tm_; }
@@ -92,9 +115,63 @@ class Solver final : public SolverBase {
         *dev = nullptr;
         if (!host || count == 0) return AVN_OK;
         AVN_CUDA(buf.ensure(count * sizeof(T)));
-        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        AVN_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, up_stream_));
         *dev = buf.as<T>();
         h2d_bytes_ += count * sizeof(T);
+        return AVN_OK;
+    }
+    // ---- body columns: uploaded by upload_impl, or ahead of it by avn_solver_prefetch_bodies on the copy stream so that the copy overlaps the
+    //      kernels of the stages that run before the solver (broad phase, contact pipeline)
+    struct BodyCols {
+        const uint8_t* kind = nullptr; const uint8_t* locked = nullptr; const int8_t* dominance = nullptr; const uint8_t* integ_flags = nullptr;
+        const S* position = nullptr; const S* rotation = nullptr; const S* linvel = nullptr; const S* angvel = nullptr; const S* inv_mass = nullptr;
+        const S* inv_inertia_local = nullptr; const S* com = nullptr; const S* lin_damp = nullptr; const S* ang_damp = nullptr; const S* grav_scale = nullptr;
+        const S* lin_acc = nullptr; const S* ang_acc = nullptr; const S* max_lin = nullptr; const S* max_ang = nullptr;
+        size_t count = 0;
+    };
+    BodyCols bcols_{};
+    AvnBodyColumns pref_host_{};
+    bool prefetched_ = false;
+    cudaStream_t copy_stream_ = nullptr, up_stream_ = nullptr;
+    cudaEvent_t ev_prefetch_ = nullptr;
+    bool prefetch_matches(const AvnBodyColumns& bc) const {
+        return bc.count == pref_host_.count && bc.position == pref_host_.position && bc.rotation == pref_host_.rotation &&
+               bc.linear_velocity == pref_host_.linear_velocity && bc.angular_velocity == pref_host_.angular_velocity && bc.kind == pref_host_.kind &&
+               bc.inverse_mass == pref_host_.inverse_mass && bc.inverse_inertia_local == pref_host_.inverse_inertia_local;
+    }
+    // keep_static: the columns that describe the body (kind, locked axes, dominance, integration markers, mass properties, damping, gravity
+    // scale, speed limits) equal those of the previous upload of the same number of bodies and stay where they are
+    AvnStatus upload_body_columns(const AvnBodyColumns& bc, bool keep_static, DevSolver<S>& d) {
+        const size_t B = bc.count;
+        AvnStatus st;
+        keep_static = keep_static && bcols_.count == B && B > 0;
+#define UPB(buf, host, n, T, field) if ((st = up<T>(buf, host, n, &d.field)) != AVN_OK) return st
+#define UPS(buf, host, n, T, field) if (keep_static) d.field = (host) ? bcols_.field : nullptr; else UPB(buf, host, n, T, field)
+        UPS(b_kind_, bc.kind, B, uint8_t, kind);
+        UPS(b_locked_, bc.locked_axes, B, uint8_t, locked);
+        UPS(b_dom_, bc.dominance, B, int8_t, dominance);
+        UPS(b_iflags_, bc.integration_flags, B, uint8_t, integ_flags);
+        UPB(b_pos_, bc.position, 3 * B, S, position);
+        UPB(b_rot_, bc.rotation, 4 * B, S, rotation);
+        UPB(b_lv_, bc.linear_velocity, 3 * B, S, linvel);
+        UPB(b_av_, bc.angular_velocity, 3 * B, S, angvel);
+        UPS(b_im_, bc.inverse_mass, B, S, inv_mass);
+        UPS(b_iil_, bc.inverse_inertia_local, 6 * B, S, inv_inertia_local);
+        UPS(b_com_, bc.center_of_mass, 3 * B, S, com);
+        UPS(b_ld_, bc.linear_damping, B, S, lin_damp);
+        UPS(b_ad_, bc.angular_damping, B, S, ang_damp);
+        UPS(b_gs_, bc.gravity_scale, B, S, grav_scale);
+        UPB(b_la_, bc.linear_acceleration, 3 * B, S, lin_acc);
+        UPB(b_aa_, bc.angular_acceleration, 3 * B, S, ang_acc);
+        UPS(b_ml_, bc.max_linear_speed, B, S, max_lin);
+        UPS(b_ma_, bc.max_angular_speed, B, S, max_ang);
+#undef UPS
+#undef UPB
+        bcols_.kind = d.kind; bcols_.locked = d.locked; bcols_.dominance = d.dominance; bcols_.integ_flags = d.integ_flags;
+        bcols_.position = d.position; bcols_.rotation = d.rotation; bcols_.linvel = d.linvel; bcols_.angvel = d.angvel; bcols_.inv_mass = d.inv_mass;
+        bcols_.inv_inertia_local = d.inv_inertia_local; bcols_.com = d.com; bcols_.lin_damp = d.lin_damp; bcols_.ang_damp = d.ang_damp;
+        bcols_.grav_scale = d.grav_scale; bcols_.lin_acc = d.lin_acc; bcols_.ang_acc = d.ang_acc; bcols_.max_lin = d.max_lin; bcols_.max_ang = d.max_ang;
+        bcols_.count = B;
         return AVN_OK;
     }
     AvnStatus build_joint_schedule(const AvnBodyColumns& bc, const AvnJointSet& js);
@@ -378,24 +455,19 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
     // ---- body columns
     AvnStatus st;
 #define UP(buf, host, n, T, field) if ((st = up<T>(buf, host, n, &d.field)) != AVN_OK) return st
-    UP(b_kind_, bc->kind, B, uint8_t, kind);
-    UP(b_locked_, bc->locked_axes, B, uint8_t, locked);
-    UP(b_dom_, bc->dominance, B, int8_t, dominance);
-    UP(b_iflags_, bc->integration_flags, B, uint8_t, integ_flags);
-    UP(b_pos_, bc->position, 3 * B, S, position);
-    UP(b_rot_, bc->rotation, 4 * B, S, rotation);
-    UP(b_lv_, bc->linear_velocity, 3 * B, S, linvel);
-    UP(b_av_, bc->angular_velocity, 3 * B, S, angvel);
-    UP(b_im_, bc->inverse_mass, B, S, inv_mass);
-    UP(b_iil_, bc->inverse_inertia_local, 6 * B, S, inv_inertia_local);
-    UP(b_com_, bc->center_of_mass, 3 * B, S, com);
-    UP(b_ld_, bc->linear_damping, B, S, lin_damp);
-    UP(b_ad_, bc->angular_damping, B, S, ang_damp);
-    UP(b_gs_, bc->gravity_scale, B, S, grav_scale);
-    UP(b_la_, bc->linear_acceleration, 3 * B, S, lin_acc);
-    UP(b_aa_, bc->angular_acceleration, 3 * B, S, ang_acc);
-    UP(b_ml_, bc->max_linear_speed, B, S, max_lin);
-    UP(b_ma_, bc->max_angular_speed, B, S, max_ang);
+    if (prefetched_ && prefetch_matches(*bc)) {
+        // avn_solver_prefetch_bodies already put this step's body columns on the device (copy stream): the kernels wait for that copy
+        d.kind = bcols_.kind; d.locked = bcols_.locked; d.dominance = bcols_.dominance; d.integ_flags = bcols_.integ_flags;
+        d.position = bcols_.position; d.rotation = bcols_.rotation; d.linvel = bcols_.linvel; d.angvel = bcols_.angvel;
+        d.inv_mass = bcols_.inv_mass; d.inv_inertia_local = bcols_.inv_inertia_local; d.com = bcols_.com; d.lin_damp = bcols_.lin_damp;
+        d.ang_damp = bcols_.ang_damp; d.grav_scale = bcols_.grav_scale; d.lin_acc = bcols_.lin_acc; d.ang_acc = bcols_.ang_acc;
+        d.max_lin = bcols_.max_lin; d.max_ang = bcols_.max_ang;
+        AVN_CUDA(cudaStreamWaitEvent(stream_, ev_prefetch_, 0));
+    } else {
+        if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_prefetch_, 0));   // a prefetch of other columns is still writing these buffers
+        if ((st = upload_body_columns(*bc, false, d)) != AVN_OK) return st;
+    }
+    prefetched_ = false;
     AVN_CUDA(o_pos_.ensure(3 * B * sizeof(S) + 16)); d.out_position = o_pos_.as<S>();
     AVN_CUDA(o_rot_.ensure(4 * B * sizeof(S) + 16)); d.out_rotation = o_rot_.as<S>();
     AVN_CUDA(o_lv_.ensure(3 * B * sizeof(S) + 16)); d.out_linvel = o_lv_.as<S>();

@@ -380,6 +380,7 @@ class DeviceGraphWorld(World):
         self._shape = np.ascontiguousarray(scene.shape_type, dtype=np.uint8)
         self._dims = np.ascontiguousarray(scene.dims, dtype=self.scalar)
         self._order_out = np.empty(n, dtype=np.uint32)
+        self._uploaded_once = False     # from the second step on the static columns (shapes, mass properties ...) stay on the device
 
     def intervals(self, aabb_min: np.ndarray, aabb_max: np.ndarray) -> api.Aabbs:
         o, kind = self.order, self.bodies.kind
@@ -394,12 +395,16 @@ class DeviceGraphWorld(World):
         ctx, b = self.ctx, self.bodies
         ctx.broadphase_upload(aabbs)
         ctx.broadphase_run()
+        # the solver's body columns start moving now, on the library's copy stream, under the broad phase and the contact pipeline
+        ctx.solver_prefetch_bodies(b, static_unchanged=self._uploaded_once)
+        colliders = {"shape": self._shape, "dims": self._dims, "position": b.position, "rotation": b.rotation, "aabb_min": aabb_min, "aabb_max": aabb_max}
+        self.stats = ctx.contacts_step(self.params.dt, 0.005, colliders, b.linear_velocity, b.angular_velocity, bool(self.params.match_contacts), take_pairs=True,
+                                       shapes_unchanged=self._uploaded_once)
         self.new_pairs = ctx.broadphase_download_order()
         kept = int(aabbs.retained_count if aabbs.retained_count is not None else aabbs.collider.shape[0])
         self.order = np.ascontiguousarray(aabbs.collider[aabbs.order_out[:kept]])
-        colliders = {"shape": self._shape, "dims": self._dims, "position": b.position, "rotation": b.rotation, "aabb_min": aabb_min, "aabb_max": aabb_max}
-        self.stats = ctx.contacts_step(self.params.dt, 0.005, colliders, b.linear_velocity, b.angular_velocity, bool(self.params.match_contacts), take_pairs=True)
         ctx.solver_step_resident(self.params, b, self.joints)
+        self._uploaded_once = True
         self.step_index += 1
         return self.stats
 

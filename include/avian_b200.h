@@ -511,6 +511,7 @@ typedef struct AvnContactStep {
     uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];
 } AvnContactStep;
 #define AVN_CONTACTS_TAKE_BROADPHASE_PAIRS 0x1u   /* add the new pairs of the context's last avn_broadphase_run (read in device memory) */
+#define AVN_CONTACTS_SHAPES_UNCHANGED 0x2u        /* input->shape and input->dims equal the previous call's: not copied again */
 /* One step of the contact pipeline on the device: (new pairs ->) rows, geometry + match_contacts for every live row, the status loop, the
  * graphs, the colour-major list.  input: the collider / body columns of AvnNarrowInput (pair arrays ignored).  From the first call on the
  * contact store's pair set is the broad phase's "existing pairs" set (AvnAabbColumns::existing_pairs may stay NULL). */
@@ -519,6 +520,14 @@ AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, cons
 /* The solver stage fed entirely from the device: manifolds from the contact rows, the constraint graph from the last avn_contacts_step.
  * Then avn_solver_run / avn_solver_download (bodies only) as usual. */
 AvnStatus avn_solver_upload_resident(AvnContext* ctx, const AvnStepParams* params, AvnBodyColumns* bodies, AvnJointSet* joints);
+/* Optional, any pipeline: start copying the body columns of the NEXT avn_solver_upload* / avn_solver_step call to the device now, on a second
+ * stream, so that the copy overlaps the stages that run before the solver (broad phase, contact pipeline).  The next upload must be given the
+ * same column pointers (otherwise it simply copies again); the host columns must not change in between.
+ * AVN_BODIES_STATIC_UNCHANGED: the columns that describe the bodies (kind, locked_axes, dominance, integration_flags, inverse_mass,
+ * inverse_inertia_local, center_of_mass, dampings, gravity_scale, max speeds) equal those of the previous upload of the same number of
+ * bodies; only position, rotation, velocities and accelerations are copied. */
+#define AVN_BODIES_STATIC_UNCHANGED 0x1u
+AvnStatus avn_solver_prefetch_bodies(AvnContext* ctx, AvnBodyColumns* bodies, uint32_t flags);
 /* After avn_broadphase_run in the device-resident pipeline: waits for the run, writes order_out / retained_count of the uploaded columns and
  * returns the number of new pairs; the pairs themselves stay on the device for avn_contacts_step. */
 AvnStatus avn_broadphase_download_order(AvnContext* ctx, uint64_t* out_pair_count);
