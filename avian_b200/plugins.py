@@ -402,7 +402,9 @@ class DeviceGraphWorld(World):
                                        shapes_unchanged=self._uploaded_once)
         self.new_pairs = ctx.broadphase_download_order()
         kept = int(aabbs.retained_count if aabbs.retained_count is not None else aabbs.collider.shape[0])
-        self.order = np.ascontiguousarray(aabbs.collider[aabbs.order_out[:kept]])
+        oo = aabbs.order_out[:kept]
+        if kept != aabbs.collider.shape[0] or oo[0] != 0 or not (oo[1:] == oo[:-1] + 1).all():   # (a sorted scene keeps its order: nothing to permute)
+            self.order = np.ascontiguousarray(aabbs.collider[oo])
         ctx.solver_step_resident(self.params, b, self.joints)
         self._uploaded_once = True
         self.step_index += 1

@@ -51,6 +51,10 @@ with api.Context(device=0, scalar=np.float64 if scene.startswith("spheres") else
     print(f"scene {scene}: {steps} steps, {total / steps * 1e3:.3f} ms per step (calls serialised)")
     for k, v in acc.items():
         print(f"  {k:28s} {v / steps * 1e3:8.3f} ms")
-    print("  last solver call on the device:", {k: round(t[k], 3) for k in ("h2d_ms", "total_ms", "d2h_ms")})
+    print("  last solver call on the device:", {k: (round(t[k], 3) if isinstance(t[k], float) else t[k]) for k in
+                                                ("h2d_ms", "prepare_ms", "substep_loop_ms", "finalize_ms", "total_ms", "d2h_ms", "launch_mode", "kernel_launches")})
+    # the same constraints as CSR columns from the host (the ordinary upload path), for comparison of the solver stage alone
+    g = ctx.contacts_download_graph(st["rows_high_water"], st["manifold_count"])
+    print("  colour sizes:", np.diff(st["color_offsets"]).tolist())
     print("  changes per step:", np.mean([s["started_touching"] + s["stopped_touching"] for s in stats]), " colouring rounds:",
           [s["colouring_rounds"] for s in stats][:10], " first frame:", first)
