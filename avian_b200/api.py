@@ -334,6 +334,17 @@ CONTACTS_TAKE_BROADPHASE_PAIRS, CONTACTS_SHAPES_UNCHANGED = 1, 2
 BODIES_STATIC_UNCHANGED = 1
 
 
+class AvnIslandsConfig(C.Structure):
+    _fields_ = [("body_count", C.c_uint32), ("joint_count", C.c_uint32), ("body_kind", _vp), ("sleep_threshold_linear", _vp), ("sleep_threshold_angular", _vp),
+                ("sleeping_disabled", _vp), ("joint_body1", _vp), ("joint_body2", _vp), ("time_to_sleep", C.c_float), ("length_unit", C.c_float)]
+
+
+class AvnIslandsStep(C.Structure):
+    _fields_ = [("delta_secs", C.c_float), ("_pad", C.c_uint32), ("linear_velocity", _vp), ("angular_velocity", _vp), ("wake", _vp), ("island", _vp),
+                ("sleeping", _vp), ("sleep_timer", _vp)] + [(n, C.c_uint32) for n in ("island_count", "sleeping_islands", "islands_put_to_sleep", "islands_woken",
+                                                                                     "split_bodies", "merges")]
+
+
 class AvnNarrowInput(C.Structure):
     _fields_ = [("pair_count", C.c_uint32), ("collider_count", C.c_uint32), ("body_count", C.c_uint32), ("_pad", C.c_uint32)] + [
         (n, _vp) for n in ("collider1", "collider2", "body1", "body2", "shape", "dims", "position", "rotation", "linear_velocity", "angular_velocity",
@@ -396,6 +407,8 @@ def bind_abi(lib: C.CDLL, prefix: str = "avn") -> None:
         "broadphase_download_order": ([_vp, P(C.c_uint64)], C.c_int),
         "contacts_download_graph": ([_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
         "solver_prefetch_bodies": ([_vp, P(AvnBodyColumns), C.c_uint32], C.c_int),
+        "islands_configure": ([_vp, P(AvnIslandsConfig)], C.c_int),
+        "islands_step": ([_vp, P(AvnIslandsStep)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, f"{prefix}_{name}")
@@ -411,7 +424,7 @@ ABI_SYMBOLS = [
     "avn_solver_step_partitioned", "avn_comm_unique_id", "avn_comm_init", "avn_comm_destroy", "avn_comm_all_gather", "avn_narrow_phase", "avn_solver_upload_edges", "avn_solver_upload_graph",
     "avn_contacts_reserve", "avn_contacts_add", "avn_contacts_remove", "avn_contacts_narrow_phase", "avn_contacts_download_impulses",
     "avn_contacts_configure", "avn_contacts_step", "avn_solver_upload_resident", "avn_broadphase_download_order", "avn_contacts_download_graph",
-    "avn_solver_prefetch_bodies"]
+    "avn_solver_prefetch_bodies", "avn_islands_configure", "avn_islands_step"]
 
 RUN_PREPARE, RUN_RESTITUTION, RUN_FINALIZE = 1, 2, 4
 COMM_ID_BYTES = 128
@@ -764,6 +777,32 @@ class Context:
                "touching": np.zeros(capacity, dtype=np.uint8), "colour": np.zeros(capacity, dtype=np.int8), "edge": np.zeros(manifold_count, dtype=np.uint32)}
         self._check(self.lib.avn_contacts_download_graph(self.handle, int(capacity), *(out[k].ctypes.data for k in ("collider1", "collider2", "live", "touching",
                                                                                                                    "colour", "edge"))))
+        return out
+
+    # ---- persistent islands + sleeping decisions (include/avian_b200.h avn_islands_configure / _step)
+    def islands_configure(self, body_kind, joints=None, thr_lin=None, thr_ang=None, disabled=None, time_to_sleep: float = 0.5, length_unit: float = 1.0) -> None:
+        kind = np.ascontiguousarray(body_kind, dtype=np.uint8)
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        tl, ta = f32(thr_lin), f32(thr_ang)
+        dis = None if disabled is None else np.ascontiguousarray(disabled, dtype=np.uint8)
+        j1 = j2 = None
+        nj = 0
+        if joints is not None and len(joints):
+            jj = np.ascontiguousarray(joints, dtype=np.uint32).reshape(-1, 2)
+            j1, j2, nj = np.ascontiguousarray(jj[:, 0]), np.ascontiguousarray(jj[:, 1]), int(jj.shape[0])
+        cfg = AvnIslandsConfig(int(kind.shape[0]), nj, _ptr(kind), _ptr(tl), _ptr(ta), _ptr(dis), _ptr(j1), _ptr(j2), float(time_to_sleep), float(length_unit))
+        self._check(self.lib.avn_islands_configure(self.handle, C.byref(cfg)))
+        self._isl_B = int(kind.shape[0])
+
+    def islands_step(self, delta_secs: float, lin_vel, ang_vel, wake=None) -> dict:
+        B = self._isl_B
+        lv, av = np.ascontiguousarray(lin_vel, dtype=self.scalar), np.ascontiguousarray(ang_vel, dtype=self.scalar)
+        wk = None if wake is None else np.ascontiguousarray(wake, dtype=np.uint8)
+        out = {"island": np.zeros(B, dtype=np.uint32), "sleeping": np.zeros(B, dtype=np.uint8), "sleep_timer": np.zeros(B, dtype=np.float32)}
+        st = AvnIslandsStep(float(delta_secs), 0, _ptr(lv), _ptr(av), _ptr(wk), _ptr(out["island"]), _ptr(out["sleeping"]), _ptr(out["sleep_timer"]))
+        self._check(self.lib.avn_islands_step(self.handle, C.byref(st)))
+        for n in ("island_count", "sleeping_islands", "islands_put_to_sleep", "islands_woken", "split_bodies", "merges"):
+            out[n] = int(getattr(st, n))
         return out
 
     def contacts_download_impulses(self, capacity: int):

@@ -275,6 +275,8 @@ AvnStatus avn_contacts_download_graph(AvnContext* ctx, uint32_t capacity, uint32
                                       uint32_t* edge_list) {
     return guarded(ctx, [&] { return ctx->contacts->download_graph(capacity, collider1, collider2, live, touching, colour, edge_list); });
 }
+AvnStatus avn_islands_configure(AvnContext* ctx, const AvnIslandsConfig* config) { return guarded(ctx, [&] { return ctx->contacts->islands_configure(config); }); }
+AvnStatus avn_islands_step(AvnContext* ctx, AvnIslandsStep* step) { return guarded(ctx, [&] { return ctx->contacts->islands_step(step); }); }
 AvnStatus avn_contacts_download_impulses(AvnContext* ctx, void* warm_start_normal, void* warm_start_tangent, void* normal_impulse) {
     return guarded(ctx, [&] { return ctx->contacts->download_impulses(warm_start_normal, warm_start_tangent, normal_impulse); });
 }

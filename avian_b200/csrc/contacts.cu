@@ -38,6 +38,7 @@ namespace cg = cooperative_groups;
 // push / swap_remove list order, maintained by one thread.
 // =====================================================================================================================================
 enum { CH_NONE = 0, CH_PUSH = 1, CH_POP = 2, CH_REMOVE = 3, CH_MASK = 3, CH_DONE = 0x10 };
+enum { ISL_NONE = 0, ISL_ADD = 1, ISL_REMOVE = 2 };
 
 struct GraphCounters {          // device block, copied to the host once per step
     // cleared at the start of every step
@@ -53,6 +54,7 @@ struct GraphRows {
     uint32_t* c1; uint32_t* c2; uint32_t* b1; uint32_t* b2;
     uint8_t* live; uint8_t* count; uint8_t* disjoint; uint8_t* prev_count;
     uint8_t* pflags; uint8_t* touching; uint8_t* colour /* 0 = none, c + 1 */; uint8_t* change; uint8_t* old_colour;
+    uint8_t* isl_event;                           // this step's event for the islands: ISL_ADD / ISL_REMOVE (a linked contact came or went)
     uint32_t* ovf_pos; uint32_t* ovf;
     const uint8_t* body_kind; int n_bodies;
     uint32_t* body_bits;                          // [B] bit c: the body is in colour c's body set
@@ -68,6 +70,7 @@ __global__ void add_rows_kernel(GraphRows g, uint32_t n_new, const uint32_t* __r
     const uint32_t e = k < n_free ? free_list[k] : old_hw + (k - n_free);
     g.c1[e] = pc1[k]; g.c2[e] = pc2[k]; g.b1[e] = pb1[k]; g.b2[e] = pb2[k];
     g.pflags[e] = pfl[k];
+    g.isl_event[e] = 0;
     g.live[e] = 1;            // a ContactId handed to a new pair starts without history
     g.count[e] = 0; g.prev_count[e] = 0; g.touching[e] = 0; g.colour[e] = 0; g.change[e] = 0;
 }
@@ -84,25 +87,28 @@ __global__ void free_keys_kernel(const uint8_t* __restrict__ live, int n, uint32
 __global__ void classify_kernel(GraphRows g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= g.hw) return;
-    uint8_t ch = CH_NONE;
+    uint8_t ch = CH_NONE, ev = ISL_NONE;
     if (g.live[e]) {
         const bool gen = (g.pflags[e] & AVN_PAIR_GENERATE_CONSTRAINTS) != 0;
         if (g.disjoint[e]) {
             ch = CH_REMOVE | (g.colour[e] ? 0 : CH_DONE);
             atomicAdd(&g.ctr->removed, 1u);
+            if (gen && g.touching[e]) ev = ISL_REMOVE;    // PhysicsIslands::remove_contact (system_param.rs:196-205)
         } else {
             const bool now = g.count[e] > 0, was = g.touching[e] != 0;
             if (now && !was) {
                 g.touching[e] = 1;
                 atomicAdd(&g.ctr->started, 1u);
-                if (gen) ch = CH_PUSH;
+                if (gen) { ch = CH_PUSH; ev = ISL_ADD; }   // add_contact (system_param.rs:244-258)
             } else if (!now && was) {
                 g.touching[e] = 0;
                 atomicAdd(&g.ctr->stopped, 1u);
                 if (gen && g.colour[e]) ch = CH_POP;
+                if (gen) ev = ISL_REMOVE;                  // remove_contact (system_param.rs:306-313)
             }
         }
     }
+    g.isl_event[e] = ev;
     g.change[e] = ch;
     if (ch) atomicAdd(&g.ctr->changed, 1u);
     keys[e] = ch ? 0u : 1u;
@@ -343,6 +349,188 @@ __global__ void __launch_bounds__(128) narrow_edges_kernel(const __grid_constant
     if (e < a.r.E) narrow_edge_row<S>(a, e);   // csrc/contact_rows.hpp: the same function the CPU tests run
 }
 
+
+// =====================================================================================================================================
+// Persistent simulation islands + sleeping (dynamics/solver/islands/mod.rs, islands/sleeping.rs).
+// An island is a tree of a lock-free union-find forest over the non-static bodies (root = smallest body index).  Merging is the classic
+// CAS hook (every edge is processed once, in any order); the per-island state (constraints_removed, is_sleeping) lives at the root and moves
+// to the new root when a root is hooked under another.  Nothing is rebuilt per step: islands only change when a linked contact comes (merge),
+// goes (constraints_removed += 1) or when the split candidate is split (its bodies are reset to singletons and re-linked through the contacts
+// and joints that are still there).
+// =====================================================================================================================================
+struct IslandCounters { uint32_t islands, sleeping, put_to_sleep, woken, split_bodies, merges, split_root, _pad; unsigned long long cand; };
+constexpr uint32_t ISL_NONE_BODY = 0xffffffffu;
+
+struct IslandState {
+    int B;
+    const uint8_t* kind;
+    uint32_t* parent; uint32_t* root; uint32_t* root_prev; uint32_t* removed;
+    uint8_t* isl_sleeping; uint8_t* awake; uint8_t* need_wake; uint8_t* touched; uint8_t* in_split;
+    float* timer;
+    const float* thr_lin; const float* thr_ang; const uint8_t* disabled; const uint8_t* host_wake;
+    uint32_t* cand_body;
+    IslandCounters* ctr;
+    float time_to_sleep, delta_secs;
+};
+__device__ __forceinline__ bool isl_static(const IslandState& s, uint32_t b) { return b >= uint32_t(s.B) || s.kind[b] == AVN_BODY_STATIC; }
+__device__ __forceinline__ uint32_t isl_find(uint32_t* parent, uint32_t x) {
+    uint32_t p = *reinterpret_cast<volatile uint32_t*>(&parent[x]);
+    while (p != x) {
+        const uint32_t gp = *reinterpret_cast<volatile uint32_t*>(&parent[p]);
+        if (gp != p) parent[x] = gp;   // path halving: any ancestor is a valid parent (roots only ever move under smaller roots)
+        x = p; p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ bool isl_union(uint32_t* parent, uint32_t u, uint32_t v) {
+    for (;;) {
+        uint32_t ru = isl_find(parent, u), rv = isl_find(parent, v);
+        if (ru == rv) return false;
+        if (ru < rv) { const uint32_t t = ru; ru = rv; rv = t; }
+        if (atomicCAS(&parent[ru], ru, rv) == ru) return true;   // the larger root goes under the smaller one
+    }
+}
+__global__ void isl_init_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    s.parent[b] = uint32_t(b); s.root[b] = uint32_t(b); s.root_prev[b] = uint32_t(b); s.removed[b] = 0;
+    s.isl_sleeping[b] = 0; s.awake[b] = 0; s.need_wake[b] = 0; s.touched[b] = 0; s.in_split[b] = 0; s.timer[b] = 0.f;
+    if (b == 0) { *s.cand_body = ISL_NONE_BODY; }
+}
+// PhysicsIslands::add_joint at configuration time, and the joints of a split island
+__global__ void isl_joint_kernel(IslandState s, const uint32_t* __restrict__ j1, const uint32_t* __restrict__ j2, int J, int only_split) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    const uint32_t a = j1[j], b = j2[j];
+    if (isl_static(s, a) || isl_static(s, b)) return;
+    if (only_split && !(s.in_split[a] && s.in_split[b])) return;
+    isl_union(s.parent, a, b);
+}
+// add_contact: merge the islands of the two bodies (mod.rs:513-592); a contact that reaches a sleeping island wakes it (system_param.rs:253-258)
+__global__ void isl_add_kernel(IslandState s, GraphRows g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw || g.isl_event[e] != ISL_ADD) return;
+    const uint32_t a = g.b1[e], b = g.b2[e];
+    const bool sa = isl_static(s, a), sb = isl_static(s, b);
+    if (!sa) s.touched[a] = 1;
+    if (!sb) s.touched[b] = 1;
+    if (!sa && !sb && isl_union(s.parent, a, b)) atomicAdd(&s.ctr->merges, 1u);
+}
+// after the merges: every body learns its root; a root that was hooked under another hands its island state over (merge_islands, mod.rs:965)
+__global__ void isl_flatten_kernel(IslandState s, int split_only) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b))) return;
+    if (split_only) {
+        if (!s.in_split[b]) return;
+        s.root[b] = isl_find(s.parent, uint32_t(b));
+        s.removed[b] = 0;               // the islands that come out of a split start clean (split_island, mod.rs:995-1270)
+        return;
+    }
+    const uint32_t r = isl_find(s.parent, uint32_t(b));
+    s.root[b] = r;
+    if (s.root_prev[b] == uint32_t(b) && r != uint32_t(b)) {
+        if (s.removed[b]) { atomicAdd(&s.removed[r], s.removed[b]); s.removed[b] = 0; }
+        if (s.isl_sleeping[b]) { s.isl_sleeping[b] = 0; s.need_wake[r] = 1; s.touched[b] = 1; }
+    }
+}
+__global__ void isl_wake_marks_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b))) return;
+    if (s.touched[b] || (s.host_wake && s.host_wake[b])) s.need_wake[s.root[b]] = 1;
+}
+// remove_contact: constraints_removed += 1 on the island the contact was linked to (mod.rs:594-667)
+__global__ void isl_remove_kernel(IslandState s, GraphRows g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw || g.isl_event[e] != ISL_REMOVE) return;
+    const uint32_t a = g.b1[e], b = g.b2[e];
+    const uint32_t x = !isl_static(s, a) ? a : b;
+    if (isl_static(s, x)) return;
+    atomicAdd(&s.removed[s.root[x]], 1u);
+}
+// split_island (SolverSystems::Finalize): the island that holds last step's candidate, if it is awake and lost a constraint
+__global__ void isl_split_pick_kernel(IslandState s) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t pick = ISL_NONE_BODY;
+    const uint32_t c = *s.cand_body;
+    if (c != ISL_NONE_BODY && !isl_static(s, c)) {
+        const uint32_t r = s.root[c];
+        if (!s.isl_sleeping[r] && !s.need_wake[r] && s.removed[r] > 0) pick = r;
+    }
+    s.ctr->split_root = pick;
+}
+__global__ void isl_split_reset_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    const uint32_t R = s.ctr->split_root;
+    const bool in = R != ISL_NONE_BODY && !isl_static(s, uint32_t(b)) && s.root[b] == R;
+    s.in_split[b] = in ? 1 : 0;
+    if (in) { s.parent[b] = uint32_t(b); atomicAdd(&s.ctr->split_bodies, 1u); }
+}
+__global__ void isl_split_link_kernel(IslandState s, GraphRows g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw || s.ctr->split_root == ISL_NONE_BODY) return;
+    if (!g.live[e] || !g.touching[e] || !(g.pflags[e] & AVN_PAIR_GENERATE_CONSTRAINTS)) return;
+    const uint32_t a = g.b1[e], b = g.b2[e];
+    if (isl_static(s, a) || isl_static(s, b) || !s.in_split[a] || !s.in_split[b]) return;
+    isl_union(s.parent, a, b);
+}
+// WakeIslands for the marked islands: timers back to zero (sleeping.rs WakeIslands::apply)
+__global__ void isl_wake_bodies_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b))) return;
+    const uint32_t r = s.root[b];
+    if (s.need_wake[r] && s.isl_sleeping[r]) s.timer[b] = 0.f;
+}
+__global__ void isl_wake_roots_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b)) || s.root[b] != uint32_t(b)) return;
+    if (s.need_wake[b] && s.isl_sleeping[b]) { s.isl_sleeping[b] = 0; atomicAdd(&s.ctr->woken, 1u); }
+}
+// update_sleeping_states + wake_islands_with_sleeping_disabled (sleeping.rs:164-246)
+template <class S>
+__global__ void isl_timers_kernel(IslandState s, const S* __restrict__ lv, const S* __restrict__ av, S length_unit_squared) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b))) return;
+    const uint32_t r = s.root[b];
+    if (s.isl_sleeping[r]) return;                       // Without<Sleeping>
+    if (s.disabled && s.disabled[b]) { s.awake[r] = 1; s.timer[b] = 0.f; return; }
+    const S lx = lv[3 * b], ly = lv[3 * b + 1], lz = lv[3 * b + 2], ax = av[3 * b], ay = av[3 * b + 1], az = av[3 * b + 2];
+    const S lin2 = (lx * lx + ly * ly) + lz * lz, ang2 = (ax * ax + ay * ay) + az * az;
+    const float tl = s.thr_lin ? s.thr_lin[b] : 0.15f, ta = s.thr_ang ? s.thr_ang[b] : 0.15f;
+    const float tl2 = tl * fabsf(tl), ta2 = ta * fabsf(ta);   // keep signs
+    float t = s.timer[b];
+    if (lin2 < length_unit_squared * S(tl2) && ang2 < S(ta2)) t += s.delta_secs; else t = 0.f;
+    s.timer[b] = t;
+    if (t < s.time_to_sleep) {
+        s.awake[r] = 1;
+    } else if (s.removed[r] > 0) {
+        // the sleepiest body that wants to sleep in an island that needs splitting; the first such body in index order on ties
+        atomicMax(&s.ctr->cand, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(0xffffffffu - uint32_t(b)));
+    }
+}
+// sleep_islands (sleeping.rs:248-292)
+__global__ void isl_decide_kernel(IslandState s) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B || isl_static(s, uint32_t(b)) || s.root[b] != uint32_t(b)) return;
+    atomicAdd(&s.ctr->islands, 1u);
+    if (!s.awake[b] && !s.isl_sleeping[b] && s.removed[b] == 0) { s.isl_sleeping[b] = 1; atomicAdd(&s.ctr->put_to_sleep, 1u); }
+    if (s.isl_sleeping[b]) atomicAdd(&s.ctr->sleeping, 1u);
+}
+__global__ void isl_finish_kernel(IslandState s, uint32_t* __restrict__ out_island, uint8_t* __restrict__ out_sleeping) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= s.B) return;
+    const bool st = isl_static(s, uint32_t(b));
+    const uint32_t r = st ? ISL_NONE_BODY : s.root[b];
+    out_island[b] = r;
+    out_sleeping[b] = (!st && s.isl_sleeping[r]) ? 1 : 0;
+    s.root_prev[b] = st ? uint32_t(b) : r;
+    s.awake[b] = 0; s.need_wake[b] = 0; s.touched[b] = 0; s.in_split[b] = 0;
+    if (b == 0) {
+        const unsigned long long c = s.ctr->cand;
+        if (c != 0ull) *s.cand_body = 0xffffffffu - uint32_t(c & 0xffffffffull);   // otherwise the previous candidate stands (sleeping.rs:199)
+    }
+}
+
 template <class S>
 class Contacts final : public ContactsBase {
    public:
@@ -359,6 +547,7 @@ class Contacts final : public ContactsBase {
     }
     ~Contacts() override {
         if (h_ctr_) cudaFreeHost(h_ctr_);
+        if (h_isl_) cudaFreeHost(h_isl_);
         if (ev_in_) cudaEventDestroy(ev_in_);
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
     }
@@ -372,7 +561,7 @@ class Contacts final : public ContactsBase {
                       {&prev_a2_, 12 * sizeof(double)}, {&ws_n_in_, 4 * sizeof(S)}, {&ws_t_in_, 8 * sizeof(S)}, {&ws_n_out_, 4 * sizeof(S)},
                       {&ws_t_out_, 8 * sizeof(S)}, {&nimp_in_, 4 * sizeof(S)}, {&nimp_out_, 4 * sizeof(S)},
                       // graph state per row (zero = no flags, not touching, no colour)
-                      {&pflags_, 1}, {&touching_, 1}, {&colour_, 1}, {&change_, 1}, {&old_colour_, 1}, {&ovf_pos_, 4}, {&ovf_, 4}};
+                      {&pflags_, 1}, {&touching_, 1}, {&colour_, 1}, {&change_, 1}, {&old_colour_, 1}, {&ovf_pos_, 4}, {&ovf_, 4}, {&isl_event_, 1}};
         for (Col& c : cols) {   // grow, keep the old rows, zero the new ones
             void* fresh = nullptr;
             AVN_CUDA(cudaMalloc(&fresh, n * c.bytes_per_row));
@@ -611,6 +800,114 @@ class Contacts final : public ContactsBase {
         return AVN_OK;
     }
 
+    // ---- islands + sleeping -------------------------------------------------------------------------------------------------------
+    AvnStatus islands_configure(const AvnIslandsConfig* cfg) override {
+        if (!cfg || !cfg->body_kind) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "islands_configure: config and body_kind are required");
+        if (cfg->joint_count && (!cfg->joint_body1 || !cfg->joint_body2)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "islands_configure: joint bodies are required");
+        const size_t B = cfg->body_count, Bp = std::max<size_t>(B, 1);
+        // one allocation: kind | parent root root_prev removed | 5 byte arrays | timer | thresholds | disabled | cand_body | counters
+        const size_t words = 4 * Bp, bytes = 6 * Bp, floats = 3 * Bp;
+        AVN_CUDA(isl_buf_.ensure(words * 4 + floats * 4 + bytes + Bp + 64 + sizeof(IslandCounters) + 256));
+        char* p = isl_buf_.as<char>();
+        IslandState s{};
+        s.B = int(B);
+        s.parent = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
+        s.root = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
+        s.root_prev = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
+        s.removed = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
+        s.timer = reinterpret_cast<float*>(p); p += Bp * 4;
+        float* thr_lin = reinterpret_cast<float*>(p); p += Bp * 4;
+        float* thr_ang = reinterpret_cast<float*>(p); p += Bp * 4;
+        s.cand_body = reinterpret_cast<uint32_t*>(p); p += 16;
+        s.ctr = reinterpret_cast<IslandCounters*>(p); p += (sizeof(IslandCounters) + 15) & ~size_t(15);
+        uint8_t* kind = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.isl_sleeping = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.awake = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.need_wake = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.touched = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.in_split = reinterpret_cast<uint8_t*>(p); p += Bp;
+        uint8_t* disabled = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.kind = kind;
+        AVN_CUDA(cudaMemcpyAsync(kind, cfg->body_kind, B, cudaMemcpyHostToDevice, stream_));
+        isl_has_thr_lin_ = cfg->sleep_threshold_linear != nullptr; isl_has_thr_ang_ = cfg->sleep_threshold_angular != nullptr;
+        isl_has_disabled_ = cfg->sleeping_disabled != nullptr;
+        if (isl_has_thr_lin_) AVN_CUDA(cudaMemcpyAsync(thr_lin, cfg->sleep_threshold_linear, B * 4, cudaMemcpyHostToDevice, stream_));
+        if (isl_has_thr_ang_) AVN_CUDA(cudaMemcpyAsync(thr_ang, cfg->sleep_threshold_angular, B * 4, cudaMemcpyHostToDevice, stream_));
+        if (isl_has_disabled_) AVN_CUDA(cudaMemcpyAsync(disabled, cfg->sleeping_disabled, B, cudaMemcpyHostToDevice, stream_));
+        s.thr_lin = isl_has_thr_lin_ ? thr_lin : nullptr; s.thr_ang = isl_has_thr_ang_ ? thr_ang : nullptr; s.disabled = isl_has_disabled_ ? disabled : nullptr;
+        s.time_to_sleep = cfg->time_to_sleep > 0.f ? cfg->time_to_sleep : 0.5f;
+        isl_length_unit_ = cfg->length_unit > 0.f ? cfg->length_unit : 1.f;
+        AVN_CUDA(cudaMemsetAsync(s.ctr, 0, sizeof(IslandCounters), stream_));
+        isl_ = s;
+        isl_B_ = uint32_t(B);
+        isl_J_ = cfg->joint_count;
+        if (B) isl_init_kernel<<<unsigned((B + 255) / 256), 256, 0, stream_>>>(isl_);
+        if (isl_J_) {   // joints link their bodies' islands from the start (PhysicsIslands::add_joint, mod.rs:669-747)
+            AVN_CUDA(isl_j_.ensure(size_t(isl_J_) * 8));
+            AVN_CUDA(cudaMemcpyAsync(isl_j_.p, cfg->joint_body1, size_t(isl_J_) * 4, cudaMemcpyHostToDevice, stream_));
+            AVN_CUDA(cudaMemcpyAsync(isl_j_.as<uint32_t>() + isl_J_, cfg->joint_body2, size_t(isl_J_) * 4, cudaMemcpyHostToDevice, stream_));
+            isl_joint_kernel<<<(isl_J_ + 255) / 256, 256, 0, stream_>>>(isl_, isl_j_.as<uint32_t>(), isl_j_.as<uint32_t>() + isl_J_, int(isl_J_), 0);
+            IslandState t = isl_;
+            t.root_prev = t.root;   // (nothing to hand over yet)
+            isl_flatten_kernel<<<unsigned((B + 255) / 256), 256, 0, stream_>>>(isl_, 0);
+            AVN_CUDA(cudaMemcpyAsync(isl_.root_prev, isl_.root, B * 4, cudaMemcpyDeviceToDevice, stream_));
+        }
+        AVN_CUDA(cudaGetLastError());
+        if (!h_isl_) AVN_CUDA(cudaHostAlloc(&h_isl_, sizeof(IslandCounters), cudaHostAllocDefault));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        isl_configured_ = true;
+        return AVN_OK;
+    }
+
+    AvnStatus islands_step(AvnIslandsStep* st) override {
+        if (!st || !st->linear_velocity || !st->angular_velocity) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "islands_step: step and the velocity columns are required");
+        if (!isl_configured_) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "avn_islands_step before avn_islands_configure");
+        const size_t B = isl_B_;
+        if (B == 0) return AVN_OK;
+        AVN_CUDA(isl_in_.ensure(2 * 3 * B * sizeof(S) + B));
+        S* lv = isl_in_.as<S>(); S* av = lv + 3 * B;
+        uint8_t* wake = reinterpret_cast<uint8_t*>(av + 3 * B);
+        AVN_CUDA(cudaMemcpyAsync(lv, st->linear_velocity, 3 * B * sizeof(S), cudaMemcpyHostToDevice, stream_));
+        AVN_CUDA(cudaMemcpyAsync(av, st->angular_velocity, 3 * B * sizeof(S), cudaMemcpyHostToDevice, stream_));
+        if (st->wake) AVN_CUDA(cudaMemcpyAsync(wake, st->wake, B, cudaMemcpyHostToDevice, stream_));
+        AVN_CUDA(isl_out_.ensure(B * 4 + B));
+        uint32_t* out_island = isl_out_.as<uint32_t>();
+        uint8_t* out_sleeping = reinterpret_cast<uint8_t*>(out_island + B);
+        IslandState s = isl_;
+        s.host_wake = st->wake ? wake : nullptr;
+        s.delta_secs = st->delta_secs;
+        AVN_CUDA(cudaMemsetAsync(s.ctr, 0, sizeof(IslandCounters), stream_));
+        const unsigned bb = unsigned((B + 255) / 256);
+        GraphRows g = graph_rows();
+        const unsigned rb = g.hw > 0 ? unsigned((g.hw + 255) / 256) : 0;
+        // narrow-phase part: contacts that came (merge) and went (constraints_removed), islands reached by a new contact wake up
+        if (rb) isl_add_kernel<<<rb, 256, 0, stream_>>>(s, g);
+        isl_flatten_kernel<<<bb, 256, 0, stream_>>>(s, 0);
+        isl_wake_marks_kernel<<<bb, 256, 0, stream_>>>(s);
+        if (rb) isl_remove_kernel<<<rb, 256, 0, stream_>>>(s, g);
+        // SolverSystems::Finalize: split last step's candidate
+        isl_split_pick_kernel<<<1, 32, 0, stream_>>>(s);
+        isl_split_reset_kernel<<<bb, 256, 0, stream_>>>(s);
+        if (rb) isl_split_link_kernel<<<rb, 256, 0, stream_>>>(s, g);
+        if (isl_J_) isl_joint_kernel<<<(isl_J_ + 255) / 256, 256, 0, stream_>>>(s, isl_j_.as<uint32_t>(), isl_j_.as<uint32_t>() + isl_J_, int(isl_J_), 1);
+        isl_flatten_kernel<<<bb, 256, 0, stream_>>>(s, 1);
+        // PhysicsStepSystems::Sleeping
+        isl_wake_bodies_kernel<<<bb, 256, 0, stream_>>>(s);
+        isl_wake_roots_kernel<<<bb, 256, 0, stream_>>>(s);
+        isl_timers_kernel<S><<<bb, 256, 0, stream_>>>(s, lv, av, S(isl_length_unit_) * S(isl_length_unit_));
+        isl_decide_kernel<<<bb, 256, 0, stream_>>>(s);
+        isl_finish_kernel<<<bb, 256, 0, stream_>>>(s, out_island, out_sleeping);
+        AVN_CUDA(cudaGetLastError());
+        AVN_CUDA(cudaMemcpyAsync(h_isl_, s.ctr, sizeof(IslandCounters), cudaMemcpyDeviceToHost, stream_));
+        if (st->island) AVN_CUDA(cudaMemcpyAsync(st->island, out_island, B * 4, cudaMemcpyDeviceToHost, stream_));
+        if (st->sleeping) AVN_CUDA(cudaMemcpyAsync(st->sleeping, out_sleeping, B, cudaMemcpyDeviceToHost, stream_));
+        if (st->sleep_timer) AVN_CUDA(cudaMemcpyAsync(st->sleep_timer, s.timer, B * 4, cudaMemcpyDeviceToHost, stream_));
+        AVN_CUDA(cudaStreamSynchronize(stream_));
+        st->island_count = h_isl_->islands; st->sleeping_islands = h_isl_->sleeping; st->islands_put_to_sleep = h_isl_->put_to_sleep;
+        st->islands_woken = h_isl_->woken; st->split_bodies = h_isl_->split_bodies; st->merges = h_isl_->merges;
+        return AVN_OK;
+    }
+
    private:
     // the collider / body columns of a step -> device (on `s`); keep_shapes: shape and dims are those of the previous call
     AvnStatus upload_inputs(const AvnNarrowInput* in, bool keep_shapes, cudaStream_t s) {
@@ -677,7 +974,7 @@ class Contacts final : public ContactsBase {
         g.c1 = c1_.as<uint32_t>(); g.c2 = c2_.as<uint32_t>(); g.b1 = b1_.as<uint32_t>(); g.b2 = b2_.as<uint32_t>();
         g.live = live_.as<uint8_t>(); g.count = count_.as<uint8_t>(); g.disjoint = disjoint_.as<uint8_t>(); g.prev_count = prev_count_.as<uint8_t>();
         g.pflags = pflags_.as<uint8_t>(); g.touching = touching_.as<uint8_t>(); g.colour = colour_.as<uint8_t>(); g.change = change_.as<uint8_t>();
-        g.old_colour = old_colour_.as<uint8_t>(); g.ovf_pos = ovf_pos_.as<uint32_t>(); g.ovf = ovf_.as<uint32_t>();
+        g.old_colour = old_colour_.as<uint8_t>(); g.ovf_pos = ovf_pos_.as<uint32_t>(); g.ovf = ovf_.as<uint32_t>(); g.isl_event = isl_event_.as<uint8_t>();
         g.body_kind = kind_.as<uint8_t>(); g.n_bodies = int(n_bodies_);
         g.body_bits = body_bits_.as<uint32_t>(); g.body_min = body_min_.as<unsigned long long>();
         g.ctr = ctr_.as<GraphCounters>();
@@ -714,6 +1011,12 @@ class Contacts final : public ContactsBase {
     DevBuf i_shape_, i_dims_, i_pos_, i_rot_, i_lv_, i_av_, i_amin_, i_amax_;
     // graphs
     using ResidentGraph = ContactsBase::ResidentGraph;
+    DevBuf isl_event_, isl_buf_, isl_in_, isl_out_, isl_j_;
+    IslandState isl_{};
+    IslandCounters* h_isl_ = nullptr;
+    uint32_t isl_B_ = 0, isl_J_ = 0;
+    float isl_length_unit_ = 1.f;
+    bool isl_configured_ = false, isl_has_thr_lin_ = false, isl_has_thr_ang_ = false, isl_has_disabled_ = false;
     DevBuf pflags_, touching_, colour_, change_, old_colour_, ovf_pos_, ovf_, kind_, fr_, re_, body_bits_, body_min_, ctr_, k0_, k1_, v0_, v1_, hist_, list_, m_b1_, m_b2_,
         m_fr_, m_re_, table_;
     GraphCounters* h_ctr_ = nullptr;

@@ -149,6 +149,9 @@ struct ContactsBase {
     virtual AvnStatus graph_view(ResidentGraph* out) = 0;
     virtual void pair_set(const uint64_t** table, uint64_t* mask) = 0;
     virtual AvnStatus download_graph(uint32_t capacity, uint32_t* c1, uint32_t* c2, uint8_t* live, uint8_t* touching, int8_t* colour, uint32_t* edge_list) = 0;
+    // ---- persistent simulation islands + sleeping decisions (contacts.cu)
+    virtual AvnStatus islands_configure(const AvnIslandsConfig* cfg) = 0;
+    virtual AvnStatus islands_step(AvnIslandsStep* step) = 0;
 };
 ContactsBase* make_contacts(uint32_t scalar_bits, cudaStream_t stream, ErrorSink* err);
 

@@ -536,6 +536,43 @@ AvnStatus avn_broadphase_download_order(AvnContext* ctx, uint64_t* out_pair_coun
 AvnStatus avn_contacts_download_graph(AvnContext* ctx, uint32_t capacity, uint32_t* collider1, uint32_t* collider2, uint8_t* live, uint8_t* touching,
                                       int8_t* colour, uint32_t* edge_list);
 
+/* ---- simulation islands and sleeping on the device (SURVEY.md 8f "next #4").  Replaces the bookkeeping and the decisions of
+ *        PhysicsIslands::add_contact / remove_contact / add_joint / merge_islands / split_island   (dynamics/solver/islands/mod.rs:513-1270)
+ *        update_sleeping_states, wake_islands_with_sleeping_disabled, sleep_islands                 (dynamics/solver/islands/sleeping.rs:164-292)
+ *      Islands are PERSISTENT like the reference's: merged when a touching, constraint-generating contact (or a joint) links two of them,
+ *      marked (constraints_removed) when such a contact goes, and split lazily — one island per step, the one holding the sleepiest body
+ *      that wants to sleep — by recomputing its connected components.  The contact events come from the last avn_contacts_step of this
+ *      context (the rows on the device); the body velocities are the solver's results of the same step.  Output: island label and Sleeping
+ *      flag per body; APPLYING a decision (taking a sleeping body's constraints out of the step, `Sleeping` component) stays with the host
+ *      shim, like the reference's SleepIslands / WakeIslands commands.
+ *      One deviation, stated: the reference tracks the split candidate as an island id that a merge can retire (when the candidate is the
+ *      smaller island of the merge); here the candidate is the sleepiest BODY, and the island that holds it one step later is split. -------- */
+typedef struct AvnIslandsConfig {
+    uint32_t body_count, joint_count;
+    const uint8_t* body_kind;            /* [B] AvnBodyKind: static bodies have no island */
+    const float* sleep_threshold_linear; /* [B] SleepThreshold::linear  (NULL = 0.15; negative = never sleeps) */
+    const float* sleep_threshold_angular;/* [B] SleepThreshold::angular (NULL = 0.15) */
+    const uint8_t* sleeping_disabled;    /* [B] SleepingDisabled marker (NULL = none) */
+    const uint32_t* joint_body1;         /* [J] bodies linked by joints (PhysicsIslands::add_joint) */
+    const uint32_t* joint_body2;
+    float time_to_sleep;                 /* TimeToSleep (default 0.5 s) */
+    float length_unit;                   /* PhysicsLengthUnit */
+} AvnIslandsConfig;
+AvnStatus avn_islands_configure(AvnContext* ctx, const AvnIslandsConfig* config);
+
+typedef struct AvnIslandsStep {
+    float delta_secs;                    /* in: Time::delta_secs of the step */
+    uint32_t _pad;
+    const void* linear_velocity;         /* in: [B][3] SolverBody velocities after the solve (column scalar type) */
+    const void* angular_velocity;        /* in: [B][3] */
+    const uint8_t* wake;                 /* in: [B] optional: bodies the application touched (wake_on_changed): their islands wake up */
+    uint32_t* island;                    /* out: [B] island label = smallest body index of the island (0xFFFFFFFF for static bodies); NULL = skip */
+    uint8_t* sleeping;                   /* out: [B] 1 = the body's island sleeps; NULL = skip */
+    float* sleep_timer;                  /* out: [B] SleepTimer; NULL = skip */
+    uint32_t island_count, sleeping_islands, islands_put_to_sleep, islands_woken, split_bodies, merges;   /* out */
+} AvnIslandsStep;
+AvnStatus avn_islands_step(AvnContext* ctx, AvnIslandsStep* step);
+
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
 
 /*

@@ -1,0 +1,80 @@
+"""Persistent simulation islands + sleeping decisions on the device (avn_islands_configure / avn_islands_step) against the
+CPU restatement of dynamics/solver/islands/{mod,sleeping}.rs (oracle/islands_oracle.py).  The contact events are the device contact store's
+own (avn_contacts_step); the oracle receives the same events, reconstructed from the downloaded rows, and the same velocities.  Every step:
+the same partition of the bodies into islands, the same Sleeping flags, the same sleep timers."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests")); sys.path.insert(0, str(ROOT / "oracle"))
+from avian_b200 import api, plugins, scenes  # noqa: E402
+from islands_oracle import IslandsOracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _events(prev, now):
+    """(contact id, 'add' | 'remove', body1, body2) from two snapshots of the rows (colliders are the bodies in this fixture; every pair
+    generates constraints)"""
+    ev = []
+    n = max(prev["live"].shape[0], now["live"].shape[0])
+    def col(g, k, fill=0):
+        a = np.full(n, fill, dtype=g[k].dtype); a[:g[k].shape[0]] = g[k]; return a
+    pt, nt = col(prev, "touching").astype(bool), col(now, "touching").astype(bool)
+    same = (col(prev, "collider1") == col(now, "collider1")) & (col(prev, "collider2") == col(now, "collider2"))
+    for e in np.nonzero(pt & ~(nt & same))[0]:
+        ev.append((int(e), "remove", int(prev["collider1"][e]), int(prev["collider2"][e])))
+    for e in np.nonzero(nt & ~(pt & same))[0]:
+        ev.append((int(e), "add", int(now["collider1"][e]), int(now["collider2"][e])))
+    return ev
+
+
+def _kick(w, seed):
+    rng = np.random.default_rng(seed)
+    dyn = w.bodies.kind == api.BODY_DYNAMIC
+    w.bodies.linear_velocity[dyn] = rng.normal(0, 1.5, size=(int(dyn.sum()), 3)).astype(w.scalar)
+    w.bodies.angular_velocity[dyn] = rng.normal(0, 2.0, size=(int(dyn.sum()), 3)).astype(w.scalar)
+
+
+@pytest.mark.parametrize("scene_fn,steps,kick,time_to_sleep", [
+    (lambda: scenes.cube_stack(4, 3, 4, brick=False), 90, 0, 0.5),     # 16 independent columns: merge, settle, sleep after 0.5 s
+    (lambda: scenes.cubes_example(3), 150, 7, 0.25),                   # tumbling cubes: merges, removals, deferred splits, sleep, wake by contact
+    (lambda: scenes.cube_stack(5, 4, 4, brick=True), 120, 0, 0.3),     # one coupled pile
+    (lambda: scenes.ragdoll_field(6, pitch=2.5, drop_height=0.3), 100, 0, 0.4),   # joints keep the bodies of a ragdoll in one island
+])
+def test_islands_and_sleeping_equal_the_oracle(gpu_ctx, scene_fn, steps, kick, time_to_sleep):
+    sc = scene_fn()
+    scalar = sc.bodies.position.dtype
+    with api.Context(device=0, scalar=scalar) as ctx:
+        w = plugins.DeviceGraphWorld(sc, plugins.PhysicsPlugins(ctx), ctx, substeps=4)
+        if kick:
+            _kick(w, kick)
+        kind = w.bodies.kind
+        joints = None
+        if w.joints is not None and w.joints.count:
+            joints = np.concatenate([np.stack([t.body1, t.body2], axis=1) for t in w.joints.types.values() if t.count]).astype(np.uint32)
+        rng = np.random.default_rng(1)
+        disabled = (rng.random(kind.shape[0]) < 0.03).astype(np.uint8)      # a few SleepingDisabled bodies keep their islands awake
+        ctx.islands_configure(kind, joints=joints, disabled=disabled, time_to_sleep=time_to_sleep)
+        orc = IslandsOracle(kind, joints=[] if joints is None else joints.tolist(), disabled=disabled, time_to_sleep=time_to_sleep, scalar=scalar)
+        empty = {k: np.zeros(0, dtype=d) for k, d in (("collider1", np.uint32), ("collider2", np.uint32), ("live", np.uint8), ("touching", np.uint8))}
+        prev = empty
+        slept = woke = splits = 0
+        for i in range(steps):
+            w.step()
+            st = w.stats
+            now = ctx.contacts_download_graph(st["rows_high_water"], 0)
+            ev = _events(prev, now)
+            prev = now
+            dt = float(w.params.dt)
+            got = ctx.islands_step(dt, w.bodies.linear_velocity, w.bodies.angular_velocity)
+            lab, slp = orc.step(ev, w.bodies.linear_velocity, w.bodies.angular_velocity, np.float32(dt))
+            assert np.array_equal(got["island"], lab), f"step {i}: island labels differ for bodies {np.nonzero(got['island'] != lab)[0][:10]}"
+            assert np.array_equal(got["sleep_timer"], orc.timer), f"step {i}: sleep timers"
+            assert np.array_equal(got["sleeping"], slp), f"step {i}: Sleeping flags differ for bodies {np.nonzero(got['sleeping'] != slp)[0][:10]}"
+            slept += got["islands_put_to_sleep"]; woke += got["islands_woken"]; splits += got["split_bodies"] > 0
+        assert slept > 0, "nothing went to sleep: the scene or the thresholds do not exercise the path"
+        print(f"islands at the end: {got['island_count']}, asleep {got['sleeping_islands']}; put to sleep {slept}, woken {woke}, steps with a split {splits}")
