@@ -775,8 +775,9 @@ class Context:
     def contacts_download_graph(self, capacity: int, manifold_count: int) -> dict:
         out = {"collider1": np.zeros(capacity, dtype=np.uint32), "collider2": np.zeros(capacity, dtype=np.uint32), "live": np.zeros(capacity, dtype=np.uint8),
                "touching": np.zeros(capacity, dtype=np.uint8), "colour": np.zeros(capacity, dtype=np.int8), "edge": np.zeros(manifold_count, dtype=np.uint32)}
-        self._check(self.lib.avn_contacts_download_graph(self.handle, int(capacity), *(out[k].ctypes.data for k in ("collider1", "collider2", "live", "touching",
-                                                                                                                   "colour", "edge"))))
+        # edge_list receives the WHOLE colour-major list of the last step: only ask for it with a buffer of that size
+        ptrs = [out[k].ctypes.data for k in ("collider1", "collider2", "live", "touching", "colour")] + [out["edge"].ctypes.data if manifold_count else None]
+        self._check(self.lib.avn_contacts_download_graph(self.handle, int(capacity), *ptrs))
         return out
 
     # ---- persistent islands + sleeping decisions (include/avian_b200.h avn_islands_configure / _step)

@@ -454,7 +454,7 @@ __global__ void isl_split_pick_kernel(IslandState s) {
     const uint32_t c = *s.cand_body;
     if (c != ISL_NONE_BODY && !isl_static(s, c)) {
         const uint32_t r = s.root[c];
-        if (!s.isl_sleeping[r] && !s.need_wake[r] && s.removed[r] > 0) pick = r;
+        if (!s.isl_sleeping[r] && s.removed[r] > 0) pick = r;
     }
     s.ctr->split_root = pick;
 }
@@ -805,28 +805,29 @@ class Contacts final : public ContactsBase {
         if (!cfg || !cfg->body_kind) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "islands_configure: config and body_kind are required");
         if (cfg->joint_count && (!cfg->joint_body1 || !cfg->joint_body2)) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "islands_configure: joint bodies are required");
         const size_t B = cfg->body_count, Bp = std::max<size_t>(B, 1);
-        // one allocation: kind | parent root root_prev removed | 5 byte arrays | timer | thresholds | disabled | cand_body | counters
-        const size_t words = 4 * Bp, bytes = 6 * Bp, floats = 3 * Bp;
-        AVN_CUDA(isl_buf_.ensure(words * 4 + floats * 4 + bytes + Bp + 64 + sizeof(IslandCounters) + 256));
+        // one allocation, every array 16-byte aligned
+        auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+        AVN_CUDA(isl_buf_.ensure(7 * up16(Bp * 4) + 7 * up16(Bp) + 64 + up16(sizeof(IslandCounters)) + 256));
         char* p = isl_buf_.as<char>();
+        auto take = [&](size_t bytes) { char* q = p; p += up16(bytes); return q; };
         IslandState s{};
         s.B = int(B);
-        s.parent = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
-        s.root = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
-        s.root_prev = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
-        s.removed = reinterpret_cast<uint32_t*>(p); p += Bp * 4;
-        s.timer = reinterpret_cast<float*>(p); p += Bp * 4;
-        float* thr_lin = reinterpret_cast<float*>(p); p += Bp * 4;
-        float* thr_ang = reinterpret_cast<float*>(p); p += Bp * 4;
-        s.cand_body = reinterpret_cast<uint32_t*>(p); p += 16;
-        s.ctr = reinterpret_cast<IslandCounters*>(p); p += (sizeof(IslandCounters) + 15) & ~size_t(15);
-        uint8_t* kind = reinterpret_cast<uint8_t*>(p); p += Bp;
-        s.isl_sleeping = reinterpret_cast<uint8_t*>(p); p += Bp;
-        s.awake = reinterpret_cast<uint8_t*>(p); p += Bp;
-        s.need_wake = reinterpret_cast<uint8_t*>(p); p += Bp;
-        s.touched = reinterpret_cast<uint8_t*>(p); p += Bp;
-        s.in_split = reinterpret_cast<uint8_t*>(p); p += Bp;
-        uint8_t* disabled = reinterpret_cast<uint8_t*>(p); p += Bp;
+        s.ctr = reinterpret_cast<IslandCounters*>(take(sizeof(IslandCounters)));
+        s.cand_body = reinterpret_cast<uint32_t*>(take(16));
+        s.parent = reinterpret_cast<uint32_t*>(take(Bp * 4));
+        s.root = reinterpret_cast<uint32_t*>(take(Bp * 4));
+        s.root_prev = reinterpret_cast<uint32_t*>(take(Bp * 4));
+        s.removed = reinterpret_cast<uint32_t*>(take(Bp * 4));
+        s.timer = reinterpret_cast<float*>(take(Bp * 4));
+        float* thr_lin = reinterpret_cast<float*>(take(Bp * 4));
+        float* thr_ang = reinterpret_cast<float*>(take(Bp * 4));
+        uint8_t* kind = reinterpret_cast<uint8_t*>(take(Bp));
+        s.isl_sleeping = reinterpret_cast<uint8_t*>(take(Bp));
+        s.awake = reinterpret_cast<uint8_t*>(take(Bp));
+        s.need_wake = reinterpret_cast<uint8_t*>(take(Bp));
+        s.touched = reinterpret_cast<uint8_t*>(take(Bp));
+        s.in_split = reinterpret_cast<uint8_t*>(take(Bp));
+        uint8_t* disabled = reinterpret_cast<uint8_t*>(take(Bp));
         s.kind = kind;
         AVN_CUDA(cudaMemcpyAsync(kind, cfg->body_kind, B, cudaMemcpyHostToDevice, stream_));
         isl_has_thr_lin_ = cfg->sleep_threshold_linear != nullptr; isl_has_thr_ang_ = cfg->sleep_threshold_angular != nullptr;
@@ -885,6 +886,9 @@ class Contacts final : public ContactsBase {
         isl_flatten_kernel<<<bb, 256, 0, stream_>>>(s, 0);
         isl_wake_marks_kernel<<<bb, 256, 0, stream_>>>(s);
         if (rb) isl_remove_kernel<<<rb, 256, 0, stream_>>>(s, g);
+        // WakeIslands queued by the narrow phase are applied before the solver runs
+        isl_wake_bodies_kernel<<<bb, 256, 0, stream_>>>(s);
+        isl_wake_roots_kernel<<<bb, 256, 0, stream_>>>(s);
         // SolverSystems::Finalize: split last step's candidate
         isl_split_pick_kernel<<<1, 32, 0, stream_>>>(s);
         isl_split_reset_kernel<<<bb, 256, 0, stream_>>>(s);
@@ -892,8 +896,6 @@ class Contacts final : public ContactsBase {
         if (isl_J_) isl_joint_kernel<<<(isl_J_ + 255) / 256, 256, 0, stream_>>>(s, isl_j_.as<uint32_t>(), isl_j_.as<uint32_t>() + isl_J_, int(isl_J_), 1);
         isl_flatten_kernel<<<bb, 256, 0, stream_>>>(s, 1);
         // PhysicsStepSystems::Sleeping
-        isl_wake_bodies_kernel<<<bb, 256, 0, stream_>>>(s);
-        isl_wake_roots_kernel<<<bb, 256, 0, stream_>>>(s);
         isl_timers_kernel<S><<<bb, 256, 0, stream_>>>(s, lv, av, S(isl_length_unit_) * S(isl_length_unit_));
         isl_decide_kernel<<<bb, 256, 0, stream_>>>(s);
         isl_finish_kernel<<<bb, 256, 0, stream_>>>(s, out_island, out_sleeping);

@@ -31,7 +31,13 @@ class Island:
 
 
 class IslandsOracle:
-    def __init__(self, kind, joints=(), thr_lin=None, thr_ang=None, disabled=None, time_to_sleep=0.5, length_unit=1.0, scalar=np.float32):
+    def __init__(self, kind, joints=(), thr_lin=None, thr_ang=None, disabled=None, time_to_sleep=0.5, length_unit=1.0, scalar=np.float32,
+                 candidate="island"):
+        """candidate = "island": the reference — the split candidate is an island ID, retired when that island is the smaller side of a merge
+        (remove_island, mod.rs:456-464).  candidate = "body": the device's stated deviation (include/avian_b200.h avn_islands_step) — the
+        candidate is the sleepiest BODY and the island that holds it one step later is split."""
+        self.candidate_mode = candidate
+        self.candidate_body = None
         self.kind = np.asarray(kind)
         self.B = int(self.kind.shape[0])
         self.S = np.dtype(scalar).type
@@ -133,7 +139,10 @@ class IslandsOracle:
         if wake is not None:                          # wake_on_changed: the application touched these bodies
             self._wake([int(self.body_island[b]) for b in np.nonzero(wake)[0] if self._has_island(b)])
         # -- Solver, SolverSystems::Finalize: split_island (mod.rs:161-179)
-        if self.split_candidate is not None and self.split_candidate in self.islands:
+        if self.candidate_mode == "body":
+            if self.candidate_body is not None:
+                self._split(int(self.body_island[self.candidate_body]))
+        elif self.split_candidate is not None and self.split_candidate in self.islands:
             self._split(self.split_candidate)
         # -- Sleeping: update_sleeping_states (sleeping.rs:185-246)
         S = self.S
@@ -160,6 +169,7 @@ class IslandsOracle:
                 awake.add(iid)
             elif isl.removed > 0 and self.timer[b] > self.split_candidate_timer:
                 self.split_candidate = iid
+                self.candidate_body = b
                 self.split_candidate_timer = self.timer[b]
         # wake_islands_with_sleeping_disabled (sleeping.rs:164-183)
         for b in np.nonzero(self.disabled)[0]:
