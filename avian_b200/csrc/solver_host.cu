@@ -56,7 +56,7 @@ class Solver final : public SolverBase {
         const char* bps = getenv("AVN_MEGA_BPS");
         bps_forced_ = bps != nullptr;
         mega_bps_ = bps ? atoi(bps) : (sizeof(S) == 8 ? 2 : 3);
-        if (mega_bps_ < 2 || mega_bps_ > 4) mega_bps_ = 3;
+        if (mega_bps_ < 2 || mega_bps_ > 6) mega_bps_ = 3;
         if (mode && !strcmp(mode, "wave")) force_wave_ = true;
         if (const char* w = getenv("AVN_WARM_BY_BODY")) warm_by_body_ = atoi(w) != 0;
         coop_ok_ = coop_ok_ && select_megakernel(AVN_MAX_MANIFOLD_POINTS);
@@ -206,6 +206,10 @@ class Solver final : public SolverBase {
         switch (bps) {
             case 2: return (const void*)step_megakernel<S, 2, MAXP>;
             case 4: return (const void*)step_megakernel<S, 4, MAXP>;
+#ifdef AVN_EXPERIMENT_BPS56   // experiment: 5 / 6 blocks per SM (102 / 85 registers: the wavefront routines spill)
+            case 5: return (const void*)step_megakernel<S, 5, MAXP>;
+            case 6: return (const void*)step_megakernel<S, 6, MAXP>;
+#endif
             default: return (const void*)step_megakernel<S, 3, MAXP>;
         }
     }
