@@ -109,6 +109,10 @@ struct DevSolver {
     const int* jbody1[AVN_JOINT_TYPE_COUNT]; const int* jbody2[AVN_JOINT_TYPE_COUNT];
     S* jforce[AVN_JOINT_TYPE_COUNT]; S* jtorque[AVN_JOINT_TYPE_COUNT];
     int any_joint_damping;
+    // island-per-warp schedule (island_lists.hpp): isl_count > 0 selects it.  Island i: bodies isl_bodies[isl_body_off[i] .. [i+1]), manifold slots of
+    // colour c isl_mslots[isl_m_off[i*25+c] .. [i*25+c+1]), joint slots of level l isl_jslots[isl_j_off[i*(L+1)+l] .. [+1])
+    int isl_count, isl_levels;
+    const int* isl_body_off; const int* isl_bodies; const int* isl_m_off; const int* isl_mslots; const int* isl_j_off; const int* isl_jslots;
     // launch range (avn_solver_run_range): which parts of the step this launch runs.  A plain avn_solver_run does everything.
     int do_prepare, sub_begin, sub_end, do_restitution, do_finalize;
     // x-slab partition (multi-GPU, include/avian_b200.h "boundary bodies"): bnd_of[b] = index into the boundary list or -1 (NULL when

@@ -59,7 +59,7 @@ SCENES = {
 }
 LABEL = {"stack100k": "100k-cube stack", "stack10k": "10k-cube stack", "stack1k": "1k-cube stack", "ragdolls5k": "5k-ragdoll field",
          "ragdolls500": "500-ragdoll field", "spheres1m": "1M falling spheres (f64)", "spheres100k": "100k falling spheres (f64)"}
-MODES = {0: "phases", 1: "megakernel, grid barriers", 2: "megakernel, wavefront counters"}
+MODES = {0: "phases", 1: "megakernel, grid barriers", 2: "megakernel, wavefront records", 3: "megakernel, one warp per island"}
 
 
 def metric_name(scene: str) -> str:

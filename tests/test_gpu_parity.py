@@ -195,6 +195,36 @@ def test_body_centric_warm_start_with_many_contacts(gpu_ctx):
     assert np.array_equal(mw.warm_start_tangent_impulse, mb.warm_start_tangent_impulse)
 
 
+def test_island_per_warp_schedule_is_bit_identical(gpu_ctx):
+    """a field of ragdolls = many small islands: one thread block takes a group of islands through the whole substep loop
+    (AVN_LAUNCH_MEGA_ISLANDS); same per-item routines in the same per-body order as the barrier schedule, so bit-identical bodies, impulses
+    and joint forces; and equal to the oracle."""
+    w, (prm, b, m, j) = advance_to_solver_input(scenes.ragdoll_field(320, pitch=1.6, drop_height=0.1), steps=25, substeps=4)
+    assert m is not None and m.count > 50 and j.count == 320 * 16, (None if m is None else m.count, j.count)
+    def run(env):
+        os.environ.update(env)
+        try:
+            with api.Context(device=0) as ctx:
+                bb, mm, jj = b.copy(), m.copy(), j.copy()
+                ctx.solver_step(prm, bb, mm, jj)
+                return bb, mm, jj, ctx.timings()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    bi, mi, ji, ti = run({"AVN_ISLAND_MODE": "1"})     # (an experiment: slower than the barrier schedule, off by default)
+    bb, mb, jb, tb = run({})
+    assert ti["launch_mode"] == 3 and tb["launch_mode"] == 1 and ti["kernel_launches"] == 1   # AVN_LAUNCH_MEGA_ISLANDS / _BARRIER
+    for name in ("position", "rotation", "linear_velocity", "angular_velocity"):
+        assert np.array_equal(getattr(bi, name), getattr(bb, name)), name
+    assert np.array_equal(mi.warm_start_normal_impulse, mb.warm_start_normal_impulse) and np.array_equal(mi.normal_impulse, mb.normal_impulse)
+    for t, jt in ji.types.items():
+        if jt.count and jt.force is not None:
+            assert np.array_equal(jt.force, jb.types[t].force) and np.array_equal(jt.torque, jb.types[t].torque)
+    bo, mo, jo = b.copy(), m.copy(), j.copy()
+    oracle_lib.solver_step(prm, bo, mo, jo)
+    assert_bodies_close(bi, bo, what="island schedule vs oracle: ")
+
+
 def test_wavefront_equals_barrier_at_headline_size(gpu_ctx):
     """BASELINE-size property: on the 100k-cube stack (no oracle at this size in seconds) the wavefront schedule and the
     barrier schedule give bit-identical bodies and impulses, and the step stays finite with non-negative normal impulses
