@@ -67,6 +67,7 @@ struct DevSolver {
     int color_off[AVN_GRAPH_COLOR_COUNT + 1];    // SLOT ranges per colour, each start a multiple of 32; [24] = Mpad
     int color_len[AVN_GRAPH_COLOR_COUNT];        // manifolds in the colour
     int wave;                                    // 1: wavefront (dependency-counter) substep loop, 0: grid barriers
+    int wave_rolled;                             // f32 wavefront: 1 = the rolled contact routines (throughput-bound steps), 0 = the unrolled ones
     unsigned int* ver;                           // [B+1] per-body event counter (wavefront mode)
     int* deg;                                    // [B+1] contact constraints touching the body (wavefront mode)
     int* stamp;                                  // [B+1] 1 + last colour that ranked the body: detects a body listed twice in one colour
@@ -428,8 +429,9 @@ __device__ __forceinline__ void stage_copy(Vec4<double>* dst, const Vec4<double>
 }
 // the tile only needs the rows of the widest manifold of the upload (single-point sphere contacts: a quarter of the tile, the rest
 // of the SM's shared-memory / L1 array stays L1)
+// (3 staged rows per point + 1 scratch row per point for its impulses + 1 row of separations: wave32_dev.cuh)
 template <class S> __host__ __device__ constexpr size_t stage_bytes(int threads, int max_points = AVN_MAX_MANIFOLD_POINTS) {
-    return size_t(3 * max_points) * threads * sizeof(Vec4<S>);
+    return size_t(4 * max_points + 1) * threads * sizeof(Vec4<S>);
 }
 
 // `slot` indexes the padded colour-major planes.  WAVE = false: barrier mode (a padding slot returns at once).

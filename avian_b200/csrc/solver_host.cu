@@ -761,6 +761,13 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
         for (int c = 0; c < AVN_COLOR_OVERFLOW; ++c) widest_colour = std::max(widest_colour, dev_.color_len[c]);
         const bool chain_bound = force_wave_ || widest_colour <= 2 * mega_grid_ * MEGA_BLOCK;
         dev_.wave = (mega && use_wave_ && chain_bound && dev_.M > 0 && dev_.J == 0 && dev_.color_len[AVN_COLOR_OVERFLOW] == 0) ? 1 : 0;
+        // which build of the f32 wavefront contact routines: rolled (17 KB per pass, instruction-cache friendly) when a colour keeps a good part
+        // of the resident warps busy, unrolled (42 KB, shorter dependent chain per item) when the step is bound by the per-body chain
+        {
+            const int resident_warps = mega_grid_ * (MEGA_BLOCK / 32);
+            dev_.wave_rolled = (widest_colour / 32 >= resident_warps / 4) ? 1 : 0;
+            if (const char* r = getenv("AVN_WAVE_ROLLED")) dev_.wave_rolled = atoi(r) != 0;
+        }
         if (dev_.M > 0) {
             // padding slots must read as "no points": clear the index plane before prepare fills the live slots
             AVN_CUDA(cudaMemsetAsync(dev_.cst + size_t(CP_IDX) * dev_.Mpad, 0, size_t(dev_.Mpad) * sizeof(Vec4<S>), stream_));

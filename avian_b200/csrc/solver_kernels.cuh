@@ -111,8 +111,12 @@ __device__ __noinline__ void wave_ip_chunk(const DevSolver<S>& d, int i, int s, 
 // (BPS and MAXP are template parameters of all of them only so that every megakernel variant owns its copies: ptxas 12.9 segfaults when two
 //  kernels share a __noinline__ function that contains the 256-bit accesses)
 template <int PASS, int MAXP, int BPS>
-__device__ __noinline__ void wave32_contact_chunk(const DevSolver<float>& d, int slot, int s, int it, bool active, int wf) {
-    w32_contact_item<PASS, MAXP>(d, slot, s, it, active, wf);
+__device__ __noinline__ void wave32_contact_chunk(const DevSolver<float>& d, int slot, int s, int it, bool active, int wf, int pass) {
+    w32_contact_item<PASS, MAXP>(d, slot, s, it, active, wf, pass);
+}
+template <int PASS, int MAXP, int BPS>
+__device__ __noinline__ void wave32_contact_chunk_unrolled(const DevSolver<float>& d, int slot, int s, int it, bool active, int wf) {
+    w32_contact_item_unrolled<PASS, MAXP>(d, slot, s, it, active, wf);
 }
 template <int BPS, int MAXP> __device__ __noinline__ void wave32_iv_chunk(const DevSolver<float>& d, int i, int s, bool active) { w32_integrate_velocity_item(d, i, s, active); }
 template <int BPS, int MAXP> __device__ __noinline__ void wave32_ip_chunk(const DevSolver<float>& d, int i, int s, bool active, int wf) { w32_integrate_position_item(d, i, s, active, wf); }
@@ -127,8 +131,12 @@ template <class S> struct UseRecords { static constexpr bool value = false; };
 template <> struct UseRecords<float> { static constexpr bool value = WAVE_RECORDS_F32; };
 template <class S, int PASS, int MAXP, int BPS>
 __device__ __forceinline__ void wave_contact(const DevSolver<S>& d, int slot, int s, int it, bool active, int wf) {
-    if constexpr (UseRecords<S>::value) wave32_contact_chunk<PASS, MAXP, BPS>(d, slot, s, it, active, wf);
-    else wave_contact_chunk<S, PASS, MAXP>(d, slot, s, it, active);
+    if constexpr (UseRecords<S>::value) {
+        if (d.wave_rolled) wave32_contact_chunk<(PASS == PASS_WARM ? PASS_WARM : PASS_SOLVE_BIAS), MAXP, BPS>(d, slot, s, it, active, wf, PASS);
+        else wave32_contact_chunk_unrolled<PASS, MAXP, BPS>(d, slot, s, it, active, wf);
+    } else {
+        wave_contact_chunk<S, PASS, MAXP>(d, slot, s, it, active);
+    }
 }
 template <class S, int BPS, int MAXP> __device__ __forceinline__ void wave_iv(const DevSolver<S>& d, int i, int s, bool active) {
     if constexpr (UseRecords<S>::value) wave32_iv_chunk<BPS, MAXP>(d, i, s, active);

@@ -54,7 +54,248 @@ __device__ __forceinline__ unsigned w32_pc_tag(int pass, int s, int it, int iter
 // Every lane of the warp must call this (warp-collective polls).
 // ---------------------------------------------------------------------------------------------------------
 template <int PASS, int MAXP>
-__device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int slot, int s, int it, bool lane_active, int wf) {
+__device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int slot, int s, int it, bool lane_active, int wf, int pass) {
+    // PASS = PASS_WARM or PASS_SOLVE_BIAS; the solve build serves the biased AND the relax pass (`pass` says which): one routine in the
+    // instruction cache instead of two
+    const bool relax = PASS != PASS_WARM && pass == PASS_RELAX;
+    using S = float;
+    const size_t MP = size_t(d.Mpad);
+    const Vec4<S>* c = d.cst + (lane_active ? slot : 0);
+    const Vec4<S> hidx = ld4(&c[CP_IDX * MP]);
+    const int info = lane_active ? as_int(hidx.z) : 0;   // an inactive lane of a partial chunk behaves like a padding slot
+    const int np = info & CI_NP_MASK;
+    const int b1 = as_int(hidx.x), b2 = as_int(hidx.y);
+    constexpr bool SOLVE = (PASS == PASS_SOLVE_BIAS || PASS == PASS_RELAX);
+    Vec4<S>* const stage = stage_base<S>() + threadIdx.x;
+    const int T = blockDim.x;
+#define ROW_A(k) stage[(3 * (k) + 0) * T]
+#define ROW_B(k) stage[(3 * (k) + 1) * T]
+#define ROW_D(k) stage[(3 * (k) + 2) * T]
+    // the item's own scratch rows behind the staged ones: the impulses of its points and their separations.  They live in shared memory so
+    // that the loops over the points can stay ROLLED (dynamic index, no local memory): the solve and relax routines shrink from 42 KB of
+    // SASS to a quarter, which matters because the SM's instruction cache (32 KB L1.5) serves warps that are in five different routines
+    // at once in the wavefront schedule (ncu: stall_no_instruction 1.18 per issue with the unrolled routines)
+#define ROW_PC(k) stage[(3 * MAXP + (k)) * T]
+    float* const sepv = reinterpret_cast<float*>(&stage[(4 * MAXP) * T]);
+    // ---- immutable part: issued before any wait
+    Vec4<S> hn = mk4<S>(0, 0, 0, 0), ht1 = hn, htv = hn;
+    BodyInertia<S> in1 = zero_inertia<S>(), in2 = zero_inertia<S>();
+    if (np != 0) {
+        hn = ld4(&c[CP_N * MP]);
+        ht1 = ld4(&c[CP_T1 * MP]);
+        if (SOLVE) htv = ld4(&c[CP_TV * MP]);
+        if (!(info & CI_ZERO1)) in1 = unpack_inertia(ld4(&d.inr[2 * b1]), ld4(&d.inr[2 * b1 + 1]));
+        if (!(info & CI_ZERO2)) in2 = unpack_inertia(ld4(&d.inr[2 * b2]), ld4(&d.inr[2 * b2 + 1]));
+#pragma unroll 1
+        for (int k = 0; k < np; ++k) {
+            stage_copy(&ROW_A(k), &c[size_t(CP_ROW(k, 0)) * MP]);
+            stage_copy(&ROW_B(k), &c[size_t(CP_ROW(k, 1)) * MP]);
+            if (SOLVE && (info & CI_TANGENT)) stage_copy(&ROW_D(k), &c[size_t(CP_ROW(k, 2)) * MP]);
+        }
+    }
+    __pipeline_commit();
+    const bool ver1 = np != 0 && (info & CI_VER1), ver2 = np != 0 && (info & CI_VER2);
+    const int rk = as_int(hidx.w);
+    const int kind = PASS == PASS_WARM ? WV_WARM : (relax ? WV_RELAX : WV_SOLVE);
+    const unsigned e1 = wave_event(kind, it, s, d.iters, (rk >> 8) & 0xff, rk & 0xff, wf);
+    const unsigned e2 = wave_event(kind, it, s, d.iters, (rk >> 24) & 0xff, (rk >> 16) & 0xff, wf);
+    const unsigned ptag = w32_pc_tag(PASS == PASS_WARM ? PASS_WARM : (relax ? PASS_RELAX : PASS_SOLVE_BIAS), s, it, d.iters);
+    const V3<S> n = xyz(hn), t1 = xyz(ht1);
+    AVN_TRACE_T(t_w0);
+
+    // ---- stage 1 (solve passes): the delta records -> separation of every point, before the velocities are even looked at
+    if (SOLVE) {
+        const unsigned dtag = unsigned(relax ? s + 1 : s);
+        Rec32 D1, D2;
+        D1.a = mk4<S>(0, 0, 0, 0); D1.b = mk4<S>(0, 0, 0, 1); D2 = D1;
+        bool n1 = ver1, n2 = ver2;
+        if (np != 0 && !ver1) { D1.a = ld4(&d.dlt[2 * b1]); D1.b = ld4(&d.dlt[2 * b1 + 1]); }   // no SolverBody: constant (0, identity)
+        if (np != 0 && !ver2) { D2.a = ld4(&d.dlt[2 * b2]); D2.b = ld4(&d.dlt[2 * b2 + 1]); }
+        for (unsigned spins = 0;; ++spins) {
+            if (n1) D1 = ld_rec(&d.dlt[2 * b1]);
+            if (n2) D2 = ld_rec(&d.dlt[2 * b2]);
+            if (n1) n1 = tag_of(D1.a.w) != dtag;
+            if (n2) n2 = tag_of(D2.a.w) != dtag;
+            if (__all_sync(0xffffffffu, !(n1 || n2))) break;
+            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+        }
+        __pipeline_wait_prior(0);   // this thread's staged rows have landed (only the issuing thread reads them)
+        AVN_TRACE_T(t_p0);
+        AVN_TRACE_ADD(d, 5, t_p0 - t_w0);
+        if (np != 0) {
+            Q4<S> q1; q1.x = D1.b.x; q1.y = D1.b.y; q1.z = D1.b.z; q1.w = D1.b.w;
+            Q4<S> q2; q2.x = D2.b.x; q2.y = D2.b.y; q2.z = D2.b.z; q2.w = D2.b.w;
+            const V3<S> delta_translation = xyz(D2.a) - xyz(D1.a);
+#pragma unroll 1
+            for (int k = 0; k < np; ++k) {
+                const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
+                V3<S> rr1 = qrot(q1, xyz(PAk)), rr2 = qrot(q2, xyz(PBk));
+                V3<S> dsep = delta_translation + (rr2 - rr1);
+                sepv[k] = dot(dsep, n) + PAk.w;
+            }
+        }
+#ifdef AVN_WAVE_TRACE
+        { S sink = sepv[0]; if (sink == S(1.2345e33)) d.any_restitution[1] = 2; AVN_TRACE_ADD(d, 1, clock64() - t_p0); }
+#endif
+    }
+
+    // ---- stage 2: velocity records of the two bodies and the impulse records of the points, all self-validating
+    Rec32 R1, R2;
+    R1.a = mk4<S>(0, 0, 0, 0); R1.b = R1.a; R2 = R1;
+    {
+        bool n1 = ver1, n2 = ver2;
+        unsigned pend = np != 0 ? ((1u << np) - 1u) : 0u;
+        if (np != 0 && !ver1) { R1.a = ld4(&d.vel[2 * b1]); R1.b = ld4(&d.vel[2 * b1 + 1]); }
+        if (np != 0 && !ver2) { R2.a = ld4(&d.vel[2 * b2]); R2.b = ld4(&d.vel[2 * b2 + 1]); }
+        AVN_TRACE_T(t_w1);
+        for (unsigned spins = 0;; ++spins) {
+            if (n1) R1 = ld_rec(&d.vel[2 * b1]);
+            if (n2) R2 = ld_rec(&d.vel[2 * b2]);
+#pragma unroll 1
+            for (int k = 0; k < np; ++k) {
+                if (pend & (1u << k)) {
+                    const Rec32 p = ld_rec(pc_ptr(d, k, slot));
+                    ROW_PC(k) = p.a;
+                    if (tag_of(p.b.x) == ptag) pend &= ~(1u << k);
+                }
+            }
+            if (n1) n1 = tag_of(R1.a.w) != e1;
+            if (n2) n2 = tag_of(R2.a.w) != e2;
+            if (__all_sync(0xffffffffu, !(n1 || n2 || pend != 0u))) break;
+            if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+        }
+#ifdef AVN_WAVE_TRACE
+        AVN_TRACE_ADD(d, 0, clock64() - t_w1);
+#endif
+    }
+    if (!SOLVE) __pipeline_wait_prior(0);
+    if (np == 0) return;   // padding slot / inactive lane (after the warp-collective polls)
+    AVN_TRACE_T(t_c0);
+    V3<S> v1 = xyz(R1.a), w1 = xyz(R1.b), v2 = xyz(R2.a), w2 = xyz(R2.b);
+    const V3<S> t2 = cross(t1, n);  // tangent_directions(): [tangent1, tangent1 x normal] (contact/mod.rs:411-421)
+
+    if (PASS == PASS_WARM) {
+        // ContactConstraint::warm_start (contact/mod.rs:223-264)
+#pragma unroll 1
+        for (int k = 0; k < np; ++k) {
+            const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), pck = ROW_PC(k);
+            V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
+            S tx = (info & CI_TANGENT) ? pck.z : S(0), ty = (info & CI_TANGENT) ? pck.w : S(0);
+            V3<S> p = d.warm_coeff * ((pck.x * n + tx * t1) + ty * t2);
+            apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, p);
+        }
+    } else {
+        // ContactConstraint::solve (contact/mod.rs:267-354)
+        const Soft<S> soft = (info & CI_NONDYN) ? d.soft_nondyn : d.soft_dyn;
+#pragma unroll 1
+        for (int k = 0; k < np; ++k) {
+            {
+                const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k);
+                Vec4<S> pck = ROW_PC(k);
+                V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
+                const S separation = sepv[k];
+                V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
+                // ContactNormalPart::solve_impulse (normal_part.rs:116-166)
+                S vn = dot(relv, n);
+                S meff = PBk.w, acc = pck.x;
+                S impulse;
+                if (separation > S(0)) {
+                    impulse = -meff * (vn + separation / d.h);
+                } else if (!relax) {
+                    S bias = avn_max(soft.bias * separation, -d.max_overlap_speed);
+                    S scaled_mass = soft.mass_scale * meff;
+                    S scaled_impulse = soft.impulse_scale * acc;
+                    impulse = -scaled_mass * (vn + bias) - scaled_impulse;
+                } else {
+                    impulse = -meff * vn;
+                }
+                S new_impulse = avn_max(acc + impulse, S(0));
+                impulse = new_impulse - acc;
+                pck.x = new_impulse;
+                pck.y = pck.y + new_impulse;
+                ROW_PC(k) = pck;
+                apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, impulse * n);
+            }
+        }
+        if (info & CI_TANGENT) {
+            const S friction = hn.w;
+            const V3<S> surf = xyz(htv);
+#pragma unroll 1
+            for (int k = 0; k < np; ++k) {
+                {
+                    const Vec4<S> PAk = ROW_A(k), PBk = ROW_B(k), PDk = ROW_D(k);
+                    Vec4<S> pck = ROW_PC(k);
+                    V3<S> r1 = xyz(PAk), r2 = xyz(PBk);
+                    V3<S> relv = (v2 + cross(w2, r2)) - (v1 + cross(w1, r1));
+                    // ContactTangentPart::solve_impulse (tangent_part.rs:155-244)
+                    S limit = friction * pck.x;
+                    relv = relv + surf;
+                    S ts1 = dot(relv, t1), ts2 = dot(relv, t2);
+                    S t11 = ts1 * ts1, t22 = ts2 * ts2, t12 = ts1 * ts2;
+                    S inv = (t11 * PDk.x + t22 * PDk.y) + t12 * PDk.z;
+                    S em = (t11 + t22) * (S(1) / inv);
+                    V3<S> imp = zero3<S>();
+                    if (avn_finite(em)) {
+                        S nx = pck.z - em * ts1, ny = pck.w - em * ts2;
+                        S l2 = nx * nx + ny * ny;
+                        if (l2 > limit * limit) {  // Vec2::clamp_length_max
+                            S l = avn_sqrt(l2);
+                            nx = limit * (nx / l);
+                            ny = limit * (ny / l);
+                        }
+                        S dx = nx - pck.z, dy = ny - pck.w;
+                        pck.z = nx;
+                        pck.w = ny;
+                        ROW_PC(k) = pck;
+                        imp = dx * t1 + dy * t2;
+                    }
+                    apply_impulse(v1, w1, v2, w2, in1, in2, r1, r2, imp);
+                }
+            }
+        }
+    }
+    // ---- publish: every record this item is the next writer of, with the next tag.  A side without inertia here (dominated, kinematic)
+    //      keeps the value it had bit for bit — only its event number moves on.
+#ifdef AVN_WAVE_TRACE
+    if ((v1.x + v2.x + w1.x + w2.x) == S(1.2345e33)) d.any_restitution[1] = 2;
+    AVN_TRACE_T(t_s0);
+    AVN_TRACE_ADD(d, 2, t_s0 - t_c0);
+#endif
+    if (PASS != PASS_WARM) {
+        const float nt = tag_lane(ptag + 1u);
+#pragma unroll 1
+        for (int k = 0; k < np; ++k) {
+            const Vec4<S> pck = ROW_PC(k);
+            st_rec(pc_ptr(d, k, slot), pck.x, pck.y, pck.z, pck.w, nt, 0.f, 0.f, 0.f);
+        }
+    }
+    if (ver1) {
+        if (info & CI_ZERO1) st_rec(&d.vel[2 * b1], R1.a.x, R1.a.y, R1.a.z, tag_lane(e1 + 1u), R1.b.x, R1.b.y, R1.b.z, 0.f);
+        else st_rec(&d.vel[2 * b1], v1.x, v1.y, v1.z, tag_lane(e1 + 1u), w1.x, w1.y, w1.z, 0.f);
+    }
+    if (ver2) {
+        if (info & CI_ZERO2) st_rec(&d.vel[2 * b2], R2.a.x, R2.a.y, R2.a.z, tag_lane(e2 + 1u), R2.b.x, R2.b.y, R2.b.z, 0.f);
+        else st_rec(&d.vel[2 * b2], v2.x, v2.y, v2.z, tag_lane(e2 + 1u), w2.x, w2.y, w2.z, 0.f);
+    }
+#ifdef AVN_WAVE_TRACE
+    AVN_TRACE_ADD(d, 3, clock64() - t_s0);
+    AVN_TRACE_ADD(d, 4, 1);
+#endif
+#undef ROW_A
+#undef ROW_B
+#undef ROW_D
+#undef ROW_PC
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same routine with the loops over the points UNROLLED and the impulses / separations in registers (round 2's first version): 42 KB of
+// SASS per pass instead of 17 KB, but no shared-memory round trip inside the dependent chain of an item.  The rolled routine wins when the
+// step is throughput-bound (100k cubes: 1.61 -> 1.42 ms, the warps of an SM are in five routines at once and the 32 KB instruction cache
+// holds the rolled ones), the unrolled one when it is bound by the per-body chain (10k cubes: 0.74 ms vs 0.90 ms rolled).  The host picks
+// per step (DevSolver::wave_rolled).
+// ---------------------------------------------------------------------------------------------------------
+template <int PASS, int MAXP>
+__device__ __forceinline__ void w32_contact_item_unrolled(const DevSolver<float>& d, int slot, int s, int it, bool lane_active, int wf) {
     using S = float;
     const size_t MP = size_t(d.Mpad);
     const Vec4<S>* c = d.cst + (lane_active ? slot : 0);
