@@ -236,6 +236,7 @@ class Solver final : public SolverBase {
             mega_grid_ = per_sm * sm_count_;
         else
             (void)cudaGetLastError();
+        if (getenv("AVN_DEBUG_GRID")) fprintf(stderr, "[avn] megakernel bps=%d maxp=%d: %d blocks/SM resident, grid %d, %zu B dynamic smem\n", bps, maxp, per_sm, mega_grid_, smem);
         return mega_grid_ > 0;
     }
     int max_np_ = AVN_MAX_MANIFOLD_POINTS;  // widest manifold of the current upload
