@@ -247,7 +247,7 @@ AvnStatus avn_contacts_step(AvnContext* ctx, const AvnNarrowParams* params, cons
         const bool take = (flags & AVN_CONTACTS_TAKE_BROADPHASE_PAIRS) != 0;
         // this step's collider / body columns start moving to the device before the broad phase is waited for
         if (params && input && out) {
-            AvnStatus st = ctx->contacts->prefetch_inputs(input, flags);
+            AvnStatus st = ctx->contacts->prefetch_inputs(params, input, match_contacts, length_unit, flags);
             if (st != AVN_OK) return st;
         }
         if (take) {

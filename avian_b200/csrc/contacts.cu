@@ -31,7 +31,8 @@ namespace cg = cooperative_groups;
 // The colour a push gets depends on every earlier push and pop that shares a body, so the result is order dependent — and the order of
 // the colours IS the Gauss-Seidel order of the solver.  The device reproduces the sequential result exactly with a dependency wavefront:
 // in every round a changed edge runs iff it is the smallest pending ContactId on each of its non-static bodies (64-bit atomicMin tagged
-// with the round: no reset pass); edges of one round share no non-static body, so they commute.  The number of rounds is the longest chain
+// with the round: no reset pass); edges of one round share no non-static body, so they commute.  Pops only clear bits, so they commute with each
+// other anyway: a POP waits only for the earlier pending PUSHES on its bodies (second minimum per body), a PUSH for everything earlier.  The number of rounds is the longest chain
 // of changed edges linked through shared bodies in ascending id (a few in the steady state, thousands on the first frame of a big pile).
 // Inside a colour the order of the manifolds does not influence the solve (they share no dynamic body), so the colour-major list is built
 // in ascending ContactId by one stable radix pass; only the overflow colour, which the solver walks serially, keeps the reference's
@@ -54,11 +55,12 @@ struct GraphRows {
     uint32_t* c1; uint32_t* c2; uint32_t* b1; uint32_t* b2;
     uint8_t* live; uint8_t* count; uint8_t* disjoint; uint8_t* prev_count;
     uint8_t* pflags; uint8_t* touching; uint8_t* colour /* 0 = none, c + 1 */; uint8_t* change; uint8_t* old_colour;
+    uint8_t* fresh;                               // the row was added in this step (its geometry is still to be computed)
     uint8_t* isl_event;                           // this step's event for the islands: ISL_ADD / ISL_REMOVE (a linked contact came or went)
     uint32_t* ovf_pos; uint32_t* ovf;
     const uint8_t* body_kind; int n_bodies;
     uint32_t* body_bits;                          // [B] bit c: the body is in colour c's body set
-    unsigned long long* body_min;                 // [B] round-tagged smallest pending ContactId
+    unsigned long long* body_min;                 // [B][2] round-tagged smallest pending ContactId: [0] over all pending edges, [1] over the pending PUSHES
     GraphCounters* ctr;
 };
 
@@ -71,6 +73,7 @@ __global__ void add_rows_kernel(GraphRows g, uint32_t n_new, const uint32_t* __r
     g.c1[e] = pc1[k]; g.c2[e] = pc2[k]; g.b1[e] = pb1[k]; g.b2[e] = pb2[k];
     g.pflags[e] = pfl[k];
     g.isl_event[e] = 0;
+    g.fresh[e] = 1;
     g.live[e] = 1;            // a ContactId handed to a new pair starts without history
     g.count[e] = 0; g.prev_count[e] = 0; g.touching[e] = 0; g.colour[e] = 0; g.change[e] = 0;
 }
@@ -117,6 +120,15 @@ __global__ void classify_kernel(GraphRows g, uint32_t* __restrict__ keys, uint32
 
 __device__ __forceinline__ bool graph_static(const GraphRows& g, uint32_t b) { return b >= uint32_t(g.n_bodies) || g.body_kind[b] == AVN_BODY_STATIC; }
 
+// is it this edge's turn on (non-static) body b?  A push needs to be the smallest pending edge of the body; a pop only needs every earlier
+// pending PUSH of the body to be done (pops clear different bits and commute)
+__device__ __forceinline__ bool graph_turn_body(const GraphRows& g, uint32_t b, unsigned long long key, bool push) {
+    return push ? g.body_min[2 * size_t(b)] == key : g.body_min[2 * size_t(b) + 1] > key;
+}
+__device__ __forceinline__ bool graph_turn(const GraphRows& g, uint32_t b, unsigned long long key, bool push) {
+    return graph_static(g, b) || graph_turn_body(g, b, key, push);
+}
+
 // ConstraintGraph::push_manifold / pop_manifold for ONE edge whose turn it is
 __device__ __forceinline__ void graph_apply(const GraphRows& g, uint32_t e, uint8_t ch) {
     const uint32_t b1 = g.b1[e], b2 = g.b2[e];
@@ -137,8 +149,8 @@ __device__ __forceinline__ void graph_apply(const GraphRows& g, uint32_t e, uint
         const int c = int(g.colour[e]) - 1;
         g.old_colour[e] = uint8_t(c + 1);
         if (c >= 0 && c != AVN_COLOR_OVERFLOW) {
-            if (!s1) g.body_bits[b1] &= ~(1u << c);
-            if (!s2) g.body_bits[b2] &= ~(1u << c);
+            if (!s1) atomicAnd(&g.body_bits[b1], ~(1u << c));   // several pops of one body may run in the same round
+            if (!s2) atomicAnd(&g.body_bits[b2], ~(1u << c));
         }
         if (c == AVN_COLOR_OVERFLOW) g.ctr->ovf_dirty = 1;
         g.colour[e] = 0;
@@ -160,8 +172,9 @@ __global__ void __launch_bounds__(256) colour_rounds_kernel(GraphRows g, const u
             const uint8_t ch = g.change[e];
             if (ch & CH_DONE) continue;
             const uint32_t b1 = g.b1[e], b2 = g.b2[e];
-            if (!graph_static(g, b1)) atomicMin(&g.body_min[b1], tag | e);
-            if (!graph_static(g, b2)) atomicMin(&g.body_min[b2], tag | e);
+            const bool push = (ch & CH_MASK) == CH_PUSH;
+            if (!graph_static(g, b1)) { atomicMin(&g.body_min[2 * size_t(b1)], tag | e); if (push) atomicMin(&g.body_min[2 * size_t(b1) + 1], tag | e); }
+            if (!graph_static(g, b2)) { atomicMin(&g.body_min[2 * size_t(b2)], tag | e); if (push) atomicMin(&g.body_min[2 * size_t(b2) + 1], tag | e); }
         }
         grid.sync();
         uint32_t left = 0;
@@ -170,7 +183,8 @@ __global__ void __launch_bounds__(256) colour_rounds_kernel(GraphRows g, const u
             const uint8_t ch = g.change[e];
             if (ch & CH_DONE) continue;
             const uint32_t b1 = g.b1[e], b2 = g.b2[e];
-            const bool mine = (graph_static(g, b1) || g.body_min[b1] == (tag | e)) && (graph_static(g, b2) || g.body_min[b2] == (tag | e));
+            const bool push = (ch & CH_MASK) == CH_PUSH;
+            const bool mine = graph_turn(g, b1, tag | e, push) && graph_turn(g, b2, tag | e, push);
             if (mine) { graph_apply(g, e, ch); g.change[e] = ch | CH_DONE; }
             else ++left;
         }
@@ -221,15 +235,17 @@ __global__ void __launch_bounds__(CL_THREADS) colour_rounds_cluster_kernel(Graph
 #pragma unroll
         for (int k = 0; k < CL_ITEMS; ++k) {
             if (!pend[k]) continue;
-            if (b1[k] != NONE) atomicMin(&g.body_min[b1[k]], tag | e[k]);
-            if (b2[k] != NONE) atomicMin(&g.body_min[b2[k]], tag | e[k]);
+            const bool push = (ch[k] & CH_MASK) == CH_PUSH;
+            if (b1[k] != NONE) { atomicMin(&g.body_min[2 * size_t(b1[k])], tag | e[k]); if (push) atomicMin(&g.body_min[2 * size_t(b1[k]) + 1], tag | e[k]); }
+            if (b2[k] != NONE) { atomicMin(&g.body_min[2 * size_t(b2[k])], tag | e[k]); if (push) atomicMin(&g.body_min[2 * size_t(b2[k]) + 1], tag | e[k]); }
         }
         cluster.sync();
         int left = 0;
 #pragma unroll
         for (int k = 0; k < CL_ITEMS; ++k) {
             if (!pend[k]) continue;
-            const bool mine = (b1[k] == NONE || g.body_min[b1[k]] == (tag | e[k])) && (b2[k] == NONE || g.body_min[b2[k]] == (tag | e[k]));
+            const bool push = (ch[k] & CH_MASK) == CH_PUSH;
+            const bool mine = (b1[k] == NONE || graph_turn_body(g, b1[k], tag | e[k], push)) && (b2[k] == NONE || graph_turn_body(g, b2[k], tag | e[k], push));
             if (mine) { graph_apply(g, e[k], ch[k]); g.change[e[k]] = ch[k] | CH_DONE; pend[k] = false; }
             else left = 1;
         }
@@ -344,9 +360,14 @@ __global__ void edge_remove_kernel(int n, const uint32_t* __restrict__ ids, uint
 }
 
 template <class S>
-__global__ void __launch_bounds__(128) narrow_edges_kernel(const __grid_constant__ NarrowEdgeArgs<S> a) {
+__global__ void __launch_bounds__(128) narrow_edges_kernel(const __grid_constant__ NarrowEdgeArgs<S> a, uint8_t* fresh, int only_fresh) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < a.r.E) narrow_edge_row<S>(a, e);   // csrc/contact_rows.hpp: the same function the CPU tests run
+    if (e >= a.r.E) return;
+    if (only_fresh) {            // the rows added after the early pass over the existing rows (Contacts::prefetch_inputs)
+        if (!fresh[e]) return;
+        fresh[e] = 0;
+    }
+    narrow_edge_row<S>(a, e);   // csrc/contact_rows.hpp: the same function the CPU tests run
 }
 
 
@@ -561,7 +582,7 @@ class Contacts final : public ContactsBase {
                       {&prev_a2_, 12 * sizeof(double)}, {&ws_n_in_, 4 * sizeof(S)}, {&ws_t_in_, 8 * sizeof(S)}, {&ws_n_out_, 4 * sizeof(S)},
                       {&ws_t_out_, 8 * sizeof(S)}, {&nimp_in_, 4 * sizeof(S)}, {&nimp_out_, 4 * sizeof(S)},
                       // graph state per row (zero = no flags, not touching, no colour)
-                      {&pflags_, 1}, {&touching_, 1}, {&colour_, 1}, {&change_, 1}, {&old_colour_, 1}, {&ovf_pos_, 4}, {&ovf_, 4}, {&isl_event_, 1}};
+                      {&pflags_, 1}, {&touching_, 1}, {&colour_, 1}, {&change_, 1}, {&old_colour_, 1}, {&ovf_pos_, 4}, {&ovf_, 4}, {&isl_event_, 1}, {&fresh_, 1}};
         for (Col& c : cols) {   // grow, keep the old rows, zero the new ones
             void* fresh = nullptr;
             AVN_CUDA(cudaMalloc(&fresh, n * c.bytes_per_row));
@@ -642,7 +663,7 @@ class Contacts final : public ContactsBase {
         if (have_re_) { AVN_CUDA(re_.ensure(size_t(n_colliders_) * 8)); AVN_CUDA(cudaMemcpyAsync(re_.p, cfg->restitution, size_t(n_colliders_) * 8, cudaMemcpyHostToDevice, stream_)); }
         // the body sets of the colours and the round-tagged minima; a (re)configuration starts from an empty ConstraintGraph
         AVN_CUDA(body_bits_.ensure(std::max<size_t>(n_bodies_, 1) * 4));
-        AVN_CUDA(body_min_.ensure(std::max<size_t>(n_bodies_, 1) * 8));
+        AVN_CUDA(body_min_.ensure(std::max<size_t>(n_bodies_, 1) * 16));
         AVN_CUDA(cudaMemsetAsync(body_bits_.p, 0, std::max<size_t>(n_bodies_, 1) * 4, stream_));
         AVN_CUDA(ctr_.ensure(sizeof(GraphCounters)));
         AVN_CUDA(cudaMemsetAsync(ctr_.p, 0, sizeof(GraphCounters), stream_));
@@ -656,12 +677,19 @@ class Contacts final : public ContactsBase {
         return AVN_OK;
     }
 
-    AvnStatus prefetch_inputs(const AvnNarrowInput* in, uint32_t flags) override {
+    AvnStatus prefetch_inputs(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t flags) override {
         prefetched_ = nullptr;
-        if (!copy_stream_ || !in) return AVN_OK;
+        early_rows_ = 0;
+        if (!copy_stream_ || !in || !prm) return AVN_OK;
         // (the device copies were read by the previous step's narrow phase, which the previous step waited for)
         AvnStatus st = upload_inputs(in, (flags & AVN_CONTACTS_SHAPES_UNCHANGED) != 0, copy_stream_);
         if (st != AVN_OK) return st;
+        // the rows that exist already do not depend on this step's broad phase: their geometry + matching starts now, on the copy stream, under
+        // the broad-phase kernels; the rows the new pairs add are computed after them (narrow_edges_kernel, only_fresh)
+        if (configured_ && hw_ > 0 && in->body_count <= n_bodies_ && in->collider_count <= n_colliders_) {
+            if ((st = enqueue_narrow(prm, match_contacts, length_unit, hw_, copy_stream_, false)) != AVN_OK) return st;
+            early_rows_ = hw_;
+        }
         AVN_CUDA(cudaEventRecord(ev_in_, copy_stream_));
         prefetched_ = in;
         return AVN_OK;
@@ -677,7 +705,9 @@ class Contacts final : public ContactsBase {
         const uint64_t n_new64 = np ? np->count : 0;
         if (n_new64 > 0x7fffffffull - hw_) return err_->fail(AVN_ERR_CAPACITY, "contacts_step: too many contact pairs");
         const uint32_t n_new = uint32_t(n_new64);
+        added_this_step_ = n_new > 0;
         if (hw_ + n_new > E_ || E_ == 0) {
+            if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));   // the early narrow pass writes the rows that are about to move
             AvnStatus st = reserve(std::max<uint32_t>(1024u, std::max(2 * E_, hw_ + n_new + 1024u)));
             if (st != AVN_OK) return st;
         }
@@ -692,6 +722,7 @@ class Contacts final : public ContactsBase {
                 radix_pass(int(hw_));
                 free_list = v1_.as<uint32_t>();
             }
+            if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));   // the early narrow pass visits the free rows too: it must be through with them
             add_rows_kernel<<<(n_new + 255) / 256, 256, 0, stream_>>>(g, n_new, np->c1, np->c2, np->b1, np->b2, np->flags, free_list, n_free, hw_);
             AVN_CUDA(cudaGetLastError());
             if (n_new > n_free) hw_ += n_new - n_free;
@@ -706,7 +737,7 @@ class Contacts final : public ContactsBase {
             classify_kernel<<<rb, 256, 0, stream_>>>(g, k0_.as<uint32_t>(), v0_.as<uint32_t>());
             radix_pass(int(hw_));
             AVN_CUDA(cudaMemcpyAsync(list_.p, v1_.p, size_t(hw_) * 4, cudaMemcpyDeviceToDevice, stream_));   // changed rows first, ascending ContactId
-            AVN_CUDA(cudaMemsetAsync(body_min_.p, 0xff, std::max<size_t>(n_bodies_, 1) * 8, stream_));
+            AVN_CUDA(cudaMemsetAsync(body_min_.p, 0xff, std::max<size_t>(n_bodies_, 1) * 16, stream_));
             if (use_cluster_) {   // small change sets: one thread-block cluster (returns at once when there are more than CL_MAX changed edges)
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3(CL_BLOCKS); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream_;
@@ -937,14 +968,21 @@ class Contacts final : public ContactsBase {
     }
     // geometry + match_contacts over rows [0, n)
     AvnStatus launch_narrow(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t n) {
-        if (prefetched_ == in) {   // prefetch_inputs copied this call's columns on the copy stream
+        bool only_fresh = false;
+        if (prefetched_ == in) {   // prefetch_inputs copied this call's columns on the copy stream (and ran the rows that existed then)
             AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));
+            only_fresh = early_rows_ > 0;
+            if (only_fresh && n == early_rows_ && !added_this_step_) { prefetched_ = nullptr; early_rows_ = 0; return AVN_OK; }   // nothing new
         } else {
             if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));
             AvnStatus st = upload_inputs(in, false, stream_);
             if (st != AVN_OK) return st;
         }
         prefetched_ = nullptr;
+        early_rows_ = 0;
+        return enqueue_narrow(prm, match_contacts, length_unit, n, stream_, only_fresh);
+    }
+    AvnStatus enqueue_narrow(const AvnNarrowParams* prm, uint32_t match_contacts, double length_unit, uint32_t n, cudaStream_t s, bool only_fresh) {
         NarrowEdgeArgs<S> a{};
         a.r = rows();
         a.r.E = int(n);
@@ -953,7 +991,7 @@ class Contacts final : public ContactsBase {
         a.tol = prm->contact_tolerance;
         a.thr2 = (0.1 * length_unit) * (0.1 * length_unit);
         a.match = match_contacts ? 1 : 0;
-        narrow_edges_kernel<S><<<(n + 127) / 128, 128, 0, stream_>>>(a);
+        narrow_edges_kernel<S><<<(n + 127) / 128, 128, 0, s>>>(a, fresh_.as<uint8_t>(), only_fresh ? 1 : 0);
         AVN_CUDA(cudaGetLastError());
         return AVN_OK;
     }
@@ -976,7 +1014,7 @@ class Contacts final : public ContactsBase {
         g.c1 = c1_.as<uint32_t>(); g.c2 = c2_.as<uint32_t>(); g.b1 = b1_.as<uint32_t>(); g.b2 = b2_.as<uint32_t>();
         g.live = live_.as<uint8_t>(); g.count = count_.as<uint8_t>(); g.disjoint = disjoint_.as<uint8_t>(); g.prev_count = prev_count_.as<uint8_t>();
         g.pflags = pflags_.as<uint8_t>(); g.touching = touching_.as<uint8_t>(); g.colour = colour_.as<uint8_t>(); g.change = change_.as<uint8_t>();
-        g.old_colour = old_colour_.as<uint8_t>(); g.ovf_pos = ovf_pos_.as<uint32_t>(); g.ovf = ovf_.as<uint32_t>(); g.isl_event = isl_event_.as<uint8_t>();
+        g.old_colour = old_colour_.as<uint8_t>(); g.ovf_pos = ovf_pos_.as<uint32_t>(); g.ovf = ovf_.as<uint32_t>(); g.isl_event = isl_event_.as<uint8_t>(); g.fresh = fresh_.as<uint8_t>();
         g.body_kind = kind_.as<uint8_t>(); g.n_bodies = int(n_bodies_);
         g.body_bits = body_bits_.as<uint32_t>(); g.body_min = body_min_.as<unsigned long long>();
         g.ctr = ctr_.as<GraphCounters>();
@@ -1013,7 +1051,9 @@ class Contacts final : public ContactsBase {
     DevBuf i_shape_, i_dims_, i_pos_, i_rot_, i_lv_, i_av_, i_amin_, i_amax_;
     // graphs
     using ResidentGraph = ContactsBase::ResidentGraph;
-    DevBuf isl_event_, isl_buf_, isl_in_, isl_out_, isl_j_;
+    DevBuf isl_event_, fresh_, isl_buf_, isl_in_, isl_out_, isl_j_;
+    uint32_t early_rows_ = 0;     // rows whose geometry prefetch_inputs already launched on the copy stream
+    bool added_this_step_ = false;
     IslandState isl_{};
     IslandCounters* h_isl_ = nullptr;
     uint32_t isl_B_ = 0, isl_J_ = 0;

@@ -137,7 +137,7 @@ struct ContactsBase {
     // ---- the ContactGraph + ConstraintGraph on the device (contacts.cu)
     virtual AvnStatus configure(const AvnContactGraphConfig* cfg) = 0;
     // start the host-to-device copy of step()'s collider / body columns on a second stream (before the broad phase is waited for)
-    virtual AvnStatus prefetch_inputs(const AvnNarrowInput* in, uint32_t flags) = 0;
+    virtual AvnStatus prefetch_inputs(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, uint32_t flags) = 0;
     virtual AvnStatus step(const AvnNarrowParams* prm, const AvnNarrowInput* in, uint32_t match_contacts, double length_unit, const DevicePairs* new_pairs,
                            AvnContactStep* out) = 0;
     struct ResidentGraph {          // device pointers of the colour-major list the last step() built
