@@ -248,6 +248,8 @@ class Solver final : public SolverBase {
     bool uploaded_ = false, ran_ = false, host_any_restitution_ = false, prepared_ = false, mega_step_ = false;
     DevBuf bnd_of_, bnd_body_, bnd_slot_, bnd_owner_, vel_ref_, bnd_table_, bnd_gathered_, bnd_agree_;
     int* h_agree_ = nullptr;
+    int agreed_rest_ = 0;
+    bool agreed_valid_ = false;   // the restitution agreement of step_partitioned holds until the next upload
     int bnd_n_ = 0, bnd_rank_ = 0, bnd_world_ = 1, step_bps_ = 0;
     size_t bnd_slots_ = 0;
 
@@ -435,6 +437,7 @@ AvnStatus Solver<S>::upload_impl(const AvnStepParams* prm, AvnBodyColumns* bc, c
     if (!(prm->h > 0) || !(prm->dt > 0) || prm->substeps == 0) return err_->fail(AVN_ERR_INVALID_ARGUMENT, "dt, h and substeps must be positive");
     uploaded_ = false;
     ran_ = false;
+    agreed_valid_ = false;
     h2d_bytes_ = 0;
     DevSolver<S>& d = dev_;
     d = DevSolver<S>{};
@@ -1032,7 +1035,9 @@ AvnStatus Solver<S>::step_partitioned(CommBase* comm) {
     exchanges_ = 0;
     // agreement on the restitution pass (every rank must launch it, and exchange after it, or none): max over ranks of the host flag
     int any_rest = host_any_restitution_ ? 1 : 0;
-    if (world > 1) {
+    if (world > 1 && agreed_valid_) {
+        any_rest = agreed_rest_;     // agreed right after this upload already (every rank uploads once per step, in lockstep)
+    } else if (world > 1) {
         AVN_CUDA(bnd_agree_.ensure(sizeof(int)));
         if (!h_agree_) AVN_CUDA(cudaHostAlloc(&h_agree_, sizeof(int), cudaHostAllocDefault));
         *h_agree_ = any_rest;
@@ -1041,6 +1046,8 @@ AvnStatus Solver<S>::step_partitioned(CommBase* comm) {
         AVN_CUDA(cudaMemcpyAsync(h_agree_, bnd_agree_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
         AVN_CUDA(cudaStreamSynchronize(stream_));
         any_rest = *h_agree_;
+        agreed_rest_ = any_rest;
+        agreed_valid_ = true;
     }
     const uint32_t substeps = uint32_t(dev_.substeps);
     for (uint32_t s = 0; s < substeps; ++s) {
