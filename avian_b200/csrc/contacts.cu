@@ -43,7 +43,7 @@ enum { ISL_NONE = 0, ISL_ADD = 1, ISL_REMOVE = 2 };
 
 struct GraphCounters {          // device block, copied to the host once per step
     // cleared at the start of every step
-    uint32_t removed, started, stopped, changed, rounds, ovf_dirty, manifolds, any_restitution, aborted;
+    uint32_t removed, started, stopped, changed, rounds, ovf_dirty, manifolds, any_restitution, aborted, bad_pairs;
     uint32_t round_left[3];
     uint32_t color_offsets[AVN_GRAPH_COLOR_COUNT + 1];
     // persistent
@@ -66,10 +66,19 @@ struct GraphRows {
 
 __global__ void add_rows_kernel(GraphRows g, uint32_t n_new, const uint32_t* __restrict__ pc1, const uint32_t* __restrict__ pc2, const uint32_t* __restrict__ pb1,
                                 const uint32_t* __restrict__ pb2, const uint8_t* __restrict__ pfl, const uint32_t* __restrict__ free_list, uint32_t n_free,
-                                uint32_t old_hw) {
+                                uint32_t old_hw, uint32_t n_colliders) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_new) return;
     const uint32_t e = k < n_free ? free_list[k] : old_hw + (k - n_free);
+    // the rows are gathered through on the device (collider poses, body velocities, body sets): a pair outside the configured counts is
+    // counted and stored as a pair of body 0 / collider 0 that can never touch (the step then fails with AVN_ERR_INVALID_ARGUMENT)
+    const bool bad = pc1[k] >= n_colliders || pc2[k] >= n_colliders || pb1[k] >= uint32_t(g.n_bodies) || pb2[k] >= uint32_t(g.n_bodies);
+    if (bad) {
+        atomicAdd(&g.ctr->bad_pairs, 1u);
+        g.c1[e] = 0; g.c2[e] = 0; g.b1[e] = 0; g.b2[e] = 0; g.pflags[e] = 0; g.isl_event[e] = 0; g.fresh[e] = 0;
+        g.live[e] = 0; g.count[e] = 0; g.prev_count[e] = 0; g.touching[e] = 0; g.colour[e] = 0; g.change[e] = 0;
+        return;
+    }
     g.c1[e] = pc1[k]; g.c2[e] = pc2[k]; g.b1[e] = pb1[k]; g.b2[e] = pb2[k];
     g.pflags[e] = pfl[k];
     g.isl_event[e] = 0;
@@ -711,6 +720,7 @@ class Contacts final : public ContactsBase {
             AvnStatus st = reserve(std::max<uint32_t>(1024u, std::max(2 * E_, hw_ + n_new + 1024u)));
             if (st != AVN_OK) return st;
         }
+        AVN_CUDA(cudaMemsetAsync(ctr_.p, 0, offsetof(GraphCounters, ovf_count), stream_));   // the per-step counters; ovf_count persists
         GraphRows g = graph_rows();
         const uint32_t added = n_new;
         if (n_new) {
@@ -723,13 +733,12 @@ class Contacts final : public ContactsBase {
                 free_list = v1_.as<uint32_t>();
             }
             if (prefetched_) AVN_CUDA(cudaStreamWaitEvent(stream_, ev_in_, 0));   // the early narrow pass visits the free rows too: it must be through with them
-            add_rows_kernel<<<(n_new + 255) / 256, 256, 0, stream_>>>(g, n_new, np->c1, np->c2, np->b1, np->b2, np->flags, free_list, n_free, hw_);
+            add_rows_kernel<<<(n_new + 255) / 256, 256, 0, stream_>>>(g, n_new, np->c1, np->c2, np->b1, np->b2, np->flags, free_list, n_free, hw_, n_colliders_);
             AVN_CUDA(cudaGetLastError());
             if (n_new > n_free) hw_ += n_new - n_free;
             live_n_ += n_new;
             g.hw = int(hw_);
         }
-        AVN_CUDA(cudaMemsetAsync(ctr_.p, 0, offsetof(GraphCounters, ovf_count), stream_));   // the per-step counters; ovf_count persists
         if (hw_) {
             AvnStatus st = launch_narrow(prm, in, match_contacts, length_unit, hw_);
             if (st != AVN_OK) return st;
@@ -771,6 +780,12 @@ class Contacts final : public ContactsBase {
         AVN_CUDA(cudaStreamSynchronize(stream_));
         if (h_ctr_->aborted) return err_->fail(AVN_ERR_CUDA, "contacts_step: the colouring did not converge");
         live_n_ -= h_ctr_->removed;
+        if (h_ctr_->bad_pairs) {
+            live_n_ -= h_ctr_->bad_pairs;
+            table_dirty_ = true;
+            return err_->fail(AVN_ERR_INVALID_ARGUMENT, "contacts_step: %u new pair(s) name a collider >= %u or a body >= %u (avn_contacts_configure): not added",
+                              h_ctr_->bad_pairs, n_colliders_, n_bodies_);
+        }
         if (hw_ && (added || h_ctr_->removed || table_dirty_)) {   // ContactGraph::pair_set for the next broad phase
             AVN_CUDA(cudaMemsetAsync(table_.p, 0, (table_mask_ + 1) * sizeof(uint64_t), stream_));
             pair_set_kernel<<<(hw_ + 255) / 256, 256, 0, stream_>>>(g, table_.as<uint64_t>(), table_mask_);

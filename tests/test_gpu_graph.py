@@ -117,3 +117,22 @@ def test_first_frame_of_a_pile_and_the_steady_state(gpu_ctx):
                 assert np.array_equal(getattr(wa.bodies, k), getattr(wb.bodies, k)), f"step {i}: {k}"
         assert wb.stats["manifold_count"] > 30_000
         print("colouring rounds per step:", rounds)
+
+
+def test_pairs_outside_the_configured_counts_are_refused(gpu_ctx):
+    """the rows are gathered through on the device: a new pair that names a body or collider beyond avn_contacts_configure's counts is not
+    added and the step reports AVN_ERR_INVALID_ARGUMENT instead of reading out of bounds"""
+    sc = scenes.cube_stack(3, 2, 3, brick=True)
+    with api.Context(device=0) as ctx:
+        w = plugins.DeviceGraphWorld(sc, plugins.PhysicsPlugins(ctx), ctx, substeps=2)
+        mn, mx = w.pipeline.update_aabbs(w.bodies, w.params.dt)
+        aabbs = w.intervals(mn, mx)
+        aabbs.body = aabbs.body.copy(); aabbs.body[3] = 9999          # a collider whose ColliderOf::body is not among the configured bodies
+        with pytest.raises(api.AvianError) as e:
+            w.step_from(aabbs, mn, mx)
+        assert e.value.status == api.ERR_INVALID_ARGUMENT and "not added" in str(e.value), str(e.value)
+        # and a step whose inputs outgrow the configuration is refused up front
+        ctx.contacts_configure(w.bodies.kind[:5], 5, sc.friction[:5], sc.restitution[:5])
+        with pytest.raises(api.AvianError) as e:
+            w.step()
+        assert e.value.status == api.ERR_INVALID_ARGUMENT
