@@ -77,9 +77,13 @@ def test_islands_and_sleeping_equal_the_oracle(gpu_ctx, scene_fn, steps, kick, t
             ev = _events(prev, now)
             prev = now
             dt = float(w.params.dt)
-            got = ctx.islands_step(dt, w.bodies.linear_velocity, w.bodies.angular_velocity)
-            lab, slp = orc.step(ev, w.bodies.linear_velocity, w.bodies.angular_velocity, np.float32(dt))
-            rlab, rslp = ref.step(ev, w.bodies.linear_velocity, w.bodies.angular_velocity, np.float32(dt))
+            wake = None
+            if i == steps - 20:                       # the application touches two bodies (wake_on_changed): their islands wake, timers restart
+                wake = np.zeros(kind.shape[0], dtype=np.uint8)
+                wake[np.nonzero(kind == api.BODY_DYNAMIC)[0][[0, -1]]] = 1
+            got = ctx.islands_step(dt, w.bodies.linear_velocity, w.bodies.angular_velocity, wake=wake)
+            lab, slp = orc.step(ev, w.bodies.linear_velocity, w.bodies.angular_velocity, np.float32(dt), wake=wake)
+            rlab, rslp = ref.step(ev, w.bodies.linear_velocity, w.bodies.angular_velocity, np.float32(dt), wake=wake)
             deviating += not (np.array_equal(lab, rlab) and np.array_equal(slp, rslp))
             assert np.array_equal(got["island"], lab), f"step {i}: island labels differ for bodies {np.nonzero(got['island'] != lab)[0][:10]}"
             assert np.array_equal(got["sleep_timer"], orc.timer), f"step {i}: sleep timers"

@@ -195,6 +195,28 @@ def test_body_centric_warm_start_with_many_contacts(gpu_ctx):
     assert np.array_equal(mw.warm_start_tangent_impulse, mb.warm_start_tangent_impulse)
 
 
+def test_prefetched_body_columns(gpu_ctx):
+    """avn_solver_prefetch_bodies: the columns copied ahead on the copy stream give the same step; AVN_BODIES_STATIC_UNCHANGED keeps the mass
+    properties of the previous upload; a prefetch of OTHER columns than the upload's is ignored (the upload copies again)"""
+    _, (prm, b, m, j) = advance_to_solver_input(scenes.cube_stack(5, 4, 5, brick=True), steps=2, substeps=4)
+    ref_b, ref_m = b.copy(), m.copy()
+    gpu_ctx.solver_step(prm, ref_b, ref_m)
+    with api.Context(device=0) as ctx:
+        b1, m1 = b.copy(), m.copy()
+        ctx.solver_prefetch_bodies(b1)
+        ctx.solver_step(prm, b1, m1)
+        assert np.array_equal(b1.position, ref_b.position) and np.array_equal(b1.angular_velocity, ref_b.angular_velocity)
+        b2, m2 = b.copy(), m.copy()
+        ctx.solver_prefetch_bodies(b2, static_unchanged=True)       # same scene: the static columns of the previous upload stand
+        ctx.solver_step(prm, b2, m2)
+        assert np.array_equal(b2.position, ref_b.position) and np.array_equal(b2.linear_velocity, ref_b.linear_velocity)
+        other, b3, m3 = b.copy(), b.copy(), m.copy()
+        other.linear_velocity[:] = 7.0
+        ctx.solver_prefetch_bodies(other)                            # not the columns the upload is given
+        ctx.solver_step(prm, b3, m3)
+        assert np.array_equal(b3.position, ref_b.position) and np.array_equal(m3.normal_impulse, ref_m.normal_impulse)
+
+
 def test_island_per_warp_schedule_is_bit_identical(gpu_ctx):
     """a field of ragdolls = many small islands: one thread block takes a group of islands through the whole substep loop
     (AVN_LAUNCH_MEGA_ISLANDS); same per-item routines in the same per-body order as the barrier schedule, so bit-identical bodies, impulses
