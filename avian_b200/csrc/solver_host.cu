@@ -771,6 +771,8 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
             const int resident_warps = mega_grid_ * (MEGA_BLOCK / 32);
             dev_.wave_rolled = (widest_colour / 32 >= resident_warps / 4) ? 1 : 0;
             if (const char* r = getenv("AVN_WAVE_ROLLED")) dev_.wave_rolled = atoi(r) != 0;
+            dev_.poll_ns = 0;
+            if (const char* r = getenv("AVN_WAVE_POLL_NS")) dev_.poll_ns = std::max(0, atoi(r));
         }
         if (dev_.M > 0) {
             // padding slots must read as "no points": clear the index plane before prepare fills the live slots

@@ -118,6 +118,7 @@ __device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int 
             if (n2) n2 = tag_of(D2.a.w) != dtag;
             if (__all_sync(0xffffffffu, !(n1 || n2))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
         __pipeline_wait_prior(0);   // this thread's staged rows have landed (only the issuing thread reads them)
         AVN_TRACE_T(t_p0);
@@ -163,6 +164,7 @@ __device__ __forceinline__ void w32_contact_item(const DevSolver<float>& d, int 
             if (n2) n2 = tag_of(R2.a.w) != e2;
             if (__all_sync(0xffffffffu, !(n1 || n2 || pend != 0u))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
 #ifdef AVN_WAVE_TRACE
         AVN_TRACE_ADD(d, 0, clock64() - t_w1);
@@ -355,6 +357,7 @@ __device__ __forceinline__ void w32_contact_item_unrolled(const DevSolver<float>
             if (n2) n2 = tag_of(D2.a.w) != dtag;
             if (__all_sync(0xffffffffu, !(n1 || n2))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
         __pipeline_wait_prior(0);   // this thread's staged rows have landed (only the issuing thread reads them)
         AVN_TRACE_T(t_p0);
@@ -405,6 +408,7 @@ __device__ __forceinline__ void w32_contact_item_unrolled(const DevSolver<float>
             if (n2) n2 = tag_of(R2.a.w) != e2;
             if (__all_sync(0xffffffffu, !(n1 || n2 || pend != 0u))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
 #ifdef AVN_WAVE_TRACE
         AVN_TRACE_ADD(d, 0, clock64() - t_w1);
@@ -594,6 +598,7 @@ __device__ __forceinline__ void w32_integrate_velocity_item(const DevSolver<floa
             if (nd) nd = tag_of(D.a.w) != unsigned(s);
             if (__all_sync(0xffffffffu, !(nr || nd))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
     }
     if (!live) return;
@@ -683,6 +688,7 @@ __device__ __forceinline__ void w32_ivw_item(const DevSolver<float>& d, int chun
             }
             if (__all_sync(0xffffffffu, pend == 0u)) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
         const V3<S> n = xyz(hn), t1 = xyz(ht1), t2 = cross(t1, n);
 #pragma unroll
@@ -710,6 +716,7 @@ __device__ __forceinline__ void w32_ivw_item(const DevSolver<float>& d, int chun
             if (nd) nd = tag_of(D.a.w) != unsigned(s);
             if (__all_sync(0xffffffffu, !(nr || nd))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
     }
     if (lead) {
@@ -735,6 +742,7 @@ __device__ __forceinline__ void w32_ivw_item(const DevSolver<float>& d, int chun
                     Rec32 p = ld_rec(pc_ptr(d, k, slot));
                     for (unsigned spins = 0; tag_of(p.b.x) != ptag; ++spins) {
                         if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
                         p = ld_rec(pc_ptr(d, k, slot));
                     }
                     const W32WarmDelta o = w32_warm_delta(d, in, n, t1, t2, r, p.a, tangent, side2);
@@ -767,6 +775,7 @@ __device__ __forceinline__ void w32_integrate_position_item(const DevSolver<floa
             if (nd) nd = tag_of(D.a.w) != unsigned(s);
             if (__all_sync(0xffffffffu, !(nr || nd))) break;
             if (spins > W32_SPIN_LIMIT) { d.any_restitution[1] = WAVE_WATCHDOG; break; }
+            if (d.poll_ns) __nanosleep(unsigned(d.poll_ns));   // (experiment: back off between polls, AVN_WAVE_POLL_NS)
         }
     }
     if (!live) return;
