@@ -67,6 +67,7 @@ struct DevSolver {
     int color_off[AVN_GRAPH_COLOR_COUNT + 1];    // SLOT ranges per colour, each start a multiple of 32; [24] = Mpad
     int color_len[AVN_GRAPH_COLOR_COUNT];        // manifolds in the colour
     int wave;                                    // 1: wavefront (dependency-counter) substep loop, 0: grid barriers
+    int* sm_slots;                               // [SMs] block tickets for the SM-major warp numbering of the wavefront loop (NULL = block-major)
     int poll_ns;                                 // f32 wavefront: nanoseconds a warp sleeps after a failed poll (0 = spin)
     int wave_rolled;                             // f32 wavefront: 1 = the rolled contact routines (throughput-bound steps), 0 = the unrolled ones
     unsigned int* ver;                           // [B+1] per-body event counter (wavefront mode)

@@ -61,6 +61,7 @@ class Solver final : public SolverBase {
         if (mode && !strcmp(mode, "wave")) force_wave_ = true;
         if (const char* w = getenv("AVN_WARM_BY_BODY")) warm_by_body_ = atoi(w) != 0;
         if (const char* w = getenv("AVN_ISLAND_MODE")) island_mode_ = atoi(w) != 0;
+        if (const char* w = getenv("AVN_WAVE_SM_ORDER")) sm_order_ = atoi(w) != 0;
         coop_ok_ = coop_ok_ && select_megakernel(AVN_MAX_MANIFOLD_POINTS);
         for (auto& e : ev_) cudaEventCreate(&e);
         up_stream_ = stream_;
@@ -287,7 +288,8 @@ class Solver final : public SolverBase {
     DevBuf o_pos_, o_rot_, o_lv_, o_av_;
     DevBuf s_inr_, s_itg_, s_pre_;
     DevBuf m_b1_, m_b2_, m_n_, m_f_, m_r_, m_tv_, m_po_, p_a1_, p_a2_, p_pen_, p_ns_, p_wn_, p_wt_, p_ni_, p_nin_, p_own_, p_owt_;
-    DevBuf hot_, c_flag_, adj_, isl_buf_;
+    DevBuf hot_, c_flag_, adj_, isl_buf_, sm_slots_;
+    bool sm_order_ = false;
     IslandLists isl_;
     std::vector<int> isl_jb1_, isl_jb2_;
     // island-group schedule (solver_kernels.cuh island_substep_loop): bit-identical, but measured SLOWER than the barrier schedule on the scene it
@@ -771,6 +773,14 @@ AvnStatus Solver<S>::run_range(uint32_t first, uint32_t count, uint32_t flags) {
             const int resident_warps = mega_grid_ * (MEGA_BLOCK / 32);
             dev_.wave_rolled = (widest_colour / 32 >= resident_warps / 4) ? 1 : 0;
             if (const char* r = getenv("AVN_WAVE_ROLLED")) dev_.wave_rolled = atoi(r) != 0;
+            dev_.sm_slots = nullptr;
+            if (sm_order_ && mega_grid_ == step_bps_ * sm_count_) {
+                if (!sm_slots_.p) {
+                    AVN_CUDA(sm_slots_.ensure(1024 * sizeof(int)));
+                    AVN_CUDA(cudaMemsetAsync(sm_slots_.p, 0, 1024 * sizeof(int), stream_));
+                }
+                dev_.sm_slots = sm_slots_.as<int>();
+            }
             dev_.poll_ns = 0;
             if (const char* r = getenv("AVN_WAVE_POLL_NS")) dev_.poll_ns = std::max(0, atoi(r));
         }

@@ -168,7 +168,29 @@ __device__ __forceinline__ void wave_substep_loop(const DevSolver<S>& d) {
     const int lane = threadIdx.x & 31;
     const bool active = lane < WAVE_CHUNK;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d.sm_slots) {
+        // SM-major numbering of the warps: the BPS blocks of one SM take 4 * BPS CONSECUTIVE chunks of the schedule — the same pass, the same
+        // colour, neighbouring plane rows — instead of chunks 148 blocks apart, so the warps of an SM run the same routine on adjacent memory.
+        // Exactly BPS blocks are resident per SM (cooperative launch of BPS x SM-count blocks under a BPS-blocks register limit), every block
+        // draws one ticket of its SM; the counters only ever grow by BPS per launch, so they stay multiples of BPS without a reset.
+        // %smid values need not be dense (disabled SMs leave gaps): the first block that arrives on an SM claims the next dense index for it,
+        // once for the lifetime of the context (sm_slots[256 + smid] = dense index + 1, sm_slots[512] = SMs seen)
+        __shared__ int ticket, dense;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) {
+            const int t = atomicAdd(&d.sm_slots[smid & 255u], 1);
+            ticket = t % BPS;
+            int* slot = &d.sm_slots[256 + (smid & 255u)];
+            if (ticket == 0 && atomicAdd(slot, 0) == 0) atomicExch(slot, atomicAdd(&d.sm_slots[512], 1) + 1);
+            int v;
+            while ((v = atomicAdd(slot, 0)) == 0) { }      // the SM's other blocks are resident with this one: the claim is on its way
+            dense = v - 1;
+        }
+        __syncthreads();
+        warp_id = ((long long)dense * BPS + ticket) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    }
     const int body_chunks = (d.B + WAVE_CHUNK - 1) / WAVE_CHUNK, slot_chunks = d.Mpad / WAVE_CHUNK;
     // body-centric warm start (f32 records): the first phase of a substep is integrate_velocities + warm start, 8 bodies per warp, and the
     // slot-centric warm pass disappears.  The adjacency it needs was built by the rank pass; a body with too many constraints (flag, read
