@@ -436,6 +436,13 @@ __global__ void isl_joint_kernel(IslandState s, const uint32_t* __restrict__ j1,
     if (only_split && !(s.in_split[a] && s.in_split[b])) return;
     isl_union(s.parent, a, b);
 }
+// configuration in the middle of a run: the contacts that are touching already link their bodies' islands (as if add_contact had seen them)
+__global__ void isl_link_existing_kernel(IslandState s, GraphRows g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.hw || !g.live[e] || !g.touching[e] || !(g.pflags[e] & AVN_PAIR_GENERATE_CONSTRAINTS)) return;
+    const uint32_t a = g.b1[e], b = g.b2[e];
+    if (!isl_static(s, a) && !isl_static(s, b)) isl_union(s.parent, a, b);
+}
 // add_contact: merge the islands of the two bodies (mod.rs:513-592); a contact that reaches a sleeping island wakes it (system_param.rs:253-258)
 __global__ void isl_add_kernel(IslandState s, GraphRows g) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -889,14 +896,21 @@ class Contacts final : public ContactsBase {
         isl_B_ = uint32_t(B);
         isl_J_ = cfg->joint_count;
         if (B) isl_init_kernel<<<unsigned((B + 255) / 256), 256, 0, stream_>>>(isl_);
+        bool linked = false;
         if (isl_J_) {   // joints link their bodies' islands from the start (PhysicsIslands::add_joint, mod.rs:669-747)
             AVN_CUDA(isl_j_.ensure(size_t(isl_J_) * 8));
             AVN_CUDA(cudaMemcpyAsync(isl_j_.p, cfg->joint_body1, size_t(isl_J_) * 4, cudaMemcpyHostToDevice, stream_));
             AVN_CUDA(cudaMemcpyAsync(isl_j_.as<uint32_t>() + isl_J_, cfg->joint_body2, size_t(isl_J_) * 4, cudaMemcpyHostToDevice, stream_));
             isl_joint_kernel<<<(isl_J_ + 255) / 256, 256, 0, stream_>>>(isl_, isl_j_.as<uint32_t>(), isl_j_.as<uint32_t>() + isl_J_, int(isl_J_), 0);
-            IslandState t = isl_;
-            t.root_prev = t.root;   // (nothing to hand over yet)
-            isl_flatten_kernel<<<unsigned((B + 255) / 256), 256, 0, stream_>>>(isl_, 0);
+            linked = true;
+        }
+        if (B && configured_ && hw_ > 0 && n_bodies_ <= isl_B_) {   // contacts that are touching already (configuration in the middle of a run)
+            GraphRows g = graph_rows();
+            isl_link_existing_kernel<<<(hw_ + 255) / 256, 256, 0, stream_>>>(isl_, g);
+            linked = true;
+        }
+        if (linked && B) {
+            isl_flatten_kernel<<<unsigned((B + 255) / 256), 256, 0, stream_>>>(isl_, 0);   // (root_prev == the body itself: nothing is handed over)
             AVN_CUDA(cudaMemcpyAsync(isl_.root_prev, isl_.root, B * 4, cudaMemcpyDeviceToDevice, stream_));
         }
         AVN_CUDA(cudaGetLastError());

@@ -559,6 +559,7 @@ typedef struct AvnIslandsConfig {
     float time_to_sleep;                 /* TimeToSleep (default 0.5 s) */
     float length_unit;                   /* PhysicsLengthUnit */
 } AvnIslandsConfig;
+/* Islands start as one per non-static body, linked by the joints and — when the contact store already holds touching pairs — by those. */
 AvnStatus avn_islands_configure(AvnContext* ctx, const AvnIslandsConfig* config);
 
 typedef struct AvnIslandsStep {
@@ -572,6 +573,7 @@ typedef struct AvnIslandsStep {
     float* sleep_timer;                  /* out: [B] SleepTimer; NULL = skip */
     uint32_t island_count, sleeping_islands, islands_put_to_sleep, islands_woken, split_bodies, merges;   /* out */
 } AvnIslandsStep;
+/* Once per step, after avn_contacts_step and the solver stage of the same step (it consumes that step's contact events). */
 AvnStatus avn_islands_step(AvnContext* ctx, AvnIslandsStep* step);
 
 AvnStatus avn_get_timings(const AvnContext* ctx, AvnTimings* out);
