@@ -398,9 +398,12 @@ def e2e_resident(args, info, barrier):
         wall_ms = parallel.reduce_max([(time.perf_counter() - t0) * 1e3], info, device="cuda")[0]
         b, sb = w.bodies, w.bodies.position.dtype.itemsize
         C = int(aabbs.collider.shape[0])
+        # what crosses the bus per step in the steady state: the interval columns of the broad phase; collider poses + AABBs and body velocities of
+        # the contact step; position, rotation, velocities (and accelerations) of the solver's bodies.  Shapes and the columns that describe
+        # the bodies (mass properties, damping ...) stay on the device (AVN_CONTACTS_SHAPES_UNCHANGED / AVN_BODIES_STATIC_UNCHANGED).
+        acc = sum(v.nbytes for k, v in b.__dict__.items() if isinstance(v, np.ndarray) and k in ("linear_acceleration", "angular_acceleration"))
         h2d = sum(v.nbytes for k, v in aabbs.__dict__.items() if isinstance(v, np.ndarray) and k != "order_out") \
-            + C * (1 + 3 * sb + 3 * sb + 4 * sb + 3 * sb + 3 * sb) + 2 * b.count * 3 * sb \
-            + sum(v.nbytes for k, v in b.__dict__.items() if isinstance(v, np.ndarray))
+            + C * (3 + 4 + 3 + 3) * sb + b.count * (3 + 3) * sb + b.count * (3 + 4 + 3 + 3) * sb + acc
         d2h = b.count * (3 + 4 + 3 + 3) * sb + C * 4 + 35 * 4 + 16
         st = w.stats
         return {"wall_ms": wall_ms, "h2d": int(h2d), "d2h": int(d2h),
