@@ -16,6 +16,8 @@ Scenes (every branch named is hit at least once, checked by the asserts at the b
   spherical_dominant  spherical joint (point only) where body 1 has higher Dominance: its inertia is treated as infinite
   revolute_limited    revolute joint bent beyond its angle limit (AngleLimit::compute_correction: asin, clamp, from_axis_angle) + JointDamping
   spherical_limited   spherical joint beyond its swing AND twist limits
+  prismatic_slider    prismatic joint beyond its slider limit and off its axis, with a rotation error: fixed-angle constraint, then the limit
+                      along the free axis and the two zero limits along glam's any_orthogonal_vector axes
   sap_six             six intervals swept by hand (ties on min.x with -0.0/+0.0, touching y bounds, same body, layer mismatch, both inactive)
 """
 import json
@@ -132,6 +134,15 @@ SCENES["spherical_limited"] = {     # swing 1.0 rad against a 0.4 limit, twist 0
                 "swing_limit": [-0.4, 0.4], "twist_limit": [-0.3, 0.3], "compliance0": 0.0, "compliance1": 0.0, "compliance2": 0.0}],
 }
 
+SCENES["prismatic_slider"] = {      # slid 0.5 along the free axis against a [-0.2, 0.3] limit, 0.08 / 0.05 off it, tilted: fixed angle + three axes
+    "params": params(2),
+    "bodies": [body(W.DYNAMIC, (0, 1, 0), rot=axis_angle((0, 1, 0), 0.2), inv_mass=1.0, inv_inertia=(5.0, 0, 0, 5.0, 0, 5.0)),
+               body(W.DYNAMIC, (0.52, 1.08, -0.05), rot=axis_angle((1, 0, 1), 0.15), v=(0.2, 0, 0), w=(0, 0.3, 0.1), inv_mass=2.0,
+                    inv_inertia=(9.0, 0, 0, 9.0, 0, 9.0))],
+    "joints": [{"type": W.PRISMATIC, "body1": 0, "body2": 1, "local_anchor1": [0.1, 0, 0], "local_anchor2": [-0.1, 0, 0], "axis": [1, 0, 0],
+                "limits": [-0.2, 0.3], "compliance0": 0.0, "compliance1": 1e-5}],
+}
+
 SAP = {
     "intervals": [
         {"collider": 10, "body": 10, "min": [2.0, 0.0, 0.0], "max": [3.0, 1.0, 1.0], "memberships": 1, "filters": 0xFFFFFFFF, "inactive": True},
@@ -177,6 +188,8 @@ def main():
     for nm in ("revolute_limited", "spherical_limited"):
         t = vectors["scenes"][nm]["expected_f32"]["joint_torque"][0]
         assert sum(abs(x) for x in t) > 1.0, f"{nm}: the limits must act"
+    pz = vectors["scenes"]["prismatic_slider"]["expected_f32"]
+    assert abs(pz["joint_force"][0][0]) > 1.0 and sum(abs(x) for x in pz["joint_torque"][0]) > 0.1, "prismatic_slider: limit and angle constraint must act"
     d = vectors["scenes"]["distance_pendulum"]["expected_f32"]
     assert abs(d["joint_force"][0][0]) > 1.0, "distance_pendulum: the joint must pull"
     (HERE / "vectors.json").write_text(json.dumps(vectors, indent=1))

@@ -91,6 +91,12 @@ def any_orthonormal_vector(N, v):   # glam Vec3::any_orthonormal_vector (Pixar "
     return np.array([b, sign + v[1] * v[1] * a, -v[1]], dtype=T)
 
 
+def any_orthogonal_vector(N, v):   # glam Vec3::any_orthogonal_vector: abs(x) > abs(y) ? (-z, 0, x) : (0, z, -y)  (not normalised)
+    if abs(v[0]) > abs(v[1]):
+        return N.v(-v[2], 0, v[0])
+    return N.v(0, v[2], -v[1])
+
+
 def mat3_from_quat(q):   # glam Mat3::from_quat; returns columns
     x, y, z, w = q
     T = q.dtype.type
@@ -383,6 +389,11 @@ def step(scene, dtype=np.float32):
         d["cd"] = (b2["pos"] - b1["pos"]) + (quat_rotate(b2["rot"], b2["com"]) - quat_rotate(b1["rot"], b1["com"]))
         d["lam_p"] = N.v(0, 0, 0)
         d["lam_a"] = N.v(0, 0, 0)
+        if j["type"] == PRISMATIC:                            # xpbd/joints/prismatic.rs:43-77
+            basis1 = np.array(j.get("local_basis1", [0, 0, 0, 1]), dtype=T)
+            basis2 = np.array(j.get("local_basis2", [0, 0, 0, 1]), dtype=T)
+            d["rd"] = quat_mul(quat_mul(b1["rot"], basis1), quat_conj(quat_mul(b2["rot"], basis2)))   # FixedAngleConstraintShared::prepare
+            d["ax1"] = quat_rotate(quat_mul(b1["rot"], basis1), np.array(j.get("axis", [1, 0, 0]), dtype=T))   # free_axis1
         if j["type"] in (FIXED, REVOLUTE):
             basis1 = np.array(j.get("local_basis1", [0, 0, 0, 1]), dtype=T)
             basis2 = np.array(j.get("local_basis2", [0, 0, 0, 1]), dtype=T)
@@ -526,6 +537,36 @@ def step(scene, dtype=np.float32):
                 if corr is not None:
                     j["lam_b"] = j["lam_b"] + align_orientation(j, b1, b2, in1, in2, corr, T(j.get("compliance2", 0.0)))
             point_constraint(j, b1, b2, in1, in2, c0)
+        elif j["type"] == PRISMATIC:                          # xpbd/joints/prismatic.rs:79-193: fixed angle, then translation off the free axis
+            q = quat_mul(quat_mul(j["rd"], b1["dq"]), quat_conj(b2["dq"]))
+            j["lam_a"] = j["lam_a"] + align_orientation(j, b1, b2, in1, in2, T(-2) * q[:3], c1)      # angle_compliance
+            wr1, wr2 = quat_rotate(b1["dq"], j["r1"]), quat_rotate(b2["dq"], j["r2"])
+            axis1 = quat_rotate(b1["dq"], j["ax1"])
+
+            def along(lo, hi, sep, axis):                     # DistanceLimit::compute_correction_along_axis (joints/mod.rs:344-357)
+                a = dot(sep, axis)
+                if a < lo:
+                    return axis * (lo - a)
+                if a > hi:
+                    return -axis * (a - hi)
+                return N.v(0, 0, 0)
+            dx = N.v(0, 0, 0)
+            sep = ((b2["dp"] - b1["dp"]) + (wr2 - wr1)) + j["cd"]
+            if j.get("limits") is not None:
+                dx = dx + along(T(j["limits"][0]), T(j["limits"][1]), sep, axis1)
+            axis2 = any_orthogonal_vector(N, axis1)
+            axis3 = cross(axis1, axis2)
+            dx = dx + along(T(0), T(0), sep, axis2)
+            dx = dx + along(T(0), T(0), sep, axis3)
+            mag = length(N, dx)
+            if mag <= N.eps:
+                return
+            dirn = dx / mag
+            w1 = generalized_inverse_mass(in1[0], in1[1], wr1, dirn)
+            w2 = generalized_inverse_mass(in2[0], in2[1], wr2, dirn)
+            imp = lagrange_update(mag, [w1, w2], c0) * dirn   # align_compliance
+            j["lam_p"] = j["lam_p"] + imp
+            positional_impulse(b1, b2, in1, in2, imp, wr1, wr2)
         elif j["type"] == FIXED:                              # xpbd/joints/fixed.rs:73-89, shared/fixed_angle_constraint.rs:59-96
             q = quat_mul(quat_mul(j["rd"], b1["dq"]), quat_conj(b2["dq"]))
             difference = T(-2) * q[:3]

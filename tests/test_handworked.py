@@ -72,7 +72,7 @@ def _build(sc, dtype):
             if t == api.JOINT_DISTANCE:
                 en1, lo1, hi1 = np.zeros(n, dtype=bool), g("limit_min", 0.0, 1), g("limit_max", 0.0, 1)
             else:
-                en1, lo1, hi1 = lim("angle_limit" if t == api.JOINT_REVOLUTE else "swing_limit")
+                en1, lo1, hi1 = lim({api.JOINT_REVOLUTE: "angle_limit", api.JOINT_PRISMATIC: "limits"}.get(t, "swing_limit"))
             en2, lo2, hi2 = lim("twist_limit")
             damp = np.array([j.get("damping") is not None for _, j in js])
             joints.types[t] = api.Joints(
