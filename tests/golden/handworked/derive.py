@@ -16,6 +16,7 @@ Scenes (every branch named is hit at least once, checked by the asserts at the b
   spherical_dominant  spherical joint (point only) where body 1 has higher Dominance: its inertia is treated as infinite
   revolute_limited    revolute joint bent beyond its angle limit (AngleLimit::compute_correction: asin, clamp, from_axis_angle) + JointDamping
   spherical_limited   spherical joint beyond its swing AND twist limits
+  locked_on_kinematic a body with LockedAxes (translation X, rotation Y) in contact with a moving kinematic body
   prismatic_slider    prismatic joint beyond its slider limit and off its axis, with a rotation error: fixed-angle constraint, then the limit
                       along the free axis and the two zero limits along glam's any_orthogonal_vector axes
   sap_six             six intervals swept by hand (ties on min.x with -0.0/+0.0, touching y bounds, same body, layer mismatch, both inactive)
@@ -143,6 +144,18 @@ SCENES["prismatic_slider"] = {      # slid 0.5 along the free axis against a [-0
                 "limits": [-0.2, 0.3], "compliance0": 0.0, "compliance1": 1e-5}],
 }
 
+kp = []
+for sx, sz, wn in [(0.4, 0.4, 0.02), (-0.4, 0.4, 0.0), (-0.4, -0.4, 0.03), (0.4, -0.4, 0.01)]:
+    kp.append({"anchor1": [sx, -0.5, sz], "anchor2": [sx + 0.2, 0.25, sz - 0.1], "penetration": 0.004, "normal_speed": -0.05, "warm_start_normal_impulse": wn,
+               "warm_start_tangent_impulse": [0.002, -0.001]})
+SCENES["locked_on_kinematic"] = {   # a body with translation X and rotation Y locked riding a moving kinematic platform: per-axis inverse mass, cleared inertia
+    "params": params(2),            # rows, locked increments, the kinematic side dominant (2x softness frequency) and integrated but never pushed
+    "bodies": [body(W.DYNAMIC, (0, 0.996, 0), v=(0.0, -0.1, 0.05), w=(0.2, 0.0, -0.1), inv_mass=1.0, inv_inertia=(6.0, 0, 0, 6.0, 0, 6.0), locked_axes=0b100_010),
+               body(W.KINEMATIC, (-0.2, 0.25, 0.1), v=(0.6, 0.0, 0.3), w=(0, 0.2, 0), inv_mass=0.0, inv_inertia=(0,) * 6)],
+    "manifolds": [{"body1": 0, "body2": 1, "normal": [0, -1, 0], "friction": 0.6, "restitution": 0.0, "points": kp}],
+    "color_offsets": [0] + [1] * 24,   # both bodies have a SolverBody: the dynamic-dynamic rule, colour 0 (constraint_graph.rs:184-195)
+}
+
 SAP = {
     "intervals": [
         {"collider": 10, "body": 10, "min": [2.0, 0.0, 0.0], "max": [3.0, 1.0, 1.0], "memberships": 1, "filters": 0xFFFFFFFF, "inactive": True},
@@ -188,6 +201,10 @@ def main():
     for nm in ("revolute_limited", "spherical_limited"):
         t = vectors["scenes"][nm]["expected_f32"]["joint_torque"][0]
         assert sum(abs(x) for x in t) > 1.0, f"{nm}: the limits must act"
+    lk = vectors["scenes"]["locked_on_kinematic"]["expected_f32"]
+    assert lk["linear_velocity"][0][0] == 0.0 and lk["angular_velocity"][0][1] == 0.0, "locked_on_kinematic: the locked axes must not move"
+    assert lk["linear_velocity"][1] == [0.6000000238418579, 0.0, 0.30000001192092896], "the kinematic body keeps its velocity"
+    assert abs(lk["linear_velocity"][0][2] - 0.05) > 1e-3 and sum(lk["warm_start_normal_impulse"]) > 0, "friction and the normal part must act"
     pz = vectors["scenes"]["prismatic_slider"]["expected_f32"]
     assert abs(pz["joint_force"][0][0]) > 1.0 and sum(abs(x) for x in pz["joint_torque"][0]) > 0.1, "prismatic_slider: limit and angle constraint must act"
     d = vectors["scenes"]["distance_pendulum"]["expected_f32"]

@@ -199,19 +199,34 @@ def step(scene, dtype=np.float32):
         sb["inv_mass"] = T(b["inverse_mass"])
         sb["il"] = il
         sb["iw"] = rotate_inverse_inertia(il, rot)
+        # LockedAxes (rigid_body/locked_axes.rs:34-47: bits 0b XYZ_xyz = translation X Y Z, rotation x y z)
+        locked = int(b.get("locked_axes", 0))
+        sb["locked"] = locked
+        # SolverBodyInertia::new (solver_body/mod.rs:378-423): a locked rotation axis clears its row and column of the world inverse inertia
+        iw = sb["iw"].copy()
+        if locked & 0b000_100: iw[0] = iw[1] = iw[2] = T(0)
+        if locked & 0b000_010: iw[1] = iw[3] = iw[4] = T(0)
+        if locked & 0b000_001: iw[2] = iw[4] = iw[5] = T(0)
+        sb["iw"] = iw
         # SolverBodyInertia::new: dominance = Dominance for dynamic bodies, i8::MAX + 1 otherwise (solver_body/mod.rs:414-420)
         sb["dominance"] = int(b.get("dominance", 0)) if kind == DYNAMIC else 128
         eps = T(1e-6)
         iso = (not (abs(il[0] - il[3]) > eps or abs(il[3] - il[5]) > eps)) and abs(il[1]) < eps and abs(il[2]) < eps and abs(il[4]) < eps
-        sb["gyro"] = not iso                                # plugin.rs:241-247 (no locked axes in these scenes)
+        sb["gyro"] = (locked & 0b111) != 0b111 and not iso   # plugin.rs:241-247: rotation unlocked on at least one axis and not isotropic
         # pre_process_velocity_increments (integrator/mod.rs:260-313), dynamic bodies only
         sb["lin_rhs"], sb["ang_rhs"] = T(1), T(1)
         sb["lin_inc"], sb["ang_inc"] = N.v(0, 0, 0), N.v(0, 0, 0)
         if kind == DYNAMIC:
             sb["lin_rhs"] = T(1) / (T(1) + h * T(b.get("linear_damping", 0.0)))
             sb["ang_rhs"] = T(1) / (T(1) + h * T(b.get("angular_damping", 0.0)))
-            sb["lin_inc"] = (N.v(0, 0, 0) + g * T(b.get("gravity_scale", 1.0))) * h
-            sb["ang_inc"] = N.v(0, 0, 0) * h
+            li = N.v(0, 0, 0) + g * T(b.get("gravity_scale", 1.0))
+            ai = N.v(0, 0, 0)
+            # LockedAxes::apply_to_vec / apply_to_angular_velocity on the increments (integrator/mod.rs:296-300)
+            for ax, (tb, rb) in enumerate(((0b100_000, 0b000_100), (0b010_000, 0b000_010), (0b001_000, 0b000_001))):
+                if locked & tb: li[ax] = T(0)
+                if locked & rb: ai[ax] = T(0)
+            sb["lin_inc"] = li * h
+            sb["ang_inc"] = ai * h
         B.append(sb)
 
     def inertia_of(i, zeroed):
@@ -219,7 +234,8 @@ def step(scene, dtype=np.float32):
         if i < 0 or not B[i]["has_solver_body"] or zeroed:
             return N.v(0, 0, 0), np.zeros(6, dtype=T)
         m = B[i]["inv_mass"]
-        return N.v(m, m, m), B[i]["iw"]
+        lk = B[i]["locked"]                                   # effective_inv_mass (solver_body/mod.rs:437-451)
+        return N.v(T(0) if lk & 0b100_000 else m, T(0) if lk & 0b010_000 else m, T(0) if lk & 0b001_000 else m), B[i]["iw"]
 
     dummy = {"v": N.v(0, 0, 0), "w": N.v(0, 0, 0), "dp": N.v(0, 0, 0), "dq": np.array([0, 0, 0, 1], dtype=T), "kind": STATIC, "dominance": 128,
              "has_solver_body": False}

@@ -41,6 +41,8 @@ def _build(sc, dtype):
                         inverse_mass=col("inverse_mass", None, 1), inverse_inertia_local=col("inverse_inertia_local", None, 6),
                         center_of_mass=col("center_of_mass", [0, 0, 0], 3), dominance=np.array([b.get("dominance", 0) for b in bs], dtype=np.int8),
                         linear_damping=col("linear_damping", 0.0, 1), angular_damping=col("angular_damping", 0.0, 1), gravity_scale=col("gravity_scale", 1.0, 1))
+    if any(b.get("locked_axes") for b in bs):
+        bodies.locked_axes = np.array([b.get("locked_axes", 0) for b in bs], dtype=np.uint8)
     man = None
     if sc.get("manifolds"):
         ms = sc["manifolds"]
