@@ -62,3 +62,31 @@ def test_joints_hold_an_island_together():
     for _ in range(4):
         lab, slp = o.step([], lv, av, 1 / 60)
     assert lab.tolist() == [0, 0, 2] and slp.all()      # the split keeps the jointed pair together
+
+
+def test_the_stated_deviation_of_the_device_candidate_rule():
+    """The one place where the device's islands differ from the reference (include/avian_b200.h avn_islands_step): the reference's split
+    candidate is an island ID that merge_islands retires when the candidate is the SMALLER side of a merge (remove_island, mod.rs:456-464);
+    the device remembers the sleepiest BODY and splits whatever island holds it a step later.  Here: {1,2} lost a contact and rests (candidate);
+    in the next step it is merged into the bigger moving island {3,4,5}.  Reference: no split that step (the candidate is gone), the merged island
+    is split a step later.  Device rule: the merged island is split at once.  One step later both agree again."""
+    kind = np.array([STATIC, DYN, DYN, DYN, DYN, DYN], dtype=np.uint8)
+    lv, av = _still(6)
+    res = {}
+    for mode in ("island", "body"):
+        o = IslandsOracle(kind, time_to_sleep=0.045, candidate=mode)
+        fast = lv.copy(); fast[3:] = 1.0                      # bodies 3, 4, 5 keep moving: their island never gets sleepy
+        o.step([(0, "add", 1, 2), (1, "add", 3, 4), (2, "add", 4, 5)], fast, av, 1 / 60)
+        o.step([(0, "remove", 1, 2)], fast, av, 1 / 60)      # {1,2} is marked (constraints_removed = 1) and keeps resting
+        lab, _ = o.step([], fast, av, 1 / 60)                # timers of 1 and 2 reach time_to_sleep: {1,2} becomes the split candidate
+        assert lab.tolist() == [0xFFFFFFFF, 1, 1, 3, 3, 3]
+        a, _ = o.step([(7, "add", 2, 3)], fast, av, 1 / 60)  # merged into the bigger island in the narrow phase of the next step
+        b, _ = o.step([], fast, av, 1 / 60)
+        c, _ = o.step([], fast, av, 1 / 60)
+        res[mode] = (a.tolist(), b.tolist(), c.tolist())
+    # reference: the candidate was retired by the merge, {1,2,3,4,5} stays whole for that step
+    assert res["island"][0] == [0xFFFFFFFF, 1, 1, 1, 1, 1]
+    # device rule: body 1 (the sleepiest) is still the candidate: its island is split right away — 1 is alone, 2-3-4-5 hang together
+    assert res["body"][0] == [0xFFFFFFFF, 1, 2, 2, 2, 2]
+    # afterwards the reference picks the merged island (it still carries constraints_removed) and splits it too
+    assert res["island"][2] == res["body"][2] == [0xFFFFFFFF, 1, 2, 2, 2, 2]
