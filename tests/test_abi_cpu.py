@@ -107,3 +107,18 @@ def test_fixture_manifolds_are_sane():
     dyn1 = b.kind[m.body1] == api.BODY_DYNAMIC
     a1 = m.anchor1[np.repeat(dyn1, cnt)]
     assert (np.abs(a1).max(axis=1) <= 0.5 + 2e-2).all()      # on the (slightly rotated) unit cube of body1, world-frame offsets
+
+
+def test_c_example_compiles_and_links():
+    """examples/resident_step.c — the device-resident step written against include/avian_b200.h in plain C — compiles with -Wall -Werror
+    and links with the library (every entry point it calls exists with that signature).  It is not run here (no GPU)."""
+    import subprocess, tempfile
+    from avian_b200 import _build
+    root = Path(__file__).resolve().parent.parent
+    lib = _build.build_cuda()
+    with tempfile.TemporaryDirectory() as d:
+        exe = Path(d) / "resident_step"
+        r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", str(root / "include"), str(root / "examples" / "resident_step.c"),
+                            "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert exe.exists()
