@@ -390,12 +390,17 @@ def e2e_resident(args, info, barrier):
         barrier()
         changes = rounds = 0
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            st = w.step_from(aabbs, mn, mx)
-            changes += st["started_touching"] + st["stopped_touching"] + st["pairs_added"] + st["pairs_removed"]
-            rounds = max(rounds, st["colouring_rounds"])
+        try:
+            for _ in range(args.steps):
+                st = w.step_from(aabbs, mn, mx)
+                changes += st["started_touching"] + st["stopped_touching"] + st["pairs_added"] + st["pairs_removed"]
+                rounds = max(rounds, st["colouring_rounds"])
+        except Exception as exc:   # a rank that fails must still reach the barrier the others wait at; the arm is then reported as failed
+            error = f"{type(exc).__name__}: {exc}"
         barrier()
         wall_ms = parallel.reduce_max([(time.perf_counter() - t0) * 1e3], info, device="cuda")[0]
+        if parallel.reduce_max([0.0 if error is None else 1.0], info, device="cuda")[0] > 0:
+            return {"error": error or "another rank failed inside the resident arm"}
         b, sb = w.bodies, w.bodies.position.dtype.itemsize
         C = int(aabbs.collider.shape[0])
         # what crosses the bus per step in the steady state: the interval columns of the broad phase; collider poses + AABBs and body velocities of
